@@ -1,0 +1,188 @@
+"""Pins oracle/kf_oracle.py (the numpy restatement) to the golden vectors that
+oracle/make_golden.py produced by running the UNMODIFIED reference.  CPU only."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import kf_oracle as ko
+from oracle.make_golden import arrays_to_events, states_arr
+
+TOL = dict(rtol=1e-11, atol=1e-11)
+
+
+@pytest.fixture(scope="module")
+def loops(golden):
+    g = golden("ca15_loops.npz")
+    g["events"] = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    return g
+
+
+def test_full_cold(loops):
+    m = ko.get_model("CA15")
+    st, ld, P, prev = ko.run_full(m, loops["events"], 0, 400)
+    np.testing.assert_allclose(states_arr(st), loops["full_cold_states"], **TOL)
+    np.testing.assert_allclose(ld, loops["full_cold_logdet"], **TOL)
+    np.testing.assert_allclose(P, loops["full_cold_P"], **TOL)
+    assert prev == loops["full_cold_prev"]
+
+
+def test_full_warm(loops):
+    m = ko.get_model("CA15")
+    st, ld, P, prev = ko.run_full(m, loops["events"], 200, 400, loops["full_warm_init_P"],
+                                  tuple(loops["full_warm_init_state"]))
+    np.testing.assert_allclose(states_arr(st), loops["full_warm_states"], **TOL)
+    np.testing.assert_allclose(ld, loops["full_warm_logdet"], **TOL)
+    np.testing.assert_allclose(P, loops["full_warm_P"], **TOL)
+    assert prev == loops["full_warm_prev"]
+
+
+def test_legacy(loops):
+    m = ko.get_model("CA15")
+    st, covs = ko.run_legacy(m, loops["events"], 0, 300)
+    assert len(covs) == int(loops["legacy_n"])
+    np.testing.assert_allclose(states_arr(st), loops["legacy_states"], **TOL)
+    np.testing.assert_allclose(covs[-1], loops["legacy_P_last"], **TOL)
+    np.testing.assert_allclose(covs[len(covs) // 2], loops["legacy_P_mid"], **TOL)
+
+
+def test_adaptive_and_no_update(loops):
+    m = ko.get_model("CA15")
+    st, ld, P, prev, mt = ko.run_adaptive(m, loops["events"], 0, 300, float(loops["adaptive_thr"]))
+    np.testing.assert_allclose(states_arr(st), loops["adaptive_states"], **TOL)
+    np.testing.assert_allclose(ld, loops["adaptive_logdet"], **TOL)
+    np.testing.assert_allclose(P, loops["adaptive_P"], **TOL)
+    np.testing.assert_array_equal(np.array(mt), loops["adaptive_mtimes"])
+    assert prev == loops["adaptive_prev"]
+    st, ld, P, prev, mt = ko.run_adaptive(m, loops["events"], 200, 330, float(loops["adaptive_warm_thr"]),
+                                          loops["full_warm_init_P"], tuple(loops["full_warm_init_state"]))
+    np.testing.assert_allclose(states_arr(st), loops["adaptive_warm_states"], **TOL)
+    np.testing.assert_allclose(ld, loops["adaptive_warm_logdet"], **TOL)
+    np.testing.assert_array_equal(np.array(mt), loops["adaptive_warm_mtimes"])
+    st, ld, P, prev, mt = ko.run_adaptive(m, loops["events"], 0, 120, None, never_update=True)
+    np.testing.assert_allclose(states_arr(st), loops["noupdate_states"], **TOL)
+    np.testing.assert_allclose(ld, loops["noupdate_logdet"], **TOL)
+    np.testing.assert_allclose(P, loops["noupdate_P"], **TOL)
+    np.testing.assert_array_equal(np.array(mt), loops["noupdate_mtimes"])
+
+
+@pytest.mark.parametrize("f", [20, 50, 120])
+def test_scheduled_greedy(loops, f):
+    m = ko.get_model("CA15")
+    st, ld, P = ko.run_scheduled(m, loops["events"], f, 0, 400)
+    np.testing.assert_allclose(states_arr(st), loops[f"sched_greedy_{f}_states"], **TOL)
+    np.testing.assert_allclose(ld, loops[f"sched_greedy_{f}_logdet"], **TOL)
+    np.testing.assert_allclose(P, loops[f"sched_greedy_{f}_P"], **TOL)
+
+
+def test_scheduled_warm_and_random(loops):
+    m = ko.get_model("CA15")
+    st, ld, P = ko.run_scheduled(m, loops["events"], 50, 200, 400, loops["full_warm_init_P"],
+                                 tuple(loops["full_warm_init_state"]))
+    np.testing.assert_allclose(states_arr(st), loops["sched_warm_states"], **TOL)
+    np.testing.assert_allclose(ld, loops["sched_warm_logdet"], **TOL)
+    np.random.seed(int(loops["sched_random_seed"]))
+    st, ld, P = ko.run_scheduled(m, loops["events"], 50, 0, 400, selection="random",
+                                 rng_choice=np.random.choice)
+    np.testing.assert_allclose(states_arr(st), loops["sched_random_states"], **TOL)
+    np.testing.assert_allclose(P, loops["sched_random_P"], **TOL)
+
+
+@pytest.fixture(scope="module")
+def brute(golden):
+    g = golden("ca15_bruteforce.npz")
+    g["events"] = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    return g
+
+
+def test_worker_all_subsets(brute):
+    m = ko.get_model("CA15")
+    L, w0 = int(brute["L"]), int(brute["w0"])
+    window = brute["events"][w0:w0 + L]
+    init = brute["init_state"]
+    xt = np.zeros(15)
+    xt[0:6] = init[1:7]
+    order = list(ko.enumerate_subsets(L))
+    assert [ko.subset_mask(c) for c in order] == [int(v) for v in brute["masks"]]
+    types = [0 if e[1] == "GPS" else 1 for e in window]
+    times = [e[2] for e in window]
+    for r in range(0, len(order), 7):  # every 7th subset keeps the CPU suite short
+        combo = tuple(window[i] for i in order[r])
+        traj, x, P, lds = ko.worker_combo(m, combo, xt, brute["P0"], init[0], float(brute["t_end"]))
+        ref = brute["traces"][r]
+        ref = ref[~np.isnan(ref)]
+        np.testing.assert_allclose(lds, ref, **TOL)
+        np.testing.assert_allclose(x, brute["x_final"][r], **TOL)
+        assert len(traj) == int(brute["n_traj"][r])
+        np.testing.assert_allclose([float(v) for v in traj[-1]], brute["traj_last"][r], **TOL)
+        # the covariance-only trace is the same list (measurement independence)
+        cov_only = ko.schedule_trace(m, types, times, int(brute["masks"][r]), brute["P0"], init[0],
+                                     float(brute["t_end"]))
+        np.testing.assert_allclose(cov_only, ref, **TOL)
+
+
+def test_driver_selection(brute):
+    m = ko.get_model("CA15")
+    Ld, w0 = int(brute["drv_L"]), int(brute["w0"])
+    window = brute["events"][w0:w0 + Ld]
+    init = brute["init_state"]
+    xt = np.zeros(15)
+    xt[0:6] = init[1:7]
+    t_end = window[-1][2]
+    for thr, mask, xf, lds in zip(brute["drv_thr"], brute["drv_mask"], brute["drv_final_state"],
+                                  brute["drv_logdet"]):
+        out = ko.brute_force_select(m, window, xt, brute["P0"], init[0], t_end, float(thr))
+        if int(mask) < 0:  # reference returned None: the max includes the shared initial term
+            assert out is None
+            continue
+        assert out is not None and ko.subset_mask(out["selected_indices"]) == int(mask)
+        np.testing.assert_allclose(out["final_state"], xf, **TOL)
+        np.testing.assert_allclose(out["log_determinants"], lds[~np.isnan(lds)], **TOL)
+    assert ko.brute_force_select(m, window, xt, brute["P0"], init[0], t_end,
+                                 float(brute["drv_infeasible_thr"])) is None
+
+
+def test_lex_rank_key_matches_enumeration():
+    L = 7
+    order = [ko.subset_mask(c) for c in ko.enumerate_subsets(L)]
+    assert sorted(order, key=lambda mk: ko.lex_rank_key(mk, L)) == order
+
+
+def test_scheduler(golden):
+    g = golden("scheduler.npz")
+    m = ko.get_model("CA15")
+    for k, S in enumerate(g["Sigma"]):
+        np.testing.assert_allclose(ko.cov_matrix([1], S, m.R_gps(), m.H_gps()), g["post_gps1"][k], **TOL)
+        np.testing.assert_allclose(ko.cov_matrix([1, 2, 3], S, m.R_gps(), m.H_gps()), g["post_gps3"][k], **TOL)
+        np.testing.assert_allclose(ko.cov_matrix([1], S, m.R_imu(), m.H_imu()), g["post_imu1"][k], **TOL)
+        np.testing.assert_allclose(ko.cov_matrix(list(range(1, 16)), S, m.R_imu(), m.H_imu()),
+                                   g["post_imu_all"][k], **TOL)
+        for q, pick in zip(g["queues"], g["greedy_pick"][k]):
+            queue = [(j, "GPS" if c == 0 else "IMU", float(j), None) for j, c in enumerate(q) if c >= 0]
+            assert ko.greedy_schedule(m, queue, S) == int(pick)
+
+
+def test_hw5_2(golden):
+    g = golden("ca8_hw5_2.npz")
+    ev = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    m = ko.get_model("CA8")
+    np.testing.assert_allclose(np.array(ko.hw5_2_run(m, ev), dtype=float), g["kf_states"], **TOL)
+    np.testing.assert_allclose(np.array(ko.hw5_2_dead_reckoning(m, ev), dtype=float), g["dr_states"], **TOL)
+
+
+def test_batch_matches_event_loop(loops):
+    """The packed run_batch (what the C ABI computes) equals the event loop on the same stream."""
+    m = ko.get_model("CA15")
+    ev = loops["events"][3:120]  # starts at the first GPS fix, no negative dt inside
+    assert ev[0][1] == "GPS"
+    st, ld, P, _ = ko.run_full(m, ev, 0, len(ev))
+    times = np.array([e[2] for e in ev])
+    dts = np.diff(times, prepend=times[0])
+    types = np.array([0 if e[1] == "GPS" else 1 for e in ev], dtype=np.uint8)
+    payload = np.stack([ko.event_payload(m, e[1], e[3]) for e in ev])[:, :, None]
+    x0 = np.zeros((1, 15))
+    x0[0, :3] = [ev[0][3]["easting"], ev[0][3]["northing"], ev[0][3]["altitude"]]
+    out = ko.run_batch(m, types, dts, payload, x0, m.P0()[None])
+    np.testing.assert_allclose(out["traj"][:, :6, 0], states_arr(st)[1:, 1:], **TOL)
+    np.testing.assert_allclose(out["logdet"][:, 0], ld[1:], **TOL)
+    np.testing.assert_allclose(out["P"][0], P, **TOL)
