@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- filter-steps/s of the batched GPS/IMU Kalman-filter hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on): 2^20 independent 6-state
+GPS/IMU constant-velocity filters x 10 000 steps, FP64, sharded by filter over 8 GPUs = 131 072
+filters x 10 000 steps per GPU.  That per-GPU shard is what every rank runs (weak scaling: N=8 is
+the full config; the full 1M x 10k input, 252 GB, does not fit one GPU's HBM).  One "step" of the
+bench = one pass of all the rank's filters over the T-step stream (inputs resident in HBM, 31.5 GB
+> L2, so no L2 flush is needed between steps).
+
+Prints ONE JSON line (rank 0).  value = filter-steps/s, whole job.  e2e = same metric through
+b200kf_run_batch_host with pinned HOST buffers (H2D of the payload + D2H of the results inside the
+timed region).  roofline = the dominant kernel against the measured HBM peak, plus the FP64 view.
+cpu_baseline = the oracle port (numpy restatement of the reference loop) on this box's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "filter_steps_per_sec"
+UNIT = "filter-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="CV6")
+    ap.add_argument("--filters", type=int, default=131072, help="filters per GPU")
+    ap.add_argument("--tsteps", type=int, default=10000, help="events per filter per bench step")
+    ap.add_argument("--e2e-tsteps", type=int, default=1250, help="events per filter in the host-buffer e2e leg")
+    ap.add_argument("--mode", default="auto", choices=["auto", "dense", "decoupled"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-search", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.model} {a.filters} filters x {a.tsteps} steps per GPU, {a.precision}, GPS every 20th event "
+            f"(BASELINE configs[2]: 2^20 x 10k sharded over 8 GPUs)")
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference loop on the host cores
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    model_name, n_filters, n_steps, seed = job
+    from oracle import kf_oracle as ko
+    from sensorfusion_kalmanfilter_b200 import synth
+    m = ko.get_model(model_name)
+    types, dts = synth.gps_imu_schedule(n_steps)
+    rng = np.random.default_rng(seed)
+    done = 0
+    for _ in range(n_filters):
+        payload = rng.normal(0, 0.1, (n_steps, m.d))
+        x, P = np.zeros(m.n), m.P0()
+        for k in range(n_steps):  # one filter at a time, as the reference's loop (kf_workers.py:681-721)
+            x, P = ko.step(m, x, P, int(types[k]), float(dts[k]), payload[k])
+            ko.logdet(P)
+            done += 1
+    return done
+
+
+def cpu_sample(model_name, filters_per_core, n_steps, cores):
+    """Pool(cores) x filters_per_core filters x n_steps events of the per-filter numpy loop."""
+    import multiprocessing as mp
+    jobs = [(model_name, filters_per_core, n_steps, 100 + i) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(model_name, 1, 20, 0)] * cores)  # warm the workers (imports)
+        t0 = time.perf_counter()
+        done = sum(pool.map(_cpu_worker, jobs, chunksize=1))
+        dt = time.perf_counter() - t0
+    return done, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    fpc, ns = 2, 2000
+    for _ in range(max(0, a.warmup)):
+        cpu_sample(a.model, 1, 200, cores)
+    t_total, done_total = 0.0, 0
+    for _ in range(a.steps):
+        done, dt = cpu_sample(a.model, fpc, ns, cores)
+        t_total += dt
+        done_total += done
+    v = done_total / t_total
+    sample = (f"{cores} processes x {fpc} filters x {ns} events per bench step, per-filter numpy float64 loop "
+              f"(oracle port of kf_workers.py:681-721 for {a.model})")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * t_total / max(1, a.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reference_is": "oracle port (the reference is pure Python; "
+                       "/root/reference does not exist on the GPU box)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in out.strip().splitlines():
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    from sensorfusion_kalmanfilter_b200 import synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload, probe_fma_peak
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    eng = Engine(a.model, precision=a.precision)
+    sp = eng.spec
+    N, T = a.filters, a.tsteps
+    rb = 4 if a.precision == "f32" else 8
+    types, dts = synth.gps_imu_schedule(T)
+    types_d = torch.from_numpy(types).to(dev)
+    dts_d = torch.from_numpy(dts).to(dev)
+    payload = fill_payload(eng, types_d, N, seed=1234 + rank)
+    x = torch.zeros((N, sp.n), dtype=eng.real, device=dev)
+    P = torch.from_numpy(np.repeat(sp.default_P0()[None], N, axis=0)).to(device=dev, dtype=eng.real).contiguous()
+    agg = torch.empty((N, 4), dtype=torch.float64, device=dev)
+
+    def one_step(mode):
+        # state carries over from pass to pass (the filters keep running over the stream)
+        eng.run_batch(types_d, dts_d, payload, x, P, mode=mode, inplace=True, want_agg=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        one_step(a.mode)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        one_step(a.mode)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches_per_step = 3 if a.mode == "auto" else 1
+    total_steps = float(world) * N * T * a.steps
+    value = total_steps / (ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---- dominant kernel alone (decoupled/dense as dispatched), CUDA events on the launch stream
+        kmode = a.mode if a.mode != "auto" else "decoupled"
+        for _ in range(2):
+            one_step(kmode)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, a.steps)
+        k0.record()
+        for _ in range(reps):
+            one_step(kmode)
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / reps
+        hbm_peak, peak_src = load_peaks()
+        alg_bytes = float(N) * T * sp.d * rb + float(N) * (2 * (sp.n + sp.n * sp.n) * rb + 32)
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        fma_peak = probe_fma_peak(a.precision)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "kernel": f"kf_run_kernel<{a.model},{kmode},{a.precision},agg>",
+                    "kernel_ms": kms, "algorithmic_bytes_per_filter_step": sp.d * rb,
+                    "fp_pipe": {"measured_fma_peak_tflops": fma_peak, "kernel_filter_steps_per_s": N * T / (kms * 1e-3)}}
+
+        # ---- e2e: host buffers through b200kf_run_batch_host
+        e2e = None
+        if not a.no_e2e:
+            Te = min(a.e2e_tsteps, T)
+            pay_h = torch.empty((Te, sp.d, N), dtype=eng.real, pin_memory=True)
+            pay_h.copy_(payload[:Te])
+            x_h = np.zeros((N, sp.n), dtype=np.float32 if a.precision == "f32" else np.float64)
+            P_h = np.repeat(sp.default_P0()[None], N, axis=0).astype(x_h.dtype)
+            torch.cuda.synchronize()
+            for _ in range(2):
+                eng.run_batch_host(types[:Te], dts[:Te], pay_h, x_h, P_h, mode=a.mode)
+            reps_e = max(3, a.steps)
+            t0 = time.perf_counter()
+            for _ in range(reps_e):
+                res = eng.run_batch_host(types[:Te], dts[:Te], pay_h, x_h, P_h, mode=a.mode)
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0) / reps_e
+            h2d = Te * sp.d * N * rb + N * (sp.n + sp.n * sp.n) * rb + Te * 9
+            d2h = N * (sp.n + sp.n * sp.n) * rb + N * 36
+            e2e = {"value": world * N * Te / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "workload": f"{N} filters x {Te} steps per call, pinned host payload",
+                   "ms_per_call": te * 1e3, "note": "rank-0 measurement x n_gpus" if world > 1 else "",
+                   "check_sum_logdet": float(res["agg"][:, 1].mean())}
+            del pay_h
+
+        # ---- secondary metric: schedules scored / s (BASELINE configs[3]: 2^20 schedules, L = 20, CA15)
+        search = None
+        if not a.no_search:
+            e15 = Engine("CA15")
+            L = 20
+            rng = np.random.default_rng(0)
+            stypes = np.where(np.arange(L) % 7 == 3, 0, 1).astype(np.uint8)
+            times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
+            P0 = e15.spec.default_P0() * 1e-3
+            for _ in range(2):
+                e15.score_schedules(stypes, times, 999.995, float(times[-1]), P0, threshold=0.0)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(5):
+                best, _ = e15.score_schedules(stypes, times, 999.995, float(times[-1]), P0, threshold=0.0)
+            s1.record()
+            torch.cuda.synchronize()
+            sms = s0.elapsed_time(s1) / 5
+            search = {"metric": "schedules_scored_per_sec", "value": (1 << L) / (sms * 1e-3), "unit": "schedules/s",
+                      "workload": "CA15, 2^20 subset schedules of a 20-event window, 1 GPU", "ms": sms,
+                      "argmin_sum_index": best["argmin_sum_index"]}
+
+        cpu = None
+        if not a.no_cpu_baseline:
+            cores = host_cores()
+            done, dt = cpu_sample(a.model, 2, 2000, cores)
+            cpu = {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cores} processes x 2 filters x 2000 events, per-filter numpy float64 loop "
+                             f"(oracle port of kf_workers.py:681-721 for {a.model}); {dt:.1f} s"}
+
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": a.precision, "data": "synthetic (device-generated payload, GPS ~N(0,3), accel ~N(0,0.1^2))",
+                "config": {"workload": workload_name(a), "mode": a.mode, "l2": "inputs (31.5 GB at defaults) larger than L2; no flush",
+                           "filters_per_gpu": N, "events_per_filter": T, "payload_layout": "[T, d, N] time-major"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
+                "roofline": roofline, "cpu_baseline": cpu, "search": search}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

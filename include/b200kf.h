@@ -1,0 +1,173 @@
+/* b200kf.h -- C ABI of libb200kf.so, the B200-native batched GPS/IMU Kalman-filter engine.
+ *
+ * The reference (IseanB/SensorFusion-KalmanFilter) is pure Python and has no FFI; the boundary
+ * it offers is the Python call surface of kf_workers.py / hw5_2.py.  Each entry
+ * point below names the reference code it replaces; INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.  Conventions:
+ *
+ *   - every function returns an int status: 0 = OK, negative = error (b200kf_last_error gives the
+ *     thread-local message); no C++ exception crosses the boundary;
+ *   - pointers documented DEVICE are caller-owned CUDA allocations of the current device, all
+ *     others are host pointers; the library never frees caller memory and keeps no pointer past
+ *     the call;
+ *   - work is enqueued on the caller's stream (a cudaStream_t passed as void*, NULL = default
+ *     stream); functions are asynchronous unless stated;
+ *   - "real" buffers hold float64 or float32 according to the model's precision; time steps
+ *     `dt` are ALWAYS float64 and are computed by the host as t - t_prev from float64 epoch
+ *     seconds (kf_workers.py:682), never from float32 timestamps.
+ */
+#ifndef B200KF_H_
+#define B200KF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200KF_VERSION_MAJOR 0
+#define B200KF_VERSION_MINOR 1
+
+/* status codes */
+#define B200KF_OK 0
+#define B200KF_ERR_INVALID (-1)     /* bad argument */
+#define B200KF_ERR_UNSUPPORTED (-2) /* shape / model outside the compiled family */
+#define B200KF_ERR_CUDA (-3)        /* CUDA runtime error, text in b200kf_last_error */
+#define B200KF_ERR_NO_DEVICE (-4)   /* no CUDA device: there is NO CPU fallback */
+
+/* model ids: state layouts and F(dt) sparsity are compiled in, rate constants are data */
+#define B200KF_MODEL_CV6 0   /* [p(3),v(3)]: kf_workers.py model restricted to rows {0,1,2,6,7,8} */
+#define B200KF_MODEL_CA8 1   /* hw5_2.py:219-304  [x,y,th,vx,vy,thdot,ax,ay] */
+#define B200KF_MODEL_BIAS9 2 /* [p(3),v(3),b(3)], IMU acceleration as control input */
+#define B200KF_MODEL_CA15 3  /* kf_workers.py:493-614  [p,rpy,v,w,a] */
+
+#define B200KF_F64 0
+#define B200KF_F32 1
+
+/* event types of a schedule (uint8) */
+#define B200KF_EV_GPS 0          /* predict + GPS update   kf_workers.py:694-697 */
+#define B200KF_EV_IMU 1          /* predict + IMU pseudo-measurement update (or control) :698-706 */
+#define B200KF_EV_PREDICT_ONLY 2 /* predict, no update     kf_workers.py:74-82, 1060-1159 */
+
+/* b200kf_run_batch flags */
+#define B200KF_RUN_AUTO 0u            /* decoupled kernel when every P is chain-compatible, else dense */
+#define B200KF_RUN_FORCE_DENSE 1u     /* always the dense (all-states-coupled) kernel */
+#define B200KF_RUN_FORCE_DECOUPLED 2u /* caller guarantees chain-compatible P (no check) */
+#define B200KF_RUN_AGG_CONTINUE 4u    /* agg holds the running aggregates of earlier chunks */
+
+typedef struct b200kf_model b200kf_model; /* opaque, library-owned */
+
+/* Replaces the eight model getters of KF_SensorFusion (kf_workers.py:493-621, hw5_2.py:219-311):
+ * their VALUES travel here, their sparsity pattern is fixed by model_id. */
+typedef struct b200kf_model_desc {
+  int32_t model_id;
+  int32_t precision;  /* B200KF_F64 / B200KF_F32 */
+  double q[16];       /* Q(dt) = dt * diag(q)           get_process_noise_covariance_matrix */
+  double r_gps[4];    /* R_GPS = diag(r_gps)            get_gps_measurement_noise_covariance_matrix */
+  double r_imu[16];   /* R_IMU = diag(r_imu)            get_imu_measurement_noise_covariance_matrix */
+  double accel_coef;  /* coefficient of dt^2 in F (0.5) get_state_transition_matrix */
+} b200kf_model_desc;
+
+/* Results of a schedule search over one index range (one GPU's shard). */
+typedef struct b200kf_best {
+  double argmin_sum_score;       /* min over the range of sum(log det P); +inf if range empty */
+  uint64_t argmin_sum_index;     /* its schedule index, ties -> lowest index */
+  uint64_t first_feasible_key;   /* (popcount << 32) | order-in-cardinality; UINT64_MAX if none */
+  uint64_t first_feasible_index; /* first schedule, in the reference's enumeration order
+                                    (kf_workers.py:1325-1336), with max(log det) < threshold */
+  uint64_t n_feasible;           /* schedules in range with max(log det) < threshold */
+  uint64_t n_near_threshold;     /* schedules with |max - threshold| <= 1e-9*max(1,|threshold|):
+                                    the feasibility decisions a 1e-12 rounding difference could flip */
+} b200kf_best;
+
+int b200kf_version(int* major, int* minor);
+size_t b200kf_last_error(char* buf, size_t n);
+
+/* number of CUDA devices visible (0 = the library cannot compute) */
+int b200kf_device_count(int* count);
+
+/* fills desc with the reference's constants for model_id (kf_workers.py:519-614, hw5_2.py:233-304) */
+int b200kf_model_default_desc(int32_t model_id, int32_t precision, b200kf_model_desc* desc);
+int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out);
+int b200kf_model_destroy(b200kf_model* model);
+/* n = states, d = payload reals per event, m_gps = GPS rows */
+int b200kf_model_dims(const b200kf_model* model, int32_t* n, int32_t* d, int32_t* m_gps);
+
+/* The filter loop: replaces the event loops of run_kalman_filter_full (kf_workers.py:681-721),
+ * run_kalman_filter (:767-823), run_adaptive_threshold_kalman_filter (:1010-1053),
+ * run_no_update_kalman_filter (:1111-1154), the inner loop of run_kalman_filter_scheduled
+ * (:914-947) and hw5_2.run_kalman_filter (hw5_2.py:332-379), for n_filters independent filters
+ * that share one event schedule.
+ *
+ *   types   DEVICE u8  [T]        event type per step
+ *   dts     DEVICE f64 [T]        t - t_prev per step
+ *   payload DEVICE real[T, d, N]  time-major, filter index fastest.  GPS rows: (E, N, alt) in
+ *                                 columns 0..m_gps-1; IMU rows: CA15 (r,p,y,wx,wy,wz,ax,ay,az),
+ *                                 CA8 (yaw, wz, ax, ay), CV6/BIAS9 (ax, ay, az)
+ *   x       DEVICE real[N, n]     in: state before step 0, out: state after step T-1
+ *   P       DEVICE real[N, n, n]  in/out covariance, row-major, full symmetric
+ *   agg     DEVICE f64 [N, 4]     nullable; (max, sum, last) of log det P over the steps and the
+ *                                 step count; with B200KF_RUN_AGG_CONTINUE max/sum/count continue
+ *   traj    DEVICE real[T, traj_ncomp, N]  nullable; x[0:traj_ncomp] after each step (:714)
+ *   logdet  DEVICE real[T, N]     nullable; log det P after each step (:716-717)
+ *   used    DEVICE u8  [T, N]     nullable; 1 where the update ran (adaptive gate, :1025-1027)
+ *   status  DEVICE i32 [N]        nullable; 0 ok, 1 = a non-positive determinant was seen
+ *   gate_threshold  NaN disables; else update only when log det of the PREDICTED P exceeds it
+ */
+int b200kf_run_batch(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
+                     const uint8_t* types, const double* dts, const void* payload, void* x, void* P,
+                     double* agg, void* traj, int32_t traj_ncomp, void* logdet, uint8_t* used,
+                     int32_t* status, double gate_threshold, uint32_t flags, void* stream);
+
+/* Same computation from HOST buffers (the call a drop-in user makes): streams `payload` to the
+ * device in time chunks, overlapping host->device copies with the kernel, and copies x, P, agg
+ * back.  Synchronous.  payload/x/P/agg are HOST pointers (pinned memory copies fastest); types
+ * and dts are host arrays.  chunk_steps = 0 picks a default. */
+int b200kf_run_batch_host(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
+                          const uint8_t* types, const double* dts, const void* payload, void* x,
+                          void* P, double* agg, int32_t* status, int64_t chunk_steps, uint32_t flags);
+
+/* The brute-force schedule search: replaces evaluate_combo_chunk_worker's log_det trace
+ * (kf_workers.py:22-97) and the enumeration + selection of
+ * run_brute_force_kalman_filter_no_sampling_min_usage (:1325-1371) for the schedules
+ * [first, first + count) of a window of n_events <= 32 events.  Schedule s uses event i iff bit i
+ * of s is set; gaps over skipped events merge into one predict (:37) and the filter is propagated
+ * to t_end at the end (:74-82).  Covariance-only: log det P never depends on measurement values.
+ *
+ *   types, times  HOST [n_events]   event types and float64 epoch times of the window
+ *   P0            HOST f64 [n, n]   covariance at t_prev
+ *   per_schedule  DEVICE f64 [count, 4] nullable: max, sum, last of the log-det trace (the max
+ *                                   and sum include the initial and the end-propagation terms,
+ *                                   :32, :81-82, :1353) and the number of terms
+ *   best          DEVICE b200kf_best, written when the stream reaches it
+ */
+int b200kf_score_schedules(const b200kf_model* model, int32_t n_events, const uint8_t* types,
+                           const double* times, double t_prev, double t_end, const double* P0,
+                           uint64_t first, uint64_t count, double threshold, double* per_schedule,
+                           b200kf_best* best, uint32_t flags, void* stream);
+
+/* Batched Scheduler.cov_matrix (kf_workers.py:112-171; the reference's only device='cuda'
+ * branch): Sigma_post = Sigma - K H^ Sigma with H^ = the k selected rows of H, for `batch`
+ * covariances.  H HOST f64 [m, n], R HOST f64 [m, m], rows HOST i32 [k] (0-based),
+ * Sigma / Sigma_post DEVICE f64 [batch, n, n], trace DEVICE f64 [batch] nullable (gain, :174-185).
+ * n <= 16, k <= 16. */
+int b200kf_cov_update(int32_t n, int32_t m, int32_t k, const int32_t* rows, const double* H,
+                      const double* R, int64_t batch, const double* Sigma, double* Sigma_post,
+                      double* trace, void* stream);
+
+/* Synthetic payload of BASELINE config 3/5 generated on the device (counter-based hash keyed by
+ * (seed, step, column, filter)): GPS rows ~ N(0, 3) in the first m_gps columns, other rows
+ * ~ N(0, 0.1^2).  payload DEVICE real [T, d, N]. */
+int b200kf_fill_payload(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
+                        const uint8_t* types /* DEVICE u8 [T] */, uint64_t seed, void* payload,
+                        void* stream);
+
+/* Measures the FP64 (or FP32) FMA peak of the current device with a register-only kernel; the
+ * FP-roofline denominator (MEASURED_PEAKS.json has none).  Synchronous. */
+int b200kf_probe_fma_peak(int32_t precision, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KF_H_ */

@@ -1,0 +1,621 @@
+// kf_api.cu -- the extern "C" surface of libb200kf.so (include/b200kf.h): argument checking,
+// model objects, dispatch to the per-model kernels, the host-buffer streaming path, and the
+// small model-independent kernels (schedule-search finaliser, batched cov_matrix, synthetic
+// payload generator, FMA-peak probe).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "kf_internal.h"
+
+namespace b200kf {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", static_cast<int>(e),
+           cudaGetErrorString(e), what);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? B200KF_ERR_NO_DEVICE
+                                                                      : B200KF_ERR_CUDA;
+}
+
+struct ModelInfo {
+  int n, d, m_gps;
+};
+static const ModelInfo kInfo[MODEL_COUNT] = {{6, 3, 3}, {8, 4, 2}, {9, 3, 3}, {15, 9, 3}};
+
+static int dispatch_run(const b200kf_model* m, const RunParams& p, unsigned flags, cudaStream_t st) {
+  switch (m->desc.model_id) {
+    case MODEL_CV6: return launch_run_m<MODEL_CV6>(m, p, flags, st);
+    case MODEL_CA8: return launch_run_m<MODEL_CA8>(m, p, flags, st);
+    case MODEL_BIAS9: return launch_run_m<MODEL_BIAS9>(m, p, flags, st);
+    case MODEL_CA15: return launch_run_m<MODEL_CA15>(m, p, flags, st);
+  }
+  return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
+}
+
+static int dispatch_score(const b200kf_model* m, const ScoreParams& p, unsigned flags,
+                          b200kf_best* best, cudaStream_t st) {
+  switch (m->desc.model_id) {
+    case MODEL_CV6: return launch_score_m<MODEL_CV6>(m, p, flags, best, st);
+    case MODEL_CA8: return launch_score_m<MODEL_CA8>(m, p, flags, best, st);
+    case MODEL_BIAS9: return launch_score_m<MODEL_BIAS9>(m, p, flags, best, st);
+    case MODEL_CA15: return launch_score_m<MODEL_CA15>(m, p, flags, best, st);
+  }
+  return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
+}
+
+// ---- schedule-search finaliser: reduce the per-block partials to one b200kf_best -------------
+__global__ void score_final_kernel(const ScorePartial* parts, int n_parts, int L, b200kf_best* out) {
+  __shared__ ScorePartial sh[256];
+  ScorePartial r{INFINITY, ~0ULL, ~0ULL, 0ULL, 0ULL};
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) {
+    const ScorePartial q = parts[i];
+    if (q.score < r.score || (q.score == r.score && q.index < r.index)) {
+      r.score = q.score;
+      r.index = q.index;
+    }
+    r.key = q.key < r.key ? q.key : r.key;
+    r.n_feasible += q.n_feasible;
+    r.n_near += q.n_near;
+  }
+  sh[threadIdx.x] = r;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      ScorePartial& a = sh[threadIdx.x];
+      const ScorePartial b = sh[threadIdx.x + s];
+      if (b.score < a.score || (b.score == a.score && b.index < a.index)) {
+        a.score = b.score;
+        a.index = b.index;
+      }
+      a.key = b.key < a.key ? b.key : a.key;
+      a.n_feasible += b.n_feasible;
+      a.n_near += b.n_near;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const ScorePartial a = sh[0];
+    out->argmin_sum_score = a.score;
+    out->argmin_sum_index = a.index;
+    out->first_feasible_key = a.key;
+    out->n_feasible = a.n_feasible;
+    out->n_near_threshold = a.n_near;
+    if (a.key == ~0ULL) {
+      out->first_feasible_index = ~0ULL;
+    } else {
+      const unsigned long long full = (1ULL << L) - 1ULL;
+      const unsigned long long rev = full - (a.key & 0xffffffffULL);
+      out->first_feasible_index = __brevll(rev) >> (64 - L);
+    }
+  }
+}
+
+// ---- batched Scheduler.cov_matrix (kf_workers.py:112-147) ------------------------------------
+struct CovParams {
+  int n, k;
+  double H[kMaxN * kMaxN];  // row-selected H^  [k, n]
+  double R[kMaxN * kMaxN];  // row/col-selected R^ [k, k]
+};
+
+__global__ void cov_update_kernel(const CovParams p, long long batch, const double* __restrict__ Sigma,
+                                  double* __restrict__ post, double* __restrict__ trace) {
+  const long long b = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (b >= batch) return;
+  const int n = p.n, k = p.k;
+  const double* S0 = Sigma + b * n * n;
+  double A[kMaxN * kMaxN];   // H^ Sigma            [k, n]
+  double Bm[kMaxN * kMaxN];  // Sigma H^^T          [n, k]
+  double S[kMaxN * kMaxN];   // R^ + H^ Sigma H^^T  [k, k]
+  double Si[kMaxN * kMaxN];  // inverse
+  for (int r = 0; r < k; ++r)
+    for (int c = 0; c < n; ++c) {
+      double a = 0, bb = 0;
+      for (int j = 0; j < n; ++j) {
+        a += p.H[r * n + j] * S0[j * n + c];
+        bb += S0[c * n + j] * p.H[r * n + j];
+      }
+      A[r * n + c] = a;
+      Bm[c * k + r] = bb;
+    }
+  for (int r = 0; r < k; ++r)
+    for (int c = 0; c < k; ++c) {
+      double a = p.R[r * k + c];
+      for (int j = 0; j < n; ++j) a += p.H[r * n + j] * Bm[j * k + c];
+      S[r * k + c] = a;
+      Si[r * k + c] = (r == c) ? 1.0 : 0.0;
+    }
+  // Gauss-Jordan with partial pivoting (numpy's inv is LU with partial pivoting)
+  for (int c = 0; c < k; ++c) {
+    int piv = c;
+    double best = fabs(S[c * k + c]);
+    for (int r = c + 1; r < k; ++r)
+      if (fabs(S[r * k + c]) > best) {
+        best = fabs(S[r * k + c]);
+        piv = r;
+      }
+    if (piv != c)
+      for (int j = 0; j < k; ++j) {
+        double t = S[c * k + j];
+        S[c * k + j] = S[piv * k + j];
+        S[piv * k + j] = t;
+        t = Si[c * k + j];
+        Si[c * k + j] = Si[piv * k + j];
+        Si[piv * k + j] = t;
+      }
+    const double inv = 1.0 / S[c * k + c];
+    for (int j = 0; j < k; ++j) {
+      S[c * k + j] *= inv;
+      Si[c * k + j] *= inv;
+    }
+    for (int r = 0; r < k; ++r)
+      if (r != c) {
+        const double f = S[r * k + c];
+        if (f != 0.0)
+          for (int j = 0; j < k; ++j) {
+            S[r * k + j] -= f * S[c * k + j];
+            Si[r * k + j] -= f * Si[c * k + j];
+          }
+      }
+  }
+  // K = Bm Si [n, k];  post = Sigma - K A
+  double tr = 0;
+  double* out = post + b * n * n;
+  for (int r = 0; r < n; ++r) {
+    double Krow[kMaxN];
+    for (int c = 0; c < k; ++c) {
+      double a = 0;
+      for (int j = 0; j < k; ++j) a += Bm[r * k + j] * Si[j * k + c];
+      Krow[c] = a;
+    }
+    for (int c = 0; c < n; ++c) {
+      double a = 0;
+      for (int j = 0; j < k; ++j) a += Krow[j] * A[j * n + c];
+      const double v = S0[r * n + c] - a;
+      out[r * n + c] = v;
+      if (r == c) tr += v;
+    }
+  }
+  if (trace != nullptr) trace[b] = tr;
+}
+
+// ---- synthetic payload (BASELINE config 3/5 shape) --------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+template <typename real>
+__global__ void fill_payload_kernel(real* __restrict__ out, const uint8_t* __restrict__ types,
+                                    long long N, long long T, int d, int m_gps,
+                                    unsigned long long seed) {
+  const long long total = T * d * N;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / N;  // k * d + c
+    const int c = static_cast<int>(row % d);
+    const long long k = row / d;
+    const bool gps = types[k] == EV_GPS;
+    const double sigma = gps ? (c < m_gps ? 1.7320508075688772 : 0.0) : 0.1;
+    const unsigned long long h = mix64(seed ^ mix64(static_cast<unsigned long long>(i)));
+    const double u1 = (static_cast<double>(h >> 40) + 0.5) * (1.0 / 16777216.0);
+    const double u2 = (static_cast<double>((h >> 16) & 0xFFFFFF) + 0.5) * (1.0 / 16777216.0);
+    const double g = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    out[i] = static_cast<real>(sigma * g);
+  }
+}
+
+// ---- FMA peak probe ----------------------------------------------------------------------------
+template <typename real>
+__global__ void fma_probe_kernel(real* out, int iters, real a, real b) {
+  real v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5,
+       v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v0 = fma(v0, a, b);
+      v1 = fma(v1, a, b);
+      v2 = fma(v2, a, b);
+      v3 = fma(v3, a, b);
+      v4 = fma(v4, a, b);
+      v5 = fma(v5, a, b);
+      v6 = fma(v6, a, b);
+      v7 = fma(v7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+template <typename real>
+static int probe_peak(double* tflops) {
+  int dev = 0, sms = 0;
+  B200KF_CUDA_TRY(cudaGetDevice(&dev));
+  B200KF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tpb = 256, blocks = sms * 8, iters = 4096;
+  real* out = nullptr;
+  B200KF_CUDA_TRY(cudaMalloc(&out, sizeof(real) * tpb * blocks));
+  cudaEvent_t e0, e1;
+  B200KF_CUDA_TRY(cudaEventCreate(&e0));
+  B200KF_CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    B200KF_CUDA_TRY(cudaEventRecord(e0));
+    fma_probe_kernel<real><<<blocks, tpb>>>(out, iters, real(0.999999), real(1e-6));
+    B200KF_CUDA_TRY(cudaEventRecord(e1));
+    B200KF_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    B200KF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * iters * tpb * static_cast<double>(blocks);
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return B200KF_OK;
+}
+
+}  // namespace b200kf
+
+using namespace b200kf;
+
+extern "C" {
+
+int b200kf_version(int* major, int* minor) {
+  if (major) *major = B200KF_VERSION_MAJOR;
+  if (minor) *minor = B200KF_VERSION_MINOR;
+  return B200KF_OK;
+}
+
+size_t b200kf_last_error(char* buf, size_t n) {
+  const size_t len = strlen(g_err);
+  if (buf && n) {
+    strncpy(buf, g_err, n - 1);
+    buf[n - 1] = 0;
+  }
+  return len;
+}
+
+int b200kf_device_count(int* count) {
+  if (!count) return set_error(B200KF_ERR_INVALID, "count is null");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    return B200KF_OK;
+  }
+  *count = c;
+  return B200KF_OK;
+}
+
+int b200kf_model_default_desc(int32_t model_id, int32_t precision, b200kf_model_desc* desc) {
+  if (!desc) return set_error(B200KF_ERR_INVALID, "desc is null");
+  if (model_id < 0 || model_id >= MODEL_COUNT)
+    return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", model_id);
+  memset(desc, 0, sizeof(*desc));
+  desc->model_id = model_id;
+  desc->precision = precision;
+  desc->accel_coef = 0.5;
+  for (int i = 0; i < 4; ++i) desc->r_gps[i] = 3.0;  // kf_workers.py:583, hw5_2.py:282
+  auto set3 = [](double* a, int at, double v) { a[at] = a[at + 1] = a[at + 2] = v; };
+  switch (model_id) {
+    case MODEL_CV6:
+      set3(desc->q, 0, 5.0), set3(desc->q, 3, 1.0);
+      set3(desc->r_imu, 0, 50.0), set3(desc->r_imu, 3, 10.0);
+      break;
+    case MODEL_CA8: {  // hw5_2.py:235-249, 288-303
+      const double q[8] = {5, 5, 0.05, 1, 1, 0.1, 2, 2};
+      const double r[8] = {50, 50, 0.05, 10, 10, 0.1, 100, 100};
+      memcpy(desc->q, q, sizeof(q));
+      memcpy(desc->r_imu, r, sizeof(r));
+      break;
+    }
+    case MODEL_BIAS9:
+      set3(desc->q, 0, 5.0), set3(desc->q, 3, 1.0), set3(desc->q, 6, 2.0);
+      break;
+    case MODEL_CA15:  // kf_workers.py:521-543, 589-613
+      set3(desc->q, 0, 5.0), set3(desc->q, 3, 0.05), set3(desc->q, 6, 1.0), set3(desc->q, 9, 0.1),
+          set3(desc->q, 12, 2.0);
+      set3(desc->r_imu, 0, 50.0), set3(desc->r_imu, 3, 0.05), set3(desc->r_imu, 6, 10.0),
+          set3(desc->r_imu, 9, 0.1), set3(desc->r_imu, 12, 100.0);
+      break;
+  }
+  return B200KF_OK;
+}
+
+int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
+  if (!desc || !out) return set_error(B200KF_ERR_INVALID, "null argument");
+  if (desc->model_id < 0 || desc->model_id >= MODEL_COUNT)
+    return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", desc->model_id);
+  if (desc->precision != B200KF_F64 && desc->precision != B200KF_F32)
+    return set_error(B200KF_ERR_UNSUPPORTED, "unknown precision %d", desc->precision);
+  const ModelInfo info = kInfo[desc->model_id];
+  for (int i = 0; i < info.n; ++i) {
+    if (!(desc->q[i] >= 0.0)) return set_error(B200KF_ERR_INVALID, "q[%d] must be >= 0", i);
+    if (!(desc->r_imu[i] >= 0.0)) return set_error(B200KF_ERR_INVALID, "r_imu[%d] must be >= 0", i);
+  }
+  for (int i = 0; i < info.m_gps; ++i)
+    if (!(desc->r_gps[i] > 0.0)) return set_error(B200KF_ERR_INVALID, "r_gps[%d] must be > 0", i);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return set_error(B200KF_ERR_NO_DEVICE,
+                     "no CUDA device: libb200kf has no CPU fallback (cudaGetDeviceCount: %s)",
+                     e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+  }
+  b200kf_model* m = new (std::nothrow) b200kf_model();
+  if (!m) return set_error(B200KF_ERR_INVALID, "out of host memory");
+  m->desc = *desc;
+  memcpy(m->mc.q, desc->q, sizeof(m->mc.q));
+  memcpy(m->mc.r_gps, desc->r_gps, sizeof(m->mc.r_gps));
+  memcpy(m->mc.r_imu, desc->r_imu, sizeof(m->mc.r_imu));
+  m->mc.c2 = desc->accel_coef;
+  m->n = info.n, m->d = info.d, m->m_gps = info.m_gps;
+  m->arena = nullptr;
+  m->arena_bytes = kArenaBytes;
+  m->tpb = 64;
+  if (const char* s = getenv("B200KF_TPB")) {
+    const int v = atoi(s);
+    if (v >= 32 && v <= 256 && v % 32 == 0) m->tpb = v;
+  }
+  e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
+  if (e == cudaSuccess) e = cudaMalloc(&m->arena, m->arena_bytes);
+  if (e != cudaSuccess) {
+    delete m;
+    return cuda_fail(e, "b200kf_model_create");
+  }
+  *out = m;
+  return B200KF_OK;
+}
+
+int b200kf_model_destroy(b200kf_model* m) {
+  if (!m) return B200KF_OK;
+  if (m->arena) cudaFree(m->arena);
+  delete m;
+  return B200KF_OK;
+}
+
+int b200kf_model_dims(const b200kf_model* m, int32_t* n, int32_t* d, int32_t* m_gps) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (n) *n = m->n;
+  if (d) *d = m->d;
+  if (m_gps) *m_gps = m->m_gps;
+  return B200KF_OK;
+}
+
+int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const uint8_t* types,
+                     const double* dts, const void* payload, void* x, void* P, double* agg,
+                     void* traj, int32_t traj_ncomp, void* logdet, uint8_t* used, int32_t* status,
+                     double gate_threshold, uint32_t flags, void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (n_filters < 0 || n_steps < 0) return set_error(B200KF_ERR_INVALID, "negative size");
+  if (n_steps > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_steps > 2^31-1 per call");
+  if (n_filters == 0) return B200KF_OK;
+  if (!x || !P) return set_error(B200KF_ERR_INVALID, "x and P are required");
+  if (n_steps > 0 && (!types || !dts || !payload))
+    return set_error(B200KF_ERR_INVALID, "types, dts and payload are required when n_steps > 0");
+  if (traj && (traj_ncomp < 1 || traj_ncomp > m->n))
+    return set_error(B200KF_ERR_INVALID, "traj_ncomp must be in [1, %d]", m->n);
+  if ((flags & B200KF_RUN_FORCE_DENSE) && (flags & B200KF_RUN_FORCE_DECOUPLED))
+    return set_error(B200KF_ERR_INVALID, "FORCE_DENSE and FORCE_DECOUPLED are exclusive");
+  RunParams p;
+  p.mc = m->mc;
+  p.n_filters = n_filters;
+  p.n_steps = static_cast<int>(n_steps);
+  p.types = types;
+  p.dts = dts;
+  p.payload = payload;
+  p.x = x;
+  p.P = P;
+  p.agg = agg;
+  p.traj = traj;
+  p.traj_ncomp = traj ? traj_ncomp : 0;
+  p.logdet = logdet;
+  p.used = used;
+  p.status = status;
+  p.gate_enabled = std::isnan(gate_threshold) ? 0 : 1;
+  p.gate_threshold = gate_threshold;
+  p.agg_continue = (flags & B200KF_RUN_AGG_CONTINUE) ? 1 : 0;
+  p.dense_flag = nullptr;
+  return dispatch_run(m, p, flags, static_cast<cudaStream_t>(stream));
+}
+
+int b200kf_run_batch_host(const b200kf_model* m, int64_t n_filters, int64_t n_steps,
+                          const uint8_t* types, const double* dts, const void* payload, void* x,
+                          void* P, double* agg, int32_t* status, int64_t chunk_steps, uint32_t flags) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (n_filters <= 0 || n_steps < 0) return set_error(B200KF_ERR_INVALID, "bad size");
+  if (!x || !P) return set_error(B200KF_ERR_INVALID, "x and P are required");
+  if (n_steps > 0 && (!types || !dts || !payload))
+    return set_error(B200KF_ERR_INVALID, "types, dts and payload are required");
+  const size_t rs = m->desc.precision == B200KF_F32 ? 4 : 8;
+  const size_t step_bytes = static_cast<size_t>(m->d) * n_filters * rs;
+  if (chunk_steps <= 0) {
+    chunk_steps = static_cast<int64_t>((size_t(256) << 20) / (step_bytes ? step_bytes : 1));
+    if (chunk_steps < 16) chunk_steps = 16;
+  }
+  if (chunk_steps > n_steps) chunk_steps = n_steps > 0 ? n_steps : 1;
+  const size_t xb = static_cast<size_t>(n_filters) * m->n * rs;
+  const size_t Pb = xb * m->n;
+
+  int rc = B200KF_OK;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  void *d_pay[2] = {nullptr, nullptr}, *d_x = nullptr, *d_P = nullptr;
+  double* d_agg = nullptr;
+  int32_t* d_status = nullptr;
+  uint8_t* d_types = nullptr;
+  double* d_dts = nullptr;
+#define HOST_TRY(expr)                              \
+  do {                                              \
+    cudaError_t _e = (expr);                        \
+    if (_e != cudaSuccess) {                        \
+      rc = cuda_fail(_e, #expr);                    \
+      goto done;                                    \
+    }                                               \
+  } while (0)
+  HOST_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+  HOST_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    HOST_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+    HOST_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    HOST_TRY(cudaMalloc(&d_pay[i], step_bytes * chunk_steps));
+  }
+  HOST_TRY(cudaMalloc(&d_x, xb));
+  HOST_TRY(cudaMalloc(&d_P, Pb));
+  HOST_TRY(cudaMalloc(&d_agg, sizeof(double) * 4 * n_filters));
+  HOST_TRY(cudaMalloc(&d_status, sizeof(int32_t) * n_filters));
+  HOST_TRY(cudaMalloc(&d_types, n_steps > 0 ? n_steps : 1));
+  HOST_TRY(cudaMalloc(&d_dts, sizeof(double) * (n_steps > 0 ? n_steps : 1)));
+  HOST_TRY(cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, s_comp));
+  HOST_TRY(cudaMemcpyAsync(d_P, P, Pb, cudaMemcpyHostToDevice, s_comp));
+  if (n_steps > 0) {
+    HOST_TRY(cudaMemcpyAsync(d_types, types, n_steps, cudaMemcpyHostToDevice, s_comp));
+    HOST_TRY(cudaMemcpyAsync(d_dts, dts, sizeof(double) * n_steps, cudaMemcpyHostToDevice, s_comp));
+  }
+  {
+    int64_t c = 0;
+    for (int64_t k0 = 0; k0 < n_steps || c == 0; k0 += chunk_steps, ++c) {
+      const int b = static_cast<int>(c & 1);
+      const int64_t steps = (n_steps - k0) < chunk_steps ? (n_steps - k0) : chunk_steps;
+      if (steps > 0) {
+        if (c >= 2) HOST_TRY(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
+        HOST_TRY(cudaMemcpyAsync(d_pay[b], static_cast<const char*>(payload) + step_bytes * k0,
+                                 step_bytes * steps, cudaMemcpyHostToDevice, s_copy));
+        HOST_TRY(cudaEventRecord(ev_copied[b], s_copy));
+        HOST_TRY(cudaStreamWaitEvent(s_comp, ev_copied[b], 0));
+      }
+      const uint32_t f = (flags & ~B200KF_RUN_AGG_CONTINUE) | (c > 0 ? B200KF_RUN_AGG_CONTINUE : 0u);
+      rc = b200kf_run_batch(m, n_filters, steps, d_types + k0, d_dts + k0, d_pay[b], d_x, d_P, d_agg,
+                            nullptr, 0, nullptr, nullptr, d_status, NAN, f, s_comp);
+      if (rc != B200KF_OK) goto done;
+      HOST_TRY(cudaEventRecord(ev_done[b], s_comp));
+      if (n_steps == 0) break;
+    }
+  }
+  HOST_TRY(cudaMemcpyAsync(x, d_x, xb, cudaMemcpyDeviceToHost, s_comp));
+  HOST_TRY(cudaMemcpyAsync(P, d_P, Pb, cudaMemcpyDeviceToHost, s_comp));
+  if (agg) HOST_TRY(cudaMemcpyAsync(agg, d_agg, sizeof(double) * 4 * n_filters, cudaMemcpyDeviceToHost, s_comp));
+  if (status)
+    HOST_TRY(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * n_filters, cudaMemcpyDeviceToHost, s_comp));
+  HOST_TRY(cudaStreamSynchronize(s_comp));
+done:
+  if (rc != B200KF_OK) cudaDeviceSynchronize();
+  for (int i = 0; i < 2; ++i) {
+    if (d_pay[i]) cudaFree(d_pay[i]);
+    if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+    if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+  }
+  if (d_x) cudaFree(d_x);
+  if (d_P) cudaFree(d_P);
+  if (d_agg) cudaFree(d_agg);
+  if (d_status) cudaFree(d_status);
+  if (d_types) cudaFree(d_types);
+  if (d_dts) cudaFree(d_dts);
+  if (s_copy) cudaStreamDestroy(s_copy);
+  if (s_comp) cudaStreamDestroy(s_comp);
+#undef HOST_TRY
+  return rc;
+}
+
+int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_t* types,
+                           const double* times, double t_prev, double t_end, const double* P0,
+                           uint64_t first, uint64_t count, double threshold, double* per_schedule,
+                           b200kf_best* best, uint32_t flags, void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (n_events < 1 || n_events > kMaxEvents)
+    return set_error(B200KF_ERR_UNSUPPORTED, "n_events must be in [1, %d]", kMaxEvents);
+  if (!types || !times || !P0 || !best) return set_error(B200KF_ERR_INVALID, "null argument");
+  const uint64_t total = 1ULL << n_events;
+  if (first > total || count > total - first)
+    return set_error(B200KF_ERR_INVALID, "schedule range exceeds 2^n_events");
+  ScoreParams p;
+  p.mc = m->mc;
+  p.n_events = n_events;
+  memset(p.types, 0, sizeof(p.types));
+  memset(p.times, 0, sizeof(p.times));
+  memset(p.P0, 0, sizeof(p.P0));
+  for (int i = 0; i < n_events; ++i) {
+    if (types[i] > B200KF_EV_PREDICT_ONLY) return set_error(B200KF_ERR_INVALID, "bad event type");
+    p.types[i] = types[i];
+    p.times[i] = times[i];
+  }
+  memcpy(p.P0, P0, sizeof(double) * m->n * m->n);
+  p.t_prev = t_prev;
+  p.t_end = t_end;
+  p.first = first;
+  p.count = count;
+  p.threshold = threshold;
+  p.per_schedule = per_schedule;
+  p.partials = search_scratch(m);
+  p.dense_flag = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = dispatch_score(m, p, flags, best, st);
+  if (blocks < 0) return blocks;
+  score_final_kernel<<<1, 256, 0, st>>>(static_cast<const ScorePartial*>(p.partials), blocks, n_events, best);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
+}
+
+int b200kf_cov_update(int32_t n, int32_t m_rows, int32_t k, const int32_t* rows, const double* H,
+                      const double* R, int64_t batch, const double* Sigma, double* Sigma_post,
+                      double* trace, void* stream) {
+  if (n < 1 || n > kMaxN || k < 1 || k > kMaxN || m_rows < k)
+    return set_error(B200KF_ERR_UNSUPPORTED, "need 1 <= n <= 16 and 1 <= k <= min(m, 16)");
+  if (!rows || !H || !R || !Sigma || !Sigma_post) return set_error(B200KF_ERR_INVALID, "null argument");
+  if (batch <= 0) return B200KF_OK;
+  CovParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n;
+  p.k = k;
+  for (int a = 0; a < k; ++a) {
+    if (rows[a] < 0 || rows[a] >= m_rows) return set_error(B200KF_ERR_INVALID, "row index out of range");
+    for (int j = 0; j < n; ++j) p.H[a * n + j] = H[rows[a] * n + j];
+    for (int b = 0; b < k; ++b) p.R[a * k + b] = R[rows[a] * m_rows + rows[b]];
+  }
+  const int tpb = 64;
+  cov_update_kernel<<<static_cast<unsigned>((batch + tpb - 1) / tpb), tpb, 0,
+                      static_cast<cudaStream_t>(stream)>>>(p, batch, Sigma, Sigma_post, trace);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
+}
+
+int b200kf_fill_payload(const b200kf_model* m, int64_t n_filters, int64_t n_steps,
+                        const uint8_t* types, uint64_t seed, void* payload, void* stream) {
+  if (!m || !types || !payload) return set_error(B200KF_ERR_INVALID, "null argument");
+  if (n_filters <= 0 || n_steps <= 0) return B200KF_OK;
+  const int blocks = m->sm_count * 16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (m->desc.precision == B200KF_F32)
+    fill_payload_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(payload), types, n_filters,
+                                                       n_steps, m->d, m->m_gps, seed);
+  else
+    fill_payload_kernel<double><<<blocks, 256, 0, st>>>(static_cast<double*>(payload), types, n_filters,
+                                                        n_steps, m->d, m->m_gps, seed);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
+}
+
+int b200kf_probe_fma_peak(int32_t precision, double* tflops) {
+  if (!tflops) return set_error(B200KF_ERR_INVALID, "tflops is null");
+  if (precision == B200KF_F32) return probe_peak<float>(tflops);
+  return probe_peak<double>(tflops);
+}
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+// kf_core.cuh -- register-resident Kalman-filter block engine and the model tables.
+//
+// A model (CV6 / CA8 / BIAS9 / CA15) is a list of independent *chains* (blocks): with the
+// reference's diagonal Q, R and row-selector H (kf_workers.py:519-614, hw5_2.py:233-304) the
+// filter never couples axes, so a block-compatible covariance can be filtered
+// chain by chain ("decoupled"), and an arbitrary dense covariance as ONE block holding every
+// state ("dense", the Union<> of the chains).  Both run the same code below.
+//
+// Per block the state x[n] and the upper triangle of the symmetric covariance P live in
+// registers: every loop is unrolled at compile time (static_for) so all indices are constants.
+//
+//   predict   x = F x (+ B u),  P = F P F^T + Q     kf_workers.py:546-549, 688-691
+//             F = I + dt*N1 + c2*dt^2*N2 is applied as elementary row/column operations
+//   update    K = P H^T (H P H^T + R)^-1, x += K(z - Hx), P = (I - KH) P   :616-621, :709-711
+//             H selects states and R is diagonal, so the joint update equals a sequence of
+//             scalar updates (exact in exact arithmetic); each costs one reciprocal
+//   metric    det P (log taken by the caller)        :716
+#pragma once
+#include <cstdint>
+#include <type_traits>
+#include <cuda_runtime.h>
+
+namespace b200kf {
+
+constexpr int kMaxN = 16;
+constexpr int kMaxMGps = 4;
+
+// Rate constants of a model instance (host getters -> desc -> here); passed by value as a kernel
+// parameter so every access is a constant-offset ld.param.
+struct ModelConst {
+  double q[kMaxN];         // Q(dt) = dt * diag(q)              kf_workers.py:519-544
+  double r_gps[kMaxMGps];  // R_GPS = diag(r_gps)               kf_workers.py:581-585
+  double r_imu[kMaxN];     // R_IMU = diag(r_imu)               kf_workers.py:587-614
+  double c2;               // coefficient of dt^2 in F (0.5)    kf_workers.py:501-503
+};
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// IMU pseudo-measurement kinds (kf_workers.py:698-704)
+enum : int { ZK_POS = 0, ZK_VEL = 1, ZK_DIRECT = 2, ZK_NONE = 3 };
+
+// --------------------------------------------------------------------------------------
+// Chain tables.  Local state order inside a chain is (value, rate, rate-of-rate).
+//   gidx(i)   global state index           l1/l2(i)  local index multiplied by dt / c2*dt^2
+//   s1/s2(i)  sign of that coefficient      gps(i)    GPS payload column measuring state i
+//   zk(i)     IMU pseudo-measurement kind   pz(i)     payload column it reads
+//   cu(i)     control kind for imu_control models: 1 -> +c2*dt^2*u, 2 -> +dt*u, 0 none
+// --------------------------------------------------------------------------------------
+template <int AXIS>
+struct CV6Chain {  // [p, v] of one axis; global layout [p(3), v(3)]
+  static constexpr int n = 2;
+  static constexpr int gidx(int i) { return i == 0 ? AXIS : 3 + AXIS; }
+  static constexpr int l1(int i) { return i == 0 ? 1 : -1; }
+  static constexpr int l2(int) { return -1; }
+  static constexpr int s1(int) { return 1; }
+  static constexpr int s2(int) { return 1; }
+  static constexpr int gps(int i) { return i == 0 ? AXIS : -1; }
+  static constexpr int zk(int i) { return i == 0 ? ZK_POS : ZK_VEL; }
+  static constexpr int pz(int) { return AXIS; }
+  static constexpr int cu(int) { return 0; }
+};
+
+template <int AXIS>
+struct CA8LinChain {  // [x|y, v, a]; global [x, y, th, vx, vy, thdot, ax, ay]  hw5_2.py:219-231
+  static constexpr int n = 3;
+  static constexpr int gidx(int i) { return i == 0 ? AXIS : (i == 1 ? 3 + AXIS : 6 + AXIS); }
+  static constexpr int l1(int i) { return i == 0 ? 1 : (i == 1 ? 2 : -1); }
+  static constexpr int l2(int i) { return i == 0 ? 2 : -1; }
+  static constexpr int s1(int) { return 1; }
+  static constexpr int s2(int) { return 1; }
+  static constexpr int gps(int i) { return i == 0 ? AXIS : -1; }
+  static constexpr int zk(int i) { return i == 0 ? ZK_POS : (i == 1 ? ZK_VEL : ZK_DIRECT); }
+  static constexpr int pz(int) { return 2 + AXIS; }  // payload [yaw, wz, ax, ay]
+  static constexpr int cu(int) { return 0; }
+};
+
+struct CA8YawChain {  // [theta, theta_dot]
+  static constexpr int n = 2;
+  static constexpr int gidx(int i) { return i == 0 ? 2 : 5; }
+  static constexpr int l1(int i) { return i == 0 ? 1 : -1; }
+  static constexpr int l2(int) { return -1; }
+  static constexpr int s1(int) { return 1; }
+  static constexpr int s2(int) { return 1; }
+  static constexpr int gps(int) { return -1; }
+  static constexpr int zk(int) { return ZK_DIRECT; }
+  static constexpr int pz(int i) { return i; }
+  static constexpr int cu(int) { return 0; }
+};
+
+template <int AXIS>
+struct CA15LinChain {  // [p, v, a]; global [p(3), rpy(3), v(3), w(3), a(3)]  kf_workers.py:493-517
+  static constexpr int n = 3;
+  static constexpr int gidx(int i) { return i == 0 ? AXIS : (i == 1 ? 6 + AXIS : 12 + AXIS); }
+  static constexpr int l1(int i) { return i == 0 ? 1 : (i == 1 ? 2 : -1); }
+  static constexpr int l2(int i) { return i == 0 ? 2 : -1; }
+  static constexpr int s1(int) { return 1; }
+  static constexpr int s2(int) { return 1; }
+  static constexpr int gps(int i) { return i == 0 ? AXIS : -1; }
+  static constexpr int zk(int i) { return i == 0 ? ZK_POS : (i == 1 ? ZK_VEL : ZK_DIRECT); }
+  static constexpr int pz(int) { return 6 + AXIS; }  // payload [r,p,y, wx,wy,wz, ax,ay,az]
+  static constexpr int cu(int) { return 0; }
+};
+
+template <int AXIS>
+struct CA15AngChain {  // [angle, rate]
+  static constexpr int n = 2;
+  static constexpr int gidx(int i) { return i == 0 ? 3 + AXIS : 9 + AXIS; }
+  static constexpr int l1(int i) { return i == 0 ? 1 : -1; }
+  static constexpr int l2(int) { return -1; }
+  static constexpr int s1(int) { return 1; }
+  static constexpr int s2(int) { return 1; }
+  static constexpr int gps(int) { return -1; }
+  static constexpr int zk(int) { return ZK_DIRECT; }
+  static constexpr int pz(int i) { return i == 0 ? AXIS : 3 + AXIS; }
+  static constexpr int cu(int) { return 0; }
+};
+
+template <int AXIS>
+struct BIAS9Chain {  // [p, v, b]; p += dt v - c2 dt^2 b, v -= dt b; u = accel (SURVEY.md 8(d) cfg 5)
+  static constexpr int n = 3;
+  static constexpr int gidx(int i) { return AXIS + 3 * i; }
+  static constexpr int l1(int i) { return i == 0 ? 1 : (i == 1 ? 2 : -1); }
+  static constexpr int l2(int i) { return i == 0 ? 2 : -1; }
+  static constexpr int s1(int i) { return i == 0 ? 1 : -1; }
+  static constexpr int s2(int) { return -1; }
+  static constexpr int gps(int i) { return i == 0 ? AXIS : -1; }
+  static constexpr int zk(int) { return ZK_NONE; }
+  static constexpr int pz(int) { return AXIS; }
+  static constexpr int cu(int i) { return i == 0 ? 1 : (i == 1 ? 2 : 0); }
+};
+
+// The dense form of a model: one block holding every state of the listed chains.
+template <class... Bs>
+struct Union {
+  static constexpr int n = (Bs::n + ...);
+  template <class B>
+  static constexpr int local_of(int g) {
+    for (int i = 0; i < B::n; ++i)
+      if (B::gidx(i) == g) return i;
+    return -1;
+  }
+  static constexpr int gidx(int i) { return i; }
+#define B200KF_UNION_LOOKUP(name, expr, dflt)                                   \
+  template <class B>                                                            \
+  static constexpr bool name##_one(int g, int& r) {                             \
+    const int i = local_of<B>(g);                                               \
+    if (i >= 0) { r = (expr); return true; }                                    \
+    return false;                                                               \
+  }                                                                             \
+  static constexpr int name(int g) {                                            \
+    int r = (dflt);                                                             \
+    (void)(name##_one<Bs>(g, r) || ...);                                        \
+    return r;                                                                   \
+  }
+  B200KF_UNION_LOOKUP(l1, (B::l1(i) >= 0 ? B::gidx(B::l1(i)) : -1), -1)
+  B200KF_UNION_LOOKUP(l2, (B::l2(i) >= 0 ? B::gidx(B::l2(i)) : -1), -1)
+  B200KF_UNION_LOOKUP(s1, B::s1(i), 1)
+  B200KF_UNION_LOOKUP(s2, B::s2(i), 1)
+  B200KF_UNION_LOOKUP(gps, B::gps(i), -1)
+  B200KF_UNION_LOOKUP(zk, B::zk(i), ZK_NONE)
+  B200KF_UNION_LOOKUP(pz, B::pz(i), 0)
+  B200KF_UNION_LOOKUP(cu, B::cu(i), 0)
+#undef B200KF_UNION_LOOKUP
+};
+
+// --------------------------------------------------------------------------------------
+// One block in registers
+// --------------------------------------------------------------------------------------
+template <class B, typename real>
+struct BlockKF {
+  static constexpr int n = B::n;
+  static constexpr int NP = n * (n + 1) / 2;
+  real x[n];
+  real P[NP];
+  static constexpr int gidx(int i) { return B::gidx(i); }
+
+  static constexpr int pidx(int i, int j) {
+    return i <= j ? (i * n - i * (i - 1) / 2 + (j - i)) : (j * n - j * (j - 1) / 2 + (i - j));
+  }
+
+  // xg: [n_total] of this filter, Pg: [n_total, n_total] row-major of this filter.
+  __device__ __forceinline__ void load(const real* __restrict__ xg, const real* __restrict__ Pg,
+                                       int n_total) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      x[i] = xg[B::gidx(i)];
+      static_for<i, n>([&](auto J) {
+        constexpr int j = J;
+        const real a = Pg[B::gidx(i) * n_total + B::gidx(j)];
+        const real b = Pg[B::gidx(j) * n_total + B::gidx(i)];
+        P[pidx(i, j)] = real(0.5) * (a + b);
+      });
+    });
+  }
+
+  __device__ __forceinline__ void store(real* __restrict__ xg, real* __restrict__ Pg,
+                                        int n_total) const {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      xg[B::gidx(i)] = x[i];
+      static_for<i, n>([&](auto J) {
+        constexpr int j = J;
+        Pg[B::gidx(i) * n_total + B::gidx(j)] = P[pidx(i, j)];
+        Pg[B::gidx(j) * n_total + B::gidx(i)] = P[pidx(i, j)];
+      });
+    });
+  }
+
+  // covariance-only initialisation from a dense [n_total, n_total] matrix in param/constant space
+  __device__ __forceinline__ void load_cov(const double* __restrict__ Pg, int n_total) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      x[i] = real(0);
+      static_for<i, n>([&](auto J) {
+        constexpr int j = J;
+        P[pidx(i, j)] = real(0.5 * (Pg[B::gidx(i) * n_total + B::gidx(j)] +
+                                    Pg[B::gidx(j) * n_total + B::gidx(i)]));
+      });
+    });
+  }
+
+  // x = F x, P = F P F^T + Q.  F = prod of elementary ops "row i += c1*row l1 + c2*row l2";
+  // links always point to a higher local index, so ascending i reads not-yet-modified rows.
+  template <bool WITH_STATE>
+  __device__ __forceinline__ void predict(real dt, const ModelConst& mc) {
+    const real a = dt;
+    const real b = real(mc.c2) * (dt * dt);
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      constexpr int L1 = B::l1(i);
+      constexpr int L2 = B::l2(i);
+      static_assert(L1 < 0 || L1 > i, "links must point forward");
+      static_assert(L2 < 0 || L2 > i, "links must point forward");
+      if constexpr (L1 >= 0 && L2 >= 0) {
+        const real c1 = real(B::s1(i)) * a;
+        const real c2 = real(B::s2(i)) * b;
+        if constexpr (WITH_STATE) x[i] += c1 * x[L1] + c2 * x[L2];
+        // diagonal first: it needs the old P(l, i)
+        P[pidx(i, i)] += real(2) * (c1 * P[pidx(L1, i)] + c2 * P[pidx(L2, i)]) +
+                         c1 * c1 * P[pidx(L1, L1)] + real(2) * (c1 * c2) * P[pidx(L1, L2)] +
+                         c2 * c2 * P[pidx(L2, L2)];
+        static_for<0, n>([&](auto J) {
+          constexpr int j = J;
+          if constexpr (j != i) P[pidx(i, j)] += c1 * P[pidx(L1, j)] + c2 * P[pidx(L2, j)];
+        });
+      } else if constexpr (L1 >= 0) {
+        const real c1 = real(B::s1(i)) * a;
+        if constexpr (WITH_STATE) x[i] += c1 * x[L1];
+        P[pidx(i, i)] += real(2) * (c1 * P[pidx(L1, i)]) + c1 * c1 * P[pidx(L1, L1)];
+        static_for<0, n>([&](auto J) {
+          constexpr int j = J;
+          if constexpr (j != i) P[pidx(i, j)] += c1 * P[pidx(L1, j)];
+        });
+      }
+    });
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      P[pidx(i, i)] += real(mc.q[B::gidx(i)]) * dt;
+    });
+  }
+
+  // x += B u for control-input models (u = payload columns pz)
+  __device__ __forceinline__ void control(real dt, const ModelConst& mc, const real* u) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      if constexpr (B::cu(i) == 1) x[i] += (real(mc.c2) * (dt * dt)) * u[B::pz(i)];
+      if constexpr (B::cu(i) == 2) x[i] += dt * u[B::pz(i)];
+    });
+  }
+
+  // Scalar measurement of local state S with value z and variance r.
+  template <int S, bool WITH_STATE>
+  __device__ __forceinline__ void scalar_update(real z, real r) {
+    real row[n];
+    static_for<0, n>([&](auto J) { row[J] = P[pidx(S, J)]; });
+    const real inv = real(1) / (row[S] + r);
+    if constexpr (WITH_STATE) {
+      const real w = (z - x[S]) * inv;
+      static_for<0, n>([&](auto I) { x[I] += row[I] * w; });
+    }
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      if constexpr (i != S) {
+        const real k = row[i] * inv;
+        static_for<i, n>([&](auto J) {
+          constexpr int j = J;
+          if constexpr (j != S) P[pidx(i, j)] -= k * row[j];
+        });
+      }
+    });
+    const real shrink = r * inv;  // row S of (I - K H) P is row * r / (P_ss + r)
+    static_for<0, n>([&](auto J) { P[pidx(S, J)] = row[J] * shrink; });
+  }
+
+  // GPS event: H selects the states with gps(i) >= 0 (kf_workers.py:551-558, 694-697)
+  template <bool WITH_STATE>
+  __device__ __forceinline__ void update_gps(const ModelConst& mc, const real* u) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      if constexpr (B::gps(i) >= 0) {
+        real z = real(0);
+        if constexpr (WITH_STATE) z = u[B::gps(i)];
+        scalar_update<i, WITH_STATE>(z, real(mc.r_gps[B::gps(i)]));
+      }
+    });
+  }
+
+  // IMU event: H = I, z built from the PREDICTED state (kf_workers.py:698-706).  All of z is
+  // formed before the first scalar update touches x.
+  template <bool WITH_STATE>
+  __device__ __forceinline__ void update_imu(real dt, const ModelConst& mc, const real* u) {
+    real z[n];
+    if constexpr (WITH_STATE) {
+      static_for<0, n>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (B::zk(i) == ZK_POS) {
+          const real V = x[B::l1(i)] + u[B::pz(i)] * dt;
+          z[i] = x[i] + V * dt;
+        } else if constexpr (B::zk(i) == ZK_VEL) {
+          z[i] = x[i] + u[B::pz(i)] * dt;
+        } else if constexpr (B::zk(i) == ZK_DIRECT) {
+          z[i] = u[B::pz(i)];
+        } else {
+          z[i] = real(0);
+        }
+      });
+    }
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      if constexpr (B::zk(i) != ZK_NONE) {
+        real zi = real(0);
+        if constexpr (WITH_STATE) zi = z[i];
+        scalar_update<i, WITH_STATE>(zi, real(mc.r_imu[B::gidx(i)]));
+      }
+    });
+  }
+
+  // det P: closed form for n <= 3, LDL^T pivots otherwise.  ok is cleared on a non-positive pivot.
+  __device__ __forceinline__ real det(bool& ok) const {
+    if constexpr (n == 1) {
+      ok = ok && (P[0] > real(0));
+      return P[0];
+    } else if constexpr (n == 2) {
+      const real d = P[pidx(0, 0)] * P[pidx(1, 1)] - P[pidx(0, 1)] * P[pidx(0, 1)];
+      ok = ok && (d > real(0));
+      return d;
+    } else if constexpr (n == 3) {
+      const real a = P[pidx(0, 0)], b = P[pidx(0, 1)], c = P[pidx(0, 2)];
+      const real d = P[pidx(1, 1)], e = P[pidx(1, 2)], f = P[pidx(2, 2)];
+      const real r = a * (d * f - e * e) - b * (b * f - c * e) + c * (b * e - c * d);
+      ok = ok && (r > real(0));
+      return r;
+    } else {
+      real A[NP];
+      static_for<0, NP>([&](auto I) { A[I] = P[I]; });
+      real prod = real(1);
+      static_for<0, n>([&](auto K) {
+        constexpr int k = K;
+        const real d = A[pidx(k, k)];
+        ok = ok && (d > real(0));
+        prod *= d;
+        if constexpr (k + 1 < n) {
+          const real inv = real(1) / d;
+          static_for<k + 1, n>([&](auto I) {
+            constexpr int i = I;
+            const real l = A[pidx(k, i)] * inv;
+            static_for<i, n>([&](auto J) {
+              constexpr int j = J;
+              A[pidx(i, j)] -= l * A[pidx(k, j)];
+            });
+          });
+        }
+      });
+      return prod;
+    }
+  }
+};
+
+// --------------------------------------------------------------------------------------
+// A filter = a tuple of blocks
+// --------------------------------------------------------------------------------------
+template <typename real, bool IMU_CONTROL, class... Bs>
+struct FilterT;
+
+template <typename real, bool IMU_CONTROL>
+struct FilterT<real, IMU_CONTROL> {
+  template <class F>
+  __device__ __forceinline__ void each(F&&) {}
+  template <class F>
+  __device__ __forceinline__ void each(F&&) const {}
+};
+
+template <typename real, bool IMU_CONTROL, class B0, class... Bs>
+struct FilterT<real, IMU_CONTROL, B0, Bs...> {
+  BlockKF<B0, real> head;
+  FilterT<real, IMU_CONTROL, Bs...> tail;
+  template <class F>
+  __device__ __forceinline__ void each(F&& f) {
+    f(head);
+    tail.each(f);
+  }
+  template <class F>
+  __device__ __forceinline__ void each(F&& f) const {
+    f(head);
+    tail.each(f);
+  }
+};
+
+enum : int { EV_GPS = 0, EV_IMU = 1, EV_PREDICT_ONLY = 2 };
+
+// One filter step on every block.  `u` is the event payload (d reals).
+template <bool WITH_STATE, typename real, bool IMU_CONTROL, class... Bs>
+__device__ __forceinline__ void filter_predict(FilterT<real, IMU_CONTROL, Bs...>& f, real dt,
+                                               const ModelConst& mc, int etype, const real* u) {
+  f.each([&](auto& blk) {
+    blk.template predict<WITH_STATE>(dt, mc);
+    if constexpr (IMU_CONTROL && WITH_STATE) {
+      if (etype == EV_IMU) blk.control(dt, mc, u);
+    }
+  });
+}
+
+template <bool WITH_STATE, typename real, bool IMU_CONTROL, class... Bs>
+__device__ __forceinline__ void filter_update(FilterT<real, IMU_CONTROL, Bs...>& f, real dt,
+                                              const ModelConst& mc, int etype, const real* u) {
+  if (etype == EV_GPS) {
+    f.each([&](auto& blk) { blk.template update_gps<WITH_STATE>(mc, u); });
+  } else if (etype == EV_IMU) {
+    if constexpr (!IMU_CONTROL) {
+      f.each([&](auto& blk) { blk.template update_imu<WITH_STATE>(dt, mc, u); });
+    }
+  }
+}
+
+template <typename real, bool IMU_CONTROL, class... Bs>
+__device__ __forceinline__ double filter_det(const FilterT<real, IMU_CONTROL, Bs...>& f, bool& ok) {
+  double d = 1.0;
+  f.each([&](const auto& blk) { d *= double(blk.det(ok)); });
+  return d;
+}
+
+// --------------------------------------------------------------------------------------
+// Model registry: decoupled chain list and dense union per model id
+// --------------------------------------------------------------------------------------
+template <int MODEL_ID, bool DENSE, typename real>
+struct ModelTraits;
+
+// index of the chain that owns global state g (for the block-compatibility check)
+template <class... Bs>
+struct ChainIndex {
+  static constexpr int of(int g) {
+    int r = -1, k = 0;
+    ((r = (r < 0 && Union<Bs...>::template local_of<Bs>(g) >= 0) ? k : r, ++k), ...);
+    return r;
+  }
+};
+
+#define B200KF_DEFINE_MODEL(ID, N, D, MGPS, CTRL, ...)                         \
+  template <typename real>                                                     \
+  struct ModelTraits<ID, false, real> {                                        \
+    static constexpr int n = N, d = D, m_gps = MGPS;                           \
+    static constexpr bool imu_control = CTRL;                                  \
+    using Filter = FilterT<real, CTRL, __VA_ARGS__>;                           \
+    static constexpr int chain_of(int g) { return ChainIndex<__VA_ARGS__>::of(g); } \
+  };                                                                           \
+  template <typename real>                                                     \
+  struct ModelTraits<ID, true, real> {                                         \
+    static constexpr int n = N, d = D, m_gps = MGPS;                           \
+    static constexpr bool imu_control = CTRL;                                  \
+    using Filter = FilterT<real, CTRL, Union<__VA_ARGS__>>;                    \
+  };
+
+enum : int { MODEL_CV6 = 0, MODEL_CA8 = 1, MODEL_BIAS9 = 2, MODEL_CA15 = 3, MODEL_COUNT = 4 };
+
+B200KF_DEFINE_MODEL(MODEL_CV6, 6, 3, 3, false, CV6Chain<0>, CV6Chain<1>, CV6Chain<2>)
+B200KF_DEFINE_MODEL(MODEL_CA8, 8, 4, 2, false, CA8LinChain<0>, CA8LinChain<1>, CA8YawChain)
+B200KF_DEFINE_MODEL(MODEL_BIAS9, 9, 3, 3, true, BIAS9Chain<0>, BIAS9Chain<1>, BIAS9Chain<2>)
+B200KF_DEFINE_MODEL(MODEL_CA15, 15, 9, 3, false, CA15LinChain<0>, CA15LinChain<1>, CA15LinChain<2>,
+                    CA15AngChain<0>, CA15AngChain<1>, CA15AngChain<2>)
+
+// Running aggregate of log det P over the steps of one launch, kept in product form so the
+// hot loop needs no log: sum log d_k = log(mantissa product) + exponent sum * ln 2.
+struct LogDetAcc {
+  double mant = 1.0;
+  int expo = 0;
+  double maxdet = 0.0;
+  double last = 1.0;
+  int count = 0;
+  __device__ __forceinline__ void add(double det) {
+    last = det;
+    maxdet = fmax(maxdet, det);
+    count += 1;
+    double m = mant * det;
+    // renormalise m to [1, 2): valid for positive normal m (det > 0 is checked by the caller)
+    const int hi = __double2hiint(m);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    expo += e;
+    mant = __hiloint2double(hi - (e << 20), __double2loint(m));
+  }
+  __device__ __forceinline__ double sum_log() const {
+    return log(mant) + double(expo) * 0.6931471805599453094;
+  }
+};
+
+}  // namespace b200kf

@@ -1,0 +1,94 @@
+// kf_internal.h -- library-internal declarations shared by the translation units.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/b200kf.h"
+#include "kf_core.cuh"
+
+struct b200kf_model {
+  b200kf_model_desc desc;
+  b200kf::ModelConst mc;
+  int n, d, m_gps;
+  int device;
+  int sm_count;
+  // device arena: [0] dense-needed flag, then reduction scratch for the schedule search
+  void* arena;
+  size_t arena_bytes;
+  int tpb;  // threads per block for the filter kernels (env B200KF_TPB)
+};
+
+namespace b200kf {
+
+constexpr size_t kArenaBytes = 1 << 20;
+constexpr int kMaxSearchBlocks = 8192;
+
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define B200KF_CUDA_TRY(expr)                                   \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) return ::b200kf::cuda_fail(_e, #expr); \
+  } while (0)
+
+struct RunParams {
+  ModelConst mc;
+  long long n_filters;
+  int n_steps;
+  const uint8_t* types;
+  const double* dts;
+  const void* payload;
+  void* x;
+  void* P;
+  double* agg;
+  void* traj;
+  int traj_ncomp;
+  void* logdet;
+  uint8_t* used;
+  int* status;
+  double gate_threshold;
+  int gate_enabled;
+  int agg_continue;
+  const int* dense_flag;  // AUTO mode: run only if *dense_flag matches the kernel's mode
+};
+
+constexpr int kMaxEvents = 32;
+
+struct ScoreParams {
+  ModelConst mc;
+  int n_events;
+  unsigned char types[kMaxEvents];
+  double times[kMaxEvents];
+  double t_prev, t_end;
+  double P0[kMaxN * kMaxN];  // [n, n] row-major
+  unsigned long long first, count;
+  double threshold;
+  double* per_schedule;  // [count, 4] or null
+  void* partials;        // per-block results
+  const int* dense_flag;
+};
+
+struct ScorePartial {
+  double score;
+  unsigned long long index;
+  unsigned long long key;
+  unsigned long long n_feasible;
+  unsigned long long n_near;
+};
+
+// defined once per model id in kf_run_model.cu / kf_sched_model.cu
+template <int MODEL>
+int launch_run_m(const b200kf_model* m, const RunParams& p, unsigned flags, cudaStream_t st);
+template <int MODEL>
+int launch_score_m(const b200kf_model* m, ScoreParams p, unsigned flags, b200kf_best* best,
+                   cudaStream_t st);
+
+inline int* dense_flag(const b200kf_model* m) { return reinterpret_cast<int*>(m->arena); }
+inline void* search_scratch(const b200kf_model* m) {
+  return reinterpret_cast<char*>(m->arena) + 256;
+}
+
+}  // namespace b200kf

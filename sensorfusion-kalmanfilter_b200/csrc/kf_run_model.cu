@@ -1,0 +1,193 @@
+// kf_run_model.cu -- the batched filter-loop kernels for ONE model id (compiled once per model
+// with -DB200KF_INST_MODEL=<id> so the four models build in parallel).
+//
+// Thread <-> filter.  State and covariance stay in registers for the whole launch; the event
+// schedule (type, dt) is shared by all filters so every branch is warp-uniform; the payload is
+// read time-major ([T, d, N], filter fastest) so each warp load is one fully coalesced 256-byte
+// (f64) request, software-prefetched PF steps ahead.
+#include "kf_internal.h"
+
+#ifndef B200KF_INST_MODEL
+#error "compile with -DB200KF_INST_MODEL=<model id>"
+#endif
+
+namespace b200kf {
+
+constexpr int PF = 2;  // payload prefetch depth (steps)
+
+template <int MODEL, bool DENSE, typename real, bool FULL>
+__global__ void __launch_bounds__(256) kf_run_kernel(const RunParams p) {
+  using MT = ModelTraits<MODEL, DENSE, real>;
+  constexpr int n = MT::n;
+  constexpr int D = MT::d;
+  if (p.dense_flag != nullptr && *p.dense_flag != (DENSE ? 1 : 0)) return;
+  const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (f >= p.n_filters) return;
+  const long long N = p.n_filters;
+  const int T = p.n_steps;
+
+  typename MT::Filter flt;
+  {
+    const real* xg = static_cast<const real*>(p.x) + f * n;
+    const real* Pg = static_cast<const real*>(p.P) + f * (n * n);
+    flt.each([&](auto& b) { b.load(xg, Pg, n); });
+  }
+
+  LogDetAcc acc;
+  bool ok = true;
+
+  const real* pay = static_cast<const real*>(p.payload) + f;
+  const long long step_stride = static_cast<long long>(D) * N;
+  real ubuf[PF][D];
+#pragma unroll
+  for (int j = 0; j < PF; ++j) {
+    if (j < T) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) ubuf[j][c] = __ldcs(pay + j * step_stride + c * N);
+    }
+  }
+
+  for (int k0 = 0; k0 < T; k0 += PF) {
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int k = k0 + j;
+      if (k < T) {
+        real u[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) u[c] = ubuf[j][c];
+        if (k + PF < T) {
+          const real* src = pay + static_cast<long long>(k + PF) * step_stride;
+#pragma unroll
+          for (int c = 0; c < D; ++c) ubuf[j][c] = __ldcs(src + c * N);
+        }
+        const int ty = __ldg(p.types + k);
+        const real dt = static_cast<real>(__ldg(p.dts + k));
+
+        filter_predict<true>(flt, dt, p.mc, ty, u);
+        bool do_update = (ty != EV_PREDICT_ONLY);
+        if constexpr (FULL) {
+          if (p.gate_enabled) {  // kf_workers.py:1023-1025
+            const double dpre = filter_det(flt, ok);
+            do_update = do_update && (log(dpre) > p.gate_threshold);
+          }
+        }
+        if (do_update) filter_update<true>(flt, dt, p.mc, ty, u);
+        const double det = filter_det(flt, ok);
+        acc.add(det);
+
+        if constexpr (FULL) {
+          if (p.traj != nullptr) {
+            real* tr = static_cast<real*>(p.traj) + (static_cast<long long>(k) * p.traj_ncomp) * N + f;
+            const int nc = p.traj_ncomp;
+            flt.each([&](const auto& b) {
+              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+              static_for<0, BT::n>([&](auto I) {
+                constexpr int i = I;
+                constexpr int g = BT::gidx(i);
+                if (g < nc) __stcs(tr + static_cast<long long>(g) * N, b.x[i]);
+              });
+            });
+          }
+          if (p.logdet != nullptr)
+            __stcs(static_cast<real*>(p.logdet) + static_cast<long long>(k) * N + f,
+                   static_cast<real>(log(det)));
+          if (p.used != nullptr)
+            p.used[static_cast<long long>(k) * N + f] = do_update ? 1 : 0;
+        }
+      }
+    }
+  }
+
+  {
+    real* xg = static_cast<real*>(p.x) + f * n;
+    real* Pg = static_cast<real*>(p.P) + f * (n * n);
+    flt.each([&](const auto& b) { b.store(xg, Pg, n); });
+  }
+  if (p.agg != nullptr) {
+    double* a = p.agg + f * 4;
+    double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
+    double sm = acc.sum_log();
+    double cnt = static_cast<double>(acc.count);
+    if (p.agg_continue) {
+      mx = fmax(mx, a[0]);
+      sm += a[1];
+      cnt += a[3];
+    }
+    a[0] = mx;
+    a[1] = sm;
+    a[2] = (acc.count > 0) ? log(acc.last) : (p.agg_continue ? a[2] : 0.0);
+    a[3] = cnt;
+  }
+  if (p.status != nullptr) {
+    const int bad = ok ? 0 : 1;
+    p.status[f] = p.agg_continue ? (p.status[f] | bad) : bad;
+  }
+}
+
+// BlockKF::x / gidx are needed by the trajectory writer above
+template <int MODEL, typename real>
+__global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filters, int* flag) {
+  using MT = ModelTraits<MODEL, false, real>;
+  constexpr int n = MT::n;
+  const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (f >= n_filters) return;
+  const real* Pg = P + f * (n * n);
+  bool coupled = false;
+  static_for<0, n>([&](auto I) {
+    constexpr int i = I;
+    static_for<0, n>([&](auto J) {
+      constexpr int j = J;
+      if constexpr (MT::chain_of(i) != MT::chain_of(j)) coupled = coupled || (Pg[i * n + j] != real(0));
+    });
+  });
+  if (coupled) atomicOr(flag, 1);
+}
+
+template <int MODEL, bool DENSE, typename real>
+static cudaError_t launch_variant(const b200kf_model* m, const RunParams& p, bool full,
+                                  cudaStream_t st) {
+  const int tpb = m->tpb;
+  const long long blocks = (p.n_filters + tpb - 1) / tpb;
+  if (full)
+    kf_run_kernel<MODEL, DENSE, real, true><<<static_cast<unsigned>(blocks), tpb, 0, st>>>(p);
+  else
+    kf_run_kernel<MODEL, DENSE, real, false><<<static_cast<unsigned>(blocks), tpb, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int MODEL, typename real>
+static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, cudaStream_t st) {
+  const bool full = p.traj != nullptr || p.logdet != nullptr || p.used != nullptr || p.gate_enabled;
+  if (flags & B200KF_RUN_FORCE_DENSE) {
+    p.dense_flag = nullptr;
+    B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));
+    return B200KF_OK;
+  }
+  if (flags & B200KF_RUN_FORCE_DECOUPLED) {
+    p.dense_flag = nullptr;
+    B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
+    return B200KF_OK;
+  }
+  // AUTO: decide on the device, no host round trip.  Both kernels are enqueued; the one whose
+  // mode does not match the flag exits at once.
+  int* flag = dense_flag(m);
+  B200KF_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  const int ctpb = 128;
+  chain_compat_kernel<MODEL, real>
+      <<<static_cast<unsigned>((p.n_filters + ctpb - 1) / ctpb), ctpb, 0, st>>>(
+          static_cast<const real*>(p.P), p.n_filters, flag);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  p.dense_flag = flag;
+  B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
+  B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));
+  return B200KF_OK;
+}
+
+template <>
+int launch_run_m<B200KF_INST_MODEL>(const b200kf_model* m, const RunParams& p, unsigned flags,
+                                    cudaStream_t st) {
+  if (m->desc.precision == B200KF_F32) return launch_precision<B200KF_INST_MODEL, float>(m, p, flags, st);
+  return launch_precision<B200KF_INST_MODEL, double>(m, p, flags, st);
+}
+
+}  // namespace b200kf

@@ -1,0 +1,152 @@
+// kf_sched_model.cu -- brute-force schedule scoring for ONE model id (-DB200KF_INST_MODEL=<id>).
+//
+// Thread <-> candidate schedule (a bitmask over the <= 32 events of a window).  The covariance
+// recursion of a linear KF never reads a measurement (kf_workers.py:44,64,67,70 touch no z), so
+// the kernel carries P only: no state, no payload, no global loads at all in the hot loop -- the
+// window (types, times), P0 and the rate constants arrive as kernel parameters.  Per schedule it
+// reproduces evaluate_combo_chunk_worker's log_det trace (kf_workers.py:22-97): initial term,
+// one term per used event with gaps merged into one predict, and the end-of-window propagation;
+// the trace is reduced on the fly to (max, sum, last, n_terms).  Block- then grid-level
+// reductions give (a) argmin of the sum with lowest-index ties and (b) the reference's selection
+// rule -- first schedule in (cardinality, lexicographic) order whose max stays below the
+// threshold (:1325-1358).
+#include "kf_internal.h"
+
+#ifndef B200KF_INST_MODEL
+#error "compile with -DB200KF_INST_MODEL=<model id>"
+#endif
+
+namespace b200kf {
+
+constexpr int kScoreTpb = 128;
+
+__device__ __forceinline__ unsigned long long lex_key(unsigned long long s, int L) {
+  // Within one cardinality the lexicographically smaller index tuple has the LARGER bit-reversed
+  // mask (event 0 -> most significant bit), hence the complement.
+  const unsigned long long rev = __brevll(s) >> (64 - L);
+  const unsigned long long full = (L >= 64) ? ~0ULL : ((1ULL << L) - 1ULL);
+  return (static_cast<unsigned long long>(__popcll(s)) << 32) | (full - rev);
+}
+
+__device__ __forceinline__ void better_sum(double& sc, unsigned long long& ix, double osc,
+                                           unsigned long long oix) {
+  if (osc < sc || (osc == sc && oix < ix)) {
+    sc = osc;
+    ix = oix;
+  }
+}
+
+template <int MODEL, bool DENSE>
+__global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
+  using MT = ModelTraits<MODEL, DENSE, double>;
+  constexpr int n = MT::n;
+  if (p.dense_flag != nullptr && *p.dense_flag != (DENSE ? 1 : 0)) return;
+
+  double best_sc = INFINITY;
+  unsigned long long best_ix = ~0ULL, best_key = ~0ULL, n_feas = 0, n_near = 0;
+  const int L = p.n_events;
+  const double near_tol = 1e-9 * fmax(1.0, fabs(p.threshold));
+
+  for (unsigned long long idx = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+       idx < p.count; idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long s = p.first + idx;
+    typename MT::Filter flt;
+    flt.each([&](auto& b) { b.load_cov(p.P0, n); });
+    bool ok = true;
+    LogDetAcc acc;
+    acc.add(filter_det(flt, ok));  // log_det[0], kf_workers.py:32
+    double tcur = p.t_prev;
+    for (int i = 0; i < L; ++i) {
+      if (!((s >> i) & 1ULL)) continue;
+      const double dt = p.times[i] - tcur;  // merged gap, kf_workers.py:37
+      if (dt < 0) continue;                 // :38-40
+      const int ty = p.types[i];
+      filter_predict<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+      filter_update<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+      tcur = p.times[i];
+      acc.add(filter_det(flt, ok));
+    }
+    if (tcur < p.t_end - 1e-8) {  // kf_workers.py:74-82
+      const double dt = p.t_end - tcur;
+      filter_predict<false>(flt, dt, p.mc, EV_PREDICT_ONLY, static_cast<const double*>(nullptr));
+      acc.add(filter_det(flt, ok));
+    }
+    const double mx = ok ? log(acc.maxdet) : NAN;
+    const double sm = ok ? acc.sum_log() : NAN;
+    if (p.per_schedule != nullptr) {
+      double* o = p.per_schedule + idx * 4;
+      o[0] = mx;
+      o[1] = sm;
+      o[2] = ok ? log(acc.last) : NAN;
+      o[3] = static_cast<double>(acc.count);
+    }
+    if (s != 0 && ok) {  // the reference never enumerates the empty set (:1325)
+      better_sum(best_sc, best_ix, sm, s);
+      if (mx < p.threshold) {  // :1353
+        n_feas += 1;
+        const unsigned long long key = lex_key(s, L);
+        best_key = key < best_key ? key : best_key;
+      }
+      if (fabs(mx - p.threshold) <= near_tol) n_near += 1;
+    }
+  }
+
+  // block reduction
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double osc = __shfl_down_sync(0xffffffffu, best_sc, off);
+    const unsigned long long oix = __shfl_down_sync(0xffffffffu, best_ix, off);
+    better_sum(best_sc, best_ix, osc, oix);
+    const unsigned long long ok2 = __shfl_down_sync(0xffffffffu, best_key, off);
+    best_key = ok2 < best_key ? ok2 : best_key;
+    n_feas += __shfl_down_sync(0xffffffffu, n_feas, off);
+    n_near += __shfl_down_sync(0xffffffffu, n_near, off);
+  }
+  __shared__ ScorePartial sh[kScoreTpb / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = ScorePartial{best_sc, best_ix, best_key, n_feas, n_near};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ScorePartial r = sh[0];
+    for (int w = 1; w < kScoreTpb / 32; ++w) {
+      better_sum(r.score, r.index, sh[w].score, sh[w].index);
+      r.key = sh[w].key < r.key ? sh[w].key : r.key;
+      r.n_feasible += sh[w].n_feasible;
+      r.n_near += sh[w].n_near;
+    }
+    static_cast<ScorePartial*>(p.partials)[blockIdx.x] = r;
+  }
+}
+
+template <>
+int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsigned flags,
+                                      b200kf_best* best, cudaStream_t st) {
+  (void)best;
+  unsigned long long blocks = (p.count + kScoreTpb - 1) / kScoreTpb;
+  if (blocks > static_cast<unsigned long long>(kMaxSearchBlocks)) blocks = kMaxSearchBlocks;
+  if (blocks == 0) blocks = 1;
+  // every partial slot the finaliser reads is written by exactly one of the kernels below
+  if (flags & B200KF_RUN_FORCE_DENSE) {
+    p.dense_flag = nullptr;
+    score_kernel<B200KF_INST_MODEL, true><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  } else if (flags & B200KF_RUN_FORCE_DECOUPLED) {
+    p.dense_flag = nullptr;
+    score_kernel<B200KF_INST_MODEL, false><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  } else {
+    // AUTO: P0 is a host matrix, so the chain-compatibility decision is made on the host
+    using MT = ModelTraits<B200KF_INST_MODEL, false, double>;
+    bool coupled = false;
+    for (int i = 0; i < MT::n; ++i)
+      for (int j = 0; j < MT::n; ++j)
+        if (MT::chain_of(i) != MT::chain_of(j) && p.P0[i * MT::n + j] != 0.0) coupled = true;
+    p.dense_flag = nullptr;
+    if (coupled)
+      score_kernel<B200KF_INST_MODEL, true><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+    else
+      score_kernel<B200KF_INST_MODEL, false><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  }
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return static_cast<int>(blocks);
+}
+
+}  // namespace b200kf

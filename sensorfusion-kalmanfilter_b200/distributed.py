@@ -1,0 +1,96 @@
+"""Multi-GPU plumbing: one process per GPU, contiguous sharding, one tiny final collective.
+
+The path shards naturally: filters are independent, and so are candidate
+schedules, so rank r owns a contiguous index range and nothing is exchanged during compute.  The
+reference's own "parallelism" is a `multiprocessing.Pool(30)` whose chunks are awaited one by one
+(kf_workers.py:1333-1346).  The only collective here is the end-of-search all-gather of each
+rank's `b200kf_best` (48 bytes) followed by the same deterministic reduce on every rank -- an
+all-reduce(MIN) could not carry the index nor define the tie order.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_NONE = None
+
+
+def shard_range(total: int, world_size: int, rank: int):
+    """Contiguous [first, first+count) of `total` items for `rank`; sizes differ by at most 1."""
+    base, rem = divmod(int(total), int(world_size))
+    first = rank * base + min(rank, rem)
+    count = base + (1 if rank < rem else 0)
+    return first, count
+
+
+def merge_best(parts):
+    """Deterministic reduce of per-shard search results (dicts from Engine.score_schedules):
+    min sum-score with lowest-index ties; min enumeration key for the first feasible schedule."""
+    out = {"argmin_sum_score": float("inf"), "argmin_sum_index": None, "first_feasible_key": (1 << 64) - 1,
+           "first_feasible_index": None, "n_feasible": 0, "n_near_threshold": 0}
+    for b in parts:
+        if b["argmin_sum_index"] is not None:
+            s, i = b["argmin_sum_score"], b["argmin_sum_index"]
+            if (out["argmin_sum_index"] is None or s < out["argmin_sum_score"]
+                    or (s == out["argmin_sum_score"] and i < out["argmin_sum_index"])):
+                out["argmin_sum_score"], out["argmin_sum_index"] = s, i
+        if b["first_feasible_index"] is not None and b["first_feasible_key"] < out["first_feasible_key"]:
+            out["first_feasible_key"] = b["first_feasible_key"]
+            out["first_feasible_index"] = b["first_feasible_index"]
+        out["n_feasible"] += b["n_feasible"]
+        out["n_near_threshold"] += b["n_near_threshold"]
+    return out
+
+
+_FIELDS = ("argmin_sum_score", "argmin_sum_index", "first_feasible_key", "first_feasible_index",
+           "n_feasible", "n_near_threshold")
+
+
+def _pack(b):
+    none = (1 << 64) - 1
+    ints = np.array([none if b["argmin_sum_index"] is None else b["argmin_sum_index"],
+                     b["first_feasible_key"],
+                     none if b["first_feasible_index"] is None else b["first_feasible_index"],
+                     b["n_feasible"], b["n_near_threshold"]], dtype=np.uint64)
+    return np.concatenate([np.array([b["argmin_sum_score"]], dtype=np.float64).view(np.uint64), ints])
+
+
+def _unpack(row):
+    none = (1 << 64) - 1
+    row = np.asarray(row, dtype=np.uint64)
+    score = float(row[:1].view(np.float64)[0])
+    idx, key, ffi, nf, nn = (int(v) for v in row[1:])
+    return {"argmin_sum_score": score, "argmin_sum_index": None if idx == none else idx,
+            "first_feasible_key": key, "first_feasible_index": None if key == none else ffi,
+            "n_feasible": nf, "n_near_threshold": nn}
+
+
+def allgather_best(best, group=None, device=None):
+    """All-gather every rank's result (6 x 8 bytes) and reduce identically on all ranks.
+    Works on NCCL (device tensors) and gloo (CPU tensors, used by the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return merge_best([best])
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cpu")
+    if backend == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    mine = torch.from_numpy(_pack(best).view(np.int64).copy()).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    parts = [_unpack(g.cpu().numpy().view(np.uint64)) for g in gathered]
+    return merge_best(parts)
+
+
+def search_sharded(engine, types, times, t_prev, t_end, P0, threshold, group=None, **kw):
+    """Brute-force search of all 2^L subset schedules sharded over the ranks of `group`."""
+    import torch.distributed as dist
+    L = len(types)
+    rank, world = 0, 1
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first, count = shard_range(1 << L, world, rank)
+    best, _ = engine.score_schedules(types, times, t_prev, t_end, P0, first=first, count=count,
+                                     threshold=threshold, **kw)
+    return allgather_best(best, group=group, device=engine.device)

@@ -1,0 +1,230 @@
+"""Batched entry points over the C ABI (the calls the reference never had: many filters, many
+schedules at once).  PyTorch is used only to own device memory and streams; every pointer handed
+to libb200kf.so is a `tensor.data_ptr()`.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_int32, c_uint8, c_void_p
+
+import numpy as np
+
+from . import _lib
+from .models import ModelSpec, default_spec
+
+_MODES = {"auto": _lib.RUN_AUTO, "dense": _lib.RUN_FORCE_DENSE, "decoupled": _lib.RUN_FORCE_DECOUPLED}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available() or _lib.device_count() == 0:
+        raise _lib.B200KFError(_lib.ERR_NO_DEVICE, "no CUDA device visible: b200kf has no CPU fallback")
+    return torch
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+class Engine:
+    """One model instance on one device (wraps b200kf_model_create/_destroy)."""
+
+    def __init__(self, spec: ModelSpec | str = "CA15", precision: str | None = None, device=None):
+        if isinstance(spec, str):
+            spec = default_spec(spec, precision or "f64")
+        elif precision is not None and precision != spec.precision:
+            spec = ModelSpec(spec.name, precision, spec.q, spec.r_gps, spec.r_imu, spec.accel_coef)
+        self.spec = spec
+        self.lib = _lib.load()
+        torch = _require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.real = torch.float32 if spec.precision == "f32" else torch.float64
+        self._h = c_void_p(0)
+        with torch.cuda.device(self.device):
+            desc = spec.to_desc()
+            _lib.check(self.lib.b200kf_model_create(byref(desc), byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.b200kf_model_destroy(self._h)
+            self._h = c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, a, dtype):
+        torch = _torch()
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    def _stream(self, stream):
+        torch = _torch()
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        return c_void_p(s.cuda_stream)
+
+    # ------------------------------------------------------------------ filter loop
+    def run_batch(self, types, dts, payload, x, P, *, want_agg=True, traj_ncomp=0, want_logdet=False,
+                  want_used=False, gate_threshold=None, mode="auto", agg=None, stream=None,
+                  inplace=False):
+        """Run N filters over a shared schedule (b200kf_run_batch).
+
+        types [T] u8, dts [T] f64, payload [T, d, N], x [N, n], P [N, n, n]; numpy arrays or torch
+        tensors.  Returns a dict of torch CUDA tensors: x, P, agg [N,4], traj [T,traj_ncomp,N],
+        logdet [T,N], used [T,N], status [N].  `agg` continues running aggregates of a previous
+        chunk.  With inplace=True torch inputs x/P on the right device/dtype are updated in place."""
+        torch = _torch()
+        sp = self.spec
+        types_d = self._dev(types, torch.uint8)
+        dts_d = self._dev(dts, torch.float64)
+        pay_d = self._dev(payload, self.real)
+        T = int(types_d.numel())
+        x_d = self._dev(x, self.real)
+        P_d = self._dev(P, self.real)
+        if not inplace:
+            if isinstance(x, torch.Tensor) and x_d.data_ptr() == x.data_ptr():
+                x_d = x_d.clone()
+            if isinstance(P, torch.Tensor) and P_d.data_ptr() == P.data_ptr():
+                P_d = P_d.clone()
+        N = int(x_d.shape[0])
+        if tuple(x_d.shape) != (N, sp.n) or tuple(P_d.shape) != (N, sp.n, sp.n):
+            raise ValueError(f"x must be [N,{sp.n}] and P [N,{sp.n},{sp.n}]")
+        if T and tuple(pay_d.shape) != (T, sp.d, N):
+            raise ValueError(f"payload must be [T={T}, d={sp.d}, N={N}], got {tuple(pay_d.shape)}")
+        if dts_d.numel() != T:
+            raise ValueError("types and dts must have the same length")
+        flags = _MODES[mode]
+        agg_d = None
+        if agg is not None:
+            agg_d = self._dev(agg, torch.float64)
+            flags |= _lib.RUN_AGG_CONTINUE
+        elif want_agg:
+            agg_d = torch.empty((N, 4), dtype=torch.float64, device=self.device)
+        traj_d = torch.empty((T, traj_ncomp, N), dtype=self.real, device=self.device) if traj_ncomp else None
+        ld_d = torch.empty((T, N), dtype=self.real, device=self.device) if want_logdet else None
+        used_d = torch.empty((T, N), dtype=torch.uint8, device=self.device) if want_used else None
+        status_d = torch.zeros((N,), dtype=torch.int32, device=self.device)
+        gate = float("nan") if gate_threshold is None else float(gate_threshold)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_run_batch(
+                self._h, N, T, _ptr(types_d), _ptr(dts_d), _ptr(pay_d), _ptr(x_d), _ptr(P_d), _ptr(agg_d),
+                _ptr(traj_d), int(traj_ncomp), _ptr(ld_d), _ptr(used_d), _ptr(status_d), gate, flags,
+                self._stream(stream)))
+        return {"x": x_d, "P": P_d, "agg": agg_d, "traj": traj_d, "logdet": ld_d, "used": used_d,
+                "status": status_d}
+
+    def run_batch_host(self, types, dts, payload, x, P, *, chunk_steps=0, mode="auto"):
+        """Host-buffer path (b200kf_run_batch_host): numpy (or pinned torch CPU) arrays in, numpy
+        out; payload is streamed to the device in time chunks overlapped with the kernels."""
+        torch = _require_cuda()
+        sp = self.spec
+        npreal = np.float32 if sp.precision == "f32" else np.float64
+
+        def host(a, dt):
+            if isinstance(a, torch.Tensor):
+                assert a.device.type == "cpu" and a.is_contiguous()
+                return a, a.data_ptr()
+            arr = np.ascontiguousarray(a, dtype=dt)
+            return arr, arr.ctypes.data
+
+        types_h, types_p = host(types, np.uint8)
+        dts_h, dts_p = host(dts, np.float64)
+        pay_h, pay_p = host(payload, npreal)
+        x_h = np.array(x, dtype=npreal, order="C", copy=True)
+        P_h = np.array(P, dtype=npreal, order="C", copy=True)
+        N = x_h.shape[0]
+        T = int(np.prod(types_h.shape))
+        agg_h = np.zeros((N, 4), dtype=np.float64)
+        status_h = np.zeros((N,), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_run_batch_host(
+                self._h, N, T, c_void_p(types_p), c_void_p(dts_p), c_void_p(pay_p),
+                c_void_p(x_h.ctypes.data), c_void_p(P_h.ctypes.data), c_void_p(agg_h.ctypes.data),
+                c_void_p(status_h.ctypes.data), int(chunk_steps), _MODES[mode]))
+        return {"x": x_h, "P": P_h, "agg": agg_h, "status": status_h}
+
+    # ------------------------------------------------------------------ schedule search
+    def score_schedules(self, types, times, t_prev, t_end, P0, *, first=0, count=None,
+                        threshold=float("inf"), want_per_schedule=False, mode="auto", stream=None):
+        """Score the subset schedules [first, first+count) of a window (b200kf_score_schedules).
+        Returns (best: dict, per_schedule: torch [count,4] or None)."""
+        torch = _torch()
+        types = np.ascontiguousarray(types, dtype=np.uint8)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        P0 = np.ascontiguousarray(P0, dtype=np.float64)
+        L = int(types.shape[0])
+        if count is None:
+            count = (1 << L) - first
+        per = torch.empty((count, 4), dtype=torch.float64, device=self.device) if want_per_schedule else None
+        best_d = torch.zeros((ctypes.sizeof(_lib.Best),), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_score_schedules(
+                self._h, L, types.ctypes.data_as(POINTER(c_uint8)), times.ctypes.data_as(POINTER(c_double)),
+                float(t_prev), float(t_end), P0.ctypes.data_as(POINTER(c_double)), int(first), int(count),
+                float(threshold), _ptr(per), _ptr(best_d), _MODES[mode], self._stream(stream)))
+        raw = bytes(best_d.cpu().numpy().tobytes())
+        b = _lib.Best.from_buffer_copy(raw)
+        none = (1 << 64) - 1
+        best = {
+            "argmin_sum_score": b.argmin_sum_score,
+            "argmin_sum_index": None if b.argmin_sum_index == none else int(b.argmin_sum_index),
+            "first_feasible_key": int(b.first_feasible_key),
+            "first_feasible_index": None if b.first_feasible_key == none else int(b.first_feasible_index),
+            "n_feasible": int(b.n_feasible),
+            "n_near_threshold": int(b.n_near_threshold),
+        }
+        return best, per
+
+
+def cov_update(Sigma, rows, H, R, device=None, stream=None):
+    """Batched Scheduler.cov_matrix (b200kf_cov_update).  Sigma [B, n, n] (numpy or torch), rows:
+    0-based selected rows of (H, R).  Returns (Sigma_post [B,n,n], trace [B]) torch CUDA f64."""
+    torch = _require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    S = Sigma if isinstance(Sigma, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(Sigma))
+    S = S.to(device=dev, dtype=torch.float64).contiguous()
+    B, n = int(S.shape[0]), int(S.shape[-1])
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    R = np.ascontiguousarray(R, dtype=np.float64)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    post = torch.empty_like(S)
+    tr = torch.empty((B,), dtype=torch.float64, device=dev)
+    s = torch.cuda.current_stream(dev) if stream is None else stream
+    with torch.cuda.device(dev):
+        _lib.check(lib.b200kf_cov_update(
+            n, int(H.shape[0]), int(rows.shape[0]), rows.ctypes.data_as(POINTER(c_int32)),
+            H.ctypes.data_as(POINTER(c_double)), R.ctypes.data_as(POINTER(c_double)), B, _ptr(S),
+            _ptr(post), _ptr(tr), c_void_p(s.cuda_stream)))
+    return post, tr
+
+
+def fill_payload(engine: Engine, types_dev, n_filters, seed=1234, stream=None):
+    """Device-side synthetic payload [T, d, N] of BASELINE config 3/5 (b200kf_fill_payload)."""
+    torch = _torch()
+    T = int(types_dev.numel())
+    out = torch.empty((T, engine.spec.d, n_filters), dtype=engine.real, device=engine.device)
+    with torch.cuda.device(engine.device):
+        _lib.check(engine.lib.b200kf_fill_payload(engine._h, int(n_filters), T, _ptr(types_dev), int(seed),
+                                                  _ptr(out), engine._stream(stream)))
+    return out
+
+
+def probe_fma_peak(precision="f64") -> float:
+    """Measured FMA peak of the current device in TFLOP/s (b200kf_probe_fma_peak)."""
+    _require_cuda()
+    lib = _lib.load()
+    v = c_double(0.0)
+    _lib.check(lib.b200kf_probe_fma_peak(_lib.F32 if precision == "f32" else _lib.F64, byref(v)))
+    return v.value

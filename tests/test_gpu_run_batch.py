@@ -1,0 +1,171 @@
+"""GPU parity of b200kf_run_batch (through the C ABI) against the numpy oracle on identical seeded
+inputs.  Tolerances are BASELINE.json's: FP64 x, P within 1e-9 relative, log det within
+1e-9*max(1,|logdet|); FP32 mode 1e-4."""
+import numpy as np
+import pytest
+
+from oracle import kf_oracle as ko
+from sensorfusion_kalmanfilter_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-9
+RTOL32 = 1e-4
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def make_case(name, N, T, seed, dense_P0=False):
+    m = ko.get_model(name)
+    rng = np.random.default_rng(seed)
+    types, dts = synth.gps_imu_schedule(T, gps_every=7, dt=0.005)
+    dts = dts * (1.0 + 0.3 * rng.random(T))
+    dts[0] = 0.0
+    payload = synth.make_payload(m.d, types, N, seed=seed, m_gps=m.m_gps)
+    x0 = rng.normal(0, 1.0, (N, m.n))
+    P0 = np.repeat(m.P0()[None], N, axis=0)
+    if dense_P0:
+        A = rng.normal(size=(N, m.n, m.n))
+        P0 = A @ np.swapaxes(A, 1, 2) + 5.0 * np.eye(m.n)
+    return m, types, dts, payload, x0, P0
+
+
+@pytest.mark.parametrize("name", ["CV6", "CA8", "BIAS9", "CA15"])
+@pytest.mark.parametrize("mode", ["decoupled", "dense", "auto"])
+def test_run_batch_f64_matches_oracle(name, mode):
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 70, 160
+    m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=3)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0)
+    eng = Engine(name)
+    out = eng.run_batch(types, dts, payload, x0, P0, traj_ncomp=m.n, want_logdet=True, mode=mode)
+    assert int(out["status"].sum()) == 0
+    assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
+    assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
+    assert rel(out["traj"].cpu().numpy(), ref["traj"]) < RTOL64
+    ld = out["logdet"].cpu().numpy()
+    assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < RTOL64
+    agg = out["agg"].cpu().numpy()
+    assert np.max(np.abs(agg[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
+    assert np.all(agg[:, 3] == T)
+    # aggregate-only launch (the throughput path) gives the same final state and aggregates
+    out2 = eng.run_batch(types, dts, payload, x0, P0, mode=mode)
+    np.testing.assert_allclose(out2["x"].cpu().numpy(), out["x"].cpu().numpy(), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(out2["agg"].cpu().numpy(), agg, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["CV6", "CA15", "BIAS9"])
+def test_dense_P0_uses_dense_kernel_and_matches(name):
+    """An arbitrary dense initial covariance must take the dense path in auto mode."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 40, 90
+    m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=9, dense_P0=True)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0)
+    eng = Engine(name)
+    out = eng.run_batch(types, dts, payload, x0, P0, want_logdet=True, mode="auto")
+    assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
+    assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
+    ld = out["logdet"].cpu().numpy()
+    assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < RTOL64
+    # one coupled filter among block-diagonal ones still forces the dense path for the launch
+    P1 = np.repeat(m.P0()[None], N, axis=0)
+    P1[N // 2] = P0[N // 2]
+    ref1 = ko.run_batch(m, types, dts, payload, x0, P1)
+    out1 = eng.run_batch(types, dts, payload, x0, P1, mode="auto")
+    assert rel(out1["P"].cpu().numpy(), ref1["P"]) < RTOL64
+
+
+@pytest.mark.parametrize("name", ["CV6", "BIAS9", "CA15"])
+def test_run_batch_f32_mode(name):
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 64, 300
+    m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=5)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0)
+    eng = Engine(name, precision="f32")
+    out = eng.run_batch(types, dts, payload, x0, P0, want_logdet=True)
+    assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL32
+    assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL32
+    ld = out["logdet"].cpu().numpy()
+    assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < RTOL32
+
+
+def test_chunked_launches_continue_state_and_aggregates():
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 33, 240
+    m, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=7)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0)
+    eng = Engine("CV6")
+    x, P, agg = x0, P0, None
+    for k0 in range(0, T, 100):
+        sl = slice(k0, min(T, k0 + 100))
+        out = eng.run_batch(types[sl], dts[sl], payload[sl], x, P, agg=agg)
+        x, P, agg = out["x"], out["P"], out["agg"]
+    assert rel(x.cpu().numpy(), ref["x"]) < RTOL64
+    assert rel(P.cpu().numpy(), ref["P"]) < RTOL64
+    a = agg.cpu().numpy()
+    assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
+    assert np.all(a[:, 3] == T)
+
+
+def test_gate_and_predict_only():
+    """Adaptive gate (kf_workers.py:1023-1025) and predict-only events (:1060-1159)."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 48, 120
+    m, types, dts, payload, x0, P0 = make_case("CA15", N, T, seed=13)
+    base = ko.run_batch(m, types, dts, payload, x0, P0)
+    thr = float(np.median(base["logdet"][20:])) + 2.0
+    ref = ko.run_batch(m, types, dts, payload, x0, P0, gate_threshold=thr)
+    eng = Engine("CA15")
+    out = eng.run_batch(types, dts, payload, x0, P0, gate_threshold=thr, want_used=True, want_logdet=True)
+    used = out["used"].cpu().numpy().astype(bool)
+    # decisions may only differ where the predicted log det is within rounding of the threshold
+    assert (used != ref["used"]).mean() < 1e-3
+    if np.array_equal(used, ref["used"]):
+        assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
+        assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
+    assert 0.05 < used.mean() < 0.95
+    types2 = np.full(T, 2, dtype=np.uint8)
+    xs, Ps = x0.copy(), P0.copy()
+    for k in range(T):
+        xs, Ps = ko.predict(m, xs, Ps, float(dts[k]))
+    out2 = eng.run_batch(types2, dts, payload, x0, P0)
+    assert rel(out2["x"].cpu().numpy(), xs) < RTOL64
+    assert rel(out2["P"].cpu().numpy(), Ps) < RTOL64
+
+
+def test_host_buffer_path_matches_device_path():
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 257, 500
+    m, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=21)
+    eng = Engine("CV6")
+    dev = eng.run_batch(types, dts, payload, x0, P0)
+    host = eng.run_batch_host(types, dts, payload, x0, P0, chunk_steps=64)
+    np.testing.assert_allclose(host["x"], dev["x"].cpu().numpy(), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(host["P"], dev["P"].cpu().numpy(), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(host["agg"], dev["agg"].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    assert host["status"].sum() == 0
+
+
+def test_ragged_and_empty_inputs():
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    eng = Engine("CV6")
+    m = ko.get_model("CV6")
+    # N = 1 filter, T = 1 step
+    mm, types, dts, payload, x0, P0 = make_case("CV6", 1, 1, seed=2)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0)
+    out = eng.run_batch(types, dts, payload, x0, P0)
+    assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
+    # T = 0: state passes through unchanged
+    out0 = eng.run_batch(np.zeros(0, np.uint8), np.zeros(0), np.zeros((0, 3, 1)), x0, P0)
+    np.testing.assert_array_equal(out0["x"].cpu().numpy(), x0)
+    np.testing.assert_allclose(out0["P"].cpu().numpy(), P0)
+    # non-multiple-of-block filter count
+    mm, types, dts, payload, x0, P0 = make_case("CV6", 131, 37, seed=4)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0)
+    out = eng.run_batch(types, dts, payload, x0, P0)
+    assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
+    with pytest.raises(ValueError):
+        eng.run_batch(types, dts, payload[:, :2], x0, P0)

@@ -1,0 +1,126 @@
+"""GPU parity of b200kf_score_schedules / b200kf_cov_update against the golden vectors produced by
+the unmodified reference (tests/golden/ca15_bruteforce.npz, scheduler.npz) and against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import kf_oracle as ko
+from oracle.make_golden import arrays_to_events
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def brute(golden):
+    g = golden("ca15_bruteforce.npz")
+    g["events"] = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    return g
+
+
+def window_arrays(g, L):
+    w0 = int(g["w0"])
+    ev = g["events"][w0:w0 + L]
+    types = np.array([0 if e[1] == "GPS" else 1 for e in ev], dtype=np.uint8)
+    times = np.array([e[2] for e in ev], dtype=np.float64)
+    return types, times
+
+
+@pytest.mark.parametrize("mode", ["auto", "dense", "decoupled"])
+def test_all_subsets_match_reference_traces(brute, mode):
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    L = int(brute["L"])
+    types, times = window_arrays(brute, L)
+    eng = Engine("CA15")
+    best, per = eng.score_schedules(types, times, brute["init_state"][0], float(brute["t_end"]), brute["P0"],
+                                    first=0, count=1 << L, threshold=0.0, want_per_schedule=True, mode=mode)
+    per = per.cpu().numpy()
+    tr = brute["traces"]
+    masks = brute["masks"].astype(np.int64)
+    ref_max = np.nanmax(tr, axis=1)
+    ref_sum = np.nansum(tr, axis=1)
+    ref_cnt = np.sum(~np.isnan(tr), axis=1)
+    ref_last = np.array([row[~np.isnan(row)][-1] for row in tr])
+    got = per[masks]
+    assert np.max(np.abs(got[:, 0] - ref_max) / np.maximum(1, np.abs(ref_max))) < 1e-9
+    assert np.max(np.abs(got[:, 1] - ref_sum) / np.maximum(1, np.abs(ref_sum))) < 1e-9
+    assert np.max(np.abs(got[:, 2] - ref_last) / np.maximum(1, np.abs(ref_last))) < 1e-9
+    np.testing.assert_array_equal(got[:, 3], ref_cnt)
+    # argmin of the sum, ties -> lowest index (bit-exact index)
+    order = np.lexsort((masks, ref_sum))
+    assert best["argmin_sum_index"] == int(masks[order[0]])
+
+
+def test_driver_selection_bit_exact(brute):
+    """First feasible schedule in the reference's (cardinality, lexicographic) order."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    Ld = int(brute["drv_L"])
+    types, times = window_arrays(brute, Ld)
+    eng = Engine("CA15")
+    for thr, mask in zip(brute["drv_thr"], brute["drv_mask"]):
+        best, _ = eng.score_schedules(types, times, brute["init_state"][0], float(times[-1]), brute["P0"],
+                                      threshold=float(thr))
+        if int(mask) < 0:
+            assert best["first_feasible_index"] is None and best["n_feasible"] == 0
+        else:
+            assert best["first_feasible_index"] == int(mask)
+    best, _ = eng.score_schedules(types, times, brute["init_state"][0], float(times[-1]), brute["P0"],
+                                  threshold=float(brute["drv_infeasible_thr"]))
+    assert best["first_feasible_index"] is None
+
+
+def test_sharded_ranges_reduce_to_the_same_answer(brute):
+    """Index-range sharding (what each GPU rank does) + the host reduce equals one full search."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    from sensorfusion_kalmanfilter_b200.distributed import merge_best, shard_range
+    L = int(brute["L"])
+    types, times = window_arrays(brute, L)
+    eng = Engine("CA15")
+    maxes = np.nanmax(brute["traces"], axis=1)
+    thr = float(np.quantile(maxes, 0.4))
+    args = (types, times, brute["init_state"][0], float(brute["t_end"]), brute["P0"])
+    full, _ = eng.score_schedules(*args, threshold=thr)
+    parts = []
+    for r in range(5):
+        first, count = shard_range(1 << L, 5, r)
+        b, _ = eng.score_schedules(*args, first=first, count=count, threshold=thr)
+        parts.append(b)
+    merged = merge_best(parts)
+    for k in ("argmin_sum_index", "first_feasible_index", "n_feasible"):
+        assert merged[k] == full[k]
+    assert merged["argmin_sum_score"] == full["argmin_sum_score"]
+
+
+@pytest.mark.parametrize("name", ["CV6", "BIAS9", "CA8"])
+def test_other_models_match_oracle(name):
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    m = ko.get_model(name)
+    rng = np.random.default_rng(3)
+    L = 9
+    types = (rng.random(L) < 0.7).astype(np.uint8)
+    times = 100.0 + np.cumsum(0.004 + 0.004 * rng.random(L))
+    A = rng.normal(size=(m.n, m.n))
+    P0 = A @ A.T + np.eye(m.n) if name != "CA8" else m.P0()
+    eng = Engine(name)
+    best, per = eng.score_schedules(types, times, 99.99, float(times[-1]) + 0.01, P0, want_per_schedule=True)
+    per = per.cpu().numpy()
+    sums = []
+    for s in range(1 << L):
+        tr = ko.schedule_trace(m, types, times, s, P0, 99.99, float(times[-1]) + 0.01)
+        assert abs(per[s, 0] - max(tr)) < 1e-9 * max(1, abs(max(tr)))
+        assert abs(per[s, 1] - sum(tr)) < 1e-9 * max(1, abs(sum(tr)))
+        assert per[s, 3] == len(tr)
+        sums.append(sum(tr))
+    assert best["argmin_sum_index"] == 1 + int(np.argmin(sums[1:]))
+
+
+def test_cov_update_matches_reference_scheduler(golden):
+    from sensorfusion_kalmanfilter_b200.engine import cov_update
+    g = golden("scheduler.npz")
+    m = ko.get_model("CA15")
+    S = g["Sigma"]
+    for rows, H, R, key in (([0], m.H_gps(), m.R_gps(), "post_gps1"), ([0, 1, 2], m.H_gps(), m.R_gps(), "post_gps3"),
+                            ([0], m.H_imu(), m.R_imu(), "post_imu1"),
+                            (list(range(15)), m.H_imu(), m.R_imu(), "post_imu_all")):
+        post, tr = cov_update(S, rows, H, R)
+        ref = g[key]
+        assert np.max(np.abs(post.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-9
+        np.testing.assert_allclose(tr.cpu().numpy(), np.trace(ref, axis1=1, axis2=2), rtol=1e-9)
