@@ -37,7 +37,7 @@ UNIT = "filter-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="CV6")
@@ -129,7 +129,9 @@ def run_reference_arm(a):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms; stop(t0, t1) keeps the samples whose
+    timestamp lies inside the timed region [t0, t1] (host epoch seconds)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -140,38 +142,48 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.5)  # let it produce its first samples before the timed region starts
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons, pw = [], [], set(), []
+        rows = []
         for ln in out.strip().splitlines():
-            f = [s.strip() for s in ln.split(",")]
+            f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                pw.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        scope = "timed region"
+        if not inside:  # region shorter than the sampling period: use the busiest samples around it
+            inside = [r for r in rows if t0 - 0.25 <= r[0] <= t1 + 0.05]
+            scope = "timed region +-0.25 s (region shorter than the sampling period)"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        reasons = set()
+        for r in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "power_w_max": float(max(r[3] for r in inside)), "samples": len(inside), "scope": scope,
+                "reasons": sorted(reasons)}
 
 
 def load_peaks():
@@ -226,13 +238,15 @@ def run_gpu_arm(a):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.time()
     e0.record()
     for _ in range(a.steps):
         one_step(a.mode)
     e1.record()
     barrier()
+    w1 = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -137,6 +137,10 @@ int b200kf_run_batch_host(const b200kf_model* model, int64_t n_filters, int64_t 
  *
  *   types, times  HOST [n_events]   event types and float64 epoch times of the window
  *   P0            HOST f64 [n, n]   covariance at t_prev
+ *   initial_logdet  NaN: term 0 (log det P0, :32) is computed on the device.  Otherwise the
+ *                 caller's value is used verbatim for term 0 of every schedule -- the reference
+ *                 compares max(log_det) < threshold strictly (:1353) and a threshold derived from
+ *                 slogdet(P0) itself ties exactly with it
  *   per_schedule  DEVICE f64 [count, 4] nullable: max, sum, last of the log-det trace (the max
  *                                   and sum include the initial and the end-propagation terms,
  *                                   :32, :81-82, :1353) and the number of terms
@@ -144,8 +148,29 @@ int b200kf_run_batch_host(const b200kf_model* model, int64_t n_filters, int64_t 
  */
 int b200kf_score_schedules(const b200kf_model* model, int32_t n_events, const uint8_t* types,
                            const double* times, double t_prev, double t_end, const double* P0,
-                           uint64_t first, uint64_t count, double threshold, double* per_schedule,
-                           b200kf_best* best, uint32_t flags, void* stream);
+                           uint64_t first, uint64_t count, double threshold, double initial_logdet,
+                           double* per_schedule, b200kf_best* best, uint32_t flags, void* stream);
+
+/* The brute-force worker WITH state: replaces evaluate_combo_chunk_worker (kf_workers.py:22-97)
+ * for n_schedules combos that are subsets of one shared window of n_events <= 64 time-ordered
+ * events.  Schedule f uses event i iff bit i of masks[f] is set.  Float64 only.
+ *
+ *   types, times   HOST [L]          payload  HOST f64 [L, d] (row layout as b200kf_run_batch)
+ *   x0             HOST f64 [n]      P0       HOST f64 [n, n]
+ *   masks          DEVICE u64 [N]
+ *   x_final        DEVICE f64 [N, n]           state after the last term (:86)
+ *   P_final        DEVICE f64 [N, n, n]        nullable
+ *   traj           DEVICE f64 [N, L+2, 1+traj_ncomp] nullable; row r = (t, x[0:traj_ncomp]) of
+ *                                              term r: initial, one per used event, end (:31,68,80)
+ *   logdet         DEVICE f64 [N, L+2]         nullable; log det P of term r (:32,70-71,81-82)
+ *   n_terms        DEVICE i32 [N]              nullable; rows written (negative: a non-positive
+ *                                              determinant was seen)
+ */
+int b200kf_run_masked(const b200kf_model* model, int32_t n_events, const uint8_t* types,
+                      const double* times, const double* payload, double t_prev, double t_end,
+                      const double* x0, const double* P0, int64_t n_schedules, const uint64_t* masks,
+                      double* x_final, double* P_final, double* traj, int32_t traj_ncomp,
+                      double* logdet, int32_t* n_terms, uint32_t flags, void* stream);
 
 /* Batched Scheduler.cov_matrix (kf_workers.py:112-171; the reference's only device='cuda'
  * branch): Sigma_post = Sigma - K H^ Sigma with H^ = the k selected rows of H, for `batch`

@@ -54,7 +54,10 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_uint32]),
     "b200kf_score_schedules": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), c_double,
                                        c_double, POINTER(c_double), c_uint64, c_uint64, c_double,
-                                       c_void_p, c_void_p, c_uint32, c_void_p]),
+                                       c_double, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b200kf_run_masked": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), POINTER(c_double),
+                                  c_double, c_double, POINTER(c_double), POINTER(c_double), c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint32, c_void_p]),
     "b200kf_cov_update": (c_int, [c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_double),
                                   POINTER(c_double), c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200kf_fill_payload": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_uint64, c_void_p, c_void_p]),

@@ -54,6 +54,16 @@ static int dispatch_score(const b200kf_model* m, const ScoreParams& p, unsigned 
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
 
+static int dispatch_masked(const b200kf_model* m, const MaskedParams& p, unsigned flags, cudaStream_t st) {
+  switch (m->desc.model_id) {
+    case MODEL_CV6: return launch_masked_m<MODEL_CV6>(m, p, flags, st);
+    case MODEL_CA8: return launch_masked_m<MODEL_CA8>(m, p, flags, st);
+    case MODEL_BIAS9: return launch_masked_m<MODEL_BIAS9>(m, p, flags, st);
+    case MODEL_CA15: return launch_masked_m<MODEL_CA15>(m, p, flags, st);
+  }
+  return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
+}
+
 // ---- schedule-search finaliser: reduce the per-block partials to one b200kf_best -------------
 __global__ void score_final_kernel(const ScorePartial* parts, int n_parts, int L, b200kf_best* out) {
   __shared__ ScorePartial sh[256];
@@ -536,8 +546,8 @@ done:
 
 int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_t* types,
                            const double* times, double t_prev, double t_end, const double* P0,
-                           uint64_t first, uint64_t count, double threshold, double* per_schedule,
-                           b200kf_best* best, uint32_t flags, void* stream) {
+                           uint64_t first, uint64_t count, double threshold, double initial_logdet,
+                           double* per_schedule, b200kf_best* best, uint32_t flags, void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
   if (n_events < 1 || n_events > kMaxEvents)
     return set_error(B200KF_ERR_UNSUPPORTED, "n_events must be in [1, %d]", kMaxEvents);
@@ -562,6 +572,7 @@ int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_
   p.first = first;
   p.count = count;
   p.threshold = threshold;
+  p.initial_logdet = initial_logdet;
   p.per_schedule = per_schedule;
   p.partials = search_scratch(m);
   p.dense_flag = nullptr;
@@ -571,6 +582,46 @@ int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_
   score_final_kernel<<<1, 256, 0, st>>>(static_cast<const ScorePartial*>(p.partials), blocks, n_events, best);
   B200KF_CUDA_TRY(cudaGetLastError());
   return B200KF_OK;
+}
+
+int b200kf_run_masked(const b200kf_model* m, int32_t n_events, const uint8_t* types, const double* times,
+                      const double* payload, double t_prev, double t_end, const double* x0,
+                      const double* P0, int64_t n_schedules, const uint64_t* masks, double* x_final,
+                      double* P_final, double* traj, int32_t traj_ncomp, double* logdet,
+                      int32_t* n_terms, uint32_t flags, void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (m->desc.precision != B200KF_F64)
+    return set_error(B200KF_ERR_UNSUPPORTED, "b200kf_run_masked is float64 only");
+  if (n_events < 1 || n_events > kMaxMaskedEvents)
+    return set_error(B200KF_ERR_UNSUPPORTED, "n_events must be in [1, %d]", kMaxMaskedEvents);
+  if (!types || !times || !payload || !x0 || !P0 || !masks || !x_final)
+    return set_error(B200KF_ERR_INVALID, "null argument");
+  if (traj && (traj_ncomp < 0 || traj_ncomp > m->n))
+    return set_error(B200KF_ERR_INVALID, "traj_ncomp must be in [0, %d]", m->n);
+  if (n_schedules <= 0) return B200KF_OK;
+  MaskedParams p;
+  memset(&p, 0, sizeof(p));
+  p.mc = m->mc;
+  p.n_events = n_events;
+  for (int i = 0; i < n_events; ++i) {
+    if (types[i] > B200KF_EV_PREDICT_ONLY) return set_error(B200KF_ERR_INVALID, "bad event type");
+    p.types[i] = types[i];
+    p.times[i] = times[i];
+    for (int c = 0; c < m->d; ++c) p.payload[i * m->d + c] = payload[i * m->d + c];
+  }
+  p.t_prev = t_prev;
+  p.t_end = t_end;
+  memcpy(p.x0, x0, sizeof(double) * m->n);
+  memcpy(p.P0, P0, sizeof(double) * m->n * m->n);
+  p.n_schedules = n_schedules;
+  p.masks = reinterpret_cast<const unsigned long long*>(masks);
+  p.x_final = x_final;
+  p.P_final = P_final;
+  p.traj = traj;
+  p.traj_ncomp = traj ? traj_ncomp : 0;
+  p.logdet = logdet;
+  p.n_terms = n_terms;
+  return dispatch_masked(m, p, flags, static_cast<cudaStream_t>(stream));
 }
 
 int b200kf_cov_update(int32_t n, int32_t m_rows, int32_t k, const int32_t* rows, const double* H,

@@ -176,6 +176,7 @@ template <class B, typename real>
 struct BlockKF {
   static constexpr int n = B::n;
   static constexpr int NP = n * (n + 1) / 2;
+  using Traits = B;
   real x[n];
   real P[NP];
   static constexpr int gidx(int i) { return B::gidx(i); }
@@ -388,8 +389,20 @@ struct BlockKF {
 template <typename real, bool IMU_CONTROL, class... Bs>
 struct FilterT;
 
+// A chain the closed-form 2x2 path below can handle: (value, rate) with value += dt * rate and
+// both states measured by the IMU event.
+template <class B>
+constexpr bool is_pv2() {
+  if (B::n != 2) return false;
+  return B::l1(0) == 1 && B::l2(0) < 0 && B::l1(1) < 0 && B::l2(1) < 0 && B::s1(0) == 1 &&
+         (B::zk(0) == ZK_POS || B::zk(0) == ZK_DIRECT) && (B::zk(1) == ZK_VEL || B::zk(1) == ZK_DIRECT) &&
+         B::cu(0) == 0 && B::cu(1) == 0 && B::gps(1) < 0;
+}
+
 template <typename real, bool IMU_CONTROL>
 struct FilterT<real, IMU_CONTROL> {
+  static constexpr bool fast2 = !IMU_CONTROL;
+  static constexpr int nblocks = 0;
   template <class F>
   __device__ __forceinline__ void each(F&&) {}
   template <class F>
@@ -400,6 +413,8 @@ template <typename real, bool IMU_CONTROL, class B0, class... Bs>
 struct FilterT<real, IMU_CONTROL, B0, Bs...> {
   BlockKF<B0, real> head;
   FilterT<real, IMU_CONTROL, Bs...> tail;
+  static constexpr bool fast2 = is_pv2<B0>() && FilterT<real, IMU_CONTROL, Bs...>::fast2;
+  static constexpr int nblocks = 1 + FilterT<real, IMU_CONTROL, Bs...>::nblocks;
   template <class F>
   __device__ __forceinline__ void each(F&& f) {
     f(head);
@@ -443,6 +458,166 @@ __device__ __forceinline__ double filter_det(const FilterT<real, IMU_CONTROL, Bs
   double d = 1.0;
   f.each([&](const auto& blk) { d *= double(blk.det(ok)); });
   return d;
+}
+
+// --------------------------------------------------------------------------------------
+// Closed-form path for filters made only of (value, rate) chains (CV6 decoupled).
+//
+// IMU event on one chain, P = [[a, b], [b, c]], H = I2, R = diag(r0, r1), S = P + R:
+//   D    = det S = detP + a r1 + c r0 + r0 r1
+//   P+   = R S^-1 P = (1/D) [[r0 (detP + a r1), r0 r1 b], [r0 r1 b, r1 (detP + c r0)]]
+//   K    = P S^-1   = (1/D) [[detP + a r1, r0 b], [r1 b, detP + c r0]]
+//   det P+ = r0 r1 detP / D
+// which is (I - KH)P of kf_workers.py:711 written without a single cancelling subtraction.  The
+// one reciprocal per chain is shared across the chains of a filter (rcp_batch): one MUFU per step.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double a) {  // a normal and > 0; ~1 ulp
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+__device__ __forceinline__ float fast_rcp(float a) { return 1.0f / a; }
+
+template <int K>
+__device__ __forceinline__ void rcp_batch(const double (&d)[K], double (&inv)[K]) {
+  double pre[K];
+  pre[0] = d[0];
+#pragma unroll
+  for (int i = 1; i < K; ++i) pre[i] = pre[i - 1] * d[i];
+  double r = fast_rcp(pre[K - 1]);
+#pragma unroll
+  for (int i = K - 1; i > 0; --i) {
+    inv[i] = r * pre[i - 1];
+    r = r * d[i];
+  }
+  inv[0] = r;
+}
+template <int K>
+__device__ __forceinline__ void rcp_batch(const float (&d)[K], float (&inv)[K]) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) inv[i] = 1.0f / d[i];
+}
+
+template <typename real>
+struct Upd2 {
+  real t0, t1, detp;
+};
+
+template <bool WITH_STATE, class B, typename real>
+__device__ __forceinline__ void pv2_predict(BlockKF<B, real>& k, real dt, const ModelConst& mc) {
+  real& a = k.P[0];
+  real& b = k.P[1];
+  real& c = k.P[2];
+  if constexpr (WITH_STATE) k.x[0] = fma(dt, k.x[1], k.x[0]);
+  const real bn = fma(dt, c, b);
+  a = fma(dt, b + bn, fma(real(mc.q[B::gidx(0)]), dt, a));  // a + 2 dt b + dt^2 c + q0 dt
+  b = bn;
+  c = fma(real(mc.q[B::gidx(1)]), dt, c);
+}
+
+template <class B, typename real>
+__device__ __forceinline__ real pv2_imu_begin(const BlockKF<B, real>& k, const ModelConst& mc,
+                                              Upd2<real>& w) {
+  const real a = k.P[0], b = k.P[1], c = k.P[2];
+  const real r0 = real(mc.r_imu[B::gidx(0)]), r1 = real(mc.r_imu[B::gidx(1)]);
+  w.detp = fma(a, c, -(b * b));
+  w.t0 = fma(a, r1, w.detp);
+  w.t1 = fma(c, r0, w.detp);
+  return fma(r0, c + r1, w.t0);
+}
+
+template <bool WITH_STATE, class B, typename real>
+__device__ __forceinline__ real pv2_imu_finish(BlockKF<B, real>& k, real dt, const ModelConst& mc,
+                                               const real* u, real inv, const Upd2<real>& w) {
+  const real b = k.P[1];
+  const real r0 = real(mc.r_imu[B::gidx(0)]), r1 = real(mc.r_imu[B::gidx(1)]);
+  const real g0 = r0 * inv, g1 = r1 * inv;
+  const real k01 = g0 * b, k10 = g1 * b;
+  if constexpr (WITH_STATE) {
+    // innovation y = z - x with z built from the predicted state (kf_workers.py:698-709)
+    real y0, y1;
+    if constexpr (B::zk(1) == ZK_VEL) y1 = u[B::pz(1)] * dt;
+    else y1 = u[B::pz(1)] - k.x[1];
+    if constexpr (B::zk(0) == ZK_POS) y0 = (k.x[1] + u[B::pz(0)] * dt) * dt;
+    else y0 = u[B::pz(0)] - k.x[0];
+    const real k00 = w.t0 * inv, k11 = w.t1 * inv;
+    k.x[0] = fma(k00, y0, fma(k01, y1, k.x[0]));
+    k.x[1] = fma(k10, y0, fma(k11, y1, k.x[1]));
+  }
+  k.P[0] = g0 * w.t0;
+  k.P[1] = k01 * r1;
+  k.P[2] = g1 * w.t1;
+  return (g0 * r1) * w.detp;  // det P+
+}
+
+// GPS event on a chain whose state 0 is measured (variance r): scalar update, reciprocal shared.
+template <bool WITH_STATE, class B, typename real>
+__device__ __forceinline__ void pv2_gps_finish(BlockKF<B, real>& k, const ModelConst& mc, real inv,
+                                               const real* u) {
+  const real a = k.P[0], b = k.P[1];
+  const real r = real(mc.r_gps[B::gps(0)]);
+  const real k0 = a * inv, k1 = b * inv, g = r * inv;
+  if constexpr (WITH_STATE) {
+    const real y = u[B::gps(0)] - k.x[0];
+    k.x[0] = fma(k0, y, k.x[0]);
+    k.x[1] = fma(k1, y, k.x[1]);
+  }
+  k.P[2] = fma(-k1, b, k.P[2]);
+  k.P[0] = a * g;
+  k.P[1] = b * g;
+}
+
+template <bool WITH_STATE, typename real, bool IMU_CONTROL, class... Bs>
+__device__ __forceinline__ void fast2_predict(FilterT<real, IMU_CONTROL, Bs...>& f, real dt,
+                                              const ModelConst& mc) {
+  f.each([&](auto& blk) { pv2_predict<WITH_STATE>(blk, dt, mc); });
+}
+
+// Update every chain for an event of type etype; returns det P+ (product over chains).
+template <bool WITH_STATE, typename real, bool IMU_CONTROL, class... Bs>
+__device__ __forceinline__ double fast2_update(FilterT<real, IMU_CONTROL, Bs...>& f, real dt,
+                                               const ModelConst& mc, int etype, const real* u, bool& ok) {
+  constexpr int NB = FilterT<real, IMU_CONTROL, Bs...>::nblocks;
+  real den[NB], inv[NB];
+  double det = 1.0;
+  if (etype == EV_IMU) {
+    Upd2<real> w[NB];
+    int i = 0;
+    f.each([&](auto& blk) {
+      den[i] = pv2_imu_begin(blk, mc, w[i]);
+      ++i;
+    });
+    rcp_batch<NB>(den, inv);
+    i = 0;
+    f.each([&](auto& blk) {
+      const real d = pv2_imu_finish<WITH_STATE>(blk, dt, mc, u, inv[i], w[i]);
+      ok = ok && (d > real(0));
+      det *= double(d);
+      ++i;
+    });
+    return det;
+  }
+  if (etype == EV_GPS) {
+    int i = 0;
+    f.each([&](auto& blk) {
+      using BT = std::remove_reference_t<decltype(blk)>;
+      if constexpr (BT::Traits::gps(0) >= 0) den[i] = blk.P[0] + real(mc.r_gps[BT::Traits::gps(0)]);
+      else den[i] = real(1);
+      ++i;
+    });
+    rcp_batch<NB>(den, inv);
+    i = 0;
+    f.each([&](auto& blk) {
+      using BT = std::remove_reference_t<decltype(blk)>;
+      if constexpr (BT::Traits::gps(0) >= 0) pv2_gps_finish<WITH_STATE>(blk, mc, inv[i], u);
+      ++i;
+    });
+  }
+  return filter_det(f, ok);
 }
 
 // --------------------------------------------------------------------------------------

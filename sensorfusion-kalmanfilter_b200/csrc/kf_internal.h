@@ -66,9 +66,34 @@ struct ScoreParams {
   double P0[kMaxN * kMaxN];  // [n, n] row-major
   unsigned long long first, count;
   double threshold;
+  double initial_logdet;  // NaN: compute term 0 on the device; else the host's slogdet(P0)
   double* per_schedule;  // [count, 4] or null
   void* partials;        // per-block results
   const int* dense_flag;
+};
+
+constexpr int kMaxMaskedEvents = 64;
+constexpr int kMaxPayload = 9;
+
+// evaluate_combo_chunk_worker (kf_workers.py:22-97) with state: every schedule (bitmask over one
+// shared window) runs the full filter; window, payload, x0, P0 travel as kernel parameters.
+struct MaskedParams {
+  ModelConst mc;
+  int n_events;
+  unsigned char types[kMaxMaskedEvents];
+  double times[kMaxMaskedEvents];
+  double payload[kMaxMaskedEvents * kMaxPayload];  // [L, d]
+  double t_prev, t_end;
+  double x0[kMaxN];
+  double P0[kMaxN * kMaxN];
+  long long n_schedules;
+  const unsigned long long* masks;  // DEVICE [N]
+  double* x_final;                  // DEVICE [N, n]
+  double* P_final;                  // DEVICE [N, n, n] or null
+  double* traj;                     // DEVICE [N, L+2, 1+traj_ncomp] or null
+  int traj_ncomp;
+  double* logdet;                   // DEVICE [N, L+2] or null
+  int* n_terms;                     // DEVICE [N] or null
 };
 
 struct ScorePartial {
@@ -85,6 +110,9 @@ int launch_run_m(const b200kf_model* m, const RunParams& p, unsigned flags, cuda
 template <int MODEL>
 int launch_score_m(const b200kf_model* m, ScoreParams p, unsigned flags, b200kf_best* best,
                    cudaStream_t st);
+
+template <int MODEL>
+int launch_masked_m(const b200kf_model* m, const MaskedParams& p, unsigned flags, cudaStream_t st);
 
 inline int* dense_flag(const b200kf_model* m) { return reinterpret_cast<int*>(m->arena); }
 inline void* search_scratch(const b200kf_model* m) {

@@ -13,13 +13,30 @@
 
 namespace b200kf {
 
-constexpr int PF = 2;  // payload prefetch depth (steps)
+#ifndef B200KF_PF
+#define B200KF_PF 1
+#endif
+constexpr int PF = B200KF_PF;  // payload prefetch depth (steps)
+
+// Launch shape per kernel variant.  The closed-form (value, rate)-chain kernels are capped at 72
+// registers so 7 blocks x 128 threads = 896 filters are resident per SM: the 131 072-filter shard
+// of BASELINE config 3 (885.6 filters per SM over 148 SMs) then runs as ONE balanced wave
+// instead of 1.15 waves with an almost empty second one.
+template <int MODEL, bool DENSE, typename real>
+struct LaunchCfg {
+  static constexpr bool fast = ModelTraits<MODEL, DENSE, real>::Filter::fast2;
+  static constexpr int max_threads = fast ? 128 : 256;
+  static constexpr int min_blocks = fast ? 7 : 1;
+};
 
 template <int MODEL, bool DENSE, typename real, bool FULL>
-__global__ void __launch_bounds__(256) kf_run_kernel(const RunParams p) {
+__global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
+                                  (LaunchCfg<MODEL, DENSE, real>::min_blocks))
+    kf_run_kernel(const RunParams p) {
   using MT = ModelTraits<MODEL, DENSE, real>;
   constexpr int n = MT::n;
   constexpr int D = MT::d;
+  constexpr bool FAST = MT::Filter::fast2;
   if (p.dense_flag != nullptr && *p.dense_flag != (DENSE ? 1 : 0)) return;
   const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (f >= p.n_filters) return;
@@ -33,7 +50,10 @@ __global__ void __launch_bounds__(256) kf_run_kernel(const RunParams p) {
     flt.each([&](auto& b) { b.load(xg, Pg, n); });
   }
 
-  LogDetAcc acc;
+  // lean running aggregate: mantissa product + exponent sum + max; "last" is recomputed from the
+  // final P and the count is T, which keeps the hot loop inside the 72-register budget
+  double acc_mant = 1.0, acc_max = 0.0;
+  int acc_expo = 0;
   bool ok = true;
 
   const real* pay = static_cast<const real*>(p.payload) + f;
@@ -63,7 +83,8 @@ __global__ void __launch_bounds__(256) kf_run_kernel(const RunParams p) {
         const int ty = __ldg(p.types + k);
         const real dt = static_cast<real>(__ldg(p.dts + k));
 
-        filter_predict<true>(flt, dt, p.mc, ty, u);
+        if constexpr (FAST) fast2_predict<true>(flt, dt, p.mc);
+        else filter_predict<true>(flt, dt, p.mc, ty, u);
         bool do_update = (ty != EV_PREDICT_ONLY);
         if constexpr (FULL) {
           if (p.gate_enabled) {  // kf_workers.py:1023-1025
@@ -71,9 +92,21 @@ __global__ void __launch_bounds__(256) kf_run_kernel(const RunParams p) {
             do_update = do_update && (log(dpre) > p.gate_threshold);
           }
         }
-        if (do_update) filter_update<true>(flt, dt, p.mc, ty, u);
-        const double det = filter_det(flt, ok);
-        acc.add(det);
+        double det;
+        if constexpr (FAST) {
+          det = do_update ? fast2_update<true>(flt, dt, p.mc, ty, u, ok) : filter_det(flt, ok);
+        } else {
+          if (do_update) filter_update<true>(flt, dt, p.mc, ty, u);
+          det = filter_det(flt, ok);
+        }
+        {
+          acc_max = fmax(acc_max, det);
+          const double m = acc_mant * det;
+          const int hi = __double2hiint(m);
+          const int e = ((hi >> 20) & 0x7ff) - 1023;
+          acc_expo += e;
+          acc_mant = __hiloint2double(hi - (e << 20), __double2loint(m));
+        }
 
         if constexpr (FULL) {
           if (p.traj != nullptr) {
@@ -105,9 +138,9 @@ __global__ void __launch_bounds__(256) kf_run_kernel(const RunParams p) {
   }
   if (p.agg != nullptr) {
     double* a = p.agg + f * 4;
-    double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
-    double sm = acc.sum_log();
-    double cnt = static_cast<double>(acc.count);
+    double mx = (T > 0) ? log(acc_max) : -INFINITY;
+    double sm = log(acc_mant) + static_cast<double>(acc_expo) * 0.6931471805599453094;
+    double cnt = static_cast<double>(T);
     if (p.agg_continue) {
       mx = fmax(mx, a[0]);
       sm += a[1];
@@ -115,7 +148,7 @@ __global__ void __launch_bounds__(256) kf_run_kernel(const RunParams p) {
     }
     a[0] = mx;
     a[1] = sm;
-    a[2] = (acc.count > 0) ? log(acc.last) : (p.agg_continue ? a[2] : 0.0);
+    a[2] = (T > 0) ? log(filter_det(flt, ok)) : (p.agg_continue ? a[2] : 0.0);
     a[3] = cnt;
   }
   if (p.status != nullptr) {
@@ -146,7 +179,8 @@ __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filt
 template <int MODEL, bool DENSE, typename real>
 static cudaError_t launch_variant(const b200kf_model* m, const RunParams& p, bool full,
                                   cudaStream_t st) {
-  const int tpb = m->tpb;
+  using LC = LaunchCfg<MODEL, DENSE, real>;
+  const int tpb = LC::fast ? LC::max_threads : (m->tpb <= LC::max_threads ? m->tpb : LC::max_threads);
   const long long blocks = (p.n_filters + tpb - 1) / tpb;
   if (full)
     kf_run_kernel<MODEL, DENSE, real, true><<<static_cast<unsigned>(blocks), tpb, 0, st>>>(p);

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
     flt.each([&](auto& b) { b.load_cov(p.P0, n); });
     bool ok = true;
     LogDetAcc acc;
-    acc.add(filter_det(flt, ok));  // log_det[0], kf_workers.py:32
+    const bool host_ld0 = !isnan(p.initial_logdet);
+    if (!host_ld0) acc.add(filter_det(flt, ok));  // log_det[0], kf_workers.py:32
     double tcur = p.t_prev;
     for (int i = 0; i < L; ++i) {
       if (!((s >> i) & 1ULL)) continue;
@@ -71,14 +72,22 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
       filter_predict<false>(flt, dt, p.mc, EV_PREDICT_ONLY, static_cast<const double*>(nullptr));
       acc.add(filter_det(flt, ok));
     }
-    const double mx = ok ? log(acc.maxdet) : NAN;
-    const double sm = ok ? acc.sum_log() : NAN;
+    double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
+    double sm = acc.sum_log();
+    double lastv = (acc.count > 0) ? log(acc.last) : p.initial_logdet;
+    int cnt = acc.count;
+    if (host_ld0) {  // term 0 is the same for every schedule: take the caller's value verbatim
+      mx = fmax(mx, p.initial_logdet);
+      sm += p.initial_logdet;
+      cnt += 1;
+    }
+    if (!ok) mx = sm = lastv = NAN;
     if (p.per_schedule != nullptr) {
       double* o = p.per_schedule + idx * 4;
       o[0] = mx;
       o[1] = sm;
-      o[2] = ok ? log(acc.last) : NAN;
-      o[3] = static_cast<double>(acc.count);
+      o[2] = lastv;
+      o[3] = static_cast<double>(cnt);
     }
     if (s != 0 && ok) {  // the reference never enumerates the empty set (:1325)
       better_sum(best_sc, best_ix, sm, s);
@@ -116,6 +125,97 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
     }
     static_cast<ScorePartial*>(p.partials)[blockIdx.x] = r;
   }
+}
+
+// ---- worker with state: full filter per schedule over one shared window ----------------------
+template <int MODEL, bool DENSE>
+__global__ void __launch_bounds__(kScoreTpb) masked_run_kernel(const MaskedParams p) {
+  using MT = ModelTraits<MODEL, DENSE, double>;
+  constexpr int n = MT::n;
+  constexpr int D = MT::d;
+  const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (f >= p.n_schedules) return;
+  const unsigned long long s = p.masks[f];
+  const int L = p.n_events;
+  const int rows = L + 2;
+  const int tw = 1 + p.traj_ncomp;
+  typename MT::Filter flt;
+  flt.each([&](auto& b) {
+    b.load_cov(p.P0, n);
+    using BT = std::remove_reference_t<decltype(b)>;
+    static_for<0, BT::n>([&](auto I) { b.x[I] = p.x0[BT::gidx(I)]; });
+  });
+  bool ok = true;
+  int term = 0;
+  auto emit = [&](double t) {
+    if (p.logdet != nullptr) p.logdet[f * rows + term] = log(filter_det(flt, ok));
+    if (p.traj != nullptr) {
+      double* tr = p.traj + (f * rows + term) * tw;
+      tr[0] = t;
+      const int nc = p.traj_ncomp;
+      flt.each([&](const auto& b) {
+        using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+        static_for<0, BT::n>([&](auto I) {
+          constexpr int g = BT::gidx(I);
+          if (g < nc) tr[1 + g] = b.x[I];
+        });
+      });
+    }
+    term += 1;
+  };
+  emit(p.t_prev);  // traj[0], log_det[0]  (kf_workers.py:31-32)
+  double tcur = p.t_prev;
+  for (int i = 0; i < L; ++i) {
+    if (!((s >> i) & 1ULL)) continue;
+    const double dt = p.times[i] - tcur;  // :37
+    if (dt < 0) continue;                 // :38-40
+    const int ty = p.types[i];
+    double u[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) u[c] = p.payload[i * D + c];
+    filter_predict<true>(flt, dt, p.mc, ty, u);
+    filter_update<true>(flt, dt, p.mc, ty, u);
+    tcur = p.times[i];
+    emit(tcur);
+  }
+  if (tcur < p.t_end - 1e-8) {  // :74-82
+    const double dt = p.t_end - tcur;
+    filter_predict<true>(flt, dt, p.mc, EV_PREDICT_ONLY, static_cast<const double*>(nullptr));
+    emit(p.t_end);
+  }
+  if (p.n_terms != nullptr) p.n_terms[f] = ok ? term : -term;
+  flt.each([&](const auto& b) {
+    using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+    static_for<0, BT::n>([&](auto I) { p.x_final[f * n + BT::gidx(I)] = b.x[I]; });
+  });
+  if (p.P_final != nullptr) {
+    double* Pg = p.P_final + f * (n * n);
+    if constexpr (!DENSE) {
+      for (int e = 0; e < n * n; ++e) Pg[e] = 0.0;
+    }
+    double xs[n];
+    flt.each([&](const auto& b) { b.store(xs, Pg, n); });
+  }
+}
+
+template <>
+int launch_masked_m<B200KF_INST_MODEL>(const b200kf_model* m, const MaskedParams& p, unsigned flags,
+                                       cudaStream_t st) {
+  (void)m;
+  using MT = ModelTraits<B200KF_INST_MODEL, false, double>;
+  bool dense = (flags & B200KF_RUN_FORCE_DENSE) != 0;
+  if (!dense && !(flags & B200KF_RUN_FORCE_DECOUPLED)) {
+    for (int i = 0; i < MT::n; ++i)
+      for (int j = 0; j < MT::n; ++j)
+        if (MT::chain_of(i) != MT::chain_of(j) && p.P0[i * MT::n + j] != 0.0) dense = true;
+  }
+  const unsigned blocks = static_cast<unsigned>((p.n_schedules + kScoreTpb - 1) / kScoreTpb);
+  if (dense)
+    masked_run_kernel<B200KF_INST_MODEL, true><<<blocks, kScoreTpb, 0, st>>>(p);
+  else
+    masked_run_kernel<B200KF_INST_MODEL, false><<<blocks, kScoreTpb, 0, st>>>(p);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
 }
 
 template <>

@@ -156,8 +156,11 @@ class Engine:
 
     # ------------------------------------------------------------------ schedule search
     def score_schedules(self, types, times, t_prev, t_end, P0, *, first=0, count=None,
-                        threshold=float("inf"), want_per_schedule=False, mode="auto", stream=None):
+                        threshold=float("inf"), initial_logdet=None, want_per_schedule=False, mode="auto",
+                        stream=None):
         """Score the subset schedules [first, first+count) of a window (b200kf_score_schedules).
+        initial_logdet: the caller's sign*logabsdet of P0 used verbatim as term 0 (exact ties with
+        a threshold derived from it resolve as in the reference); None computes it on the device.
         Returns (best: dict, per_schedule: torch [count,4] or None)."""
         torch = _torch()
         types = np.ascontiguousarray(types, dtype=np.uint8)
@@ -172,7 +175,8 @@ class Engine:
             _lib.check(self.lib.b200kf_score_schedules(
                 self._h, L, types.ctypes.data_as(POINTER(c_uint8)), times.ctypes.data_as(POINTER(c_double)),
                 float(t_prev), float(t_end), P0.ctypes.data_as(POINTER(c_double)), int(first), int(count),
-                float(threshold), _ptr(per), _ptr(best_d), _MODES[mode], self._stream(stream)))
+                float(threshold), float("nan") if initial_logdet is None else float(initial_logdet),
+                _ptr(per), _ptr(best_d), _MODES[mode], self._stream(stream)))
         raw = bytes(best_d.cpu().numpy().tobytes())
         b = _lib.Best.from_buffer_copy(raw)
         none = (1 << 64) - 1
@@ -185,6 +189,37 @@ class Engine:
             "n_near_threshold": int(b.n_near_threshold),
         }
         return best, per
+
+
+    def run_masked(self, types, times, payload, t_prev, t_end, x0, P0, masks, *, traj_ncomp=6,
+                   want_P=False, mode="auto", stream=None):
+        """Full filter per subset schedule of one shared window (b200kf_run_masked): what
+        evaluate_combo_chunk_worker computes per combo.  payload [L, d]; masks: iterable of ints.
+        Returns dict of torch CUDA tensors x_final [N,n], P_final, traj [N,L+2,1+ncomp],
+        logdet [N,L+2], n_terms [N]."""
+        torch = _torch()
+        sp = self.spec
+        types = np.ascontiguousarray(types, dtype=np.uint8)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        payload = np.ascontiguousarray(payload, dtype=np.float64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        P0 = np.ascontiguousarray(P0, dtype=np.float64)
+        L = int(types.shape[0])
+        masks_d = torch.as_tensor(np.asarray(masks, dtype=np.uint64).view(np.int64)).to(self.device)
+        N = int(masks_d.numel())
+        x_f = torch.empty((N, sp.n), dtype=torch.float64, device=self.device)
+        P_f = torch.empty((N, sp.n, sp.n), dtype=torch.float64, device=self.device) if want_P else None
+        traj = torch.zeros((N, L + 2, 1 + traj_ncomp), dtype=torch.float64, device=self.device)
+        ld = torch.full((N, L + 2), float("nan"), dtype=torch.float64, device=self.device)
+        nt = torch.zeros((N,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_run_masked(
+                self._h, L, types.ctypes.data_as(POINTER(c_uint8)), times.ctypes.data_as(POINTER(c_double)),
+                payload.ctypes.data_as(POINTER(c_double)), float(t_prev), float(t_end),
+                x0.ctypes.data_as(POINTER(c_double)), P0.ctypes.data_as(POINTER(c_double)), N, _ptr(masks_d),
+                _ptr(x_f), _ptr(P_f), _ptr(traj), int(traj_ncomp), _ptr(ld), _ptr(nt), _MODES[mode],
+                self._stream(stream)))
+        return {"x_final": x_f, "P_final": P_f, "traj": traj, "logdet": ld, "n_terms": nt}
 
 
 def cov_update(Sigma, rows, H, R, device=None, stream=None):

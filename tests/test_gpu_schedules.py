@@ -55,9 +55,10 @@ def test_driver_selection_bit_exact(brute):
     Ld = int(brute["drv_L"])
     types, times = window_arrays(brute, Ld)
     eng = Engine("CA15")
+    sgn, lad = np.linalg.slogdet(brute["P0"])  # term 0 exactly as the caller (and the reference) has it
     for thr, mask in zip(brute["drv_thr"], brute["drv_mask"]):
         best, _ = eng.score_schedules(types, times, brute["init_state"][0], float(times[-1]), brute["P0"],
-                                      threshold=float(thr))
+                                      threshold=float(thr), initial_logdet=float(sgn * lad))
         if int(mask) < 0:
             assert best["first_feasible_index"] is None and best["n_feasible"] == 0
         else:
