@@ -172,6 +172,25 @@ int b200kf_run_masked(const b200kf_model* model, int32_t n_events, const uint8_t
                       double* x_final, double* P_final, double* traj, int32_t traj_ncomp,
                       double* logdet, int32_t* n_terms, uint32_t flags, void* stream);
 
+/* Greedy one-event-per-window scheduling: replaces the queueing + Scheduler.greedy_schedule
+ * selection of run_kalman_filter_scheduled (kf_workers.py:877-910, :174-213) for n_inst
+ * independent instances (processing period, start time, P0) walking ONE shared event list.  The
+ * selection reads P but never a measurement, so this is a covariance-only pass; feed the selected
+ * events to b200kf_run_batch for the states.
+ *
+ *   types, times  DEVICE [E]       events AFTER the initialising one (:877)
+ *   periods       DEVICE f64 [I]   1 / processing_frequency
+ *   t_prev        DEVICE f64 [I]   previous_time at entry
+ *   P0            DEVICE f64 [I, n, n]
+ *   sel           DEVICE i32 [I, max_sel]  selected event index per window (first max_sel kept)
+ *   n_sel         DEVICE i64 [I]   number of windows (may exceed max_sel: call again larger)
+ *   P_final       DEVICE f64 [I, n, n] nullable
+ */
+int b200kf_select_greedy(const b200kf_model* model, int64_t n_events, const uint8_t* types,
+                         const double* times, int32_t n_inst, const double* periods,
+                         const double* t_prev, const double* P0, int64_t max_sel, int32_t* sel,
+                         int64_t* n_sel, double* P_final, uint32_t flags, void* stream);
+
 /* Batched Scheduler.cov_matrix (kf_workers.py:112-171; the reference's only device='cuda'
  * branch): Sigma_post = Sigma - K H^ Sigma with H^ = the k selected rows of H, for `batch`
  * covariances.  H HOST f64 [m, n], R HOST f64 [m, m], rows HOST i32 [k] (0-based),

@@ -58,6 +58,8 @@ SIGNATURES = {
     "b200kf_run_masked": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), POINTER(c_double),
                                   c_double, c_double, POINTER(c_double), POINTER(c_double), c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b200kf_select_greedy": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_int64, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "b200kf_cov_update": (c_int, [c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_double),
                                   POINTER(c_double), c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200kf_fill_payload": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_uint64, c_void_p, c_void_p]),

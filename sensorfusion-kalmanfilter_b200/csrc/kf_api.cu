@@ -64,6 +64,16 @@ static int dispatch_masked(const b200kf_model* m, const MaskedParams& p, unsigne
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
 
+static int dispatch_select(const b200kf_model* m, const SelectParams& p, unsigned flags, cudaStream_t st) {
+  switch (m->desc.model_id) {
+    case MODEL_CV6: return launch_select_m<MODEL_CV6>(m, p, flags, st);
+    case MODEL_CA8: return launch_select_m<MODEL_CA8>(m, p, flags, st);
+    case MODEL_BIAS9: return launch_select_m<MODEL_BIAS9>(m, p, flags, st);
+    case MODEL_CA15: return launch_select_m<MODEL_CA15>(m, p, flags, st);
+  }
+  return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
+}
+
 // ---- schedule-search finaliser: reduce the per-block partials to one b200kf_best -------------
 __global__ void score_final_kernel(const ScorePartial* parts, int n_parts, int L, b200kf_best* out) {
   __shared__ ScorePartial sh[256];
@@ -379,6 +389,8 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   m->arena = nullptr;
   m->arena_bytes = kArenaBytes;
   m->tpb = 64;
+  m->use_tma = 1;
+  if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
   if (const char* s = getenv("B200KF_TPB")) {
     const int v = atoi(s);
     if (v >= 32 && v <= 256 && v % 32 == 0) m->tpb = v;
@@ -622,6 +634,34 @@ int b200kf_run_masked(const b200kf_model* m, int32_t n_events, const uint8_t* ty
   p.logdet = logdet;
   p.n_terms = n_terms;
   return dispatch_masked(m, p, flags, static_cast<cudaStream_t>(stream));
+}
+
+int b200kf_select_greedy(const b200kf_model* m, int64_t n_events, const uint8_t* types,
+                         const double* times, int32_t n_inst, const double* periods, const double* t_prev,
+                         const double* P0, int64_t max_sel, int32_t* sel, int64_t* n_sel, double* P_final,
+                         uint32_t flags, void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (m->desc.model_id == MODEL_BIAS9)
+    return set_error(B200KF_ERR_UNSUPPORTED, "greedy selection needs an IMU measurement model");
+  if (n_events < 0 || n_inst < 0 || max_sel < 0) return set_error(B200KF_ERR_INVALID, "negative size");
+  if (n_events > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_events > 2^31-1");
+  if (n_inst == 0) return B200KF_OK;
+  if (!periods || !t_prev || !P0 || !sel || !n_sel || (n_events > 0 && (!types || !times)))
+    return set_error(B200KF_ERR_INVALID, "null argument");
+  SelectParams p;
+  p.mc = m->mc;
+  p.n_events = n_events;
+  p.types = types;
+  p.times = times;
+  p.n_inst = n_inst;
+  p.periods = periods;
+  p.t_prev = t_prev;
+  p.P0 = P0;
+  p.max_sel = max_sel;
+  p.sel = sel;
+  p.n_sel = reinterpret_cast<long long*>(n_sel);
+  p.P_final = P_final;
+  return dispatch_select(m, p, flags, static_cast<cudaStream_t>(stream));
 }
 
 int b200kf_cov_update(int32_t n, int32_t m_rows, int32_t k, const int32_t* rows, const double* H,

@@ -17,12 +17,14 @@ struct b200kf_model {
   // device arena: [0] dense-needed flag, then reduction scratch for the schedule search
   void* arena;
   size_t arena_bytes;
-  int tpb;  // threads per block for the filter kernels (env B200KF_TPB)
+  int tpb;      // threads per block for the filter kernels (env B200KF_TPB)
+  int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };
 
 namespace b200kf {
 
-constexpr size_t kArenaBytes = 1 << 20;
+constexpr size_t kArenaBytes = 4 << 20;
+constexpr size_t kSchedOffset = 1 << 20;  // packed (dt, type) records of the TMA kernel
 constexpr int kMaxSearchBlocks = 8192;
 
 int set_error(int code, const char* fmt, ...);
@@ -96,6 +98,22 @@ struct MaskedParams {
   int* n_terms;                     // DEVICE [N] or null
 };
 
+// run_kalman_filter_scheduled's window/selection logic (kf_workers.py:877-947), covariance-only.
+struct SelectParams {
+  ModelConst mc;
+  long long n_events;
+  const unsigned char* types;  // DEVICE [E]
+  const double* times;         // DEVICE [E]
+  int n_inst;
+  const double* periods;       // DEVICE [I]  1 / processing_frequency
+  const double* t_prev;        // DEVICE [I]
+  const double* P0;            // DEVICE [I, n, n]
+  long long max_sel;
+  int* sel;                    // DEVICE [I, max_sel] selected event indices
+  long long* n_sel;            // DEVICE [I]
+  double* P_final;             // DEVICE [I, n, n] or null
+};
+
 struct ScorePartial {
   double score;
   unsigned long long index;
@@ -114,9 +132,16 @@ int launch_score_m(const b200kf_model* m, ScoreParams p, unsigned flags, b200kf_
 template <int MODEL>
 int launch_masked_m(const b200kf_model* m, const MaskedParams& p, unsigned flags, cudaStream_t st);
 
+template <int MODEL>
+int launch_select_m(const b200kf_model* m, const SelectParams& p, unsigned flags, cudaStream_t st);
+
 inline int* dense_flag(const b200kf_model* m) { return reinterpret_cast<int*>(m->arena); }
 inline void* search_scratch(const b200kf_model* m) {
   return reinterpret_cast<char*>(m->arena) + 256;
 }
+inline void* sched_scratch(const b200kf_model* m) {
+  return reinterpret_cast<char*>(m->arena) + kSchedOffset;
+}
+inline size_t sched_capacity(const b200kf_model* m) { return m->arena_bytes - kSchedOffset; }
 
 }  // namespace b200kf

@@ -157,7 +157,238 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
   }
 }
 
-// BlockKF::x / gidx are needed by the trajectory writer above
+
+// ------------------------------------------------------------------------------------------
+// TMA-staged variant for the closed-form filters (aggregate mode): one persistent 896-thread CTA
+// per SM, each thread one filter.  The payload rows of a CTA's 896 filters are contiguous in the
+// time-major layout (7 KB per (step, column)), so one elected thread streams them into a ring of
+// shared-memory stages with cp.async.bulk (UBLKCP) completing on mbarriers, together with the
+// packed (dt, type) records of the chunk.  The math warps never issue a global load in the loop:
+// they wait on the stage's "full" barrier, read their 3 reals with conflict-free LDS, and one lane
+// per warp arrives on the "empty" barrier.  Besides hiding HBM latency at 28 warps/SM, the ring
+// bounds the skew between warps to kStages-1 chunks, which removes the long single-wave tail the
+// LDG kernel shows (warps that win the issue arbitration finish early and leave the FP64 pipe
+// half empty at the end).
+// ------------------------------------------------------------------------------------------
+constexpr int kTmaThreads = 896;  // 7 warps per SM sub-partition; 896 * 72 regs = 63 K registers
+constexpr int kChunk = 2;         // steps per stage
+constexpr int kStages = 4;
+
+struct SchedRec {  // 16 bytes: bulk copies need 16-byte granularity
+  double dt;
+  int type;
+  int pad;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, const double* __restrict__ dts,
+                                     int T, SchedRec* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < T) out[k] = SchedRec{dts[k], static_cast<int>(types[k]), 0};
+}
+
+template <int MODEL, typename real>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched) {
+  using MT = ModelTraits<MODEL, false, real>;
+  constexpr int n = MT::n;
+  constexpr int D = MT::d;
+  static_assert(MT::Filter::fast2, "TMA kernel is for the closed-form filters");
+  if (p.dense_flag != nullptr && *p.dense_flag != 0) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kStages][kChunk][D][kTmaThreads]
+  constexpr size_t kStageReals = static_cast<size_t>(kChunk) * D * kTmaThreads;
+  SchedRec* sched_buf = reinterpret_cast<SchedRec*>(stage_buf + kStages * kStageReals);  // [kStages][kChunk]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sched_buf + kStages * kChunk);
+  unsigned long long* empty = full + kStages;
+
+  const int tid = threadIdx.x;
+  const long long N = p.n_filters;
+  const long long base = static_cast<long long>(blockIdx.x) * kTmaThreads;
+  const int nfb = static_cast<int>((N - base) < kTmaThreads ? (N - base) : kTmaThreads);
+  const long long f = base + tid;
+  const bool active = tid < nfb;
+  const int T = p.n_steps;
+  const int nchunks = (T + kChunk - 1) / kChunk;
+  const unsigned row_bytes = static_cast<unsigned>(nfb * sizeof(real));
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTmaThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const real* pay = static_cast<const real*>(p.payload) + base;
+  auto issue = [&](int chunk) {  // elected thread only
+    const int s = chunk % kStages;
+    const int k0 = chunk * kChunk;
+    const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+    mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * (D * row_bytes + sizeof(SchedRec)));
+    bulk_g2s(sched_buf + s * kChunk, sched + k0, static_cast<unsigned>(steps * sizeof(SchedRec)), &full[s]);
+    real* dst = stage_buf + s * kStageReals;
+    for (int c = 0; c < steps; ++c)
+#pragma unroll
+      for (int j = 0; j < D; ++j)
+        bulk_g2s(dst + (c * D + j) * kTmaThreads, pay + (static_cast<long long>(k0 + c) * D + j) * N, row_bytes,
+                 &full[s]);
+  };
+  if (tid == 0) {
+    for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
+  }
+
+  typename MT::Filter flt;
+  if (active) {
+    const real* xg = static_cast<const real*>(p.x) + f * n;
+    const real* Pg = static_cast<const real*>(p.P) + f * (n * n);
+    flt.each([&](auto& b) { b.load(xg, Pg, n); });
+  }
+  double acc_mant = 1.0, acc_max = 0.0;
+  int acc_expo = 0;
+  bool ok = true;
+
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int s = chunk % kStages;
+    const unsigned use = static_cast<unsigned>(chunk / kStages);
+    if (tid == 0) {
+      const int nxt = chunk + kStages - 1;  // refill the stage chunk-1 used, once every warp left it
+      if (nxt < nchunks) {
+        if (chunk >= 1) mbar_wait(&empty[nxt % kStages], static_cast<unsigned>((chunk - 1) / kStages) & 1u);
+        issue(nxt);
+      }
+    }
+    mbar_wait(&full[s], use & 1u);
+    const int k0 = chunk * kChunk;
+    const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+    if (active) {
+      const real* sb = stage_buf + s * kStageReals + tid;
+#pragma unroll
+      for (int c = 0; c < kChunk; ++c) {
+        if (c < steps) {
+          const SchedRec rec = sched_buf[s * kChunk + c];
+          real u[D];
+#pragma unroll
+          for (int j = 0; j < D; ++j) u[j] = sb[(c * D + j) * kTmaThreads];
+          const real dt = static_cast<real>(rec.dt);
+          const int ty = rec.type;
+          fast2_predict<true>(flt, dt, p.mc);
+          const double det = (ty != EV_PREDICT_ONLY) ? fast2_update<true>(flt, dt, p.mc, ty, u, ok)
+                                                     : filter_det(flt, ok);
+          acc_max = fmax(acc_max, det);
+          const double m = acc_mant * det;
+          const int hi = __double2hiint(m);
+          const int e = ((hi >> 20) & 0x7ff) - 1023;
+          acc_expo += e;
+          acc_mant = __hiloint2double(hi - (e << 20), __double2loint(m));
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+  }
+
+  if (!active) return;
+  {
+    real* xg = static_cast<real*>(p.x) + f * n;
+    real* Pg = static_cast<real*>(p.P) + f * (n * n);
+    flt.each([&](const auto& b) { b.store(xg, Pg, n); });
+  }
+  if (p.agg != nullptr) {
+    double* a = p.agg + f * 4;
+    double mx = (T > 0) ? log(acc_max) : -INFINITY;
+    double sm = log(acc_mant) + static_cast<double>(acc_expo) * 0.6931471805599453094;
+    double cnt = static_cast<double>(T);
+    if (p.agg_continue) {
+      mx = fmax(mx, a[0]);
+      sm += a[1];
+      cnt += a[3];
+    }
+    a[0] = mx;
+    a[1] = sm;
+    a[2] = (T > 0) ? log(filter_det(flt, ok)) : (p.agg_continue ? a[2] : 0.0);
+    a[3] = cnt;
+  }
+  if (p.status != nullptr) {
+    const int bad = ok ? 0 : 1;
+    p.status[f] = p.agg_continue ? (p.status[f] | bad) : bad;
+  }
+}
+
+template <int MODEL, typename real>
+constexpr size_t tma_smem_bytes() {
+  using MT = ModelTraits<MODEL, false, real>;
+  return static_cast<size_t>(kStages) * kChunk * MT::d * kTmaThreads * sizeof(real) +
+         static_cast<size_t>(kStages) * kChunk * sizeof(SchedRec) + 2 * kStages * sizeof(unsigned long long);
+}
+
+// true when the TMA kernel was enqueued; false -> caller uses the LDG kernel
+template <int MODEL, typename real>
+static bool try_launch_tma(const b200kf_model* m, const RunParams& p, bool full, cudaStream_t st,
+                           cudaError_t& err) {
+  err = cudaSuccess;
+  if constexpr (!ModelTraits<MODEL, false, real>::Filter::fast2) {
+    return false;
+  } else {
+    if (full || m->use_tma == 0) return false;
+    const size_t need = static_cast<size_t>(p.n_steps) * sizeof(SchedRec);
+    // bulk copies need 16-byte aligned rows: even filter count for f64, multiple of 4 for f32
+    const long long align_elems = 16 / static_cast<long long>(sizeof(real));
+    if (p.n_steps < 1 || need > sched_capacity(m) || (p.n_filters % align_elems) != 0 ||
+        (reinterpret_cast<uintptr_t>(p.payload) & 15u) != 0)
+      return false;
+    SchedRec* sched = reinterpret_cast<SchedRec*>(sched_scratch(m));
+    pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, sched);
+    constexpr size_t smem = tma_smem_bytes<MODEL, real>();
+    static bool attr_set = false;
+    if (!attr_set) {
+      err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem));
+      if (err != cudaSuccess) return true;
+      attr_set = true;
+    }
+    const unsigned blocks = static_cast<unsigned>((p.n_filters + kTmaThreads - 1) / kTmaThreads);
+    kf_run_tma_kernel<MODEL, real><<<blocks, kTmaThreads, smem, st>>>(p, sched);
+    err = cudaGetLastError();
+    return true;
+  }
+}
+
 template <int MODEL, typename real>
 __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filters, int* flag) {
   using MT = ModelTraits<MODEL, false, real>;
@@ -197,8 +428,13 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
     B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));
     return B200KF_OK;
   }
+  cudaError_t terr = cudaSuccess;
   if (flags & B200KF_RUN_FORCE_DECOUPLED) {
     p.dense_flag = nullptr;
+    if (try_launch_tma<MODEL, real>(m, p, full, st, terr)) {
+      B200KF_CUDA_TRY(terr);
+      return B200KF_OK;
+    }
     B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
     return B200KF_OK;
   }
@@ -212,7 +448,11 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
           static_cast<const real*>(p.P), p.n_filters, flag);
   B200KF_CUDA_TRY(cudaGetLastError());
   p.dense_flag = flag;
-  B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
+  if (try_launch_tma<MODEL, real>(m, p, full, st, terr)) {
+    B200KF_CUDA_TRY(terr);
+  } else {
+    B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
+  }
   B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));
   return B200KF_OK;
 }

@@ -218,6 +218,102 @@ int launch_masked_m<B200KF_INST_MODEL>(const b200kf_model* m, const MaskedParams
   return B200KF_OK;
 }
 
+// ---- greedy one-per-window scheduling (kf_workers.py:877-947 + Scheduler :174-213) -------------
+// Thread <-> instance (processing period, P0).  The selection never reads a measurement: gain()
+// uses only row 1 of (H, R) -- state 0 for both sensors -- so per window there are two candidate
+// gains, trace(P) - sum_i P[i][0]^2 / (P[0][0] + r_type), and greedy_schedule keeps the FIRST
+// queue entry that attains the maximum (strict '>' at :205).  The thread walks the event list
+// once, emitting the selected event index per window and advancing P through predict + update.
+template <int MODEL, bool DENSE>
+__global__ void select_greedy_kernel(const SelectParams p) {
+  using MT = ModelTraits<MODEL, DENSE, double>;
+  constexpr int n = MT::n;
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= p.n_inst) return;
+  typename MT::Filter flt;
+  flt.each([&](auto& b) { b.load_cov(p.P0 + static_cast<long long>(inst) * n * n, n); });
+  const double period = p.periods[inst];
+  double prev = p.t_prev[inst];
+  int* sel = p.sel + static_cast<long long>(inst) * p.max_sel;
+  long long ns = 0;
+  long long first_gps = -1, first_imu = -1, q_first = -1;  // queue summary
+  for (long long e = 0; e < p.n_events; ++e) {
+    const double t = p.times[e];
+    const int ty = p.types[e];
+    if (t - prev < period) {  // :880-882
+      if (q_first < 0) q_first = e;
+      if (ty == EV_GPS) { if (first_gps < 0) first_gps = e; }
+      else { if (first_imu < 0) first_imu = e; }
+      continue;
+    }
+    if (q_first < 0) {  // empty queue: the triggering event is the only candidate (:884-886)
+      q_first = e;
+      if (ty == EV_GPS) first_gps = e; else first_imu = e;
+    }
+    // gains of the two sensor types for the current P (Scheduler.gain, :174-185)
+    double tr = 0.0, col2 = 0.0, p00 = 0.0;
+    flt.each([&](const auto& b) {
+      using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+      static_for<0, BT::n>([&](auto I) {
+        constexpr int i = I;
+        tr += b.P[BT::pidx(i, i)];
+        static_for<0, BT::n>([&](auto J) {
+          constexpr int j = J;
+          if constexpr (BT::gidx(j) == 0) {
+            col2 += b.P[BT::pidx(i, j)] * b.P[BT::pidx(i, j)];
+            if constexpr (i == j) p00 = b.P[BT::pidx(i, i)];
+          }
+        });
+      });
+    });
+    const double gain_gps = tr - col2 / (p00 + p.mc.r_gps[0]);
+    const double gain_imu = tr - col2 / (p00 + p.mc.r_imu[0]);
+    long long pick;
+    if (first_gps < 0) pick = first_imu;
+    else if (first_imu < 0) pick = first_gps;
+    else {
+      // both present: the first entry attaining the max; on equal gains the earlier entry
+      const long long a = first_gps < first_imu ? first_gps : first_imu;
+      const double ga = (a == first_gps) ? gain_gps : gain_imu;
+      const double gb = (a == first_gps) ? gain_imu : gain_gps;
+      const long long bsel = (a == first_gps) ? first_imu : first_gps;
+      pick = (gb > ga) ? bsel : a;
+    }
+    const double ts = p.times[pick];
+    const int tys = p.types[pick];
+    const double dt = ts - prev;  // :914
+    filter_predict<false>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
+    filter_update<false>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
+    prev = ts;
+    if (ns < p.max_sel) sel[ns] = static_cast<int>(pick);
+    ns += 1;
+    first_gps = first_imu = q_first = -1;
+  }
+  p.n_sel[inst] = ns;
+  if (p.P_final != nullptr) {
+    double* Pg = p.P_final + static_cast<long long>(inst) * n * n;
+    if constexpr (!DENSE) {
+      for (int e = 0; e < n * n; ++e) Pg[e] = 0.0;
+    }
+    double xs[n];
+    flt.each([&](const auto& b) { b.store(xs, Pg, n); });
+  }
+}
+
+template <>
+int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams& p, unsigned flags,
+                                       cudaStream_t st) {
+  (void)m;
+  const int tpb = 32;
+  const unsigned blocks = static_cast<unsigned>((p.n_inst + tpb - 1) / tpb);
+  if (flags & B200KF_RUN_FORCE_DECOUPLED)
+    select_greedy_kernel<B200KF_INST_MODEL, false><<<blocks, tpb, 0, st>>>(p);
+  else  // P0 lives on the device: the dense form is always valid
+    select_greedy_kernel<B200KF_INST_MODEL, true><<<blocks, tpb, 0, st>>>(p);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
+}
+
 template <>
 int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsigned flags,
                                       b200kf_best* best, cudaStream_t st) {

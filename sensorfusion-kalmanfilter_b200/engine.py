@@ -222,6 +222,33 @@ class Engine:
         return {"x_final": x_f, "P_final": P_f, "traj": traj, "logdet": ld, "n_terms": nt}
 
 
+    def select_greedy(self, types, times, periods, t_prev, P0, *, max_sel=None, mode="auto", stream=None):
+        """Greedy one-event-per-window selection (b200kf_select_greedy) for I instances over one
+        event list.  Returns (list of int32 numpy index arrays, P_final torch [I,n,n])."""
+        torch = _torch()
+        sp = self.spec
+        types_d = self._dev(types, torch.uint8)
+        times_d = self._dev(times, torch.float64)
+        E = int(types_d.numel())
+        per_d = self._dev(np.atleast_1d(periods), torch.float64)
+        tp_d = self._dev(np.atleast_1d(t_prev), torch.float64)
+        I = int(per_d.numel())
+        P0_d = self._dev(np.asarray(P0, dtype=np.float64).reshape(I, sp.n, sp.n), torch.float64)
+        if max_sel is None:
+            max_sel = E
+        max_sel = max(1, int(max_sel))
+        sel = torch.empty((I, max_sel), dtype=torch.int32, device=self.device)
+        n_sel = torch.zeros((I,), dtype=torch.int64, device=self.device)
+        P_f = torch.empty((I, sp.n, sp.n), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_select_greedy(
+                self._h, E, _ptr(types_d), _ptr(times_d), I, _ptr(per_d), _ptr(tp_d), _ptr(P0_d), max_sel,
+                _ptr(sel), _ptr(n_sel), _ptr(P_f), _MODES[mode], self._stream(stream)))
+        ns = n_sel.cpu().numpy()
+        sel_h = sel.cpu().numpy()
+        return [sel_h[i, :min(int(ns[i]), max_sel)].copy() for i in range(I)], P_f
+
+
 def cov_update(Sigma, rows, H, R, device=None, stream=None):
     """Batched Scheduler.cov_matrix (b200kf_cov_update).  Sigma [B, n, n] (numpy or torch), rows:
     0-based selected rows of (H, R).  Returns (Sigma_post [B,n,n], trace [B]) torch CUDA f64."""

@@ -169,3 +169,30 @@ def test_ragged_and_empty_inputs():
     assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
     with pytest.raises(ValueError):
         eng.run_batch(types, dts, payload[:, :2], x0, P0)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_tma_staged_kernel_matches_ldg_kernel_and_oracle(precision, monkeypatch):
+    """The aggregate-mode CV6 launch uses the TMA-staged persistent kernel (cp.async.bulk + mbarrier
+    ring); B200KF_TMA=0 selects the plain LDG kernel.  Same inputs -> same results, both = oracle.
+    N spans 3 CTAs with a partial last one, T is odd (tail chunk)."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 2000, 101
+    m, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=17)
+    monkeypatch.setenv("B200KF_TMA", "1")
+    tma = Engine("CV6", precision=precision).run_batch(types, dts, payload, x0, P0)
+    monkeypatch.setenv("B200KF_TMA", "0")
+    ldg = Engine("CV6", precision=precision).run_batch(types, dts, payload, x0, P0)
+    for k in ("x", "P", "agg"):
+        np.testing.assert_array_equal(tma[k].cpu().numpy(), ldg[k].cpu().numpy())
+    assert int(tma["status"].sum()) == 0
+    ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
+    tol = RTOL64 if precision == "f64" else RTOL32
+    assert rel(tma["x"].cpu().numpy(), ref["x"]) < tol
+    assert rel(tma["P"].cpu().numpy(), ref["P"]) < tol
+    a = tma["agg"].cpu().numpy()
+    assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < tol
+    # odd filter count cannot use 16-byte bulk rows: falls back to the LDG kernel, same answer
+    monkeypatch.setenv("B200KF_TMA", "1")
+    odd = Engine("CV6", precision=precision).run_batch(types, dts, payload[:, :, :1999], x0[:1999], P0[:1999])
+    np.testing.assert_array_equal(odd["P"].cpu().numpy(), tma["P"].cpu().numpy()[:1999])
