@@ -110,6 +110,7 @@ int b200kf_model_dims(const b200kf_model* model, int32_t* n, int32_t* d, int32_t
  *   agg     DEVICE f64 [N, 4]     nullable; (max, sum, last) of log det P over the steps and the
  *                                 step count; with B200KF_RUN_AGG_CONTINUE max/sum/count continue
  *   traj    DEVICE real[T, traj_ncomp, N]  nullable; x[0:traj_ncomp] after each step (:714)
+ *   ptraj   DEVICE real[T, n*n, N] nullable; full covariance after each step (:822, legacy loop)
  *   logdet  DEVICE real[T, N]     nullable; log det P after each step (:716-717)
  *   used    DEVICE u8  [T, N]     nullable; 1 where the update ran (adaptive gate, :1025-1027)
  *   status  DEVICE i32 [N]        nullable; 0 ok, 1 = a non-positive determinant was seen
@@ -117,8 +118,9 @@ int b200kf_model_dims(const b200kf_model* model, int32_t* n, int32_t* d, int32_t
  */
 int b200kf_run_batch(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
                      const uint8_t* types, const double* dts, const void* payload, void* x, void* P,
-                     double* agg, void* traj, int32_t traj_ncomp, void* logdet, uint8_t* used,
-                     int32_t* status, double gate_threshold, uint32_t flags, void* stream);
+                     double* agg, void* traj, int32_t traj_ncomp, void* ptraj, void* logdet,
+                     uint8_t* used, int32_t* status, double gate_threshold, uint32_t flags,
+                     void* stream);
 
 /* Same computation from HOST buffers (the call a drop-in user makes): streams `payload` to the
  * device in time chunks, overlapping host->device copies with the kernel, and copies x, P, agg

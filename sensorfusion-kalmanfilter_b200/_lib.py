@@ -12,7 +12,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_int, c_int3
                     c_uint8, c_uint32, c_uint64, c_void_p)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libb200kf.so")
+LIB_PATH = os.environ.get("B200KF_LIB") or os.path.join(PKG_DIR, "libb200kf.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 MODEL_CV6, MODEL_CA8, MODEL_BIAS9, MODEL_CA15 = 0, 1, 2, 3
@@ -48,7 +48,7 @@ SIGNATURES = {
     "b200kf_model_destroy": (c_int, [c_void_p]),
     "b200kf_model_dims": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "b200kf_run_batch": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_double, c_uint32, c_void_p]),
     "b200kf_run_batch_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_uint32]),

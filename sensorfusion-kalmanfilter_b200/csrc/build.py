@@ -18,11 +18,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(PKG, "libb200kf.so")
+# B200KF_VARIANT=<tag> + B200KF_EXTRA_FLAGS="-D..." build an experimental libb200kf_<tag>.so beside the
+# default library (select it at run time with B200KF_LIB); used for A/B timing on the GPU box.
+VARIANT = os.environ.get("B200KF_VARIANT", "")
+EXTRA = os.environ.get("B200KF_EXTRA_FLAGS", "").split()
+LIB = os.path.join(PKG, f"libb200kf_{VARIANT}.so" if VARIANT else "libb200kf.so")
+if VARIANT:
+    BUILD = os.path.join(HERE, "build_" + VARIANT)
 NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-lineinfo", "-Xcompiler", "-fPIC",
-          "-Xptxas", "-v"] + ARCH
+          "-Xptxas", "-v"] + ARCH + EXTRA
 MODELS = (0, 1, 2, 3)
 HEADERS = ["kf_core.cuh", "kf_internal.h", os.path.join(ROOT, "include", "b200kf.h")]
 

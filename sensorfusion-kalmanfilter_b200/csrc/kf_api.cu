@@ -423,8 +423,8 @@ int b200kf_model_dims(const b200kf_model* m, int32_t* n, int32_t* d, int32_t* m_
 
 int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const uint8_t* types,
                      const double* dts, const void* payload, void* x, void* P, double* agg,
-                     void* traj, int32_t traj_ncomp, void* logdet, uint8_t* used, int32_t* status,
-                     double gate_threshold, uint32_t flags, void* stream) {
+                     void* traj, int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used,
+                     int32_t* status, double gate_threshold, uint32_t flags, void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
   if (n_filters < 0 || n_steps < 0) return set_error(B200KF_ERR_INVALID, "negative size");
   if (n_steps > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_steps > 2^31-1 per call");
@@ -448,6 +448,7 @@ int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
   p.agg = agg;
   p.traj = traj;
   p.traj_ncomp = traj ? traj_ncomp : 0;
+  p.ptraj = ptraj;
   p.logdet = logdet;
   p.used = used;
   p.status = status;
@@ -525,7 +526,7 @@ int b200kf_run_batch_host(const b200kf_model* m, int64_t n_filters, int64_t n_st
       }
       const uint32_t f = (flags & ~B200KF_RUN_AGG_CONTINUE) | (c > 0 ? B200KF_RUN_AGG_CONTINUE : 0u);
       rc = b200kf_run_batch(m, n_filters, steps, d_types + k0, d_dts + k0, d_pay[b], d_x, d_P, d_agg,
-                            nullptr, 0, nullptr, nullptr, d_status, NAN, f, s_comp);
+                            nullptr, 0, nullptr, nullptr, nullptr, d_status, NAN, f, s_comp);
       if (rc != B200KF_OK) goto done;
       HOST_TRY(cudaEventRecord(ev_done[b], s_comp));
       if (n_steps == 0) break;

@@ -482,24 +482,32 @@ __device__ __forceinline__ double fast_rcp(double a) {  // a normal and > 0; ~1 
 }
 __device__ __forceinline__ float fast_rcp(float a) { return 1.0f / a; }
 
+// inv[i] = 1 / d[i] from ONE reciprocal; returns 1 / prod(d)
 template <int K>
-__device__ __forceinline__ void rcp_batch(const double (&d)[K], double (&inv)[K]) {
+__device__ __forceinline__ double rcp_batch(const double (&d)[K], double (&inv)[K]) {
   double pre[K];
   pre[0] = d[0];
 #pragma unroll
   for (int i = 1; i < K; ++i) pre[i] = pre[i - 1] * d[i];
-  double r = fast_rcp(pre[K - 1]);
+  const double rall = fast_rcp(pre[K - 1]);
+  double r = rall;
 #pragma unroll
   for (int i = K - 1; i > 0; --i) {
     inv[i] = r * pre[i - 1];
     r = r * d[i];
   }
   inv[0] = r;
+  return rall;
 }
 template <int K>
-__device__ __forceinline__ void rcp_batch(const float (&d)[K], float (&inv)[K]) {
+__device__ __forceinline__ double rcp_batch(const float (&d)[K], float (&inv)[K]) {
+  double rall = 1.0;
 #pragma unroll
-  for (int i = 0; i < K; ++i) inv[i] = 1.0f / d[i];
+  for (int i = 0; i < K; ++i) {
+    inv[i] = 1.0f / d[i];
+    rall *= double(inv[i]);
+  }
+  return rall;
 }
 
 template <typename real>
@@ -531,12 +539,12 @@ __device__ __forceinline__ real pv2_imu_begin(const BlockKF<B, real>& k, const M
 }
 
 template <bool WITH_STATE, class B, typename real>
-__device__ __forceinline__ real pv2_imu_finish(BlockKF<B, real>& k, real dt, const ModelConst& mc,
+__device__ __forceinline__ void pv2_imu_finish(BlockKF<B, real>& k, real dt, const ModelConst& mc,
                                                const real* u, real inv, const Upd2<real>& w) {
-  const real b = k.P[1];
   const real r0 = real(mc.r_imu[B::gidx(0)]), r1 = real(mc.r_imu[B::gidx(1)]);
-  const real g0 = r0 * inv, g1 = r1 * inv;
-  const real k01 = g0 * b, k10 = g1 * b;
+  const real bi = k.P[1] * inv;
+  const real k00 = w.t0 * inv, k11 = w.t1 * inv;  // K = P S^-1 = P+ R^-1
+  const real k01 = bi * r0, k10 = bi * r1;
   if constexpr (WITH_STATE) {
     // innovation y = z - x with z built from the predicted state (kf_workers.py:698-709)
     real y0, y1;
@@ -544,14 +552,12 @@ __device__ __forceinline__ real pv2_imu_finish(BlockKF<B, real>& k, real dt, con
     else y1 = u[B::pz(1)] - k.x[1];
     if constexpr (B::zk(0) == ZK_POS) y0 = (k.x[1] + u[B::pz(0)] * dt) * dt;
     else y0 = u[B::pz(0)] - k.x[0];
-    const real k00 = w.t0 * inv, k11 = w.t1 * inv;
     k.x[0] = fma(k00, y0, fma(k01, y1, k.x[0]));
     k.x[1] = fma(k10, y0, fma(k11, y1, k.x[1]));
   }
-  k.P[0] = g0 * w.t0;
+  k.P[0] = k00 * r0;
   k.P[1] = k01 * r1;
-  k.P[2] = g1 * w.t1;
-  return (g0 * r1) * w.detp;  // det P+
+  k.P[2] = k11 * r1;
 }
 
 // GPS event on a chain whose state 0 is measured (variance r): scalar update, reciprocal shared.
@@ -577,28 +583,41 @@ __device__ __forceinline__ void fast2_predict(FilterT<real, IMU_CONTROL, Bs...>&
   f.each([&](auto& blk) { pv2_predict<WITH_STATE>(blk, dt, mc); });
 }
 
+// prod over chains of r0 * r1: det P+ = rprod * prod(det P-) / prod(det S) on an IMU event
+template <typename real, bool IMU_CONTROL, class... Bs>
+__device__ __forceinline__ double fast2_rprod(const FilterT<real, IMU_CONTROL, Bs...>& f, const ModelConst& mc) {
+  double r = 1.0;
+  f.each([&](const auto& blk) {
+    using BT = std::remove_cv_t<std::remove_reference_t<decltype(blk)>>;
+    r *= mc.r_imu[BT::gidx(0)] * mc.r_imu[BT::gidx(1)];
+  });
+  return r;
+}
+
 // Update every chain for an event of type etype; returns det P+ (product over chains).
 template <bool WITH_STATE, typename real, bool IMU_CONTROL, class... Bs>
 __device__ __forceinline__ double fast2_update(FilterT<real, IMU_CONTROL, Bs...>& f, real dt,
-                                               const ModelConst& mc, int etype, const real* u, bool& ok) {
+                                               const ModelConst& mc, int etype, const real* u, double rprod,
+                                               bool& ok) {
   constexpr int NB = FilterT<real, IMU_CONTROL, Bs...>::nblocks;
   real den[NB], inv[NB];
-  double det = 1.0;
   if (etype == EV_IMU) {
     Upd2<real> w[NB];
+    double detp = 1.0;
     int i = 0;
     f.each([&](auto& blk) {
       den[i] = pv2_imu_begin(blk, mc, w[i]);
+      detp *= double(w[i].detp);
       ++i;
     });
-    rcp_batch<NB>(den, inv);
+    const double rall = rcp_batch<NB>(den, inv);
     i = 0;
     f.each([&](auto& blk) {
-      const real d = pv2_imu_finish<WITH_STATE>(blk, dt, mc, u, inv[i], w[i]);
-      ok = ok && (d > real(0));
-      det *= double(d);
+      pv2_imu_finish<WITH_STATE>(blk, dt, mc, u, inv[i], w[i]);
       ++i;
     });
+    const double det = detp * (rall * rprod);
+    ok = ok && (det > 0.0);
     return det;
   }
   if (etype == EV_GPS) {

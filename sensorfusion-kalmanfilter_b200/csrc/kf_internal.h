@@ -48,6 +48,7 @@ struct RunParams {
   double* agg;
   void* traj;
   int traj_ncomp;
+  void* ptraj;  // [T, n*n, N] covariance after every step, or null
   void* logdet;
   uint8_t* used;
   int* status;

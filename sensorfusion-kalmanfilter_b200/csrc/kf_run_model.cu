@@ -50,9 +50,12 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
     flt.each([&](auto& b) { b.load(xg, Pg, n); });
   }
 
+  double rprod = 1.0;
+  if constexpr (FAST) rprod = fast2_rprod(flt, p.mc);
   // lean running aggregate: mantissa product + exponent sum + max; "last" is recomputed from the
   // final P and the count is T, which keeps the hot loop inside the 72-register budget
-  double acc_mant = 1.0, acc_max = 0.0;
+  double acc_mant = 1.0;
+  long long acc_max = 0;  // max det as raw bits: positive doubles order like their bit patterns
   int acc_expo = 0;
   bool ok = true;
 
@@ -94,13 +97,13 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
         }
         double det;
         if constexpr (FAST) {
-          det = do_update ? fast2_update<true>(flt, dt, p.mc, ty, u, ok) : filter_det(flt, ok);
+          det = do_update ? fast2_update<true>(flt, dt, p.mc, ty, u, rprod, ok) : filter_det(flt, ok);
         } else {
           if (do_update) filter_update<true>(flt, dt, p.mc, ty, u);
           det = filter_det(flt, ok);
         }
         {
-          acc_max = fmax(acc_max, det);
+          acc_max = max(acc_max, __double_as_longlong(det));
           const double m = acc_mant * det;
           const int hi = __double2hiint(m);
           const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -121,6 +124,22 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
               });
             });
           }
+          if (p.ptraj != nullptr) {  // sf_KF_covariance.append(Pt.copy()), kf_workers.py:822
+            real* pt = static_cast<real*>(p.ptraj) + (static_cast<long long>(k) * (n * n)) * N + f;
+            if constexpr (!DENSE) {
+              for (int e = 0; e < n * n; ++e) pt[static_cast<long long>(e) * N] = real(0);
+            }
+            flt.each([&](const auto& b) {
+              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+              static_for<0, BT::n>([&](auto I) {
+                constexpr int i = I;
+                static_for<0, BT::n>([&](auto J) {
+                  constexpr int j = J;
+                  pt[static_cast<long long>(BT::gidx(i) * n + BT::gidx(j)) * N] = b.P[BT::pidx(i, j)];
+                });
+              });
+            });
+          }
           if (p.logdet != nullptr)
             __stcs(static_cast<real*>(p.logdet) + static_cast<long long>(k) * N + f,
                    static_cast<real>(log(det)));
@@ -138,7 +157,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
   }
   if (p.agg != nullptr) {
     double* a = p.agg + f * 4;
-    double mx = (T > 0) ? log(acc_max) : -INFINITY;
+    double mx = (T > 0) ? log(__longlong_as_double(acc_max)) : -INFINITY;
     double sm = log(acc_mant) + static_cast<double>(acc_expo) * 0.6931471805599453094;
     double cnt = static_cast<double>(T);
     if (p.agg_continue) {
@@ -171,8 +190,14 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
 // half empty at the end).
 // ------------------------------------------------------------------------------------------
 constexpr int kTmaThreads = 896;  // 7 warps per SM sub-partition; 896 * 72 regs = 63 K registers
-constexpr int kChunk = 2;         // steps per stage
-constexpr int kStages = 4;
+#ifndef B200KF_CHUNK
+#define B200KF_CHUNK 2
+#endif
+#ifndef B200KF_STAGES
+#define B200KF_STAGES 4
+#endif
+constexpr int kChunk = B200KF_CHUNK;    // steps per stage
+constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 KB of shared memory)
 
 struct SchedRec {  // 16 bytes: bulk copies need 16-byte granularity
   double dt;
@@ -279,7 +304,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const real* Pg = static_cast<const real*>(p.P) + f * (n * n);
     flt.each([&](auto& b) { b.load(xg, Pg, n); });
   }
-  double acc_mant = 1.0, acc_max = 0.0;
+  const double rprod = fast2_rprod(flt, p.mc);
+  double acc_mant = 1.0;
+  long long acc_max = 0;  // max det as raw bits: positive doubles order like their bit patterns
   int acc_expo = 0;
   bool ok = true;
 
@@ -308,9 +335,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           const real dt = static_cast<real>(rec.dt);
           const int ty = rec.type;
           fast2_predict<true>(flt, dt, p.mc);
-          const double det = (ty != EV_PREDICT_ONLY) ? fast2_update<true>(flt, dt, p.mc, ty, u, ok)
+          const double det = (ty != EV_PREDICT_ONLY) ? fast2_update<true>(flt, dt, p.mc, ty, u, rprod, ok)
                                                      : filter_det(flt, ok);
-          acc_max = fmax(acc_max, det);
+          acc_max = max(acc_max, __double_as_longlong(det));
           const double m = acc_mant * det;
           const int hi = __double2hiint(m);
           const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -331,7 +358,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   if (p.agg != nullptr) {
     double* a = p.agg + f * 4;
-    double mx = (T > 0) ? log(acc_max) : -INFINITY;
+    double mx = (T > 0) ? log(__longlong_as_double(acc_max)) : -INFINITY;
     double sm = log(acc_mant) + static_cast<double>(acc_expo) * 0.6931471805599453094;
     double cnt = static_cast<double>(T);
     if (p.agg_continue) {
@@ -422,7 +449,7 @@ static cudaError_t launch_variant(const b200kf_model* m, const RunParams& p, boo
 
 template <int MODEL, typename real>
 static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, cudaStream_t st) {
-  const bool full = p.traj != nullptr || p.logdet != nullptr || p.used != nullptr || p.gate_enabled;
+  const bool full = p.traj != nullptr || p.ptraj != nullptr || p.logdet != nullptr || p.used != nullptr || p.gate_enabled;
   if (flags & B200KF_RUN_FORCE_DENSE) {
     p.dense_flag = nullptr;
     B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));

@@ -76,8 +76,8 @@ class Engine:
 
     # ------------------------------------------------------------------ filter loop
     def run_batch(self, types, dts, payload, x, P, *, want_agg=True, traj_ncomp=0, want_logdet=False,
-                  want_used=False, gate_threshold=None, mode="auto", agg=None, stream=None,
-                  inplace=False):
+                  want_used=False, want_ptraj=False, gate_threshold=None, mode="auto", agg=None,
+                  stream=None, inplace=False):
         """Run N filters over a shared schedule (b200kf_run_batch).
 
         types [T] u8, dts [T] f64, payload [T, d, N], x [N, n], P [N, n, n]; numpy arrays or torch
@@ -114,15 +114,16 @@ class Engine:
         traj_d = torch.empty((T, traj_ncomp, N), dtype=self.real, device=self.device) if traj_ncomp else None
         ld_d = torch.empty((T, N), dtype=self.real, device=self.device) if want_logdet else None
         used_d = torch.empty((T, N), dtype=torch.uint8, device=self.device) if want_used else None
+        ptraj_d = torch.empty((T, sp.n * sp.n, N), dtype=self.real, device=self.device) if want_ptraj else None
         status_d = torch.zeros((N,), dtype=torch.int32, device=self.device)
         gate = float("nan") if gate_threshold is None else float(gate_threshold)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200kf_run_batch(
                 self._h, N, T, _ptr(types_d), _ptr(dts_d), _ptr(pay_d), _ptr(x_d), _ptr(P_d), _ptr(agg_d),
-                _ptr(traj_d), int(traj_ncomp), _ptr(ld_d), _ptr(used_d), _ptr(status_d), gate, flags,
+                _ptr(traj_d), int(traj_ncomp), _ptr(ptraj_d), _ptr(ld_d), _ptr(used_d), _ptr(status_d), gate, flags,
                 self._stream(stream)))
         return {"x": x_d, "P": P_d, "agg": agg_d, "traj": traj_d, "logdet": ld_d, "used": used_d,
-                "status": status_d}
+                "ptraj": ptraj_d, "status": status_d}
 
     def run_batch_host(self, types, dts, payload, x, P, *, chunk_steps=0, mode="auto"):
         """Host-buffer path (b200kf_run_batch_host): numpy (or pinned torch CPU) arrays in, numpy

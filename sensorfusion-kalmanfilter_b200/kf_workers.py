@@ -1,0 +1,593 @@
+"""Drop-in mirror of the reference's `kf_workers.py` call surface on the B200 engine.
+
+Same names, arguments and return structures as IseanB/SensorFusion-KalmanFilter `kf_workers.py`
+(`KF_SensorFusion`, `Scheduler`, `evaluate_combo_chunk_worker`), so the reference's drivers
+(kf_workers.py:2251-2396) run unchanged after `import sensorfusion_kalmanfilter_b200.kf_workers as
+kf_workers`.  Every filter step, log det, schedule score and cov_matrix runs in the CUDA kernels of
+libb200kf.so; this module only does what the reference also does on the host before/after the
+loop: pick the start event, compute `dt = t - prev` in float64, and re-shape results into the
+reference's lists of tuples.  There is no CPU fallback: without the library or a GPU the run_*
+methods raise.
+
+Where the reference's loops are reproduced, the line they follow is cited.  Out of scope (SURVEY.md
+section 2): plotting/animation, KalmanFilterLogger, the rosbag extractor, lat/lon -> UTM (needs the
+third-party `utm`; feed eastings/northings through `utm_data` / `indexed_sensor_data` directly).
+"""
+from __future__ import annotations
+
+import csv
+import math
+from itertools import combinations
+
+import numpy as np
+
+from . import streams
+from .engine import Engine, cov_update
+from .models import DIMS, spec_from_getters
+
+_NAME_BY_N = {n: name for name, (n, _, _) in DIMS.items()}
+_engines = {}
+
+
+def _engine_for(getters_obj, name):
+    """Engine for the model the getters describe (cached per distinct constants)."""
+    spec = spec_from_getters(getters_obj, name)
+    key = (name, spec.q.tobytes(), spec.r_gps.tobytes(), spec.r_imu.tobytes(), spec.accel_coef)
+    eng = _engines.get(key)
+    if eng is None:
+        eng = Engine(spec)
+        _engines[key] = eng
+    return eng
+
+
+def _slogdet_signed(P):
+    s, l = np.linalg.slogdet(P)  # term 0 is a property of the INPUT matrix (kf_workers.py:32, :675)
+    return s * l
+
+
+class _Getters:
+    """Adapter: the `class_args` dict of bound methods (kf_workers.py:1242-1251) as an object."""
+
+    def __init__(self, class_args):
+        for k, v in class_args.items():
+            if callable(v):
+                setattr(self, k, v)
+
+
+# ------------------------------------------------------------------------------------------
+# evaluate_combo_chunk_worker (kf_workers.py:22-97)
+# ------------------------------------------------------------------------------------------
+def evaluate_combo_chunk_worker(chunk, xt, Pt, class_args, prev_time, target_end_time):
+    """Per combo: the full filter over its events (gaps merged into one predict, :37), the log-det
+    trace, and the final propagation to target_end_time (:74-82).  Returns the reference's list of
+    `(0, traj, combo, x_final, None, log_det, len(combo))` (:86).
+
+    All combos of the chunk run as one batch of b200kf_run_masked: they must be time-ordered
+    subsets of one window of at most 64 distinct events (what the reference's driver produces,
+    :1330); anything else raises NotImplementedError rather than being computed elsewhere."""
+    chunk = list(chunk)
+    if not chunk:
+        return []
+    g = _Getters(class_args)
+    n = int(np.asarray(g.get_imu_observation_matrix()).shape[0])
+    name = _NAME_BY_N.get(n)
+    if name is None:
+        raise NotImplementedError(f"no compiled model with {n} states")
+    eng = _engine_for(g, name)
+    # the shared window: distinct events of the chunk, in time order
+    seen = {}
+    for combo in chunk:
+        for ev in combo:
+            seen.setdefault(ev[0], ev)
+    window = sorted(seen.values(), key=lambda e: (e[2], e[0]))
+    if len(window) > 64:
+        raise NotImplementedError("combos of one chunk must come from a window of <= 64 events")
+    pos = {ev[0]: i for i, ev in enumerate(window)}
+    masks = []
+    for combo in chunk:
+        last, m = -1, 0
+        for ev in combo:
+            i = pos[ev[0]]
+            if i <= last:
+                raise NotImplementedError("each combo must list its events in time order")
+            last = i
+            m |= 1 << i
+        masks.append(m)
+    ps = streams.PackedStream.from_events(window)
+    out = eng.run_masked(ps.types, ps.times, ps.payload(name), prev_time, target_end_time,
+                         np.asarray(xt, dtype=np.float64), np.asarray(Pt, dtype=np.float64), masks,
+                         traj_ncomp=min(6, n))
+    xf = out["x_final"].cpu().numpy()
+    traj = out["traj"].cpu().numpy()
+    ld = out["logdet"].cpu().numpy()
+    nt = out["n_terms"].cpu().numpy()
+    ld0 = _slogdet_signed(np.asarray(Pt, dtype=np.float64))
+    results = []
+    for r, combo in enumerate(chunk):
+        k = abs(int(nt[r]))
+        tr = [(float(row[0]), *row[1:]) for row in traj[r, :k]]
+        tr[0] = (prev_time, *np.asarray(xt, dtype=np.float64)[:6])
+        lds = [ld0] + [v for v in ld[r, 1:k]]
+        results.append((0, tr, combo, xf[r].copy(), None, lds, len(combo)))
+    return results
+
+
+# ------------------------------------------------------------------------------------------
+# Scheduler (kf_workers.py:99-233)
+# ------------------------------------------------------------------------------------------
+class Scheduler:
+    """Sensor scheduler.  `device` is accepted for signature compatibility; the posterior
+    covariance is always computed by the batched CUDA kernel (b200kf_cov_update) -- the reference's
+    own device='cuda' branch (:148-169) is the one place it already meant to use the GPU."""
+
+    def cov_matrix(_, S, Sigma_prev, R, H, device="cuda"):  # noqa: N805  (reference signature, :112)
+        assert type(S) == list, "S should be a list"
+        assert len(S) > 0, "S should not be empty"
+        assert type(Sigma_prev) == np.ndarray, "Sigma_prev should be a np.ndarray array"
+        assert type(R) == np.ndarray, "R should be a np.ndarray array"
+        assert type(H) == np.ndarray, "H should be a np.ndarray array"
+        rows = np.array(sorted(S), dtype=np.int32) - 1 if len(S) != R.shape[0] else np.arange(R.shape[0], dtype=np.int32)
+        post, _ = cov_update(Sigma_prev[None].astype(np.float64), rows, H.astype(np.float64), R.astype(np.float64))
+        return post[0].cpu().numpy()
+
+    def gain(self, measurement=None, S_sigma=None, measurement_cov=(tuple), observation_cov=(tuple), device="cuda"):
+        assert type(measurement) != list, "only have one measurement"
+        assert S_sigma is not None, "S_sigma should not be None"
+        if measurement is None or len(measurement) == 0:
+            return 0
+        kind = "GPS" if measurement[1] == "GPS" else "IMU"
+        if measurement[1] not in ("GPS", "IMU"):
+            return None
+        return np.trace(self.cov_matrix(S=[1], Sigma_prev=S_sigma, R=measurement_cov[kind],
+                                        H=observation_cov[kind], device=device))
+
+    def random_schedule(self, num_measurements=None):
+        assert num_measurements is not None, "measurements should not be None"
+        return np.random.choice(num_measurements)
+
+    def greedy_schedule(self, measurements=None, S_sigma=None, measurement_cov=None, observation_cov=None,
+                        device="cuda"):
+        """Index of the queue entry with the LARGEST posterior trace, first wins ties (:195-213).
+        The two candidate gains (one per sensor type) come from one batched kernel call each."""
+        assert measurements is not None
+        gains = {}
+        for kind in ("GPS", "IMU"):
+            if any(m[1] == kind for m in measurements):
+                _, tr = cov_update(np.asarray(S_sigma, dtype=np.float64)[None], np.array([0], dtype=np.int32),
+                                   np.asarray(observation_cov[kind], dtype=np.float64),
+                                   np.asarray(measurement_cov[kind], dtype=np.float64))
+                gains[kind] = float(tr[0].item())
+        best_gain, best = -np.inf, None
+        for i, m in enumerate(measurements):
+            gcur = gains[m[1]]
+            if gcur > best_gain:
+                best_gain, best = gcur, i
+        if best is None:
+            raise ValueError("None is not in list")  # what measurements.index(None) raises (:213)
+        return best
+
+    def randomized_greedy_schedule(self, total_num_sensors, device="cuda"):
+        return None
+
+
+# ------------------------------------------------------------------------------------------
+# KF_SensorFusion (kf_workers.py:277-1392)
+# ------------------------------------------------------------------------------------------
+class KF_SensorFusion:
+    MODEL_NAME = "CA15"
+
+    def __init__(self, gps_csv_file, imu_csv_file):
+        self.gps_csv_file = gps_csv_file
+        self.imu_csv_file = imu_csv_file
+        self.gps_data = []
+        self.imu_data = []
+        self.utm_data = []
+        self.scheduler = Scheduler()
+        self.processing_frequency = None
+
+    def set_processing_frequency(self, frequency):
+        self.processing_frequency = frequency
+
+    # ---- data preparation (host side, as the reference; kf_workers.py:290-425) -------------
+    def load_data_from_csv(self, filename, has_header=True):
+        data = []
+        with open(filename, newline="") as csvfile:
+            reader = csv.reader(csvfile)
+            if has_header:
+                next(reader)
+            for row in reader:
+                data.append(row)
+        return data
+
+    def load_data(self):
+        self.gps_data = self.load_data_from_csv(self.gps_csv_file)
+        self.imu_data = self.load_data_from_csv(self.imu_csv_file)
+
+    @staticmethod
+    def compute_imu_biases(gps_data, imu_data):
+        first_valid_index = next((i for i, entry in enumerate(gps_data) if "nan" not in entry[1].lower()), None)
+        if first_valid_index is None:
+            print("Warning: No valid GPS data found. Cannot compute IMU biases.")
+            return None, None
+        stationary = imu_data[:first_valid_index]
+        w = np.array([[float(e[5]), float(e[6]), float(e[7])] for e in stationary])
+        a = np.array([[float(e[8]), float(e[9]), float(e[10])] for e in stationary])
+        return np.mean(w, axis=0), np.mean(a, axis=0), first_valid_index
+
+    def quaternion_to_euler(self, x, y, z, w):
+        roll = np.arctan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
+        sinp = 2 * (w * y - z * x)
+        pitch = np.pi / 2 * np.sign(sinp) if abs(sinp) >= 1 else np.arcsin(sinp)
+        yaw = np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+        return roll, pitch, yaw
+
+    def unbias_imu_data(self, angular_velocity_bias, linear_acceleration_bias):
+        out = []
+        for entry in self.imu_data:
+            w = np.array([float(entry[5]), float(entry[6]), float(entry[7])]) - angular_velocity_bias
+            a = np.array([float(entry[8]), float(entry[9]), float(entry[10])]) - linear_acceleration_bias
+            roll, pitch, yaw = self.quaternion_to_euler(float(entry[1]), float(entry[2]), float(entry[3]),
+                                                        float(entry[4]))
+            out.append(entry[:1] + [roll, pitch, yaw] + w.tolist() + a.tolist() + entry[11:])
+        self.unbias_imu_data = out
+
+    def combine_sensor_data(self):
+        combined = [("GPS", float(g["time"]), g) for g in self.utm_data]
+        combined += [("IMU", float(e[0]), e) for e in self.unbias_imu_data]
+        combined.sort(key=lambda x: x[1])
+        self.indexed_sensor_data = [(i, *d) for i, d in enumerate(combined)]
+
+    # ---- the eight model getters (kf_workers.py:493-621); overriding them changes the GPU model
+    def get_state_transition_matrix(self, dt):
+        F = np.eye(15)
+        for ax in range(3):
+            F[ax, 6 + ax] = dt
+            F[ax, 12 + ax] = 0.5 * dt ** 2
+            F[3 + ax, 9 + ax] = dt
+            F[6 + ax, 12 + ax] = dt
+        return F
+
+    def get_process_noise_covariance_matrix(self, dt):
+        return np.diag([5 * dt] * 3 + [0.05 * dt] * 3 + [1 * dt] * 3 + [0.1 * dt] * 3 + [2 * dt] * 3)
+
+    def predict_covariance(self, Pt, F, Qt):
+        return np.dot(np.dot(F, Pt), F.T) + Qt
+
+    def get_gps_observation_matrix(self):
+        H = np.zeros((3, 15), dtype=np.int64)
+        H[0, 0] = H[1, 1] = H[2, 2] = 1
+        return H
+
+    def get_imu_observation_matrix(self):
+        return np.eye(15, dtype=np.int64)
+
+    def get_gps_measurement_noise_covariance_matrix(self):
+        return np.diag([3, 3, 3])
+
+    def get_imu_measurement_noise_covariance_matrix(self):
+        return np.diag([50] * 3 + [0.05] * 3 + [10] * 3 + [0.1] * 3 + [100] * 3)
+
+    def calculate_kalman_gain(self, P_next, H, R):
+        S = np.dot(np.dot(H, P_next), H.T) + R
+        return np.dot(np.dot(P_next, H.T), np.linalg.inv(S))
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _engine(self):
+        return _engine_for(self, self.MODEL_NAME)
+
+    def _default_P0(self):
+        return np.diag([10000] * 3 + [1000] * 3 + [1000] * 3 + [1000] * 3 + [10000] * 3)
+
+    def _clip(self, start_idx, end_idx):
+        if start_idx is None or start_idx < 0:
+            start_idx = 0
+            print("Overriding start_idx to 0.")
+        if end_idx is None or end_idx > len(self.indexed_sensor_data):
+            end_idx = len(self.indexed_sensor_data)
+            print("Overriding end_idx to the length of indexed_sensor_data.")
+        return start_idx, end_idx
+
+    def _first_gps(self, start_idx, stop):
+        """First-GPS initialisation (kf_workers.py:655-666): (x0, t0, absolute index) or None."""
+        xt = np.zeros(15)
+        for i, (_, stype, time, sdata) in enumerate(self.indexed_sensor_data[start_idx:stop]):
+            if stype == "GPS":
+                xt[0], xt[1], xt[2] = sdata["easting"], sdata["northing"], sdata["altitude"]
+                return xt, time, start_idx + i
+        return None
+
+    def _run(self, idx, dts, xt, Pt, *, types=None, gate=None, want_used=False, want_ptraj=False):
+        """Filter the events `idx` (absolute indices) with time steps `dts` on the GPU."""
+        ps = streams.pack_events(self.indexed_sensor_data)
+        eng = self._engine()
+        ty = ps.types[idx] if types is None else types
+        pay = ps.payload(self.MODEL_NAME, idx)
+        out = eng.run_batch(ty, dts, pay[:, :, None], np.asarray(xt, dtype=np.float64)[None],
+                            np.asarray(Pt, dtype=np.float64)[None], want_agg=False, traj_ncomp=6,
+                            want_logdet=True, want_used=want_used, want_ptraj=want_ptraj, gate_threshold=gate)
+        traj = out["traj"].cpu().numpy()[:, :, 0]
+        ld = out["logdet"].cpu().numpy()[:, 0]
+        times = ps.times[idx]
+        states = [(float(t), *row) for t, row in zip(times, traj)]
+        res = {"states": states, "logdet": [v for v in ld], "x": out["x"].cpu().numpy()[0],
+               "P": out["P"].cpu().numpy()[0], "times": times}
+        if want_used:
+            res["used"] = out["used"].cpu().numpy()[:, 0].astype(bool)
+        if want_ptraj:
+            res["ptraj"] = out["ptraj"].cpu().numpy()[:, :, 0].reshape(-1, 15, 15)
+        return res
+
+    # ---- run_kalman_filter_full (kf_workers.py:623-728) ----------------------------------------
+    def run_kalman_filter_full(self, start_idx=None, end_idx=None, initial_pt=None, initial_state=None,
+                               print_output=False):
+        if not hasattr(self, "indexed_sensor_data") or not self.indexed_sensor_data:
+            print("Sensor data has not been combined or is empty.")
+            return [], [], []
+        start_idx, end_idx = self._clip(start_idx, end_idx)
+        xt = np.zeros(15)
+        if initial_pt is not None and initial_state is not None:
+            Pt = np.asarray(initial_pt, dtype=np.float64)
+            xt[0:6] = initial_state[1:7]
+            prev_time = initial_state[0]
+            first = start_idx
+        else:
+            Pt = self._default_P0().astype(np.float64)
+            init = self._first_gps(start_idx, end_idx + 1)
+            if init is None:
+                print("No GPS data found to initialize the filter.")
+                return [], [], []
+            xt, prev_time, first = init
+        states = [(prev_time, *xt[:6])]
+        logdets = [np.linalg.slogdet(Pt)[1]]
+        ps = streams.pack_events(self.indexed_sensor_data)
+        keep, dts, prev_out = streams.schedule_dts(ps.times[first:end_idx], prev_time, skip_advances_prev=True)
+        if len(keep):
+            r = self._run(first + keep, dts, xt, Pt)
+            states += r["states"]
+            logdets += r["logdet"]
+            Pt = r["P"]
+        self._ground_truth = states
+        self._ground_truth_cov = None  # write-only in the reference (:724); not materialised
+        if print_output:
+            print("---------------------------- Full Kalman Filter ----------------------------\n"
+                  f" Processed {len(keep)} measurements out of {end_idx - first} in total, from index {first} to {end_idx}")
+        return states, logdets, Pt, prev_out
+
+    def get_GT(self):
+        if hasattr(self, "_ground_truth"):
+            return self._ground_truth
+        print("Ground truth not computed yet. Please run run_kalman_filter_full() first.")
+        return None
+
+    # ---- run_kalman_filter (legacy, kf_workers.py:738-824) -------------------------------------
+    def run_kalman_filter(self, start_idx, end_idx):
+        xt = np.zeros(15)
+        Pt = self._default_P0().astype(np.float64)
+        states = [(0, xt[0], xt[1], xt[2], xt[3], xt[4], xt[5])]
+        covs = [Pt.copy()]
+        ev = self.indexed_sensor_data[start_idx:end_idx]
+        first = next((i for i, e in enumerate(ev) if e[1] == "GPS"), None)
+        if first is None:
+            return states, covs
+        ps = streams.pack_events(self.indexed_sensor_data)
+        lo = (start_idx if start_idx >= 0 else len(self.indexed_sensor_data) + start_idx) + first
+        idx = np.arange(lo, lo + len(ev) - first)
+        times = ps.times[idx]
+        dts = np.diff(times, prepend=times[0])  # first GPS: dt = 0 (:771-775); no dt<0 rule here
+        r = self._run(idx, dts, xt, Pt, want_ptraj=True)
+        states += r["states"]
+        covs += [P for P in r["ptraj"]]
+        return states, covs
+
+    # ---- run_kalman_filter_scheduled (kf_workers.py:826-957) -----------------------------------
+    def run_kalman_filter_scheduled(self, start_idx=None, end_idx=None, initial_pt=None, initial_state=None,
+                                    selection_method=None, print_output=False):
+        start_idx, end_idx = self._clip(start_idx, end_idx)
+        if selection_method not in ["random", "greedy"]:
+            print("Invalid selection_method. Choose either 'random' or 'greedy'.")
+            return None
+        xt = np.zeros(15)
+        if initial_state is not None:
+            Pt = np.asarray(initial_pt, dtype=np.float64)
+            xt[0:6] = initial_state[1:7]
+            first = start_idx
+            previous_time = initial_state[0]
+        else:
+            Pt = self._default_P0().astype(np.float64)
+            init = self._first_gps(start_idx, end_idx)
+            if init is None:
+                print("WARN: No GPS measurement found in the sensor subset.")
+                return None, None
+            xt, previous_time, first = init
+        states = [(previous_time, *xt[:6])]
+        logdets = [np.linalg.slogdet(Pt)[1]]
+        if end_idx == -1:
+            end_idx = len(self.indexed_sensor_data)
+        ps = streams.pack_events(self.indexed_sensor_data)
+        lo = first + 1
+        types, times = ps.types[lo:end_idx], ps.times[lo:end_idx]
+        period = 1 / self.processing_frequency
+        if selection_method == "greedy":
+            sel, _ = self._engine().select_greedy(types, times, [period], [previous_time], Pt[None])
+            sel = sel[0].astype(np.int64)
+        else:  # random: window bookkeeping only, no filter arithmetic (:877-893)
+            sel, prev, q0 = [], previous_time, None
+            for e in range(len(times)):
+                if times[e] - prev < period:
+                    if q0 is None:
+                        q0 = e
+                    continue
+                if q0 is None:
+                    q0 = e
+                    qlen = 1
+                else:
+                    qlen = e - q0
+                pick = q0 + int(self.scheduler.random_schedule(num_measurements=qlen))
+                sel.append(pick)
+                prev = times[pick]
+                q0 = None
+            sel = np.array(sel, dtype=np.int64)
+        if len(sel):
+            st = times[sel]
+            dts = np.diff(st, prepend=previous_time)  # dt = selected_time - previous_time (:914)
+            r = self._run(lo + sel, dts, xt, Pt)
+            states += r["states"]
+            logdets += r["logdet"]
+            Pt = r["P"]
+        if print_output:
+            print(f"Scheduled KF processed {len(sel)} measurements from index {first + 1} to {end_idx}")
+        return states, logdets, Pt
+
+    # ---- adaptive threshold / no update (kf_workers.py:959-1159) -------------------------------
+    def _adaptive(self, start_idx, end_idx, R_threshold, initial_pt, initial_state, never_update, print_output):
+        start_idx, end_idx = self._clip(start_idx, end_idx)
+        if R_threshold is None:
+            R_threshold = -float("inf")
+            print("Overriding R_threshold to - infinity (i.e. max information utilization).")
+        measurement_times = []
+        xt = np.zeros(15)
+        if initial_pt is not None and initial_state is not None:
+            Pt = np.asarray(initial_pt, dtype=np.float64)
+            xt[0:6] = initial_state[1:7]
+            previous_time = initial_state[0]
+            first = start_idx
+        else:
+            Pt = self._default_P0().astype(np.float64)
+            init = self._first_gps(start_idx, end_idx)
+            if init is None:
+                print("WARN: No GPS measurement found in the sensor subset.")
+                return None
+            xt, previous_time, first = init
+            measurement_times.append(previous_time)
+        states = [(previous_time, *xt[:6])]
+        logdets = [np.linalg.slogdet(Pt)[1]]
+        ps = streams.pack_events(self.indexed_sensor_data)
+        # dt < 0: `continue` without moving previous_time (the reference assigns a dead variable, :1013-1015)
+        keep, dts, prev_out = streams.schedule_dts(ps.times[first:end_idx], previous_time, skip_advances_prev=False)
+        if len(keep):
+            idx = first + keep
+            if never_update:
+                r = self._run(idx, dts, xt, Pt, types=np.full(len(idx), streams.PREDICT_ONLY, dtype=np.uint8))
+            else:
+                gate = R_threshold if R_threshold != -float("inf") else -1.0e300
+                r = self._run(idx, dts, xt, Pt, gate=gate, want_used=True)
+                measurement_times += [float(t) for t in r["times"][r["used"]]]
+            states += r["states"]
+            logdets += r["logdet"]
+            Pt = r["P"]
+            previous_time = prev_out
+        if print_output:
+            print("---------------------------- Adaptive Kalman Filter ----------------------------\n"
+                  f" Processed {len(keep)} measurements out of {end_idx - first} in total, from index {first} to {end_idx}")
+        return states, logdets, Pt, previous_time, measurement_times
+
+    def run_adaptive_threshold_kalman_filter(self, start_idx=None, end_idx=None, R_threshold=None, initial_pt=None,
+                                             initial_state=None, print_output=False):
+        return self._adaptive(start_idx, end_idx, R_threshold, initial_pt, initial_state, False, print_output)
+
+    def run_no_update_kalman_filter(self, start_idx=None, end_idx=None, R_threshold=None, initial_pt=None,
+                                    initial_state=None, print_output=False):
+        return self._adaptive(start_idx, end_idx, R_threshold, initial_pt, initial_state, True, print_output)
+
+    # ---- accuracy metric (kf_workers.py:1162-1216; host-side, linear interpolation) ------------
+    def calculate_accuracy_metrics(self, candidate_trajectory):
+        if not candidate_trajectory:
+            print("Candidate trajectory is empty. Cannot calculate accuracy.")
+            return None
+        if not (hasattr(self, "_ground_truth") and self._ground_truth):
+            print("Ground truth trajectory is not available. Run run_kalman_filter_full() first.")
+            return None
+        c0, c1 = candidate_trajectory[0][0], candidate_trajectory[-1][0]
+        gt = self._ground_truth
+        sec = [s for s in gt if c0 <= s[0] <= c1]
+        if len(sec) < 2:
+            sec = gt
+        gt_t = np.array([s[0] for s in sec], dtype=np.float64)
+        gt_p = np.array([s[1:4] for s in sec], dtype=np.float64)
+        ct = np.array([s[0] for s in candidate_trajectory], dtype=np.float64)
+        cp = np.array([s[1:4] for s in candidate_trajectory], dtype=np.float64)
+        interp = np.stack([_lerp_extrapolate(ct, gt_t, gt_p[:, k]) for k in range(3)], axis=1)
+        err = cp - interp
+        eu = np.linalg.norm(err, axis=1)
+        return {"total_position_rmse": np.sqrt(np.mean(eu ** 2)), "position_errors": err, "euclidean_errors": eu,
+                "candidate_times": ct, "candidate_positions": cp, "ground_truth_interp": interp,
+                "gt_start_time": c0, "gt_end_time": c1}
+
+    # ---- brute-force schedule search (kf_workers.py:1218-1392) ----------------------------------
+    def run_brute_force_kalman_filter_no_sampling_min_usage(self, start_idx=0, end_idx=None, R_threshold=None,
+                                                            initial_pt=None, initial_state=None,
+                                                            max_combos_in_memory=10000):
+        if R_threshold is None:
+            raise ValueError("R_threshold must be specified for brute force KF.")
+        start_idx, end_idx = self._clip(start_idx, end_idx)
+        xt = np.zeros(15)
+        if initial_pt is not None and initial_state is not None:
+            Pt = np.asarray(initial_pt, dtype=np.float64)
+            xt[0:6] = initial_state[1:7]
+            prev_time = initial_state[0]
+            sensor_measurements = list(self.indexed_sensor_data[start_idx:end_idx])
+        else:
+            Pt = self._default_P0().astype(np.float64)
+            init = self._first_gps(start_idx, end_idx + 1)
+            sensor_measurements = []
+            if init is not None:
+                xt, prev_time, first = init
+                sensor_measurements = list(self.indexed_sensor_data[first:end_idx + 1])
+            if len(sensor_measurements) == 0:
+                print("No sensor measurements found after GPS initialization.")
+                return None
+        last_measurement_time = self.indexed_sensor_data[end_idx - 1][2]
+        n = len(sensor_measurements)
+        print(f"Total combinations: {2 ** n} (2^{n})")
+        print(f"Target end time: {last_measurement_time}")
+        if n > 32:
+            raise NotImplementedError(f"window of {n} events: the schedule-search kernel enumerates at most 2^32 "
+                                      "subsets (the reference itself cannot finish 2^25)")
+        ps = streams.PackedStream.from_events(sensor_measurements)
+        eng = self._engine()
+        best, _ = eng.score_schedules(ps.types, ps.times, prev_time, last_measurement_time, Pt,
+                                      threshold=R_threshold, initial_logdet=_slogdet_signed(Pt))
+        mask = best["first_feasible_index"]
+        if mask is None:
+            print("\nBrute force search complete. No combination met the R_threshold.")
+            return None
+        sel = [i for i in range(n) if (mask >> i) & 1]
+        combo = tuple(sensor_measurements[i] for i in sel)
+        out = eng.run_masked(ps.types, ps.times, ps.payload(self.MODEL_NAME), prev_time, last_measurement_time, xt, Pt,
+                             [mask], traj_ncomp=6)
+        k = abs(int(out["n_terms"][0].item()))
+        traj = out["traj"].cpu().numpy()[0, :k]
+        ld = out["logdet"].cpu().numpy()[0, :k]
+        tr = [(float(row[0]), *row[1:]) for row in traj]
+        tr[0] = (prev_time, *xt[:6])
+        print(f"\nFound valid combination with {len(sel)} measurements meeting R_threshold!!!!")
+        return {"selected_sensors": combo, "final_state": out["x_final"].cpu().numpy()[0], "final_covariance": None,
+                "trajectory": tr, "accuracy_metric": 0,
+                "log_determinants": [_slogdet_signed(Pt)] + [v for v in ld[1:]],
+                "num_measurements_used": len(sel),
+                # extras (not in the reference): how many feasibility decisions sat within 1e-9 of the
+                # threshold, and the winner as a bitmask over the window
+                "n_near_threshold": best["n_near_threshold"], "selected_mask": mask}
+
+
+def _lerp_extrapolate(x, xp, fp):
+    """scipy interp1d(kind='linear', fill_value='extrapolate') for sorted xp (kf_workers.py:1195-1197)."""
+    if len(xp) == 1:
+        return np.full_like(x, fp[0], dtype=np.float64)
+    i = np.clip(np.searchsorted(xp, x, side="right") - 1, 0, len(xp) - 2)
+    slope = (fp[i + 1] - fp[i]) / (xp[i + 1] - xp[i])
+    return fp[i] + slope * (x - xp[i])
+
+
+def find_start_idx_for_time_offset(sensor_fusion, time_offset, t0=1697739552.3362827):
+    """First event index whose time is >= t0 + time_offset (the helper the reference's __main__ uses;
+    t0 is its hard-coded first-fix epoch, kf_workers.py:1993)."""
+    target = t0 + time_offset
+    for i, ev in enumerate(sensor_fusion.indexed_sensor_data):
+        if ev[2] >= target:
+            return i
+    return len(sensor_fusion.indexed_sensor_data)
+
+
+__all__ = ["KF_SensorFusion", "Scheduler", "evaluate_combo_chunk_worker", "find_start_idx_for_time_offset",
+           "combinations", "math"]

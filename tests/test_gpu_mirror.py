@@ -1,0 +1,220 @@
+"""The reference-facing Python surface (sensorfusion_kalmanfilter_b200.kf_workers / .hw5_2) against the
+golden vectors produced by the UNMODIFIED reference (tests/golden/*.npz, oracle/make_golden.py).
+These read like the calls the reference's own drivers make (kf_workers.py:2301-2345)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle.make_golden import arrays_to_events, states_arr
+
+pytestmark = pytest.mark.gpu
+
+R = 1e-9  # BASELINE.json: FP64 states / covariances within 1e-9 relative
+
+
+def close(a, b, tol=R):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(b))), np.max(np.abs(a - b))
+
+
+def close_states(got, ref):
+    got, ref = states_arr(got), np.asarray(ref)
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got[:, 0], ref[:, 0])  # timestamps are copied, not computed
+    for c in range(1, got.shape[1]):
+        close(got[:, c], ref[:, c])
+
+
+def close_ld(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < R
+
+
+@pytest.fixture(scope="module")
+def kf(golden):
+    from sensorfusion_kalmanfilter_b200.kf_workers import KF_SensorFusion
+    g = golden("ca15_loops.npz")
+    k = KF_SensorFusion("gps_data.csv", "imu_data.csv")
+    k.indexed_sensor_data = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    return k, g
+
+
+def test_run_kalman_filter_full_cold_and_warm(kf):
+    k, g = kf
+    st, ld, P, prev = k.run_kalman_filter_full(0, 400)
+    close_states(st, g["full_cold_states"])
+    close_ld(ld, g["full_cold_logdet"])
+    close(P, g["full_cold_P"])
+    assert prev == g["full_cold_prev"]
+    assert isinstance(st[0], tuple) and len(st[0]) == 7 and isinstance(ld, list) and P.shape == (15, 15)
+    assert k.get_GT() is st
+    st, ld, P, prev = k.run_kalman_filter_full(200, 400, g["full_warm_init_P"], tuple(g["full_warm_init_state"]))
+    close_states(st, g["full_warm_states"])
+    close_ld(ld, g["full_warm_logdet"])
+    close(P, g["full_warm_P"])
+    assert prev == g["full_warm_prev"]
+
+
+def test_run_kalman_filter_legacy(kf):
+    k, g = kf
+    st, covs = k.run_kalman_filter(0, 300)
+    assert len(covs) == int(g["legacy_n"])
+    close_states(st, g["legacy_states"])
+    close(covs[-1], g["legacy_P_last"])
+    close(covs[len(covs) // 2], g["legacy_P_mid"])
+
+
+def test_adaptive_threshold_and_no_update(kf):
+    k, g = kf
+    st, ld, P, prev, mt = k.run_adaptive_threshold_kalman_filter(0, 300, float(g["adaptive_thr"]))
+    np.testing.assert_array_equal(np.array(mt), g["adaptive_mtimes"])  # same gate decisions
+    close_states(st, g["adaptive_states"])
+    close_ld(ld, g["adaptive_logdet"])
+    close(P, g["adaptive_P"])
+    assert prev == g["adaptive_prev"]
+    st, ld, P, prev, mt = k.run_adaptive_threshold_kalman_filter(
+        200, 330, float(g["adaptive_warm_thr"]), g["full_warm_init_P"], tuple(g["full_warm_init_state"]))
+    np.testing.assert_array_equal(np.array(mt), g["adaptive_warm_mtimes"])
+    close_states(st, g["adaptive_warm_states"])
+    close_ld(ld, g["adaptive_warm_logdet"])
+    st, ld, P, prev, mt = k.run_no_update_kalman_filter(0, 120)
+    close_states(st, g["noupdate_states"])
+    close_ld(ld, g["noupdate_logdet"])
+    close(P, g["noupdate_P"])
+    np.testing.assert_array_equal(np.array(mt), g["noupdate_mtimes"])
+    assert prev == g["noupdate_prev"]
+
+
+@pytest.mark.parametrize("f", [20, 50, 120])
+def test_scheduled_greedy(kf, f):
+    k, g = kf
+    k.set_processing_frequency(f)
+    st, ld, P = k.run_kalman_filter_scheduled(0, 400, None, None, "greedy")
+    close_states(st, g[f"sched_greedy_{f}_states"])  # identical timestamps = identical selections
+    close_ld(ld, g[f"sched_greedy_{f}_logdet"])
+    close(P, g[f"sched_greedy_{f}_P"])
+
+
+def test_scheduled_warm_and_random(kf):
+    k, g = kf
+    k.set_processing_frequency(50)
+    st, ld, P = k.run_kalman_filter_scheduled(200, 400, g["full_warm_init_P"], tuple(g["full_warm_init_state"]),
+                                              "greedy")
+    close_states(st, g["sched_warm_states"])
+    close_ld(ld, g["sched_warm_logdet"])
+    np.random.seed(int(g["sched_random_seed"]))
+    st, ld, P = k.run_kalman_filter_scheduled(0, 400, None, None, "random")
+    close_states(st, g["sched_random_states"])
+    close(P, g["sched_random_P"])
+    assert k.run_kalman_filter_scheduled(0, 400, None, None, "best") is None
+
+
+@pytest.fixture(scope="module")
+def bf(golden):
+    from sensorfusion_kalmanfilter_b200.kf_workers import KF_SensorFusion
+    g = golden("ca15_bruteforce.npz")
+    k = KF_SensorFusion("gps_data.csv", "imu_data.csv")
+    k.indexed_sensor_data = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    return k, g
+
+
+def test_evaluate_combo_chunk_worker(bf):
+    from sensorfusion_kalmanfilter_b200.kf_workers import evaluate_combo_chunk_worker
+    k, g = bf
+    L, w0 = int(g["L"]), int(g["w0"])
+    window = k.indexed_sensor_data[w0:w0 + L]
+    init = g["init_state"]
+    xt = np.zeros(15)
+    xt[0:6] = init[1:7]
+    class_args = {name: getattr(k, name) for name in (
+        "get_state_transition_matrix", "get_process_noise_covariance_matrix", "predict_covariance",
+        "get_gps_observation_matrix", "get_gps_measurement_noise_covariance_matrix",
+        "get_imu_observation_matrix", "get_imu_measurement_noise_covariance_matrix", "calculate_kalman_gain")}
+    order = [c for kk in range(1, L + 1) for c in itertools.combinations(range(L), kk)]
+    chunk = [tuple(window[i] for i in c) for c in order]
+    res = evaluate_combo_chunk_worker(chunk, xt, g["P0"], class_args, init[0], float(g["t_end"]))
+    assert len(res) == len(chunk) == 1023
+    for r, (metric, traj, combo, xf, Pn, log_det, used) in enumerate(res):
+        ref = g["traces"][r]
+        ref = ref[~np.isnan(ref)]
+        assert metric == 0 and Pn is None and used == len(order[r]) and combo is chunk[r]
+        close_ld(log_det, ref)
+        close(xf, g["x_final"][r])
+        assert len(traj) == int(g["n_traj"][r])
+        assert traj[-1][0] == g["traj_last"][r][0]
+        close(np.array(traj[-1][1:], dtype=float), g["traj_last"][r][1:])
+
+
+def test_brute_force_driver(bf):
+    k, g = bf
+    Ld, w0 = int(g["drv_L"]), int(g["w0"])
+    init = tuple(g["init_state"])
+    for thr, mask, xf, lds in zip(g["drv_thr"], g["drv_mask"], g["drv_final_state"], g["drv_logdet"]):
+        out = k.run_brute_force_kalman_filter_no_sampling_min_usage(w0, w0 + Ld, float(thr), g["P0"].copy(), init)
+        if int(mask) < 0:
+            assert out is None
+            continue
+        sel = tuple(e[0] - w0 for e in out["selected_sensors"])
+        assert sum(1 << i for i in sel) == int(mask)  # bit-exact selected schedule
+        assert out["num_measurements_used"] == len(sel) and out["accuracy_metric"] == 0
+        assert out["final_covariance"] is None
+        close(out["final_state"], xf)
+        close_ld(out["log_determinants"], lds[~np.isnan(lds)])
+    assert k.run_brute_force_kalman_filter_no_sampling_min_usage(
+        w0, w0 + Ld, float(g["drv_infeasible_thr"]), g["P0"].copy(), init) is None
+    with pytest.raises(ValueError):
+        k.run_brute_force_kalman_filter_no_sampling_min_usage(w0, w0 + Ld, None, g["P0"].copy(), init)
+
+
+def test_scheduler_class(golden):
+    from sensorfusion_kalmanfilter_b200.kf_workers import KF_SensorFusion, Scheduler
+    g = golden("scheduler.npz")
+    k = KF_SensorFusion("a", "b")
+    sch = Scheduler()
+    Hg, Rg = k.get_gps_observation_matrix(), k.get_gps_measurement_noise_covariance_matrix()
+    Hi, Ri = k.get_imu_observation_matrix(), k.get_imu_measurement_noise_covariance_matrix()
+    for n, S in enumerate(g["Sigma"][:3]):
+        close(sch.cov_matrix([1], S, Rg, Hg, "cpu"), g["post_gps1"][n])
+        close(sch.cov_matrix([1, 2, 3], S, Rg, Hg, "cuda"), g["post_gps3"][n])
+        close(sch.cov_matrix(list(range(1, 16)), S, Ri, Hi, "cpu"), g["post_imu_all"][n])
+        for q, pick in zip(g["queues"], g["greedy_pick"][n]):
+            queue = [(j, "GPS" if c == 0 else "IMU", float(j), None) for j, c in enumerate(q) if c >= 0]
+            assert sch.greedy_schedule(queue, S, {"IMU": Ri, "GPS": Rg}, {"IMU": Hi, "GPS": Hg}, "cpu") == int(pick)
+
+
+def test_overridden_getter_changes_result_or_raises(kf):
+    from sensorfusion_kalmanfilter_b200.kf_workers import KF_SensorFusion
+    k, g = kf
+
+    class NoisierGPS(KF_SensorFusion):
+        def get_gps_measurement_noise_covariance_matrix(self):
+            return np.diag([30.0, 30.0, 30.0])
+
+    k2 = NoisierGPS("a", "b")
+    k2.indexed_sensor_data = k.indexed_sensor_data
+    _, _, P2, _ = k2.run_kalman_filter_full(0, 100)
+    _, _, P1, _ = k.run_kalman_filter_full(0, 100)
+    assert abs(P2[0, 0] - P1[0, 0]) > 1e-3 * P1[0, 0]  # the override reached the GPU model
+
+    class DenseQ(KF_SensorFusion):
+        def get_process_noise_covariance_matrix(self, dt):
+            Q = super().get_process_noise_covariance_matrix(dt)
+            Q[0, 1] = Q[1, 0] = 0.1 * dt
+            return Q
+
+    k3 = DenseQ("a", "b")
+    k3.indexed_sensor_data = k.indexed_sensor_data
+    with pytest.raises(NotImplementedError):
+        k3.run_kalman_filter_full(0, 100)
+
+
+def test_hw5_2_mirror(golden):
+    from sensorfusion_kalmanfilter_b200.hw5_2 import KF_SensorFusion
+    g = golden("ca8_hw5_2.npz")
+    k = KF_SensorFusion("gps_data.csv", "imu_data.csv")
+    k.indexed_sensor_data = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    close(np.array(k.run_kalman_filter(), dtype=float), g["kf_states"])
+    close(np.array(k.run_dead_reckoning_for_IMU(), dtype=float), g["dr_states"])
