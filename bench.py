@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-traj", action="store_true")
+    ap.add_argument("--traj-tsteps", type=int, default=1000, help="events per filter in the trajectory-mode leg")
     return ap.parse_args()
 
 
@@ -274,10 +276,40 @@ def run_gpu_arm(a):
         alg_bytes = float(N) * T * sp.d * rb + float(N) * (2 * (sp.n + sp.n * sp.n) * rb + 32)
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         fma_peak = probe_fma_peak(a.precision)
+        fma_peak_distinct = probe_fma_peak(a.precision, distinct_operands=True)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": None, "peak_source": peak_src, "kernel": f"kf_run_kernel<{a.model},{kmode},{a.precision},agg>",
                     "kernel_ms": kms, "algorithmic_bytes_per_filter_step": sp.d * rb,
-                    "fp_pipe": {"measured_fma_peak_tflops": fma_peak, "kernel_filter_steps_per_s": N * T / (kms * 1e-3)}}
+                    "fp_pipe": {"measured_fma_peak_tflops": fma_peak,
+                                "measured_fma_peak_distinct_operands_tflops": fma_peak_distinct, "kernel_filter_steps_per_s": N * T / (kms * 1e-3)}}
+
+        # ---- trajectory mode: per-step (x[0:6], log det) written out as the reference does
+        # (kf_workers.py:714-717): 24 B in + 56 B out per filter-step
+        traj_mode = None
+        if not a.no_traj:
+            Tt = min(a.traj_tsteps, T)
+            xt = torch.zeros((N, sp.n), dtype=eng.real, device=dev)
+            Pt = P.clone()
+            for _ in range(2):
+                o = eng.run_batch(types_d[:Tt], dts_d[:Tt], payload[:Tt], xt, Pt, want_agg=False, traj_ncomp=6,
+                                  want_logdet=True, inplace=True, mode=a.mode)
+                del o
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(3):
+                o = eng.run_batch(types_d[:Tt], dts_d[:Tt], payload[:Tt], xt, Pt, want_agg=False, traj_ncomp=6,
+                                  want_logdet=True, inplace=True, mode=a.mode)
+                del o
+            t1e.record()
+            torch.cuda.synchronize()
+            tms = t0e.elapsed_time(t1e) / 3
+            tbytes = float(N) * Tt * (sp.d + 7) * rb
+            traj_mode = {"value": N * Tt / (tms * 1e-3), "unit": UNIT, "workload": f"{N} filters x {Tt} steps, traj[0:6] + logdet out",
+                         "ms": tms, "algorithmic_bytes_per_filter_step": (sp.d + 7) * rb,
+                         "achieved_gbs": tbytes / (tms * 1e-3) / 1e9, "frac_of_hbm_peak": tbytes / (tms * 1e-3) / 1e9 / hbm_peak,
+                         "includes": "output allocation by the caching allocator + chain-compat check + kernel"}
+            del xt, Pt
 
         # ---- e2e: host buffers through b200kf_run_batch_host
         e2e = None
@@ -341,7 +373,7 @@ def run_gpu_arm(a):
                 "config": {"workload": workload_name(a), "mode": a.mode, "l2": "inputs (31.5 GB at defaults) larger than L2; no flush",
                            "filters_per_gpu": N, "events_per_filter": T, "payload_layout": "[T, d, N] time-major"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
-                "roofline": roofline, "cpu_baseline": cpu, "search": search}
+                "roofline": roofline, "cpu_baseline": cpu, "search": search, "trajectory_mode": traj_mode}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

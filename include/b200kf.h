@@ -210,7 +210,9 @@ int b200kf_fill_payload(const b200kf_model* model, int64_t n_filters, int64_t n_
                         void* stream);
 
 /* Measures the FP64 (or FP32) FMA peak of the current device with a register-only kernel; the
- * FP-roofline denominator (MEASURED_PEAKS.json has none).  Synchronous. */
+ * FP-roofline denominator (MEASURED_PEAKS.json has none).  precision bit 0: B200KF_F64/F32; bit 1
+ * set: every FMA reads three distinct, changing registers (the register-file-limited rate a
+ * filter step sees) instead of two loop-invariant ones.  Synchronous. */
 int b200kf_probe_fma_peak(int32_t precision, double* tflops);
 
 #ifdef __cplusplus

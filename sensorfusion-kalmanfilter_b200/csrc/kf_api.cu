@@ -258,8 +258,30 @@ __global__ void fma_probe_kernel(real* out, int iters, real a, real b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
 }
 
+// Same FMA count, but every FMA reads three DISTINCT, changing registers (no operand-reuse cache
+// hits): the register-file-bandwidth-limited rate a real filter step sees.
 template <typename real>
-static int probe_peak(double* tflops) {
+__global__ void fma_probe_distinct_kernel(real* out, int iters, real a) {
+  real v0 = threadIdx.x * real(1e-3), v1 = v0 + a, v2 = v0 - a, v3 = v0 * a, v4 = v0 + 2, v5 = v0 + 3,
+       v6 = v0 + 4, v7 = v0 + 5;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v0 = fma(v1, v2, v0);
+      v1 = fma(v2, v3, v1);
+      v2 = fma(v3, v4, v2);
+      v3 = fma(v4, v5, v3);
+      v4 = fma(v5, v6, v4);
+      v5 = fma(v6, v7, v5);
+      v6 = fma(v7, v0, v6);
+      v7 = fma(v0, v1, v7);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+template <typename real>
+static int probe_peak(double* tflops, bool distinct) {
   int dev = 0, sms = 0;
   B200KF_CUDA_TRY(cudaGetDevice(&dev));
   B200KF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -272,7 +294,10 @@ static int probe_peak(double* tflops) {
   double best = 0;
   for (int rep = 0; rep < 5; ++rep) {
     B200KF_CUDA_TRY(cudaEventRecord(e0));
-    fma_probe_kernel<real><<<blocks, tpb>>>(out, iters, real(0.999999), real(1e-6));
+    if (distinct)
+      fma_probe_distinct_kernel<real><<<blocks, tpb>>>(out, iters, real(1e-9));
+    else
+      fma_probe_kernel<real><<<blocks, tpb>>>(out, iters, real(0.999999), real(1e-6));
     B200KF_CUDA_TRY(cudaEventRecord(e1));
     B200KF_CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;
@@ -706,8 +731,9 @@ int b200kf_fill_payload(const b200kf_model* m, int64_t n_filters, int64_t n_step
 
 int b200kf_probe_fma_peak(int32_t precision, double* tflops) {
   if (!tflops) return set_error(B200KF_ERR_INVALID, "tflops is null");
-  if (precision == B200KF_F32) return probe_peak<float>(tflops);
-  return probe_peak<double>(tflops);
+  const bool distinct = (precision & 2) != 0;  // bit 1: three distinct register operands per FMA
+  if ((precision & 1) == B200KF_F32) return probe_peak<float>(tflops, distinct);
+  return probe_peak<double>(tflops, distinct);
 }
 
 }  // extern "C"

@@ -284,10 +284,12 @@ def fill_payload(engine: Engine, types_dev, n_filters, seed=1234, stream=None):
     return out
 
 
-def probe_fma_peak(precision="f64") -> float:
-    """Measured FMA peak of the current device in TFLOP/s (b200kf_probe_fma_peak)."""
+def probe_fma_peak(precision="f64", distinct_operands=False) -> float:
+    """Measured FMA peak of the current device in TFLOP/s (b200kf_probe_fma_peak).  With
+    distinct_operands every FMA reads three different, changing registers."""
     _require_cuda()
     lib = _lib.load()
     v = c_double(0.0)
-    _lib.check(lib.b200kf_probe_fma_peak(_lib.F32 if precision == "f32" else _lib.F64, byref(v)))
+    code = (_lib.F32 if precision == "f32" else _lib.F64) | (2 if distinct_operands else 0)
+    _lib.check(lib.b200kf_probe_fma_peak(code, byref(v)))
     return v.value
