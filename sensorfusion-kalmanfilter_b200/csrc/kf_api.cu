@@ -413,6 +413,7 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   m->n = info.n, m->d = info.d, m->m_gps = info.m_gps;
   m->arena = nullptr;
   m->arena_bytes = kArenaBytes;
+  memset(&m->host_ws, 0, sizeof(m->host_ws));
   m->tpb = 64;
   m->use_tma = 1;
   if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
@@ -434,6 +435,15 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
 int b200kf_model_destroy(b200kf_model* m) {
   if (!m) return B200KF_OK;
   if (m->arena) cudaFree(m->arena);
+  if (m->host_ws.slab) cudaFree(m->host_ws.slab);
+  if (m->host_ws.ready) {
+    cudaStreamDestroy(m->host_ws.s_copy);
+    cudaStreamDestroy(m->host_ws.s_comp);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(m->host_ws.ev_copied[i]);
+      cudaEventDestroy(m->host_ws.ev_done[i]);
+    }
+  }
   delete m;
   return B200KF_OK;
 }
@@ -495,21 +505,22 @@ int b200kf_run_batch_host(const b200kf_model* m, int64_t n_filters, int64_t n_st
   const size_t rs = m->desc.precision == B200KF_F32 ? 4 : 8;
   const size_t step_bytes = static_cast<size_t>(m->d) * n_filters * rs;
   if (chunk_steps <= 0) {
-    chunk_steps = static_cast<int64_t>((size_t(256) << 20) / (step_bytes ? step_bytes : 1));
+    chunk_steps = static_cast<int64_t>((size_t(128) << 20) / (step_bytes ? step_bytes : 1));
     if (chunk_steps < 16) chunk_steps = 16;
   }
   if (chunk_steps > n_steps) chunk_steps = n_steps > 0 ? n_steps : 1;
   const size_t xb = static_cast<size_t>(n_filters) * m->n * rs;
   const size_t Pb = xb * m->n;
 
+  // Persistent workspace owned by the model (streams, events, one growable device slab): the
+  // per-call cudaMalloc/cudaFree of the first version cost more than the copies once NCCL had
+  // peer-mapped the device.  Not re-entrant for concurrent calls on the same model.
+  HostWorkspace& ws = const_cast<b200kf_model*>(m)->host_ws;
+  auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t pay_b = up(step_bytes * chunk_steps);
+  const size_t nst = n_steps > 0 ? static_cast<size_t>(n_steps) : 1;
+  const size_t need = 2 * pay_b + up(xb) + up(Pb) + up(32 * n_filters) + up(4 * n_filters) + up(nst) + up(8 * nst);
   int rc = B200KF_OK;
-  cudaStream_t s_copy = nullptr, s_comp = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  void *d_pay[2] = {nullptr, nullptr}, *d_x = nullptr, *d_P = nullptr;
-  double* d_agg = nullptr;
-  int32_t* d_status = nullptr;
-  uint8_t* d_types = nullptr;
-  double* d_dts = nullptr;
 #define HOST_TRY(expr)                              \
   do {                                              \
     cudaError_t _e = (expr);                        \
@@ -518,66 +529,74 @@ int b200kf_run_batch_host(const b200kf_model* m, int64_t n_filters, int64_t n_st
       goto done;                                    \
     }                                               \
   } while (0)
-  HOST_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-  HOST_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    HOST_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
-    HOST_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
-    HOST_TRY(cudaMalloc(&d_pay[i], step_bytes * chunk_steps));
+  char* base = nullptr;
+  void *d_pay[2], *d_x, *d_P;
+  double *d_agg, *d_dts;
+  int32_t* d_status;
+  uint8_t* d_types;
+  if (!ws.ready) {
+    HOST_TRY(cudaStreamCreateWithFlags(&ws.s_copy, cudaStreamNonBlocking));
+    HOST_TRY(cudaStreamCreateWithFlags(&ws.s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      HOST_TRY(cudaEventCreateWithFlags(&ws.ev_copied[i], cudaEventDisableTiming));
+      HOST_TRY(cudaEventCreateWithFlags(&ws.ev_done[i], cudaEventDisableTiming));
+    }
+    ws.ready = 1;
   }
-  HOST_TRY(cudaMalloc(&d_x, xb));
-  HOST_TRY(cudaMalloc(&d_P, Pb));
-  HOST_TRY(cudaMalloc(&d_agg, sizeof(double) * 4 * n_filters));
-  HOST_TRY(cudaMalloc(&d_status, sizeof(int32_t) * n_filters));
-  HOST_TRY(cudaMalloc(&d_types, n_steps > 0 ? n_steps : 1));
-  HOST_TRY(cudaMalloc(&d_dts, sizeof(double) * (n_steps > 0 ? n_steps : 1)));
-  HOST_TRY(cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, s_comp));
-  HOST_TRY(cudaMemcpyAsync(d_P, P, Pb, cudaMemcpyHostToDevice, s_comp));
-  if (n_steps > 0) {
-    HOST_TRY(cudaMemcpyAsync(d_types, types, n_steps, cudaMemcpyHostToDevice, s_comp));
-    HOST_TRY(cudaMemcpyAsync(d_dts, dts, sizeof(double) * n_steps, cudaMemcpyHostToDevice, s_comp));
+  if (ws.cap < need) {
+    if (ws.slab) cudaFree(ws.slab);
+    ws.slab = nullptr;
+    ws.cap = 0;
+    HOST_TRY(cudaMalloc(&ws.slab, need));
+    ws.cap = need;
   }
+  base = static_cast<char*>(ws.slab);
+  d_pay[0] = base;
+  d_pay[1] = base + pay_b;
+  base += 2 * pay_b;
+  d_x = base, base += up(xb);
+  d_P = base, base += up(Pb);
+  d_agg = reinterpret_cast<double*>(base), base += up(32 * n_filters);
+  d_status = reinterpret_cast<int32_t*>(base), base += up(4 * n_filters);
+  d_types = reinterpret_cast<uint8_t*>(base), base += up(nst);
+  d_dts = reinterpret_cast<double*>(base);
   {
+    cudaStream_t s_copy = ws.s_copy, s_comp = ws.s_comp;
+    HOST_TRY(cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, s_comp));
+    HOST_TRY(cudaMemcpyAsync(d_P, P, Pb, cudaMemcpyHostToDevice, s_comp));
+    if (n_steps > 0) {
+      HOST_TRY(cudaMemcpyAsync(d_types, types, n_steps, cudaMemcpyHostToDevice, s_comp));
+      HOST_TRY(cudaMemcpyAsync(d_dts, dts, sizeof(double) * n_steps, cudaMemcpyHostToDevice, s_comp));
+    }
     int64_t c = 0;
     for (int64_t k0 = 0; k0 < n_steps || c == 0; k0 += chunk_steps, ++c) {
       const int b = static_cast<int>(c & 1);
       const int64_t steps = (n_steps - k0) < chunk_steps ? (n_steps - k0) : chunk_steps;
       if (steps > 0) {
-        if (c >= 2) HOST_TRY(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
+        if (c >= 2) HOST_TRY(cudaStreamWaitEvent(s_copy, ws.ev_done[b], 0));
         HOST_TRY(cudaMemcpyAsync(d_pay[b], static_cast<const char*>(payload) + step_bytes * k0,
                                  step_bytes * steps, cudaMemcpyHostToDevice, s_copy));
-        HOST_TRY(cudaEventRecord(ev_copied[b], s_copy));
-        HOST_TRY(cudaStreamWaitEvent(s_comp, ev_copied[b], 0));
+        HOST_TRY(cudaEventRecord(ws.ev_copied[b], s_copy));
+        HOST_TRY(cudaStreamWaitEvent(s_comp, ws.ev_copied[b], 0));
       }
       const uint32_t f = (flags & ~B200KF_RUN_AGG_CONTINUE) | (c > 0 ? B200KF_RUN_AGG_CONTINUE : 0u);
       rc = b200kf_run_batch(m, n_filters, steps, d_types + k0, d_dts + k0, d_pay[b], d_x, d_P, d_agg,
                             nullptr, 0, nullptr, nullptr, nullptr, d_status, NAN, f, s_comp);
       if (rc != B200KF_OK) goto done;
-      HOST_TRY(cudaEventRecord(ev_done[b], s_comp));
+      HOST_TRY(cudaEventRecord(ws.ev_done[b], s_comp));
       if (n_steps == 0) break;
     }
+    HOST_TRY(cudaMemcpyAsync(x, d_x, xb, cudaMemcpyDeviceToHost, s_comp));
+    HOST_TRY(cudaMemcpyAsync(P, d_P, Pb, cudaMemcpyDeviceToHost, s_comp));
+    if (agg)
+      HOST_TRY(cudaMemcpyAsync(agg, d_agg, sizeof(double) * 4 * n_filters, cudaMemcpyDeviceToHost, s_comp));
+    if (status)
+      HOST_TRY(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * n_filters, cudaMemcpyDeviceToHost, s_comp));
+    HOST_TRY(cudaStreamSynchronize(s_comp));
+    HOST_TRY(cudaStreamSynchronize(s_copy));
   }
-  HOST_TRY(cudaMemcpyAsync(x, d_x, xb, cudaMemcpyDeviceToHost, s_comp));
-  HOST_TRY(cudaMemcpyAsync(P, d_P, Pb, cudaMemcpyDeviceToHost, s_comp));
-  if (agg) HOST_TRY(cudaMemcpyAsync(agg, d_agg, sizeof(double) * 4 * n_filters, cudaMemcpyDeviceToHost, s_comp));
-  if (status)
-    HOST_TRY(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * n_filters, cudaMemcpyDeviceToHost, s_comp));
-  HOST_TRY(cudaStreamSynchronize(s_comp));
 done:
   if (rc != B200KF_OK) cudaDeviceSynchronize();
-  for (int i = 0; i < 2; ++i) {
-    if (d_pay[i]) cudaFree(d_pay[i]);
-    if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
-    if (ev_done[i]) cudaEventDestroy(ev_done[i]);
-  }
-  if (d_x) cudaFree(d_x);
-  if (d_P) cudaFree(d_P);
-  if (d_agg) cudaFree(d_agg);
-  if (d_status) cudaFree(d_status);
-  if (d_types) cudaFree(d_types);
-  if (d_dts) cudaFree(d_dts);
-  if (s_copy) cudaStreamDestroy(s_copy);
-  if (s_comp) cudaStreamDestroy(s_comp);
 #undef HOST_TRY
   return rc;
 }

@@ -8,6 +8,15 @@
 #include "../../include/b200kf.h"
 #include "kf_core.cuh"
 
+// b200kf_run_batch_host's persistent resources (created on first use, freed with the model)
+struct HostWorkspace {
+  int ready;
+  cudaStream_t s_copy, s_comp;
+  cudaEvent_t ev_copied[2], ev_done[2];
+  void* slab;
+  size_t cap;
+};
+
 struct b200kf_model {
   b200kf_model_desc desc;
   b200kf::ModelConst mc;
@@ -18,6 +27,7 @@ struct b200kf_model {
   void* arena;
   size_t arena_bytes;
   int tpb;      // threads per block for the filter kernels (env B200KF_TPB)
+  HostWorkspace host_ws;
   int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };
 

@@ -125,9 +125,11 @@ class Engine:
         return {"x": x_d, "P": P_d, "agg": agg_d, "traj": traj_d, "logdet": ld_d, "used": used_d,
                 "ptraj": ptraj_d, "status": status_d}
 
-    def run_batch_host(self, types, dts, payload, x, P, *, chunk_steps=0, mode="auto"):
+    def run_batch_host(self, types, dts, payload, x, P, *, chunk_steps=0, mode="auto", inplace=False):
         """Host-buffer path (b200kf_run_batch_host): numpy (or pinned torch CPU) arrays in, numpy
-        out; payload is streamed to the device in time chunks overlapped with the kernels."""
+        out; payload is streamed to the device in time chunks overlapped with the kernels.  With
+        inplace=True, x and P (contiguous arrays / CPU tensors of the model precision) are updated
+        in place instead of being copied first."""
         torch = _require_cuda()
         sp = self.spec
         npreal = np.float32 if sp.precision == "f32" else np.float64
@@ -142,8 +144,14 @@ class Engine:
         types_h, types_p = host(types, np.uint8)
         dts_h, dts_p = host(dts, np.float64)
         pay_h, pay_p = host(payload, npreal)
-        x_h = np.array(x, dtype=npreal, order="C", copy=True)
-        P_h = np.array(P, dtype=npreal, order="C", copy=True)
+        if inplace:
+            x_h = x.numpy() if isinstance(x, torch.Tensor) else x
+            P_h = P.numpy() if isinstance(P, torch.Tensor) else P
+            if not (x_h.dtype == npreal and P_h.dtype == npreal and x_h.flags.c_contiguous and P_h.flags.c_contiguous):
+                raise ValueError("inplace=True needs C-contiguous x, P of the model precision")
+        else:
+            x_h = np.array(x, dtype=npreal, order="C", copy=True)
+            P_h = np.array(P, dtype=npreal, order="C", copy=True)
         N = x_h.shape[0]
         T = int(np.prod(types_h.shape))
         agg_h = np.zeros((N, 4), dtype=np.float64)
