@@ -417,6 +417,8 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   m->tpb = 64;
   m->use_tma = 1;
   if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
+  m->use_sym = 1;
+  if (const char* s = getenv("B200KF_SYM")) m->use_sym = atoi(s) != 0;
   if (const char* s = getenv("B200KF_TPB")) {
     const int v = atoi(s);
     if (v >= 32 && v <= 256 && v % 32 == 0) m->tpb = v;

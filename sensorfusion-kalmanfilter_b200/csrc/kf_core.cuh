@@ -640,6 +640,167 @@ __device__ __forceinline__ double fast2_update(FilterT<real, IMU_CONTROL, Bs...>
 }
 
 // --------------------------------------------------------------------------------------
+// Filter objects for the TMA kernel.  Dec2Filter: every (value, rate) chain carries its own
+// covariance.  Sym2Filter: the chains of a filter are the SAME model on different axes (CV6: x, y,
+// z share q, r and -- for the reference's axis-symmetric P0, kf_workers.py:651 -- P), so the
+// covariance / gain recursion, which never reads a measurement, is evaluated ONCE per filter and
+// applied to the M axis states.  Valid only while the M chain blocks of P are bit-identical and
+// the rate constants agree (checked per launch: chain_compat_kernel + sym2_constants_equal);
+// results are the same numbers as Dec2Filter, det P = (det chain)^M.
+// --------------------------------------------------------------------------------------
+template <class A, class B>
+constexpr bool same_pv2_shape() {
+  return is_pv2<A>() && is_pv2<B>() && A::zk(0) == B::zk(0) && A::zk(1) == B::zk(1) &&
+         ((A::gps(0) >= 0) == (B::gps(0) >= 0));
+}
+
+template <typename real, class... Bs>
+struct Dec2Filter {
+  FilterT<real, false, Bs...> f;
+  double rprod;
+  __device__ __forceinline__ void load(const real* xg, const real* Pg, int n, const ModelConst& mc) {
+    f.each([&](auto& b) { b.load(xg, Pg, n); });
+    rprod = fast2_rprod(f, mc);
+  }
+  __device__ __forceinline__ void store(real* xg, real* Pg, int n) const {
+    f.each([&](const auto& b) { b.store(xg, Pg, n); });
+  }
+  __device__ __forceinline__ void predict(real dt, const ModelConst& mc) { fast2_predict<true>(f, dt, mc); }
+  __device__ __forceinline__ double update(real dt, const ModelConst& mc, int ty, const real* u, bool& ok) {
+    return fast2_update<true>(f, dt, mc, ty, u, rprod, ok);
+  }
+  __device__ __forceinline__ double det(bool& ok) const { return filter_det(f, ok); }
+};
+
+template <typename real, class B0, class... Bs>
+struct Sym2Filter {
+  static constexpr int M = 1 + sizeof...(Bs);
+  static constexpr bool eligible = (same_pv2_shape<B0, Bs>() && ... && is_pv2<B0>());
+  real a, b, c;  // the shared chain covariance [[a, b], [b, c]]
+  real x0[M], x1[M];
+  real r0r1;
+
+  template <class F>
+  __device__ __forceinline__ static void members(F&& fn) {
+    int m = 0;
+    fn(B0{}, m++);
+    (fn(Bs{}, m++), ...);
+  }
+  __device__ __forceinline__ static double powM(double d) {
+    double r = d;
+#pragma unroll
+    for (int i = 1; i < M; ++i) r *= d;
+    return r;
+  }
+  // device-side validity check of one filter's P [n, n]
+  __device__ __forceinline__ static bool is_symmetric(const real* Pg, int n) {
+    bool same = true;
+    members([&](auto Bm, int) {
+      using BM = decltype(Bm);
+      static_for<0, 2>([&](auto I) {
+        static_for<0, 2>([&](auto J) {
+          same = same && (Pg[BM::gidx(I) * n + BM::gidx(J)] == Pg[B0::gidx(I) * n + B0::gidx(J)]);
+        });
+      });
+    });
+    return same;
+  }
+  // host-side: the rate constants of all members agree
+  static bool constants_equal(const ModelConst& mc) {
+    bool same = true;
+    auto chk = [&](auto Bm) {
+      using BM = decltype(Bm);
+      for (int i = 0; i < 2; ++i) {
+        same = same && mc.q[BM::gidx(i)] == mc.q[B0::gidx(i)] && mc.r_imu[BM::gidx(i)] == mc.r_imu[B0::gidx(i)];
+      }
+      if (B0::gps(0) >= 0) same = same && mc.r_gps[BM::gps(0)] == mc.r_gps[B0::gps(0)];
+    };
+    (chk(Bs{}), ...);
+    return same;
+  }
+
+  __device__ __forceinline__ void load(const real* xg, const real* Pg, int n, const ModelConst& mc) {
+    a = Pg[B0::gidx(0) * n + B0::gidx(0)];
+    b = real(0.5) * (Pg[B0::gidx(0) * n + B0::gidx(1)] + Pg[B0::gidx(1) * n + B0::gidx(0)]);
+    c = Pg[B0::gidx(1) * n + B0::gidx(1)];
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      x0[m] = xg[BM::gidx(0)];
+      x1[m] = xg[BM::gidx(1)];
+    });
+    r0r1 = real(mc.r_imu[B0::gidx(0)] * mc.r_imu[B0::gidx(1)]);
+  }
+  __device__ __forceinline__ void store(real* xg, real* Pg, int n) const {
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      xg[BM::gidx(0)] = x0[m];
+      xg[BM::gidx(1)] = x1[m];
+      Pg[BM::gidx(0) * n + BM::gidx(0)] = a;
+      Pg[BM::gidx(0) * n + BM::gidx(1)] = b;
+      Pg[BM::gidx(1) * n + BM::gidx(0)] = b;
+      Pg[BM::gidx(1) * n + BM::gidx(1)] = c;
+    });
+  }
+  __device__ __forceinline__ void predict(real dt, const ModelConst& mc) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) x0[m] = fma(dt, x1[m], x0[m]);
+    const real bn = fma(dt, c, b);
+    a = fma(dt, b + bn, fma(real(mc.q[B0::gidx(0)]), dt, a));
+    b = bn;
+    c = fma(real(mc.q[B0::gidx(1)]), dt, c);
+  }
+  __device__ __forceinline__ double det(bool& ok) const {
+    const real d = fma(a, c, -(b * b));
+    ok = ok && (d > real(0));
+    return powM(double(d));
+  }
+  __device__ __forceinline__ double update(real dt, const ModelConst& mc, int ty, const real* u, bool& ok) {
+    if (ty == EV_IMU) {
+      const real r0 = real(mc.r_imu[B0::gidx(0)]), r1 = real(mc.r_imu[B0::gidx(1)]);
+      const real detp = fma(a, c, -(b * b));
+      const real t0 = fma(a, r1, detp);
+      const real t1 = fma(c, r0, detp);
+      const real inv = fast_rcp(fma(r0, c + r1, t0));
+      const real bi = b * inv;
+      const real k00 = t0 * inv, k11 = t1 * inv, k01 = bi * r0, k10 = bi * r1;
+      members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        real y0, y1;
+        if constexpr (BM::zk(1) == ZK_VEL) y1 = u[BM::pz(1)] * dt;
+        else y1 = u[BM::pz(1)] - x1[m];
+        if constexpr (BM::zk(0) == ZK_POS) y0 = (x1[m] + u[BM::pz(0)] * dt) * dt;
+        else y0 = u[BM::pz(0)] - x0[m];
+        x0[m] = fma(k00, y0, fma(k01, y1, x0[m]));
+        x1[m] = fma(k10, y0, fma(k11, y1, x1[m]));
+      });
+      a = k00 * r0;
+      b = k01 * r1;
+      c = k11 * r1;
+      const real dc = detp * (inv * r0r1);
+      ok = ok && (dc > real(0));
+      return powM(double(dc));
+    }
+    if (ty == EV_GPS) {
+      if constexpr (B0::gps(0) >= 0) {
+        const real r = real(mc.r_gps[B0::gps(0)]);
+        const real inv = fast_rcp(a + r);
+        const real k0 = a * inv, k1 = b * inv, g = r * inv;
+        members([&](auto Bm, int m) {
+          using BM = decltype(Bm);
+          const real y = u[BM::gps(0)] - x0[m];
+          x0[m] = fma(k0, y, x0[m]);
+          x1[m] = fma(k1, y, x1[m]);
+        });
+        c = fma(-k1, b, c);
+        a = a * g;
+        b = b * g;
+      }
+    }
+    return det(ok);
+  }
+};
+
+// --------------------------------------------------------------------------------------
 // Model registry: decoupled chain list and dense union per model id
 // --------------------------------------------------------------------------------------
 template <int MODEL_ID, bool DENSE, typename real>
@@ -661,6 +822,8 @@ struct ChainIndex {
     static constexpr int n = N, d = D, m_gps = MGPS;                           \
     static constexpr bool imu_control = CTRL;                                  \
     using Filter = FilterT<real, CTRL, __VA_ARGS__>;                           \
+    using Dec2 = Dec2Filter<real, __VA_ARGS__>;                                \
+    using Sym2 = Sym2Filter<real, __VA_ARGS__>;                                \
     static constexpr int chain_of(int g) { return ChainIndex<__VA_ARGS__>::of(g); } \
   };                                                                           \
   template <typename real>                                                     \

@@ -28,6 +28,7 @@ struct b200kf_model {
   size_t arena_bytes;
   int tpb;      // threads per block for the filter kernels (env B200KF_TPB)
   HostWorkspace host_ws;
+  int use_sym;  // 1: axis-symmetric kernel when every filter's chains share one covariance (env B200KF_SYM=0 disables)
   int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };
 
@@ -65,7 +66,7 @@ struct RunParams {
   double gate_threshold;
   int gate_enabled;
   int agg_continue;
-  const int* dense_flag;  // AUTO mode: run only if *dense_flag matches the kernel's mode
+  const int* dense_flag;  // AUTO mode: int[2] {coupled, asymmetric}; a kernel runs only if they select its mode
 };
 
 constexpr int kMaxEvents = 32;

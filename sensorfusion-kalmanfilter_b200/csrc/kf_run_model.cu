@@ -29,6 +29,15 @@ struct LaunchCfg {
   static constexpr int min_blocks = fast ? 7 : 1;
 };
 
+// AUTO dispatch: mode_flags[0] != 0 -> some P couples chains (dense kernel); else mode_flags[1] != 0
+// -> the chains of some filter differ (per-chain kernel); else the axis-symmetric kernel.
+enum : int { MODE_DECOUPLED = 0, MODE_DENSE = 1, MODE_SYMMETRIC = 2 };
+__device__ __forceinline__ bool mode_selected(const int* flags, int mine) {
+  if (flags == nullptr) return true;
+  const int actual = flags[0] ? MODE_DENSE : (flags[1] ? MODE_DECOUPLED : MODE_SYMMETRIC);
+  return actual == mine;
+}
+
 template <int MODEL, bool DENSE, typename real, bool FULL>
 __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
                                   (LaunchCfg<MODEL, DENSE, real>::min_blocks))
@@ -37,7 +46,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
   constexpr int n = MT::n;
   constexpr int D = MT::d;
   constexpr bool FAST = MT::Filter::fast2;
-  if (p.dense_flag != nullptr && *p.dense_flag != (DENSE ? 1 : 0)) return;
+  if (!mode_selected(p.dense_flag, DENSE ? MODE_DENSE : MODE_DECOUPLED)) return;
   const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (f >= p.n_filters) return;
   const long long N = p.n_filters;
@@ -245,14 +254,15 @@ static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, c
   if (k < T) out[k] = SchedRec{dts[k], static_cast<int>(types[k]), 0};
 }
 
-template <int MODEL, typename real>
+template <int MODEL, typename real, bool SYM>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched) {
   using MT = ModelTraits<MODEL, false, real>;
+  using Flt = std::conditional_t<SYM, typename MT::Sym2, typename MT::Dec2>;
   constexpr int n = MT::n;
   constexpr int D = MT::d;
   static_assert(MT::Filter::fast2, "TMA kernel is for the closed-form filters");
-  if (p.dense_flag != nullptr && *p.dense_flag != 0) return;
+  if (!mode_selected(p.dense_flag, SYM ? MODE_SYMMETRIC : MODE_DECOUPLED)) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kStages][kChunk][D][kTmaThreads]
@@ -298,13 +308,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
   }
 
-  typename MT::Filter flt;
+  Flt flt;
   if (active) {
     const real* xg = static_cast<const real*>(p.x) + f * n;
     const real* Pg = static_cast<const real*>(p.P) + f * (n * n);
-    flt.each([&](auto& b) { b.load(xg, Pg, n); });
+    flt.load(xg, Pg, n, p.mc);
   }
-  const double rprod = fast2_rprod(flt, p.mc);
   double acc_mant = 1.0;
   long long acc_max = 0;  // max det as raw bits: positive doubles order like their bit patterns
   int acc_expo = 0;
@@ -334,9 +343,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           for (int j = 0; j < D; ++j) u[j] = sb[(c * D + j) * kTmaThreads];
           const real dt = static_cast<real>(rec.dt);
           const int ty = rec.type;
-          fast2_predict<true>(flt, dt, p.mc);
-          const double det = (ty != EV_PREDICT_ONLY) ? fast2_update<true>(flt, dt, p.mc, ty, u, rprod, ok)
-                                                     : filter_det(flt, ok);
+          flt.predict(dt, p.mc);
+          const double det = (ty != EV_PREDICT_ONLY) ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
           acc_max = max(acc_max, __double_as_longlong(det));
           const double m = acc_mant * det;
           const int hi = __double2hiint(m);
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   {
     real* xg = static_cast<real*>(p.x) + f * n;
     real* Pg = static_cast<real*>(p.P) + f * (n * n);
-    flt.each([&](const auto& b) { b.store(xg, Pg, n); });
+    flt.store(xg, Pg, n);
   }
   if (p.agg != nullptr) {
     double* a = p.agg + f * 4;
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     a[0] = mx;
     a[1] = sm;
-    a[2] = (T > 0) ? log(filter_det(flt, ok)) : (p.agg_continue ? a[2] : 0.0);
+    a[2] = (T > 0) ? log(flt.det(ok)) : (p.agg_continue ? a[2] : 0.0);
     a[3] = cnt;
   }
   if (p.status != nullptr) {
@@ -384,11 +392,12 @@ constexpr size_t tma_smem_bytes() {
          static_cast<size_t>(kStages) * kChunk * sizeof(SchedRec) + 2 * kStages * sizeof(unsigned long long);
 }
 
-// true when the TMA kernel was enqueued; false -> caller uses the LDG kernel
+// AUTO/forced launch of the TMA kernels.  Returns true when they were enqueued (then the caller
+// skips the LDG per-chain kernel); false -> caller uses the LDG kernel.  `flags_dev` != null: AUTO,
+// both the per-chain and (when the model allows) the axis-symmetric variants are enqueued and
+// pick themselves from the device flags.
 template <int MODEL, typename real>
-static bool try_launch_tma(const b200kf_model* m, const RunParams& p, bool full, cudaStream_t st,
-                           cudaError_t& err) {
-  err = cudaSuccess;
+static bool tma_possible(const b200kf_model* m, const RunParams& p, bool full) {
   if constexpr (!ModelTraits<MODEL, false, real>::Filter::fast2) {
     return false;
   } else {
@@ -396,23 +405,49 @@ static bool try_launch_tma(const b200kf_model* m, const RunParams& p, bool full,
     const size_t need = static_cast<size_t>(p.n_steps) * sizeof(SchedRec);
     // bulk copies need 16-byte aligned rows: even filter count for f64, multiple of 4 for f32
     const long long align_elems = 16 / static_cast<long long>(sizeof(real));
-    if (p.n_steps < 1 || need > sched_capacity(m) || (p.n_filters % align_elems) != 0 ||
-        (reinterpret_cast<uintptr_t>(p.payload) & 15u) != 0)
-      return false;
+    return p.n_steps >= 1 && need <= sched_capacity(m) && (p.n_filters % align_elems) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.payload) & 15u) == 0;
+  }
+}
+
+template <int MODEL, typename real>
+static bool sym_possible(const b200kf_model* m) {
+  using MT = ModelTraits<MODEL, false, real>;
+  if constexpr (!MT::Filter::fast2) {
+    return false;
+  } else if constexpr (!MT::Sym2::eligible) {
+    return false;
+  } else {
+    return m->use_sym != 0 && MT::Sym2::constants_equal(m->mc);
+  }
+}
+
+template <int MODEL, typename real>
+static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool with_sym, bool with_dec,
+                              cudaStream_t st) {
+  if constexpr (!ModelTraits<MODEL, false, real>::Filter::fast2) {
+    return cudaErrorInvalidValue;
+  } else {
     SchedRec* sched = reinterpret_cast<SchedRec*>(sched_scratch(m));
     pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, sched);
     constexpr size_t smem = tma_smem_bytes<MODEL, real>();
-    static bool attr_set = false;
-    if (!attr_set) {
-      err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem));
-      if (err != cudaSuccess) return true;
-      attr_set = true;
-    }
     const unsigned blocks = static_cast<unsigned>((p.n_filters + kTmaThreads - 1) / kTmaThreads);
-    kf_run_tma_kernel<MODEL, real><<<blocks, kTmaThreads, smem, st>>>(p, sched);
-    err = cudaGetLastError();
-    return true;
+    cudaError_t err = cudaSuccess;
+    if (with_dec) {
+      err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (err != cudaSuccess) return err;
+      kf_run_tma_kernel<MODEL, real, false><<<blocks, kTmaThreads, smem, st>>>(p, sched);
+    }
+    if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
+      if (with_sym) {
+        err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+        kf_run_tma_kernel<MODEL, real, true><<<blocks, kTmaThreads, smem, st>>>(p, sched);
+      }
+    }
+    return cudaGetLastError();
   }
 }
 
@@ -423,6 +458,11 @@ __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filt
   const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (f >= n_filters) return;
   const real* Pg = P + f * (n * n);
+  if constexpr (MT::Filter::fast2) {
+    if constexpr (MT::Sym2::eligible) {
+      if (flag[1] == 0 && !MT::Sym2::is_symmetric(Pg, n)) atomicOr(flag + 1, 1);
+    }
+  }
   bool coupled = false;
   static_for<0, n>([&](auto I) {
     constexpr int i = I;
@@ -455,28 +495,30 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
     B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));
     return B200KF_OK;
   }
-  cudaError_t terr = cudaSuccess;
+  const bool tma = tma_possible<MODEL, real>(m, p, full);
   if (flags & B200KF_RUN_FORCE_DECOUPLED) {
     p.dense_flag = nullptr;
-    if (try_launch_tma<MODEL, real>(m, p, full, st, terr)) {
-      B200KF_CUDA_TRY(terr);
+    if (tma) {
+      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, false, true, st)));
       return B200KF_OK;
     }
     B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
     return B200KF_OK;
   }
-  // AUTO: decide on the device, no host round trip.  Both kernels are enqueued; the one whose
-  // mode does not match the flag exits at once.
+  // AUTO: decide on the device, no host round trip.  Every candidate kernel is enqueued; the ones
+  // whose mode does not match the flags exit at once.
   int* flag = dense_flag(m);
+  const bool sym = tma && sym_possible<MODEL, real>(m);
   B200KF_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  B200KF_CUDA_TRY(cudaMemsetAsync(flag + 1, sym ? 0 : 1, sizeof(int), st));
   const int ctpb = 128;
   chain_compat_kernel<MODEL, real>
       <<<static_cast<unsigned>((p.n_filters + ctpb - 1) / ctpb), ctpb, 0, st>>>(
           static_cast<const real*>(p.P), p.n_filters, flag);
   B200KF_CUDA_TRY(cudaGetLastError());
   p.dense_flag = flag;
-  if (try_launch_tma<MODEL, real>(m, p, full, st, terr)) {
-    B200KF_CUDA_TRY(terr);
+  if (tma) {
+    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym, true, st)));
   } else {
     B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
   }

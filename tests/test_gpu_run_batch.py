@@ -196,3 +196,47 @@ def test_tma_staged_kernel_matches_ldg_kernel_and_oracle(precision, monkeypatch)
     monkeypatch.setenv("B200KF_TMA", "1")
     odd = Engine("CV6", precision=precision).run_batch(types, dts, payload[:, :, :1999], x0[:1999], P0[:1999])
     np.testing.assert_array_equal(odd["P"].cpu().numpy(), tma["P"].cpu().numpy()[:1999])
+
+
+def test_axis_symmetric_kernel_matches_per_chain_kernel_and_oracle(monkeypatch):
+    """CV6 with the reference's axis-symmetric P0: AUTO evaluates the covariance recursion once per
+    filter (Sym2Filter).  B200KF_SYM=0 keeps one covariance per chain.  Same numbers either way; a
+    P0 that differs between axes must NOT take the symmetric path."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 1800, 157
+    m, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=29)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
+    monkeypatch.setenv("B200KF_SYM", "1")
+    sym = Engine("CV6").run_batch(types, dts, payload, x0, P0)
+    monkeypatch.setenv("B200KF_SYM", "0")
+    dec = Engine("CV6").run_batch(types, dts, payload, x0, P0)
+    for out in (sym, dec):
+        assert int(out["status"].sum()) == 0
+        assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
+        assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
+        a = out["agg"].cpu().numpy()
+        assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
+    np.testing.assert_allclose(sym["P"].cpu().numpy(), dec["P"].cpu().numpy(), rtol=1e-13, atol=0)
+    np.testing.assert_allclose(sym["x"].cpu().numpy(), dec["x"].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    # asymmetric axes (one filter is enough): the launch must fall back to per-chain covariances
+    monkeypatch.setenv("B200KF_SYM", "1")
+    P1 = P0.copy()
+    P1[N // 3, 1, 1] *= 1.5
+    P1[N // 3, 4, 4] *= 0.5
+    ref1 = ko.run_batch(m, types, dts, payload, x0, P1, want_traj=False)
+    out1 = Engine("CV6").run_batch(types, dts, payload, x0, P1)
+    assert rel(out1["P"].cpu().numpy(), ref1["P"]) < RTOL64
+    assert rel(out1["x"].cpu().numpy(), ref1["x"]) < RTOL64
+    # different noise per axis in the MODEL disables it on the host side
+    from sensorfusion_kalmanfilter_b200.models import default_spec
+    spec = default_spec("CV6")
+    spec.r_imu = spec.r_imu.copy()
+    spec.r_imu[1] = 77.0
+
+    class M2(ko.CV6):
+        def R_imu(self):
+            return np.diag([50.0, 77.0, 50.0, 10.0, 10.0, 10.0])
+    ref2 = ko.run_batch(M2(), types, dts, payload, x0, P0, want_traj=False)
+    out2 = Engine(spec).run_batch(types, dts, payload, x0, P0)
+    assert rel(out2["P"].cpu().numpy(), ref2["P"]) < RTOL64
+    assert rel(out2["x"].cpu().numpy(), ref2["x"]) < RTOL64
