@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--filters", type=int, default=131072, help="filters per GPU")
     ap.add_argument("--tsteps", type=int, default=10000, help="events per filter per bench step")
     ap.add_argument("--e2e-tsteps", type=int, default=1250, help="events per filter in the host-buffer e2e leg")
-    ap.add_argument("--mode", default="auto", choices=["auto", "dense", "decoupled"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "dense", "decoupled", "symmetric"])
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -256,14 +256,17 @@ def run_gpu_arm(a):
     # kernels of libb200kf launched per bench step: auto = chain_compat + pack_schedule + TMA filter kernel
     # + dense kernel (exits at once); decoupled = pack_schedule + TMA kernel; dense = 1
     tma_on = os.environ.get("B200KF_TMA", "1") != "0" and a.model == "CV6"
-    launches_per_step = {"auto": 3 + tma_on, "decoupled": 1 + tma_on, "dense": 1}[a.mode]
+    sym_k = tma_on and os.environ.get("B200KF_SYM", "1") != "0"
+    launches_per_step = {"auto": 3 + tma_on + sym_k, "decoupled": 1 + tma_on, "symmetric": 1 + tma_on, "dense": 1}[a.mode]
     total_steps = float(world) * N * T * a.steps
     value = total_steps / (ms * 1e-3)
 
     line = None
     if rank == 0:
         # ---- dominant kernel alone (decoupled/dense as dispatched), CUDA events on the launch stream
-        kmode = a.mode if a.mode != "auto" else "decoupled"
+        # (auto resolves to the axis-symmetric kernel for this workload: P0 and the rates are the same on x, y, z)
+        sym_on = os.environ.get("B200KF_SYM", "1") != "0" and tma_on
+        kmode = a.mode if a.mode != "auto" else ("symmetric" if sym_on else "decoupled")
         for _ in range(2):
             one_step(kmode)
         torch.cuda.synchronize()
@@ -281,7 +284,8 @@ def run_gpu_arm(a):
         fma_peak = probe_fma_peak(a.precision)
         fma_peak_distinct = probe_fma_peak(a.precision, distinct_operands=True)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": f"kf_run_kernel<{a.model},{kmode},{a.precision},agg>",
+                    "traffic": None, "peak_source": peak_src, "kernel": (f"kf_run_tma_kernel<{a.model},{a.precision},{'sym' if kmode == 'symmetric' else 'per-chain'}>" if tma_on and kmode != "dense"
+                               else f"kf_run_kernel<{a.model},{kmode},{a.precision},agg>"),
                     "kernel_ms": kms, "algorithmic_bytes_per_filter_step": sp.d * rb,
                     "fp_pipe": {"measured_fma_peak_tflops": fma_peak,
                                 "measured_fma_peak_distinct_operands_tflops": fma_peak_distinct, "kernel_filter_steps_per_s": N * T / (kms * 1e-3)}}

@@ -55,6 +55,10 @@ extern "C" {
 #define B200KF_RUN_FORCE_DENSE 1u     /* always the dense (all-states-coupled) kernel */
 #define B200KF_RUN_FORCE_DECOUPLED 2u /* caller guarantees chain-compatible P (no check) */
 #define B200KF_RUN_AGG_CONTINUE 4u    /* agg holds the running aggregates of earlier chunks */
+#define B200KF_RUN_FORCE_SYMMETRIC 8u /* caller guarantees chain-compatible P whose chain blocks are
+                                         identical across axes (and the model's rates agree): one
+                                         covariance recursion per filter; falls back to
+                                         FORCE_DECOUPLED when the model / launch cannot use it */
 
 typedef struct b200kf_model b200kf_model; /* opaque, library-owned */
 

@@ -18,7 +18,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 MODEL_CV6, MODEL_CA8, MODEL_BIAS9, MODEL_CA15 = 0, 1, 2, 3
 F64, F32 = 0, 1
 EV_GPS, EV_IMU, EV_PREDICT_ONLY = 0, 1, 2
-RUN_AUTO, RUN_FORCE_DENSE, RUN_FORCE_DECOUPLED, RUN_AGG_CONTINUE = 0, 1, 2, 4
+RUN_AUTO, RUN_FORCE_DENSE, RUN_FORCE_DECOUPLED, RUN_AGG_CONTINUE, RUN_FORCE_SYMMETRIC = 0, 1, 2, 4, 8
 
 
 class ModelDesc(Structure):

@@ -471,8 +471,8 @@ int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
     return set_error(B200KF_ERR_INVALID, "types, dts and payload are required when n_steps > 0");
   if (traj && (traj_ncomp < 1 || traj_ncomp > m->n))
     return set_error(B200KF_ERR_INVALID, "traj_ncomp must be in [1, %d]", m->n);
-  if ((flags & B200KF_RUN_FORCE_DENSE) && (flags & B200KF_RUN_FORCE_DECOUPLED))
-    return set_error(B200KF_ERR_INVALID, "FORCE_DENSE and FORCE_DECOUPLED are exclusive");
+  if ((flags & B200KF_RUN_FORCE_DENSE) && (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC)))
+    return set_error(B200KF_ERR_INVALID, "FORCE_DENSE excludes FORCE_DECOUPLED / FORCE_SYMMETRIC");
   RunParams p;
   p.mc = m->mc;
   p.n_filters = n_filters;

@@ -42,6 +42,46 @@ __device__ __forceinline__ void static_for(F&& f) {
   }
 }
 
+// ---- reciprocals: every 1/x in the filters has x = P_ss + r > 0 and normal --------------------
+__device__ __forceinline__ double fast_rcp(double a) {  // a normal and > 0; ~1 ulp
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+__device__ __forceinline__ float fast_rcp(float a) { return 1.0f / a; }
+
+// inv[i] = 1 / d[i] from ONE reciprocal; returns 1 / prod(d)
+template <int K>
+__device__ __forceinline__ double rcp_batch(const double (&d)[K], double (&inv)[K]) {
+  double pre[K];
+  pre[0] = d[0];
+#pragma unroll
+  for (int i = 1; i < K; ++i) pre[i] = pre[i - 1] * d[i];
+  const double rall = fast_rcp(pre[K - 1]);
+  double r = rall;
+#pragma unroll
+  for (int i = K - 1; i > 0; --i) {
+    inv[i] = r * pre[i - 1];
+    r = r * d[i];
+  }
+  inv[0] = r;
+  return rall;
+}
+template <int K>
+__device__ __forceinline__ double rcp_batch(const float (&d)[K], float (&inv)[K]) {
+  double rall = 1.0;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    inv[i] = 1.0f / d[i];
+    rall *= double(inv[i]);
+  }
+  return rall;
+}
+
 // IMU pseudo-measurement kinds (kf_workers.py:698-704)
 enum : int { ZK_POS = 0, ZK_VEL = 1, ZK_DIRECT = 2, ZK_NONE = 3 };
 
@@ -275,12 +315,12 @@ struct BlockKF {
     });
   }
 
-  // Scalar measurement of local state S with value z and variance r.
+  // Scalar measurement of local state S with value z and variance r; inv = 1 / (P_ss + r) is
+  // supplied by the caller so the blocks of a filter can share one reciprocal per stage.
   template <int S, bool WITH_STATE>
-  __device__ __forceinline__ void scalar_update(real z, real r) {
+  __device__ __forceinline__ void scalar_update(real z, real r, real inv) {
     real row[n];
     static_for<0, n>([&](auto J) { row[J] = P[pidx(S, J)]; });
-    const real inv = real(1) / (row[S] + r);
     if constexpr (WITH_STATE) {
       const real w = (z - x[S]) * inv;
       static_for<0, n>([&](auto I) { x[I] += row[I] * w; });
@@ -299,45 +339,21 @@ struct BlockKF {
     static_for<0, n>([&](auto J) { P[pidx(S, J)] = row[J] * shrink; });
   }
 
-  // GPS event: H selects the states with gps(i) >= 0 (kf_workers.py:551-558, 694-697)
-  template <bool WITH_STATE>
-  __device__ __forceinline__ void update_gps(const ModelConst& mc, const real* u) {
-    static_for<0, n>([&](auto I) {
-      constexpr int i = I;
-      if constexpr (B::gps(i) >= 0) {
-        real z = real(0);
-        if constexpr (WITH_STATE) z = u[B::gps(i)];
-        scalar_update<i, WITH_STATE>(z, real(mc.r_gps[B::gps(i)]));
-      }
-    });
-  }
-
-  // IMU event: H = I, z built from the PREDICTED state (kf_workers.py:698-706).  All of z is
+  // IMU pseudo-measurement z built from the PREDICTED state (kf_workers.py:698-706); all of z is
   // formed before the first scalar update touches x.
-  template <bool WITH_STATE>
-  __device__ __forceinline__ void update_imu(real dt, const ModelConst& mc, const real* u) {
-    real z[n];
-    if constexpr (WITH_STATE) {
-      static_for<0, n>([&](auto I) {
-        constexpr int i = I;
-        if constexpr (B::zk(i) == ZK_POS) {
-          const real V = x[B::l1(i)] + u[B::pz(i)] * dt;
-          z[i] = x[i] + V * dt;
-        } else if constexpr (B::zk(i) == ZK_VEL) {
-          z[i] = x[i] + u[B::pz(i)] * dt;
-        } else if constexpr (B::zk(i) == ZK_DIRECT) {
-          z[i] = u[B::pz(i)];
-        } else {
-          z[i] = real(0);
-        }
-      });
-    }
+  real zbuf[n];
+  __device__ __forceinline__ void build_imu_z(real dt, const real* u) {
     static_for<0, n>([&](auto I) {
       constexpr int i = I;
-      if constexpr (B::zk(i) != ZK_NONE) {
-        real zi = real(0);
-        if constexpr (WITH_STATE) zi = z[i];
-        scalar_update<i, WITH_STATE>(zi, real(mc.r_imu[B::gidx(i)]));
+      if constexpr (B::zk(i) == ZK_POS) {
+        const real V = x[B::l1(i)] + u[B::pz(i)] * dt;
+        zbuf[i] = x[i] + V * dt;
+      } else if constexpr (B::zk(i) == ZK_VEL) {
+        zbuf[i] = x[i] + u[B::pz(i)] * dt;
+      } else if constexpr (B::zk(i) == ZK_DIRECT) {
+        zbuf[i] = u[B::pz(i)];
+      } else {
+        zbuf[i] = real(0);
       }
     });
   }
@@ -367,7 +383,7 @@ struct BlockKF {
         ok = ok && (d > real(0));
         prod *= d;
         if constexpr (k + 1 < n) {
-          const real inv = real(1) / d;
+          const real inv = fast_rcp(d);
           static_for<k + 1, n>([&](auto I) {
             constexpr int i = I;
             const real l = A[pidx(k, i)] * inv;
@@ -441,14 +457,67 @@ __device__ __forceinline__ void filter_predict(FilterT<real, IMU_CONTROL, Bs...>
   });
 }
 
+// Update = a sequence of scalar updates (exact for selector H and diagonal R).  Stage S handles
+// local state S of every block that measures it; the blocks of a stage are independent, so their
+// reciprocals 1 / (P_ss + r) come from ONE hardware reciprocal (rcp_batch).
+template <class... Bs>
+constexpr int max_block_n() {
+  int m = 0;
+  ((m = Bs::n > m ? Bs::n : m), ...);
+  return m;
+}
+
+template <bool GPS_EVENT, class B>
+constexpr bool measures(int s) {
+  if (s >= B::n) return false;
+  return GPS_EVENT ? (B::gps(s) >= 0) : (B::zk(s) != ZK_NONE);
+}
+
+template <bool GPS_EVENT, bool WITH_STATE, typename real, bool IMU_CONTROL, class... Bs>
+__device__ __forceinline__ void staged_update(FilterT<real, IMU_CONTROL, Bs...>& f, const ModelConst& mc,
+                                              const real* u) {
+  constexpr int MAXN = max_block_n<Bs...>();
+  static_for<0, MAXN>([&](auto Sc) {
+    constexpr int S = Sc;
+    constexpr int NPART = (0 + ... + (measures<GPS_EVENT, Bs>(S) ? 1 : 0));
+    if constexpr (NPART > 0) {
+      real den[NPART], inv[NPART];
+      int i = 0;
+      f.each([&](auto& blk) {
+        using BT = std::remove_reference_t<decltype(blk)>;
+        using TB = typename BT::Traits;
+        if constexpr (measures<GPS_EVENT, TB>(S)) {
+          const real r = GPS_EVENT ? real(mc.r_gps[TB::gps(S) >= 0 ? TB::gps(S) : 0]) : real(mc.r_imu[TB::gidx(S)]);
+          den[i] = blk.P[BT::pidx(S, S)] + r;
+          ++i;
+        }
+      });
+      rcp_batch<NPART>(den, inv);
+      i = 0;
+      f.each([&](auto& blk) {
+        using BT = std::remove_reference_t<decltype(blk)>;
+        using TB = typename BT::Traits;
+        if constexpr (measures<GPS_EVENT, TB>(S)) {
+          const real r = GPS_EVENT ? real(mc.r_gps[TB::gps(S) >= 0 ? TB::gps(S) : 0]) : real(mc.r_imu[TB::gidx(S)]);
+          real z = real(0);
+          if constexpr (WITH_STATE) z = GPS_EVENT ? u[TB::gps(S) >= 0 ? TB::gps(S) : 0] : blk.zbuf[S];
+          blk.template scalar_update<S, WITH_STATE>(z, r, inv[i]);
+          ++i;
+        }
+      });
+    }
+  });
+}
+
 template <bool WITH_STATE, typename real, bool IMU_CONTROL, class... Bs>
 __device__ __forceinline__ void filter_update(FilterT<real, IMU_CONTROL, Bs...>& f, real dt,
                                               const ModelConst& mc, int etype, const real* u) {
   if (etype == EV_GPS) {
-    f.each([&](auto& blk) { blk.template update_gps<WITH_STATE>(mc, u); });
+    staged_update<true, WITH_STATE>(f, mc, u);
   } else if (etype == EV_IMU) {
     if constexpr (!IMU_CONTROL) {
-      f.each([&](auto& blk) { blk.template update_imu<WITH_STATE>(dt, mc, u); });
+      if constexpr (WITH_STATE) f.each([&](auto& blk) { blk.build_imu_z(dt, u); });
+      staged_update<false, WITH_STATE>(f, mc, u);
     }
   }
 }
@@ -471,45 +540,6 @@ __device__ __forceinline__ double filter_det(const FilterT<real, IMU_CONTROL, Bs
 // which is (I - KH)P of kf_workers.py:711 written without a single cancelling subtraction.  The
 // one reciprocal per chain is shared across the chains of a filter (rcp_batch): one MUFU per step.
 // --------------------------------------------------------------------------------------
-__device__ __forceinline__ double fast_rcp(double a) {  // a normal and > 0; ~1 ulp
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-  double e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  return x;
-}
-__device__ __forceinline__ float fast_rcp(float a) { return 1.0f / a; }
-
-// inv[i] = 1 / d[i] from ONE reciprocal; returns 1 / prod(d)
-template <int K>
-__device__ __forceinline__ double rcp_batch(const double (&d)[K], double (&inv)[K]) {
-  double pre[K];
-  pre[0] = d[0];
-#pragma unroll
-  for (int i = 1; i < K; ++i) pre[i] = pre[i - 1] * d[i];
-  const double rall = fast_rcp(pre[K - 1]);
-  double r = rall;
-#pragma unroll
-  for (int i = K - 1; i > 0; --i) {
-    inv[i] = r * pre[i - 1];
-    r = r * d[i];
-  }
-  inv[0] = r;
-  return rall;
-}
-template <int K>
-__device__ __forceinline__ double rcp_batch(const float (&d)[K], float (&inv)[K]) {
-  double rall = 1.0;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    inv[i] = 1.0f / d[i];
-    rall *= double(inv[i]);
-  }
-  return rall;
-}
-
 template <typename real>
 struct Upd2 {
   real t0, t1, detp;

@@ -496,7 +496,12 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
     return B200KF_OK;
   }
   const bool tma = tma_possible<MODEL, real>(m, p, full);
-  if (flags & B200KF_RUN_FORCE_DECOUPLED) {
+  if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && tma && sym_possible<MODEL, real>(m)) {
+    p.dense_flag = nullptr;
+    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, st)));
+    return B200KF_OK;
+  }
+  if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC)) {
     p.dense_flag = nullptr;
     if (tma) {
       B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, false, true, st)));

@@ -12,7 +12,8 @@ import numpy as np
 from . import _lib
 from .models import ModelSpec, default_spec
 
-_MODES = {"auto": _lib.RUN_AUTO, "dense": _lib.RUN_FORCE_DENSE, "decoupled": _lib.RUN_FORCE_DECOUPLED}
+_MODES = {"auto": _lib.RUN_AUTO, "dense": _lib.RUN_FORCE_DENSE, "decoupled": _lib.RUN_FORCE_DECOUPLED,
+          "symmetric": _lib.RUN_FORCE_SYMMETRIC}
 
 
 def _torch():

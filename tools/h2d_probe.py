@@ -2,6 +2,7 @@
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from sensorfusion_kalmanfilter_b200 import synth
 from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload
 dev = torch.device("cuda", 0)
