@@ -699,6 +699,13 @@ struct Dec2Filter {
   __device__ __forceinline__ double update(real dt, const ModelConst& mc, int ty, const real* u, bool& ok) {
     return fast2_update<true>(f, dt, mc, ty, u, rprod, ok);
   }
+  template <class F>
+  __device__ __forceinline__ void for_each_state(F&& fn) const {  // fn(global index, value)
+    f.each([&](const auto& b) {
+      using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+      static_for<0, BT::n>([&](auto I) { fn(std::integral_constant<int, BT::gidx(I)>{}, b.x[I]); });
+    });
+  }
   __device__ __forceinline__ double det(bool& ok) const { return filter_det(f, ok); }
 };
 
@@ -769,6 +776,14 @@ struct Sym2Filter {
       Pg[BM::gidx(0) * n + BM::gidx(1)] = b;
       Pg[BM::gidx(1) * n + BM::gidx(0)] = b;
       Pg[BM::gidx(1) * n + BM::gidx(1)] = c;
+    });
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_state(F&& fn) const {  // fn(global index, value)
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      fn(std::integral_constant<int, BM::gidx(0)>{}, x0[m]);
+      fn(std::integral_constant<int, BM::gidx(1)>{}, x1[m]);
     });
   }
   __device__ __forceinline__ void predict(real dt, const ModelConst& mc) {

@@ -254,7 +254,7 @@ static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, c
   if (k < T) out[k] = SchedRec{dts[k], static_cast<int>(types[k]), 0};
 }
 
-template <int MODEL, typename real, bool SYM>
+template <int MODEL, typename real, bool SYM, bool FULL>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched) {
   using MT = ModelTraits<MODEL, false, real>;
@@ -344,7 +344,24 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           const real dt = static_cast<real>(rec.dt);
           const int ty = rec.type;
           flt.predict(dt, p.mc);
-          const double det = (ty != EV_PREDICT_ONLY) ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
+          bool do_update = (ty != EV_PREDICT_ONLY);
+          if constexpr (FULL) {
+            if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > p.gate_threshold);  // :1023-1025
+          }
+          const double det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
+          if constexpr (FULL) {
+            const long long k = k0 + c;
+            if (p.traj != nullptr) {
+              real* tr = static_cast<real*>(p.traj) + (k * p.traj_ncomp) * N + f;
+              const int nc = p.traj_ncomp;
+              flt.for_each_state([&](auto G, real v) {
+                constexpr int g = G;
+                if (g < nc) __stcs(tr + static_cast<long long>(g) * N, v);
+              });
+            }
+            if (p.logdet != nullptr) __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(log(det)));
+            if (p.used != nullptr) p.used[k * N + f] = do_update ? 1 : 0;
+          }
           acc_max = max(acc_max, __double_as_longlong(det));
           const double m = acc_mant * det;
           const int hi = __double2hiint(m);
@@ -401,7 +418,8 @@ static bool tma_possible(const b200kf_model* m, const RunParams& p, bool full) {
   if constexpr (!ModelTraits<MODEL, false, real>::Filter::fast2) {
     return false;
   } else {
-    if (full || m->use_tma == 0) return false;
+    if (p.ptraj != nullptr || m->use_tma == 0) return false;  // per-step P output: LDG kernel only
+    (void)full;
     const size_t need = static_cast<size_t>(p.n_steps) * sizeof(SchedRec);
     // bulk copies need 16-byte aligned rows: even filter count for f64, multiple of 4 for f32
     const long long align_elems = 16 / static_cast<long long>(sizeof(real));
@@ -422,9 +440,19 @@ static bool sym_possible(const b200kf_model* m) {
   }
 }
 
+template <int MODEL, typename real, bool SYM, bool FULL>
+static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, unsigned blocks, size_t smem,
+                                  cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, FULL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  kf_run_tma_kernel<MODEL, real, SYM, FULL><<<blocks, kTmaThreads, smem, st>>>(p, sched);
+  return cudaGetLastError();
+}
+
 template <int MODEL, typename real>
 static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool with_sym, bool with_dec,
-                              cudaStream_t st) {
+                              bool full, cudaStream_t st) {
   if constexpr (!ModelTraits<MODEL, false, real>::Filter::fast2) {
     return cudaErrorInvalidValue;
   } else {
@@ -434,20 +462,18 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     const unsigned blocks = static_cast<unsigned>((p.n_filters + kTmaThreads - 1) / kTmaThreads);
     cudaError_t err = cudaSuccess;
     if (with_dec) {
-      err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, blocks, smem, st)
+                 : launch_tma_one<MODEL, real, false, false>(p, sched, blocks, smem, st);
       if (err != cudaSuccess) return err;
-      kf_run_tma_kernel<MODEL, real, false><<<blocks, kTmaThreads, smem, st>>>(p, sched);
     }
     if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
       if (with_sym) {
-        err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, blocks, smem, st)
+                   : launch_tma_one<MODEL, real, true, false>(p, sched, blocks, smem, st);
         if (err != cudaSuccess) return err;
-        kf_run_tma_kernel<MODEL, real, true><<<blocks, kTmaThreads, smem, st>>>(p, sched);
       }
     }
-    return cudaGetLastError();
+    return err;
   }
 }
 
@@ -498,13 +524,13 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   const bool tma = tma_possible<MODEL, real>(m, p, full);
   if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && tma && sym_possible<MODEL, real>(m)) {
     p.dense_flag = nullptr;
-    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, st)));
+    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, st)));
     return B200KF_OK;
   }
   if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC)) {
     p.dense_flag = nullptr;
     if (tma) {
-      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, false, true, st)));
+      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, false, true, full, st)));
       return B200KF_OK;
     }
     B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
@@ -523,7 +549,7 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   B200KF_CUDA_TRY(cudaGetLastError());
   p.dense_flag = flag;
   if (tma) {
-    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym, true, st)));
+    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym, true, full, st)));
   } else {
     B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
   }
