@@ -188,6 +188,21 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def load_traffic(a, kernel_name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), when
+    the workload matches the one that was profiled; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        w = t["workload"]
+        if (w["model"], w["precision"], w["filters"], w["tsteps"]) == (a.model, a.precision, a.filters, a.tsteps) \
+                and "sym" in kernel_name:
+            return t["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -284,11 +299,13 @@ def run_gpu_arm(a):
         fma_peak = probe_fma_peak(a.precision)
         fma_peak_distinct = probe_fma_peak(a.precision, distinct_operands=True)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": (f"kf_run_tma_kernel<{a.model},{a.precision},{'sym' if kmode == 'symmetric' else 'per-chain'}>" if tma_on and kmode != "dense"
+                    "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel": (f"kf_run_tma_kernel<{a.model},{a.precision},{'sym' if kmode == 'symmetric' else 'per-chain'}>" if tma_on and kmode != "dense"
                                else f"kf_run_kernel<{a.model},{kmode},{a.precision},agg>"),
                     "kernel_ms": kms, "algorithmic_bytes_per_filter_step": sp.d * rb,
                     "fp_pipe": {"measured_fma_peak_tflops": fma_peak,
                                 "measured_fma_peak_distinct_operands_tflops": fma_peak_distinct, "kernel_filter_steps_per_s": N * T / (kms * 1e-3)}}
+
+        roofline["traffic"] = load_traffic(a, roofline["kernel"])
 
         # ---- trajectory mode: per-step (x[0:6], log det) written out as the reference does
         # (kf_workers.py:714-717): 24 B in + 56 B out per filter-step
