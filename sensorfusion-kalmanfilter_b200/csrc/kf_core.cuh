@@ -358,6 +358,39 @@ struct BlockKF {
     });
   }
 
+  // ---- the block interface the filter-level code uses (BlockKF and SymBlock both provide it) ----
+  template <int S, bool GPS_EVENT>
+  __device__ __forceinline__ real stage_den(const ModelConst& mc) const {
+    const real r = GPS_EVENT ? real(mc.r_gps[B::gps(S) >= 0 ? B::gps(S) : 0]) : real(mc.r_imu[B::gidx(S)]);
+    return P[pidx(S, S)] + r;
+  }
+  template <int S, bool GPS_EVENT, bool WITH_STATE>
+  __device__ __forceinline__ void stage_apply(const ModelConst& mc, const real* u, real inv) {
+    const real r = GPS_EVENT ? real(mc.r_gps[B::gps(S) >= 0 ? B::gps(S) : 0]) : real(mc.r_imu[B::gidx(S)]);
+    real z = real(0);
+    if constexpr (WITH_STATE) z = GPS_EVENT ? u[B::gps(S) >= 0 ? B::gps(S) : 0] : zbuf[S];
+    scalar_update<S, WITH_STATE>(z, r, inv);
+  }
+  __device__ __forceinline__ double det_total(bool& ok) const { return double(det(ok)); }
+  template <typename T>
+  __device__ __forceinline__ static bool blocks_identical(const T*, int) { return true; }
+  template <typename T>
+  static bool blocks_identical_host(const T*, int) { return true; }
+  static bool constants_equal(const ModelConst&) { return true; }
+  template <class F>
+  __device__ __forceinline__ void for_each_state(F&& fn) const {  // fn(integral_constant global index, value)
+    static_for<0, n>([&](auto I) { fn(std::integral_constant<int, B::gidx(I)>{}, x[I]); });
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_cov(F&& fn) const {  // fn(global row, global col, value)
+    static_for<0, n>([&](auto I) {
+      static_for<0, n>([&](auto J) { fn(B::gidx(I), B::gidx(J), P[pidx(I, J)]); });
+    });
+  }
+  __device__ __forceinline__ void load_state(const double* x0) {
+    static_for<0, n>([&](auto I) { x[I] = real(x0[B::gidx(I)]); });
+  }
+
   // det P: closed form for n <= 3, LDL^T pivots otherwise.  ok is cleared on a non-positive pivot.
   __device__ __forceinline__ real det(bool& ok) const {
     if constexpr (n == 1) {
@@ -400,6 +433,268 @@ struct BlockKF {
 };
 
 // --------------------------------------------------------------------------------------
+// SymBlock: M chains that are the SAME model on different axes (x/y/z position chains, or
+// roll/pitch/yaw) and whose covariance blocks are identical share ONE covariance.  The covariance
+// and gain recursion never reads a measurement, so it is evaluated once and applied to the M
+// member states.  Validity (identical P blocks, equal rate constants) is checked per launch.
+// SymGroup<B0, B1, ...> is the tag that selects it inside a FilterT.
+// --------------------------------------------------------------------------------------
+template <class B0, class... Bs>
+struct SymGroup : B0 {
+  static constexpr bool is_group = true;
+};
+
+template <typename real, class B0, class... Bs>
+struct SymBlock {
+  static constexpr int n = B0::n;
+  static constexpr int NP = n * (n + 1) / 2;
+  static constexpr int M = 1 + sizeof...(Bs);
+  using Traits = B0;
+  using B = B0;
+  real P[NP];
+  real x[M][n];
+  real zbuf[M][n];
+  static constexpr int pidx(int i, int j) {
+    return i <= j ? (i * n - i * (i - 1) / 2 + (j - i)) : (j * n - j * (j - 1) / 2 + (i - j));
+  }
+  template <class F>
+  __device__ __forceinline__ static void members(F&& fn) {  // fn(member tables, member index)
+    fn(B0{}, std::integral_constant<int, 0>{});
+    members_tail<1, Bs...>(fn);
+  }
+  template <int K, class F>
+  __device__ __forceinline__ static void members_tail(F&&) {}
+  template <int K, class C0, class... Cs, class F>
+  __device__ __forceinline__ static void members_tail(F&& fn) {
+    fn(C0{}, std::integral_constant<int, K>{});
+    members_tail<K + 1, Cs...>(fn);
+  }
+
+  // every member's block of P equals member 0's (device, one filter)
+  template <typename T>
+  __device__ __forceinline__ static bool blocks_identical(const T* Pg, int n_total) {
+    bool same = true;
+    members([&](auto Bm, auto) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) {
+        static_for<0, n>([&](auto J) {
+          same = same && (Pg[BM::gidx(I) * n_total + BM::gidx(J)] == Pg[B0::gidx(I) * n_total + B0::gidx(J)]);
+        });
+      });
+    });
+    return same;
+  }
+  template <typename T>
+  static bool blocks_identical_host(const T* Pg, int n_total) {
+    bool same = true;
+    auto chk = [&](auto Bm) {
+      using BM = decltype(Bm);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          same = same && (Pg[BM::gidx(i) * n_total + BM::gidx(j)] == Pg[B0::gidx(i) * n_total + B0::gidx(j)]);
+    };
+    (chk(Bs{}), ...);
+    return same;
+  }
+  static bool constants_equal(const ModelConst& mc) {
+    bool same = true;
+    auto chk = [&](auto Bm) {
+      using BM = decltype(Bm);
+      for (int i = 0; i < n; ++i) {
+        same = same && mc.q[BM::gidx(i)] == mc.q[B0::gidx(i)] && mc.r_imu[BM::gidx(i)] == mc.r_imu[B0::gidx(i)];
+        if (B0::gps(i) >= 0) same = same && mc.r_gps[BM::gps(i)] == mc.r_gps[B0::gps(i)];
+      }
+    };
+    (chk(Bs{}), ...);
+    return same;
+  }
+
+  __device__ __forceinline__ void load(const real* __restrict__ xg, const real* __restrict__ Pg, int n_total) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      static_for<i, n>([&](auto J) {
+        constexpr int j = J;
+        P[pidx(i, j)] = real(0.5) * (Pg[B0::gidx(i) * n_total + B0::gidx(j)] + Pg[B0::gidx(j) * n_total + B0::gidx(i)]);
+      });
+    });
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) { x[Mi][I] = xg[BM::gidx(I)]; });
+    });
+  }
+  __device__ __forceinline__ void store(real* __restrict__ xg, real* __restrict__ Pg, int n_total) const {
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) {
+        xg[BM::gidx(I)] = x[Mi][I];
+        static_for<0, n>([&](auto J) { Pg[BM::gidx(I) * n_total + BM::gidx(J)] = P[pidx(I, J)]; });
+      });
+    });
+  }
+  __device__ __forceinline__ void load_cov(const double* __restrict__ Pg, int n_total) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      static_for<i, n>([&](auto J) {
+        constexpr int j = J;
+        P[pidx(i, j)] = real(0.5 * (Pg[B0::gidx(i) * n_total + B0::gidx(j)] + Pg[B0::gidx(j) * n_total + B0::gidx(i)]));
+      });
+    });
+#pragma unroll
+    for (int m = 0; m < M; ++m) static_for<0, n>([&](auto I) { x[m][I] = real(0); });
+  }
+  __device__ __forceinline__ void load_state(const double* x0) {
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) { x[Mi][I] = real(x0[BM::gidx(I)]); });
+    });
+  }
+
+  template <bool WITH_STATE>
+  __device__ __forceinline__ void predict(real dt, const ModelConst& mc) {
+    const real a = dt;
+    const real b = real(mc.c2) * (dt * dt);
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      constexpr int L1 = B0::l1(i);
+      constexpr int L2 = B0::l2(i);
+      if constexpr (L1 >= 0 && L2 >= 0) {
+        const real c1 = real(B0::s1(i)) * a;
+        const real c2 = real(B0::s2(i)) * b;
+        if constexpr (WITH_STATE) {
+#pragma unroll
+          for (int m = 0; m < M; ++m) x[m][i] += c1 * x[m][L1] + c2 * x[m][L2];
+        }
+        P[pidx(i, i)] += real(2) * (c1 * P[pidx(L1, i)] + c2 * P[pidx(L2, i)]) + c1 * c1 * P[pidx(L1, L1)] +
+                         real(2) * (c1 * c2) * P[pidx(L1, L2)] + c2 * c2 * P[pidx(L2, L2)];
+        static_for<0, n>([&](auto J) {
+          constexpr int j = J;
+          if constexpr (j != i) P[pidx(i, j)] += c1 * P[pidx(L1, j)] + c2 * P[pidx(L2, j)];
+        });
+      } else if constexpr (L1 >= 0) {
+        const real c1 = real(B0::s1(i)) * a;
+        if constexpr (WITH_STATE) {
+#pragma unroll
+          for (int m = 0; m < M; ++m) x[m][i] += c1 * x[m][L1];
+        }
+        P[pidx(i, i)] += real(2) * (c1 * P[pidx(L1, i)]) + c1 * c1 * P[pidx(L1, L1)];
+        static_for<0, n>([&](auto J) {
+          constexpr int j = J;
+          if constexpr (j != i) P[pidx(i, j)] += c1 * P[pidx(L1, j)];
+        });
+      }
+    });
+    static_for<0, n>([&](auto I) { P[pidx(I, I)] += real(mc.q[B0::gidx(I)]) * dt; });
+  }
+  __device__ __forceinline__ void control(real dt, const ModelConst& mc, const real* u) {
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (BM::cu(i) == 1) x[Mi][i] += (real(mc.c2) * (dt * dt)) * u[BM::pz(i)];
+        if constexpr (BM::cu(i) == 2) x[Mi][i] += dt * u[BM::pz(i)];
+      });
+    });
+  }
+  __device__ __forceinline__ void build_imu_z(real dt, const real* u) {
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (BM::zk(i) == ZK_POS) {
+          const real V = x[Mi][BM::l1(i)] + u[BM::pz(i)] * dt;
+          zbuf[Mi][i] = x[Mi][i] + V * dt;
+        } else if constexpr (BM::zk(i) == ZK_VEL) {
+          zbuf[Mi][i] = x[Mi][i] + u[BM::pz(i)] * dt;
+        } else if constexpr (BM::zk(i) == ZK_DIRECT) {
+          zbuf[Mi][i] = u[BM::pz(i)];
+        } else {
+          zbuf[Mi][i] = real(0);
+        }
+      });
+    });
+  }
+  template <int S, bool GPS_EVENT>
+  __device__ __forceinline__ real stage_den(const ModelConst& mc) const {
+    const real r = GPS_EVENT ? real(mc.r_gps[B0::gps(S) >= 0 ? B0::gps(S) : 0]) : real(mc.r_imu[B0::gidx(S)]);
+    return P[pidx(S, S)] + r;
+  }
+  template <int S, bool GPS_EVENT, bool WITH_STATE>
+  __device__ __forceinline__ void stage_apply(const ModelConst& mc, const real* u, real inv) {
+    const real r = GPS_EVENT ? real(mc.r_gps[B0::gps(S) >= 0 ? B0::gps(S) : 0]) : real(mc.r_imu[B0::gidx(S)]);
+    real row[n];
+    static_for<0, n>([&](auto J) { row[J] = P[pidx(S, J)]; });
+    if constexpr (WITH_STATE) {
+      members([&](auto Bm, auto Mi) {
+        using BM = decltype(Bm);
+        const real z = GPS_EVENT ? u[BM::gps(S) >= 0 ? BM::gps(S) : 0] : zbuf[Mi][S];
+        const real w = (z - x[Mi][S]) * inv;
+        static_for<0, n>([&](auto I) { x[Mi][I] += row[I] * w; });
+      });
+    }
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      if constexpr (i != S) {
+        const real k = row[i] * inv;
+        static_for<i, n>([&](auto J) {
+          constexpr int j = J;
+          if constexpr (j != S) P[pidx(i, j)] -= k * row[j];
+        });
+      }
+    });
+    const real shrink = r * inv;
+    static_for<0, n>([&](auto J) { P[pidx(S, J)] = row[J] * shrink; });
+  }
+  __device__ __forceinline__ real det(bool& ok) const {
+    static_assert(n <= 3, "SymBlock chains have at most 3 states");
+    real d;
+    if constexpr (n == 1) {
+      d = P[0];
+    } else if constexpr (n == 2) {
+      d = P[pidx(0, 0)] * P[pidx(1, 1)] - P[pidx(0, 1)] * P[pidx(0, 1)];
+    } else {
+      const real a = P[pidx(0, 0)], b = P[pidx(0, 1)], c = P[pidx(0, 2)];
+      const real dd = P[pidx(1, 1)], e = P[pidx(1, 2)], f = P[pidx(2, 2)];
+      d = a * (dd * f - e * e) - b * (b * f - c * e) + c * (b * e - c * dd);
+    }
+    ok = ok && (d > real(0));
+    return d;
+  }
+  __device__ __forceinline__ double det_total(bool& ok) const {
+    const double d = double(det(ok));
+    double r = d;
+#pragma unroll
+    for (int m = 1; m < M; ++m) r *= d;
+    return r;
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_state(F&& fn) const {
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) { fn(std::integral_constant<int, BM::gidx(I)>{}, x[Mi][I]); });
+    });
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_cov(F&& fn) const {
+    members([&](auto Bm, auto) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) {
+        static_for<0, n>([&](auto J) { fn(BM::gidx(I), BM::gidx(J), P[pidx(I, J)]); });
+      });
+    });
+  }
+};
+
+// block object for a table type: plain chain -> BlockKF, SymGroup<...> -> SymBlock
+template <class B, typename real>
+struct BlockObj {
+  using type = BlockKF<B, real>;
+};
+template <typename real, class B0, class... Bs>
+struct BlockObj<SymGroup<B0, Bs...>, real> {
+  using type = SymBlock<real, B0, Bs...>;
+};
+
+// --------------------------------------------------------------------------------------
 // A filter = a tuple of blocks
 // --------------------------------------------------------------------------------------
 template <typename real, bool IMU_CONTROL, class... Bs>
@@ -407,8 +702,14 @@ struct FilterT;
 
 // A chain the closed-form 2x2 path below can handle: (value, rate) with value += dt * rate and
 // both states measured by the IMU event.
+template <class B, class = void>
+struct is_group_tag : std::false_type {};
+template <class B>
+struct is_group_tag<B, std::void_t<decltype(B::is_group)>> : std::true_type {};
+
 template <class B>
 constexpr bool is_pv2() {
+  if (is_group_tag<B>::value) return false;
   if (B::n != 2) return false;
   return B::l1(0) == 1 && B::l2(0) < 0 && B::l1(1) < 0 && B::l2(1) < 0 && B::s1(0) == 1 &&
          (B::zk(0) == ZK_POS || B::zk(0) == ZK_DIRECT) && (B::zk(1) == ZK_VEL || B::zk(1) == ZK_DIRECT) &&
@@ -419,6 +720,11 @@ template <typename real, bool IMU_CONTROL>
 struct FilterT<real, IMU_CONTROL> {
   static constexpr bool fast2 = !IMU_CONTROL;
   static constexpr int nblocks = 0;
+  template <typename T>
+  __device__ __forceinline__ static bool blocks_identical(const T*, int) { return true; }
+  template <typename T>
+  static bool blocks_identical_host(const T*, int) { return true; }
+  static bool constants_equal(const ModelConst&) { return true; }
   template <class F>
   __device__ __forceinline__ void each(F&&) {}
   template <class F>
@@ -427,10 +733,22 @@ struct FilterT<real, IMU_CONTROL> {
 
 template <typename real, bool IMU_CONTROL, class B0, class... Bs>
 struct FilterT<real, IMU_CONTROL, B0, Bs...> {
-  BlockKF<B0, real> head;
+  typename BlockObj<B0, real>::type head;
   FilterT<real, IMU_CONTROL, Bs...> tail;
   static constexpr bool fast2 = is_pv2<B0>() && FilterT<real, IMU_CONTROL, Bs...>::fast2;
   static constexpr int nblocks = 1 + FilterT<real, IMU_CONTROL, Bs...>::nblocks;
+  using Head = typename BlockObj<B0, real>::type;
+  using Tail = FilterT<real, IMU_CONTROL, Bs...>;
+  // symmetric-group validity: every group's member blocks of P identical / rate constants equal
+  template <typename T>
+  __device__ __forceinline__ static bool blocks_identical(const T* Pg, int n) {
+    return Head::blocks_identical(Pg, n) && Tail::blocks_identical(Pg, n);
+  }
+  template <typename T>
+  static bool blocks_identical_host(const T* Pg, int n) {
+    return Head::blocks_identical_host(Pg, n) && Tail::blocks_identical_host(Pg, n);
+  }
+  static bool constants_equal(const ModelConst& mc) { return Head::constants_equal(mc) && Tail::constants_equal(mc); }
   template <class F>
   __device__ __forceinline__ void each(F&& f) {
     f(head);
@@ -487,8 +805,7 @@ __device__ __forceinline__ void staged_update(FilterT<real, IMU_CONTROL, Bs...>&
         using BT = std::remove_reference_t<decltype(blk)>;
         using TB = typename BT::Traits;
         if constexpr (measures<GPS_EVENT, TB>(S)) {
-          const real r = GPS_EVENT ? real(mc.r_gps[TB::gps(S) >= 0 ? TB::gps(S) : 0]) : real(mc.r_imu[TB::gidx(S)]);
-          den[i] = blk.P[BT::pidx(S, S)] + r;
+          den[i] = blk.template stage_den<S, GPS_EVENT>(mc);
           ++i;
         }
       });
@@ -498,10 +815,7 @@ __device__ __forceinline__ void staged_update(FilterT<real, IMU_CONTROL, Bs...>&
         using BT = std::remove_reference_t<decltype(blk)>;
         using TB = typename BT::Traits;
         if constexpr (measures<GPS_EVENT, TB>(S)) {
-          const real r = GPS_EVENT ? real(mc.r_gps[TB::gps(S) >= 0 ? TB::gps(S) : 0]) : real(mc.r_imu[TB::gidx(S)]);
-          real z = real(0);
-          if constexpr (WITH_STATE) z = GPS_EVENT ? u[TB::gps(S) >= 0 ? TB::gps(S) : 0] : blk.zbuf[S];
-          blk.template scalar_update<S, WITH_STATE>(z, r, inv[i]);
+          blk.template stage_apply<S, GPS_EVENT, WITH_STATE>(mc, u, inv[i]);
           ++i;
         }
       });
@@ -525,7 +839,7 @@ __device__ __forceinline__ void filter_update(FilterT<real, IMU_CONTROL, Bs...>&
 template <typename real, bool IMU_CONTROL, class... Bs>
 __device__ __forceinline__ double filter_det(const FilterT<real, IMU_CONTROL, Bs...>& f, bool& ok) {
   double d = 1.0;
-  f.each([&](const auto& blk) { d *= double(blk.det(ok)); });
+  f.each([&](const auto& blk) { d *= blk.det_total(ok); });
   return d;
 }
 
@@ -885,6 +1199,37 @@ B200KF_DEFINE_MODEL(MODEL_CA8, 8, 4, 2, false, CA8LinChain<0>, CA8LinChain<1>, C
 B200KF_DEFINE_MODEL(MODEL_BIAS9, 9, 3, 3, true, BIAS9Chain<0>, BIAS9Chain<1>, BIAS9Chain<2>)
 B200KF_DEFINE_MODEL(MODEL_CA15, 15, 9, 3, false, CA15LinChain<0>, CA15LinChain<1>, CA15LinChain<2>,
                     CA15AngChain<0>, CA15AngChain<1>, CA15AngChain<2>)
+
+// Axis-symmetric form of each model: chains that are the same model on different axes grouped
+// into SymBlocks (one covariance per group).
+template <int MODEL_ID, typename real>
+struct SymTraits;
+template <typename real>
+struct SymTraits<MODEL_CV6, real> {
+  using Filter = FilterT<real, false, SymGroup<CV6Chain<0>, CV6Chain<1>, CV6Chain<2>>>;
+};
+template <typename real>
+struct SymTraits<MODEL_CA8, real> {
+  using Filter = FilterT<real, false, SymGroup<CA8LinChain<0>, CA8LinChain<1>>, CA8YawChain>;
+};
+template <typename real>
+struct SymTraits<MODEL_BIAS9, real> {
+  using Filter = FilterT<real, true, SymGroup<BIAS9Chain<0>, BIAS9Chain<1>, BIAS9Chain<2>>>;
+};
+template <typename real>
+struct SymTraits<MODEL_CA15, real> {
+  using Filter = FilterT<real, false, SymGroup<CA15LinChain<0>, CA15LinChain<1>, CA15LinChain<2>>,
+                         SymGroup<CA15AngChain<0>, CA15AngChain<1>, CA15AngChain<2>>>;
+};
+
+// kernel variants: 0 = one covariance per chain, 1 = dense, 2 = one covariance per symmetric group
+enum : int { VAR_DECOUPLED = 0, VAR_DENSE = 1, VAR_SYMMETRIC = 2 };
+template <int MODEL_ID, int VAR, typename real>
+struct VariantTraits : ModelTraits<MODEL_ID, VAR == VAR_DENSE, real> {};
+template <int MODEL_ID, typename real>
+struct VariantTraits<MODEL_ID, VAR_SYMMETRIC, real> : ModelTraits<MODEL_ID, false, real> {
+  using Filter = typename SymTraits<MODEL_ID, real>::Filter;
+};
 
 // Running aggregate of log det P over the steps of one launch, kept in product form so the
 // hot loop needs no log: sum log d_k = log(mantissa product) + exponent sum * ln 2.

@@ -22,9 +22,9 @@ constexpr int PF = B200KF_PF;  // payload prefetch depth (steps)
 // registers so 7 blocks x 128 threads = 896 filters are resident per SM: the 131 072-filter shard
 // of BASELINE config 3 (885.6 filters per SM over 148 SMs) then runs as ONE balanced wave
 // instead of 1.15 waves with an almost empty second one.
-template <int MODEL, bool DENSE, typename real>
+template <int MODEL, int VAR, typename real>
 struct LaunchCfg {
-  static constexpr bool fast = ModelTraits<MODEL, DENSE, real>::Filter::fast2;
+  static constexpr bool fast = VariantTraits<MODEL, VAR, real>::Filter::fast2;
   static constexpr int max_threads = fast ? 128 : 256;
   static constexpr int min_blocks = fast ? 7 : 1;
 };
@@ -38,15 +38,16 @@ __device__ __forceinline__ bool mode_selected(const int* flags, int mine) {
   return actual == mine;
 }
 
-template <int MODEL, bool DENSE, typename real, bool FULL>
-__global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
-                                  (LaunchCfg<MODEL, DENSE, real>::min_blocks))
+template <int MODEL, int VAR, typename real, bool FULL>
+__global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
+                                  (LaunchCfg<MODEL, VAR, real>::min_blocks))
     kf_run_kernel(const RunParams p) {
-  using MT = ModelTraits<MODEL, DENSE, real>;
+  using MT = VariantTraits<MODEL, VAR, real>;
+  constexpr bool DENSE = (VAR == VAR_DENSE);
   constexpr int n = MT::n;
   constexpr int D = MT::d;
   constexpr bool FAST = MT::Filter::fast2;
-  if (!mode_selected(p.dense_flag, DENSE ? MODE_DENSE : MODE_DECOUPLED)) return;
+  if (!mode_selected(p.dense_flag, VAR)) return;
   const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (f >= p.n_filters) return;
   const long long N = p.n_filters;
@@ -125,11 +126,9 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
             real* tr = static_cast<real*>(p.traj) + (static_cast<long long>(k) * p.traj_ncomp) * N + f;
             const int nc = p.traj_ncomp;
             flt.each([&](const auto& b) {
-              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
-              static_for<0, BT::n>([&](auto I) {
-                constexpr int i = I;
-                constexpr int g = BT::gidx(i);
-                if (g < nc) __stcs(tr + static_cast<long long>(g) * N, b.x[i]);
+              b.for_each_state([&](auto G, real v) {
+                constexpr int g = G;
+                if (g < nc) __stcs(tr + static_cast<long long>(g) * N, v);
               });
             });
           }
@@ -139,14 +138,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, DENSE, real>::max_threads),
               for (int e = 0; e < n * n; ++e) pt[static_cast<long long>(e) * N] = real(0);
             }
             flt.each([&](const auto& b) {
-              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
-              static_for<0, BT::n>([&](auto I) {
-                constexpr int i = I;
-                static_for<0, BT::n>([&](auto J) {
-                  constexpr int j = J;
-                  pt[static_cast<long long>(BT::gidx(i) * n + BT::gidx(j)) * N] = b.P[BT::pidx(i, j)];
-                });
-              });
+              b.for_each_cov([&](int gi, int gj, real v) { pt[static_cast<long long>(gi * n + gj) * N] = v; });
             });
           }
           if (p.logdet != nullptr)
@@ -203,7 +195,7 @@ constexpr int kTmaThreads = 896;  // 7 warps per SM sub-partition; 896 * 72 regs
 #define B200KF_CHUNK 2
 #endif
 #ifndef B200KF_STAGES
-#define B200KF_STAGES 4
+#define B200KF_STAGES 5
 #endif
 constexpr int kChunk = B200KF_CHUNK;    // steps per stage
 constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 KB of shared memory)
@@ -430,14 +422,14 @@ static bool tma_possible(const b200kf_model* m, const RunParams& p, bool full) {
 
 template <int MODEL, typename real>
 static bool sym_possible(const b200kf_model* m) {
+  return m->use_sym != 0 && SymTraits<MODEL, real>::Filter::constants_equal(m->mc);
+}
+// the TMA kernel has its own closed-form symmetric filter (Sym2Filter) for all-(value, rate) models
+template <int MODEL, typename real>
+constexpr bool tma_sym_eligible() {
   using MT = ModelTraits<MODEL, false, real>;
-  if constexpr (!MT::Filter::fast2) {
-    return false;
-  } else if constexpr (!MT::Sym2::eligible) {
-    return false;
-  } else {
-    return m->use_sym != 0 && MT::Sym2::constants_equal(m->mc);
-  }
+  if constexpr (!MT::Filter::fast2) return false;
+  else return MT::Sym2::eligible;
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL>
@@ -484,11 +476,7 @@ __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filt
   const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (f >= n_filters) return;
   const real* Pg = P + f * (n * n);
-  if constexpr (MT::Filter::fast2) {
-    if constexpr (MT::Sym2::eligible) {
-      if (flag[1] == 0 && !MT::Sym2::is_symmetric(Pg, n)) atomicOr(flag + 1, 1);
-    }
-  }
+  if (flag[1] == 0 && !SymTraits<MODEL, real>::Filter::blocks_identical(Pg, n)) atomicOr(flag + 1, 1);
   bool coupled = false;
   static_for<0, n>([&](auto I) {
     constexpr int i = I;
@@ -500,16 +488,16 @@ __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filt
   if (coupled) atomicOr(flag, 1);
 }
 
-template <int MODEL, bool DENSE, typename real>
+template <int MODEL, int VAR, typename real>
 static cudaError_t launch_variant(const b200kf_model* m, const RunParams& p, bool full,
                                   cudaStream_t st) {
-  using LC = LaunchCfg<MODEL, DENSE, real>;
+  using LC = LaunchCfg<MODEL, VAR, real>;
   const int tpb = LC::fast ? LC::max_threads : (m->tpb <= LC::max_threads ? m->tpb : LC::max_threads);
   const long long blocks = (p.n_filters + tpb - 1) / tpb;
   if (full)
-    kf_run_kernel<MODEL, DENSE, real, true><<<static_cast<unsigned>(blocks), tpb, 0, st>>>(p);
+    kf_run_kernel<MODEL, VAR, real, true><<<static_cast<unsigned>(blocks), tpb, 0, st>>>(p);
   else
-    kf_run_kernel<MODEL, DENSE, real, false><<<static_cast<unsigned>(blocks), tpb, 0, st>>>(p);
+    kf_run_kernel<MODEL, VAR, real, false><<<static_cast<unsigned>(blocks), tpb, 0, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -518,13 +506,19 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   const bool full = p.traj != nullptr || p.ptraj != nullptr || p.logdet != nullptr || p.used != nullptr || p.gate_enabled;
   if (flags & B200KF_RUN_FORCE_DENSE) {
     p.dense_flag = nullptr;
-    B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));
+    B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DENSE, real>(m, p, full, st)));
     return B200KF_OK;
   }
   const bool tma = tma_possible<MODEL, real>(m, p, full);
-  if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && tma && sym_possible<MODEL, real>(m)) {
+  const bool sym = sym_possible<MODEL, real>(m);
+  const bool tma_sym = tma && tma_sym_eligible<MODEL, real>();
+  if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && sym) {
     p.dense_flag = nullptr;
-    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, st)));
+    if (tma_sym) {
+      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, st)));
+    } else {
+      B200KF_CUDA_TRY((launch_variant<MODEL, VAR_SYMMETRIC, real>(m, p, full, st)));
+    }
     return B200KF_OK;
   }
   if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC)) {
@@ -533,13 +527,12 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
       B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, false, true, full, st)));
       return B200KF_OK;
     }
-    B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
+    B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DECOUPLED, real>(m, p, full, st)));
     return B200KF_OK;
   }
   // AUTO: decide on the device, no host round trip.  Every candidate kernel is enqueued; the ones
   // whose mode does not match the flags exit at once.
   int* flag = dense_flag(m);
-  const bool sym = tma && sym_possible<MODEL, real>(m);
   B200KF_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
   B200KF_CUDA_TRY(cudaMemsetAsync(flag + 1, sym ? 0 : 1, sizeof(int), st));
   const int ctpb = 128;
@@ -549,11 +542,12 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   B200KF_CUDA_TRY(cudaGetLastError());
   p.dense_flag = flag;
   if (tma) {
-    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym, true, full, st)));
+    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym && tma_sym, true, full, st)));
   } else {
-    B200KF_CUDA_TRY((launch_variant<MODEL, false, real>(m, p, full, st)));
+    B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DECOUPLED, real>(m, p, full, st)));
   }
-  B200KF_CUDA_TRY((launch_variant<MODEL, true, real>(m, p, full, st)));
+  if (sym && !tma_sym) B200KF_CUDA_TRY((launch_variant<MODEL, VAR_SYMMETRIC, real>(m, p, full, st)));
+  B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DENSE, real>(m, p, full, st)));
   return B200KF_OK;
 }
 

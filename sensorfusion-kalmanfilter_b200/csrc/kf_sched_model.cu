@@ -36,11 +36,10 @@ __device__ __forceinline__ void better_sum(double& sc, unsigned long long& ix, d
   }
 }
 
-template <int MODEL, bool DENSE>
+template <int MODEL, int VAR>
 __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
-  using MT = ModelTraits<MODEL, DENSE, double>;
+  using MT = VariantTraits<MODEL, VAR, double>;
   constexpr int n = MT::n;
-  if (p.dense_flag != nullptr && *p.dense_flag != (DENSE ? 1 : 0)) return;
 
   double best_sc = INFINITY;
   unsigned long long best_ix = ~0ULL, best_key = ~0ULL, n_feas = 0, n_near = 0;
@@ -321,26 +320,32 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
   unsigned long long blocks = (p.count + kScoreTpb - 1) / kScoreTpb;
   if (blocks > static_cast<unsigned long long>(kMaxSearchBlocks)) blocks = kMaxSearchBlocks;
   if (blocks == 0) blocks = 1;
-  // every partial slot the finaliser reads is written by exactly one of the kernels below
+  // P0 is a host matrix, so the variant is chosen on the host: dense when P0 couples chains,
+  // one covariance per symmetric group when the member blocks of P0 are identical and the rates
+  // agree (the reference's P0 and any P it produces, kf_workers.py:651), else one per chain.
+  using MT = ModelTraits<B200KF_INST_MODEL, false, double>;
+  using SymF = typename SymTraits<B200KF_INST_MODEL, double>::Filter;
+  int var = VAR_DECOUPLED;
   if (flags & B200KF_RUN_FORCE_DENSE) {
-    p.dense_flag = nullptr;
-    score_kernel<B200KF_INST_MODEL, true><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+    var = VAR_DENSE;
   } else if (flags & B200KF_RUN_FORCE_DECOUPLED) {
-    p.dense_flag = nullptr;
-    score_kernel<B200KF_INST_MODEL, false><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+    var = VAR_DECOUPLED;
   } else {
-    // AUTO: P0 is a host matrix, so the chain-compatibility decision is made on the host
-    using MT = ModelTraits<B200KF_INST_MODEL, false, double>;
     bool coupled = false;
     for (int i = 0; i < MT::n; ++i)
       for (int j = 0; j < MT::n; ++j)
         if (MT::chain_of(i) != MT::chain_of(j) && p.P0[i * MT::n + j] != 0.0) coupled = true;
-    p.dense_flag = nullptr;
-    if (coupled)
-      score_kernel<B200KF_INST_MODEL, true><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
-    else
-      score_kernel<B200KF_INST_MODEL, false><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+    if (coupled) var = VAR_DENSE;
+    else if (m->use_sym && SymF::constants_equal(m->mc) && SymF::blocks_identical_host(p.P0, MT::n)) var = VAR_SYMMETRIC;
   }
+  if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && !(flags & B200KF_RUN_FORCE_DENSE)) var = VAR_SYMMETRIC;
+  p.dense_flag = nullptr;
+  if (var == VAR_DENSE)
+    score_kernel<B200KF_INST_MODEL, VAR_DENSE><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  else if (var == VAR_SYMMETRIC)
+    score_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  else
+    score_kernel<B200KF_INST_MODEL, VAR_DECOUPLED><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
   B200KF_CUDA_TRY(cudaGetLastError());
   return static_cast<int>(blocks);
 }

@@ -34,7 +34,7 @@ def make_case(name, N, T, seed, dense_P0=False):
 
 
 @pytest.mark.parametrize("name", ["CV6", "CA8", "BIAS9", "CA15"])
-@pytest.mark.parametrize("mode", ["decoupled", "dense", "auto"])
+@pytest.mark.parametrize("mode", ["decoupled", "dense", "auto", "symmetric"])
 def test_run_batch_f64_matches_oracle(name, mode):
     from sensorfusion_kalmanfilter_b200.engine import Engine
     N, T = 70, 160

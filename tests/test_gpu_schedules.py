@@ -24,7 +24,7 @@ def window_arrays(g, L):
     return types, times
 
 
-@pytest.mark.parametrize("mode", ["auto", "dense", "decoupled"])
+@pytest.mark.parametrize("mode", ["auto", "dense", "decoupled", "symmetric"])
 def test_all_subsets_match_reference_traces(brute, mode):
     from sensorfusion_kalmanfilter_b200.engine import Engine
     L = int(brute["L"])
