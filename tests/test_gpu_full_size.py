@@ -1,0 +1,79 @@
+"""Size-independent properties at the bench's full per-GPU width (131 072 filters), where replaying
+every filter through the oracle would take hours: the covariance / log-det path of a linear KF
+does not depend on the measurements, the state is linear in them, and time-chunking is exact."""
+import numpy as np
+import pytest
+
+from oracle import kf_oracle as ko
+from sensorfusion_kalmanfilter_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+N, T = 131072, 600
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+    from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload
+    eng = Engine("CV6")
+    types, dts = synth.gps_imu_schedule(T)
+    dev = eng.device
+    types_d = torch.from_numpy(types).to(dev)
+    pay1 = fill_payload(eng, types_d, N, seed=1)
+    pay2 = fill_payload(eng, types_d, N, seed=2)
+    P0 = torch.from_numpy(np.repeat(eng.spec.default_P0()[None], N, axis=0)).to(dev)
+    x0 = torch.zeros((N, 6), dtype=torch.float64, device=dev)
+    return eng, types, dts, pay1, pay2, x0, P0
+
+
+def test_covariance_path_is_measurement_independent_and_matches_oracle(setup):
+    eng, types, dts, pay1, pay2, x0, P0 = setup
+    out = eng.run_batch(types, dts, pay1, x0, P0)
+    assert int(out["status"].sum()) == 0
+    P = out["P"]
+    agg = out["agg"]
+    # every filter started from the same P0 over the same schedule: identical covariance and log dets
+    assert bool((P == P[0]).all()) and bool((agg == agg[0]).all())
+    m = ko.get_model("CV6")
+    ref = ko.run_batch(m, types, dts, pay1[:, :, :1].cpu().numpy(), np.zeros((1, 6)), m.P0()[None], want_traj=False)
+    assert np.max(np.abs(P[0].cpu().numpy() - ref["P"][0])) <= 1e-9 * np.max(np.abs(ref["P"][0]))
+    a, r = agg[0, :3].cpu().numpy(), ref["agg"][0]
+    assert np.max(np.abs(a - r) / np.maximum(1, np.abs(r))) < 1e-9
+    # ... and the first filter's state matches the oracle replay of its own measurements
+    assert np.max(np.abs(out["x"][0].cpu().numpy() - ref["x"][0])) <= 1e-9 * max(1.0, np.max(np.abs(ref["x"][0])))
+
+
+def test_state_is_linear_in_the_measurements(setup):
+    eng, types, dts, pay1, pay2, x0, P0 = setup
+    x1 = eng.run_batch(types, dts, pay1, x0, P0, want_agg=False)["x"]
+    x2 = eng.run_batch(types, dts, pay2, x0, P0, want_agg=False)["x"]
+    x12 = eng.run_batch(types, dts, pay1 + pay2, x0, P0, want_agg=False)["x"]
+    err = (x12 - (x1 + x2)).abs().max().item()
+    scale = x12.abs().max().item()
+    assert err <= 1e-11 * max(1.0, scale), (err, scale)
+
+
+def test_time_chunked_launches_equal_one_launch(setup):
+    eng, types, dts, pay1, pay2, x0, P0 = setup
+    one = eng.run_batch(types, dts, pay1, x0, P0)
+    x, P, agg = x0, P0, None
+    for k0 in range(0, T, 250):
+        sl = slice(k0, min(T, k0 + 250))
+        o = eng.run_batch(types[sl], dts[sl], pay1[sl], x, P, agg=agg)
+        x, P, agg = o["x"], o["P"], o["agg"]
+    assert bool((x == one["x"]).all()) and bool((P == one["P"]).all())
+    d = (agg[:, :3] - one["agg"][:, :3]).abs().max().item()
+    assert d < 1e-9 * max(1.0, one["agg"][:, :3].abs().max().item())
+
+
+def test_trajectory_outputs_consistent_with_aggregates(setup):
+    eng, types, dts, pay1, pay2, x0, P0 = setup
+    Ts = 200
+    o = eng.run_batch(types[:Ts], dts[:Ts], pay1[:Ts], x0, P0, traj_ncomp=6, want_logdet=True)
+    ld = o["logdet"]
+    agg = o["agg"]
+    assert (ld.max(dim=0).values - agg[:, 0]).abs().max().item() < 1e-9 * 100
+    assert (ld.sum(dim=0) - agg[:, 1]).abs().max().item() < 1e-9 * max(1.0, agg[:, 1].abs().max().item())
+    assert (ld[-1] - agg[:, 2]).abs().max().item() < 1e-9 * 100
+    assert bool((o["traj"][-1].T == o["x"]).all())
