@@ -259,6 +259,41 @@ class Engine:
         return [sel_h[i, :min(int(ns[i]), max_sel)].copy() for i in range(I)], P_f
 
 
+    def scheduled_sweep(self, types, times, payload, rates, x0, P0, t_prev, *, traj_ncomp=0, mode="auto"):
+        """Sampling-rate sweep x Monte-Carlo seeds (BASELINE configs[1]; run_kalman_filter_scheduled
+        with selection_method='greedy', kf_workers.py:826-957, for many seeds at once).
+
+        types/times [E]: the base event stream AFTER the initialising event; payload [E, d, N]: each
+        seed's measurements of those events; rates: processing frequencies (Hz); x0 [N, n], P0 [n, n]
+        and t_prev: state at the initialising event.  The greedy selection never reads a measurement,
+        so it runs once per rate (all rates in one covariance-only launch); the N seeds of a rate then
+        share the selected schedule in one b200kf_run_batch.  Returns {rate: dict(sel, times, x, P, agg,
+        traj)}."""
+        torch = _torch()
+        sp = self.spec
+        rates = list(rates)
+        types_d = self._dev(types, torch.uint8)
+        times_d = self._dev(times, torch.float64)
+        pay_d = self._dev(payload, self.real)
+        N = int(pay_d.shape[2])
+        P0 = np.asarray(P0, dtype=np.float64)
+        sels, _ = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
+                                     np.repeat(P0[None], len(rates), axis=0))
+        x0_d = self._dev(x0, self.real)
+        P0_d = self._dev(np.repeat(P0[None], N, axis=0), self.real)
+        out = {}
+        for f, sel in zip(rates, sels):
+            sel_d = torch.from_numpy(sel.astype(np.int64)).to(self.device)
+            st = times_d.index_select(0, sel_d)
+            dts = torch.diff(st, prepend=torch.tensor([t_prev], dtype=torch.float64, device=self.device))
+            r = self.run_batch(types_d.index_select(0, sel_d), dts, pay_d.index_select(0, sel_d).contiguous(),
+                               x0_d, P0_d, traj_ncomp=traj_ncomp, mode=mode)
+            r["sel"] = sel
+            r["times"] = st
+            out[f] = r
+        return out
+
+
 def cov_update(Sigma, rows, H, R, device=None, stream=None):
     """Batched Scheduler.cov_matrix (b200kf_cov_update).  Sigma [B, n, n] (numpy or torch), rows:
     0-based selected rows of (H, R).  Returns (Sigma_post [B,n,n], trace [B]) torch CUDA f64."""

@@ -218,3 +218,35 @@ def test_hw5_2_mirror(golden):
     k.indexed_sensor_data = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
     close(np.array(k.run_kalman_filter(), dtype=float), g["kf_states"])
     close(np.array(k.run_dead_reckoning_for_IMU(), dtype=float), g["dr_states"])
+
+
+def test_rate_sweep_x_monte_carlo_seeds(golden):
+    """BASELINE configs[1] in miniature: rates x seeds of the greedy scheduled filter, every seed
+    checked against the oracle's restatement of run_kalman_filter_scheduled on that seed's events."""
+    from oracle import kf_oracle as ko
+    from sensorfusion_kalmanfilter_b200 import streams
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    g = golden("ca15_loops.npz")
+    base = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])[3:260]
+    assert base[0][1] == "GPS"
+    rng = np.random.default_rng(4)
+    seeds, rates = 5, [20, 50, 120]
+    ps = streams.PackedStream.from_events(base)
+    noise = rng.normal(0, 0.05, (len(base), 9, seeds))
+    noise[ps.types == 0, 3:, :] = 0.0
+    pay = ps.data[:, :, None] + noise
+    m = ko.get_model("CA15")
+    x0 = np.zeros((seeds, 15))
+    x0[:, :3] = pay[0, :3, :].T
+    eng = Engine("CA15")
+    out = eng.scheduled_sweep(ps.types[1:], ps.times[1:], pay[1:], rates, x0, m.P0(), float(ps.times[0]))
+    for f in rates:
+        for sd in range(seeds):
+            ev = arrays_to_events(ps.types, ps.times, pay[:, :, sd])
+            st, ld, P = ko.run_scheduled(m, ev, f, 0, len(ev))
+            r = out[f]
+            assert len(st) - 1 == len(r["sel"])
+            np.testing.assert_array_equal(np.array([s[0] for s in st[1:]]), r["times"].cpu().numpy())
+            close(r["P"][sd].cpu().numpy(), P)
+            close(r["x"][sd, :6].cpu().numpy(), np.array(st[-1][1:], dtype=float))
+            assert abs(r["agg"][sd, 2].item() - ld[-1]) < 1e-9 * max(1.0, abs(ld[-1]))
