@@ -645,3 +645,80 @@ def hw5_2_dead_reckoning(model, events):
 
 def comb(n, k):
     return math.comb(n, k)
+
+
+# ---- notebook brute force: product of per-window queues, RMSE objective -----------------
+# (KF_SensorFusion.ipynb:766-802 metric, :804-954 search; raw JSON line numbers)
+def nb_P0(n=15):
+    """Initial covariance of the notebook's brute force (KF_SensorFusion.ipynb:813)."""
+    return np.diag([1000.0] * 3 + [100.0] * 3 + [100.0] * 3 + [100.0] * 3 + [1000.0] * 3)
+
+
+def bucket_queues(events, start_idx, end_idx, processing_frequency):
+    """Step 1 (KF_SensorFusion.ipynb:826-847): one queue per sampling period, starting at the
+    first GPS event; the event that closes a non-empty window is dropped and previous_time moves
+    to ITS time; a trailing partial queue is discarded."""
+    if end_idx is None:
+        end_idx = len(events)
+    queues, queue = [], []
+    started, prev = False, None
+    for ev in events[start_idx:end_idx]:
+        if not started and ev[1] == "GPS":
+            started, prev = True, ev[2]
+        if not started:
+            continue
+        if ev[2] - prev < 1 / processing_frequency:
+            queue.append(ev)
+            continue
+        if len(queue) == 0:
+            queue.append(ev)
+        queues.append(list(queue))
+        queue = []
+        prev = ev[2]
+    return queues
+
+
+def lerp_extrapolate(x, xp, fp):
+    """scipy interp1d(kind='linear', fill_value='extrapolate') on sorted xp."""
+    x, xp, fp = np.asarray(x, float), np.asarray(xp, float), np.asarray(fp, float)
+    i = np.clip(np.searchsorted(xp, x, side="right") - 1, 0, len(xp) - 2)
+    return fp[i] + (fp[i + 1] - fp[i]) / (xp[i + 1] - xp[i]) * (x - xp[i])
+
+
+def rmse_vs_track(traj, track_t, track_p):
+    """calculate_accuracy_metrics (KF_SensorFusion.ipynb:766-802): RMSE of the Euclidean position
+    error of traj [(t, x, y, z, ...)] against the linearly interpolated track."""
+    t = np.array([s[0] for s in traj], dtype=float)
+    p = np.array([s[1:4] for s in traj], dtype=float)
+    ref = np.stack([lerp_extrapolate(t, track_t, track_p[:, k]) for k in range(3)], axis=1)
+    e = np.linalg.norm(p - ref, axis=1)
+    return np.sqrt(np.mean(e ** 2))
+
+
+def product_combo_run(model, combo, x0, P0):
+    """One sequence of the product search (KF_SensorFusion.ipynb:896-930): first event dt = 0."""
+    x, P = np.array(x0, float).copy(), np.array(P0, float).copy()
+    traj, prev = [], None
+    for (_, stype, t, sdata) in combo:
+        dt = t - prev if prev is not None else 0
+        x, P = step(model, x, P, _type_code(stype), dt, event_payload(model, stype, sdata))
+        traj.append((t, *x[:6]))
+        prev = t
+    return traj, x, P
+
+
+def product_search(model, queues, track_t, track_p, x0=None, P0=None):
+    """itertools.product(*queues) in order, strict '<' keeps the first minimum (:932-938)."""
+    x0 = np.zeros(model.n) if x0 is None else x0
+    P0 = nb_P0() if P0 is None else P0
+    best = (float("inf"), None, None, None, None, -1)
+    metrics = []
+    for ci, combo in enumerate(itertools.product(*queues)):
+        traj, x, P = product_combo_run(model, combo, x0, P0)
+        mtr = rmse_vs_track(traj, track_t, track_p)
+        metrics.append(mtr)
+        if mtr < best[0]:
+            best = (mtr, traj, combo, x, P, ci)
+    return {"selected_sensors": best[2], "final_state": best[3], "final_covariance": best[4],
+            "trajectory": best[1], "accuracy_metric": best[0], "combo_index": best[5],
+            "metrics": np.array(metrics)}

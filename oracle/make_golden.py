@@ -67,8 +67,38 @@ def quiet(fn, *a, **kw):
         return fn(*a, **kw)
 
 
+def notebook_bruteforce():
+    """Product-of-queues brute force with the RMSE objective, which exists only in the notebook
+    (KF_SensorFusion.ipynb:804-954): cells 0-2 exec'd unmodified (oracle/ref_import.py)."""
+    from oracle.ref_import import load_notebook_class
+    K = load_notebook_class()
+    events = make_indexed_sensor_data(80, seed=31)
+    ty, tm, da = events_to_arrays(events)
+    events = arrays_to_events(ty, tm, da)
+    k = K("gps.csv", "imu.csv")
+    k.indexed_sensor_data = events
+    k.utm_data = [e[3] for e in events if e[1] == "GPS"]
+    g = {"ev_type": ty, "ev_time": tm, "ev_data": da}
+    for tag, f, s0, s1 in (("a", 50, 0, 40), ("b", 70, 5, 44)):
+        k.set_processing_frequency(f)
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            out = k.run_brute_force_kalman_filter(s0, s1)
+        g[f"{tag}_freq"] = np.float64(f)
+        g[f"{tag}_range"] = np.array([s0, s1])
+        g[f"{tag}_selected"] = np.array([e[0] for e in out["selected_sensors"]])
+        g[f"{tag}_metric"] = np.float64(out["accuracy_metric"])
+        g[f"{tag}_final_state"] = out["final_state"]
+        g[f"{tag}_final_cov"] = out["final_covariance"]
+        g[f"{tag}_trajectory"] = states_arr(out["trajectory"])
+        g[f"{tag}_rmse_of_best"] = np.float64(k.calculate_accuracy_metrics(out["trajectory"]))
+    np.savez_compressed(os.path.join(OUT, "nb_bruteforce.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "nb":
+        notebook_bruteforce()
+        return
     kw, hw = load_reference()
 
     # ---------------- 15-state filter loops (kf_workers.py) ----------------
@@ -240,6 +270,7 @@ def main():
     d8 = quiet(k8.run_dead_reckoning_for_IMU)
     np.savez_compressed(os.path.join(OUT, "ca8_hw5_2.npz"), ev_type=ty8, ev_time=tm8, ev_data=da8,
                         kf_states=np.array(s8, dtype=np.float64), dr_states=np.array(d8, dtype=np.float64))
+    notebook_bruteforce()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -53,3 +53,20 @@ def load_reference():
     import kf_workers as ref_kf_workers  # noqa: E402
     import hw5_2 as ref_hw5_2  # noqa: E402
     return ref_kf_workers, ref_hw5_2
+
+
+def load_notebook_class():
+    """KF_SensorFusion (and Scheduler) as defined in cells 0-2 of the reference's
+    KF_SensorFusion.ipynb, exec'd unmodified -- the only place run_brute_force_kalman_filter
+    (product-of-queues search, RMSE objective; KF_SensorFusion.ipynb:804-954) exists."""
+    import json
+    load_reference()  # installs the utm / matplotlib stand-ins
+    with open(os.path.join(REFERENCE_DIR, "KF_SensorFusion.ipynb")) as f:
+        nb = json.load(f)
+    ns = {"__name__": "kf_notebook"}
+    code_cells = [c for c in nb["cells"] if c["cell_type"] == "code"]
+    for c in code_cells[:3]:
+        # IPython shell magics ("!pip install ...") are not Python: dropped, nothing else is touched
+        src = "".join(ln for ln in c["source"] if not ln.lstrip().startswith(("!", "%")))
+        exec(compile(src, "KF_SensorFusion.ipynb", "exec"), ns)
+    return ns["KF_SensorFusion"]

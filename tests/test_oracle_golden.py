@@ -186,3 +186,22 @@ def test_batch_matches_event_loop(loops):
     np.testing.assert_allclose(out["traj"][:, :6, 0], states_arr(st)[1:, 1:], **TOL)
     np.testing.assert_allclose(out["logdet"][:, 0], ld[1:], **TOL)
     np.testing.assert_allclose(out["P"][0], P, **TOL)
+
+
+def test_notebook_product_search(golden):
+    """The product-of-queues / RMSE brute force that only exists in the reference's notebook."""
+    g = golden("nb_bruteforce.npz")
+    ev = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    m = ko.get_model("CA15")
+    gps = [e for e in ev if e[1] == "GPS"]
+    tt = np.array([e[2] for e in gps])
+    tp = np.array([[e[3]["easting"], e[3]["northing"], e[3]["altitude"]] for e in gps])
+    for tag in "ab":
+        s0, s1 = (int(v) for v in g[f"{tag}_range"])
+        queues = ko.bucket_queues(ev, s0, s1, float(g[f"{tag}_freq"]))
+        out = ko.product_search(m, queues, tt, tp)
+        assert [e[0] for e in out["selected_sensors"]] == [int(v) for v in g[f"{tag}_selected"]]
+        np.testing.assert_allclose(out["accuracy_metric"], g[f"{tag}_metric"], **TOL)
+        np.testing.assert_allclose(out["final_state"], g[f"{tag}_final_state"], **TOL)
+        np.testing.assert_allclose(out["final_covariance"], g[f"{tag}_final_cov"], **TOL)
+        np.testing.assert_allclose(states_arr(out["trajectory"]), g[f"{tag}_trajectory"], **TOL)
