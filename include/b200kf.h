@@ -85,6 +85,15 @@ typedef struct b200kf_best {
                                     the feasibility decisions a 1e-12 rounding difference could flip */
 } b200kf_best;
 
+/* Result of a product-of-queues search over one index range. */
+typedef struct b200kf_best_product {
+  double score;           /* min RMSE over the range; +inf if the range is empty */
+  uint64_t index;         /* its sequence index in itertools.product order, ties -> lowest index */
+  double runner_up_score; /* second-smallest RMSE in the range (+inf if none): a gap below ~1e-9
+                             relative means a rounding difference could flip the selection */
+  uint64_t n_scored;
+} b200kf_best_product;
+
 int b200kf_version(int* major, int* minor);
 size_t b200kf_last_error(char* buf, size_t n);
 
@@ -177,6 +186,43 @@ int b200kf_run_masked(const b200kf_model* model, int32_t n_events, const uint8_t
                       const double* x0, const double* P0, int64_t n_schedules, const uint64_t* masks,
                       double* x_final, double* P_final, double* traj, int32_t traj_ncomp,
                       double* logdet, int32_t* n_terms, uint32_t flags, void* stream);
+
+/* The notebook's brute force: replaces the enumeration, the per-sequence filter and the RMSE
+ * objective of run_brute_force_kalman_filter (KF_SensorFusion.ipynb:849-938) for the sequences
+ * [first, first + count) of itertools.product(*queues) (last queue fastest, :873-875).  A sequence
+ * takes ONE event from each of the n_windows <= 64 window queues, runs the full filter with state
+ * from (x0, P0) with dt = 0 at its first event (:898), and is scored by
+ * sqrt(mean_k |x_k[0:3] - ref(event_k)|^2) (calculate_accuracy_metrics, :766-802).  Float64 only.
+ *
+ *   queue_len  HOST  i32 [n_windows]   events per queue (each >= 1), E = sum
+ *   types, times  DEVICE [E]           the queues' events, flattened queue after queue
+ *   payload    DEVICE f64 [E, d]       row layout as b200kf_run_batch
+ *   ref_pos    DEVICE f64 [E, 3]       track position interpolated at each event time
+ *                                      (b200kf_track_lerp)
+ *   x0, P0     HOST f64 [n], [n, n]
+ *   per_combo  DEVICE f64 [count]      nullable: RMSE of every sequence
+ *   best       DEVICE b200kf_best_product; first minimum in enumeration order (strict '<', :933)
+ */
+int b200kf_score_products(const b200kf_model* model, int32_t n_windows, const int32_t* queue_len,
+                          const uint8_t* types, const double* times, const double* payload,
+                          const double* ref_pos, const double* x0, const double* P0, uint64_t first,
+                          uint64_t count, double* per_combo, b200kf_best_product* best,
+                          uint32_t flags, void* stream);
+
+/* scipy interp1d(kind='linear', fill_value='extrapolate') of a time-sorted track at n_query times
+ * (kf_workers.py:1195-1201, KF_SensorFusion.ipynb:779-783).  track_t DEVICE f64 [n_track],
+ * track_p DEVICE f64 [n_track, k], query_t DEVICE f64 [n_query], out DEVICE f64 [n_query, k].
+ * n_track = 1 returns the single point. */
+int b200kf_track_lerp(int64_t n_track, const double* track_t, const double* track_p, int32_t k,
+                      int64_t n_query, const double* query_t, double* out, void* stream);
+
+/* total_position_rmse of calculate_accuracy_metrics (kf_workers.py:1204-1208) for every filter of
+ * a time-major trajectory as written by b200kf_run_batch: traj DEVICE real [T, traj_ncomp, N]
+ * (components 0..2 = position), ref_pos DEVICE f64 [T, 3] the track at the step times,
+ * rmse DEVICE f64 [N].  Deterministic (fixed summation order). */
+int b200kf_rmse_vs_track(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
+                         const void* traj, int32_t traj_ncomp, const double* ref_pos, double* rmse,
+                         void* stream);
 
 /* Greedy one-event-per-window scheduling: replaces the queueing + Scheduler.greedy_schedule
  * selection of run_kalman_filter_scheduled (kf_workers.py:877-910, :174-213) for n_inst

@@ -679,10 +679,13 @@ def bucket_queues(events, start_idx, end_idx, processing_frequency):
 
 
 def lerp_extrapolate(x, xp, fp):
-    """scipy interp1d(kind='linear', fill_value='extrapolate') on sorted xp."""
+    """scipy interp1d(kind='linear', fill_value='extrapolate') on sorted xp, in the form scipy 1.18
+    evaluates it (interp1d._call_linear: side='left' search clipped to [1, n-1], two-weight blend)
+    so it is bit-identical to what the reference computes in this container."""
     x, xp, fp = np.asarray(x, float), np.asarray(xp, float), np.asarray(fp, float)
-    i = np.clip(np.searchsorted(xp, x, side="right") - 1, 0, len(xp) - 2)
-    return fp[i] + (fp[i + 1] - fp[i]) / (xp[i + 1] - xp[i]) * (x - xp[i])
+    hi = np.clip(np.searchsorted(xp, x), 1, len(xp) - 1)
+    lo = hi - 1
+    return ((x - xp[lo]) / (xp[hi] - xp[lo])) * fp[hi] + ((xp[hi] - x) / (xp[hi] - xp[lo])) * fp[lo]
 
 
 def rmse_vs_track(traj, track_t, track_p):
@@ -693,6 +696,23 @@ def rmse_vs_track(traj, track_t, track_p):
     ref = np.stack([lerp_extrapolate(t, track_t, track_p[:, k]) for k in range(3)], axis=1)
     e = np.linalg.norm(p - ref, axis=1)
     return np.sqrt(np.mean(e ** 2))
+
+
+def accuracy_metrics(candidate, ground_truth):
+    """kf_workers.calculate_accuracy_metrics (kf_workers.py:1162-1216): the ground-truth section
+    inside the candidate's time span (whole track if it has < 2 samples, :1185-1187), interpolated
+    at the candidate times; returns (rmse, interpolated positions)."""
+    c0, c1 = candidate[0][0], candidate[-1][0]
+    sec = [s for s in ground_truth if c0 <= s[0] <= c1]
+    if len(sec) < 2:
+        sec = ground_truth
+    gt_t = np.array([s[0] for s in sec], dtype=float)
+    gt_p = np.array([s[1:4] for s in sec], dtype=float)
+    ct = np.array([s[0] for s in candidate], dtype=float)
+    cp = np.array([s[1:4] for s in candidate], dtype=float)
+    interp = np.stack([lerp_extrapolate(ct, gt_t, gt_p[:, k]) for k in range(3)], axis=1)
+    e = np.linalg.norm(cp - interp, axis=1)
+    return np.sqrt(np.mean(e ** 2)), interp
 
 
 def product_combo_run(model, combo, x0, P0):

@@ -94,10 +94,37 @@ def notebook_bruteforce():
     np.savez_compressed(os.path.join(OUT, "nb_bruteforce.npz"), **g)
 
 
+def accuracy_metrics():
+    """kf_workers.calculate_accuracy_metrics (kf_workers.py:1162-1216) of a 30 Hz greedy-scheduled
+    trajectory against the full-rate run of the same stream (the reference's __main__ comparison),
+    plus the < 2-sample fallback branch (:1185-1187)."""
+    kw, _ = load_reference()
+    events = make_indexed_sensor_data(420, seed=11)
+    ty, tm, da = events_to_arrays(events)
+    events = arrays_to_events(ty, tm, da)
+    kf = kw.KF_SensorFusion("gps.csv", "imu.csv")
+    kf.indexed_sensor_data = events
+    quiet(kf.run_kalman_filter_full, 0, 400)  # sets _ground_truth
+    kf.set_processing_frequency(30)
+    st, _, _ = quiet(kf.run_kalman_filter_scheduled, 40, 360, None, None, "greedy")
+    m = kf.calculate_accuracy_metrics(st)
+    g = {"ev_type": ty, "ev_time": tm, "ev_data": da, "cand_states": states_arr(st),
+         "rmse": np.float64(m["total_position_rmse"]), "position_errors": m["position_errors"],
+         "euclidean_errors": m["euclidean_errors"], "ground_truth_interp": m["ground_truth_interp"]}
+    tiny = [(events[100][2] + 1e-4, *st[5][1:]), (events[100][2] + 2e-4, *st[6][1:])]  # no GT sample inside
+    m2 = kf.calculate_accuracy_metrics(tiny)
+    g.update(tiny_states=states_arr(tiny), tiny_rmse=np.float64(m2["total_position_rmse"]),
+             tiny_interp=m2["ground_truth_interp"])
+    np.savez_compressed(os.path.join(OUT, "ca15_accuracy.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "nb":
         notebook_bruteforce()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "acc":
+        accuracy_metrics()
         return
     kw, hw = load_reference()
 
@@ -271,6 +298,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "ca8_hw5_2.npz"), ev_type=ty8, ev_time=tm8, ev_data=da8,
                         kf_states=np.array(s8, dtype=np.float64), dr_states=np.array(d8, dtype=np.float64))
     notebook_bruteforce()
+    accuracy_metrics()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

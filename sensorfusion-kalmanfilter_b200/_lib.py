@@ -32,6 +32,10 @@ class Best(Structure):
                 ("n_feasible", c_uint64), ("n_near_threshold", c_uint64)]
 
 
+class BestProduct(Structure):
+    _fields_ = [("score", c_double), ("index", c_uint64), ("runner_up_score", c_double), ("n_scored", c_uint64)]
+
+
 class B200KFError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"libb200kf status {status}: {message}")
@@ -58,6 +62,11 @@ SIGNATURES = {
     "b200kf_run_masked": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), POINTER(c_double),
                                   c_double, c_double, POINTER(c_double), POINTER(c_double), c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b200kf_score_products": (c_int, [c_void_p, c_int32, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p,
+                                      POINTER(c_double), POINTER(c_double), c_uint64, c_uint64, c_void_p,
+                                      c_void_p, c_uint32, c_void_p]),
+    "b200kf_track_lerp": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b200kf_rmse_vs_track": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "b200kf_select_greedy": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "b200kf_cov_update": (c_int, [c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_double),

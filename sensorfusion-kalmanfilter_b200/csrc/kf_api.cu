@@ -64,6 +64,16 @@ static int dispatch_masked(const b200kf_model* m, const MaskedParams& p, unsigne
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
 
+static int dispatch_product(const b200kf_model* m, const ProductParams& p, unsigned flags, cudaStream_t st) {
+  switch (m->desc.model_id) {
+    case MODEL_CV6: return launch_product_m<MODEL_CV6>(m, p, flags, st);
+    case MODEL_CA8: return launch_product_m<MODEL_CA8>(m, p, flags, st);
+    case MODEL_BIAS9: return launch_product_m<MODEL_BIAS9>(m, p, flags, st);
+    case MODEL_CA15: return launch_product_m<MODEL_CA15>(m, p, flags, st);
+  }
+  return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
+}
+
 static int dispatch_select(const b200kf_model* m, const SelectParams& p, unsigned flags, cudaStream_t st) {
   switch (m->desc.model_id) {
     case MODEL_CV6: return launch_select_m<MODEL_CV6>(m, p, flags, st);
@@ -119,6 +129,92 @@ __global__ void score_final_kernel(const ScorePartial* parts, int n_parts, int L
       out->first_feasible_index = __brevll(rev) >> (64 - L);
     }
   }
+}
+
+// ---- product-search finaliser ------------------------------------------------------------------
+__global__ void product_final_kernel(const ProductPartial* parts, int n_parts, unsigned long long count,
+                                     b200kf_best_product* out) {
+  __shared__ ProductPartial sh[256];
+  ProductPartial r{INFINITY, ~0ULL, INFINITY};
+  auto merge = [](ProductPartial& a, const ProductPartial& b) {
+    const bool take = b.score < a.score || (b.score == a.score && b.index < a.index);
+    const double loser = take ? a.score : b.score;
+    a.runner_up = fmin(fmin(a.runner_up, b.runner_up), loser);
+    if (take) {
+      a.score = b.score;
+      a.index = b.index;
+    }
+  };
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) merge(r, parts[i]);
+  sh[threadIdx.x] = r;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) merge(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out->score = sh[0].score;
+    out->index = sh[0].index;
+    out->runner_up_score = sh[0].runner_up;
+    out->n_scored = count;
+  }
+}
+
+// ---- accuracy metric (kf_workers.py:1162-1216, KF_SensorFusion.ipynb:766-802) ------------------
+// interp1d(kind='linear', fill_value='extrapolate') on a sorted track, evaluated as scipy does
+// (_call_linear): hi = clip(searchsorted(t, x, side='left'), 1, n-1), lo = hi - 1,
+// y = ((x - t_lo) / (t_hi - t_lo)) * y_hi + ((t_hi - x) / (t_hi - t_lo)) * y_lo, every operation
+// rounded separately (no FMA contraction) so the result is bit-identical to numpy's.
+__global__ void track_lerp_kernel(long long n_track, const double* __restrict__ tt, const double* __restrict__ tp,
+                                  int k, long long n_query, const double* __restrict__ qt, double* __restrict__ out) {
+  const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (q >= n_query) return;
+  const double x = qt[q];
+  if (n_track == 1) {
+    for (int c = 0; c < k; ++c) out[q * k + c] = tp[c];
+    return;
+  }
+  long long lo = 0, hi = n_track;  // first index with tt[i] >= x
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (tt[mid] < x) lo = mid + 1;
+    else hi = mid;
+  }
+  long long ih = lo < 1 ? 1 : (lo > n_track - 1 ? n_track - 1 : lo);
+  const long long il = ih - 1;
+  const double w = __dsub_rn(tt[ih], tt[il]);
+  const double w1 = __ddiv_rn(__dsub_rn(x, tt[il]), w), w0 = __ddiv_rn(__dsub_rn(tt[ih], x), w);
+  for (int c = 0; c < k; ++c)
+    out[q * k + c] = __dadd_rn(__dmul_rn(w1, tp[ih * k + c]), __dmul_rn(w0, tp[il * k + c]));
+}
+
+// Partial sums of |x[0:3] - ref|^2 over one time segment for every filter of a time-major
+// trajectory [T, ncomp, N] (coalesced over filters); segments are summed in order by the finaliser
+// so the result does not depend on scheduling.
+template <typename real>
+__global__ void rmse_partial_kernel(const real* __restrict__ traj, int ncomp, long long N, long long T,
+                                    const double* __restrict__ ref, long long seg_len, double* __restrict__ part) {
+  const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (f >= N) return;
+  const long long k0 = blockIdx.y * seg_len;
+  const long long k1 = (k0 + seg_len < T) ? k0 + seg_len : T;
+  double sse = 0.0;
+  for (long long k = k0; k < k1; ++k) {
+    const real* row = traj + (k * ncomp) * N + f;
+    const double dx = double(row[0]) - ref[k * 3 + 0];
+    const double dy = double(row[N]) - ref[k * 3 + 1];
+    const double dz = double(row[2 * N]) - ref[k * 3 + 2];
+    const double nrm = sqrt(dx * dx + dy * dy + dz * dz);  // np.linalg.norm, then **2 (:1207-1208)
+    sse += nrm * nrm;
+  }
+  part[blockIdx.y * N + f] = sse;
+}
+__global__ void rmse_final_kernel(const double* part, int n_seg, long long N, long long T, double* rmse) {
+  const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (f >= N) return;
+  double s = 0.0;
+  for (int g = 0; g < n_seg; ++g) s += part[g * N + f];
+  rmse[f] = sqrt(s / static_cast<double>(T));
 }
 
 // ---- batched Scheduler.cov_matrix (kf_workers.py:112-147) ------------------------------------
@@ -681,6 +777,105 @@ int b200kf_run_masked(const b200kf_model* m, int32_t n_events, const uint8_t* ty
   p.logdet = logdet;
   p.n_terms = n_terms;
   return dispatch_masked(m, p, flags, static_cast<cudaStream_t>(stream));
+}
+
+int b200kf_score_products(const b200kf_model* m, int32_t n_windows, const int32_t* queue_len,
+                          const uint8_t* types, const double* times, const double* payload,
+                          const double* ref_pos, const double* x0, const double* P0, uint64_t first,
+                          uint64_t count, double* per_combo, b200kf_best_product* best, uint32_t flags,
+                          void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (m->desc.precision != B200KF_F64)
+    return set_error(B200KF_ERR_UNSUPPORTED, "b200kf_score_products is float64 only");
+  if (n_windows < 1 || n_windows > kMaxWindows)
+    return set_error(B200KF_ERR_UNSUPPORTED, "n_windows must be in [1, %d]", kMaxWindows);
+  if (!queue_len || !types || !times || !payload || !ref_pos || !x0 || !P0 || !best)
+    return set_error(B200KF_ERR_INVALID, "null argument");
+  ProductParams p;
+  memset(&p, 0, sizeof(p));
+  p.mc = m->mc;
+  p.n_windows = n_windows;
+  long long off = 0;
+  for (int w = 0; w < n_windows; ++w) {
+    if (queue_len[w] < 1) return set_error(B200KF_ERR_INVALID, "queue %d is empty: no sequence exists", w);
+    p.q_len[w] = queue_len[w];
+    p.q_off[w] = static_cast<int>(off);
+    off += queue_len[w];
+    if (off > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "more than 2^31-1 queued events");
+  }
+  unsigned long long total = 1;
+  for (int w = n_windows - 1; w >= 0; --w) {  // itertools.product: the last queue varies fastest
+    p.stride[w] = total;
+    if (total > (~0ULL) / static_cast<unsigned long long>(queue_len[w]))
+      return set_error(B200KF_ERR_UNSUPPORTED, "the product of the queue lengths exceeds 2^64");
+    total *= static_cast<unsigned long long>(queue_len[w]);
+  }
+  if (first > total || count > total - first)
+    return set_error(B200KF_ERR_INVALID, "sequence range exceeds the product of the queue lengths");
+  p.types = types;
+  p.times = times;
+  p.payload = payload;
+  p.ref = ref_pos;
+  memcpy(p.x0, x0, sizeof(double) * m->n);
+  memcpy(p.P0, P0, sizeof(double) * m->n * m->n);
+  p.first = first;
+  p.count = count;
+  p.per_combo = per_combo;
+  p.partials = search_scratch(m);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = dispatch_product(m, p, flags, st);
+  if (blocks < 0) return blocks;
+  product_final_kernel<<<1, 256, 0, st>>>(static_cast<const ProductPartial*>(p.partials), blocks, count, best);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
+}
+
+int b200kf_track_lerp(int64_t n_track, const double* track_t, const double* track_p, int32_t k,
+                      int64_t n_query, const double* query_t, double* out, void* stream) {
+  if (n_track < 1 || k < 1 || n_query < 0) return set_error(B200KF_ERR_INVALID, "need n_track >= 1, k >= 1");
+  if (n_query == 0) return B200KF_OK;
+  if (!track_t || !track_p || !query_t || !out) return set_error(B200KF_ERR_INVALID, "null argument");
+  const int tpb = 128;
+  track_lerp_kernel<<<static_cast<unsigned>((n_query + tpb - 1) / tpb), tpb, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_track, track_t, track_p, k, n_query, query_t, out);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
+}
+
+int b200kf_rmse_vs_track(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const void* traj,
+                         int32_t traj_ncomp, const double* ref_pos, double* rmse, void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (n_filters < 0 || n_steps < 1) return set_error(B200KF_ERR_INVALID, "need n_steps >= 1");
+  if (traj_ncomp < 3) return set_error(B200KF_ERR_INVALID, "the trajectory must hold the 3 position components");
+  if (n_filters == 0) return B200KF_OK;
+  if (!traj || !ref_pos || !rmse) return set_error(B200KF_ERR_INVALID, "null argument");
+  // time segments: enough threads to fill the GPU when there are few filters, bounded by the scratch
+  double* part = static_cast<double*>(search_scratch(m));
+  const long long cap = static_cast<long long>((kSchedOffset - 256) / sizeof(double));
+  long long seg = (static_cast<long long>(m->sm_count) * 2048 + n_filters - 1) / n_filters;
+  if (seg > n_steps) seg = n_steps;
+  if (seg * n_filters > cap) seg = cap / n_filters;
+  double* dst = part;
+  if (seg < 1) {  // more filters than scratch doubles: one segment, partials straight into rmse
+    seg = 1;
+    dst = rmse;
+  }
+  if (seg > 65535) seg = 65535;
+  const long long seg_len = (n_steps + seg - 1) / seg;
+  const int n_seg = static_cast<int>((n_steps + seg_len - 1) / seg_len);
+  const int tpb = 128;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(static_cast<unsigned>((n_filters + tpb - 1) / tpb), static_cast<unsigned>(n_seg));
+  if (m->desc.precision == B200KF_F32)
+    rmse_partial_kernel<float><<<grid, tpb, 0, st>>>(static_cast<const float*>(traj), traj_ncomp, n_filters, n_steps,
+                                                    ref_pos, seg_len, dst);
+  else
+    rmse_partial_kernel<double><<<grid, tpb, 0, st>>>(static_cast<const double*>(traj), traj_ncomp, n_filters,
+                                                     n_steps, ref_pos, seg_len, dst);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  rmse_final_kernel<<<grid.x, tpb, 0, st>>>(dst, n_seg, n_filters, n_steps, rmse);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return B200KF_OK;
 }
 
 int b200kf_select_greedy(const b200kf_model* m, int64_t n_events, const uint8_t* types,

@@ -126,6 +126,33 @@ struct SelectParams {
   double* P_final;             // DEVICE [I, n, n] or null
 };
 
+// run_brute_force_kalman_filter (KF_SensorFusion.ipynb:804-954): one event per window queue,
+// full filter with state per sequence, RMSE-vs-track objective.
+constexpr int kMaxWindows = 64;
+
+struct ProductParams {
+  ModelConst mc;
+  int n_windows;
+  int q_len[kMaxWindows];                 // events in queue w
+  int q_off[kMaxWindows];                 // first flattened event of queue w
+  unsigned long long stride[kMaxWindows]; // index stride of digit w (itertools.product: last fastest)
+  const unsigned char* types;             // DEVICE [E]
+  const double* times;                    // DEVICE [E]
+  const double* payload;                  // DEVICE [E, d]
+  const double* ref;                      // DEVICE [E, 3] track position at each event time
+  double x0[kMaxN];
+  double P0[kMaxN * kMaxN];
+  unsigned long long first, count;
+  double* per_combo;                      // DEVICE [count] or null
+  void* partials;                         // per-block ProductPartial
+};
+
+struct ProductPartial {
+  double score;            // min RMSE
+  unsigned long long index;
+  double runner_up;        // second-smallest RMSE seen
+};
+
 struct ScorePartial {
   double score;
   unsigned long long index;
@@ -143,6 +170,9 @@ int launch_score_m(const b200kf_model* m, ScoreParams p, unsigned flags, b200kf_
 
 template <int MODEL>
 int launch_masked_m(const b200kf_model* m, const MaskedParams& p, unsigned flags, cudaStream_t st);
+
+template <int MODEL>
+int launch_product_m(const b200kf_model* m, const ProductParams& p, unsigned flags, cudaStream_t st);
 
 template <int MODEL>
 int launch_select_m(const b200kf_model* m, const SelectParams& p, unsigned flags, cudaStream_t st);

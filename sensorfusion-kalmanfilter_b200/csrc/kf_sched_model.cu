@@ -350,4 +350,121 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
   return static_cast<int>(blocks);
 }
 
+// ---- product-of-queues brute force, RMSE objective (KF_SensorFusion.ipynb:804-954) -------------
+// Thread <-> candidate sequence: one event out of each window queue, index in itertools.product
+// order (last queue fastest, :873-875).  Every sequence runs the full filter WITH state from
+// (x0, P0) -- first event dt = 0 (:898) -- and is scored by the RMSE of the Euclidean position
+// error against the track interpolated at the event times (calculate_accuracy_metrics, :766-802;
+// the interpolation depends on the event only, so `ref` holds it per flattened event).  Events are
+// gathered from small L1-resident tables; the block/grid reduction keeps the FIRST minimum
+// (strict '<' at :933) and the runner-up score.
+__device__ __forceinline__ void product_merge(double& sc, unsigned long long& ix, double& ru, double osc,
+                                              unsigned long long oix, double oru) {
+  const bool take = osc < sc || (osc == sc && oix < ix);
+  const double loser = take ? sc : osc;
+  ru = fmin(fmin(ru, oru), loser);
+  if (take) {
+    sc = osc;
+    ix = oix;
+  }
+}
+
+template <int MODEL, int VAR>
+__global__ void __launch_bounds__(kScoreTpb) product_kernel(const ProductParams p) {
+  using MT = VariantTraits<MODEL, VAR, double>;
+  constexpr int n = MT::n;
+  constexpr int D = MT::d;
+  const int W = p.n_windows;
+  double best_sc = INFINITY, best_ru = INFINITY;
+  unsigned long long best_ix = ~0ULL;
+
+  for (unsigned long long idx = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+       idx < p.count; idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long c = p.first + idx;
+    typename MT::Filter flt;
+    flt.each([&](auto& b) {
+      b.load_cov(p.P0, n);
+      b.load_state(p.x0);
+    });
+    unsigned long long rem = c;
+    double tprev = 0.0, sse = 0.0;
+    for (int w = 0; w < W; ++w) {
+      const unsigned long long digit = rem / p.stride[w];
+      rem -= digit * p.stride[w];
+      const int e = p.q_off[w] + static_cast<int>(digit);
+      const double t = __ldg(p.times + e);
+      const double dt = (w == 0) ? 0.0 : t - tprev;  // :898
+      const int ty = __ldg(p.types + e);
+      double u[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) u[j] = __ldg(p.payload + static_cast<long long>(e) * D + j);
+      filter_predict<true>(flt, dt, p.mc, ty, u);
+      filter_update<true>(flt, dt, p.mc, ty, u);
+      double d2 = 0.0;  // |x[0:3] - ref|^2, then norm and square as numpy does (:788-790)
+      flt.each([&](const auto& b) {
+        b.for_each_state([&](auto G, double v) {
+          constexpr int g = G;
+          if constexpr (g < 3) {
+            const double d = v - __ldg(p.ref + static_cast<long long>(e) * 3 + g);
+            d2 += d * d;
+          }
+        });
+      });
+      const double nrm = sqrt(d2);
+      sse += nrm * nrm;
+      tprev = t;
+    }
+    const double metric = sqrt(sse / static_cast<double>(W));
+    if (p.per_combo != nullptr) p.per_combo[idx] = metric;
+    if (!isnan(metric)) product_merge(best_sc, best_ix, best_ru, metric, c, INFINITY);  // NaN < best is false (:933)
+  }
+
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double osc = __shfl_down_sync(0xffffffffu, best_sc, off);
+    const unsigned long long oix = __shfl_down_sync(0xffffffffu, best_ix, off);
+    const double oru = __shfl_down_sync(0xffffffffu, best_ru, off);
+    product_merge(best_sc, best_ix, best_ru, osc, oix, oru);
+  }
+  __shared__ ProductPartial sh[kScoreTpb / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = ProductPartial{best_sc, best_ix, best_ru};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ProductPartial r = sh[0];
+    for (int w = 1; w < kScoreTpb / 32; ++w) product_merge(r.score, r.index, r.runner_up, sh[w].score, sh[w].index, sh[w].runner_up);
+    static_cast<ProductPartial*>(p.partials)[blockIdx.x] = r;
+  }
+}
+
+template <>
+int launch_product_m<B200KF_INST_MODEL>(const b200kf_model* m, const ProductParams& p, unsigned flags,
+                                        cudaStream_t st) {
+  unsigned long long blocks = (p.count + kScoreTpb - 1) / kScoreTpb;
+  if (blocks > static_cast<unsigned long long>(kMaxSearchBlocks)) blocks = kMaxSearchBlocks;
+  if (blocks == 0) blocks = 1;
+  using MT = ModelTraits<B200KF_INST_MODEL, false, double>;
+  using SymF = typename SymTraits<B200KF_INST_MODEL, double>::Filter;
+  int var = VAR_DECOUPLED;
+  if (flags & B200KF_RUN_FORCE_DENSE) {
+    var = VAR_DENSE;
+  } else if (!(flags & B200KF_RUN_FORCE_DECOUPLED)) {
+    bool coupled = false;
+    for (int i = 0; i < MT::n; ++i)
+      for (int j = 0; j < MT::n; ++j)
+        if (MT::chain_of(i) != MT::chain_of(j) && p.P0[i * MT::n + j] != 0.0) coupled = true;
+    if (coupled) var = VAR_DENSE;
+    else if (m->use_sym && SymF::constants_equal(m->mc) && SymF::blocks_identical_host(p.P0, MT::n)) var = VAR_SYMMETRIC;
+  }
+  if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && !(flags & B200KF_RUN_FORCE_DENSE)) var = VAR_SYMMETRIC;
+  if (var == VAR_DENSE)
+    product_kernel<B200KF_INST_MODEL, VAR_DENSE><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  else if (var == VAR_SYMMETRIC)
+    product_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  else
+    product_kernel<B200KF_INST_MODEL, VAR_DECOUPLED><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  B200KF_CUDA_TRY(cudaGetLastError());
+  return static_cast<int>(blocks);
+}
+
 }  // namespace b200kf

@@ -232,6 +232,73 @@ class Engine:
         return {"x_final": x_f, "P_final": P_f, "traj": traj, "logdet": ld, "n_terms": nt}
 
 
+    # ------------------------------------------------------------------ product search / accuracy
+    def track_lerp(self, track_t, track_p, query_t, *, stream=None):
+        """Track positions at query times, linear with extrapolation (b200kf_track_lerp; the
+        interp1d calls of calculate_accuracy_metrics).  Returns torch CUDA f64 [n_query, k]."""
+        torch = _torch()
+        tt = self._dev(track_t, torch.float64)
+        tp = self._dev(track_p, torch.float64)
+        if tp.dim() == 1:
+            tp = tp[:, None].contiguous()
+        qt = self._dev(query_t, torch.float64)
+        out = torch.empty((int(qt.numel()), int(tp.shape[1])), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_track_lerp(int(tt.numel()), _ptr(tt), _ptr(tp), int(tp.shape[1]),
+                                                  int(qt.numel()), _ptr(qt), _ptr(out), self._stream(stream)))
+        return out
+
+    def rmse_vs_track(self, traj, ref_pos, *, stream=None):
+        """Per-filter total_position_rmse of a time-major trajectory [T, ncomp>=3, N] against
+        ref_pos [T, 3] (b200kf_rmse_vs_track).  Returns torch CUDA f64 [N]."""
+        torch = _torch()
+        tr = self._dev(traj, self.real)
+        ref = self._dev(ref_pos, torch.float64)
+        T, nc, N = (int(v) for v in tr.shape)
+        if tuple(ref.shape) != (T, 3):
+            raise ValueError(f"ref_pos must be [T={T}, 3]")
+        out = torch.empty((N,), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_rmse_vs_track(self._h, N, T, _ptr(tr), nc, _ptr(ref), _ptr(out),
+                                                     self._stream(stream)))
+        return out
+
+    def score_products(self, queue_len, types, times, payload, ref_pos, x0, P0, *, first=0, count=None,
+                       want_per_combo=False, mode="auto", stream=None):
+        """Score the sequences [first, first+count) of itertools.product(*queues) by RMSE against
+        the track (b200kf_score_products).  types/times [E], payload [E, d], ref_pos [E, 3]: the
+        queues' events flattened.  Returns (best: dict, per_combo: torch [count] or None)."""
+        torch = _torch()
+        sp = self.spec
+        ql = np.ascontiguousarray(queue_len, dtype=np.int32)
+        total = 1
+        for q in ql:
+            total *= int(q)
+        if count is None:
+            count = total - first
+        types_d = self._dev(types, torch.uint8)
+        times_d = self._dev(times, torch.float64)
+        pay_d = self._dev(payload, torch.float64)
+        ref_d = self._dev(ref_pos, torch.float64)
+        E = int(ql.sum())
+        if int(types_d.numel()) != E or int(times_d.numel()) != E or tuple(pay_d.shape) != (E, sp.d) \
+                or tuple(ref_d.shape) != (E, 3):
+            raise ValueError(f"need types/times [E={E}], payload [E, {sp.d}], ref_pos [E, 3]")
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        P0 = np.ascontiguousarray(P0, dtype=np.float64)
+        per = torch.empty((count,), dtype=torch.float64, device=self.device) if want_per_combo else None
+        best_d = torch.zeros((ctypes.sizeof(_lib.BestProduct),), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_score_products(
+                self._h, int(ql.shape[0]), ql.ctypes.data_as(POINTER(c_int32)), _ptr(types_d), _ptr(times_d),
+                _ptr(pay_d), _ptr(ref_d), x0.ctypes.data_as(POINTER(c_double)), P0.ctypes.data_as(POINTER(c_double)),
+                int(first), int(count), _ptr(per), _ptr(best_d), _MODES[mode], self._stream(stream)))
+        b = _lib.BestProduct.from_buffer_copy(bytes(best_d.cpu().numpy().tobytes()))
+        none = (1 << 64) - 1
+        best = {"score": b.score, "index": None if b.index == none else int(b.index),
+                "runner_up_score": b.runner_up_score, "n_scored": int(b.n_scored)}
+        return best, per
+
     def select_greedy(self, types, times, periods, t_prev, P0, *, max_sel=None, mode="auto", stream=None):
         """Greedy one-event-per-window selection (b200kf_select_greedy) for I instances over one
         event list.  Returns (list of int32 numpy index arrays, P_final torch [I,n,n])."""

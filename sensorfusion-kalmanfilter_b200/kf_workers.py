@@ -489,7 +489,7 @@ class KF_SensorFusion:
                                     initial_state=None, print_output=False):
         return self._adaptive(start_idx, end_idx, R_threshold, initial_pt, initial_state, True, print_output)
 
-    # ---- accuracy metric (kf_workers.py:1162-1216; host-side, linear interpolation) ------------
+    # ---- accuracy metric (kf_workers.py:1162-1216) ----------------------------------------------
     def calculate_accuracy_metrics(self, candidate_trajectory):
         if not candidate_trajectory:
             print("Candidate trajectory is empty. Cannot calculate accuracy.")
@@ -506,10 +506,15 @@ class KF_SensorFusion:
         gt_p = np.array([s[1:4] for s in sec], dtype=np.float64)
         ct = np.array([s[0] for s in candidate_trajectory], dtype=np.float64)
         cp = np.array([s[1:4] for s in candidate_trajectory], dtype=np.float64)
-        interp = np.stack([_lerp_extrapolate(ct, gt_t, gt_p[:, k]) for k in range(3)], axis=1)
+        # interpolation and RMSE on the device (b200kf_track_lerp / b200kf_rmse_vs_track); the
+        # per-sample error arrays the reference also returns are differences of those outputs
+        eng = self._engine()
+        ref_d = eng.track_lerp(gt_t, gt_p, ct)
+        rmse = np.float64(eng.rmse_vs_track(cp[:, :, None], ref_d)[0].item())
+        interp = ref_d.cpu().numpy()
         err = cp - interp
         eu = np.linalg.norm(err, axis=1)
-        return {"total_position_rmse": np.sqrt(np.mean(eu ** 2)), "position_errors": err, "euclidean_errors": eu,
+        return {"total_position_rmse": rmse, "position_errors": err, "euclidean_errors": eu,
                 "candidate_times": ct, "candidate_positions": cp, "ground_truth_interp": interp,
                 "gt_start_time": c0, "gt_end_time": c1}
 
@@ -571,12 +576,13 @@ class KF_SensorFusion:
 
 
 def _lerp_extrapolate(x, xp, fp):
-    """scipy interp1d(kind='linear', fill_value='extrapolate') for sorted xp (kf_workers.py:1195-1197)."""
+    """scipy interp1d(kind='linear', fill_value='extrapolate') for sorted xp (kf_workers.py:1195-1197),
+    in scipy's own two-weight form (interp1d._call_linear)."""
     if len(xp) == 1:
         return np.full_like(x, fp[0], dtype=np.float64)
-    i = np.clip(np.searchsorted(xp, x, side="right") - 1, 0, len(xp) - 2)
-    slope = (fp[i + 1] - fp[i]) / (xp[i + 1] - xp[i])
-    return fp[i] + slope * (x - xp[i])
+    hi = np.clip(np.searchsorted(xp, x), 1, len(xp) - 1)
+    lo = hi - 1
+    return ((x - xp[lo]) / (xp[hi] - xp[lo])) * fp[hi] + ((xp[hi] - x) / (xp[hi] - xp[lo])) * fp[lo]
 
 
 def find_start_idx_for_time_offset(sensor_fusion, time_offset, t0=1697739552.3362827):

@@ -205,3 +205,26 @@ def test_notebook_product_search(golden):
         np.testing.assert_allclose(out["final_state"], g[f"{tag}_final_state"], **TOL)
         np.testing.assert_allclose(out["final_covariance"], g[f"{tag}_final_cov"], **TOL)
         np.testing.assert_allclose(states_arr(out["trajectory"]), g[f"{tag}_trajectory"], **TOL)
+
+
+def test_lerp_is_bit_identical_to_scipy():
+    from scipy.interpolate import interp1d
+    rng = np.random.default_rng(5)
+    xp = np.sort(rng.uniform(1.6977e9, 1.6977e9 + 50, 40))
+    fp = rng.normal(4.6e6, 30.0, 40)
+    x = np.concatenate([rng.uniform(xp[0] - 5, xp[-1] + 5, 200), xp[::3]])  # incl. knots and extrapolation
+    want = interp1d(xp, fp, kind="linear", fill_value="extrapolate")(x)
+    np.testing.assert_array_equal(ko.lerp_extrapolate(x, xp, fp), want)
+
+
+def test_accuracy_metrics(golden):
+    """calculate_accuracy_metrics (kf_workers.py:1162-1216) incl. the < 2-sample fallback."""
+    g = golden("ca15_accuracy.npz")
+    ev = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    m = ko.get_model("CA15")
+    gt, _, _, _ = ko.run_full(m, ev, 0, 400)
+    for tag, key in (("cand_states", "rmse"), ("tiny_states", "tiny_rmse")):
+        cand = [tuple(r) for r in g[tag]]
+        rmse, interp = ko.accuracy_metrics(cand, gt)
+        np.testing.assert_allclose(rmse, g[key], rtol=1e-9)
+        np.testing.assert_allclose(interp, g["ground_truth_interp" if key == "rmse" else "tiny_interp"], rtol=1e-11)
