@@ -51,7 +51,8 @@ extern "C" {
 #define B200KF_EV_PREDICT_ONLY 2 /* predict, no update     kf_workers.py:74-82, 1060-1159 */
 
 /* b200kf_run_batch flags */
-#define B200KF_RUN_AUTO 0u            /* decoupled kernel when every P is chain-compatible, else dense */
+#define B200KF_RUN_AUTO 0u            /* the cheapest valid variant, decided on the device per launch:
+                                         shared > symmetric > decoupled > dense */
 #define B200KF_RUN_FORCE_DENSE 1u     /* always the dense (all-states-coupled) kernel */
 #define B200KF_RUN_FORCE_DECOUPLED 2u /* caller guarantees chain-compatible P (no check) */
 #define B200KF_RUN_AGG_CONTINUE 4u    /* agg holds the running aggregates of earlier chunks */
@@ -59,6 +60,11 @@ extern "C" {
                                          identical across axes (and the model's rates agree): one
                                          covariance recursion per filter; falls back to
                                          FORCE_DECOUPLED when the model / launch cannot use it */
+
+#define B200KF_RUN_FORCE_SHARED 16u   /* caller guarantees FORCE_SYMMETRIC's conditions AND that every
+                                         filter of the launch carries the same P: one covariance /
+                                         gain recursion per launch; falls back to FORCE_SYMMETRIC
+                                         when the model / launch cannot use it */
 
 typedef struct b200kf_model b200kf_model; /* opaque, library-owned */
 

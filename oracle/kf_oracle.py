@@ -29,7 +29,7 @@ import math
 
 import numpy as np
 
-GPS, IMU = 0, 1  # event type codes used by the packed (array) form
+GPS, IMU, PREDICT_ONLY = 0, 1, 2  # event type codes used by the packed (array) form
 
 
 # --------------------------------------------------------------------------------------
@@ -238,7 +238,7 @@ def step(model, x, P, etype, dt, payload, do_update=True):
     if model.imu_is_control and etype == IMU:
         return predict(model, x, P, dt, u=payload[..., : model.d])
     x, P = predict(model, x, P, dt)
-    if not do_update:
+    if not do_update or etype == PREDICT_ONLY:  # no-update events (kf_workers.py:74-82, :1060-1159)
         return x, P
     if etype == GPS:
         return update(x, P, payload[..., : model.m_gps], model.H_gps(), model.R_gps())

@@ -19,6 +19,7 @@ MODEL_CV6, MODEL_CA8, MODEL_BIAS9, MODEL_CA15 = 0, 1, 2, 3
 F64, F32 = 0, 1
 EV_GPS, EV_IMU, EV_PREDICT_ONLY = 0, 1, 2
 RUN_AUTO, RUN_FORCE_DENSE, RUN_FORCE_DECOUPLED, RUN_AGG_CONTINUE, RUN_FORCE_SYMMETRIC = 0, 1, 2, 4, 8
+RUN_FORCE_SHARED = 16
 
 
 class ModelDesc(Structure):

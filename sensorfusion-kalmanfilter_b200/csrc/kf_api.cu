@@ -515,6 +515,8 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
   m->use_sym = 1;
   if (const char* s = getenv("B200KF_SYM")) m->use_sym = atoi(s) != 0;
+  m->use_shared = 1;
+  if (const char* s = getenv("B200KF_SHARED")) m->use_shared = atoi(s) != 0;
   if (const char* s = getenv("B200KF_TPB")) {
     const int v = atoi(s);
     if (v >= 32 && v <= 256 && v % 32 == 0) m->tpb = v;
@@ -567,8 +569,9 @@ int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
     return set_error(B200KF_ERR_INVALID, "types, dts and payload are required when n_steps > 0");
   if (traj && (traj_ncomp < 1 || traj_ncomp > m->n))
     return set_error(B200KF_ERR_INVALID, "traj_ncomp must be in [1, %d]", m->n);
-  if ((flags & B200KF_RUN_FORCE_DENSE) && (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC)))
-    return set_error(B200KF_ERR_INVALID, "FORCE_DENSE excludes FORCE_DECOUPLED / FORCE_SYMMETRIC");
+  if ((flags & B200KF_RUN_FORCE_DENSE) &&
+      (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC | B200KF_RUN_FORCE_SHARED)))
+    return set_error(B200KF_ERR_INVALID, "FORCE_DENSE excludes FORCE_DECOUPLED / FORCE_SYMMETRIC / FORCE_SHARED");
   RunParams p;
   p.mc = m->mc;
   p.n_filters = n_filters;

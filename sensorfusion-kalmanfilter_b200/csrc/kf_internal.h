@@ -29,12 +29,13 @@ struct b200kf_model {
   int tpb;      // threads per block for the filter kernels (env B200KF_TPB)
   HostWorkspace host_ws;
   int use_sym;  // 1: axis-symmetric kernel when every filter's chains share one covariance (env B200KF_SYM=0 disables)
+  int use_shared;  // 1: shared-covariance kernel when every filter of a launch carries the same P (env B200KF_SHARED=0 disables)
   int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };
 
 namespace b200kf {
 
-constexpr size_t kArenaBytes = 4 << 20;
+constexpr size_t kArenaBytes = 8 << 20;
 constexpr size_t kSchedOffset = 1 << 20;  // packed (dt, type) records of the TMA kernel
 constexpr int kMaxSearchBlocks = 8192;
 
@@ -66,7 +67,7 @@ struct RunParams {
   double gate_threshold;
   int gate_enabled;
   int agg_continue;
-  const int* dense_flag;  // AUTO mode: int[2] {coupled, asymmetric}; a kernel runs only if they select its mode
+  const int* dense_flag;  // AUTO mode: int[3] {coupled, asymmetric, P differs between filters}; a kernel runs only if they select its mode
 };
 
 constexpr int kMaxEvents = 32;

@@ -30,11 +30,14 @@ struct LaunchCfg {
 };
 
 // AUTO dispatch: mode_flags[0] != 0 -> some P couples chains (dense kernel); else mode_flags[1] != 0
-// -> the chains of some filter differ (per-chain kernel); else the axis-symmetric kernel.
-enum : int { MODE_DECOUPLED = 0, MODE_DENSE = 1, MODE_SYMMETRIC = 2 };
+// -> the chains of some filter differ (per-chain kernel); else mode_flags[2] != 0 -> the filters'
+// covariances differ from each other (axis-symmetric kernel, one covariance per filter); else all
+// filters of the launch carry the SAME covariance (shared-covariance kernel, one per launch).
+enum : int { MODE_DECOUPLED = 0, MODE_DENSE = 1, MODE_SYMMETRIC = 2, MODE_SHARED = 3 };
 __device__ __forceinline__ bool mode_selected(const int* flags, int mine) {
   if (flags == nullptr) return true;
-  const int actual = flags[0] ? MODE_DENSE : (flags[1] ? MODE_DECOUPLED : MODE_SYMMETRIC);
+  const int actual = flags[0] ? MODE_DENSE
+                              : (flags[1] ? MODE_DECOUPLED : (flags[2] ? MODE_SYMMETRIC : MODE_SHARED));
   return actual == mine;
 }
 
@@ -190,7 +193,8 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
 // LDG kernel shows (warps that win the issue arbitration finish early and leave the FP64 pipe
 // half empty at the end).
 // ------------------------------------------------------------------------------------------
-constexpr int kTmaThreads = 896;  // 7 warps per SM sub-partition; 896 * 72 regs = 63 K registers
+constexpr int kTmaThreads = 896;            // math threads: 7 warps per SM sub-partition, one filter each
+constexpr int kWsThreads = kTmaThreads + 32;  // + the producer warp (928 * 64 regs = 58 K registers)
 #ifndef B200KF_CHUNK
 #define B200KF_CHUNK 2
 #endif
@@ -200,8 +204,9 @@ constexpr int kTmaThreads = 896;  // 7 warps per SM sub-partition; 896 * 72 regs
 constexpr int kChunk = B200KF_CHUNK;    // steps per stage
 constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 KB of shared memory)
 
-struct SchedRec {  // 16 bytes: bulk copies need 16-byte granularity
+struct SchedRec {  // 32 bytes (bulk copies need 16-byte granularity)
   double dt;
+  double w0, w1;  // dt / r_imu of the symmetric group's two states: gains folded with dt (Sym2Filter::step_lean)
   int type;
   int pad;
 };
@@ -232,6 +237,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity), "r"(0x100000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
+#ifndef B200KF_L2PF
+#define B200KF_L2PF 0
+#endif
+constexpr int kL2Prefetch = B200KF_L2PF;  // chunks of look-ahead for the L2 prefetch of payload rows (0 = off)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -241,14 +253,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 
 static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, const double* __restrict__ dts,
-                                     int T, SchedRec* __restrict__ out) {
+                                     int T, double r0, double r1, SchedRec* __restrict__ out, int* n_imu) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < T) out[k] = SchedRec{dts[k], static_cast<int>(types[k]), 0};
+  const bool imu = k < T && types[k] == EV_IMU;
+  if (k < T) out[k] = SchedRec{dts[k], dts[k] / r0, dts[k] / r1, static_cast<int>(types[k]), 0};
+  const unsigned votes = __ballot_sync(0xffffffffu, imu);  // the launch's IMU count for the lean aggregate
+  if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(n_imu, __popc(votes));
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL>
-__global__ void __launch_bounds__(kTmaThreads, 1)
-    kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched) {
+__global__ void __launch_bounds__(kWsThreads, 1)
+    kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched, const int* __restrict__ n_imu) {
   using MT = ModelTraits<MODEL, false, real>;
   using Flt = std::conditional_t<SYM, typename MT::Sym2, typename MT::Dec2>;
   constexpr int n = MT::n;
@@ -271,7 +286,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const bool active = tid < nfb;
   const int T = p.n_steps;
   const int nchunks = (T + kChunk - 1) / kChunk;
-  const unsigned row_bytes = static_cast<unsigned>(nfb * sizeof(real));
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -282,22 +296,35 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   __syncthreads();
 
-  const real* pay = static_cast<const real*>(p.payload) + base;
-  auto issue = [&](int chunk) {  // elected thread only
-    const int s = chunk % kStages;
-    const int k0 = chunk * kChunk;
-    const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
-    mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * (D * row_bytes + sizeof(SchedRec)));
-    bulk_g2s(sched_buf + s * kChunk, sched + k0, static_cast<unsigned>(steps * sizeof(SchedRec)), &full[s]);
-    real* dst = stage_buf + s * kStageReals;
-    for (int c = 0; c < steps; ++c)
+  if (tid >= kTmaThreads) {
+    // ---- producer warp: one lane keeps the ring full, decoupled from the math warps' progress ----
+    if (tid == kTmaThreads) {
+      const unsigned row_bytes = static_cast<unsigned>(nfb * sizeof(real));
+      const real* pay = static_cast<const real*>(p.payload) + base;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int s = chunk % kStages;
+        if (chunk >= kStages) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kStages - 1) & 1u);
+        const int k0 = chunk * kChunk;
+        const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+        mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * (D * row_bytes + sizeof(SchedRec)));
+        bulk_g2s(sched_buf + s * kChunk, sched + k0, static_cast<unsigned>(steps * sizeof(SchedRec)), &full[s]);
+        real* dst = stage_buf + s * kStageReals;
+        for (int c = 0; c < steps; ++c)
 #pragma unroll
-      for (int j = 0; j < D; ++j)
-        bulk_g2s(dst + (c * D + j) * kTmaThreads, pay + (static_cast<long long>(k0 + c) * D + j) * N, row_bytes,
-                 &full[s]);
-  };
-  if (tid == 0) {
-    for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
+          for (int j = 0; j < D; ++j)
+            bulk_g2s(dst + (c * D + j) * kTmaThreads, pay + (static_cast<long long>(k0 + c) * D + j) * N, row_bytes,
+                     &full[s]);
+        if constexpr (kL2Prefetch > 0) {  // pull the rows of a later chunk into L2 ahead of the ring
+          const int kp = (chunk + kL2Prefetch) * kChunk;
+          for (int c = 0; c < kChunk; ++c)
+            if (kp + c < T)
+#pragma unroll
+              for (int j = 0; j < D; ++j)
+                bulk_prefetch_l2(pay + (static_cast<long long>(kp + c) * D + j) * N, row_bytes);
+        }
+      }
+    }
+    return;
   }
 
   Flt flt;
@@ -310,17 +337,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   long long acc_max = 0;  // max det as raw bits: positive doubles order like their bit patterns
   int acc_expo = 0;
   bool ok = true;
+  // lean aggregate of the symmetric filter: IMU events contribute det / (r0 r1) of ONE chain, the
+  // constant and the chain multiplicity are restored after the loop; validity (every det finite
+  // and > 0) is tracked with integer min / max of the raw bits instead of an FP64 compare
+  constexpr bool LEAN = SYM && !FULL && Flt::lean_ok;
+  long long lean_max_imu = 0;
+  int lean_sign = 0;  // sticky sign bit of every det seen (a zero det zeroes acc_mant; NaN / inf show in the max)
 
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int s = chunk % kStages;
     const unsigned use = static_cast<unsigned>(chunk / kStages);
-    if (tid == 0) {
-      const int nxt = chunk + kStages - 1;  // refill the stage chunk-1 used, once every warp left it
-      if (nxt < nchunks) {
-        if (chunk >= 1) mbar_wait(&empty[nxt % kStages], static_cast<unsigned>((chunk - 1) / kStages) & 1u);
-        issue(nxt);
-      }
-    }
     mbar_wait(&full[s], use & 1u);
     const int k0 = chunk * kChunk;
     const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
@@ -335,6 +361,23 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           for (int j = 0; j < D; ++j) u[j] = sb[(c * D + j) * kTmaThreads];
           const real dt = static_cast<real>(rec.dt);
           const int ty = rec.type;
+          if constexpr (LEAN) {
+            real v;
+            const bool imu = flt.step_lean(dt, static_cast<real>(rec.w0), static_cast<real>(rec.w1), ty, p.mc, u, v);
+            const long long vb = __double_as_longlong(double(v));
+            lean_sign |= __double2hiint(double(v));
+            if (imu) {
+              lean_max_imu = max(lean_max_imu, vb);
+            } else {
+              acc_max = max(acc_max, vb);
+            }
+            const double m = acc_mant * double(v);
+            const int hi = __double2hiint(m);
+            const int e = ((hi >> 20) & 0x7ff) - 1023;
+            acc_expo += e;
+            acc_mant = __hiloint2double(hi - (e << 20), __double2loint(m));
+            continue;
+          }
           flt.predict(dt, p.mc);
           bool do_update = (ty != EV_PREDICT_ONLY);
           if constexpr (FULL) {
@@ -373,10 +416,26 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     real* Pg = static_cast<real*>(p.P) + f * (n * n);
     flt.store(xg, Pg, n);
   }
+  int lean_n_imu = 0;
+  if constexpr (LEAN) {
+    if (T > 0)
+      ok = ok && lean_sign >= 0 && acc_mant >= 1.0 && acc_max < 0x7ff0000000000000LL &&
+           lean_max_imu < 0x7ff0000000000000LL;
+    lean_n_imu = *n_imu;  // IMU events of the launch, counted by pack_schedule_kernel
+  }
   if (p.agg != nullptr) {
     double* a = p.agg + f * 4;
     double mx = (T > 0) ? log(__longlong_as_double(acc_max)) : -INFINITY;
     double sm = log(acc_mant) + static_cast<double>(acc_expo) * 0.6931471805599453094;
+    if constexpr (LEAN) {  // restore r0 r1 on the IMU terms, then the chain multiplicity
+      const double lr = log(double(flt.r0r1));
+      if (T > 0) {
+        mx = (acc_max > 0) ? mx : -INFINITY;
+        if (lean_n_imu > 0) mx = fmax(mx, log(__longlong_as_double(lean_max_imu)) + lr);
+      }
+      mx *= static_cast<double>(Flt::M);
+      sm = (sm + static_cast<double>(lean_n_imu) * lr) * static_cast<double>(Flt::M);
+    }
     double cnt = static_cast<double>(T);
     if (p.agg_continue) {
       mx = fmax(mx, a[0]);
@@ -392,6 +451,294 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const int bad = ok ? 0 : 1;
     p.status[f] = p.agg_continue ? (p.status[f] | bad) : bad;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-covariance variant.  The covariance / gain recursion never reads a measurement
+// (kf_workers.py:546-549, 616-621, 711 touch no z) and the event schedule is shared by the launch,
+// so when every filter ALSO starts from the same P -- Monte-Carlo seeds of one rate (BASELINE
+// configs[1]), or the reference's fixed P0 (kf_workers.py:651) for a whole batch -- all filters
+// have the same gains at every step.  One lane of a dedicated producer warp per CTA runs that
+// recursion ONCE (in float64, whatever the model precision), writes a 64-byte gain record per step
+// into the ring stage next to the TMA'd payload rows, and issues the bulk copies; the 28 math warps
+// only apply the gains to their filter's state: 6 FMAs per axis and event.  Validity (all P
+// bit-identical, axis-symmetric, chain-compatible; equal rate constants) is checked per launch on
+// the device like the other variants.  The kernel is a pure HBM stream.
+// ------------------------------------------------------------------------------------------
+constexpr int kMathThreads = kTmaThreads;           // 896 consumer threads, one filter each
+constexpr int kSharedThreads = kMathThreads + 64;   // + the gain warp + the copy warp
+
+struct GainRec {  // 56 bytes
+  double dt;
+  double g00, g01, g10, g11;  // IMU: K diag(dt, dt); GPS: (k0, -, k1, -)
+  double logdet;              // log det P of the whole filter after the step (per-step output only)
+  int type;                   // event type actually applied
+  int pad;
+};
+
+template <int MODEL, typename real, bool FULL>
+__global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_kernel(const RunParams p) {
+  using MT = ModelTraits<MODEL, false, real>;
+  using S2 = typename MT::Sym2;
+  using B0 = typename S2::Lead;
+  constexpr int n = MT::n;
+  constexpr int D = MT::d;
+  constexpr int M = S2::M;
+  static_assert(S2::lean_ok, "shared-covariance kernel: (position, velocity) pseudo-measurement chains only");
+  if (!mode_selected(p.dense_flag, MODE_SHARED)) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kStages][kChunk][D][kMathThreads]
+  constexpr size_t kStageReals = static_cast<size_t>(kChunk) * D * kMathThreads;
+  GainRec* gain_buf = reinterpret_cast<GainRec*>(stage_buf + kStages * kStageReals);  // [kStages][kChunk]
+  double* fin = reinterpret_cast<double*>(gain_buf + kStages * kChunk);  // a, b, c, max, sum, last, ok
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(fin + 8);
+  unsigned long long* empty = full + kStages;
+
+  const int tid = threadIdx.x;
+  const long long N = p.n_filters;
+  const long long base = static_cast<long long>(blockIdx.x) * kMathThreads;
+  const int nfb = static_cast<int>((N - base) < kMathThreads ? (N - base) : kMathThreads);
+  const int T = p.n_steps;
+  const int nchunks = (T + kChunk - 1) / kChunk;
+  const unsigned row_bytes = static_cast<unsigned>(nfb * sizeof(real));
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 2);  // the copy warp's expect_tx arrival + the gain warp's arrival
+      mbar_init(&empty[s], kMathThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= kMathThreads + 32) {
+    // ---------------- copy warp: one lane keeps the payload ring full ------------------------------
+    if (tid == kMathThreads + 32) {
+      const real* pay = static_cast<const real*>(p.payload) + base;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int s = chunk % kStages;
+        if (chunk >= kStages) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kStages - 1) & 1u);
+        const int k0 = chunk * kChunk;
+        const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+        mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * D * row_bytes);
+        real* dst = stage_buf + s * kStageReals;
+        for (int cc = 0; cc < steps; ++cc)
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            bulk_g2s(dst + (cc * D + j) * kMathThreads, pay + (static_cast<long long>(k0 + cc) * D + j) * N,
+                     row_bytes, &full[s]);
+        if constexpr (kL2Prefetch > 0) {
+          const int kp = (chunk + kL2Prefetch) * kChunk;
+          for (int cc = 0; cc < kChunk; ++cc)
+            if (kp + cc < T)
+#pragma unroll
+              for (int j = 0; j < D; ++j)
+                bulk_prefetch_l2(pay + (static_cast<long long>(kp + cc) * D + j) * N, row_bytes);
+        }
+      }
+    }
+  } else if (tid >= kMathThreads) {
+    // ---------------- gain warp: the one covariance recursion of the launch ------------------------
+    if (tid == kMathThreads) {
+      // every filter carries the same P: read this CTA's first filter (only this CTA writes it, at the end)
+      const real* Pg = static_cast<const real*>(p.P) + base * (n * n);
+      double a = double(Pg[B0::gidx(0) * n + B0::gidx(0)]);
+      double b = 0.5 * (double(Pg[B0::gidx(0) * n + B0::gidx(1)]) + double(Pg[B0::gidx(1) * n + B0::gidx(0)]));
+      double c = double(Pg[B0::gidx(1) * n + B0::gidx(1)]);
+      const double q0 = p.mc.q[B0::gidx(0)], q1 = p.mc.q[B0::gidx(1)];
+      const double r0 = p.mc.r_imu[B0::gidx(0)], r1 = p.mc.r_imu[B0::gidx(1)];
+      const double rg = p.mc.r_gps[B0::gps(0)];
+      const double r0r1 = r0 * r1, ir0 = 1.0 / r0, ir1 = 1.0 / r1;
+      LogDetAcc acc;
+      bool ok = true;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int s = chunk % kStages;
+        if (chunk >= kStages) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kStages - 1) & 1u);
+        const int k0 = chunk * kChunk;
+        const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+        for (int cc = 0; cc < steps; ++cc) {
+          const double dt = __ldg(p.dts + k0 + cc);
+          const int ty = __ldg(p.types + k0 + cc);
+          GainRec rec;
+          rec.dt = dt;
+          rec.type = ty;
+          rec.pad = 0;
+          rec.g00 = rec.g01 = rec.g10 = rec.g11 = 0.0;
+          // same formulas as Sym2Filter::step_lean, evaluated once for the launch
+          const double bn = fma(dt, c, b);
+          const double ap = fma(dt, b + bn, fma(q0, dt, a));
+          const double cp = fma(q1, dt, c);
+          double det;
+          if (ty == EV_IMU) {
+            const double detp = fma(ap, cp, -(bn * bn));
+            const double t0 = fma(ap, r1, detp), t1 = fma(cp, r0, detp);
+            const double inv = fast_rcp(fma(r0, cp + r1, t0));
+            const double i0 = r0 * inv, i1 = r1 * inv;
+            a = t0 * i0;
+            c = t1 * i1;
+            b = bn * (i0 * r1);
+            const double w0 = dt * ir0, w1 = dt * ir1;
+            rec.g00 = a * w0;
+            rec.g10 = b * w0;
+            rec.g01 = b * w1;
+            rec.g11 = c * w1;
+            det = detp * inv * r0r1;
+          } else if (ty == EV_GPS) {
+            const double inv = fast_rcp(ap + rg);
+            rec.g00 = ap * inv;
+            rec.g10 = bn * inv;
+            const double g = rg * inv;
+            c = fma(-rec.g10, bn, cp);
+            a = ap * g;
+            b = bn * g;
+            det = fma(a, c, -(b * b));
+          } else {
+            a = ap;
+            b = bn;
+            c = cp;
+            det = fma(a, c, -(b * b));
+          }
+          ok = ok && (det > 0.0) && (det < INFINITY);
+          const double detM = S2::powM(det);
+          acc.add(detM);
+          rec.logdet = 0.0;
+          if constexpr (FULL) {
+            if (p.logdet != nullptr) rec.logdet = log(detM);
+          }
+          gain_buf[s * kChunk + cc] = rec;
+        }
+        mbar_arrive(&full[s]);  // release: the gain records are visible to whoever sees the phase flip
+      }
+      fin[0] = a;
+      fin[1] = b;
+      fin[2] = c;
+      fin[3] = (T > 0) ? log(acc.maxdet) : -INFINITY;
+      fin[4] = acc.sum_log();
+      fin[5] = (T > 0) ? log(acc.last) : 0.0;
+      fin[6] = ok ? 1.0 : 0.0;
+    }
+  } else {
+    // ---------------- math warps: x += G [v + u dt, u] --------------------------------------------
+    const bool active = tid < nfb;
+    const long long f = base + tid;
+    real x0[M], x1[M];
+    if (active) {
+      const real* xg = static_cast<const real*>(p.x) + f * n;
+      S2::members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        x0[m] = xg[BM::gidx(0)];
+        x1[m] = xg[BM::gidx(1)];
+      });
+    }
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int s = chunk % kStages;
+      mbar_wait(&full[s], static_cast<unsigned>(chunk / kStages) & 1u);
+      const int k0 = chunk * kChunk;
+      const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+      if (active) {
+        const real* sb = stage_buf + s * kStageReals + tid;
+#pragma unroll
+        for (int cc = 0; cc < kChunk; ++cc) {
+          if (cc < steps) {
+            const GainRec* rec = gain_buf + s * kChunk + cc;
+            const real dt = static_cast<real>(rec->dt);
+            const int ty = rec->type;
+            real u[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) u[j] = sb[(cc * D + j) * kMathThreads];
+            if (ty == EV_IMU) {
+              const real g00 = static_cast<real>(rec->g00), g01 = static_cast<real>(rec->g01);
+              const real g10 = static_cast<real>(rec->g10), g11 = static_cast<real>(rec->g11);
+              S2::members([&](auto Bm, int m) {
+                using BM = decltype(Bm);
+                const real acc = u[BM::pz(1)];
+                const real sv = fma(acc, dt, x1[m]);
+                x0[m] = fma(g00, sv, fma(g01, acc, fma(dt, x1[m], x0[m])));
+                x1[m] = fma(g10, sv, fma(g11, acc, x1[m]));
+              });
+            } else if (ty == EV_GPS) {
+              const real k0g = static_cast<real>(rec->g00), k1g = static_cast<real>(rec->g10);
+              S2::members([&](auto Bm, int m) {
+                using BM = decltype(Bm);
+                const real xp = fma(dt, x1[m], x0[m]);
+                const real y = u[BM::gps(0)] - xp;
+                x0[m] = fma(k0g, y, xp);
+                x1[m] = fma(k1g, y, x1[m]);
+              });
+            } else {
+#pragma unroll
+              for (int m = 0; m < M; ++m) x0[m] = fma(dt, x1[m], x0[m]);
+            }
+            if constexpr (FULL) {
+              const long long k = k0 + cc;
+              if (p.traj != nullptr) {
+                real* tr = static_cast<real*>(p.traj) + (k * p.traj_ncomp) * N + f;
+                const int nc = p.traj_ncomp;
+                S2::members([&](auto Bm, int m) {
+                  using BM = decltype(Bm);
+                  if (BM::gidx(0) < nc) __stcs(tr + static_cast<long long>(BM::gidx(0)) * N, x0[m]);
+                  if (BM::gidx(1) < nc) __stcs(tr + static_cast<long long>(BM::gidx(1)) * N, x1[m]);
+                });
+              }
+              if (p.logdet != nullptr) __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(rec->logdet));
+              if (p.used != nullptr) p.used[k * N + f] = (ty != EV_PREDICT_ONLY) ? 1 : 0;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    }
+    if (active) {
+      real* xg = static_cast<real*>(p.x) + f * n;
+      S2::members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        xg[BM::gidx(0)] = x0[m];
+        xg[BM::gidx(1)] = x1[m];
+      });
+    }
+  }
+
+  __syncthreads();  // the producer's final covariance and aggregates
+  if (tid >= nfb) return;
+  const long long f = base + tid;
+  if (T > 0) {
+    real* Pg = static_cast<real*>(p.P) + f * (n * n);
+    const real a = static_cast<real>(fin[0]), b = static_cast<real>(fin[1]), c = static_cast<real>(fin[2]);
+    S2::members([&](auto Bm, int) {
+      using BM = decltype(Bm);
+      Pg[BM::gidx(0) * n + BM::gidx(0)] = a;
+      Pg[BM::gidx(0) * n + BM::gidx(1)] = b;
+      Pg[BM::gidx(1) * n + BM::gidx(0)] = b;
+      Pg[BM::gidx(1) * n + BM::gidx(1)] = c;
+    });
+  }
+  if (p.agg != nullptr) {
+    double* ag = p.agg + f * 4;
+    double mx = fin[3], sm = fin[4], cnt = static_cast<double>(T);
+    if (p.agg_continue) {
+      mx = fmax(mx, ag[0]);
+      sm += ag[1];
+      cnt += ag[3];
+    }
+    ag[0] = mx;
+    ag[1] = sm;
+    ag[2] = (T > 0) ? fin[5] : (p.agg_continue ? ag[2] : 0.0);
+    ag[3] = cnt;
+  }
+  if (p.status != nullptr) {
+    const int bad = (T > 0 && fin[6] == 0.0) ? 1 : 0;
+    p.status[f] = p.agg_continue ? (p.status[f] | bad) : bad;
+  }
+}
+
+template <int MODEL, typename real>
+constexpr size_t shared_smem_bytes() {
+  using MT = ModelTraits<MODEL, false, real>;
+  return static_cast<size_t>(kStages) * kChunk * MT::d * kMathThreads * sizeof(real) +
+         static_cast<size_t>(kStages) * kChunk * sizeof(GainRec) + 8 * sizeof(double) +
+         2 * kStages * sizeof(unsigned long long);
 }
 
 template <int MODEL, typename real>
@@ -433,12 +780,12 @@ constexpr bool tma_sym_eligible() {
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL>
-static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, unsigned blocks, size_t smem,
-                                  cudaStream_t st) {
+static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, const int* n_imu, unsigned blocks,
+                                  size_t smem, cudaStream_t st) {
   cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, FULL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kf_run_tma_kernel<MODEL, real, SYM, FULL><<<blocks, kTmaThreads, smem, st>>>(p, sched);
+  kf_run_tma_kernel<MODEL, real, SYM, FULL><<<blocks, kWsThreads, smem, st>>>(p, sched, n_imu);
   return cudaGetLastError();
 }
 
@@ -449,23 +796,64 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     return cudaErrorInvalidValue;
   } else {
     SchedRec* sched = reinterpret_cast<SchedRec*>(sched_scratch(m));
-    pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, sched);
+    double r0 = 1.0, r1 = 1.0;  // IMU variances of the symmetric group (only its lean step reads w0, w1)
+    if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
+      using G0 = typename ModelTraits<MODEL, false, real>::Sym2::Lead;
+      r0 = m->mc.r_imu[G0::gidx(0)];
+      r1 = m->mc.r_imu[G0::gidx(1)];
+    }
+    int* n_imu = dense_flag(m) + 8;
+    cudaError_t err = cudaMemsetAsync(n_imu, 0, sizeof(int), st);
+    if (err != cudaSuccess) return err;
+    pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, r0, r1, sched, n_imu);
     constexpr size_t smem = tma_smem_bytes<MODEL, real>();
     const unsigned blocks = static_cast<unsigned>((p.n_filters + kTmaThreads - 1) / kTmaThreads);
-    cudaError_t err = cudaSuccess;
     if (with_dec) {
-      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, blocks, smem, st)
-                 : launch_tma_one<MODEL, real, false, false>(p, sched, blocks, smem, st);
+      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, n_imu, blocks, smem, st)
+                 : launch_tma_one<MODEL, real, false, false>(p, sched, n_imu, blocks, smem, st);
       if (err != cudaSuccess) return err;
     }
     if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
       if (with_sym) {
-        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, blocks, smem, st)
-                   : launch_tma_one<MODEL, real, true, false>(p, sched, blocks, smem, st);
+        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, n_imu, blocks, smem, st)
+                   : launch_tma_one<MODEL, real, true, false>(p, sched, n_imu, blocks, smem, st);
         if (err != cudaSuccess) return err;
       }
     }
     return err;
+  }
+}
+
+// shared-covariance kernel: eligible models (all chains one axis-symmetric (position, velocity) group),
+// aggregate / trajectory / log-det outputs; the adaptive gate and per-step P stay with the other kernels
+template <int MODEL, typename real>
+constexpr bool shared_eligible() {
+  using MT = ModelTraits<MODEL, false, real>;
+  if constexpr (!MT::Filter::fast2) return false;
+  else if constexpr (!MT::Sym2::eligible) return false;
+  else return MT::Sym2::lean_ok;
+}
+
+template <int MODEL, typename real>
+static cudaError_t launch_shared(const RunParams& p, bool full, cudaStream_t st) {
+  if constexpr (!shared_eligible<MODEL, real>()) {
+    return cudaErrorInvalidValue;
+  } else {
+    constexpr size_t smem = shared_smem_bytes<MODEL, real>();
+    const unsigned blocks = static_cast<unsigned>((p.n_filters + kMathThreads - 1) / kMathThreads);
+    cudaError_t err;
+    if (full) {
+      err = cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (err != cudaSuccess) return err;
+      kf_run_shared_kernel<MODEL, real, true><<<blocks, kSharedThreads, smem, st>>>(p);
+    } else {
+      err = cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (err != cudaSuccess) return err;
+      kf_run_shared_kernel<MODEL, real, false><<<blocks, kSharedThreads, smem, st>>>(p);
+    }
+    return cudaGetLastError();
   }
 }
 
@@ -477,6 +865,11 @@ __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filt
   if (f >= n_filters) return;
   const real* Pg = P + f * (n * n);
   if (flag[1] == 0 && !SymTraits<MODEL, real>::Filter::blocks_identical(Pg, n)) atomicOr(flag + 1, 1);
+  if (flag[2] == 0) {  // shared-covariance mode needs every P bit-identical to filter 0's
+    bool same = true;
+    for (int e = 0; e < n * n; ++e) same = same && (Pg[e] == P[e]);
+    if (!same) atomicOr(flag + 2, 1);
+  }
   bool coupled = false;
   static_for<0, n>([&](auto I) {
     constexpr int i = I;
@@ -512,6 +905,13 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   const bool tma = tma_possible<MODEL, real>(m, p, full);
   const bool sym = sym_possible<MODEL, real>(m);
   const bool tma_sym = tma && tma_sym_eligible<MODEL, real>();
+  const bool shared = tma_sym && sym && shared_eligible<MODEL, real>() && m->use_shared != 0 && !p.gate_enabled;
+  if ((flags & B200KF_RUN_FORCE_SHARED) && shared) {
+    p.dense_flag = nullptr;
+    B200KF_CUDA_TRY((launch_shared<MODEL, real>(p, full, st)));
+    return B200KF_OK;
+  }
+  if (flags & B200KF_RUN_FORCE_SHARED) flags |= B200KF_RUN_FORCE_SYMMETRIC;  // next-best guarantee
   if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && sym) {
     p.dense_flag = nullptr;
     if (tma_sym) {
@@ -535,12 +935,14 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   int* flag = dense_flag(m);
   B200KF_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
   B200KF_CUDA_TRY(cudaMemsetAsync(flag + 1, sym ? 0 : 1, sizeof(int), st));
+  B200KF_CUDA_TRY(cudaMemsetAsync(flag + 2, shared ? 0 : 1, sizeof(int), st));
   const int ctpb = 128;
   chain_compat_kernel<MODEL, real>
       <<<static_cast<unsigned>((p.n_filters + ctpb - 1) / ctpb), ctpb, 0, st>>>(
           static_cast<const real*>(p.P), p.n_filters, flag);
   B200KF_CUDA_TRY(cudaGetLastError());
   p.dense_flag = flag;
+  if (shared) B200KF_CUDA_TRY((launch_shared<MODEL, real>(p, full, st)));
   if (tma) {
     B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym && tma_sym, true, full, st)));
   } else {

@@ -13,7 +13,7 @@ from . import _lib
 from .models import ModelSpec, default_spec
 
 _MODES = {"auto": _lib.RUN_AUTO, "dense": _lib.RUN_FORCE_DENSE, "decoupled": _lib.RUN_FORCE_DECOUPLED,
-          "symmetric": _lib.RUN_FORCE_SYMMETRIC}
+          "symmetric": _lib.RUN_FORCE_SYMMETRIC, "shared": _lib.RUN_FORCE_SHARED}
 
 
 def _torch():

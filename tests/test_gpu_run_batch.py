@@ -34,7 +34,7 @@ def make_case(name, N, T, seed, dense_P0=False):
 
 
 @pytest.mark.parametrize("name", ["CV6", "CA8", "BIAS9", "CA15"])
-@pytest.mark.parametrize("mode", ["decoupled", "dense", "auto", "symmetric"])
+@pytest.mark.parametrize("mode", ["decoupled", "dense", "auto", "symmetric", "shared"])
 def test_run_batch_f64_matches_oracle(name, mode):
     from sensorfusion_kalmanfilter_b200.engine import Engine
     N, T = 70, 160
@@ -242,3 +242,64 @@ def test_axis_symmetric_kernel_matches_per_chain_kernel_and_oracle(monkeypatch):
     out2 = Engine(spec).run_batch(types, dts, payload, x0, P0)
     assert rel(out2["P"].cpu().numpy(), ref2["P"]) < RTOL64
     assert rel(out2["x"].cpu().numpy(), ref2["x"]) < RTOL64
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_shared_covariance_kernel_matches_symmetric_kernel_and_oracle(precision, monkeypatch):
+    """All filters start from the SAME P (Monte-Carlo seeds of one configuration): AUTO runs the
+    covariance / gain recursion once per launch (kf_run_shared_kernel).  B200KF_SHARED=0 keeps one
+    covariance per filter.  Same numbers either way, both = oracle; N spans 3 CTAs with a partial
+    last one and T is odd.  A launch in which ONE filter's P differs must not take the shared path."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 2000, 151
+    m, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=41)
+    tol = RTOL64 if precision == "f64" else RTOL32
+    ref = ko.run_batch(m, types, dts, payload, x0, P0)
+    monkeypatch.setenv("B200KF_SHARED", "1")
+    sh = Engine("CV6", precision=precision).run_batch(types, dts, payload, x0, P0)
+    shf = Engine("CV6", precision=precision).run_batch(types, dts, payload, x0, P0, traj_ncomp=6, want_logdet=True,
+                                                      mode="shared")
+    monkeypatch.setenv("B200KF_SHARED", "0")
+    sym = Engine("CV6", precision=precision).run_batch(types, dts, payload, x0, P0)
+    for out in (sh, shf, sym):
+        assert int(out["status"].sum()) == 0
+        assert rel(out["x"].cpu().numpy(), ref["x"]) < tol
+        assert rel(out["P"].cpu().numpy(), ref["P"]) < tol
+        a = out["agg"].cpu().numpy()
+        assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < tol
+        assert np.all(a[:, 3] == T)
+    assert rel(shf["traj"].cpu().numpy(), ref["traj"]) < tol
+    ld = shf["logdet"].cpu().numpy()
+    assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < tol
+    if precision == "f64":  # the two kernels evaluate the same formulas
+        np.testing.assert_allclose(sh["x"].cpu().numpy(), sym["x"].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    # one filter with a different (still axis-symmetric) covariance: per-filter recursion for the launch
+    monkeypatch.setenv("B200KF_SHARED", "1")
+    P1 = P0.copy()
+    P1[N - 3] *= 1.5
+    ref1 = ko.run_batch(m, types, dts, payload, x0, P1, want_traj=False)
+    out1 = Engine("CV6", precision=precision).run_batch(types, dts, payload, x0, P1)
+    assert rel(out1["P"].cpu().numpy(), ref1["P"]) < tol
+    assert rel(out1["x"].cpu().numpy(), ref1["x"]) < tol
+    a = out1["agg"].cpu().numpy()
+    assert np.max(np.abs(a[:, :3] - ref1["agg"]) / np.maximum(1.0, np.abs(ref1["agg"]))) < tol
+
+
+def test_shared_covariance_chunked_continuation_and_predict_only():
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 900, 240
+    m, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=43)
+    types = types.copy()
+    types[5::11] = 2  # predict-only events
+    ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
+    eng = Engine("CV6")
+    x, P, agg = x0, P0, None
+    for k0 in range(0, T, 100):
+        sl = slice(k0, min(T, k0 + 100))
+        out = eng.run_batch(types[sl], dts[sl], payload[sl], x, P, agg=agg, mode="shared")
+        x, P, agg = out["x"], out["P"], out["agg"]
+    assert rel(x.cpu().numpy(), ref["x"]) < RTOL64
+    assert rel(P.cpu().numpy(), ref["P"]) < RTOL64
+    a = agg.cpu().numpy()
+    assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
+    assert np.all(a[:, 3] == T)
