@@ -1126,43 +1126,69 @@ struct Sym2Filter {
   }
   // Lean fused predict + update for the aggregate-only loop of (position, velocity) chains whose
   // IMU event is the reference's pseudo-measurement z = [p + (v + u dt) dt, v + u dt]
-  // (kf_workers.py:698-704): the innovation is y = [(v + u dt) dt, u dt], so with the gains folded
-  // with dt -- g = K diag(dt, dt) = P+ diag(dt/r0, dt/r1), w0 = dt/r0 and w1 = dt/r1 arrive with the
-  // step record -- the state update is x += g [v + u dt, u]: 6 FMAs per axis including the predict.
-  // Returns in v the chain's det P+ / (r0 r1) on an IMU event (the constant factor is restored once
-  // at the end of the launch) and det P+ otherwise; the return value says which.
+  // (kf_workers.py:698-704).  Two rewrites, both exact in exact arithmetic:
+  //  * the covariance is carried in R-normalised coordinates a~ = a / r0, b~ = b / sqrt(r0 r1),
+  //    c~ = c / r1, where the H = I update is P~+ = P~ (P~ + I)^-1: D~ = det P~ + a~ + c~ + 1,
+  //    a~+ = (det P~ + a~) / D~, b~+ = b~ / D~, c~+ = (det P~ + c~) / D~ -- no multiplication by r;
+  //  * the innovation is y = [(v + u dt) dt, u dt], so predict and update of the state collapse to
+  //    x0+ = x0 + cA v + cB u, x1+ = cC v + cE u with four per-filter coefficients (4 FP64 per axis).
+  // The per-step constants that depend only on (dt, q, r) arrive with the step record (LeanRec).
+  // v returns det P+ / (r0 r1) of ONE chain for every event type; the constant factor and the chain
+  // multiplicity are restored once at the end of the launch.
   static constexpr bool lean_ok =
       (B0::zk(0) == ZK_POS && B0::zk(1) == ZK_VEL && B0::pz(0) == B0::pz(1) && B0::gps(0) >= 0);
-  __device__ __forceinline__ bool step_lean(real dt, real w0, real w1, int ty, const ModelConst& mc,
-                                            const real* u, real& v) {
-    const real bn = fma(dt, c, b);
-    const real ap = fma(dt, b + bn, fma(real(mc.q[B0::gidx(0)]), dt, a));
-    const real cp = fma(real(mc.q[B0::gidx(1)]), dt, c);
-    if (ty == EV_IMU) {
-      const real r0 = real(mc.r_imu[B0::gidx(0)]), r1 = real(mc.r_imu[B0::gidx(1)]);
+  struct LeanRec {  // 64 bytes, warp-uniform
+    double dt, dt2;
+    double kap;   // dt sqrt(r1 / r0)
+    double lam;   // IMU: dt sqrt(r0 / r1)       GPS: sqrt(r1 / r0)
+    double kdt;   // IMU: kap dt                 GPS: r_gps / r0
+    double phi0;  // q0 dt / r0
+    double phi1;  // q1 dt / r1
+    int type;
+    int pad;
+  };
+  __device__ __forceinline__ void to_normalized(const ModelConst& mc) {
+    const double r0 = mc.r_imu[B0::gidx(0)], r1 = mc.r_imu[B0::gidx(1)];
+    a = real(double(a) / r0);
+    b = real(double(b) / sqrt(r0 * r1));
+    c = real(double(c) / r1);
+  }
+  __device__ __forceinline__ void from_normalized(const ModelConst& mc) {
+    const double r0 = mc.r_imu[B0::gidx(0)], r1 = mc.r_imu[B0::gidx(1)];
+    a = real(double(a) * r0);
+    b = real(double(b) * sqrt(r0 * r1));
+    c = real(double(c) * r1);
+  }
+  __device__ __forceinline__ void step_lean(const LeanRec& r, const real* u, real& v) {
+    const real dt = real(r.dt), kap = real(r.kap);
+    const real bn = fma(kap, c, b);
+    const real ap = fma(kap, b + bn, a + real(r.phi0));
+    const real cp = c + real(r.phi1);
+    if (r.type == EV_IMU) {
       const real detp = fma(ap, cp, -(bn * bn));
-      const real t0 = fma(ap, r1, detp);
-      const real t1 = fma(cp, r0, detp);
-      const real inv = fast_rcp3(fma(r0, cp + r1, t0));
-      const real i0 = r0 * inv, i1 = r1 * inv;
-      a = t0 * i0;
-      c = t1 * i1;
-      b = bn * (i0 * r1);
-      const real g00 = a * w0, g10 = b * w0, g01 = b * w1, g11 = c * w1;
+      const real t0 = detp + ap, t1 = detp + cp;
+      const real inv = fast_rcp3((t0 + real(1)) + cp);
+      a = t0 * inv;
+      c = t1 * inv;
+      b = bn * inv;
+      const real cA = fma(a, dt, dt);                        // dt + k00 dt
+      const real cB = fma(a, real(r.dt2), real(r.lam) * b);  // k00 dt^2 + k01 dt
+      const real cC = fma(kap, b, real(1));                  // 1 + k10 dt
+      const real cE = fma(real(r.kdt), b, dt * c);           // k10 dt^2 + k11 dt
       members([&](auto Bm, int m) {
         using BM = decltype(Bm);
         const real acc = u[BM::pz(1)];
-        const real s = fma(acc, dt, x1[m]);
-        x0[m] = fma(g00, s, fma(g01, acc, fma(dt, x1[m], x0[m])));
-        x1[m] = fma(g10, s, fma(g11, acc, x1[m]));
+        x0[m] = fma(cA, x1[m], fma(cB, acc, x0[m]));
+        x1[m] = fma(cE, acc, cC * x1[m]);
       });
       v = detp * inv;
-      return true;
+      return;
     }
-    if (ty == EV_GPS) {
-      const real r = real(mc.r_gps[B0::gps(0)]);
-      const real inv = fast_rcp3(ap + r);
-      const real k0 = ap * inv, k1 = bn * inv, g = r * inv;
+    if (r.type == EV_GPS) {
+      const real gam = real(r.kdt);
+      const real inv = fast_rcp3(ap + gam);
+      const real k0 = ap * inv, bi = bn * inv, g = gam * inv;
+      const real k1 = real(r.lam) * bi;
       members([&](auto Bm, int m) {
         using BM = decltype(Bm);
         const real xp = fma(dt, x1[m], x0[m]);
@@ -1170,7 +1196,7 @@ struct Sym2Filter {
         x0[m] = fma(k0, y, xp);
         x1[m] = fma(k1, y, x1[m]);
       });
-      c = fma(-k1, bn, cp);
+      c = fma(-bi, bn, cp);
       a = ap * g;
       b = bn * g;
     } else {
@@ -1181,7 +1207,6 @@ struct Sym2Filter {
       c = cp;
     }
     v = fma(a, c, -(b * b));
-    return false;
   }
 
   __device__ __forceinline__ double update(real dt, const ModelConst& mc, int ty, const real* u, bool& ok) {

@@ -204,9 +204,9 @@ constexpr int kWsThreads = kTmaThreads + 32;  // + the producer warp (928 * 64 r
 constexpr int kChunk = B200KF_CHUNK;    // steps per stage
 constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 KB of shared memory)
 
-struct SchedRec {  // 32 bytes (bulk copies need 16-byte granularity)
-  double dt;
-  double w0, w1;  // dt / r_imu of the symmetric group's two states: gains folded with dt (Sym2Filter::step_lean)
+struct SchedRec {  // 64 bytes (bulk copies need 16-byte granularity); layout of Sym2Filter::LeanRec:
+  double dt, dt2;  // only (dt, type) are read outside the lean symmetric loop
+  double kap, lam, kdt, phi0, phi1;
   int type;
   int pad;
 };
@@ -252,18 +252,35 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
       : "memory");
 }
 
+// Per-step records of the launch: (dt, type) plus the warp-uniform constants of the lean symmetric
+// step (Sym2Filter::LeanRec), which depend only on dt and the group's (q, r): evaluated once per
+// step here instead of once per step and filter.
+struct LeanConst {
+  double q0, q1, r0, r1, rg;
+};
 static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, const double* __restrict__ dts,
-                                     int T, double r0, double r1, SchedRec* __restrict__ out, int* n_imu) {
+                                            int T, LeanConst lc, SchedRec* __restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool imu = k < T && types[k] == EV_IMU;
-  if (k < T) out[k] = SchedRec{dts[k], dts[k] / r0, dts[k] / r1, static_cast<int>(types[k]), 0};
-  const unsigned votes = __ballot_sync(0xffffffffu, imu);  // the launch's IMU count for the lean aggregate
-  if ((threadIdx.x & 31) == 0 && votes != 0) atomicAdd(n_imu, __popc(votes));
+  if (k >= T) return;
+  const double dt = dts[k];
+  const int ty = types[k];
+  const double s10 = sqrt(lc.r1 / lc.r0), s01 = sqrt(lc.r0 / lc.r1);
+  SchedRec r;
+  r.dt = dt;
+  r.dt2 = dt * dt;
+  r.kap = dt * s10;
+  r.lam = (ty == EV_GPS) ? s10 : dt * s01;
+  r.kdt = (ty == EV_GPS) ? lc.rg / lc.r0 : r.kap * dt;
+  r.phi0 = lc.q0 * dt / lc.r0;
+  r.phi1 = lc.q1 * dt / lc.r1;
+  r.type = ty;
+  r.pad = 0;
+  out[k] = r;
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL>
 __global__ void __launch_bounds__(kWsThreads, 1)
-    kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched, const int* __restrict__ n_imu) {
+    kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched) {
   using MT = ModelTraits<MODEL, false, real>;
   using Flt = std::conditional_t<SYM, typename MT::Sym2, typename MT::Dec2>;
   constexpr int n = MT::n;
@@ -341,8 +358,11 @@ __global__ void __launch_bounds__(kWsThreads, 1)
   // constant and the chain multiplicity are restored after the loop; validity (every det finite
   // and > 0) is tracked with integer min / max of the raw bits instead of an FP64 compare
   constexpr bool LEAN = SYM && !FULL && Flt::lean_ok;
-  long long lean_max_imu = 0;
   int lean_sign = 0;  // sticky sign bit of every det seen (a zero det zeroes acc_mant; NaN / inf show in the max)
+  if constexpr (LEAN) {
+    static_assert(sizeof(SchedRec) == sizeof(typename Flt::LeanRec), "SchedRec must mirror LeanRec");
+    if (active && T > 0) flt.to_normalized(p.mc);
+  }
 
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int s = chunk % kStages;
@@ -363,14 +383,9 @@ __global__ void __launch_bounds__(kWsThreads, 1)
           const int ty = rec.type;
           if constexpr (LEAN) {
             real v;
-            const bool imu = flt.step_lean(dt, static_cast<real>(rec.w0), static_cast<real>(rec.w1), ty, p.mc, u, v);
-            const long long vb = __double_as_longlong(double(v));
+            flt.step_lean(*reinterpret_cast<const typename Flt::LeanRec*>(&sched_buf[s * kChunk + c]), u, v);
             lean_sign |= __double2hiint(double(v));
-            if (imu) {
-              lean_max_imu = max(lean_max_imu, vb);
-            } else {
-              acc_max = max(acc_max, vb);
-            }
+            acc_max = max(acc_max, __double_as_longlong(double(v)));
             const double m = acc_mant * double(v);
             const int hi = __double2hiint(m);
             const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -411,30 +426,25 @@ __global__ void __launch_bounds__(kWsThreads, 1)
   }
 
   if (!active) return;
+  if constexpr (LEAN) {
+    if (T > 0) {
+      ok = ok && lean_sign >= 0 && acc_mant >= 1.0 && acc_max < 0x7ff0000000000000LL;
+      flt.from_normalized(p.mc);
+    }
+  }
   {
     real* xg = static_cast<real*>(p.x) + f * n;
     real* Pg = static_cast<real*>(p.P) + f * (n * n);
     flt.store(xg, Pg, n);
   }
-  int lean_n_imu = 0;
-  if constexpr (LEAN) {
-    if (T > 0)
-      ok = ok && lean_sign >= 0 && acc_mant >= 1.0 && acc_max < 0x7ff0000000000000LL &&
-           lean_max_imu < 0x7ff0000000000000LL;
-    lean_n_imu = *n_imu;  // IMU events of the launch, counted by pack_schedule_kernel
-  }
   if (p.agg != nullptr) {
     double* a = p.agg + f * 4;
     double mx = (T > 0) ? log(__longlong_as_double(acc_max)) : -INFINITY;
     double sm = log(acc_mant) + static_cast<double>(acc_expo) * 0.6931471805599453094;
-    if constexpr (LEAN) {  // restore r0 r1 on the IMU terms, then the chain multiplicity
+    if constexpr (LEAN) {  // every term was det / (r0 r1) of one chain: restore the constant, then the multiplicity
       const double lr = log(double(flt.r0r1));
-      if (T > 0) {
-        mx = (acc_max > 0) ? mx : -INFINITY;
-        if (lean_n_imu > 0) mx = fmax(mx, log(__longlong_as_double(lean_max_imu)) + lr);
-      }
-      mx *= static_cast<double>(Flt::M);
-      sm = (sm + static_cast<double>(lean_n_imu) * lr) * static_cast<double>(Flt::M);
+      mx = (mx + lr) * static_cast<double>(Flt::M);
+      sm = (sm + static_cast<double>(T) * lr) * static_cast<double>(Flt::M);
     }
     double cnt = static_cast<double>(T);
     if (p.agg_continue) {
@@ -461,7 +471,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 // have the same gains at every step.  One lane of a dedicated producer warp per CTA runs that
 // recursion ONCE (in float64, whatever the model precision), writes a 64-byte gain record per step
 // into the ring stage next to the TMA'd payload rows, and issues the bulk copies; the 28 math warps
-// only apply the gains to their filter's state: 6 FMAs per axis and event.  Validity (all P
+// only apply the gains to their filter's state: 4 FP64 per axis and event.  Validity (all P
 // bit-identical, axis-symmetric, chain-compatible; equal rate constants) is checked per launch on
 // the device like the other variants.  The kernel is a pure HBM stream.
 // ------------------------------------------------------------------------------------------
@@ -470,7 +480,7 @@ constexpr int kSharedThreads = kMathThreads + 64;   // + the gain warp + the cop
 
 struct GainRec {  // 56 bytes
   double dt;
-  double g00, g01, g10, g11;  // IMU: K diag(dt, dt); GPS: (k0, -, k1, -)
+  double g00, g01, g10, g11;  // IMU: x0 += g00 v + g01 u, x1 = g10 v + g11 u (predict folded in); GPS: (k0, -, k1, -)
   double logdet;              // log det P of the whole filter after the step (per-step output only)
   int type;                   // event type actually applied
   int pad;
@@ -579,10 +589,11 @@ __global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_kernel(const 
             c = t1 * i1;
             b = bn * (i0 * r1);
             const double w0 = dt * ir0, w1 = dt * ir1;
-            rec.g00 = a * w0;
-            rec.g10 = b * w0;
-            rec.g01 = b * w1;
-            rec.g11 = c * w1;
+            const double g00 = a * w0, g10 = b * w0, g01 = b * w1, g11 = c * w1;
+            rec.g00 = dt + g00;           // x0+ = x0 + (dt + g00) v + (g00 dt + g01) u
+            rec.g01 = fma(g00, dt, g01);
+            rec.g10 = 1.0 + g10;          // x1+ = (1 + g10) v + (g10 dt + g11) u
+            rec.g11 = fma(g10, dt, g11);
             det = detp * inv * r0r1;
           } else if (ty == EV_GPS) {
             const double inv = fast_rcp(ap + rg);
@@ -653,9 +664,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_kernel(const 
               S2::members([&](auto Bm, int m) {
                 using BM = decltype(Bm);
                 const real acc = u[BM::pz(1)];
-                const real sv = fma(acc, dt, x1[m]);
-                x0[m] = fma(g00, sv, fma(g01, acc, fma(dt, x1[m], x0[m])));
-                x1[m] = fma(g10, sv, fma(g11, acc, x1[m]));
+                x0[m] = fma(g00, x1[m], fma(g01, acc, x0[m]));
+                x1[m] = fma(g11, acc, g10 * x1[m]);
               });
             } else if (ty == EV_GPS) {
               const real k0g = static_cast<real>(rec->g00), k1g = static_cast<real>(rec->g10);
@@ -780,12 +790,12 @@ constexpr bool tma_sym_eligible() {
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL>
-static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, const int* n_imu, unsigned blocks,
-                                  size_t smem, cudaStream_t st) {
+static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, unsigned blocks, size_t smem,
+                                  cudaStream_t st) {
   cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, FULL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kf_run_tma_kernel<MODEL, real, SYM, FULL><<<blocks, kWsThreads, smem, st>>>(p, sched, n_imu);
+  kf_run_tma_kernel<MODEL, real, SYM, FULL><<<blocks, kWsThreads, smem, st>>>(p, sched);
   return cudaGetLastError();
 }
 
@@ -796,27 +806,28 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     return cudaErrorInvalidValue;
   } else {
     SchedRec* sched = reinterpret_cast<SchedRec*>(sched_scratch(m));
-    double r0 = 1.0, r1 = 1.0;  // IMU variances of the symmetric group (only its lean step reads w0, w1)
+    LeanConst lc{1.0, 1.0, 1.0, 1.0, 1.0};  // rate constants of the symmetric group (only its lean step reads them)
     if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
       using G0 = typename ModelTraits<MODEL, false, real>::Sym2::Lead;
-      r0 = m->mc.r_imu[G0::gidx(0)];
-      r1 = m->mc.r_imu[G0::gidx(1)];
+      lc.q0 = m->mc.q[G0::gidx(0)];
+      lc.q1 = m->mc.q[G0::gidx(1)];
+      lc.r0 = m->mc.r_imu[G0::gidx(0)];
+      lc.r1 = m->mc.r_imu[G0::gidx(1)];
+      if constexpr (G0::gps(0) >= 0) lc.rg = m->mc.r_gps[G0::gps(0)];
     }
-    int* n_imu = dense_flag(m) + 8;
-    cudaError_t err = cudaMemsetAsync(n_imu, 0, sizeof(int), st);
-    if (err != cudaSuccess) return err;
-    pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, r0, r1, sched, n_imu);
+    pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc, sched);
+    cudaError_t err = cudaSuccess;
     constexpr size_t smem = tma_smem_bytes<MODEL, real>();
     const unsigned blocks = static_cast<unsigned>((p.n_filters + kTmaThreads - 1) / kTmaThreads);
     if (with_dec) {
-      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, n_imu, blocks, smem, st)
-                 : launch_tma_one<MODEL, real, false, false>(p, sched, n_imu, blocks, smem, st);
+      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, blocks, smem, st)
+                 : launch_tma_one<MODEL, real, false, false>(p, sched, blocks, smem, st);
       if (err != cudaSuccess) return err;
     }
     if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
       if (with_sym) {
-        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, n_imu, blocks, smem, st)
-                   : launch_tma_one<MODEL, real, true, false>(p, sched, n_imu, blocks, smem, st);
+        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, blocks, smem, st)
+                   : launch_tma_one<MODEL, real, true, false>(p, sched, blocks, smem, st);
         if (err != cudaSuccess) return err;
       }
     }
