@@ -169,7 +169,7 @@ class ClockSampler:
                 continue
             try:
                 ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[5:9]))
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[5:9], f[4]))
             except ValueError:
                 continue
         inside = [r for r in rows if t0 <= r[0] <= t1]
@@ -180,11 +180,22 @@ class ClockSampler:
         if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
         reasons = set()
+        # NVML bit mask of clocks_event_reasons.active (the per-reason columns lag behind it on this driver)
+        bits = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
         for r in inside:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+            try:
+                mask = int(r[5], 16)
+            except ValueError:
+                mask = 0
+            for b, name in bits.items():
+                if mask & b:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_mhz_min": float(min(r[1] for r in inside)),
+                "sm_max_mhz": float(max(r[2] for r in inside)),
                 "power_w_max": float(max(r[3] for r in inside)), "samples": len(inside), "scope": scope,
                 "reasons": sorted(reasons)}
 
