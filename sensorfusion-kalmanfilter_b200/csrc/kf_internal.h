@@ -30,6 +30,7 @@ struct b200kf_model {
   HostWorkspace host_ws;
   int use_sym;  // 1: axis-symmetric kernel when every filter's chains share one covariance (env B200KF_SYM=0 disables)
   int use_shared;  // 1: shared-covariance kernel when every filter of a launch carries the same P (env B200KF_SHARED=0 disables)
+  int use_tree;  // 1: prefix-sharing schedule-search kernel for aligned blocks (env B200KF_TREE=0 disables)
   int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };
 
@@ -38,6 +39,7 @@ namespace b200kf {
 constexpr size_t kArenaBytes = 8 << 20;
 constexpr size_t kSchedOffset = 1 << 20;  // packed (dt, type) records of the TMA kernel
 constexpr int kMaxSearchBlocks = 8192;
+constexpr int kMaxSearchPartials = 24000;  // 40-byte ScorePartial entries in the search scratch (< 1 MB)
 
 int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
@@ -82,9 +84,11 @@ struct ScoreParams {
   unsigned long long first, count;
   double threshold;
   double initial_logdet;  // NaN: compute term 0 on the device; else the host's slogdet(P0)
-  double* per_schedule;  // [count, 4] or null
+  double* per_schedule;  // [count of the API call, 4] or null; row = schedule index - out_base
   void* partials;        // per-block results
   const int* dense_flag;
+  unsigned long long out_base;  // first schedule of the API call (a call may be split into several launches)
+  int tree_a, tree_k;           // prefix-sharing kernel: [first, first + 2^tree_a) aligned block, DFS over its top tree_k bits
 };
 
 constexpr int kMaxMaskedEvents = 64;

@@ -36,6 +36,36 @@ __device__ __forceinline__ void better_sum(double& sc, unsigned long long& ix, d
   }
 }
 
+// warp shuffle + shared-memory reduction of a block's results into partials[blockIdx.x]
+__device__ __forceinline__ void score_block_reduce(double best_sc, unsigned long long best_ix,
+                                                   unsigned long long best_key, unsigned long long n_feas,
+                                                   unsigned long long n_near, ScorePartial* partials) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double osc = __shfl_down_sync(0xffffffffu, best_sc, off);
+    const unsigned long long oix = __shfl_down_sync(0xffffffffu, best_ix, off);
+    better_sum(best_sc, best_ix, osc, oix);
+    const unsigned long long ok2 = __shfl_down_sync(0xffffffffu, best_key, off);
+    best_key = ok2 < best_key ? ok2 : best_key;
+    n_feas += __shfl_down_sync(0xffffffffu, n_feas, off);
+    n_near += __shfl_down_sync(0xffffffffu, n_near, off);
+  }
+  __shared__ ScorePartial sh[kScoreTpb / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = ScorePartial{best_sc, best_ix, best_key, n_feas, n_near};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ScorePartial r = sh[0];
+    for (int w = 1; w < kScoreTpb / 32; ++w) {
+      better_sum(r.score, r.index, sh[w].score, sh[w].index);
+      r.key = sh[w].key < r.key ? sh[w].key : r.key;
+      r.n_feasible += sh[w].n_feasible;
+      r.n_near += sh[w].n_near;
+    }
+    partials[blockIdx.x] = r;
+  }
+}
+
 template <int MODEL, int VAR>
 __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
   using MT = VariantTraits<MODEL, VAR, double>;
@@ -82,7 +112,7 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
     }
     if (!ok) mx = sm = lastv = NAN;
     if (p.per_schedule != nullptr) {
-      double* o = p.per_schedule + idx * 4;
+      double* o = p.per_schedule + (s - p.out_base) * 4;
       o[0] = mx;
       o[1] = sm;
       o[2] = lastv;
@@ -99,31 +129,161 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
     }
   }
 
-  // block reduction
+  score_block_reduce(best_sc, best_ix, best_key, n_feas, n_near, static_cast<ScorePartial*>(p.partials));
+}
+
+// ---- prefix-sharing variant ----------------------------------------------------------------------
+// Schedules that agree on the first events share the filter up to there.  For an aligned block
+// [first, first + 2^a) the low a bits are free: thread <-> the low a-k bits (the EARLY events, walked
+// once), then a depth-first walk over the next k bits with the covariance, the running log-det
+// aggregate and the current time saved per level (local memory, L1-resident).  Leaves are visited
+// in bit-reversed order so the earliest DFS event changes least often: going from one leaf to the
+// next re-enters the tree at the level of the lowest set bit of the counter, which costs one filter
+// step per leaf on average instead of one per used event (L/2).  Bits >= a (fixed by `first`) and
+// the end-of-window propagation are applied per leaf.  Same arithmetic, order of operations and
+// reductions as score_kernel, so the two agree bit for bit.
+constexpr int kTreeMaxK = 8;
+
+template <class Flt>
+struct CovCount {
+  static constexpr int value = 0;
+};
+template <typename real, bool IC>
+struct CovCount<FilterT<real, IC>> {
+  static constexpr int value = 0;
+};
+template <typename real, bool IC, class B0, class... Bs>
+struct CovCount<FilterT<real, IC, B0, Bs...>> {
+  static constexpr int value = BlockObj<B0, real>::type::NP + CovCount<FilterT<real, IC, Bs...>>::value;
+};
+
+template <int MODEL, int VAR>
+__global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams p) {
+  using MT = VariantTraits<MODEL, VAR, double>;
+  using Flt = typename MT::Filter;
+  constexpr int n = MT::n;
+  constexpr int NC = CovCount<Flt>::value;
+
+  double best_sc = INFINITY;
+  unsigned long long best_ix = ~0ULL, best_key = ~0ULL, n_feas = 0, n_near = 0;
+  const int L = p.n_events;
+  const int a = p.tree_a, k = p.tree_k;
+  const int npre = a - k;  // events decided by the thread index
+  const double near_tol = 1e-9 * fmax(1.0, fabs(p.threshold));
+  const bool host_ld0 = !isnan(p.initial_logdet);
+
+  struct Saved {
+    double cov[NC];
+    double mant, maxdet, last, tcur;
+    int expo, count, ok;
+  };
+  Saved stk[kTreeMaxK + 1];
+
+  Flt flt;
+  LogDetAcc acc;
+  bool ok;
+  double tcur;
+  auto save = [&](int lvl) {
+    Saved& sv = stk[lvl];
+    int o = 0;
+    flt.each([&](const auto& b) {
+      using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const double osc = __shfl_down_sync(0xffffffffu, best_sc, off);
-    const unsigned long long oix = __shfl_down_sync(0xffffffffu, best_ix, off);
-    better_sum(best_sc, best_ix, osc, oix);
-    const unsigned long long ok2 = __shfl_down_sync(0xffffffffu, best_key, off);
-    best_key = ok2 < best_key ? ok2 : best_key;
-    n_feas += __shfl_down_sync(0xffffffffu, n_feas, off);
-    n_near += __shfl_down_sync(0xffffffffu, n_near, off);
-  }
-  __shared__ ScorePartial sh[kScoreTpb / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) sh[warp] = ScorePartial{best_sc, best_ix, best_key, n_feas, n_near};
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ScorePartial r = sh[0];
-    for (int w = 1; w < kScoreTpb / 32; ++w) {
-      better_sum(r.score, r.index, sh[w].score, sh[w].index);
-      r.key = sh[w].key < r.key ? sh[w].key : r.key;
-      r.n_feasible += sh[w].n_feasible;
-      r.n_near += sh[w].n_near;
+      for (int e = 0; e < BT::NP; ++e) sv.cov[o + e] = b.P[e];
+      o += BT::NP;
+    });
+    sv.mant = acc.mant;
+    sv.maxdet = acc.maxdet;
+    sv.last = acc.last;
+    sv.expo = acc.expo;
+    sv.count = acc.count;
+    sv.tcur = tcur;
+    sv.ok = ok ? 1 : 0;
+  };
+  auto restore = [&](int lvl) {
+    const Saved& sv = stk[lvl];
+    int o = 0;
+    flt.each([&](auto& b) {
+      using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+#pragma unroll
+      for (int e = 0; e < BT::NP; ++e) b.P[e] = sv.cov[o + e];
+      o += BT::NP;
+    });
+    acc.mant = sv.mant;
+    acc.maxdet = sv.maxdet;
+    acc.last = sv.last;
+    acc.expo = sv.expo;
+    acc.count = sv.count;
+    tcur = sv.tcur;
+    ok = sv.ok != 0;
+  };
+  auto apply = [&](int i) {  // use event i (kf_workers.py:36-71)
+    const double dt = p.times[i] - tcur;  // merged gap, :37
+    if (dt < 0) return;                   // :38-40
+    const int ty = p.types[i];
+    filter_predict<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+    filter_update<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+    tcur = p.times[i];
+    acc.add(filter_det(flt, ok));
+  };
+
+  const unsigned long long n_prefix = 1ULL << npre;
+  for (unsigned long long t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; t < n_prefix;
+       t += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    flt.each([&](auto& b) { b.load_cov(p.P0, n); });
+    acc = LogDetAcc();
+    ok = true;
+    if (!host_ld0) acc.add(filter_det(flt, ok));  // log_det[0], kf_workers.py:32
+    tcur = p.t_prev;
+    for (int i = 0; i < npre; ++i)
+      if ((t >> i) & 1ULL) apply(i);
+    save(0);
+    const unsigned n_leaf = 1u << k;
+    for (unsigned c = 0; c < n_leaf; ++c) {
+      const int lvl0 = (c == 0) ? 0 : (k - 1 - (__ffs(c) - 1));  // first level whose decision changed
+      if (c != 0) restore(lvl0);
+      for (int lv = lvl0; lv < k; ++lv) {
+        if ((c >> (k - 1 - lv)) & 1u) apply(npre + lv);
+        if (lv + 1 < k) save(lv + 1);
+      }
+      const unsigned long long m = (k > 0) ? (static_cast<unsigned long long>(__brev(c)) >> (32 - k)) : 0ULL;
+      const unsigned long long s = p.first | t | (m << npre);
+      for (int i = a; i < L; ++i)
+        if ((s >> i) & 1ULL) apply(i);
+      if (tcur < p.t_end - 1e-8) {  // kf_workers.py:74-82
+        const double dt = p.t_end - tcur;
+        filter_predict<false>(flt, dt, p.mc, EV_PREDICT_ONLY, static_cast<const double*>(nullptr));
+        acc.add(filter_det(flt, ok));
+      }
+      double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
+      double sm = acc.sum_log();
+      double lastv = (acc.count > 0) ? log(acc.last) : p.initial_logdet;
+      int cnt = acc.count;
+      if (host_ld0) {
+        mx = fmax(mx, p.initial_logdet);
+        sm += p.initial_logdet;
+        cnt += 1;
+      }
+      if (!ok) mx = sm = lastv = NAN;
+      if (p.per_schedule != nullptr) {
+        double* o = p.per_schedule + (s - p.out_base) * 4;
+        o[0] = mx;
+        o[1] = sm;
+        o[2] = lastv;
+        o[3] = static_cast<double>(cnt);
+      }
+      if (s != 0 && ok) {
+        better_sum(best_sc, best_ix, sm, s);
+        if (mx < p.threshold) {
+          n_feas += 1;
+          const unsigned long long key = lex_key(s, L);
+          best_key = key < best_key ? key : best_key;
+        }
+        if (fabs(mx - p.threshold) <= near_tol) n_near += 1;
+      }
     }
-    static_cast<ScorePartial*>(p.partials)[blockIdx.x] = r;
   }
+  score_block_reduce(best_sc, best_ix, best_key, n_feas, n_near, static_cast<ScorePartial*>(p.partials));
 }
 
 // ---- worker with state: full filter per schedule over one shared window ----------------------
@@ -313,13 +473,25 @@ int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams
   return B200KF_OK;
 }
 
+template <int VAR>
+static void launch_score_var(const ScoreParams& p, bool tree, unsigned blocks, cudaStream_t st) {
+  if (tree)
+    score_tree_kernel<B200KF_INST_MODEL, VAR><<<blocks, kScoreTpb, 0, st>>>(p);
+  else
+    score_kernel<B200KF_INST_MODEL, VAR><<<blocks, kScoreTpb, 0, st>>>(p);
+}
+
+// The range [first, first + count) is cut into aligned power-of-two blocks: blocks of at least
+// 2^kTreeMinA schedules go to the prefix-sharing kernel, the ragged head and tail to the flat one.
+// Every launch appends its per-block partials to the same array; returns their total number.
+constexpr int kTreeMinA = 14;
+constexpr int kMaxFlatBlocks = 2048;  // grid-stride beyond that
+constexpr int kMaxTreeBlocks = 512;   // <= 2 * (32 - kTreeMinA) tree launches per call: partials stay inside the scratch
+
 template <>
 int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsigned flags,
                                       b200kf_best* best, cudaStream_t st) {
   (void)best;
-  unsigned long long blocks = (p.count + kScoreTpb - 1) / kScoreTpb;
-  if (blocks > static_cast<unsigned long long>(kMaxSearchBlocks)) blocks = kMaxSearchBlocks;
-  if (blocks == 0) blocks = 1;
   // P0 is a host matrix, so the variant is chosen on the host: dense when P0 couples chains,
   // one covariance per symmetric group when the member blocks of P0 are identical and the rates
   // agree (the reference's P0 and any P it produces, kf_workers.py:651), else one per chain.
@@ -340,14 +512,62 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
   }
   if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && !(flags & B200KF_RUN_FORCE_DENSE)) var = VAR_SYMMETRIC;
   p.dense_flag = nullptr;
-  if (var == VAR_DENSE)
-    score_kernel<B200KF_INST_MODEL, VAR_DENSE><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
-  else if (var == VAR_SYMMETRIC)
-    score_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
-  else
-    score_kernel<B200KF_INST_MODEL, VAR_DECOUPLED><<<static_cast<unsigned>(blocks), kScoreTpb, 0, st>>>(p);
+  p.out_base = p.first;
+  const bool tree_ok = m->use_tree != 0 && var != VAR_DENSE;  // the dense covariance is too large for the DFS stack
+  ScorePartial* parts = static_cast<ScorePartial*>(p.partials);
+  const unsigned long long end = p.first + p.count;
+  unsigned long long cur = p.first;
+  int total_blocks = 0;
+  bool overflow = false;
+  auto launch = [&](unsigned long long lo, unsigned long long cnt, int a) {  // a >= 0: aligned tree block
+    ScoreParams q = p;
+    q.first = lo;
+    q.count = cnt;
+    q.partials = parts + total_blocks;
+    unsigned long long threads = cnt;
+    q.tree_a = q.tree_k = 0;
+    if (a >= 0) {
+      int k = a - 16;
+      k = k < 3 ? 3 : (k > kTreeMaxK ? kTreeMaxK : k);
+      q.tree_a = a;
+      q.tree_k = k;
+      threads = 1ULL << (a - k);
+    }
+    unsigned long long blocks = (threads + kScoreTpb - 1) / kScoreTpb;
+    const unsigned long long cap = (a >= 0) ? kMaxTreeBlocks : kMaxFlatBlocks;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    const unsigned nb = static_cast<unsigned>(blocks);
+    if (total_blocks + static_cast<int>(nb) > kMaxSearchPartials) {
+      overflow = true;
+      return;
+    }
+    if (var == VAR_DENSE) launch_score_var<VAR_DENSE>(q, false, nb, st);
+    else if (var == VAR_SYMMETRIC) launch_score_var<VAR_SYMMETRIC>(q, a >= 0, nb, st);
+    else launch_score_var<VAR_DECOUPLED>(q, a >= 0, nb, st);
+    total_blocks += static_cast<int>(nb);
+  };
+  if (p.count == 0) {
+    launch(p.first, 0, -1);  // one block of idle threads writes the neutral partial
+  }
+  unsigned long long flat_lo = cur;  // start of the pending flat (ragged) piece
+  while (cur < end) {
+    const int align = (cur == 0) ? 63 : __builtin_ctzll(cur);
+    int a = 63 - __builtin_clzll(end - cur);
+    if (a > align) a = align;
+    if (tree_ok && a >= kTreeMinA) {
+      if (cur > flat_lo) launch(flat_lo, cur - flat_lo, -1);
+      launch(cur, 1ULL << a, a);
+      cur += 1ULL << a;
+      flat_lo = cur;
+    } else {
+      cur += 1ULL << a;
+    }
+  }
+  if (end > flat_lo) launch(flat_lo, end - flat_lo, -1);
+  if (overflow) return set_error(B200KF_ERR_UNSUPPORTED, "schedule range needs more partial results than the scratch holds");
   B200KF_CUDA_TRY(cudaGetLastError());
-  return static_cast<int>(blocks);
+  return total_blocks;
 }
 
 // ---- product-of-queues brute force, RMSE objective (KF_SensorFusion.ipynb:804-954) -------------

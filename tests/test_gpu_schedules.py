@@ -125,3 +125,47 @@ def test_cov_update_matches_reference_scheduler(golden):
         ref = g[key]
         assert np.max(np.abs(post.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-9
         np.testing.assert_allclose(tr.cpu().numpy(), np.trace(ref, axis1=1, axis2=2), rtol=1e-9)
+
+
+@pytest.mark.parametrize("name,mode", [("CA15", "auto"), ("CA15", "decoupled"), ("CV6", "auto"), ("CA8", "auto")])
+def test_prefix_sharing_kernel_is_bit_identical_to_flat_kernel(name, mode, monkeypatch):
+    """Aligned blocks of >= 2^14 schedules take the prefix-sharing (DFS) kernel; B200KF_TREE=0 keeps
+    one thread per schedule.  Same arithmetic in the same order -> every per-schedule aggregate, the
+    argmin, the first feasible schedule and the counts agree exactly, for the full range, a ragged
+    range (flat head + tree blocks + flat tail) and the shards of a 2-GPU / 8-GPU split; a sample of
+    schedules is also held to the oracle's trace."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    m = ko.get_model(name)
+    L = 17
+    rng = np.random.default_rng(23)
+    types = np.where(np.arange(L) % 5 == 2, 0, 1).astype(np.uint8)
+    times = 500.0 + np.cumsum(0.004 + 0.002 * rng.random(L))
+    times[9] = times[7] - 1e-4  # an out-of-order event: skipped when it would step back (kf_workers.py:38-40)
+    P0 = m.P0() * 1e-2
+    t_prev, t_end = 499.99, float(times[-1]) + 0.01
+    monkeypatch.setenv("B200KF_TREE", "0")
+    flat_eng = Engine(name)
+    monkeypatch.setenv("B200KF_TREE", "1")
+    tree_eng = Engine(name)
+    bf, pf = flat_eng.score_schedules(types, times, t_prev, t_end, P0, want_per_schedule=True, mode=mode)
+    thr = float(np.median(pf[:, 0].cpu().numpy()[1:]))
+    for first, count in ((0, 1 << L), (12345, 100001), (1 << 16, 1 << 16), (3 << 14, 1 << 14), (5, 300)):
+        bf, pf = flat_eng.score_schedules(types, times, t_prev, t_end, P0, first=first, count=count, threshold=thr,
+                                          want_per_schedule=True, mode=mode)
+        bt, pt = tree_eng.score_schedules(types, times, t_prev, t_end, P0, first=first, count=count, threshold=thr,
+                                          want_per_schedule=True, mode=mode)
+        np.testing.assert_array_equal(pt.cpu().numpy(), pf.cpu().numpy())
+        assert bt == bf
+    per = pt.cpu().numpy()  # last range: [5, 305)
+    for s in (5, 77, 304):
+        tr = ko.schedule_trace(m, types, times, s, P0, t_prev, t_end)
+        row = per[s - 5]
+        assert abs(row[0] - np.max(tr)) <= 1e-9 * max(1, abs(np.max(tr)))
+        assert abs(row[1] - np.sum(tr)) <= 1e-9 * max(1, abs(np.sum(tr)))
+        assert row[3] == len(tr)
+    bt, pt = tree_eng.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, want_per_schedule=True, mode=mode)
+    per = pt.cpu().numpy()
+    for s in (1, 0x1ABCD, (1 << L) - 1, 1 << 16):
+        tr = ko.schedule_trace(m, types, times, s, P0, t_prev, t_end)
+        assert abs(per[s][1] - np.sum(tr)) <= 1e-9 * max(1, abs(np.sum(tr)))
+        assert abs(per[s][2] - tr[-1]) <= 1e-9 * max(1, abs(tr[-1]))
