@@ -118,8 +118,51 @@ def accuracy_metrics():
     np.savez_compressed(os.path.join(OUT, "ca15_accuracy.npz"), **g)
 
 
+def experiment_windows():
+    """The reference's experiment loop (kf_workers.py:2298-2396, the body of its __main__, which is
+    not importable as a function): per window a warm-up adaptive filter from the start of the stream,
+    the full / greedy (adaptive) / optimal (brute force) / no-update runs over the window, and the
+    row the KalmanFilterLogger would write (:2150-2162).  Every call is the unmodified reference's;
+    only the loop that strings them together is restated here, with fixed r factors in place of
+    random.choice (:2309) and 8-event windows (2^8 subsets) so that the Python brute force ends."""
+    from multiprocessing.pool import ThreadPool
+    kw, _ = load_reference()
+    kw.Pool = lambda processes=None: ThreadPool(2)  # see the note in main(): forked Pool(30) hangs on early return
+    events = make_indexed_sensor_data(620, seed=17)
+    ty, tm, da = events_to_arrays(events)
+    events = arrays_to_events(ty, tm, da)
+    kf = kw.KF_SensorFusion("gps.csv", "imu.csv")
+    kf.indexed_sensor_data = events
+    lb_end, off = 100, 8
+    starts = [130, 275, 410, 505]
+    factors = [0.87, 0.94, 0.3, 0.9]  # mid-range thresholds select a few events; 0.3 (the reference's set) selects one
+    _, ld_full, _, _ = quiet(kf.run_kalman_filter_full, 0, lb_end)
+    lb = min(ld_full)
+    rows = []
+    for start_idx, fac in zip(starts, factors):
+        r_value = lb * fac
+        st_g, _, pt_g, _, _ = quiet(kf.run_adaptive_threshold_kalman_filter, end_idx=start_idx, R_threshold=r_value)
+        _, ld_w, _, _ = quiet(kf.run_kalman_filter_full, start_idx, start_idx + off, pt_g, st_g[-1], True)
+        r_value = (r_value / lb) * min(ld_w)
+        _, ldg, _, _, mtg = quiet(kf.run_adaptive_threshold_kalman_filter, start_idx, start_idx + off, r_value,
+                                  pt_g, st_g[-1], True)
+        bf = quiet(kf.run_brute_force_kalman_filter_no_sampling_min_usage, start_idx, start_idx + off, r_value,
+                   pt_g, st_g[-1])
+        _, ldn, _, _, _ = quiet(kf.run_no_update_kalman_filter, start_idx, start_idx + off, r_value, pt_g, st_g[-1], True)
+        rows.append([start_idx, len(mtg), len(bf["selected_sensors"]) if bf else 0,
+                     bf["log_determinants"][0] if bf else np.nan, ldg[-1], ldn[-1],
+                     bf["log_determinants"][-1] if bf else np.nan, r_value, off,
+                     sum(1 << (e[0] - start_idx) for e in bf["selected_sensors"]) if bf else -1])
+    np.savez_compressed(os.path.join(OUT, "ca15_experiment.npz"), ev_type=ty, ev_time=tm, ev_data=da,
+                        lb_end=np.int64(lb_end), lb=np.float64(lb), starts=np.array(starts), factors=np.array(factors),
+                        rows=np.array(rows, dtype=np.float64))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "exp":
+        experiment_windows()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "nb":
         notebook_bruteforce()
         return
@@ -299,6 +342,7 @@ def main():
                         kf_states=np.array(s8, dtype=np.float64), dr_states=np.array(d8, dtype=np.float64))
     notebook_bruteforce()
     accuracy_metrics()
+    experiment_windows()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

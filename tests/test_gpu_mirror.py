@@ -250,3 +250,38 @@ def test_rate_sweep_x_monte_carlo_seeds(golden):
             close(r["P"][sd].cpu().numpy(), P)
             close(r["x"][sd, :6].cpu().numpy(), np.array(st[-1][1:], dtype=float))
             assert abs(r["agg"][sd, 2].item() - ld[-1]) < 1e-9 * max(1.0, abs(ld[-1]))
+
+
+def test_window_experiment_matches_reference_rows(golden):
+    """The reference's experiment loop (kf_workers.py:2298-2358): greedy vs optimal vs no-update per
+    window, against rows produced by the unmodified reference's methods (oracle/make_golden.py exp)."""
+    from sensorfusion_kalmanfilter_b200.experiment import COLUMNS, adaptive_warmups, run_window_experiment
+    from sensorfusion_kalmanfilter_b200.kf_workers import KF_SensorFusion
+    g = golden("ca15_experiment.npz")
+    k = KF_SensorFusion("gps.csv", "imu.csv")
+    k.indexed_sensor_data = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])
+    starts = [int(v) for v in g["starts"]]
+    rows = run_window_experiment(k, starts, [float(v) for v in g["factors"]], start_offset=int(g["rows"][0][8]),
+                                 lb_end_idx=int(g["lb_end"]))
+    assert len(rows) == len(starts) and set(COLUMNS) <= set(rows[0])
+    for row, ref in zip(rows, g["rows"]):
+        assert row["start_idx"] == int(ref[0])
+        assert row["num_greedy_measurements"] == int(ref[1])      # the same gate decisions
+        assert row["num_optimal_measurements"] == int(ref[2])     # the same optimal schedule size ...
+        assert row["selected_mask"] == int(ref[9])                 # ... and the same schedule, bit-exact
+        for key, col in (("initial_optimal_log_det", 3), ("final_greedy_log_det", 4), ("final_noupdate_log_det", 5),
+                         ("final_optimal_log_det", 6), ("r_value", 7)):
+            assert abs(row[key] - ref[col]) <= R * max(1.0, abs(ref[col])), (key, row[key], ref[col])
+        assert row["logged"] == (int(ref[1]) != 0)
+    # the shared warm-up pass equals one warm-up per window from the start of the stream (:2316)
+    lb = float(g["lb"])
+    thr = [lb * float(f) for f in g["factors"]]
+    warm = adaptive_warmups(k, starts, thr)
+    for (st_last, P), s0, t in zip(warm, starts, thr):
+        st, _, Pd, _, _ = k.run_adaptive_threshold_kalman_filter(end_idx=s0, R_threshold=t)
+        assert st_last[0] == st[-1][0]
+        close(np.array(st_last[1:]), np.array(st[-1][1:]))
+        close(P, Pd)
+    # a window that starts before the first GPS fix: the reference fails at :2316 and logs an ERROR row
+    rows = run_window_experiment(k, [0], [0.5], start_offset=8, lb_end_idx=int(g["lb_end"]))
+    assert rows[0]["final_greedy_log_det"] == "ERROR"
