@@ -400,6 +400,102 @@ struct BlockKF {
     static_for<0, n>([&](auto I) { x[I] = real(x0[B::gidx(I)]); });
   }
 
+  // ---- shared-covariance interface: the gain warp extracts K = P+ H^T R^-1 once per step, the math
+  // warps predict and correct the state only (BlockKF and SymBlock both provide it) ----
+  template <bool GPS_EVENT>
+  static constexpr bool measured(int s) {
+    return GPS_EVENT ? (B::gps(s) >= 0) : (B::zk(s) != ZK_NONE);
+  }
+  template <bool GPS_EVENT>
+  static constexpr int n_meas() {
+    int c = 0;
+    for (int s = 0; s < n; ++s) c += measured<GPS_EVENT>(s) ? 1 : 0;
+    return c;
+  }
+  template <bool GPS_EVENT>
+  static constexpr int meas_state(int c) {  // local state of measured column c
+    int k = 0;
+    for (int s = 0; s < n; ++s)
+      if (measured<GPS_EVENT>(s)) {
+        if (k == c) return s;
+        ++k;
+      }
+    return 0;
+  }
+  static constexpr int kslots = n * (n_meas<true>() > n_meas<false>() ? n_meas<true>() : n_meas<false>());
+  template <typename T>
+  __device__ __forceinline__ void load_cov_from(const T* __restrict__ Pg, int n_total) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      static_for<i, n>([&](auto J) {
+        constexpr int j = J;
+        P[pidx(i, j)] = real(0.5 * (double(Pg[B::gidx(i) * n_total + B::gidx(j)]) +
+                                    double(Pg[B::gidx(j) * n_total + B::gidx(i)])));
+      });
+    });
+  }
+  template <typename T>
+  __device__ __forceinline__ void load_state_from(const T* __restrict__ xg) {
+    static_for<0, n>([&](auto I) { x[I] = real(xg[B::gidx(I)]); });
+  }
+  template <typename T>
+  __device__ __forceinline__ void store_state_to(T* __restrict__ xg) const {
+    static_for<0, n>([&](auto I) { xg[B::gidx(I)] = T(x[I]); });
+  }
+  // K[i][c] = P+[i][s_c] / r_{s_c} for the event's measured local states s_c (row-major [n][n_meas])
+  // ir[c] = 1 / r_{s_c}, evaluated once per launch by the gain warp
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ static void inv_noise(const ModelConst& mc, double* ir) {
+    static_for<0, n_meas<GPS_EVENT>()>([&](auto C) {
+      constexpr int sc = meas_state<GPS_EVENT>(C);
+      ir[C] = 1.0 / (GPS_EVENT ? mc.r_gps[B::gps(sc) >= 0 ? B::gps(sc) : 0] : mc.r_imu[B::gidx(sc)]);
+    });
+  }
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void extract_gain(const double* ir, double* K) const {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    static_for<0, NM>([&](auto C) {
+      constexpr int c = C;
+      constexpr int sc = meas_state<GPS_EVENT>(c);
+      static_for<0, n>([&](auto I) { K[I * NM + c] = double(P[pidx(I, sc)]) * ir[c]; });
+    });
+  }
+  __device__ __forceinline__ void predict_state(real dt, const ModelConst& mc) {
+    const real a = dt;
+    const real b = real(mc.c2) * (dt * dt);
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      constexpr int L1 = B::l1(i);
+      constexpr int L2 = B::l2(i);
+      if constexpr (L1 >= 0 && L2 >= 0) x[i] += (real(B::s1(i)) * a) * x[L1] + (real(B::s2(i)) * b) * x[L2];
+      else if constexpr (L1 >= 0) x[i] += (real(B::s1(i)) * a) * x[L1];
+    });
+  }
+  // x += K (z - H x) with the innovation formed from the predicted state before any component moves
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void apply_gain(const double* __restrict__ K, const real* u) {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    if constexpr (NM > 0) {
+      real y[NM];
+      static_for<0, NM>([&](auto C) {
+        constexpr int sc = meas_state<GPS_EVENT>(C);
+        const real z = GPS_EVENT ? u[B::gps(sc) >= 0 ? B::gps(sc) : 0] : zbuf[sc];
+        y[C] = z - x[sc];
+      });
+      static_for<0, n>([&](auto I) {
+        real acc = x[I];
+        static_for<0, NM>([&](auto C) { acc = fma(real(K[I * NM + C]), y[C], acc); });
+        x[I] = acc;
+      });
+    }
+  }
+  template <typename T>
+  __device__ __forceinline__ void store_cov_to(const double* cov, T* __restrict__ Pg, int n_total) const {
+    static_for<0, n>([&](auto I) {
+      static_for<0, n>([&](auto J) { Pg[B::gidx(I) * n_total + B::gidx(J)] = T(cov[pidx(I, J)]); });
+    });
+  }
+
   // det P: closed form for n <= 3, LDL^T pivots otherwise.  ok is cleared on a non-positive pivot.
   __device__ __forceinline__ real det(bool& ok) const {
     if constexpr (n == 1) {
@@ -555,6 +651,119 @@ struct SymBlock {
     members([&](auto Bm, auto Mi) {
       using BM = decltype(Bm);
       static_for<0, n>([&](auto I) { x[Mi][I] = real(x0[BM::gidx(I)]); });
+    });
+  }
+
+  // ---- shared-covariance interface (see BlockKF) ----
+  template <bool GPS_EVENT>
+  static constexpr bool measured(int s) {
+    return GPS_EVENT ? (B0::gps(s) >= 0) : (B0::zk(s) != ZK_NONE);
+  }
+  template <bool GPS_EVENT>
+  static constexpr int n_meas() {
+    int c = 0;
+    for (int s = 0; s < n; ++s) c += measured<GPS_EVENT>(s) ? 1 : 0;
+    return c;
+  }
+  template <bool GPS_EVENT>
+  static constexpr int meas_state(int c) {
+    int k = 0;
+    for (int s = 0; s < n; ++s)
+      if (measured<GPS_EVENT>(s)) {
+        if (k == c) return s;
+        ++k;
+      }
+    return 0;
+  }
+  static constexpr int kslots = n * (n_meas<true>() > n_meas<false>() ? n_meas<true>() : n_meas<false>());
+  template <typename T>
+  __device__ __forceinline__ void load_cov_from(const T* __restrict__ Pg, int n_total) {
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      static_for<i, n>([&](auto J) {
+        constexpr int j = J;
+        P[pidx(i, j)] = real(0.5 * (double(Pg[B0::gidx(i) * n_total + B0::gidx(j)]) +
+                                    double(Pg[B0::gidx(j) * n_total + B0::gidx(i)])));
+      });
+    });
+  }
+  template <typename T>
+  __device__ __forceinline__ void load_state_from(const T* __restrict__ xg) {
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) { x[Mi][I] = real(xg[BM::gidx(I)]); });
+    });
+  }
+  template <typename T>
+  __device__ __forceinline__ void store_state_to(T* __restrict__ xg) const {
+    members([&](auto Bm, auto Mi) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) { xg[BM::gidx(I)] = T(x[Mi][I]); });
+    });
+  }
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ static void inv_noise(const ModelConst& mc, double* ir) {
+    static_for<0, n_meas<GPS_EVENT>()>([&](auto C) {
+      constexpr int sc = meas_state<GPS_EVENT>(C);
+      ir[C] = 1.0 / (GPS_EVENT ? mc.r_gps[B0::gps(sc) >= 0 ? B0::gps(sc) : 0] : mc.r_imu[B0::gidx(sc)]);
+    });
+  }
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void extract_gain(const double* ir, double* K) const {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    static_for<0, NM>([&](auto C) {
+      constexpr int c = C;
+      constexpr int sc = meas_state<GPS_EVENT>(c);
+      static_for<0, n>([&](auto I) { K[I * NM + c] = double(P[pidx(I, sc)]) * ir[c]; });
+    });
+  }
+  __device__ __forceinline__ void predict_state(real dt, const ModelConst& mc) {
+    const real a = dt;
+    const real b = real(mc.c2) * (dt * dt);
+    static_for<0, n>([&](auto I) {
+      constexpr int i = I;
+      constexpr int L1 = B0::l1(i);
+      constexpr int L2 = B0::l2(i);
+      if constexpr (L1 >= 0 && L2 >= 0) {
+        const real c1 = real(B0::s1(i)) * a, c2 = real(B0::s2(i)) * b;
+#pragma unroll
+        for (int m = 0; m < M; ++m) x[m][i] += c1 * x[m][L1] + c2 * x[m][L2];
+      } else if constexpr (L1 >= 0) {
+        const real c1 = real(B0::s1(i)) * a;
+#pragma unroll
+        for (int m = 0; m < M; ++m) x[m][i] += c1 * x[m][L1];
+      }
+    });
+  }
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void apply_gain(const double* __restrict__ K, const real* u) {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    if constexpr (NM > 0) {
+      real k[n * NM];
+      static_for<0, n * NM>([&](auto E) { k[E] = real(K[E]); });  // one broadcast read per gain, all members use it
+      members([&](auto Bm, auto Mi) {
+        using BM = decltype(Bm);
+        real y[NM];
+        static_for<0, NM>([&](auto C) {
+          constexpr int sc = meas_state<GPS_EVENT>(C);
+          const real z = GPS_EVENT ? u[BM::gps(sc) >= 0 ? BM::gps(sc) : 0] : zbuf[Mi][sc];
+          y[C] = z - x[Mi][sc];
+        });
+        static_for<0, n>([&](auto I) {
+          real acc = x[Mi][I];
+          static_for<0, NM>([&](auto C) { acc = fma(k[I * NM + C], y[C], acc); });
+          x[Mi][I] = acc;
+        });
+      });
+    }
+  }
+  template <typename T>
+  __device__ __forceinline__ void store_cov_to(const double* cov, T* __restrict__ Pg, int n_total) const {
+    members([&](auto Bm, auto) {
+      using BM = decltype(Bm);
+      static_for<0, n>([&](auto I) {
+        static_for<0, n>([&](auto J) { Pg[BM::gidx(I) * n_total + BM::gidx(J)] = T(cov[pidx(I, J)]); });
+      });
     });
   }
 

@@ -743,6 +743,307 @@ __global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Shared-covariance kernel for every model (CA15 / CA8 / BIAS9; CV6 keeps the tuned kernel above).
+// Same structure -- copy warp, gain warp, 28 math warps, payload ring -- with the model's generic
+// block engine: the gain warp runs the covariance-only filter of the axis-symmetric form
+// (filter_predict<false> / filter_update<false>, float64) and publishes per step the gain matrix
+// K = P+ H^T R^-1 of every block (columns of P+ over the measurement variances, exact for selector
+// H and diagonal R) plus the log-det; a math thread predicts its filter's state with the chain
+// tables, builds the IMU pseudo-measurement from the predicted state (kf_workers.py:698-706) and
+// applies x += K (z - H x) jointly -- the same update as the stage-by-stage scalar form, in exact
+// arithmetic.  Monte-Carlo seeds of one configuration (BASELINE configs[1]: 4096 seeds per rate)
+// and batches started from the reference's fixed P0 (configs[4]) take this path in AUTO mode.
+// ------------------------------------------------------------------------------------------
+template <class Flt>
+struct GainSlots {
+  static constexpr int value = 0;
+  static constexpr int cov = 0;
+};
+template <typename real, bool IC, class B0, class... Bs>
+struct GainSlots<FilterT<real, IC, B0, Bs...>> {
+  using Blk = typename BlockObj<B0, real>::type;
+  static constexpr int value = Blk::kslots + GainSlots<FilterT<real, IC, Bs...>>::value;
+  static constexpr int cov = Blk::NP + GainSlots<FilterT<real, IC, Bs...>>::cov;
+};
+
+template <int MODEL, typename real>
+struct SharedRing {  // ring depth per model: stages * chunk * d rows of 896 reals within ~200 KB
+  static constexpr int d = ModelTraits<MODEL, false, real>::d;
+  static constexpr int chunk = (d >= 8) ? 1 : 2;
+  static constexpr int stages = (d >= 8) ? 3 : (d >= 4 ? 3 : 4);
+};
+
+#ifndef B200KF_L2PF_G
+#define B200KF_L2PF_G 0
+#endif
+constexpr int kL2PrefetchG = B200KF_L2PF_G;  // chunks of L2 look-ahead beyond the chunk being issued (generic shared kernel)
+
+template <int NG>
+struct GainRecG {
+  double dt;
+  double logdet;
+  int type;
+  int pad;
+  double g[NG > 0 ? NG : 1];
+};
+
+template <int MODEL, typename real, bool FULL>
+__global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_generic_kernel(const RunParams p) {
+  using MT = ModelTraits<MODEL, false, real>;
+  using FltX = typename SymTraits<MODEL, real>::Filter;    // math warps: state only
+  using FltP = typename SymTraits<MODEL, double>::Filter;  // gain warp: covariance only, float64
+  constexpr int n = MT::n;
+  constexpr int D = MT::d;
+  constexpr bool CTRL = MT::imu_control;
+  constexpr int NG = GainSlots<FltP>::value;
+  constexpr int NCOV = GainSlots<FltP>::cov;
+  using Rec = GainRecG<NG>;
+  constexpr int kSt = SharedRing<MODEL, real>::stages;
+  constexpr int kCh = SharedRing<MODEL, real>::chunk;
+  if (!mode_selected(p.dense_flag, MODE_SHARED)) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kSt][kCh][D][kMathThreads]
+  constexpr size_t kStageReals = static_cast<size_t>(kCh) * D * kMathThreads;
+  Rec* gain_buf = reinterpret_cast<Rec*>(stage_buf + kSt * kStageReals);  // [kSt][kCh]
+  double* fin = reinterpret_cast<double*>(gain_buf + kSt * kCh);          // cov[NCOV], max, sum, last, ok
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(fin + NCOV + 4);
+  unsigned long long* empty = full + kSt;
+
+  const int tid = threadIdx.x;
+  const long long N = p.n_filters;
+  const long long base = static_cast<long long>(blockIdx.x) * kMathThreads;
+  const int nfb = static_cast<int>((N - base) < kMathThreads ? (N - base) : kMathThreads);
+  const int T = p.n_steps;
+  const int nchunks = (T + kCh - 1) / kCh;
+  const unsigned row_bytes = static_cast<unsigned>(nfb * sizeof(real));
+
+  if (tid == 0) {
+    for (int s = 0; s < kSt; ++s) {
+      mbar_init(&full[s], 2);  // the copy warp's expect_tx arrival + the gain warp's arrival
+      mbar_init(&empty[s], kMathThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= kMathThreads + 32) {
+    // ---------------- copy warp ----------------------------------------------------------------
+    if (tid == kMathThreads + 32) {
+      const real* pay = static_cast<const real*>(p.payload) + base;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int s = chunk % kSt;
+        if (chunk >= kSt) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kSt - 1) & 1u);
+        const int k0 = chunk * kCh;
+        const int steps = (T - k0) < kCh ? (T - k0) : kCh;
+        mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * D * row_bytes);
+        real* dst = stage_buf + s * kStageReals;
+        for (int cc = 0; cc < steps; ++cc)
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            bulk_g2s(dst + (cc * D + j) * kMathThreads, pay + (static_cast<long long>(k0 + cc) * D + j) * N,
+                     row_bytes, &full[s]);
+        if constexpr (kL2PrefetchG > 0) {  // a shallow ring (d = 9: 3 steps) sees the DRAM latency: pull later rows into L2
+          const int kp = (chunk + kL2PrefetchG) * kCh;
+          for (int cc = 0; cc < kCh; ++cc)
+            if (kp + cc < T)
+#pragma unroll
+              for (int j = 0; j < D; ++j)
+                bulk_prefetch_l2(pay + (static_cast<long long>(kp + cc) * D + j) * N, row_bytes);
+        }
+      }
+    }
+  } else if (tid >= kMathThreads) {
+    // ---------------- gain warp: the launch's one covariance recursion ------------------------------
+    if (tid == kMathThreads) {
+      FltP flt;
+      const real* Pg = static_cast<const real*>(p.P) + base * (n * n);  // this CTA's first filter (all are equal)
+      flt.each([&](auto& b) { b.load_cov_from(Pg, n); });
+      double ir_gps[kMaxN], ir_imu[kMaxN];  // 1 / r per measured column, block after block
+      {
+        int og = 0, oi = 0;
+        flt.each([&](const auto& b) {
+          using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+          BT::template inv_noise<true>(p.mc, ir_gps + og);
+          og += BT::template n_meas<true>();
+          if constexpr (!CTRL) {
+            BT::template inv_noise<false>(p.mc, ir_imu + oi);
+            oi += BT::template n_meas<false>();
+          }
+        });
+      }
+      LogDetAcc acc;
+      bool ok = true;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int s = chunk % kSt;
+        if (chunk >= kSt) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kSt - 1) & 1u);
+        const int k0 = chunk * kCh;
+        const int steps = (T - k0) < kCh ? (T - k0) : kCh;
+        for (int cc = 0; cc < steps; ++cc) {
+          const double dt = __ldg(p.dts + k0 + cc);
+          const int ty = __ldg(p.types + k0 + cc);
+          Rec* rec = gain_buf + s * kCh + cc;
+          filter_predict<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+          filter_update<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+          int o = 0, oc = 0;
+          if (ty == EV_GPS) {
+            flt.each([&](const auto& b) {
+              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+              b.template extract_gain<true>(ir_gps + oc, rec->g + o);
+              o += BT::kslots;
+              oc += BT::template n_meas<true>();
+            });
+          } else if (ty == EV_IMU) {
+            if constexpr (!CTRL) {
+              flt.each([&](const auto& b) {
+                using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+                b.template extract_gain<false>(ir_imu + oc, rec->g + o);
+                o += BT::kslots;
+                oc += BT::template n_meas<false>();
+              });
+            }
+          }
+          const double det = filter_det(flt, ok);
+          ok = ok && (det < INFINITY);
+          acc.add(det);
+          rec->dt = dt;
+          rec->type = ty;
+          rec->pad = 0;
+          rec->logdet = 0.0;
+          if constexpr (FULL) {
+            if (p.logdet != nullptr) rec->logdet = log(det);
+          }
+        }
+        mbar_arrive(&full[s]);  // release: the records are visible to whoever sees the phase flip
+      }
+      int o = 0;
+      flt.each([&](const auto& b) {
+        using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+#pragma unroll
+        for (int e = 0; e < BT::NP; ++e) fin[o + e] = b.P[e];
+        o += BT::NP;
+      });
+      fin[NCOV + 0] = (T > 0) ? log(acc.maxdet) : -INFINITY;
+      fin[NCOV + 1] = acc.sum_log();
+      fin[NCOV + 2] = (T > 0) ? log(acc.last) : 0.0;
+      fin[NCOV + 3] = ok ? 1.0 : 0.0;
+    }
+  } else {
+    // ---------------- math warps: predict the state, x += K (z - H x) -----------------------------
+    const bool active = tid < nfb;
+    const long long f = base + tid;
+    FltX flt;
+    if (active) {
+      const real* xg = static_cast<const real*>(p.x) + f * n;
+      flt.each([&](auto& b) { b.load_state_from(xg); });
+    }
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int s = chunk % kSt;
+      mbar_wait(&full[s], static_cast<unsigned>(chunk / kSt) & 1u);
+      const int k0 = chunk * kCh;
+      const int steps = (T - k0) < kCh ? (T - k0) : kCh;
+      if (active) {
+        const real* sb = stage_buf + s * kStageReals + tid;
+#pragma unroll
+        for (int cc = 0; cc < kCh; ++cc) {
+          if (cc < steps) {
+            const Rec* rec = gain_buf + s * kCh + cc;
+            const real dt = static_cast<real>(rec->dt);
+            const int ty = rec->type;
+            real u[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) u[j] = sb[(cc * D + j) * kMathThreads];
+            flt.each([&](auto& b) { b.predict_state(dt, p.mc); });
+            if (ty == EV_IMU) {
+              if constexpr (CTRL) {
+                flt.each([&](auto& b) { b.control(dt, p.mc, u); });
+              } else {
+                flt.each([&](auto& b) { b.build_imu_z(dt, u); });
+                int o = 0;
+                flt.each([&](auto& b) {
+                  using BT = std::remove_reference_t<decltype(b)>;
+                  b.template apply_gain<false>(rec->g + o, u);
+                  o += BT::kslots;
+                });
+              }
+            } else if (ty == EV_GPS) {
+              int o = 0;
+              flt.each([&](auto& b) {
+                using BT = std::remove_reference_t<decltype(b)>;
+                b.template apply_gain<true>(rec->g + o, u);
+                o += BT::kslots;
+              });
+            }
+            if constexpr (FULL) {
+              const long long k = k0 + cc;
+              if (p.traj != nullptr) {
+                real* tr = static_cast<real*>(p.traj) + (k * p.traj_ncomp) * N + f;
+                const int nc = p.traj_ncomp;
+                flt.each([&](const auto& b) {
+                  b.for_each_state([&](auto G, real v) {
+                    constexpr int g = G;
+                    if (g < nc) __stcs(tr + static_cast<long long>(g) * N, v);
+                  });
+                });
+              }
+              if (p.logdet != nullptr) __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(rec->logdet));
+              if (p.used != nullptr) p.used[k * N + f] = (ty != EV_PREDICT_ONLY) ? 1 : 0;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    }
+    if (active) {
+      real* xg = static_cast<real*>(p.x) + f * n;
+      flt.each([&](const auto& b) { b.store_state_to(xg); });
+    }
+  }
+
+  __syncthreads();  // the gain warp's final covariance and aggregates
+  if (tid >= nfb) return;
+  const long long f = base + tid;
+  if (T > 0) {
+    real* Pg = static_cast<real*>(p.P) + f * (n * n);
+    FltP shape;  // only its static tables are used
+    int o = 0;
+    shape.each([&](const auto& b) {
+      using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+      b.store_cov_to(fin + o, Pg, n);
+      o += BT::NP;
+    });
+  }
+  if (p.agg != nullptr) {
+    double* ag = p.agg + f * 4;
+    double mx = fin[NCOV + 0], sm = fin[NCOV + 1], cnt = static_cast<double>(T);
+    if (p.agg_continue) {
+      mx = fmax(mx, ag[0]);
+      sm += ag[1];
+      cnt += ag[3];
+    }
+    ag[0] = mx;
+    ag[1] = sm;
+    ag[2] = (T > 0) ? fin[NCOV + 2] : (p.agg_continue ? ag[2] : 0.0);
+    ag[3] = cnt;
+  }
+  if (p.status != nullptr) {
+    const int bad = (T > 0 && fin[NCOV + 3] == 0.0) ? 1 : 0;
+    p.status[f] = p.agg_continue ? (p.status[f] | bad) : bad;
+  }
+}
+
+template <int MODEL, typename real>
+constexpr size_t shared_generic_smem_bytes() {
+  using MT = ModelTraits<MODEL, false, real>;
+  using FltP = typename SymTraits<MODEL, double>::Filter;
+  constexpr int kSt = SharedRing<MODEL, real>::stages, kCh = SharedRing<MODEL, real>::chunk;
+  return static_cast<size_t>(kSt) * kCh * MT::d * kMathThreads * sizeof(real) +
+         static_cast<size_t>(kSt) * kCh * sizeof(GainRecG<GainSlots<FltP>::value>) +
+         (GainSlots<FltP>::cov + 4) * sizeof(double) + 2 * kSt * sizeof(unsigned long long);
+}
+
 template <int MODEL, typename real>
 constexpr size_t shared_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
@@ -838,17 +1139,35 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
 // shared-covariance kernel: eligible models (all chains one axis-symmetric (position, velocity) group),
 // aggregate / trajectory / log-det outputs; the adaptive gate and per-step P stay with the other kernels
 template <int MODEL, typename real>
-constexpr bool shared_eligible() {
+constexpr bool shared_lean() {  // the tuned (position, velocity) kernel; every other model takes the generic one
   using MT = ModelTraits<MODEL, false, real>;
   if constexpr (!MT::Filter::fast2) return false;
   else if constexpr (!MT::Sym2::eligible) return false;
   else return MT::Sym2::lean_ok;
 }
+template <int MODEL, typename real>
+constexpr bool shared_eligible() {
+  return true;
+}
 
 template <int MODEL, typename real>
 static cudaError_t launch_shared(const RunParams& p, bool full, cudaStream_t st) {
-  if constexpr (!shared_eligible<MODEL, real>()) {
-    return cudaErrorInvalidValue;
+  if constexpr (!shared_lean<MODEL, real>()) {
+    constexpr size_t smem = shared_generic_smem_bytes<MODEL, real>();
+    const unsigned blocks = static_cast<unsigned>((p.n_filters + kMathThreads - 1) / kMathThreads);
+    cudaError_t err;
+    if (full) {
+      err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (err != cudaSuccess) return err;
+      kf_run_shared_generic_kernel<MODEL, real, true><<<blocks, kSharedThreads, smem, st>>>(p);
+    } else {
+      err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (err != cudaSuccess) return err;
+      kf_run_shared_generic_kernel<MODEL, real, false><<<blocks, kSharedThreads, smem, st>>>(p);
+    }
+    return cudaGetLastError();
   } else {
     constexpr size_t smem = shared_smem_bytes<MODEL, real>();
     const unsigned blocks = static_cast<unsigned>((p.n_filters + kMathThreads - 1) / kMathThreads);
@@ -916,7 +1235,12 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   const bool tma = tma_possible<MODEL, real>(m, p, full);
   const bool sym = sym_possible<MODEL, real>(m);
   const bool tma_sym = tma && tma_sym_eligible<MODEL, real>();
-  const bool shared = tma_sym && sym && shared_eligible<MODEL, real>() && m->use_shared != 0 && !p.gate_enabled;
+  // the shared-covariance kernels stream the payload with bulk copies: 16-byte aligned rows
+  const long long align_elems = 16 / static_cast<long long>(sizeof(real));
+  const bool ring_ok = p.n_steps >= 1 && p.ptraj == nullptr && m->use_tma != 0 && (p.n_filters % align_elems) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p.payload) & 15u) == 0;
+  const bool shared = ring_ok && sym && shared_eligible<MODEL, real>() && m->use_shared != 0 && !p.gate_enabled &&
+                      (!shared_lean<MODEL, real>() || tma_sym);
   if ((flags & B200KF_RUN_FORCE_SHARED) && shared) {
     p.dense_flag = nullptr;
     B200KF_CUDA_TRY((launch_shared<MODEL, real>(p, full, st)));

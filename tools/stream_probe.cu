@@ -23,7 +23,6 @@
     }                                                                                \
   } while (0)
 
-constexpr int D = 3;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned c) {
@@ -50,7 +49,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 
 // (a) TMA ring: F consumer threads + one producer warp; STAGES x CHUNK steps x D rows of F doubles
-template <int F, int STAGES, int CHUNK>
+template <int F, int STAGES, int CHUNK, int D>
 __global__ void __launch_bounds__(F + 32) ring_kernel(const double* __restrict__ pay, long long N, int T, double* out) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* buf = reinterpret_cast<double*>(smem);
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(F + 32) ring_kernel(const double* __restrict__
 }
 
 // (b) per-thread LDG, U steps in flight
-template <int U>
+template <int U, int D>
 __global__ void ldg_kernel(const double* __restrict__ pay, long long N, int T, double* out) {
   const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (f >= N) return;
@@ -174,29 +173,28 @@ static double time_ms(L&& launch, int reps = 5) {
   return ms / reps;
 }
 
-template <int F, int STAGES, int CHUNK>
+template <int F, int STAGES, int CHUNK, int D = 3>
 static void run_ring(const double* pay, long long N, int T, double* out, double bytes) {
   constexpr size_t smem = static_cast<size_t>(STAGES) * CHUNK * D * F * 8 + 2 * STAGES * 8;
   if (smem > 227 * 1024) return;
-  CK(cudaFuncSetAttribute(ring_kernel<F, STAGES, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CK(cudaFuncSetAttribute(ring_kernel<F, STAGES, CHUNK, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const unsigned blocks = static_cast<unsigned>((N + F - 1) / F);
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, STAGES, CHUNK>, F + 32, smem));
-  const double ms = time_ms([&] { ring_kernel<F, STAGES, CHUNK><<<blocks, F + 32, smem>>>(pay, N, T, out); });
-  printf("ring  F=%4d stages=%2d chunk=%d  smem=%6zu B  ctas=%4u (%d/SM)  %8.3f ms  %7.1f GB/s\n", F, STAGES, CHUNK, smem,
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, STAGES, CHUNK, D>, F + 32, smem));
+  const double ms = time_ms([&] { ring_kernel<F, STAGES, CHUNK, D><<<blocks, F + 32, smem>>>(pay, N, T, out); });
+  printf("ring  D=%d F=%4d stages=%2d chunk=%d  smem=%6zu B  ctas=%4u (%d/SM)  %8.3f ms  %7.1f GB/s\n", D, F, STAGES, CHUNK, smem,
          blocks, occ, ms, bytes / ms / 1e6);
 }
 
-template <int U>
+template <int U, int D = 3>
 static void run_ldg(const double* pay, long long N, int T, double* out, double bytes, int tpb) {
   const unsigned blocks = static_cast<unsigned>((N + tpb - 1) / tpb);
-  const double ms = time_ms([&] { ldg_kernel<U><<<blocks, tpb>>>(pay, N, T, out); });
+  const double ms = time_ms([&] { ldg_kernel<U, D><<<blocks, tpb>>>(pay, N, T, out); });
   printf("ldg   U=%2d tpb=%4d  ctas=%5u  %8.3f ms  %7.1f GB/s\n", U, tpb, blocks, ms, bytes / ms / 1e6);
 }
 
-int main(int argc, char** argv) {
-  const long long N = argc > 1 ? atoll(argv[1]) : 131072;
-  const int T = argc > 2 ? atoi(argv[2]) : 2000;
+template <int D>
+static void sweep(long long N, int T) {
   const long long total = static_cast<long long>(T) * D * N;
   const double bytes = static_cast<double>(total) * 8;
   double *pay, *out;
@@ -209,29 +207,47 @@ int main(int argc, char** argv) {
     const double ms = time_ms([&] { flat_kernel<<<148 * 16, 512>>>(reinterpret_cast<const double2*>(pay), total / 2, out); });
     printf("flat  LDG.128 grid-stride                      %8.3f ms  %7.1f GB/s\n", ms, bytes / ms / 1e6);
   }
-  run_ring<896, 5, 2>(pay, N, T, out, bytes);
-  run_ring<896, 3, 3>(pay, N, T, out, bytes);
-  run_ring<896, 10, 1>(pay, N, T, out, bytes);
-  run_ring<896, 2, 5>(pay, N, T, out, bytes);
-  run_ring<448, 8, 2>(pay, N, T, out, bytes);
-  run_ring<448, 4, 2>(pay, N, T, out, bytes);
-  run_ring<448, 4, 4>(pay, N, T, out, bytes);
-  run_ring<448, 5, 2>(pay, N, T, out, bytes);
-  run_ring<224, 8, 2>(pay, N, T, out, bytes);
-  run_ring<224, 4, 4>(pay, N, T, out, bytes);
-  run_ring<128, 8, 2>(pay, N, T, out, bytes);
-  run_ring<128, 4, 4>(pay, N, T, out, bytes);
-  run_ring<1024 - 32, 4, 2>(pay, N, T, out, bytes);
-  run_ring<512, 6, 2>(pay, N, T, out, bytes);
-  run_ring<256, 6, 2>(pay, N, T, out, bytes);
-  run_ring<256, 12, 1>(pay, N, T, out, bytes);
+  if constexpr (D == 3) {
+    run_ring<896, 5, 2, D>(pay, N, T, out, bytes);
+    run_ring<896, 3, 3, D>(pay, N, T, out, bytes);
+    run_ring<896, 10, 1, D>(pay, N, T, out, bytes);
+    run_ring<896, 2, 5, D>(pay, N, T, out, bytes);
+    run_ring<448, 8, 2, D>(pay, N, T, out, bytes);
+    run_ring<448, 4, 2, D>(pay, N, T, out, bytes);
+    run_ring<448, 4, 4, D>(pay, N, T, out, bytes);
+    run_ring<224, 4, 4, D>(pay, N, T, out, bytes);
+    run_ring<128, 4, 4, D>(pay, N, T, out, bytes);
+    run_ring<1024 - 32, 4, 2, D>(pay, N, T, out, bytes);
+    run_ring<512, 6, 2, D>(pay, N, T, out, bytes);
+    run_ring<256, 6, 2, D>(pay, N, T, out, bytes);
+  } else {
+    run_ring<896, 3, 1, D>(pay, N, T, out, bytes);
+    run_ring<896, 2, 1, D>(pay, N, T, out, bytes);
+    run_ring<448, 6, 1, D>(pay, N, T, out, bytes);
+    run_ring<448, 3, 1, D>(pay, N, T, out, bytes);
+    run_ring<448, 3, 2, D>(pay, N, T, out, bytes);
+    run_ring<224, 6, 1, D>(pay, N, T, out, bytes);
+    run_ring<224, 12, 1, D>(pay, N, T, out, bytes);
+    run_ring<224, 6, 2, D>(pay, N, T, out, bytes);
+    run_ring<128, 5, 1, D>(pay, N, T, out, bytes);
+    run_ring<128, 10, 2, D>(pay, N, T, out, bytes);
+    run_ring<640, 4, 1, D>(pay, N, T, out, bytes);
+  }
   for (int tpb : {128, 256, 896}) {
-    run_ldg<1>(pay, N, T, out, bytes, tpb);
-    run_ldg<2>(pay, N, T, out, bytes, tpb);
-    run_ldg<4>(pay, N, T, out, bytes, tpb);
-    run_ldg<8>(pay, N, T, out, bytes, tpb);
+    run_ldg<1, D>(pay, N, T, out, bytes, tpb);
+    run_ldg<2, D>(pay, N, T, out, bytes, tpb);
+    run_ldg<4, D>(pay, N, T, out, bytes, tpb);
   }
   CK(cudaFree(pay));
   CK(cudaFree(out));
+}
+
+int main(int argc, char** argv) {
+  const long long N = argc > 1 ? atoll(argv[1]) : 131072;
+  const int T = argc > 2 ? atoi(argv[2]) : 2000;
+  const int d = argc > 3 ? atoi(argv[3]) : 3;
+  if (d == 9) sweep<9>(N, T);
+  else if (d == 4) sweep<4>(N, T);
+  else sweep<3>(N, T);
   return 0;
 }
