@@ -300,7 +300,8 @@ def run_gpu_arm(a):
         # ---- dominant kernel alone (decoupled/dense as dispatched), CUDA events on the launch stream
         # (auto resolves to the axis-symmetric kernel for this workload: P0 and the rates are the same on x, y, z)
         sym_on = os.environ.get("B200KF_SYM", "1") != "0" and tma_on
-        kmode = a.mode if a.mode != "auto" else ("symmetric" if sym_on else "decoupled")
+        sym_any = os.environ.get("B200KF_SYM", "1") != "0"  # every model has an axis-symmetric form (LDG kernel if not CV6)
+        kmode = a.mode if a.mode != "auto" else ("symmetric" if (sym_on or (sym_any and a.model != "CV6")) else "decoupled")
         for _ in range(2):
             one_step(kmode)
         torch.cuda.synchronize()
@@ -357,7 +358,7 @@ def run_gpu_arm(a):
         # ---- shared-covariance leg: all filters start from the SAME P0 (SURVEY 8(d) config 3 as written;
         # Monte-Carlo seeds of one configuration): AUTO runs ONE covariance / gain recursion per launch
         shared_mode = None
-        if tma_on and not a.no_shared:
+        if os.environ.get("B200KF_TMA", "1") != "0" and os.environ.get("B200KF_SHARED", "1") != "0" and not a.no_shared:
             eng_sh = Engine(a.model, precision=a.precision)
             xs = torch.zeros((N, sp.n), dtype=eng.real, device=dev)
             Ps = torch.from_numpy(np.repeat(sp.default_P0()[None], N, axis=0)).to(device=dev, dtype=eng.real).contiguous()
@@ -373,7 +374,7 @@ def run_gpu_arm(a):
             hms = h0.elapsed_time(h1) / reps
             shared_mode = {"value": N * T / (hms * 1e-3), "unit": UNIT, "ms": hms,
                            "workload": f"{N} filters x {T} steps, identical P0 for every filter, mode auto "
-                                       "(chain-compat check + kf_run_shared_kernel)",
+                                       f"(chain-compat check + {'kf_run_shared_kernel' if a.model == 'CV6' else 'kf_run_shared_generic_kernel'})",
                            "achieved_gbs": alg_bytes / (hms * 1e-3) / 1e9,
                            "frac_of_hbm_peak": alg_bytes / (hms * 1e-3) / 1e9 / hbm_peak}
             del xs, Ps, eng_sh

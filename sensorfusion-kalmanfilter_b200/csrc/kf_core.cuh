@@ -489,6 +489,28 @@ struct BlockKF {
       });
     }
   }
+  // build the innovation from the predicted state and apply the gains in one pass (no z buffer):
+  // y = z - x is (v + u dt) dt for the position pseudo-measurement, u dt for the velocity one
+  // (kf_workers.py:698-709) and u - x for directly measured states
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void correct(const double* __restrict__ K, real dt, const real* u) {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    if constexpr (NM > 0) {
+      real y[NM];
+      static_for<0, NM>([&](auto C) {
+        constexpr int sc = meas_state<GPS_EVENT>(C);
+        if constexpr (GPS_EVENT) y[C] = u[B::gps(sc) >= 0 ? B::gps(sc) : 0] - x[sc];
+        else if constexpr (B::zk(sc) == ZK_POS) y[C] = (x[B::l1(sc)] + u[B::pz(sc)] * dt) * dt;
+        else if constexpr (B::zk(sc) == ZK_VEL) y[C] = u[B::pz(sc)] * dt;
+        else y[C] = u[B::pz(sc)] - x[sc];
+      });
+      static_for<0, n>([&](auto I) {
+        real acc = x[I];
+        static_for<0, NM>([&](auto C) { acc = fma(real(K[I * NM + C]), y[C], acc); });
+        x[I] = acc;
+      });
+    }
+  }
   template <typename T>
   __device__ __forceinline__ void store_cov_to(const double* cov, T* __restrict__ Pg, int n_total) const {
     static_for<0, n>([&](auto I) {
@@ -752,6 +774,28 @@ struct SymBlock {
         static_for<0, n>([&](auto I) {
           real acc = x[Mi][I];
           static_for<0, NM>([&](auto C) { acc = fma(k[I * NM + C], y[C], acc); });
+          x[Mi][I] = acc;
+        });
+      });
+    }
+  }
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void correct(const double* __restrict__ K, real dt, const real* u) {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    if constexpr (NM > 0) {
+      members([&](auto Bm, auto Mi) {
+        using BM = decltype(Bm);
+        real y[NM];
+        static_for<0, NM>([&](auto C) {
+          constexpr int sc = meas_state<GPS_EVENT>(C);
+          if constexpr (GPS_EVENT) y[C] = u[BM::gps(sc) >= 0 ? BM::gps(sc) : 0] - x[Mi][sc];
+          else if constexpr (BM::zk(sc) == ZK_POS) y[C] = (x[Mi][BM::l1(sc)] + u[BM::pz(sc)] * dt) * dt;
+          else if constexpr (BM::zk(sc) == ZK_VEL) y[C] = u[BM::pz(sc)] * dt;
+          else y[C] = u[BM::pz(sc)] - x[Mi][sc];
+        });
+        static_for<0, n>([&](auto I) {
+          real acc = x[Mi][I];
+          static_for<0, NM>([&](auto C) { acc = fma(real(K[I * NM + C]), y[C], acc); });
           x[Mi][I] = acc;
         });
       });

@@ -278,9 +278,13 @@ static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, c
   out[k] = r;
 }
 
-template <int MODEL, typename real, bool SYM, bool FULL>
-__global__ void __launch_bounds__(kWsThreads, 1)
+template <int MODEL, typename real, bool SYM, bool FULL, int F>
+__global__ void __launch_bounds__(F + 32, 1)
     kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched) {
+  // F math threads (filters) per CTA: 896 fills an SM with one CTA; 448 / 224 keep every SM busy when a
+  // GPU's shard is small (N <= 148 * 448), with a proportionally deeper ring in the same shared memory
+  constexpr int kTmaThreads = F;
+  constexpr int kStages = b200kf::kStages * (896 / F);
   using MT = ModelTraits<MODEL, false, real>;
   using Flt = std::conditional_t<SYM, typename MT::Sym2, typename MT::Dec2>;
   constexpr int n = MT::n;
@@ -486,8 +490,10 @@ struct GainRec {  // 56 bytes
   int pad;
 };
 
-template <int MODEL, typename real, bool FULL>
-__global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_kernel(const RunParams p) {
+template <int MODEL, typename real, bool FULL, int F>
+__global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParams p) {
+  constexpr int kMathThreads = F;
+  constexpr int kStages = b200kf::kStages * (896 / F);
   using MT = ModelTraits<MODEL, false, real>;
   using S2 = typename MT::Sym2;
   using B0 = typename S2::Lead;
@@ -788,8 +794,9 @@ struct GainRecG {
   double g[NG > 0 ? NG : 1];
 };
 
-template <int MODEL, typename real, bool FULL>
-__global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_generic_kernel(const RunParams p) {
+template <int MODEL, typename real, bool FULL, int F>
+__global__ void __launch_bounds__(F + 64, 1) kf_run_shared_generic_kernel(const RunParams p) {
+  constexpr int kMathThreads = F;
   using MT = ModelTraits<MODEL, false, real>;
   using FltX = typename SymTraits<MODEL, real>::Filter;    // math warps: state only
   using FltP = typename SymTraits<MODEL, double>::Filter;  // gain warp: covariance only, float64
@@ -799,7 +806,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_generic_kerne
   constexpr int NG = GainSlots<FltP>::value;
   constexpr int NCOV = GainSlots<FltP>::cov;
   using Rec = GainRecG<NG>;
-  constexpr int kSt = SharedRing<MODEL, real>::stages;
+  constexpr int kSt = SharedRing<MODEL, real>::stages * (896 / F);
   constexpr int kCh = SharedRing<MODEL, real>::chunk;
   if (!mode_selected(p.dense_flag, MODE_SHARED)) return;
 
@@ -959,11 +966,10 @@ __global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_generic_kerne
               if constexpr (CTRL) {
                 flt.each([&](auto& b) { b.control(dt, p.mc, u); });
               } else {
-                flt.each([&](auto& b) { b.build_imu_z(dt, u); });
                 int o = 0;
                 flt.each([&](auto& b) {
                   using BT = std::remove_reference_t<decltype(b)>;
-                  b.template apply_gain<false>(rec->g + o, u);
+                  b.template correct<false>(rec->g + o, dt, u);
                   o += BT::kslots;
                 });
               }
@@ -971,7 +977,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_generic_kerne
               int o = 0;
               flt.each([&](auto& b) {
                 using BT = std::remove_reference_t<decltype(b)>;
-                b.template apply_gain<true>(rec->g + o, u);
+                b.template correct<true>(rec->g + o, dt, u);
                 o += BT::kslots;
               });
             }
@@ -1034,29 +1040,37 @@ __global__ void __launch_bounds__(kSharedThreads, 1) kf_run_shared_generic_kerne
   }
 }
 
-template <int MODEL, typename real>
+template <int MODEL, typename real, int F>
 constexpr size_t shared_generic_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
   using FltP = typename SymTraits<MODEL, double>::Filter;
-  constexpr int kSt = SharedRing<MODEL, real>::stages, kCh = SharedRing<MODEL, real>::chunk;
-  return static_cast<size_t>(kSt) * kCh * MT::d * kMathThreads * sizeof(real) +
+  constexpr int kSt = SharedRing<MODEL, real>::stages * (896 / F), kCh = SharedRing<MODEL, real>::chunk;
+  return static_cast<size_t>(kSt) * kCh * MT::d * F * sizeof(real) +
          static_cast<size_t>(kSt) * kCh * sizeof(GainRecG<GainSlots<FltP>::value>) +
          (GainSlots<FltP>::cov + 4) * sizeof(double) + 2 * kSt * sizeof(unsigned long long);
 }
 
-template <int MODEL, typename real>
+template <int MODEL, typename real, int F>
 constexpr size_t shared_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
-  return static_cast<size_t>(kStages) * kChunk * MT::d * kMathThreads * sizeof(real) +
-         static_cast<size_t>(kStages) * kChunk * sizeof(GainRec) + 8 * sizeof(double) +
-         2 * kStages * sizeof(unsigned long long);
+  constexpr int st = kStages * (896 / F);
+  return static_cast<size_t>(st) * kChunk * MT::d * F * sizeof(real) +
+         static_cast<size_t>(st) * kChunk * sizeof(GainRec) + 8 * sizeof(double) + 2 * st * sizeof(unsigned long long);
 }
 
-template <int MODEL, typename real>
+template <int MODEL, typename real, int F>
 constexpr size_t tma_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
-  return static_cast<size_t>(kStages) * kChunk * MT::d * kTmaThreads * sizeof(real) +
-         static_cast<size_t>(kStages) * kChunk * sizeof(SchedRec) + 2 * kStages * sizeof(unsigned long long);
+  constexpr int st = kStages * (896 / F);
+  return static_cast<size_t>(st) * kChunk * MT::d * F * sizeof(real) +
+         static_cast<size_t>(st) * kChunk * sizeof(SchedRec) + 2 * st * sizeof(unsigned long long);
+}
+
+// filters per CTA of the ring kernels: the largest of {896, 448, 224} that still gives every SM a CTA
+static int pick_ring_f(long long n_filters, int sm_count) {
+  if (n_filters > static_cast<long long>(sm_count) * 448) return 896;
+  if (n_filters > static_cast<long long>(sm_count) * 224) return 448;
+  return 224;
 }
 
 // AUTO/forced launch of the TMA kernels.  Returns true when they were enqueued (then the caller
@@ -1090,14 +1104,21 @@ constexpr bool tma_sym_eligible() {
   else return MT::Sym2::eligible;
 }
 
-template <int MODEL, typename real, bool SYM, bool FULL>
-static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, unsigned blocks, size_t smem,
-                                  cudaStream_t st) {
-  cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, FULL>,
+template <int MODEL, typename real, bool SYM, bool FULL, int F>
+static cudaError_t launch_tma_f(const RunParams& p, const SchedRec* sched, cudaStream_t st) {
+  constexpr size_t smem = tma_smem_bytes<MODEL, real, F>();
+  const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
+  cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, FULL, F>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kf_run_tma_kernel<MODEL, real, SYM, FULL><<<blocks, kWsThreads, smem, st>>>(p, sched);
+  kf_run_tma_kernel<MODEL, real, SYM, FULL, F><<<blocks, F + 32, smem, st>>>(p, sched);
   return cudaGetLastError();
+}
+template <int MODEL, typename real, bool SYM, bool FULL>
+static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, int f, cudaStream_t st) {
+  if (f == 896) return launch_tma_f<MODEL, real, SYM, FULL, 896>(p, sched, st);
+  if (f == 448) return launch_tma_f<MODEL, real, SYM, FULL, 448>(p, sched, st);
+  return launch_tma_f<MODEL, real, SYM, FULL, 224>(p, sched, st);
 }
 
 template <int MODEL, typename real>
@@ -1118,17 +1139,16 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     }
     pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc, sched);
     cudaError_t err = cudaSuccess;
-    constexpr size_t smem = tma_smem_bytes<MODEL, real>();
-    const unsigned blocks = static_cast<unsigned>((p.n_filters + kTmaThreads - 1) / kTmaThreads);
+    const int f = pick_ring_f(p.n_filters, m->sm_count);
     if (with_dec) {
-      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, blocks, smem, st)
-                 : launch_tma_one<MODEL, real, false, false>(p, sched, blocks, smem, st);
+      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, f, st)
+                 : launch_tma_one<MODEL, real, false, false>(p, sched, f, st);
       if (err != cudaSuccess) return err;
     }
     if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
       if (with_sym) {
-        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, blocks, smem, st)
-                   : launch_tma_one<MODEL, real, true, false>(p, sched, blocks, smem, st);
+        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, f, st)
+                   : launch_tma_one<MODEL, real, true, false>(p, sched, f, st);
         if (err != cudaSuccess) return err;
       }
     }
@@ -1150,41 +1170,36 @@ constexpr bool shared_eligible() {
   return true;
 }
 
-template <int MODEL, typename real>
-static cudaError_t launch_shared(const RunParams& p, bool full, cudaStream_t st) {
+template <int MODEL, typename real, bool FULL, int F>
+static cudaError_t launch_shared_f(const RunParams& p, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
+  cudaError_t err;
   if constexpr (!shared_lean<MODEL, real>()) {
-    constexpr size_t smem = shared_generic_smem_bytes<MODEL, real>();
-    const unsigned blocks = static_cast<unsigned>((p.n_filters + kMathThreads - 1) / kMathThreads);
-    cudaError_t err;
-    if (full) {
-      err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (err != cudaSuccess) return err;
-      kf_run_shared_generic_kernel<MODEL, real, true><<<blocks, kSharedThreads, smem, st>>>(p);
-    } else {
-      err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (err != cudaSuccess) return err;
-      kf_run_shared_generic_kernel<MODEL, real, false><<<blocks, kSharedThreads, smem, st>>>(p);
-    }
-    return cudaGetLastError();
+    constexpr size_t smem = shared_generic_smem_bytes<MODEL, real, F>();
+    err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, FULL, F>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    kf_run_shared_generic_kernel<MODEL, real, FULL, F><<<blocks, F + 64, smem, st>>>(p);
   } else {
-    constexpr size_t smem = shared_smem_bytes<MODEL, real>();
-    const unsigned blocks = static_cast<unsigned>((p.n_filters + kMathThreads - 1) / kMathThreads);
-    cudaError_t err;
-    if (full) {
-      err = cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (err != cudaSuccess) return err;
-      kf_run_shared_kernel<MODEL, real, true><<<blocks, kSharedThreads, smem, st>>>(p);
-    } else {
-      err = cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (err != cudaSuccess) return err;
-      kf_run_shared_kernel<MODEL, real, false><<<blocks, kSharedThreads, smem, st>>>(p);
-    }
-    return cudaGetLastError();
+    constexpr size_t smem = shared_smem_bytes<MODEL, real, F>();
+    err = cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, FULL, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    kf_run_shared_kernel<MODEL, real, FULL, F><<<blocks, F + 64, smem, st>>>(p);
   }
+  return cudaGetLastError();
+}
+template <int MODEL, typename real>
+static cudaError_t launch_shared(const b200kf_model* m, const RunParams& p, bool full, cudaStream_t st) {
+  const int f = pick_ring_f(p.n_filters, m->sm_count);
+  if (full) {
+    if (f == 896) return launch_shared_f<MODEL, real, true, 896>(p, st);
+    if (f == 448) return launch_shared_f<MODEL, real, true, 448>(p, st);
+    return launch_shared_f<MODEL, real, true, 224>(p, st);
+  }
+  if (f == 896) return launch_shared_f<MODEL, real, false, 896>(p, st);
+  if (f == 448) return launch_shared_f<MODEL, real, false, 448>(p, st);
+  return launch_shared_f<MODEL, real, false, 224>(p, st);
 }
 
 template <int MODEL, typename real>
@@ -1243,7 +1258,7 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
                       (!shared_lean<MODEL, real>() || tma_sym);
   if ((flags & B200KF_RUN_FORCE_SHARED) && shared) {
     p.dense_flag = nullptr;
-    B200KF_CUDA_TRY((launch_shared<MODEL, real>(p, full, st)));
+    B200KF_CUDA_TRY((launch_shared<MODEL, real>(m, p, full, st)));
     return B200KF_OK;
   }
   if (flags & B200KF_RUN_FORCE_SHARED) flags |= B200KF_RUN_FORCE_SYMMETRIC;  // next-best guarantee
@@ -1277,7 +1292,7 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
           static_cast<const real*>(p.P), p.n_filters, flag);
   B200KF_CUDA_TRY(cudaGetLastError());
   p.dense_flag = flag;
-  if (shared) B200KF_CUDA_TRY((launch_shared<MODEL, real>(p, full, st)));
+  if (shared) B200KF_CUDA_TRY((launch_shared<MODEL, real>(m, p, full, st)));
   if (tma) {
     B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym && tma_sym, true, full, st)));
   } else {

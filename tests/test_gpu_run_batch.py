@@ -305,3 +305,23 @@ def test_shared_covariance_chunked_continuation_and_predict_only(name):
     a = agg.cpu().numpy()
     assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
     assert np.all(a[:, 3] == T)
+
+
+@pytest.mark.parametrize("N", [33150, 40000, 70002])
+def test_ring_kernels_at_every_cta_size(N, monkeypatch):
+    """The ring kernels pick 224 / 448 / 896 filters per CTA from the shard size (every SM gets a CTA
+    when a GPU's shard is small, e.g. BASELINE configs[4] on 8 GPUs = 32768 filters per GPU).  One
+    launch of each size class, per-filter covariance and shared covariance, against the oracle."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    T = 45
+    for name in ("CV6", "BIAS9"):
+        m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=51)
+        ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
+        for shared in ("1", "0"):
+            monkeypatch.setenv("B200KF_SHARED", shared)
+            out = Engine(name).run_batch(types, dts, payload, x0, P0)
+            assert int(out["status"].sum()) == 0
+            assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
+            assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
+            a = out["agg"].cpu().numpy()
+            assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
