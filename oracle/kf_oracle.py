@@ -292,7 +292,7 @@ def event_payload(model, stype, sdata):
     """Extract the packed payload of one event for `model` (what the host packer ships)."""
     u = np.zeros(model.d)
     if stype == "GPS":
-        vals = [sdata["easting"], sdata["northing"], sdata["altitude"]][: model.m_gps]
+        vals = [sdata["easting"], sdata["northing"], sdata.get("altitude", 0.0)][: model.m_gps]
         u[: model.m_gps] = vals
     elif model.name == "CA15":
         u[:] = [float(v) for v in sdata[1:10]]

@@ -158,8 +158,53 @@ def experiment_windows():
                         rows=np.array(rows, dtype=np.float64))
 
 
+def csv_front_end():
+    """The reference's CSV front end (kf_workers.py:290-385 and hw5_2.py:17-112: load_data ->
+    gps_to_modified_utm -> compute_imu_biases -> unbias_imu_data -> combine_sensor_data) run
+    unmodified on CSVs written by synth.write_config1_csvs(seed=3), and the first filter states on the
+    result.  Harness accommodation: the un-vendored third-party `utm` module the reference imports is
+    given the product's restatement (geo.from_latlon) as `utm.from_latlon`, so this pins everything of
+    the front end EXCEPT the lat/lon -> UTM series itself (which stays unpinned)."""
+    import tempfile
+    from sensorfusion_kalmanfilter_b200 import geo, synth
+    kw, hw = load_reference()
+    sys.modules["utm"].from_latlon = geo.from_latlon
+    g = {}
+    with tempfile.TemporaryDirectory() as d:
+        gps_path, imu_path = synth.write_config1_csvs(d, n_imu=1200, n_gps_nan=8, seed=3)
+        for tag, mod in (("kw", kw), ("hw", hw)):
+            k = mod.KF_SensorFusion(gps_path, imu_path)
+            quiet(k.load_data)
+            quiet(k.gps_to_modified_utm if tag == "kw" else k.gps_to_utm)
+            wb, ab, fvi = quiet(k.compute_imu_biases, k.gps_data, k.imu_data)
+            quiet(k.unbias_imu_data, wb, ab)
+            quiet(k.combine_sensor_data)
+            ev = k.indexed_sensor_data
+            ty = np.array([0 if e[1] == "GPS" else 1 for e in ev], dtype=np.uint8)
+            tm = np.array([e[2] for e in ev])
+            da = np.zeros((len(ev), 9))
+            for i, e in enumerate(ev):
+                if e[1] == "GPS":
+                    da[i, :2] = [e[3]["easting"], e[3]["northing"]]
+                    da[i, 2] = e[3].get("altitude", 0.0)
+                else:
+                    da[i] = [float(v) for v in e[3][1:10]]
+            g.update({f"{tag}_type": ty, f"{tag}_time": tm, f"{tag}_data": da, f"{tag}_wbias": wb, f"{tag}_abias": ab,
+                      f"{tag}_first_valid": np.int64(fvi)})
+            if tag == "kw":
+                st, ld, P, _ = quiet(k.run_kalman_filter_full, 0, 300)
+                g.update(kw_states=states_arr(st), kw_logdet=np.array(ld), kw_P=P)
+            else:
+                st = quiet(k.run_kalman_filter)
+                g.update(hw_states=np.array(st, dtype=np.float64))
+    np.savez_compressed(os.path.join(OUT, "csv_front_end.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "csv":
+        csv_front_end()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "exp":
         experiment_windows()
         return
@@ -343,6 +388,7 @@ def main():
     notebook_bruteforce()
     accuracy_metrics()
     experiment_windows()
+    csv_front_end()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

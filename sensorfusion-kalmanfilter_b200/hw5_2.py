@@ -3,13 +3,14 @@
 `KF_SensorFusion.run_kalman_filter()` -> `[(x, y, theta), ...]` (hw5_2.py:313-380) and
 `run_dead_reckoning_for_IMU()` (hw5_2.py:382-436).  The loops run in b200kf_run_batch with the
 compiled CA8 model; the getters below carry the reference's constants (hw5_2.py:219-304) and may be
-overridden (values only -- see models.spec_from_getters).  Data loading / plotting are out of scope.
+overridden (values only -- see models.spec_from_getters).  Plotting is out of scope.
 """
 from __future__ import annotations
 
 import numpy as np
 
-from . import streams
+from . import geo, streams
+from . import kf_workers as _kw
 from .kf_workers import _engine_for
 
 
@@ -22,6 +23,28 @@ class KF_SensorFusion:
         self.gps_data = []
         self.imu_data = []
         self.utm_data = []
+
+    # ---- CSV front end (hw5_2.py:17-112): the same preparation code as kf_workers.py, without altitude
+    load_data_from_csv = _kw.KF_SensorFusion.load_data_from_csv
+    load_data = _kw.KF_SensorFusion.load_data
+    compute_imu_biases = staticmethod(_kw.KF_SensorFusion.compute_imu_biases)
+    quaternion_to_euler = _kw.KF_SensorFusion.quaternion_to_euler
+    unbias_imu_data = _kw.KF_SensorFusion.unbias_imu_data
+    combine_sensor_data = _kw.KF_SensorFusion.combine_sensor_data
+
+    def gps_to_utm(self):
+        """hw5_2.py:29-52 (lat/lon -> UTM restated in geo.py, parity unpinned)."""
+        initial_easting = initial_northing = None
+        for entry in self.gps_data:
+            time, lat_str, lon_str, _ = entry
+            if "nan" in lat_str.lower() or "nan" in lon_str.lower():
+                continue
+            easting, northing, zone_number, zone_letter = geo.from_latlon(float(lat_str), float(lon_str))
+            if initial_easting is None or initial_northing is None:
+                initial_easting, initial_northing = easting, northing
+            self.utm_data.append({"time": float(time), "easting": easting - initial_easting,
+                                  "northing": northing - initial_northing, "zone_number": zone_number,
+                                  "zone_letter": zone_letter})
 
     # ---- model getters (hw5_2.py:219-311) ------------------------------------------------------
     def get_state_transition_matrix(self, dt):

@@ -10,8 +10,10 @@ reference's lists of tuples.  There is no CPU fallback: without the library or a
 methods raise.
 
 Where the reference's loops are reproduced, the line they follow is cited.  Out of scope (SURVEY.md
-section 2): plotting/animation, KalmanFilterLogger, the rosbag extractor, lat/lon -> UTM (needs the
-third-party `utm`; feed eastings/northings through `utm_data` / `indexed_sensor_data` directly).
+section 2): plotting/animation, KalmanFilterLogger, the rosbag extractor.  The CSV front end
+(load_data -> gps_to_modified_utm -> compute_imu_biases -> unbias_imu_data -> combine_sensor_data,
+kf_workers.py:290-385) is host-side as in the reference; its lat/lon -> UTM step restates the
+un-vendored third-party `utm` package (geo.py, parity unpinned).
 """
 from __future__ import annotations
 
@@ -21,7 +23,7 @@ from itertools import combinations
 
 import numpy as np
 
-from . import streams
+from . import geo, streams
 from .engine import Engine, cov_update
 from .models import DIMS, spec_from_getters
 
@@ -202,6 +204,22 @@ class KF_SensorFusion:
     def load_data(self):
         self.gps_data = self.load_data_from_csv(self.gps_csv_file)
         self.imu_data = self.load_data_from_csv(self.imu_csv_file)
+
+    def gps_to_modified_utm(self):
+        """kf_workers.py:304-332: UTM eastings / northings relative to the first valid fix, plus the
+        altitude; rows with a NaN field are dropped.  `utm.from_latlon` is restated in geo.py (the
+        third-party package is not vendored by the reference: parity for this step is unpinned)."""
+        initial_easting = initial_northing = None
+        for entry in self.gps_data:
+            time, lat_str, lon_str, alt_str = entry
+            if "nan" in lat_str.lower() or "nan" in lon_str.lower() or "nan" in alt_str.lower():
+                continue
+            easting, northing, zone_number, zone_letter = geo.from_latlon(float(lat_str), float(lon_str))
+            if initial_easting is None or initial_northing is None:
+                initial_easting, initial_northing = easting, northing
+            self.utm_data.append({"time": float(time), "easting": easting - initial_easting,
+                                  "northing": northing - initial_northing, "zone_number": zone_number,
+                                  "zone_letter": zone_letter, "altitude": float(alt_str)})
 
     @staticmethod
     def compute_imu_biases(gps_data, imu_data):

@@ -38,7 +38,7 @@ class PackedStream:
                 types[k] = GPS
                 data[k, 0] = sdata["easting"]
                 data[k, 1] = sdata["northing"]
-                data[k, 2] = sdata["altitude"]
+                data[k, 2] = sdata.get("altitude", 0.0)  # the 2-D loader (hw5_2.py:52) keeps no altitude
             else:
                 types[k] = IMU
                 data[k] = sdata[1:10]

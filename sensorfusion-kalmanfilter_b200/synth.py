@@ -89,3 +89,55 @@ def make_payload(model_d, types, n_filters, seed=1234, m_gps=3, dtype=np.float64
         rows[:, m_gps:, :] = 0.0
         out[g] = rows
     return np.ascontiguousarray(out.astype(dtype))
+
+
+def write_config1_csvs(directory, n_imu=4000, n_gps_nan=12, seed=0, gps_csv=None):
+    """BASELINE configs[0] inputs: `imu_data.csv` in the schema hw5_1.py:29-31
+    writes -- header + 11 columns (time, orientation x/y/z/w, angular_velocity x/y/z,
+    linear_acceleration x/y/z), 200 Hz, t_k = 1697739278.7381794 + 0.005 k, quaternion of small Euler
+    angles around (-0.0004, -0.0547, -0.0008) rad, w = bias + N(0, 0.002^2), a = bias + N(0, 0.05^2)
+    with the biases the reference measured (KF_SensorFusion.ipynb:1325-1328) -- and, unless `gps_csv`
+    names the reference's own gps_data.csv, a synthetic `gps_data.csv` in its schema (hw5_1.py:28:
+    time, latitude, longitude, altitude; ~10 Hz; leading rows without a fix are 'nan') on a slow
+    track around the data set's location.  Values are written with csv.writer so float(entry[k])
+    round-trips.  Returns (gps_path, imu_path)."""
+    import csv
+    import os
+    rng = np.random.default_rng(seed)
+    t0 = 1697739278.7381794
+    t_imu = t0 + 0.005 * np.arange(n_imu)
+    rpy = np.array([-0.0004, -0.0547, -0.0008]) + rng.normal(0.0, 0.002, (n_imu, 3))
+    cr, sr = np.cos(rpy[:, 0] / 2), np.sin(rpy[:, 0] / 2)
+    cp, sp = np.cos(rpy[:, 1] / 2), np.sin(rpy[:, 1] / 2)
+    cy, sy = np.cos(rpy[:, 2] / 2), np.sin(rpy[:, 2] / 2)
+    quat = np.stack([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                     cr * cp * cy + sr * sp * sy], axis=1)  # x, y, z, w
+    omg = np.array([-0.0016706, -0.00751355, -0.03627881]) + rng.normal(0.0, 0.002, (n_imu, 3))
+    acc = np.array([-0.523625, 0.00864235, -9.5308909]) + rng.normal(0.0, 0.05, (n_imu, 3))
+    imu_path = os.path.join(directory, "imu_data.csv")
+    with open(imu_path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["time", "orientation_x", "orientation_y", "orientation_z", "orientation_w",
+                    "angular_velocity_x", "angular_velocity_y", "angular_velocity_z",
+                    "linear_acceleration_x", "linear_acceleration_y", "linear_acceleration_z"])
+        for k in range(n_imu):
+            w.writerow([repr(float(t_imu[k]))] + [repr(float(v)) for v in quat[k]] + [repr(float(v)) for v in omg[k]]
+                       + [repr(float(v)) for v in acc[k]])
+    if gps_csv is not None:
+        return gps_csv, imu_path
+    n_gps = max(2, int(n_imu * 0.005 / 0.1))
+    t_gps = t0 + 0.0234 + 0.1 * np.arange(n_gps) + 1e-4 * rng.random(n_gps)
+    s = t_gps - t_gps[0]
+    lat = 42.3482 + 1e-6 * s + 2e-7 * rng.normal(size=n_gps)       # ~0.1 m/s northwards, ~2 cm noise
+    lon = -71.0924 + 2e-6 * np.sin(0.05 * s) + 2e-7 * rng.normal(size=n_gps)
+    alt = -19.5 + 0.01 * s + 0.05 * rng.normal(size=n_gps)
+    gps_path = os.path.join(directory, "gps_data.csv")
+    with open(gps_path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["time", "latitude", "longitude", "altitude"])
+        for k in range(n_gps):
+            if k < n_gps_nan:
+                w.writerow([repr(float(t_gps[k])), "nan", "nan", "nan"])
+            else:
+                w.writerow([repr(float(t_gps[k])), repr(float(lat[k])), repr(float(lon[k])), repr(float(alt[k]))])
+    return gps_path, imu_path
