@@ -310,6 +310,12 @@ class Engine:
         per_d = self._dev(np.atleast_1d(periods), torch.float64)
         tp_d = self._dev(np.atleast_1d(t_prev), torch.float64)
         I = int(per_d.numel())
+        if mode == "auto" and not isinstance(P0, torch.Tensor):
+            # P0 still on the host: a chain-compatible covariance takes the per-chain form of the kernel
+            # (an order of magnitude faster than the dense 15 x 15 one for the reference's P0, :851)
+            from .models import chain_compatible
+            if chain_compatible(sp.name, np.asarray(P0, dtype=np.float64).reshape(I, sp.n, sp.n)):
+                mode = "decoupled"
         P0_d = self._dev(np.asarray(P0, dtype=np.float64).reshape(I, sp.n, sp.n), torch.float64)
         if max_sel is None:
             max_sel = E
@@ -326,7 +332,8 @@ class Engine:
         return [sel_h[i, :min(int(ns[i]), max_sel)].copy() for i in range(I)], P_f
 
 
-    def scheduled_sweep(self, types, times, payload, rates, x0, P0, t_prev, *, traj_ncomp=0, mode="auto"):
+    def scheduled_sweep(self, types, times, payload, rates, x0, P0, t_prev, *, traj_ncomp=0, mode="auto",
+                        concurrent=True):
         """Sampling-rate sweep x Monte-Carlo seeds (BASELINE configs[1]; run_kalman_filter_scheduled
         with selection_method='greedy', kf_workers.py:826-957, for many seeds at once).
 
@@ -334,8 +341,11 @@ class Engine:
         seed's measurements of those events; rates: processing frequencies (Hz); x0 [N, n], P0 [n, n]
         and t_prev: state at the initialising event.  The greedy selection never reads a measurement,
         so it runs once per rate (all rates in one covariance-only launch); the N seeds of a rate then
-        share the selected schedule in one b200kf_run_batch.  Returns {rate: dict(sel, times, x, P, agg,
-        traj)}."""
+        share the selected schedule AND the covariance (same P0): one b200kf_run_batch per rate, which
+        AUTO resolves to the shared-covariance kernel.  A rate's batch of a few thousand seeds fills
+        only part of the GPU, so with concurrent=True every rate runs on its own stream (and its own
+        model object: the per-model scratch is not shared between in-flight launches).  Returns
+        {rate: dict(sel, times, x, P, agg, traj)}."""
         torch = _torch()
         sp = self.spec
         rates = list(rates)
@@ -348,16 +358,37 @@ class Engine:
                                      np.repeat(P0[None], len(rates), axis=0))
         x0_d = self._dev(x0, self.real)
         P0_d = self._dev(np.repeat(P0[None], N, axis=0), self.real)
+        engines = [self]
+        side = []
+        if concurrent and len(rates) > 1:
+            pool = getattr(self, "_sweep_engines", [])
+            while len(pool) < len(rates) - 1:
+                pool.append(Engine(self.spec, device=self.device.index))
+            self._sweep_engines = pool
+            engines = [self] + pool[:len(rates) - 1]
+            spool = getattr(self, "_sweep_streams", [])  # reused: the caching allocator keeps blocks per stream
+            while len(spool) < len(rates):
+                spool.append(torch.cuda.Stream(device=self.device))
+            self._sweep_streams = spool
+            side = spool[:len(rates)]
+        cur = torch.cuda.current_stream(self.device)
         out = {}
-        for f, sel in zip(rates, sels):
-            sel_d = torch.from_numpy(sel.astype(np.int64)).to(self.device)
-            st = times_d.index_select(0, sel_d)
-            dts = torch.diff(st, prepend=torch.tensor([t_prev], dtype=torch.float64, device=self.device))
-            r = self.run_batch(types_d.index_select(0, sel_d), dts, pay_d.index_select(0, sel_d).contiguous(),
-                               x0_d, P0_d, traj_ncomp=traj_ncomp, mode=mode)
+        for i, (f, sel) in enumerate(zip(rates, sels)):
+            eng = engines[i] if side else self
+            st_ = side[i] if side else cur
+            if side:
+                st_.wait_stream(cur)
+            with torch.cuda.stream(st_):
+                sel_d = torch.from_numpy(sel.astype(np.int64)).to(self.device)
+                st = times_d.index_select(0, sel_d)
+                dts = torch.diff(st, prepend=torch.tensor([t_prev], dtype=torch.float64, device=self.device))
+                r = eng.run_batch(types_d.index_select(0, sel_d), dts, pay_d.index_select(0, sel_d).contiguous(),
+                                  x0_d, P0_d, traj_ncomp=traj_ncomp, mode=mode, stream=st_)
             r["sel"] = sel
             r["times"] = st
             out[f] = r
+        for st_ in side:
+            cur.wait_stream(st_)
         return out
 
 
