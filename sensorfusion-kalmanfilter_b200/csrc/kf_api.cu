@@ -515,6 +515,8 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
   m->use_sym = 1;
   if (const char* s = getenv("B200KF_SYM")) m->use_sym = atoi(s) != 0;
+  m->ring_f_cap = 896;
+  if (const char* s = getenv("B200KF_RING_F")) m->ring_f_cap = atoi(s);
   m->use_tree = 1;
   if (const char* s = getenv("B200KF_TREE")) m->use_tree = atoi(s) != 0;
   m->use_shared = 1;

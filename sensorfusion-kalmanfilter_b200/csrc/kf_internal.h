@@ -30,6 +30,7 @@ struct b200kf_model {
   HostWorkspace host_ws;
   int use_sym;  // 1: axis-symmetric kernel when every filter's chains share one covariance (env B200KF_SYM=0 disables)
   int use_shared;  // 1: shared-covariance kernel when every filter of a launch carries the same P (env B200KF_SHARED=0 disables)
+  int ring_f_cap;  // largest filters-per-CTA the ring kernels may pick: 896 / 448 / 224 (env B200KF_RING_F)
   int use_tree;  // 1: prefix-sharing schedule-search kernel for aligned blocks (env B200KF_TREE=0 disables)
   int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };

@@ -5,6 +5,8 @@
 // schedule (type, dt) is shared by all filters so every branch is warp-uniform; the payload is
 // read time-major ([T, d, N], filter fastest) so each warp load is one fully coalesced 256-byte
 // (f64) request, software-prefetched PF steps ahead.
+#include <tuple>
+
 #include "kf_internal.h"
 
 #ifndef B200KF_INST_MODEL
@@ -785,21 +787,51 @@ struct SharedRing {  // ring depth per model: stages * chunk * d rows of 896 rea
 #endif
 constexpr int kL2PrefetchG = B200KF_L2PF_G;  // chunks of L2 look-ahead beyond the chunk being issued (generic shared kernel)
 
+// the blocks (tags) of a filter type, for "one gain warp per block"
+template <class Flt>
+struct FilterTags;
+template <typename real, bool IC, class... Bs>
+struct FilterTags<FilterT<real, IC, Bs...>> {
+  static constexpr int count = sizeof...(Bs);
+  template <int K>
+  using tag = std::tuple_element_t<K, std::tuple<Bs...>>;
+  template <int K>
+  using block = typename BlockObj<tag<K>, real>::type;
+  static constexpr int slot_offset(int k) {  // first gain slot of block k
+    constexpr int sl[] = {BlockObj<Bs, real>::type::kslots...};
+    int o = 0;
+    for (int i = 0; i < k; ++i) o += sl[i];
+    return o;
+  }
+  static constexpr int cov_offset(int k) {
+    constexpr int np[] = {BlockObj<Bs, real>::type::NP...};
+    int o = 0;
+    for (int i = 0; i < k; ++i) o += np[i];
+    return o;
+  }
+};
+
+constexpr int kMaxGainBlocks = 4;
 template <int NG>
 struct GainRecG {
   double dt;
-  double logdet;
+  double det[kMaxGainBlocks];    // det of each block (with its axis multiplicity), by its gain warp
+  double ldet[kMaxGainBlocks];   // log of it (per-step log-det output only)
   int type;
   int pad;
   double g[NG > 0 ? NG : 1];
 };
 
 template <int MODEL, typename real, bool FULL, int F>
-__global__ void __launch_bounds__(F + 64, 1) kf_run_shared_generic_kernel(const RunParams p) {
+__global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL, double>::Filter>::count + 2), 1)
+    kf_run_shared_generic_kernel(const RunParams p) {
   constexpr int kMathThreads = F;
   using MT = ModelTraits<MODEL, false, real>;
   using FltX = typename SymTraits<MODEL, real>::Filter;    // math warps: state only
-  using FltP = typename SymTraits<MODEL, double>::Filter;  // gain warp: covariance only, float64
+  using FltP = typename SymTraits<MODEL, double>::Filter;  // gain warps: covariance only, float64
+  using Tags = FilterTags<FltP>;
+  constexpr int NB = Tags::count;
+  static_assert(NB <= kMaxGainBlocks, "too many blocks");
   constexpr int n = MT::n;
   constexpr int D = MT::d;
   constexpr bool CTRL = MT::imu_control;
@@ -808,6 +840,8 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_generic_kernel(const 
   using Rec = GainRecG<NG>;
   constexpr int kSt = SharedRing<MODEL, real>::stages * (896 / F);
   constexpr int kCh = SharedRing<MODEL, real>::chunk;
+  // warp roles after the F / 32 math warps: NB gain warps (one block each), the copy warp, the aggregate warp
+  constexpr int kGainBase = kMathThreads, kCopyTid = kMathThreads + 32 * NB, kAggTid = kCopyTid + 32;
   if (!mode_selected(p.dense_flag, MODE_SHARED)) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -828,16 +862,44 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_generic_kernel(const 
 
   if (tid == 0) {
     for (int s = 0; s < kSt; ++s) {
-      mbar_init(&full[s], 2);  // the copy warp's expect_tx arrival + the gain warp's arrival
-      mbar_init(&empty[s], kMathThreads / 32);
+      mbar_init(&full[s], 1 + NB);                     // the copy warp's expect_tx arrival + one arrival per gain warp
+      mbar_init(&empty[s], kMathThreads / 32 + 1);     // the math warps + the aggregate warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (tid >= kMathThreads + 32) {
+  if (tid >= kAggTid) {
+    // ---------------- aggregate warp: log-det aggregates of the whole filter from the block determinants ----
+    if (tid == kAggTid) {
+      LogDetAcc acc;
+      bool ok = true;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int s = chunk % kSt;
+        mbar_wait(&full[s], static_cast<unsigned>(chunk / kSt) & 1u);
+        const int k0 = chunk * kCh;
+        const int steps = (T - k0) < kCh ? (T - k0) : kCh;
+        for (int cc = 0; cc < steps; ++cc) {
+          const Rec* rec = gain_buf + s * kCh + cc;
+          double det = 1.0;
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            const double dk = rec->det[k];
+            ok = ok && (dk > 0.0) && (dk < INFINITY);
+            det *= dk;
+          }
+          acc.add(det);
+        }
+        mbar_arrive(&empty[s]);
+      }
+      fin[NCOV + 0] = (T > 0) ? log(acc.maxdet) : -INFINITY;
+      fin[NCOV + 1] = acc.sum_log();
+      fin[NCOV + 2] = (T > 0) ? log(acc.last) : 0.0;
+      fin[NCOV + 3] = ok ? 1.0 : 0.0;
+    }
+  } else if (tid >= kCopyTid) {
     // ---------------- copy warp ----------------------------------------------------------------
-    if (tid == kMathThreads + 32) {
+    if (tid == kCopyTid) {
       const real* pay = static_cast<const real*>(p.payload) + base;
       for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int s = chunk % kSt;
@@ -861,80 +923,56 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_generic_kernel(const 
         }
       }
     }
-  } else if (tid >= kMathThreads) {
-    // ---------------- gain warp: the launch's one covariance recursion ------------------------------
-    if (tid == kMathThreads) {
-      FltP flt;
-      const real* Pg = static_cast<const real*>(p.P) + base * (n * n);  // this CTA's first filter (all are equal)
-      flt.each([&](auto& b) { b.load_cov_from(Pg, n); });
-      double ir_gps[kMaxN], ir_imu[kMaxN];  // 1 / r per measured column, block after block
-      {
-        int og = 0, oi = 0;
-        flt.each([&](const auto& b) {
-          using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
-          BT::template inv_noise<true>(p.mc, ir_gps + og);
-          og += BT::template n_meas<true>();
-          if constexpr (!CTRL) {
-            BT::template inv_noise<false>(p.mc, ir_imu + oi);
-            oi += BT::template n_meas<false>();
-          }
-        });
-      }
-      LogDetAcc acc;
-      bool ok = true;
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int s = chunk % kSt;
-        if (chunk >= kSt) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kSt - 1) & 1u);
-        const int k0 = chunk * kCh;
-        const int steps = (T - k0) < kCh ? (T - k0) : kCh;
-        for (int cc = 0; cc < steps; ++cc) {
-          const double dt = __ldg(p.dts + k0 + cc);
-          const int ty = __ldg(p.types + k0 + cc);
-          Rec* rec = gain_buf + s * kCh + cc;
-          filter_predict<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
-          filter_update<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
-          int o = 0, oc = 0;
-          if (ty == EV_GPS) {
-            flt.each([&](const auto& b) {
-              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
-              b.template extract_gain<true>(ir_gps + oc, rec->g + o);
-              o += BT::kslots;
-              oc += BT::template n_meas<true>();
-            });
-          } else if (ty == EV_IMU) {
-            if constexpr (!CTRL) {
-              flt.each([&](const auto& b) {
-                using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
-                b.template extract_gain<false>(ir_imu + oc, rec->g + o);
-                o += BT::kslots;
-                oc += BT::template n_meas<false>();
-              });
+  } else if (tid >= kGainBase) {
+    // ---------------- gain warps: block k's covariance recursion on one lane of warp k --------------
+    const int gw = (tid - kGainBase) >> 5;
+    if (((tid - kGainBase) & 31) == 0) {
+      static_for<0, NB>([&](auto Kc) {
+        constexpr int K = Kc;
+        if (gw != K) return;
+        using Tag = typename Tags::template tag<K>;
+        using Blk = typename Tags::template block<K>;
+        FilterT<double, CTRL, Tag> flt;  // this block alone: blocks never couple
+        const real* Pg = static_cast<const real*>(p.P) + base * (n * n);  // this CTA's first filter (all are equal)
+        flt.head.load_cov_from(Pg, n);
+        double ir_gps[kMaxN], ir_imu[kMaxN];  // 1 / r per measured column
+        Blk::template inv_noise<true>(p.mc, ir_gps);
+        if constexpr (!CTRL) Blk::template inv_noise<false>(p.mc, ir_imu);
+        constexpr int so = Tags::slot_offset(K);
+        bool ok = true;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+          const int s = chunk % kSt;
+          if (chunk >= kSt) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kSt - 1) & 1u);
+          const int k0 = chunk * kCh;
+          const int steps = (T - k0) < kCh ? (T - k0) : kCh;
+          for (int cc = 0; cc < steps; ++cc) {
+            const double dt = __ldg(p.dts + k0 + cc);
+            const int ty = __ldg(p.types + k0 + cc);
+            Rec* rec = gain_buf + s * kCh + cc;
+            filter_predict<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+            filter_update<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+            if (ty == EV_GPS) {
+              flt.head.template extract_gain<true>(ir_gps, rec->g + so);
+            } else if (ty == EV_IMU) {
+              if constexpr (!CTRL) flt.head.template extract_gain<false>(ir_imu, rec->g + so);
+            }
+            const double det = flt.head.det_total(ok);
+            rec->det[K] = det;
+            if constexpr (FULL) {
+              if (p.logdet != nullptr) rec->ldet[K] = log(det);
+            }
+            if constexpr (K == 0) {
+              rec->dt = dt;
+              rec->type = ty;
+              rec->pad = 0;
             }
           }
-          const double det = filter_det(flt, ok);
-          ok = ok && (det < INFINITY);
-          acc.add(det);
-          rec->dt = dt;
-          rec->type = ty;
-          rec->pad = 0;
-          rec->logdet = 0.0;
-          if constexpr (FULL) {
-            if (p.logdet != nullptr) rec->logdet = log(det);
-          }
+          mbar_arrive(&full[s]);  // release: this block's part of the records is visible with the phase flip
         }
-        mbar_arrive(&full[s]);  // release: the records are visible to whoever sees the phase flip
-      }
-      int o = 0;
-      flt.each([&](const auto& b) {
-        using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+        constexpr int co = Tags::cov_offset(K);
 #pragma unroll
-        for (int e = 0; e < BT::NP; ++e) fin[o + e] = b.P[e];
-        o += BT::NP;
+        for (int e = 0; e < Blk::NP; ++e) fin[co + e] = flt.head.P[e];
       });
-      fin[NCOV + 0] = (T > 0) ? log(acc.maxdet) : -INFINITY;
-      fin[NCOV + 1] = acc.sum_log();
-      fin[NCOV + 2] = (T > 0) ? log(acc.last) : 0.0;
-      fin[NCOV + 3] = ok ? 1.0 : 0.0;
     }
   } else {
     // ---------------- math warps: predict the state, x += K (z - H x) -----------------------------
@@ -993,7 +1031,12 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_generic_kernel(const 
                   });
                 });
               }
-              if (p.logdet != nullptr) __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(rec->logdet));
+              if (p.logdet != nullptr) {
+                double ld = 0.0;  // log det P = sum of the blocks' log-dets
+#pragma unroll
+                for (int k2 = 0; k2 < NB; ++k2) ld += rec->ldet[k2];
+                __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(ld));
+              }
               if (p.used != nullptr) p.used[k * N + f] = (ty != EV_PREDICT_ONLY) ? 1 : 0;
             }
           }
@@ -1008,7 +1051,7 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_generic_kernel(const 
     }
   }
 
-  __syncthreads();  // the gain warp's final covariance and aggregates
+  __syncthreads();  // the gain warps' final covariance and the aggregate warp's results
   if (tid >= nfb) return;
   const long long f = base + tid;
   if (T > 0) {
@@ -1067,8 +1110,9 @@ constexpr size_t tma_smem_bytes() {
 }
 
 // filters per CTA of the ring kernels: the largest of {896, 448, 224} that still gives every SM a CTA
-static int pick_ring_f(long long n_filters, int sm_count) {
-  if (n_filters > static_cast<long long>(sm_count) * 448) return 896;
+static int pick_ring_f(long long n_filters, int sm_count, int cap = 896) {
+  if (cap >= 896 && n_filters > static_cast<long long>(sm_count) * 448) return 896;
+  if (cap <= 224) return 224;
   if (n_filters > static_cast<long long>(sm_count) * 224) return 448;
   return 224;
 }
@@ -1139,7 +1183,7 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     }
     pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc, sched);
     cudaError_t err = cudaSuccess;
-    const int f = pick_ring_f(p.n_filters, m->sm_count);
+    const int f = pick_ring_f(p.n_filters, m->sm_count, m->ring_f_cap);
     if (with_dec) {
       err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, f, st)
                  : launch_tma_one<MODEL, real, false, false>(p, sched, f, st);
@@ -1179,7 +1223,8 @@ static cudaError_t launch_shared_f(const RunParams& p, cudaStream_t st) {
     err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, FULL, F>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    kf_run_shared_generic_kernel<MODEL, real, FULL, F><<<blocks, F + 64, smem, st>>>(p);
+    kf_run_shared_generic_kernel<MODEL, real, FULL, F>
+        <<<blocks, F + 32 * (FilterTags<typename SymTraits<MODEL, double>::Filter>::count + 2), smem, st>>>(p);
   } else {
     constexpr size_t smem = shared_smem_bytes<MODEL, real, F>();
     err = cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, FULL, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1191,7 +1236,11 @@ static cudaError_t launch_shared_f(const RunParams& p, cudaStream_t st) {
 }
 template <int MODEL, typename real>
 static cudaError_t launch_shared(const b200kf_model* m, const RunParams& p, bool full, cudaStream_t st) {
-  const int f = pick_ring_f(p.n_filters, m->sm_count);
+  // a step's rows must leave room for a ring deep enough to cover the loaded DRAM latency: at most ~32 KB per
+  // step and CTA (CA15 in float64 is 72 B per filter-step: 448 filters per CTA, 6 stages, +45 % over 896 / 3)
+  constexpr int kStepBytes896 = ModelTraits<MODEL, false, real>::d * static_cast<int>(sizeof(real)) * 896;
+  const int cap = (kStepBytes896 > 36 * 1024 && m->ring_f_cap > 448) ? 448 : m->ring_f_cap;
+  const int f = pick_ring_f(p.n_filters, m->sm_count, cap);
   if (full) {
     if (f == 896) return launch_shared_f<MODEL, real, true, 896>(p, st);
     if (f == 448) return launch_shared_f<MODEL, real, true, 448>(p, st);
