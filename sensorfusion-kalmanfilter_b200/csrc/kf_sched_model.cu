@@ -486,7 +486,7 @@ static void launch_score_var(const ScoreParams& p, bool tree, unsigned blocks, c
 // Every launch appends its per-block partials to the same array; returns their total number.
 constexpr int kTreeMinA = 14;
 constexpr int kMaxFlatBlocks = 2048;  // grid-stride beyond that
-constexpr int kMaxTreeBlocks = 512;   // <= 2 * (32 - kTreeMinA) tree launches per call: partials stay inside the scratch
+constexpr int kMaxTreeBlocks = 1184;  // 148 SMs x 8 blocks of 128 threads (72 registers); lowered when a call needs many tree launches
 
 template <>
 int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsigned flags,
@@ -519,6 +519,7 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
   unsigned long long cur = p.first;
   int total_blocks = 0;
   bool overflow = false;
+  unsigned long long tree_cap = kMaxTreeBlocks;
   auto launch = [&](unsigned long long lo, unsigned long long cnt, int a) {  // a >= 0: aligned tree block
     ScoreParams q = p;
     q.first = lo;
@@ -534,7 +535,7 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
       threads = 1ULL << (a - k);
     }
     unsigned long long blocks = (threads + kScoreTpb - 1) / kScoreTpb;
-    const unsigned long long cap = (a >= 0) ? kMaxTreeBlocks : kMaxFlatBlocks;
+    const unsigned long long cap = (a >= 0) ? tree_cap : kMaxFlatBlocks;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     const unsigned nb = static_cast<unsigned>(blocks);
@@ -547,6 +548,21 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
     else launch_score_var<VAR_DECOUPLED>(q, a >= 0, nb, st);
     total_blocks += static_cast<int>(nb);
   };
+  // number of tree launches of this call -> blocks per tree launch such that all partials fit in the scratch
+  int n_tree = 0;
+  if (tree_ok) {
+    for (unsigned long long c2 = p.first; c2 < end;) {
+      const int align = (c2 == 0) ? 63 : __builtin_ctzll(c2);
+      int a2 = 63 - __builtin_clzll(end - c2);
+      if (a2 > align) a2 = align;
+      if (a2 >= kTreeMinA) ++n_tree;
+      c2 += 1ULL << a2;
+    }
+  }
+  if (n_tree > 0) {
+    const int fit = (kMaxSearchPartials - 2 * kMaxFlatBlocks) / n_tree;
+    tree_cap = fit < kMaxTreeBlocks ? fit : kMaxTreeBlocks;
+  }
   if (p.count == 0) {
     launch(p.first, 0, -1);  // one block of idle threads writes the neutral partial
   }
@@ -577,7 +593,7 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
 // error against the track interpolated at the event times (calculate_accuracy_metrics, :766-802;
 // the interpolation depends on the event only, so `ref` holds it per flattened event).  Events are
 // gathered from small L1-resident tables; the block/grid reduction keeps the FIRST minimum
-// (strict '<' at :933) and the runner-up score.
+// (strict '<' at :933) and the runner-up score.  Same arithmetic per sequence whatever the sharing.
 __device__ __forceinline__ void product_merge(double& sc, unsigned long long& ix, double& ru, double osc,
                                               unsigned long long oix, double oru) {
   const bool take = osc < sc || (osc == sc && oix < ix);
@@ -592,51 +608,80 @@ __device__ __forceinline__ void product_merge(double& sc, unsigned long long& ix
 template <int MODEL, int VAR>
 __global__ void __launch_bounds__(kScoreTpb) product_kernel(const ProductParams p) {
   using MT = VariantTraits<MODEL, VAR, double>;
+  using Flt = typename MT::Filter;
   constexpr int n = MT::n;
   constexpr int D = MT::d;
   const int W = p.n_windows;
   double best_sc = INFINITY, best_ru = INFINITY;
   unsigned long long best_ix = ~0ULL;
 
-  for (unsigned long long idx = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
-       idx < p.count; idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-    const unsigned long long c = p.first + idx;
-    typename MT::Filter flt;
-    flt.each([&](auto& b) {
+  // Prefix sharing: consecutive indices differ in the LAST queues (itertools.product order), so a
+  // thread owns the q[W-2] * q[W-1] sequences that agree on windows 0..W-3, filters that prefix
+  // once and branches over the last two windows from saved copies of (filter, squared error, time).
+  const int qa = (W >= 2) ? p.q_len[W - 2] : 1;  // second-to-last queue (1 pseudo-entry when W == 1)
+  const int qb = p.q_len[W - 1];
+  const unsigned long long B = static_cast<unsigned long long>(qa) * qb;
+  const unsigned long long end = p.first + p.count;
+  const unsigned long long blk0 = p.first / B;
+  const unsigned long long nblk = (p.count == 0) ? 0 : ((end - 1) / B - blk0 + 1);
+
+  struct St {
+    Flt flt;
+    double sse, tprev;
+  };
+  auto step = [&](St& s, int w, int e) {
+    const double t = __ldg(p.times + e);
+    const double dt = (w == 0) ? 0.0 : t - s.tprev;  // :898
+    const int ty = __ldg(p.types + e);
+    double u[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) u[j] = __ldg(p.payload + static_cast<long long>(e) * D + j);
+    filter_predict<true>(s.flt, dt, p.mc, ty, u);
+    filter_update<true>(s.flt, dt, p.mc, ty, u);
+    double d2 = 0.0;  // |x[0:3] - ref|^2, then norm and square as numpy does (:788-790)
+    s.flt.each([&](const auto& b) {
+      b.for_each_state([&](auto G, double v) {
+        constexpr int g = G;
+        if constexpr (g < 3) {
+          const double d = v - __ldg(p.ref + static_cast<long long>(e) * 3 + g);
+          d2 += d * d;
+        }
+      });
+    });
+    const double nrm = sqrt(d2);
+    s.sse += nrm * nrm;
+    s.tprev = t;
+  };
+
+  for (unsigned long long bi = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; bi < nblk;
+       bi += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long c0 = (blk0 + bi) * B;
+    St s0;
+    s0.flt.each([&](auto& b) {
       b.load_cov(p.P0, n);
       b.load_state(p.x0);
     });
-    unsigned long long rem = c;
-    double tprev = 0.0, sse = 0.0;
-    for (int w = 0; w < W; ++w) {
+    s0.sse = 0.0;
+    s0.tprev = 0.0;
+    unsigned long long rem = c0;
+    for (int w = 0; w + 2 < W; ++w) {  // the shared prefix
       const unsigned long long digit = rem / p.stride[w];
       rem -= digit * p.stride[w];
-      const int e = p.q_off[w] + static_cast<int>(digit);
-      const double t = __ldg(p.times + e);
-      const double dt = (w == 0) ? 0.0 : t - tprev;  // :898
-      const int ty = __ldg(p.types + e);
-      double u[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) u[j] = __ldg(p.payload + static_cast<long long>(e) * D + j);
-      filter_predict<true>(flt, dt, p.mc, ty, u);
-      filter_update<true>(flt, dt, p.mc, ty, u);
-      double d2 = 0.0;  // |x[0:3] - ref|^2, then norm and square as numpy does (:788-790)
-      flt.each([&](const auto& b) {
-        b.for_each_state([&](auto G, double v) {
-          constexpr int g = G;
-          if constexpr (g < 3) {
-            const double d = v - __ldg(p.ref + static_cast<long long>(e) * 3 + g);
-            d2 += d * d;
-          }
-        });
-      });
-      const double nrm = sqrt(d2);
-      sse += nrm * nrm;
-      tprev = t;
+      step(s0, w, p.q_off[w] + static_cast<int>(digit));
     }
-    const double metric = sqrt(sse / static_cast<double>(W));
-    if (p.per_combo != nullptr) p.per_combo[idx] = metric;
-    if (!isnan(metric)) product_merge(best_sc, best_ix, best_ru, metric, c, INFINITY);  // NaN < best is false (:933)
+    for (int da = 0; da < qa; ++da) {
+      St s1 = s0;
+      if (W >= 2) step(s1, W - 2, p.q_off[W - 2] + da);
+      for (int db = 0; db < qb; ++db) {
+        const unsigned long long c = c0 + static_cast<unsigned long long>(da) * qb + db;
+        if (c < p.first || c >= end) continue;
+        St s2 = s1;
+        step(s2, W - 1, p.q_off[W - 1] + db);
+        const double metric = sqrt(s2.sse / static_cast<double>(W));
+        if (p.per_combo != nullptr) p.per_combo[c - p.first] = metric;
+        if (!isnan(metric)) product_merge(best_sc, best_ix, best_ru, metric, c, INFINITY);  // NaN < best is false (:933)
+      }
+    }
   }
 
 #pragma unroll
@@ -660,7 +705,10 @@ __global__ void __launch_bounds__(kScoreTpb) product_kernel(const ProductParams 
 template <>
 int launch_product_m<B200KF_INST_MODEL>(const b200kf_model* m, const ProductParams& p, unsigned flags,
                                         cudaStream_t st) {
-  unsigned long long blocks = (p.count + kScoreTpb - 1) / kScoreTpb;
+  const int W = p.n_windows;
+  const unsigned long long B = static_cast<unsigned long long>(W >= 2 ? p.q_len[W - 2] : 1) * p.q_len[W - 1];
+  const unsigned long long nthreads = (p.count == 0) ? 0 : ((p.first + p.count - 1) / B - p.first / B + 1);
+  unsigned long long blocks = (nthreads + kScoreTpb - 1) / kScoreTpb;
   if (blocks > static_cast<unsigned long long>(kMaxSearchBlocks)) blocks = kMaxSearchBlocks;
   if (blocks == 0) blocks = 1;
   using MT = ModelTraits<B200KF_INST_MODEL, false, double>;

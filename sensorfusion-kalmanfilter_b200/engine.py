@@ -333,7 +333,7 @@ class Engine:
 
 
     def scheduled_sweep(self, types, times, payload, rates, x0, P0, t_prev, *, traj_ncomp=0, mode="auto",
-                        concurrent=True):
+                        concurrent=True, sels=None):
         """Sampling-rate sweep x Monte-Carlo seeds (BASELINE configs[1]; run_kalman_filter_scheduled
         with selection_method='greedy', kf_workers.py:826-957, for many seeds at once).
 
@@ -345,7 +345,8 @@ class Engine:
         AUTO resolves to the shared-covariance kernel.  A rate's batch of a few thousand seeds fills
         only part of the GPU, so with concurrent=True every rate runs on its own stream (and its own
         model object: the per-model scratch is not shared between in-flight launches).  Returns
-        {rate: dict(sel, times, x, P, agg, traj)}."""
+        {rate: dict(sel, times, x, P, agg, traj)}; `sels={rate: sel}` skips the selection pass (further
+        batches of seeds over the same stream)."""
         torch = _torch()
         sp = self.spec
         rates = list(rates)
@@ -354,8 +355,11 @@ class Engine:
         pay_d = self._dev(payload, self.real)
         N = int(pay_d.shape[2])
         P0 = np.asarray(P0, dtype=np.float64)
-        sels, _ = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
-                                     np.repeat(P0[None], len(rates), axis=0))
+        if sels is None:  # pass the `sel` arrays of an earlier call to reuse them: they depend on (events, rates, P0) only
+            sels, _ = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
+                                         np.repeat(P0[None], len(rates), axis=0))
+        else:
+            sels = [np.asarray(sels[f]) for f in rates]
         x0_d = self._dev(x0, self.real)
         P0_d = self._dev(np.repeat(P0[None], N, axis=0), self.real)
         engines = [self]

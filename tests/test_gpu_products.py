@@ -96,12 +96,13 @@ def test_score_products_every_sequence_vs_oracle(nb, mode):
 
 
 def test_score_products_other_models_and_warm_start():
-    """CV6 / CA8 sequences from a non-trivial (x0, dense P0) against the oracle step by step."""
+    """CV6 / CA8 sequences from a non-trivial (x0, dense P0) against the oracle step by step, incl.
+    one and two windows (no shared prefix to walk)."""
+    import itertools
     from sensorfusion_kalmanfilter_b200.engine import Engine
     rng = np.random.default_rng(7)
-    for name in ("CV6", "CA8"):
+    for name, qlen in itertools.product(("CV6", "CA8"), ([3, 1, 4, 2, 3], [5], [2, 3])):
         m = ko.get_model(name)
-        qlen = [3, 1, 4, 2, 3]
         E = sum(qlen)
         times = 100.0 + np.sort(rng.uniform(0, 0.5, E))
         types = rng.integers(0, 2, E).astype(np.uint8)
@@ -115,7 +116,6 @@ def test_score_products_other_models_and_warm_start():
         per = per.cpu().numpy()
         off = np.concatenate(([0], np.cumsum(qlen)[:-1]))
         want = []
-        import itertools
         for digits in itertools.product(*[range(q) for q in qlen]):
             x, P, prev, sse = x0.copy(), P0.copy(), None, 0.0
             for w, dgt in enumerate(digits):
@@ -128,6 +128,12 @@ def test_score_products_other_models_and_warm_start():
         want = np.array(want)
         close(per, want)
         assert best["index"] == int(np.argmin(want))
+        # a ragged sub-range that starts and ends inside a thread's block of sequences
+        if len(want) > 6:
+            b2, p2 = eng.score_products(qlen, types, times, pay, ref, x0, P0, first=2, count=len(want) - 5,
+                                        want_per_combo=True)
+            close(p2.cpu().numpy(), want[2:len(want) - 3])
+            assert b2["index"] == 2 + int(np.argmin(want[2:len(want) - 3]))
 
 
 def test_score_products_argument_errors():
