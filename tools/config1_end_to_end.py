@@ -1,6 +1,7 @@
 """BASELINE configs[0] end to end: gps_data.csv + a synthetic imu_data.csv (hw5_1.py:28-31 schema) ->
 the reference's CSV front end -> the 15-state filter of kf_workers.py and the 8-state filter of hw5_2.py
-on the GPU, next to the oracle port of the same single-filter loop on one host core.
+on the GPU (the CPU port of the same single-filter loop is timed by bench.py's cpu_baseline leg:
+`single_filter_ca15`).
 
     python tools/config1_end_to_end.py [--gps-csv /path/to/gps_data.csv] [--imu-rows 60000]
 
@@ -17,7 +18,6 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-from oracle import kf_oracle as ko  # noqa: E402  (CPU baseline leg only)
 from sensorfusion_kalmanfilter_b200 import hw5_2, kf_workers, synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -44,14 +44,6 @@ with tempfile.TemporaryDirectory() as d:
         res = run()
         t_gpu = time.perf_counter() - t0
         n_steps = len(res[0]) - 1 if mod is kf_workers else len(res)
-        # CPU: the oracle port of the same loop on one core, bounded to 5000 events
-        m = ko.get_model("CA15" if mod is kf_workers else "CA8")
-        ev = k.indexed_sensor_data[:min(n_ev, 5000)]
-        t0 = time.perf_counter()
-        ref = ko.run_full(m, ev, 0, len(ev)) if mod is kf_workers else ko.hw5_2_run(m, ev)
-        t_cpu = time.perf_counter() - t0
-        n_cpu = len(ref[0]) - 1 if mod is kf_workers else len(ref)
         out[name] = {"events": n_ev, "filter_steps": n_steps, "front_end_s": round(t_front, 3),
-                     "gpu_s": round(t_gpu, 4), "gpu_steps_per_s": n_steps / t_gpu,
-                     "cpu_port_steps_per_s_1_core": n_cpu / t_cpu, "cpu_sample_events": len(ev)}
+                     "gpu_s": round(t_gpu, 4), "gpu_steps_per_s": n_steps / t_gpu}
 print(json.dumps(out))
