@@ -742,3 +742,35 @@ def product_search(model, queues, track_t, track_p, x0=None, P0=None):
     return {"selected_sensors": best[2], "final_state": best[3], "final_covariance": best[4],
             "trajectory": best[1], "accuracy_metric": best[0], "combo_index": best[5],
             "metrics": np.array(metrics)}
+
+
+# ---- sensor_scheduling_algorithm.ipynb:213-291 (a17): exhaustive multi-day schedule tree -------------
+def bf_schedule(P, H, z, days, k):
+    """Restatement of the notebook's BF_schedule sketch (not runnable as written: it reads undefined
+    globals / attributes), loop for loop: all C(G, k) subsets per day, covariance-only update
+    `cov_matrix` (:301-376) with R_t = diag(0.01 z_t^2) (:233-234), one global node index per level
+    (:246-247), minimum trace over the LAST level (:249-253), parents by divmod (:265-272), lists
+    reversed (:275-283).  Sensors are numbered 1..G as cov_matrix expects.  parity: restatement only."""
+    G = H.shape[0]
+    S_all = list(itertools.combinations(range(1, G + 1), k))
+    sets = [[np.array(P, dtype=np.float64)]]
+    best = None
+    for t in range(1, days + 1):
+        R = np.diag(0.01 * np.asarray(z[t - 1], dtype=np.float64) ** 2)
+        cur, obj_min = [], np.inf
+        for j in range(len(S_all) ** (t - 1)):
+            for S_cur in S_all:
+                Sig = cov_matrix(list(S_cur), sets[t - 1][j], R, H)
+                cur.append(Sig)
+                obj = np.trace(Sig)
+                if obj < obj_min:
+                    obj_min, best = obj, (S_cur, Sig.copy(), len(cur) - 1)
+        sets.append(cur)
+    S_g, Sig_g = [best[0]], [np.trace(best[1])]
+    a, b = divmod(best[2], len(S_all))
+    for t in range(days - 1):
+        Sig_g.append(np.trace(sets[days - t - 1][a]))
+        idx = a
+        a, b = divmod(idx, len(S_all))
+        S_g.append(S_all[b])
+    return Sig_g[::-1], S_g[::-1]

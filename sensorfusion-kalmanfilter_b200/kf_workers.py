@@ -42,6 +42,11 @@ def _engine_for(getters_obj, name):
     return eng
 
 
+def _torch_mod():
+    import torch
+    return torch
+
+
 def _slogdet_signed(P):
     s, l = np.linalg.slogdet(P)  # term 0 is a property of the INPUT matrix (kf_workers.py:32, :675)
     return s * l
@@ -170,6 +175,56 @@ class Scheduler:
 
     def randomized_greedy_schedule(self, total_num_sensors, device="cuda"):
         return None
+
+    def BF_schedule(self, z, days, device="cuda", *, P=None, H=None, total_gauges=None, selected_gauges=None):
+        """The exhaustive multi-day schedule tree sketched in sensor_scheduling_algorithm.ipynb:213-291
+        (a17): every day one of the C(G, k) sensor subsets is used for a covariance-only measurement
+        update (`cov_matrix`, no dynamics between days), day t's noise is R_t = diag(0.01 z_t^2) (:233-234),
+        all |S_all|^t posteriors of a level are kept, the leaf with the smallest trace wins (:249-253,
+        strict '<': first minimum) and its path is back-tracked through the parents (:265-272).
+
+        The sketch is not runnable (it reads undefined globals `total_gauges`, `selected_gauges` and
+        attributes `self.P`, `self.H`, `self.S`, `self.A0_day`, `self.Q0`): P, H, G and k are arguments
+        here, `z` [days, G] is taken as already de-trended (:232), and sensors are numbered 1..G as
+        `cov_matrix` expects (:118; the sketch's range(total_gauges) would wrap sensor 0 to the last row).
+        Each level is |S_all| launches of the batched kernel b200kf_cov_update over all nodes of the
+        previous level.  Returns (Sigma_g_list, S_g_list, total_time_list) as the sketch does: the trace
+        after each day along the best path, the subsets chosen, cumulative seconds per day."""
+        import time
+        from itertools import combinations as _comb
+        torch = _torch_mod()
+        P = np.asarray(self.P if P is None else P, dtype=np.float64)
+        H = np.asarray(self.H if H is None else H, dtype=np.float64)
+        G = H.shape[0] if total_gauges is None else total_gauges
+        k = selected_gauges
+        S_all = list(_comb(range(1, G + 1), k))
+        nS = len(S_all)
+        z = np.asarray(z, dtype=np.float64)
+        sigma = torch.as_tensor(P[None]).cuda()
+        level_traces, total_time_list, total_time = [], [], 0.0
+        for t in range(1, days + 1):
+            t0 = time.perf_counter()
+            R = np.diag(0.01 * z[t - 1] ** 2)
+            posts, traces = [], []
+            for S_cur in S_all:
+                rows = np.array(S_cur, dtype=np.int32) - 1
+                post, tr = cov_update(sigma, rows, H, R)
+                posts.append(post)
+                traces.append(tr)
+            # node j of the previous level expanded by subset i gets index j * |S_all| + i (:246-247)
+            sigma = torch.stack(posts, dim=1).reshape(-1, P.shape[0], P.shape[0])
+            level_traces.append(torch.stack(traces, dim=1).reshape(-1).cpu().numpy())
+            total_time += time.perf_counter() - t0
+            total_time_list.append(total_time)
+        best_idx = int(np.argmin(level_traces[-1]))  # first minimum, as the strict '<' of :249
+        S_g_list = [S_all[best_idx % nS]]
+        Sigma_g_list = [float(level_traces[-1][best_idx])]
+        a = best_idx // nS
+        for t in range(days - 1):  # walk up: the parent's trace, then the subset that produced the parent
+            Sigma_g_list.append(float(level_traces[days - t - 2][a]))
+            S_g_list.append(S_all[a % nS])
+            a //= nS
+        return Sigma_g_list[::-1], S_g_list[::-1], total_time_list
 
 
 # ------------------------------------------------------------------------------------------

@@ -169,3 +169,22 @@ def test_prefix_sharing_kernel_is_bit_identical_to_flat_kernel(name, mode, monke
         tr = ko.schedule_trace(m, types, times, s, P0, t_prev, t_end)
         assert abs(per[s][1] - np.sum(tr)) <= 1e-9 * max(1, abs(np.sum(tr)))
         assert abs(per[s][2] - tr[-1]) <= 1e-9 * max(1, abs(tr[-1]))
+
+
+def test_bf_schedule_tree_matches_restatement():
+    """a17: the exhaustive multi-day schedule tree of sensor_scheduling_algorithm.ipynb:213-291 with the
+    sizes of its first cell (n = 2 states, G = 5 sensors, K = 3 per day, horizon 3) and a larger case.
+    The sketch itself is not runnable, so parity is against the oracle's loop-for-loop restatement."""
+    from sensorfusion_kalmanfilter_b200.kf_workers import Scheduler
+    rng = np.random.default_rng(11)
+    for n, G, k, days in ((2, 5, 3, 3), (6, 6, 2, 3), (15, 4, 1, 4)):
+        H = rng.random((G, n))
+        A = rng.normal(size=(n, n))
+        P = A @ A.T + np.eye(n)
+        z = 1.0 + rng.random((days, G)) * 10.0
+        want_sig, want_S = ko.bf_schedule(P, H, z, days, k)
+        got_sig, got_S, times = Scheduler().BF_schedule(z, days, P=P, H=H, total_gauges=G, selected_gauges=k)
+        assert [tuple(s) for s in got_S] == [tuple(s) for s in want_S]  # the same path, bit-exact
+        assert len(times) == days and all(b >= a for a, b in zip(times, times[1:]))
+        for a, b in zip(got_sig, want_sig):
+            assert abs(a - b) <= 1e-9 * max(1.0, abs(b))
