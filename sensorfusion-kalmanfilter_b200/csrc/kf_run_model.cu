@@ -239,13 +239,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity), "r"(0x100000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
-#ifndef B200KF_L2PF
-#define B200KF_L2PF 0
-#endif
-constexpr int kL2Prefetch = B200KF_L2PF;  // chunks of look-ahead for the L2 prefetch of payload rows (0 = off)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -278,6 +271,34 @@ static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, c
   r.type = ty;
   r.pad = 0;
   out[k] = r;
+}
+
+// The copy lane of every ring kernel: keeps the payload ring full, gated only by the ring's empty
+// barriers.  Stage s holds CH steps x D rows of F reals; the rows of one (step, column) are contiguous in
+// the time-major payload, so each is one cp.async.bulk completing on the stage's full barrier.  With
+// `sched` the chunk's packed step records travel with it.  (An L2 prefetch of later rows with
+// cp.async.bulk.prefetch.L2 was measured 8-25 % slower for the deep d = 3 ring and neutral for the
+// shallow d = 9 one, and is not issued.)
+template <typename real, int D, int F, int ST, int CH>
+__device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long long* full, unsigned long long* empty,
+                                               const real* pay, long long N, int T, unsigned row_bytes,
+                                               SchedRec* sched_buf = nullptr, const SchedRec* sched = nullptr) {
+  constexpr size_t kStageReals = static_cast<size_t>(CH) * D * F;
+  const int nchunks = (T + CH - 1) / CH;
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int s = chunk % ST;
+    if (chunk >= ST) mbar_wait(&empty[s], static_cast<unsigned>(chunk / ST - 1) & 1u);
+    const int k0 = chunk * CH;
+    const int steps = (T - k0) < CH ? (T - k0) : CH;
+    const unsigned rec_bytes = (sched != nullptr) ? static_cast<unsigned>(steps * sizeof(SchedRec)) : 0u;
+    mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * D * row_bytes + rec_bytes);
+    if (sched != nullptr) bulk_g2s(sched_buf + s * CH, sched + k0, rec_bytes, &full[s]);
+    real* dst = stage_buf + s * kStageReals;
+    for (int c = 0; c < steps; ++c)
+#pragma unroll
+      for (int j = 0; j < D; ++j)
+        bulk_g2s(dst + (c * D + j) * F, pay + (static_cast<long long>(k0 + c) * D + j) * N, row_bytes, &full[s]);
+  }
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL, int F>
@@ -321,32 +342,9 @@ __global__ void __launch_bounds__(F + 32, 1)
 
   if (tid >= kTmaThreads) {
     // ---- producer warp: one lane keeps the ring full, decoupled from the math warps' progress ----
-    if (tid == kTmaThreads) {
-      const unsigned row_bytes = static_cast<unsigned>(nfb * sizeof(real));
-      const real* pay = static_cast<const real*>(p.payload) + base;
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int s = chunk % kStages;
-        if (chunk >= kStages) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kStages - 1) & 1u);
-        const int k0 = chunk * kChunk;
-        const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
-        mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * (D * row_bytes + sizeof(SchedRec)));
-        bulk_g2s(sched_buf + s * kChunk, sched + k0, static_cast<unsigned>(steps * sizeof(SchedRec)), &full[s]);
-        real* dst = stage_buf + s * kStageReals;
-        for (int c = 0; c < steps; ++c)
-#pragma unroll
-          for (int j = 0; j < D; ++j)
-            bulk_g2s(dst + (c * D + j) * kTmaThreads, pay + (static_cast<long long>(k0 + c) * D + j) * N, row_bytes,
-                     &full[s]);
-        if constexpr (kL2Prefetch > 0) {  // pull the rows of a later chunk into L2 ahead of the ring
-          const int kp = (chunk + kL2Prefetch) * kChunk;
-          for (int c = 0; c < kChunk; ++c)
-            if (kp + c < T)
-#pragma unroll
-              for (int j = 0; j < D; ++j)
-                bulk_prefetch_l2(pay + (static_cast<long long>(kp + c) * D + j) * N, row_bytes);
-        }
-      }
-    }
+    if (tid == kTmaThreads)
+      ring_copy_loop<real, D, F, kStages, kChunk>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
+                                                  static_cast<unsigned>(nfb * sizeof(real)), sched_buf, sched);
     return;
   }
 
@@ -532,30 +530,9 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
 
   if (tid >= kMathThreads + 32) {
     // ---------------- copy warp: one lane keeps the payload ring full ------------------------------
-    if (tid == kMathThreads + 32) {
-      const real* pay = static_cast<const real*>(p.payload) + base;
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int s = chunk % kStages;
-        if (chunk >= kStages) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kStages - 1) & 1u);
-        const int k0 = chunk * kChunk;
-        const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
-        mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * D * row_bytes);
-        real* dst = stage_buf + s * kStageReals;
-        for (int cc = 0; cc < steps; ++cc)
-#pragma unroll
-          for (int j = 0; j < D; ++j)
-            bulk_g2s(dst + (cc * D + j) * kMathThreads, pay + (static_cast<long long>(k0 + cc) * D + j) * N,
-                     row_bytes, &full[s]);
-        if constexpr (kL2Prefetch > 0) {
-          const int kp = (chunk + kL2Prefetch) * kChunk;
-          for (int cc = 0; cc < kChunk; ++cc)
-            if (kp + cc < T)
-#pragma unroll
-              for (int j = 0; j < D; ++j)
-                bulk_prefetch_l2(pay + (static_cast<long long>(kp + cc) * D + j) * N, row_bytes);
-        }
-      }
-    }
+    if (tid == kMathThreads + 32)
+      ring_copy_loop<real, D, F, kStages, kChunk>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
+                                                  row_bytes);
   } else if (tid >= kMathThreads) {
     // ---------------- gain warp: the one covariance recursion of the launch ------------------------
     if (tid == kMathThreads) {
@@ -782,11 +759,6 @@ struct SharedRing {  // ring depth per model: stages * chunk * d rows of 896 rea
   static constexpr int stages = (d >= 8) ? 3 : (d >= 4 ? 3 : 4);
 };
 
-#ifndef B200KF_L2PF_G
-#define B200KF_L2PF_G 0
-#endif
-constexpr int kL2PrefetchG = B200KF_L2PF_G;  // chunks of L2 look-ahead beyond the chunk being issued (generic shared kernel)
-
 // the blocks (tags) of a filter type, for "one gain warp per block"
 template <class Flt>
 struct FilterTags;
@@ -899,30 +871,9 @@ __global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL,
     }
   } else if (tid >= kCopyTid) {
     // ---------------- copy warp ----------------------------------------------------------------
-    if (tid == kCopyTid) {
-      const real* pay = static_cast<const real*>(p.payload) + base;
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int s = chunk % kSt;
-        if (chunk >= kSt) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kSt - 1) & 1u);
-        const int k0 = chunk * kCh;
-        const int steps = (T - k0) < kCh ? (T - k0) : kCh;
-        mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * D * row_bytes);
-        real* dst = stage_buf + s * kStageReals;
-        for (int cc = 0; cc < steps; ++cc)
-#pragma unroll
-          for (int j = 0; j < D; ++j)
-            bulk_g2s(dst + (cc * D + j) * kMathThreads, pay + (static_cast<long long>(k0 + cc) * D + j) * N,
-                     row_bytes, &full[s]);
-        if constexpr (kL2PrefetchG > 0) {  // a shallow ring (d = 9: 3 steps) sees the DRAM latency: pull later rows into L2
-          const int kp = (chunk + kL2PrefetchG) * kCh;
-          for (int cc = 0; cc < kCh; ++cc)
-            if (kp + cc < T)
-#pragma unroll
-              for (int j = 0; j < D; ++j)
-                bulk_prefetch_l2(pay + (static_cast<long long>(kp + cc) * D + j) * N, row_bytes);
-        }
-      }
-    }
+    if (tid == kCopyTid)
+      ring_copy_loop<real, D, F, kSt, kCh>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
+                                           row_bytes);
   } else if (tid >= kGainBase) {
     // ---------------- gain warps: block k's covariance recursion on one lane of warp k --------------
     const int gw = (tid - kGainBase) >> 5;
