@@ -73,3 +73,51 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_struct_layout_best_product():
+    assert ctypes.sizeof(_lib.BestProduct) == 32
+
+
+def test_header_is_plain_c_and_links_without_python(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit (no C++, no torch, no Python) includes
+    include/b200kf.h, links libb200kf.so and calls it -- what a cgo / JNI / N-API binding would do."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "b200kf.h"
+int main(void) {
+  int major = -1, minor = -1, count = -1;
+  b200kf_model_desc d;
+  b200kf_best best;
+  b200kf_best_product bp;
+  char err[256];
+  if (b200kf_version(&major, &minor) != B200KF_OK) return 2;
+  if (b200kf_model_default_desc(B200KF_MODEL_CA15, B200KF_F64, &d) != B200KF_OK) return 3;
+  if (b200kf_model_default_desc(99, B200KF_F64, &d) != B200KF_ERR_UNSUPPORTED) return 4;
+  b200kf_last_error(err, sizeof err);
+  if (strstr(err, "unknown model") == NULL) return 5;
+  b200kf_device_count(&count);
+  printf("%d.%d devices=%d q0=%g r_gps0=%g sizeof(best)=%zu sizeof(best_product)=%zu\n", major, minor, count,
+         d.q[0], d.r_gps[0], sizeof best, sizeof bp);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    pkg = os.path.join(ROOT, "sensorfusion-kalmanfilter_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", pkg, "-lb200kf", "-Wl,-rpath," + pkg]
+    cuda_lib = "/usr/local/cuda/lib64"
+    if os.path.isdir(cuda_lib):
+        cmd += ["-Wl,-rpath-link," + cuda_lib]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, LD_LIBRARY_PATH=cuda_lib + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith("0.1 devices=") and "q0=5 r_gps0=3 sizeof(best)=48 sizeof(best_product)=32" in r.stdout
