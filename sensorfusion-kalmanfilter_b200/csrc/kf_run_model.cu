@@ -1247,14 +1247,20 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
     B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DENSE, real>(m, p, full, st)));
     return B200KF_OK;
   }
+  // the lean symmetric step and the shared-covariance kernels divide by the measurement variances (R-normalised
+  // covariance, K = P+ H^T R^-1): a model with a zero variance (a perfect sensor) stays on the LDG kernels,
+  // whose scalar updates only ever divide by P_ss + r
+  bool r_pos = true;
+  for (int i = 0; i < m->n; ++i) r_pos = r_pos && (m->mc.r_imu[i] > 0.0 || ModelTraits<MODEL, false, real>::imu_control);
+  for (int i = 0; i < m->m_gps; ++i) r_pos = r_pos && m->mc.r_gps[i] > 0.0;
   const bool tma = tma_possible<MODEL, real>(m, p, full);
   const bool sym = sym_possible<MODEL, real>(m);
-  const bool tma_sym = tma && tma_sym_eligible<MODEL, real>();
+  const bool tma_sym = tma && tma_sym_eligible<MODEL, real>() && r_pos;
   // the shared-covariance kernels stream the payload with bulk copies: 16-byte aligned rows
   const long long align_elems = 16 / static_cast<long long>(sizeof(real));
   const bool ring_ok = p.n_steps >= 1 && p.ptraj == nullptr && m->use_tma != 0 && (p.n_filters % align_elems) == 0 &&
                        (reinterpret_cast<uintptr_t>(p.payload) & 15u) == 0;
-  const bool shared = ring_ok && sym && shared_eligible<MODEL, real>() && m->use_shared != 0 && !p.gate_enabled &&
+  const bool shared = ring_ok && r_pos && sym && shared_eligible<MODEL, real>() && m->use_shared != 0 && !p.gate_enabled &&
                       (!shared_lean<MODEL, real>() || tma_sym);
   if ((flags & B200KF_RUN_FORCE_SHARED) && shared) {
     p.dense_flag = nullptr;

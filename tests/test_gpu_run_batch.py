@@ -325,3 +325,31 @@ def test_ring_kernels_at_every_cta_size(N, monkeypatch):
             assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
             a = out["agg"].cpu().numpy()
             assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
+
+
+def test_zero_measurement_variance_stays_exact():
+    """A perfect sensor (r = 0 on the IMU velocity pseudo-measurement): the lean symmetric step and the
+    shared-covariance kernels divide by the variances, so such a model must take the scalar-update
+    kernels (which only divide by P_ss + r) -- and still match the reference formulation (inv(S))."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    from sensorfusion_kalmanfilter_b200.models import ModelSpec, default_spec
+    base = default_spec("CV6")
+    r_imu = base.r_imu.copy()
+    r_imu[3:] = 0.0
+    spec = ModelSpec("CV6", "f64", base.q, base.r_gps, r_imu, base.accel_coef)
+
+    class CV6PerfectVelocity(type(ko.get_model("CV6"))):
+        def R_imu(self):
+            return np.diag(r_imu)
+
+    m = CV6PerfectVelocity()
+    N, T = 2000, 60
+    _, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=61)
+    ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
+    for P in (P0, P0 * (1.0 + np.arange(N) / N)[:, None, None]):  # identical and per-filter covariances
+        refp = ref if P is P0 else ko.run_batch(m, types, dts, payload, x0, P, want_traj=False)
+        out = Engine(spec).run_batch(types, dts, payload, x0, P)
+        assert np.isfinite(out["P"].cpu().numpy()).all()
+        assert rel(out["x"].cpu().numpy(), refp["x"]) < RTOL64
+        # P has exact-zero velocity variance after an IMU event: compare absolutely on the scale of P0
+        assert np.max(np.abs(out["P"].cpu().numpy() - refp["P"])) < 1e-9 * np.max(np.abs(refp["P"]) + 1.0)
