@@ -224,6 +224,7 @@ struct Union {
 template <class B, typename real>
 struct BlockKF {
   static constexpr int n = B::n;
+  static constexpr int M = 1;  // chains that share this covariance (SymBlock: the members of the group)
   static constexpr int NP = n * (n + 1) / 2;
   using Traits = B;
   real x[n];

@@ -383,9 +383,10 @@ int launch_masked_m<B200KF_INST_MODEL>(const b200kf_model* m, const MaskedParams
 // gains, trace(P) - sum_i P[i][0]^2 / (P[0][0] + r_type), and greedy_schedule keeps the FIRST
 // queue entry that attains the maximum (strict '>' at :205).  The thread walks the event list
 // once, emitting the selected event index per window and advancing P through predict + update.
-template <int MODEL, bool DENSE>
+template <int MODEL, int VAR>
 __global__ void select_greedy_kernel(const SelectParams p) {
-  using MT = ModelTraits<MODEL, DENSE, double>;
+  using MT = VariantTraits<MODEL, VAR, double>;
+  constexpr bool DENSE = (VAR == VAR_DENSE);
   constexpr int n = MT::n;
   const int inst = blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= p.n_inst) return;
@@ -413,12 +414,13 @@ __global__ void select_greedy_kernel(const SelectParams p) {
     double tr = 0.0, col2 = 0.0, p00 = 0.0;
     flt.each([&](const auto& b) {
       using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+      using TB = typename BT::Traits;  // the chain tables (a symmetric group's first member)
       static_for<0, BT::n>([&](auto I) {
         constexpr int i = I;
-        tr += b.P[BT::pidx(i, i)];
+        tr += static_cast<double>(BT::M) * b.P[BT::pidx(i, i)];  // every member of a group carries this block
         static_for<0, BT::n>([&](auto J) {
           constexpr int j = J;
-          if constexpr (BT::gidx(j) == 0) {
+          if constexpr (TB::gidx(j) == 0) {  // column of global state 0: only the chain that owns it
             col2 += b.P[BT::pidx(i, j)] * b.P[BT::pidx(i, j)];
             if constexpr (i == j) p00 = b.P[BT::pidx(i, i)];
           }
@@ -462,13 +464,18 @@ __global__ void select_greedy_kernel(const SelectParams p) {
 template <>
 int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams& p, unsigned flags,
                                        cudaStream_t st) {
-  (void)m;
+  using SymF = typename SymTraits<B200KF_INST_MODEL, double>::Filter;
   const int tpb = 32;
   const unsigned blocks = static_cast<unsigned>((p.n_inst + tpb - 1) / tpb);
-  if (flags & B200KF_RUN_FORCE_DECOUPLED)
-    select_greedy_kernel<B200KF_INST_MODEL, false><<<blocks, tpb, 0, st>>>(p);
-  else  // P0 lives on the device: the dense form is always valid
-    select_greedy_kernel<B200KF_INST_MODEL, true><<<blocks, tpb, 0, st>>>(p);
+  // P0 lives on the device, so the caller vouches for its structure: FORCE_SYMMETRIC = chain-compatible with
+  // identical blocks across the axes of a group (one covariance per group), FORCE_DECOUPLED = chain-compatible;
+  // without a flag the dense form, which is always valid
+  if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && m->use_sym && SymF::constants_equal(m->mc))
+    select_greedy_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<blocks, tpb, 0, st>>>(p);
+  else if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC))
+    select_greedy_kernel<B200KF_INST_MODEL, VAR_DECOUPLED><<<blocks, tpb, 0, st>>>(p);
+  else
+    select_greedy_kernel<B200KF_INST_MODEL, VAR_DENSE><<<blocks, tpb, 0, st>>>(p);
   B200KF_CUDA_TRY(cudaGetLastError());
   return B200KF_OK;
 }

@@ -313,8 +313,11 @@ class Engine:
         if mode == "auto" and not isinstance(P0, torch.Tensor):
             # P0 still on the host: a chain-compatible covariance takes the per-chain form of the kernel
             # (an order of magnitude faster than the dense 15 x 15 one for the reference's P0, :851)
-            from .models import chain_compatible
-            if chain_compatible(sp.name, np.asarray(P0, dtype=np.float64).reshape(I, sp.n, sp.n)):
+            from .models import axis_symmetric, chain_compatible
+            P0h = np.asarray(P0, dtype=np.float64).reshape(I, sp.n, sp.n)
+            if axis_symmetric(sp.name, P0h):
+                mode = "symmetric"  # one covariance per group of axes (falls back to per-chain if the rates differ)
+            elif chain_compatible(sp.name, P0h):
                 mode = "decoupled"
         P0_d = self._dev(np.asarray(P0, dtype=np.float64).reshape(I, sp.n, sp.n), torch.float64)
         if max_sel is None:

@@ -192,3 +192,22 @@ def chain_compatible(name: str, P: np.ndarray) -> bool:
             for j in ch:
                 mask[i, j] = False
     return not np.any(np.asarray(P)[..., mask] != 0)
+
+
+def axis_symmetric(name: str, P: np.ndarray) -> bool:
+    """True when P [..., n, n] is chain-compatible AND the chains that are the same model on different
+    axes (the chains of equal length: x/y/z position chains, roll/pitch/yaw chains) carry bit-identical
+    blocks -- the symmetric kernels' validity condition for the covariance (kf_core.cuh SymBlock)."""
+    if not chain_compatible(name, P):
+        return False
+    P = np.asarray(P)
+    groups = {}
+    for ch in CHAINS[name]:
+        groups.setdefault(len(ch), []).append(ch)
+    for chains in groups.values():
+        ref = P[..., np.ix_(chains[0], chains[0])[0], np.ix_(chains[0], chains[0])[1]]
+        for ch in chains[1:]:
+            blk = P[..., np.ix_(ch, ch)[0], np.ix_(ch, ch)[1]]
+            if np.any(blk != ref):
+                return False
+    return True

@@ -124,3 +124,16 @@ def test_shard_range_and_merge():
     assert m["argmin_sum_index"] == 4 and m["first_feasible_index"] == 77 and m["n_feasible"] == 7
     assert m["n_near_threshold"] == 1
     assert merge_best([c, b, a]) == m
+
+
+def test_axis_symmetric():
+    from sensorfusion_kalmanfilter_b200.models import axis_symmetric, default_spec
+    for name in ("CV6", "CA8", "BIAS9", "CA15"):
+        P = default_spec(name).default_P0()
+        assert axis_symmetric(name, P) and axis_symmetric(name, np.stack([P, 2 * P]))
+        Q = P.copy()
+        Q[1, 1] *= 1.0000001  # y differs from x: per-chain covariances needed
+        assert not axis_symmetric(name, Q)
+        Q = P.copy()
+        Q[0, 1] = Q[1, 0] = 0.5  # couples two chains: not even chain-compatible
+        assert not axis_symmetric(name, Q)
