@@ -77,3 +77,35 @@ def test_trajectory_outputs_consistent_with_aggregates(setup):
     assert (ld.sum(dim=0) - agg[:, 1]).abs().max().item() < 1e-9 * max(1.0, agg[:, 1].abs().max().item())
     assert (ld[-1] - agg[:, 2]).abs().max().item() < 1e-9 * 100
     assert bool((o["traj"][-1].T == o["x"]).all())
+
+
+def test_per_filter_covariance_path_at_full_width(setup):
+    """The headline configuration: every filter with its own covariance (the lean axis-symmetric kernel,
+    one recursion per filter).  Filters that share a P0 must agree bit for bit, a sample of filters is
+    replayed through the oracle, and time-chunked launches agree with one launch to rounding."""
+    import torch
+    eng, types, dts, pay1, pay2, x0, P0 = setup
+    scale = 1.0 + (torch.arange(N, device=P0.device) % 1024).to(torch.float64) / 1024.0
+    P1 = P0 * scale[:, None, None]
+    one = eng.run_batch(types, dts, pay1, x0, P1)
+    assert int(one["status"].sum()) == 0
+    P, agg = one["P"], one["agg"]
+    assert bool((P[:N - 1024] == P[1024:]).all()) and bool((agg[:N - 1024] == agg[1024:]).all())
+    # (after 600 steps the covariances have converged to the same steady state; the aggregates remember the start)
+    assert not bool((agg[0, :2] == agg[1, :2]).all())
+    m = ko.get_model("CV6")
+    pick = [0, 517, 1023, 70001, N - 1]
+    ref = ko.run_batch(m, types, dts, pay1[:, :, pick].cpu().numpy(), np.zeros((len(pick), 6)),
+                       P1[pick].cpu().numpy(), want_traj=False)
+    got_P, got_x, got_a = P[pick].cpu().numpy(), one["x"][pick].cpu().numpy(), agg[pick, :3].cpu().numpy()
+    assert np.max(np.abs(got_P - ref["P"])) <= 1e-9 * np.max(np.abs(ref["P"]))
+    assert np.max(np.abs(got_x - ref["x"])) <= 1e-9 * max(1.0, np.max(np.abs(ref["x"])))
+    assert np.max(np.abs(got_a - ref["agg"]) / np.maximum(1, np.abs(ref["agg"]))) < 1e-9
+    x, Pc, ag = x0, P1, None
+    for k0 in range(0, T, 250):
+        sl = slice(k0, min(T, k0 + 250))
+        o = eng.run_batch(types[sl], dts[sl], pay1[sl], x, Pc, agg=ag)
+        x, Pc, ag = o["x"], o["P"], o["agg"]
+    assert (x - one["x"]).abs().max().item() <= 1e-12 * max(1.0, one["x"].abs().max().item())
+    assert (Pc - P).abs().max().item() <= 1e-12 * P.abs().max().item()
+    assert (ag[:, :3] - agg[:, :3]).abs().max().item() < 1e-9 * max(1.0, agg[:, :3].abs().max().item())
