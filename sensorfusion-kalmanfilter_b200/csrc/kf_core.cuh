@@ -1413,7 +1413,7 @@ struct Sym2Filter {
     b = real(double(b) * sqrt(r0 * r1));
     c = real(double(c) * r1);
   }
-  __device__ __forceinline__ void step_lean(const LeanRec& r, const real* u, real& v) {
+  __device__ __forceinline__ void step_lean(const LeanRec& r, const ModelConst&, const real* u, real& v) {
     const real dt = real(r.dt), kap = real(r.kap);
     const real bn = fma(kap, c, b);
     const real ap = fma(kap, b + bn, a + real(r.phi0));
@@ -1510,6 +1510,172 @@ struct Sym2Filter {
 };
 
 // --------------------------------------------------------------------------------------
+// Sym3CtrlFilter: the lean form of a filter made of M identical (value, rate, bias) chains whose IMU
+// event is a control input (BIAS9: x = F x + B u, no update) and whose GPS
+// event measures the value.  One 3 x 3 covariance per filter (axis-symmetric P, checked per launch
+// like Sym2Filter), the M axis states in registers.  With F = [[1, dt, -e], [0, 1, -dt], [0, 0, 1]],
+// e = c2 dt^2, the predict is written out entry by entry (12 FMA + 3 for Q); the IMU step costs
+// 15 (covariance) + 10 (det) + 5 per axis.
+// --------------------------------------------------------------------------------------
+template <class B>
+constexpr bool is_vrb3() {  // [value, rate, bias]: value += dt rate - c2 dt^2 bias, rate -= dt bias; control on value and rate
+  if (is_group_tag<B>::value) return false;
+  if (B::n != 3) return false;
+  return B::l1(0) == 1 && B::l2(0) == 2 && B::s1(0) == 1 && B::s2(0) == -1 && B::l1(1) == 2 && B::l2(1) < 0 &&
+         B::s1(1) == -1 && B::l1(2) < 0 && B::l2(2) < 0 && B::cu(0) == 1 && B::cu(1) == 2 && B::cu(2) == 0 &&
+         B::gps(0) >= 0 && B::gps(1) < 0 && B::gps(2) < 0 && B::zk(0) == ZK_NONE;
+}
+
+template <typename real, class B0, class... Bs>
+struct Sym3CtrlFilter {
+  static constexpr int M = 1 + sizeof...(Bs);
+  static constexpr bool eligible = (is_vrb3<B0>() && ... && is_vrb3<Bs>());
+  static constexpr bool lean_ok = eligible;
+  using Lead = B0;
+  real p00, p01, p02, p11, p12, p22;  // the shared chain covariance (upper triangle)
+  real x0[M], x1[M], x2[M];
+  real r0r1;  // unused scale of the lean aggregate (v is the chain determinant itself)
+
+  struct LeanRec {  // same 64 bytes as the step record of the launch; only (dt, dt^2, type) are read
+    double dt, dt2;
+    double unused[5];
+    int type;
+    int pad;
+  };
+  template <class F>
+  __device__ __forceinline__ static void members(F&& fn) {
+    int m = 0;
+    fn(B0{}, m++);
+    (fn(Bs{}, m++), ...);
+  }
+  __device__ __forceinline__ void load(const real* xg, const real* Pg, int n, const ModelConst&) {
+    auto sym = [&](int i, int j) {
+      return real(0.5) * (Pg[B0::gidx(i) * n + B0::gidx(j)] + Pg[B0::gidx(j) * n + B0::gidx(i)]);
+    };
+    p00 = sym(0, 0), p01 = sym(0, 1), p02 = sym(0, 2), p11 = sym(1, 1), p12 = sym(1, 2), p22 = sym(2, 2);
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      x0[m] = xg[BM::gidx(0)];
+      x1[m] = xg[BM::gidx(1)];
+      x2[m] = xg[BM::gidx(2)];
+    });
+    r0r1 = real(1);
+  }
+  __device__ __forceinline__ void store(real* xg, real* Pg, int n) const {
+    const real P[3][3] = {{p00, p01, p02}, {p01, p11, p12}, {p02, p12, p22}};
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      xg[BM::gidx(0)] = x0[m];
+      xg[BM::gidx(1)] = x1[m];
+      xg[BM::gidx(2)] = x2[m];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Pg[BM::gidx(i) * n + BM::gidx(j)] = P[i][j];
+    });
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_state(F&& fn) const {
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      fn(std::integral_constant<int, BM::gidx(0)>{}, x0[m]);
+      fn(std::integral_constant<int, BM::gidx(1)>{}, x1[m]);
+      fn(std::integral_constant<int, BM::gidx(2)>{}, x2[m]);
+    });
+  }
+  __device__ __forceinline__ void to_normalized(const ModelConst&) {}
+  __device__ __forceinline__ void from_normalized(const ModelConst&) {}
+  __device__ __forceinline__ real chain_det() const {
+    return p00 * fma(p11, p22, -(p12 * p12)) - p01 * fma(p01, p22, -(p02 * p12)) + p02 * fma(p01, p12, -(p02 * p11));
+  }
+  __device__ __forceinline__ double det(bool& ok) const {
+    const real d = chain_det();
+    ok = ok && (d > real(0));
+    double r = double(d);
+#pragma unroll
+    for (int i = 1; i < M; ++i) r *= double(d);
+    return r;
+  }
+  // P = F P F^T + Q, entry by entry
+  __device__ __forceinline__ void predict_cov(real dt, real e, const ModelConst& mc) {
+    const real a00 = fma(-e, p02, fma(dt, p01, p00));
+    const real a01 = fma(-e, p12, fma(dt, p11, p01));
+    const real a02 = fma(-e, p22, fma(dt, p12, p02));
+    const real a11 = fma(-dt, p12, p11);
+    const real a12 = fma(-dt, p22, p12);
+    p00 = fma(real(mc.q[B0::gidx(0)]), dt, fma(-e, a02, fma(dt, a01, a00)));
+    p01 = fma(-dt, a02, a01);
+    p02 = a02;
+    p11 = fma(real(mc.q[B0::gidx(1)]), dt, fma(-dt, a12, a11));
+    p12 = a12;
+    p22 = fma(real(mc.q[B0::gidx(2)]), dt, p22);
+  }
+  __device__ __forceinline__ void predict_state(real dt, real e) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      x0[m] = fma(-e, x2[m], fma(dt, x1[m], x0[m]));
+      x1[m] = fma(-dt, x2[m], x1[m]);
+    }
+  }
+  __device__ __forceinline__ void gps_update(const ModelConst& mc, const real* u) {
+    const real r = real(mc.r_gps[B0::gps(0)]);
+    const real inv = fast_rcp3(p00 + r);
+    const real k0 = p00 * inv, k1 = p01 * inv, k2 = p02 * inv, g = r * inv;
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      const real y = u[BM::gps(0)] - x0[m];
+      x0[m] = fma(k0, y, x0[m]);
+      x1[m] = fma(k1, y, x1[m]);
+      x2[m] = fma(k2, y, x2[m]);
+    });
+    p11 = fma(-k1, p01, p11);
+    p12 = fma(-k1, p02, p12);
+    p22 = fma(-k2, p02, p22);
+    p00 *= g;  // row 0 of (I - K H) P is row * r / (P00 + r)
+    p01 *= g;
+    p02 *= g;
+  }
+  // fused predict (+ control or GPS update); v = det of the chain covariance after the step
+  __device__ __forceinline__ void step_lean(const LeanRec& rec, const ModelConst& mc, const real* u, real& v) {
+    const real dt = real(rec.dt);
+    const real e = real(mc.c2) * real(rec.dt2);
+    predict_cov(dt, e, mc);
+    if (rec.type == EV_IMU) {  // x = F x + B u: the control enters value and rate
+      members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        const real acc = u[BM::pz(0)];
+        x0[m] = fma(e, acc - x2[m], fma(dt, x1[m], x0[m]));
+        x1[m] = fma(dt, acc - x2[m], x1[m]);
+      });
+    } else {
+      predict_state(dt, e);
+      if (rec.type == EV_GPS) gps_update(mc, u);
+    }
+    v = chain_det();
+  }
+  // the non-lean interface of the ring kernel (per-step outputs); the host dispatch keeps control-input
+  // models with per-step outputs or the adaptive gate on the LDG kernel, so this only has to be correct
+  __device__ __forceinline__ void predict(real dt, const ModelConst& mc) {
+    const real e = real(mc.c2) * (dt * dt);
+    predict_cov(dt, e, mc);
+    predict_state(dt, e);
+  }
+  __device__ __forceinline__ double update(real dt, const ModelConst& mc, int ty, const real* u, bool& ok) {
+    if (ty == EV_IMU) {
+      const real e = real(mc.c2) * (dt * dt);
+      members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        x0[m] = fma(e, u[BM::pz(0)], x0[m]);
+        x1[m] = fma(dt, u[BM::pz(0)], x1[m]);
+      });
+    } else if (ty == EV_GPS) {
+      gps_update(mc, u);
+    }
+    return det(ok);
+  }
+};
+
+// --------------------------------------------------------------------------------------
 // Model registry: decoupled chain list and dense union per model id
 // --------------------------------------------------------------------------------------
 template <int MODEL_ID, bool DENSE, typename real>
@@ -1533,6 +1699,7 @@ struct ChainIndex {
     using Filter = FilterT<real, CTRL, __VA_ARGS__>;                           \
     using Dec2 = Dec2Filter<real, __VA_ARGS__>;                                \
     using Sym2 = Sym2Filter<real, __VA_ARGS__>;                                \
+    using Sym3 = Sym3CtrlFilter<real, __VA_ARGS__>;                            \
     static constexpr int chain_of(int g) { return ChainIndex<__VA_ARGS__>::of(g); } \
   };                                                                           \
   template <typename real>                                                     \

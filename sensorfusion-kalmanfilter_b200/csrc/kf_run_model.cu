@@ -273,6 +273,15 @@ static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, c
   out[k] = r;
 }
 
+// filter object of the per-filter-covariance ring kernel: per-chain / axis-symmetric closed form for the
+// (value, rate) models (CV6), the lean 3-state control-chain form for BIAS9 (symmetric only)
+template <int MODEL, typename real, bool SYM>
+struct TmaFlt {
+  using MT = ModelTraits<MODEL, false, real>;
+  using type = std::conditional_t<!SYM, typename MT::Dec2,
+                                  std::conditional_t<MT::Filter::fast2, typename MT::Sym2, typename MT::Sym3>>;
+};
+
 // The copy lane of every ring kernel: keeps the payload ring full, gated only by the ring's empty
 // barriers.  Stage s holds CH steps x D rows of F reals; the rows of one (step, column) are contiguous in
 // the time-major payload, so each is one cp.async.bulk completing on the stage's full barrier.  With
@@ -309,10 +318,10 @@ __global__ void __launch_bounds__(F + 32, 1)
   constexpr int kTmaThreads = F;
   constexpr int kStages = b200kf::kStages * (896 / F);
   using MT = ModelTraits<MODEL, false, real>;
-  using Flt = std::conditional_t<SYM, typename MT::Sym2, typename MT::Dec2>;
+  using Flt = typename TmaFlt<MODEL, real, SYM>::type;
   constexpr int n = MT::n;
   constexpr int D = MT::d;
-  static_assert(MT::Filter::fast2, "TMA kernel is for the closed-form filters");
+  static_assert(MT::Filter::fast2 || (SYM && MT::Sym3::eligible), "ring kernel is for the closed-form filters");
   if (!mode_selected(p.dense_flag, SYM ? MODE_SYMMETRIC : MODE_DECOUPLED)) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(F + 32, 1)
           const int ty = rec.type;
           if constexpr (LEAN) {
             real v;
-            flt.step_lean(*reinterpret_cast<const typename Flt::LeanRec*>(&sched_buf[s * kChunk + c]), u, v);
+            flt.step_lean(*reinterpret_cast<const typename Flt::LeanRec*>(&sched_buf[s * kChunk + c]), p.mc, u, v);
             lean_sign |= __double2hiint(double(v));
             acc_max = max(acc_max, __double_as_longlong(double(v)));
             const double m = acc_mant * double(v);
@@ -1087,6 +1096,22 @@ static bool tma_possible(const b200kf_model* m, const RunParams& p, bool full) {
   }
 }
 
+// BIAS9-like models (control-input chains): the symmetric ring kernel exists for the aggregate-only launch;
+// per-step outputs, the adaptive gate and per-chain covariances stay with the LDG kernels
+template <int MODEL, typename real>
+static bool tma_sym3_possible(const b200kf_model* m, const RunParams& p, bool full) {
+  using MT = ModelTraits<MODEL, false, real>;
+  if constexpr (MT::Filter::fast2 || !MT::Sym3::eligible) {
+    return false;
+  } else {
+    if (full || p.ptraj != nullptr || m->use_tma == 0) return false;
+    const size_t need = static_cast<size_t>(p.n_steps) * sizeof(SchedRec);
+    const long long align_elems = 16 / static_cast<long long>(sizeof(real));
+    return p.n_steps >= 1 && need <= sched_capacity(m) && (p.n_filters % align_elems) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.payload) & 15u) == 0;
+  }
+}
+
 template <int MODEL, typename real>
 static bool sym_possible(const b200kf_model* m) {
   return m->use_sym != 0 && SymTraits<MODEL, real>::Filter::constants_equal(m->mc);
@@ -1119,12 +1144,14 @@ static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, int
 template <int MODEL, typename real>
 static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool with_sym, bool with_dec,
                               bool full, cudaStream_t st) {
-  if constexpr (!ModelTraits<MODEL, false, real>::Filter::fast2) {
+  using MTl = ModelTraits<MODEL, false, real>;
+  if constexpr (!MTl::Filter::fast2 && !MTl::Sym3::eligible) {
     return cudaErrorInvalidValue;
   } else {
+    constexpr bool kFast2 = MTl::Filter::fast2;
     SchedRec* sched = reinterpret_cast<SchedRec*>(sched_scratch(m));
     LeanConst lc{1.0, 1.0, 1.0, 1.0, 1.0};  // rate constants of the symmetric group (only its lean step reads them)
-    if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
+    if constexpr (kFast2 && ModelTraits<MODEL, false, real>::Sym2::eligible) {
       using G0 = typename ModelTraits<MODEL, false, real>::Sym2::Lead;
       lc.q0 = m->mc.q[G0::gidx(0)];
       lc.q1 = m->mc.q[G0::gidx(1)];
@@ -1135,12 +1162,14 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc, sched);
     cudaError_t err = cudaSuccess;
     const int f = pick_ring_f(p.n_filters, m->sm_count, m->ring_f_cap);
-    if (with_dec) {
-      err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, f, st)
-                 : launch_tma_one<MODEL, real, false, false>(p, sched, f, st);
-      if (err != cudaSuccess) return err;
+    if constexpr (kFast2) {
+      if (with_dec) {
+        err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, f, st)
+                   : launch_tma_one<MODEL, real, false, false>(p, sched, f, st);
+        if (err != cudaSuccess) return err;
+      }
     }
-    if constexpr (ModelTraits<MODEL, false, real>::Sym2::eligible) {
+    if constexpr ((kFast2 && MTl::Sym2::eligible) || (!kFast2 && MTl::Sym3::eligible)) {
       if (with_sym) {
         err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, f, st)
                    : launch_tma_one<MODEL, real, true, false>(p, sched, f, st);
@@ -1268,9 +1297,10 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
     return B200KF_OK;
   }
   if (flags & B200KF_RUN_FORCE_SHARED) flags |= B200KF_RUN_FORCE_SYMMETRIC;  // next-best guarantee
+  const bool tma3 = sym && tma_sym3_possible<MODEL, real>(m, p, full);  // BIAS9: symmetric ring kernel, aggregate mode
   if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && sym) {
     p.dense_flag = nullptr;
-    if (tma_sym) {
+    if (tma_sym || tma3) {
       B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, st)));
     } else {
       B200KF_CUDA_TRY((launch_variant<MODEL, VAR_SYMMETRIC, real>(m, p, full, st)));
@@ -1302,9 +1332,10 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   if (tma) {
     B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym && tma_sym, true, full, st)));
   } else {
+    if (tma3) B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, st)));
     B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DECOUPLED, real>(m, p, full, st)));
   }
-  if (sym && !tma_sym) B200KF_CUDA_TRY((launch_variant<MODEL, VAR_SYMMETRIC, real>(m, p, full, st)));
+  if (sym && !tma_sym && !tma3) B200KF_CUDA_TRY((launch_variant<MODEL, VAR_SYMMETRIC, real>(m, p, full, st)));
   B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DENSE, real>(m, p, full, st)));
   return B200KF_OK;
 }
