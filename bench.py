@@ -289,7 +289,7 @@ def run_gpu_arm(a):
         ms = float(t.item())
     # kernels of libb200kf launched per bench step: auto = chain_compat + pack_schedule + TMA filter kernel
     # + dense kernel (exits at once); decoupled = pack_schedule + TMA kernel; dense = 1
-    tma_on = os.environ.get("B200KF_TMA", "1") != "0" and a.model == "CV6"
+    tma_on = os.environ.get("B200KF_TMA", "1") != "0" and a.model in ("CV6", "BIAS9")  # models with a per-filter ring kernel
     sym_k = tma_on and os.environ.get("B200KF_SYM", "1") != "0"
     launches_per_step = {"auto": 3 + tma_on + sym_k, "decoupled": 1 + tma_on, "symmetric": 1 + tma_on, "dense": 1}[a.mode]
     total_steps = float(world) * N * T * a.steps
