@@ -224,6 +224,32 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore its first-touch pinned host buffers) to the NUMA node its GPU hangs off:
+    the host-buffer leg streams ~55 GB/s per GPU, which a remote socket cannot feed to 8 GPUs at once.
+    Returns the node number, or None when the topology cannot be read / the cores are not ours to use."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        mine = cpus & set(os.sched_getaffinity(0))
+        if not mine:
+            return None
+        os.sched_setaffinity(0, mine)
+        return node
+    except Exception:
+        return None
+
+
 def run_gpu_arm(a):
     import torch
     import torch.distributed as dist
@@ -234,6 +260,7 @@ def run_gpu_arm(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -407,7 +434,8 @@ def run_gpu_arm(a):
         e2e = {"value": world * N * Te / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "workload": f"{N} filters x {Te} steps per call per GPU, pinned host buffers, "
                "all ranks concurrently, max over ranks", "ms_per_call": te * 1e3,
-               "host_gbs_per_gpu": (h2d + d2h) / te / 1e9, "check_sum_logdet": float(res["agg"][:, 1].mean())}
+               "host_gbs_per_gpu": (h2d + d2h) / te / 1e9, "check_sum_logdet": float(res["agg"][:, 1].mean()),
+               "rank0_numa_node": numa_node}
         del pay_h
 
     # ---- larger horizon where several GPUs matter: 2^26 subsets sharded over the ranks, one 48-byte
