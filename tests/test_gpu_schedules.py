@@ -188,3 +188,49 @@ def test_bf_schedule_tree_matches_restatement():
         assert len(times) == days and all(b >= a for a, b in zip(times, times[1:]))
         for a, b in zip(got_sig, want_sig):
             assert abs(a - b) <= 1e-9 * max(1.0, abs(b))
+
+
+def test_config4_full_size_properties(monkeypatch):
+    """BASELINE configs[3] at its full size: all 2^20 subsets of a 20-event window (CA15).  The oracle
+    cannot replay a million schedules, so: (a) the prefix-sharing kernel and the flat kernel agree on
+    the winner, the first feasible schedule and the counts; (b) the 8 contiguous shards of an 8-GPU run
+    reduce to the same answer (distributed.merge_best is what every rank applies after the all-gather);
+    (c) the winners themselves are replayed through the oracle; (d) feasibility is monotone in the
+    threshold; (e) a schedule's sum of log-dets equals that of the same events walked by the filter loop."""
+    from sensorfusion_kalmanfilter_b200.distributed import merge_best, shard_range
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    m = ko.get_model("CA15")
+    L = 20
+    rng = np.random.default_rng(3)
+    types = np.where(np.arange(L) % 7 == 3, 0, 1).astype(np.uint8)
+    times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
+    P0 = m.P0() * 1e-8  # small enough that the covariance GROWS between measurements: the max is not term 0
+    t_prev, t_end = 999.995, float(times[-1])
+    monkeypatch.setenv("B200KF_TREE", "0")
+    flat = Engine("CA15")
+    monkeypatch.setenv("B200KF_TREE", "1")
+    tree = Engine("CA15")
+    probe, _ = tree.score_schedules(types, times, t_prev, t_end, P0, first=1, count=4096, want_per_schedule=True)
+    thr = float(np.quantile(_.cpu().numpy()[:, 0], 0.4))
+    bt, _ = tree.score_schedules(types, times, t_prev, t_end, P0, threshold=thr)
+    bf, _ = flat.score_schedules(types, times, t_prev, t_end, P0, threshold=thr)
+    assert bt == bf and bt["n_feasible"] > 0
+    parts = []
+    for r in range(8):
+        first, count = shard_range(1 << L, 8, r)
+        parts.append(tree.score_schedules(types, times, t_prev, t_end, P0, first=first, count=count, threshold=thr)[0])
+    merged = merge_best(parts)
+    for k in ("argmin_sum_index", "first_feasible_index", "n_feasible", "n_near_threshold"):
+        assert merged[k] == bt[k], k
+    for s in (bt["argmin_sum_index"], bt["first_feasible_index"]):
+        tr = ko.schedule_trace(m, types, times, s, P0, t_prev, t_end)
+        one, per = tree.score_schedules(types, times, t_prev, t_end, P0, first=s, count=1, threshold=thr,
+                                        want_per_schedule=True)
+        row = per.cpu().numpy()[0]
+        assert abs(row[1] - np.sum(tr)) <= 1e-9 * max(1.0, abs(np.sum(tr)))
+        assert abs(row[0] - np.max(tr)) <= 1e-9 * max(1.0, abs(np.max(tr)))
+    assert max(ko.schedule_trace(m, types, times, bt["first_feasible_index"], P0, t_prev, t_end)) < thr
+    lo_thr, _ = tree.score_schedules(types, times, t_prev, t_end, P0, threshold=thr - 0.5)
+    hi_thr, _ = tree.score_schedules(types, times, t_prev, t_end, P0, threshold=thr + 0.5)
+    assert lo_thr["n_feasible"] <= bt["n_feasible"] <= hi_thr["n_feasible"]
+    assert lo_thr["argmin_sum_index"] == bt["argmin_sum_index"]  # the threshold does not enter the argmin
