@@ -490,6 +490,32 @@ def run_gpu_arm(a):
                       "workload": "CA15, 2^20 subset schedules of a 20-event window, 1 GPU", "ms": sms,
                       "argmin_sum_index": best["argmin_sum_index"]}
 
+        # ---- the notebook's product-of-queues brute force (RMSE objective): sequences scored / s
+        products = None
+        if not a.no_search:
+            e15p = Engine("CA15")
+            Wp, qp = 10, 4
+            rngp = np.random.default_rng(0)
+            Ep = Wp * qp
+            tmp = 1000.0 + np.sort(rngp.uniform(0, 0.02 * Wp, Ep))
+            typ = (rngp.random(Ep) < 0.9).astype(np.uint8)
+            payp, refp = rngp.normal(0, 0.1, (Ep, 9)), rngp.normal(0, 1.0, (Ep, 3))
+            P0p = np.diag([1000.0] * 3 + [100.0] * 9 + [1000.0] * 3)
+            for _ in range(2):
+                bp, _ = e15p.score_products([qp] * Wp, typ, tmp, payp, refp, np.zeros(15), P0p)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(5):
+                bp, _ = e15p.score_products([qp] * Wp, typ, tmp, payp, refp, np.zeros(15), P0p)
+            p1.record()
+            torch.cuda.synchronize()
+            pms = p0.elapsed_time(p1) / 5
+            products = {"metric": "sequences_scored_per_sec", "value": qp ** Wp / (pms * 1e-3), "unit": "sequences/s",
+                        "workload": f"CA15, {Wp} windows x {qp} candidates = {qp ** Wp} sequences, RMSE objective "
+                                    "(KF_SensorFusion.ipynb:804-954), incl. host<->device hand-off of the call", "ms": pms,
+                        "best_index": bp["index"]}
+
         cpu = None
         if not a.no_cpu_baseline:
             cores = host_cores()
@@ -515,7 +541,7 @@ def run_gpu_arm(a):
                 "config": {"workload": workload_name(a), "mode": a.mode, "p0": "per-filter (reference P0 x (1 + (f % 1024)/1024)); shared-covariance kernel disabled for the headline", "l2": "inputs (31.5 GB at defaults) larger than L2; no flush",
                            "filters_per_gpu": N, "events_per_filter": T, "payload_layout": "[T, d, N] time-major"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
-                "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large,
+                "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large, "product_search": products,
                 "trajectory_mode": traj_mode, "shared_covariance": shared_mode}
     if world > 1:
         dist.barrier()
