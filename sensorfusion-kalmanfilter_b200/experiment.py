@@ -65,17 +65,22 @@ def adaptive_warmups(sf, end_indices, thresholds):
         keep, dts, _ = streams.schedule_dts(ps.times[first:e_max], prev_time, skip_advances_prev=False)
         state = (prev_time, *xt[:6])
         gate = thr if thr != -float("inf") else -1.0e300
+        eng = sf._engine()
+        x_d, P_d = xt[None].copy(), Pt[None].copy()  # carried on the device between launches (full 15-state x)
         done = 0  # events of `keep` already filtered
         for e, k in reqs:
             if e <= first:  # the window starts before the first GPS fix: the reference finds no GPS (:995-1004)
                 continue
             upto = int(np.searchsorted(keep, e - first, side="left"))
             if upto > done:
-                r = sf._run(first + keep[done:upto], dts[done:upto], xt, Pt, gate=gate, want_used=True)
-                xt, Pt = r["x"], r["P"]
-                state = r["states"][-1]
+                idx = first + keep[done:upto]
+                # only the state and covariance at the window start are used (:2316-2323): no per-step outputs
+                r = eng.run_batch(ps.types[idx], dts[done:upto], ps.payload(sf.MODEL_NAME, idx)[:, :, None], x_d, P_d,
+                                  want_agg=False, gate_threshold=gate)
+                x_d, P_d = r["x"], r["P"]
+                state = (float(ps.times[idx[-1]]), *x_d[0, :6].cpu().numpy())
                 done = upto
-            out[k] = (state, Pt.copy())
+            out[k] = (state, P_d[0].cpu().numpy().copy() if not isinstance(P_d, np.ndarray) else P_d[0].copy())
     return out
 
 
