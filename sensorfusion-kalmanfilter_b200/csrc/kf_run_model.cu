@@ -556,14 +556,21 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
       const double r0r1 = r0 * r1, ir0 = 1.0 / r0, ir1 = 1.0 / r1;
       LogDetAcc acc;
       bool ok = true;
+      // the step's (dt, type) are fetched one step ahead: a global load per step would sit on the serial chain
+      double dt_nx = (T > 0) ? __ldg(p.dts) : 0.0;
+      int ty_nx = (T > 0) ? __ldg(p.types) : 0;
       for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int s = chunk % kStages;
         if (chunk >= kStages) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kStages - 1) & 1u);
         const int k0 = chunk * kChunk;
         const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
         for (int cc = 0; cc < steps; ++cc) {
-          const double dt = __ldg(p.dts + k0 + cc);
-          const int ty = __ldg(p.types + k0 + cc);
+          const double dt = dt_nx;
+          const int ty = ty_nx;
+          if (k0 + cc + 1 < T) {
+            dt_nx = __ldg(p.dts + k0 + cc + 1);
+            ty_nx = __ldg(p.types + k0 + cc + 1);
+          }
           GainRec rec;
           rec.dt = dt;
           rec.type = ty;
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
           if (ty == EV_IMU) {
             const double detp = fma(ap, cp, -(bn * bn));
             const double t0 = fma(ap, r1, detp), t1 = fma(cp, r0, detp);
-            const double inv = fast_rcp(fma(r0, cp + r1, t0));
+            const double inv = fast_rcp3(fma(r0, cp + r1, t0));
             const double i0 = r0 * inv, i1 = r1 * inv;
             a = t0 * i0;
             c = t1 * i1;
@@ -590,7 +597,7 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
             rec.g11 = fma(g10, dt, g11);
             det = detp * inv * r0r1;
           } else if (ty == EV_GPS) {
-            const double inv = fast_rcp(ap + rg);
+            const double inv = fast_rcp3(ap + rg);
             rec.g00 = ap * inv;
             rec.g10 = bn * inv;
             const double g = rg * inv;
@@ -900,14 +907,20 @@ __global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL,
         if constexpr (!CTRL) Blk::template inv_noise<false>(p.mc, ir_imu);
         constexpr int so = Tags::slot_offset(K);
         bool ok = true;
+        double dt_nx = (T > 0) ? __ldg(p.dts) : 0.0;  // fetched one step ahead, off the serial chain
+        int ty_nx = (T > 0) ? __ldg(p.types) : 0;
         for (int chunk = 0; chunk < nchunks; ++chunk) {
           const int s = chunk % kSt;
           if (chunk >= kSt) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kSt - 1) & 1u);
           const int k0 = chunk * kCh;
           const int steps = (T - k0) < kCh ? (T - k0) : kCh;
           for (int cc = 0; cc < steps; ++cc) {
-            const double dt = __ldg(p.dts + k0 + cc);
-            const int ty = __ldg(p.types + k0 + cc);
+            const double dt = dt_nx;
+            const int ty = ty_nx;
+            if (k0 + cc + 1 < T) {
+              dt_nx = __ldg(p.dts + k0 + cc + 1);
+              ty_nx = __ldg(p.types + k0 + cc + 1);
+            }
             Rec* rec = gain_buf + s * kCh + cc;
             filter_predict<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
             filter_update<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
