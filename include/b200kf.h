@@ -141,6 +141,16 @@ int b200kf_run_batch(const b200kf_model* model, int64_t n_filters, int64_t n_ste
                      uint8_t* used, int32_t* status, double gate_threshold, uint32_t flags,
                      void* stream);
 
+/* b200kf_run_batch over a SELECTION of a longer stream without a gathered copy of the payload:
+ * step k reads payload row step_rows[k] (DEVICE i32 [T], 0 <= row < rows of `payload`); types and dts
+ * stay per step.  What run_kalman_filter_scheduled does with its selected events (kf_workers.py:914-947)
+ * for many seeds that share one base stream.  step_rows = NULL is b200kf_run_batch. */
+int b200kf_run_batch_rows(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
+                          const uint8_t* types, const double* dts, const void* payload,
+                          const int32_t* step_rows, void* x, void* P, double* agg, void* traj,
+                          int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used, int32_t* status,
+                          double gate_threshold, uint32_t flags, void* stream);
+
 /* Same computation from HOST buffers (the call a drop-in user makes): streams `payload` to the
  * device in time chunks, overlapping host->device copies with the kernel, and copies x, P, agg
  * back.  Synchronous.  payload/x/P/agg are HOST pointers (pinned memory copies fastest); types
@@ -248,6 +258,36 @@ int b200kf_select_greedy(const b200kf_model* model, int64_t n_events, const uint
                          const double* times, int32_t n_inst, const double* periods,
                          const double* t_prev, const double* P0, int64_t max_sel, int32_t* sel,
                          int64_t* n_sel, double* P_final, uint32_t flags, void* stream);
+
+/* b200kf_select_greedy that also publishes the gains of the selected events.  The selection walks the
+ * very covariance recursion the selected events' filter needs (kf_workers.py:914-947), so it can
+ * hand that filter its gain schedule: gain_records DEVICE [I, max_sel] records of
+ * b200kf_gain_record_bytes(model) bytes each (16-byte aligned), record j of instance i = (dt, type,
+ * K = P+ H^T R^-1 of every block of the model's axis-symmetric form, det P) of its j-th selected
+ * event.  Needs B200KF_RUN_FORCE_SYMMETRIC (the caller vouches for a chain-compatible P0 with
+ * identical blocks across axes; the reference's P0 and every P it produces).  NULL = no records. */
+int b200kf_select_greedy_gains(const b200kf_model* model, int64_t n_events, const uint8_t* types,
+                               const double* times, int32_t n_inst, const double* periods,
+                               const double* t_prev, const double* P0, int64_t max_sel, int32_t* sel,
+                               int64_t* n_sel, double* P_final, void* gain_records, uint32_t flags,
+                               void* stream);
+int b200kf_gain_record_bytes(const b200kf_model* model, size_t* bytes);
+
+/* The filter loop for n_filters filters that share a schedule AND a covariance, given that
+ * schedule's precomputed gain records (Monte-Carlo seeds of one configuration: the records are
+ * computed once, every batch of seeds is then a pure stream -- no covariance recursion, no serial
+ * work in the launch).  x += K (z - H x) per event with the reference's pseudo-measurement
+ * (kf_workers.py:698-711); the covariance never enters (its producer returned P_final).
+ *
+ *   gain_records DEVICE [T] records (b200kf_select_greedy_gains)      payload DEVICE real [T, d, N]
+ *   step_rows    DEVICE i32 [T] nullable: payload row of step k (as b200kf_run_batch_rows)
+ *   x       DEVICE real [N, n] in/out        agg DEVICE f64 [N, 4] nullable (from the records' det P)
+ *   traj / logdet / used / status as b200kf_run_batch; flags: B200KF_RUN_AGG_CONTINUE
+ * Rows must be 16-byte aligned: N even (float64) or a multiple of 4 (float32). */
+int b200kf_run_gains(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
+                     const void* gain_records, const void* payload, const int32_t* step_rows, void* x,
+                     double* agg, void* traj, int32_t traj_ncomp, void* logdet, uint8_t* used,
+                     int32_t* status, uint32_t flags, void* stream);
 
 /* Batched Scheduler.cov_matrix (kf_workers.py:112-171; the reference's only device='cuda'
  * branch): Sigma_post = Sigma - K H^ Sigma with H^ = the k selected rows of H, for `batch`

@@ -55,6 +55,9 @@ SIGNATURES = {
     "b200kf_run_batch": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_double, c_uint32, c_void_p]),
+    "b200kf_run_batch_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_double, c_uint32, c_void_p]),
     "b200kf_run_batch_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_uint32]),
     "b200kf_score_schedules": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), c_double,
@@ -70,6 +73,11 @@ SIGNATURES = {
     "b200kf_rmse_vs_track": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "b200kf_select_greedy": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b200kf_select_greedy_gains": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                           c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b200kf_gain_record_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),
+    "b200kf_run_gains": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int32, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "b200kf_cov_update": (c_int, [c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_double),
                                   POINTER(c_double), c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200kf_fill_payload": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_uint64, c_void_p, c_void_p]),

@@ -74,6 +74,16 @@ static int dispatch_product(const b200kf_model* m, const ProductParams& p, unsig
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
 
+static int dispatch_gains(const b200kf_model* m, const RunParams& p, cudaStream_t st) {
+  switch (m->desc.model_id) {
+    case MODEL_CV6: return launch_gains_m<MODEL_CV6>(m, p, st);
+    case MODEL_CA8: return launch_gains_m<MODEL_CA8>(m, p, st);
+    case MODEL_BIAS9: return launch_gains_m<MODEL_BIAS9>(m, p, st);
+    case MODEL_CA15: return launch_gains_m<MODEL_CA15>(m, p, st);
+  }
+  return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
+}
+
 static int dispatch_select(const b200kf_model* m, const SelectParams& p, unsigned flags, cudaStream_t st) {
   switch (m->desc.model_id) {
     case MODEL_CV6: return launch_select_m<MODEL_CV6>(m, p, flags, st);
@@ -564,6 +574,14 @@ int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
                      const double* dts, const void* payload, void* x, void* P, double* agg,
                      void* traj, int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used,
                      int32_t* status, double gate_threshold, uint32_t flags, void* stream) {
+  return b200kf_run_batch_rows(m, n_filters, n_steps, types, dts, payload, nullptr, x, P, agg, traj, traj_ncomp, ptraj,
+                               logdet, used, status, gate_threshold, flags, stream);
+}
+
+int b200kf_run_batch_rows(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const uint8_t* types,
+                          const double* dts, const void* payload, const int32_t* step_rows, void* x, void* P,
+                          double* agg, void* traj, int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used,
+                          int32_t* status, double gate_threshold, uint32_t flags, void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
   if (n_filters < 0 || n_steps < 0) return set_error(B200KF_ERR_INVALID, "negative size");
   if (n_steps > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_steps > 2^31-1 per call");
@@ -596,6 +614,8 @@ int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
   p.gate_threshold = gate_threshold;
   p.agg_continue = (flags & B200KF_RUN_AGG_CONTINUE) ? 1 : 0;
   p.dense_flag = nullptr;
+  p.gain_recs = nullptr;
+  p.step_rows = step_rows;
   return dispatch_run(m, p, flags, static_cast<cudaStream_t>(stream));
 }
 
@@ -885,10 +905,10 @@ int b200kf_rmse_vs_track(const b200kf_model* m, int64_t n_filters, int64_t n_ste
   return B200KF_OK;
 }
 
-int b200kf_select_greedy(const b200kf_model* m, int64_t n_events, const uint8_t* types,
-                         const double* times, int32_t n_inst, const double* periods, const double* t_prev,
-                         const double* P0, int64_t max_sel, int32_t* sel, int64_t* n_sel, double* P_final,
-                         uint32_t flags, void* stream) {
+int b200kf_select_greedy_gains(const b200kf_model* m, int64_t n_events, const uint8_t* types,
+                               const double* times, int32_t n_inst, const double* periods, const double* t_prev,
+                               const double* P0, int64_t max_sel, int32_t* sel, int64_t* n_sel, double* P_final,
+                               void* gain_records, uint32_t flags, void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
   if (m->desc.model_id == MODEL_BIAS9)
     return set_error(B200KF_ERR_UNSUPPORTED, "greedy selection needs an IMU measurement model");
@@ -910,7 +930,71 @@ int b200kf_select_greedy(const b200kf_model* m, int64_t n_events, const uint8_t*
   p.sel = sel;
   p.n_sel = reinterpret_cast<long long*>(n_sel);
   p.P_final = P_final;
+  p.gain_recs = gain_records;
   return dispatch_select(m, p, flags, static_cast<cudaStream_t>(stream));
+}
+
+int b200kf_select_greedy(const b200kf_model* m, int64_t n_events, const uint8_t* types,
+                         const double* times, int32_t n_inst, const double* periods, const double* t_prev,
+                         const double* P0, int64_t max_sel, int32_t* sel, int64_t* n_sel, double* P_final,
+                         uint32_t flags, void* stream) {
+  return b200kf_select_greedy_gains(m, n_events, types, times, n_inst, periods, t_prev, P0, max_sel, sel, n_sel,
+                                    P_final, nullptr, flags, stream);
+}
+
+int b200kf_gain_record_bytes(const b200kf_model* m, size_t* bytes) {
+  if (!m || !bytes) return set_error(B200KF_ERR_INVALID, "null argument");
+  switch (m->desc.model_id) {
+    case MODEL_CV6: *bytes = gain_record_bytes_m<MODEL_CV6>(); break;
+    case MODEL_CA8: *bytes = gain_record_bytes_m<MODEL_CA8>(); break;
+    case MODEL_BIAS9: *bytes = gain_record_bytes_m<MODEL_BIAS9>(); break;
+    case MODEL_CA15: *bytes = gain_record_bytes_m<MODEL_CA15>(); break;
+    default: return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
+  }
+  return B200KF_OK;
+}
+
+int b200kf_run_gains(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const void* gain_records,
+                     const void* payload, const int32_t* step_rows, void* x, double* agg, void* traj,
+                     int32_t traj_ncomp, void* logdet, uint8_t* used, int32_t* status, uint32_t flags, void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (n_filters < 0 || n_steps < 0) return set_error(B200KF_ERR_INVALID, "negative size");
+  if (n_steps > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_steps > 2^31-1 per call");
+  if (n_filters == 0) return B200KF_OK;
+  if (!x) return set_error(B200KF_ERR_INVALID, "x is required");
+  if (n_steps > 0 && (!gain_records || !payload))
+    return set_error(B200KF_ERR_INVALID, "gain_records and payload are required when n_steps > 0");
+  if (traj && (traj_ncomp < 1 || traj_ncomp > m->n))
+    return set_error(B200KF_ERR_INVALID, "traj_ncomp must be in [1, %d]", m->n);
+  const size_t rb = m->desc.precision == B200KF_F32 ? 4 : 8;
+  if ((n_filters * rb) % 16 != 0 || (reinterpret_cast<uintptr_t>(payload) & 15u) != 0 ||
+      (reinterpret_cast<uintptr_t>(gain_records) & 15u) != 0)
+    return set_error(B200KF_ERR_UNSUPPORTED,
+                     "b200kf_run_gains streams with bulk copies: 16-byte aligned buffers and rows (even filter count "
+                     "in float64, a multiple of 4 in float32)");
+  RunParams p;
+  p.mc = m->mc;
+  p.n_filters = n_filters;
+  p.n_steps = static_cast<int>(n_steps);
+  p.types = nullptr;
+  p.dts = nullptr;
+  p.payload = payload;
+  p.x = x;
+  p.P = nullptr;
+  p.agg = agg;
+  p.traj = traj;
+  p.traj_ncomp = traj ? traj_ncomp : 0;
+  p.ptraj = nullptr;
+  p.logdet = logdet;
+  p.used = used;
+  p.status = status;
+  p.gate_enabled = 0;
+  p.gate_threshold = 0.0;
+  p.agg_continue = (flags & B200KF_RUN_AGG_CONTINUE) ? 1 : 0;
+  p.dense_flag = nullptr;
+  p.gain_recs = gain_records;
+  p.step_rows = step_rows;
+  return dispatch_gains(m, p, static_cast<cudaStream_t>(stream));
 }
 
 int b200kf_cov_update(int32_t n, int32_t m_rows, int32_t k, const int32_t* rows, const double* H,

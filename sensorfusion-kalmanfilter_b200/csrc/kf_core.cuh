@@ -1739,6 +1739,34 @@ struct SymTraits<MODEL_CA15, real> {
                          SymGroup<CA15AngChain<0>, CA15AngChain<1>, CA15AngChain<2>>>;
 };
 
+// --------------------------------------------------------------------------------------
+// Gain records: what a covariance recursion publishes per step for filters that only apply gains
+// (shared-covariance kernels, precomputed gain schedules).  g holds, block after block of the model's
+// axis-symmetric form, K = P+ H^T R^-1 of the event's measured columns (row-major [n][n_meas]).
+// --------------------------------------------------------------------------------------
+template <class Flt>
+struct GainSlots {
+  static constexpr int value = 0;
+  static constexpr int cov = 0;
+};
+template <typename real, bool IC, class B0, class... Bs>
+struct GainSlots<FilterT<real, IC, B0, Bs...>> {
+  using Blk = typename BlockObj<B0, real>::type;
+  static constexpr int value = Blk::kslots + GainSlots<FilterT<real, IC, Bs...>>::value;
+  static constexpr int cov = Blk::NP + GainSlots<FilterT<real, IC, Bs...>>::cov;
+};
+
+constexpr int kMaxGainBlocks = 4;
+template <int NG>
+struct alignas(16) GainRecG {    // a multiple of 16 bytes: records travel by bulk copy
+  double dt;
+  double det[kMaxGainBlocks];    // det of each block (with its axis multiplicity); unused entries are 1
+  double ldet[kMaxGainBlocks];   // log of it (per-step log-det output only); unused entries are 0
+  int type;
+  int pad;
+  double g[NG > 0 ? NG : 1];
+};
+
 // kernel variants: 0 = one covariance per chain, 1 = dense, 2 = one covariance per symmetric group
 enum : int { VAR_DECOUPLED = 0, VAR_DENSE = 1, VAR_SYMMETRIC = 2 };
 template <int MODEL_ID, int VAR, typename real>

@@ -71,6 +71,8 @@ struct RunParams {
   int gate_enabled;
   int agg_continue;
   const int* dense_flag;  // AUTO mode: int[3] {coupled, asymmetric, P differs between filters}; a kernel runs only if they select its mode
+  const void* gain_recs;  // b200kf_run_gains: DEVICE [T] precomputed gain records (GainRecG of the model)
+  const int* step_rows;   // DEVICE [T] payload row of every step, or null (step k reads row k)
 };
 
 constexpr int kMaxEvents = 32;
@@ -130,6 +132,7 @@ struct SelectParams {
   int* sel;                    // DEVICE [I, max_sel] selected event indices
   long long* n_sel;            // DEVICE [I]
   double* P_final;             // DEVICE [I, n, n] or null
+  void* gain_recs;             // DEVICE [I, max_sel] gain records of the selected events (axis-symmetric form) or null
 };
 
 // run_brute_force_kalman_filter (KF_SensorFusion.ipynb:804-954): one event per window queue,
@@ -176,6 +179,11 @@ int launch_score_m(const b200kf_model* m, ScoreParams p, unsigned flags, b200kf_
 
 template <int MODEL>
 int launch_masked_m(const b200kf_model* m, const MaskedParams& p, unsigned flags, cudaStream_t st);
+
+template <int MODEL>
+int launch_gains_m(const b200kf_model* m, const RunParams& p, cudaStream_t st);
+template <int MODEL>
+size_t gain_record_bytes_m();
 
 template <int MODEL>
 int launch_product_m(const b200kf_model* m, const ProductParams& p, unsigned flags, cudaStream_t st);

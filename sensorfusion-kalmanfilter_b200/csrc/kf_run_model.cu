@@ -43,6 +43,12 @@ __device__ __forceinline__ bool mode_selected(const int* flags, int mine) {
   return actual == mine;
 }
 
+// payload row of step k: k itself, or step_rows[k] when the launch walks a selection of a longer stream
+// (the scheduled filter's selected events) without a gathered copy of the payload
+__device__ __forceinline__ long long step_row(const int* __restrict__ rows, int k) {
+  return rows != nullptr ? static_cast<long long>(__ldg(rows + k)) : static_cast<long long>(k);
+}
+
 template <int MODEL, int VAR, typename real, bool FULL>
 __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
                                   (LaunchCfg<MODEL, VAR, real>::min_blocks))
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
   for (int j = 0; j < PF; ++j) {
     if (j < T) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) ubuf[j][c] = __ldcs(pay + j * step_stride + c * N);
+      for (int c = 0; c < D; ++c) ubuf[j][c] = __ldcs(pay + step_row(p.step_rows, j) * step_stride + c * N);
     }
   }
 
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
 #pragma unroll
         for (int c = 0; c < D; ++c) u[c] = ubuf[j][c];
         if (k + PF < T) {
-          const real* src = pay + static_cast<long long>(k + PF) * step_stride;
+          const real* src = pay + step_row(p.step_rows, k + PF) * step_stride;
 #pragma unroll
           for (int c = 0; c < D; ++c) ubuf[j][c] = __ldcs(src + c * N);
         }
@@ -285,13 +291,15 @@ struct TmaFlt {
 // The copy lane of every ring kernel: keeps the payload ring full, gated only by the ring's empty
 // barriers.  Stage s holds CH steps x D rows of F reals; the rows of one (step, column) are contiguous in
 // the time-major payload, so each is one cp.async.bulk completing on the stage's full barrier.  With
-// `sched` the chunk's packed step records travel with it.  (An L2 prefetch of later rows with
+// `sched` the chunk's per-step records (packed schedule, or precomputed gain records) travel with it.  (An L2 prefetch of later rows with
 // cp.async.bulk.prefetch.L2 was measured 8-25 % slower for the deep d = 3 ring and neutral for the
 // shallow d = 9 one, and is not issued.)
-template <typename real, int D, int F, int ST, int CH>
+template <typename real, int D, int F, int ST, int CH, class AuxRec = SchedRec>
 __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long long* full, unsigned long long* empty,
                                                const real* pay, long long N, int T, unsigned row_bytes,
-                                               SchedRec* sched_buf = nullptr, const SchedRec* sched = nullptr) {
+                                               AuxRec* sched_buf = nullptr, const AuxRec* sched = nullptr,
+                                               const int* __restrict__ step_rows = nullptr) {
+  static_assert(sizeof(AuxRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
   constexpr size_t kStageReals = static_cast<size_t>(CH) * D * F;
   const int nchunks = (T + CH - 1) / CH;
   for (int chunk = 0; chunk < nchunks; ++chunk) {
@@ -299,14 +307,15 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
     if (chunk >= ST) mbar_wait(&empty[s], static_cast<unsigned>(chunk / ST - 1) & 1u);
     const int k0 = chunk * CH;
     const int steps = (T - k0) < CH ? (T - k0) : CH;
-    const unsigned rec_bytes = (sched != nullptr) ? static_cast<unsigned>(steps * sizeof(SchedRec)) : 0u;
+    const unsigned rec_bytes = (sched != nullptr) ? static_cast<unsigned>(steps * sizeof(AuxRec)) : 0u;
     mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * D * row_bytes + rec_bytes);
     if (sched != nullptr) bulk_g2s(sched_buf + s * CH, sched + k0, rec_bytes, &full[s]);
     real* dst = stage_buf + s * kStageReals;
-    for (int c = 0; c < steps; ++c)
+    for (int c = 0; c < steps; ++c) {
+      const long long row = step_row(step_rows, k0 + c);
 #pragma unroll
-      for (int j = 0; j < D; ++j)
-        bulk_g2s(dst + (c * D + j) * F, pay + (static_cast<long long>(k0 + c) * D + j) * N, row_bytes, &full[s]);
+      for (int j = 0; j < D; ++j) bulk_g2s(dst + (c * D + j) * F, pay + (row * D + j) * N, row_bytes, &full[s]);
+    }
   }
 }
 
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(F + 32, 1)
     // ---- producer warp: one lane keeps the ring full, decoupled from the math warps' progress ----
     if (tid == kTmaThreads)
       ring_copy_loop<real, D, F, kStages, kChunk>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
-                                                  static_cast<unsigned>(nfb * sizeof(real)), sched_buf, sched);
+                                                  static_cast<unsigned>(nfb * sizeof(real)), sched_buf, sched, p.step_rows);
     return;
   }
 
@@ -541,7 +550,7 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
     // ---------------- copy warp: one lane keeps the payload ring full ------------------------------
     if (tid == kMathThreads + 32)
       ring_copy_loop<real, D, F, kStages, kChunk>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
-                                                  row_bytes);
+                                                  row_bytes, static_cast<SchedRec*>(nullptr), static_cast<const SchedRec*>(nullptr), p.step_rows);
   } else if (tid >= kMathThreads) {
     // ---------------- gain warp: the one covariance recursion of the launch ------------------------
     if (tid == kMathThreads) {
@@ -756,18 +765,6 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
 // arithmetic.  Monte-Carlo seeds of one configuration (BASELINE configs[1]: 4096 seeds per rate)
 // and batches started from the reference's fixed P0 (configs[4]) take this path in AUTO mode.
 // ------------------------------------------------------------------------------------------
-template <class Flt>
-struct GainSlots {
-  static constexpr int value = 0;
-  static constexpr int cov = 0;
-};
-template <typename real, bool IC, class B0, class... Bs>
-struct GainSlots<FilterT<real, IC, B0, Bs...>> {
-  using Blk = typename BlockObj<B0, real>::type;
-  static constexpr int value = Blk::kslots + GainSlots<FilterT<real, IC, Bs...>>::value;
-  static constexpr int cov = Blk::NP + GainSlots<FilterT<real, IC, Bs...>>::cov;
-};
-
 template <int MODEL, typename real>
 struct SharedRing {  // ring depth per model: stages * chunk * d rows of 896 reals within ~200 KB
   static constexpr int d = ModelTraits<MODEL, false, real>::d;
@@ -799,19 +796,11 @@ struct FilterTags<FilterT<real, IC, Bs...>> {
   }
 };
 
-constexpr int kMaxGainBlocks = 4;
-template <int NG>
-struct GainRecG {
-  double dt;
-  double det[kMaxGainBlocks];    // det of each block (with its axis multiplicity), by its gain warp
-  double ldet[kMaxGainBlocks];   // log of it (per-step log-det output only)
-  int type;
-  int pad;
-  double g[NG > 0 ? NG : 1];
-};
-
-template <int MODEL, typename real, bool FULL, int F>
-__global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL, double>::Filter>::count + 2), 1)
+// EXT: the gain records were computed beforehand (b200kf_select_greedy's gain output, or any earlier pass over
+// the same schedule and P0) and stream in from global memory with the payload: no gain warps, no serial
+// recursion in the launch at all -- the kernel is a pure stream whatever the number of filters.
+template <int MODEL, typename real, bool FULL, int F, bool EXT = false>
+__global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTraits<MODEL, double>::Filter>::count) + 2), 1)
     kf_run_shared_generic_kernel(const RunParams p) {
   constexpr int kMathThreads = F;
   using MT = ModelTraits<MODEL, false, real>;
@@ -829,7 +818,8 @@ __global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL,
   constexpr int kSt = SharedRing<MODEL, real>::stages * (896 / F);
   constexpr int kCh = SharedRing<MODEL, real>::chunk;
   // warp roles after the F / 32 math warps: NB gain warps (one block each), the copy warp, the aggregate warp
-  constexpr int kGainBase = kMathThreads, kCopyTid = kMathThreads + 32 * NB, kAggTid = kCopyTid + 32;
+  constexpr int NGW = EXT ? 0 : NB;  // gain warps in this launch
+  constexpr int kGainBase = kMathThreads, kCopyTid = kMathThreads + 32 * NGW, kAggTid = kCopyTid + 32;
   if (!mode_selected(p.dense_flag, MODE_SHARED)) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -850,7 +840,7 @@ __global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL,
 
   if (tid == 0) {
     for (int s = 0; s < kSt; ++s) {
-      mbar_init(&full[s], 1 + NB);                     // the copy warp's expect_tx arrival + one arrival per gain warp
+      mbar_init(&full[s], 1 + NGW);                    // the copy warp's expect_tx arrival + one arrival per gain warp
       mbar_init(&empty[s], kMathThreads / 32 + 1);     // the math warps + the aggregate warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -887,10 +877,15 @@ __global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL,
     }
   } else if (tid >= kCopyTid) {
     // ---------------- copy warp ----------------------------------------------------------------
-    if (tid == kCopyTid)
-      ring_copy_loop<real, D, F, kSt, kCh>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
-                                           row_bytes);
-  } else if (tid >= kGainBase) {
+    if (tid == kCopyTid) {
+      if constexpr (EXT)
+        ring_copy_loop<real, D, F, kSt, kCh, Rec>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N,
+                                                  T, row_bytes, gain_buf, static_cast<const Rec*>(p.gain_recs), p.step_rows);
+      else
+        ring_copy_loop<real, D, F, kSt, kCh>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
+                                             row_bytes, static_cast<SchedRec*>(nullptr), static_cast<const SchedRec*>(nullptr), p.step_rows);
+    }
+  } else if (!EXT && tid >= kGainBase) {
     // ---------------- gain warps: block k's covariance recursion on one lane of warp k --------------
     const int gw = (tid - kGainBase) >> 5;
     if (((tid - kGainBase) & 31) == 0) {
@@ -1027,7 +1022,7 @@ __global__ void __launch_bounds__(F + 32 * (FilterTags<typename SymTraits<MODEL,
   __syncthreads();  // the gain warps' final covariance and the aggregate warp's results
   if (tid >= nfb) return;
   const long long f = base + tid;
-  if (T > 0) {
+  if (T > 0 && !EXT) {  // with external gains the covariance never enters the launch (its producer returns P)
     real* Pg = static_cast<real*>(p.P) + f * (n * n);
     FltP shape;  // only its static tables are used
     int o = 0;
@@ -1242,6 +1237,43 @@ static cudaError_t launch_shared(const b200kf_model* m, const RunParams& p, bool
   if (f == 896) return launch_shared_f<MODEL, real, false, 896>(p, st);
   if (f == 448) return launch_shared_f<MODEL, real, false, 448>(p, st);
   return launch_shared_f<MODEL, real, false, 224>(p, st);
+}
+
+// b200kf_run_gains: filters that only apply precomputed gain records (any model, axis-symmetric form)
+template <int MODEL, typename real, bool FULL, int F>
+static cudaError_t launch_gains_f(const RunParams& p, cudaStream_t st) {
+  constexpr size_t smem = shared_generic_smem_bytes<MODEL, real, F>();
+  const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
+  cudaError_t err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, FULL, F, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  kf_run_shared_generic_kernel<MODEL, real, FULL, F, true><<<blocks, F + 64, smem, st>>>(p);
+  return cudaGetLastError();
+}
+template <int MODEL, typename real>
+static int launch_gains_precision(const b200kf_model* m, const RunParams& p, cudaStream_t st) {
+  const bool full = p.traj != nullptr || p.logdet != nullptr || p.used != nullptr;
+  constexpr int kStepBytes896 = ModelTraits<MODEL, false, real>::d * static_cast<int>(sizeof(real)) * 896;
+  const int cap = (kStepBytes896 > 36 * 1024 && m->ring_f_cap > 448) ? 448 : m->ring_f_cap;
+  const int f = pick_ring_f(p.n_filters, m->sm_count, cap);
+  cudaError_t e;
+  if (full)
+    e = f == 896 ? launch_gains_f<MODEL, real, true, 896>(p, st)
+                 : (f == 448 ? launch_gains_f<MODEL, real, true, 448>(p, st) : launch_gains_f<MODEL, real, true, 224>(p, st));
+  else
+    e = f == 896 ? launch_gains_f<MODEL, real, false, 896>(p, st)
+                 : (f == 448 ? launch_gains_f<MODEL, real, false, 448>(p, st) : launch_gains_f<MODEL, real, false, 224>(p, st));
+  B200KF_CUDA_TRY(e);
+  return B200KF_OK;
+}
+template <>
+int launch_gains_m<B200KF_INST_MODEL>(const b200kf_model* m, const RunParams& p, cudaStream_t st) {
+  if (m->desc.precision == B200KF_F32) return launch_gains_precision<B200KF_INST_MODEL, float>(m, p, st);
+  return launch_gains_precision<B200KF_INST_MODEL, double>(m, p, st);
+}
+template <>
+size_t gain_record_bytes_m<B200KF_INST_MODEL>() {
+  return sizeof(GainRecG<GainSlots<typename SymTraits<B200KF_INST_MODEL, double>::Filter>::value>);
 }
 
 template <int MODEL, typename real>

@@ -392,6 +392,19 @@ __global__ void select_greedy_kernel(const SelectParams p) {
   if (inst >= p.n_inst) return;
   typename MT::Filter flt;
   flt.each([&](auto& b) { b.load_cov(p.P0 + static_cast<long long>(inst) * n * n, n); });
+  double ir_gps[kMaxN], ir_imu[kMaxN];  // 1 / r per measured column, block after block (gain records only)
+  if constexpr (VAR == VAR_SYMMETRIC) {
+    int og = 0, oi = 0;
+    flt.each([&](const auto& b) {
+      using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+      BT::template inv_noise<true>(p.mc, ir_gps + og);
+      og += BT::template n_meas<true>();
+      if constexpr (!MT::imu_control) {
+        BT::template inv_noise<false>(p.mc, ir_imu + oi);
+        oi += BT::template n_meas<false>();
+      }
+    });
+  }
   const double period = p.periods[inst];
   double prev = p.t_prev[inst];
   int* sel = p.sel + static_cast<long long>(inst) * p.max_sel;
@@ -447,6 +460,36 @@ __global__ void select_greedy_kernel(const SelectParams p) {
     filter_update<false>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
     prev = ts;
     if (ns < p.max_sel) sel[ns] = static_cast<int>(pick);
+    if constexpr (VAR == VAR_SYMMETRIC) {
+      // the selection walks the very covariance recursion the selected events' filter needs: publish its gains
+      // (K = P+ H^T R^-1 per block, det P) so that filter can run as a pure stream (b200kf_run_gains)
+      if (p.gain_recs != nullptr && ns < p.max_sel) {
+        using Rec = GainRecG<GainSlots<typename MT::Filter>::value>;
+        Rec* rec = static_cast<Rec*>(p.gain_recs) + static_cast<long long>(inst) * p.max_sel + ns;
+        int o = 0, oc = 0;
+        flt.each([&](const auto& b) {
+          using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+          if (tys == EV_GPS) {
+            b.template extract_gain<true>(ir_gps + oc, rec->g + o);
+            oc += BT::template n_meas<true>();
+          } else if (tys == EV_IMU) {
+            if constexpr (!MT::imu_control) b.template extract_gain<false>(ir_imu + oc, rec->g + o);
+            oc += BT::template n_meas<false>();
+          }
+          o += BT::kslots;
+        });
+        bool okd = true;
+        const double det = filter_det(flt, okd);
+        rec->dt = dt;
+        rec->type = tys;
+        rec->pad = 0;
+#pragma unroll
+        for (int q = 0; q < kMaxGainBlocks; ++q) {
+          rec->det[q] = (q == 0) ? det : 1.0;
+          rec->ldet[q] = (q == 0) ? log(det) : 0.0;
+        }
+      }
+    }
     ns += 1;
     first_gps = first_imu = q_first = -1;
   }
@@ -470,7 +513,10 @@ int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams
   // P0 lives on the device, so the caller vouches for its structure: FORCE_SYMMETRIC = chain-compatible with
   // identical blocks across the axes of a group (one covariance per group), FORCE_DECOUPLED = chain-compatible;
   // without a flag the dense form, which is always valid
-  if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && m->use_sym && SymF::constants_equal(m->mc))
+  const bool sym_ok = (flags & B200KF_RUN_FORCE_SYMMETRIC) && m->use_sym && SymF::constants_equal(m->mc);
+  if (p.gain_recs != nullptr && !sym_ok)
+    return set_error(B200KF_ERR_UNSUPPORTED, "gain records need B200KF_RUN_FORCE_SYMMETRIC (an axis-symmetric P0 and equal rates)");
+  if (sym_ok)
     select_greedy_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<blocks, tpb, 0, st>>>(p);
   else if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC))
     select_greedy_kernel<B200KF_INST_MODEL, VAR_DECOUPLED><<<blocks, tpb, 0, st>>>(p);

@@ -78,7 +78,7 @@ class Engine:
     # ------------------------------------------------------------------ filter loop
     def run_batch(self, types, dts, payload, x, P, *, want_agg=True, traj_ncomp=0, want_logdet=False,
                   want_used=False, want_ptraj=False, gate_threshold=None, mode="auto", agg=None,
-                  stream=None, inplace=False):
+                  stream=None, inplace=False, step_rows=None):
         """Run N filters over a shared schedule (b200kf_run_batch).
 
         types [T] u8, dts [T] f64, payload [T, d, N], x [N, n], P [N, n, n]; numpy arrays or torch
@@ -101,7 +101,12 @@ class Engine:
         N = int(x_d.shape[0])
         if tuple(x_d.shape) != (N, sp.n) or tuple(P_d.shape) != (N, sp.n, sp.n):
             raise ValueError(f"x must be [N,{sp.n}] and P [N,{sp.n},{sp.n}]")
-        if T and tuple(pay_d.shape) != (T, sp.d, N):
+        rows_d = None
+        if step_rows is not None:  # step k reads payload row step_rows[k]: a selection of a longer stream, no gather
+            rows_d = self._dev(step_rows, torch.int32)
+            if int(rows_d.numel()) != T or tuple(pay_d.shape[1:]) != (sp.d, N):
+                raise ValueError(f"step_rows must be [T={T}] and payload [rows, d={sp.d}, N={N}]")
+        elif T and tuple(pay_d.shape) != (T, sp.d, N):
             raise ValueError(f"payload must be [T={T}, d={sp.d}, N={N}], got {tuple(pay_d.shape)}")
         if dts_d.numel() != T:
             raise ValueError("types and dts must have the same length")
@@ -119,8 +124,8 @@ class Engine:
         status_d = torch.zeros((N,), dtype=torch.int32, device=self.device)
         gate = float("nan") if gate_threshold is None else float(gate_threshold)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.b200kf_run_batch(
-                self._h, N, T, _ptr(types_d), _ptr(dts_d), _ptr(pay_d), _ptr(x_d), _ptr(P_d), _ptr(agg_d),
+            _lib.check(self.lib.b200kf_run_batch_rows(
+                self._h, N, T, _ptr(types_d), _ptr(dts_d), _ptr(pay_d), _ptr(rows_d), _ptr(x_d), _ptr(P_d), _ptr(agg_d),
                 _ptr(traj_d), int(traj_ncomp), _ptr(ptraj_d), _ptr(ld_d), _ptr(used_d), _ptr(status_d), gate, flags,
                 self._stream(stream)))
         return {"x": x_d, "P": P_d, "agg": agg_d, "traj": traj_d, "logdet": ld_d, "used": used_d,
@@ -299,9 +304,17 @@ class Engine:
                 "runner_up_score": b.runner_up_score, "n_scored": int(b.n_scored)}
         return best, per
 
-    def select_greedy(self, types, times, periods, t_prev, P0, *, max_sel=None, mode="auto", stream=None):
+    def gain_record_bytes(self):
+        n = ctypes.c_size_t(0)
+        _lib.check(self.lib.b200kf_gain_record_bytes(self._h, byref(n)))
+        return int(n.value)
+
+    def select_greedy(self, types, times, periods, t_prev, P0, *, max_sel=None, mode="auto", stream=None,
+                      want_gains=False, _alloc_gains=True):
         """Greedy one-event-per-window selection (b200kf_select_greedy) for I instances over one
-        event list.  Returns (list of int32 numpy index arrays, P_final torch [I,n,n])."""
+        event list.  Returns (list of int32 numpy index arrays, P_final torch [I,n,n]); with
+        want_gains=True a third item: the selected events' gain records, torch uint8 [I, max_sel, bytes]
+        (None when P0 is not axis-symmetric: the records exist in the symmetric form only)."""
         torch = _torch()
         sp = self.spec
         types_d = self._dev(types, torch.uint8)
@@ -326,17 +339,59 @@ class Engine:
         sel = torch.empty((I, max_sel), dtype=torch.int32, device=self.device)
         n_sel = torch.zeros((I,), dtype=torch.int64, device=self.device)
         P_f = torch.empty((I, sp.n, sp.n), dtype=torch.float64, device=self.device)
+        recs = None
+        if want_gains and _alloc_gains and mode == "symmetric":
+            recs = torch.empty((I, max_sel, self.gain_record_bytes()), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.b200kf_select_greedy(
+            _lib.check(self.lib.b200kf_select_greedy_gains(
                 self._h, E, _ptr(types_d), _ptr(times_d), I, _ptr(per_d), _ptr(tp_d), _ptr(P0_d), max_sel,
-                _ptr(sel), _ptr(n_sel), _ptr(P_f), _MODES[mode], self._stream(stream)))
+                _ptr(sel), _ptr(n_sel), _ptr(P_f), _ptr(recs), _MODES[mode], self._stream(stream)))
         ns = n_sel.cpu().numpy()
         sel_h = sel.cpu().numpy()
-        return [sel_h[i, :min(int(ns[i]), max_sel)].copy() for i in range(I)], P_f
+        sels = [sel_h[i, :min(int(ns[i]), max_sel)].copy() for i in range(I)]
+        return (sels, P_f, recs) if want_gains else (sels, P_f)
+
+    def run_gains(self, gain_records, payload, x, *, want_agg=True, traj_ncomp=0, want_logdet=False, agg=None,
+                  stream=None, inplace=False, step_rows=None):
+        """N filters that share a schedule and a covariance, from that schedule's precomputed gain
+        records (b200kf_run_gains): gain_records torch uint8 [T, bytes] (one instance's slice of
+        select_greedy(..., want_gains=True)), payload [T, d, N], x [N, n].  Returns dict of torch CUDA
+        tensors x, agg [N, 4], traj, logdet, status."""
+        torch = _torch()
+        sp = self.spec
+        rec = gain_records.contiguous()
+        T = int(rec.shape[0])
+        pay_d = self._dev(payload, self.real)
+        x_d = self._dev(x, self.real)
+        if not inplace and isinstance(x, torch.Tensor) and x_d.data_ptr() == x.data_ptr():
+            x_d = x_d.clone()
+        N = int(x_d.shape[0])
+        rows_d = None
+        if step_rows is not None:
+            rows_d = self._dev(step_rows, torch.int32)
+            if int(rows_d.numel()) != T or tuple(pay_d.shape[1:]) != (sp.d, N):
+                raise ValueError(f"step_rows must be [T={T}] and payload [rows, d={sp.d}, N={N}]")
+        elif T and tuple(pay_d.shape) != (T, sp.d, N):
+            raise ValueError(f"payload must be [T={T}, d={sp.d}, N={N}], got {tuple(pay_d.shape)}")
+        flags = 0
+        agg_d = None
+        if agg is not None:
+            agg_d = self._dev(agg, torch.float64)
+            flags |= _lib.RUN_AGG_CONTINUE
+        elif want_agg:
+            agg_d = torch.empty((N, 4), dtype=torch.float64, device=self.device)
+        traj_d = torch.empty((T, traj_ncomp, N), dtype=self.real, device=self.device) if traj_ncomp else None
+        ld_d = torch.empty((T, N), dtype=self.real, device=self.device) if want_logdet else None
+        status_d = torch.zeros((N,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200kf_run_gains(self._h, N, T, _ptr(rec), _ptr(pay_d), _ptr(rows_d), _ptr(x_d), _ptr(agg_d), _ptr(traj_d),
+                                                 int(traj_ncomp), _ptr(ld_d), None, _ptr(status_d), flags,
+                                                 self._stream(stream)))
+        return {"x": x_d, "agg": agg_d, "traj": traj_d, "logdet": ld_d, "status": status_d}
 
 
     def scheduled_sweep(self, types, times, payload, rates, x0, P0, t_prev, *, traj_ncomp=0, mode="auto",
-                        concurrent=True, sels=None):
+                        concurrent=True, sels=None, use_gains=False):
         """Sampling-rate sweep x Monte-Carlo seeds (BASELINE configs[1]; run_kalman_filter_scheduled
         with selection_method='greedy', kf_workers.py:826-957, for many seeds at once).
 
@@ -349,7 +404,9 @@ class Engine:
         only part of the GPU, so with concurrent=True every rate runs on its own stream (and its own
         model object: the per-model scratch is not shared between in-flight launches).  Returns
         {rate: dict(sel, times, x, P, agg, traj)}; `sels={rate: sel}` skips the selection pass (further
-        batches of seeds over the same stream)."""
+        batches of seeds over the same stream).  With use_gains (and an axis-symmetric P0) the selection pass
+        also publishes the selected events' gains, and each rate's batch runs as a pure stream
+        (b200kf_run_gains) with no covariance recursion in the launch."""
         torch = _torch()
         sp = self.spec
         rates = list(rates)
@@ -358,11 +415,15 @@ class Engine:
         pay_d = self._dev(payload, self.real)
         N = int(pay_d.shape[2])
         P0 = np.asarray(P0, dtype=np.float64)
+        recs = P_fin = None
         if sels is None:  # pass the `sel` arrays of an earlier call to reuse them: they depend on (events, rates, P0) only
-            sels, _ = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
-                                         np.repeat(P0[None], len(rates), axis=0))
+            sels, P_fin, recs = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
+                                                   np.repeat(P0[None], len(rates), axis=0), want_gains=True,
+                                                   _alloc_gains=use_gains)
         else:
             sels = [np.asarray(sels[f]) for f in rates]
+        if recs is not None and (N * (4 if sp.precision == "f32" else 8)) % 16 != 0:
+            recs = None  # bulk-copy rows need 16-byte alignment: odd batches take the recursion-per-launch path
         x0_d = self._dev(x0, self.real)
         P0_d = self._dev(np.repeat(P0[None], N, axis=0), self.real)
         engines = [self]
@@ -389,8 +450,13 @@ class Engine:
                 sel_d = torch.from_numpy(sel.astype(np.int64)).to(self.device)
                 st = times_d.index_select(0, sel_d)
                 dts = torch.diff(st, prepend=torch.tensor([t_prev], dtype=torch.float64, device=self.device))
-                r = eng.run_batch(types_d.index_select(0, sel_d), dts, pay_d.index_select(0, sel_d).contiguous(),
-                                  x0_d, P0_d, traj_ncomp=traj_ncomp, mode=mode, stream=st_)
+                rows = sel_d.to(torch.int32)  # the kernels read the selected rows in place: no gathered payload copy
+                if recs is not None:  # the selection pass already walked this covariance recursion: pure stream
+                    r = eng.run_gains(recs[i, :len(sel)], pay_d, x0_d, traj_ncomp=traj_ncomp, stream=st_, step_rows=rows)
+                    r["P"] = P_fin[i].to(self.real).expand(N, sp.n, sp.n)
+                else:
+                    r = eng.run_batch(types_d.index_select(0, sel_d), dts, pay_d, x0_d, P0_d, traj_ncomp=traj_ncomp,
+                                      mode=mode, stream=st_, step_rows=rows)
             r["sel"] = sel
             r["times"] = st
             out[f] = r

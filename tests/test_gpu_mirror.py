@@ -230,7 +230,7 @@ def test_rate_sweep_x_monte_carlo_seeds(golden):
     base = arrays_to_events(g["ev_type"], g["ev_time"], g["ev_data"])[3:260]
     assert base[0][1] == "GPS"
     rng = np.random.default_rng(4)
-    seeds, rates = 5, [20, 50, 120]
+    seeds, rates = 6, [20, 50, 120]
     ps = streams.PackedStream.from_events(base)
     noise = rng.normal(0, 0.05, (len(base), 9, seeds))
     noise[ps.types == 0, 3:, :] = 0.0
@@ -239,17 +239,28 @@ def test_rate_sweep_x_monte_carlo_seeds(golden):
     x0 = np.zeros((seeds, 15))
     x0[:, :3] = pay[0, :3, :].T
     eng = Engine("CA15")
-    out = eng.scheduled_sweep(ps.types[1:], ps.times[1:], pay[1:], rates, x0, m.P0(), float(ps.times[0]))
+    refs = {}
     for f in rates:
         for sd in range(seeds):
             ev = arrays_to_events(ps.types, ps.times, pay[:, :, sd])
-            st, ld, P = ko.run_scheduled(m, ev, f, 0, len(ev))
+            refs[f, sd] = ko.run_scheduled(m, ev, f, 0, len(ev))
+    # use_gains: the selection pass publishes the selected events' gains and every rate's batch is a pure
+    # stream (b200kf_run_gains); without, every rate's launch runs the covariance recursion itself
+    for use_gains in (True, False):
+        out = eng.scheduled_sweep(ps.types[1:], ps.times[1:], pay[1:], rates, x0, m.P0(), float(ps.times[0]),
+                                  use_gains=use_gains, traj_ncomp=6)
+        for f in rates:
             r = out[f]
-            assert len(st) - 1 == len(r["sel"])
-            np.testing.assert_array_equal(np.array([s[0] for s in st[1:]]), r["times"].cpu().numpy())
-            close(r["P"][sd].cpu().numpy(), P)
-            close(r["x"][sd, :6].cpu().numpy(), np.array(st[-1][1:], dtype=float))
-            assert abs(r["agg"][sd, 2].item() - ld[-1]) < 1e-9 * max(1.0, abs(ld[-1]))
+            for sd in range(seeds):
+                st, ld, P = refs[f, sd]
+                assert len(st) - 1 == len(r["sel"])
+                np.testing.assert_array_equal(np.array([s[0] for s in st[1:]]), r["times"].cpu().numpy())
+                close(r["P"][sd].cpu().numpy(), P)
+                close(r["x"][sd, :6].cpu().numpy(), np.array(st[-1][1:], dtype=float))
+                close(r["traj"][:, :, sd].cpu().numpy(), states_arr(st)[1:, 1:])
+                assert abs(r["agg"][sd, 2].item() - ld[-1]) < 1e-9 * max(1.0, abs(ld[-1]))
+                assert abs(r["agg"][sd, 1].item() - sum(ld[1:])) < 1e-9 * max(1.0, abs(sum(ld[1:])))
+                assert abs(r["agg"][sd, 0].item() - max(ld[1:])) < 1e-9 * max(1.0, abs(max(ld[1:])))
 
 
 def test_window_experiment_matches_reference_rows(golden):

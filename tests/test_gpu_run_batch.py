@@ -353,3 +353,29 @@ def test_zero_measurement_variance_stays_exact():
         assert rel(out["x"].cpu().numpy(), refp["x"]) < RTOL64
         # P has exact-zero velocity variance after an IMU event: compare absolutely on the scale of P0
         assert np.max(np.abs(out["P"].cpu().numpy() - refp["P"])) < 1e-9 * np.max(np.abs(refp["P"]) + 1.0)
+
+
+@pytest.mark.parametrize("name,N", [("CV6", 2000), ("CV6", 33), ("CA15", 2000), ("BIAS9", 900)])
+def test_step_rows_reads_a_selection_in_place(name, N, monkeypatch):
+    """b200kf_run_batch_rows: step k reads payload row step_rows[k] of a longer stream (what the scheduled
+    filter does with its selected events).  Same bits as a launch on the gathered copy, on every kernel family
+    (ring / LDG, per-filter and shared covariance) and for the precomputed-gain path."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    E, T = 120, 47
+    m, types_all, dts_all, payload, x0, P0 = make_case(name, N, E, seed=71)
+    rng = np.random.default_rng(5)
+    rows = np.sort(rng.choice(E, T, replace=False)).astype(np.int32)
+    types, dts = types_all[rows], dts_all[:T]
+    for shared in ("1", "0"):
+        monkeypatch.setenv("B200KF_SHARED", shared)
+        eng = Engine(name)
+        a = eng.run_batch(types, dts, payload[rows], x0, P0, traj_ncomp=m.n)
+        b = eng.run_batch(types, dts, payload, x0, P0, traj_ncomp=m.n, step_rows=rows)
+        c = eng.run_batch(types, dts, payload, x0, P0, step_rows=rows)  # aggregate-only kernels
+        d = eng.run_batch(types, dts, payload[rows], x0, P0)
+        for k in ("x", "P", "agg", "traj"):
+            np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy())
+        for k in ("x", "P", "agg"):
+            np.testing.assert_array_equal(c[k].cpu().numpy(), d[k].cpu().numpy())
+    ref = ko.run_batch(m, types, dts, payload[rows], x0, P0, want_traj=False)
+    assert rel(b["x"].cpu().numpy(), ref["x"]) < RTOL64
