@@ -310,7 +310,7 @@ class Engine:
         return int(n.value)
 
     def select_greedy(self, types, times, periods, t_prev, P0, *, max_sel=None, mode="auto", stream=None,
-                      want_gains=False, _alloc_gains=True):
+                      want_gains=False):
         """Greedy one-event-per-window selection (b200kf_select_greedy) for I instances over one
         event list.  Returns (list of int32 numpy index arrays, P_final torch [I,n,n]); with
         want_gains=True a third item: the selected events' gain records, torch uint8 [I, max_sel, bytes]
@@ -340,7 +340,7 @@ class Engine:
         n_sel = torch.zeros((I,), dtype=torch.int64, device=self.device)
         P_f = torch.empty((I, sp.n, sp.n), dtype=torch.float64, device=self.device)
         recs = None
-        if want_gains and _alloc_gains and mode == "symmetric":
+        if want_gains and mode == "symmetric":
             recs = torch.empty((I, max_sel, self.gain_record_bytes()), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200kf_select_greedy_gains(
@@ -417,9 +417,9 @@ class Engine:
         P0 = np.asarray(P0, dtype=np.float64)
         recs = P_fin = None
         if sels is None:  # pass the `sel` arrays of an earlier call to reuse them: they depend on (events, rates, P0) only
-            sels, P_fin, recs = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
-                                                   np.repeat(P0[None], len(rates), axis=0), want_gains=True,
-                                                   _alloc_gains=use_gains)
+            got = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
+                                     np.repeat(P0[None], len(rates), axis=0), want_gains=use_gains)
+            sels, P_fin, recs = got if use_gains else (got[0], got[1], None)
         else:
             sels = [np.asarray(sels[f]) for f in rates]
         if recs is not None and (N * (4 if sp.precision == "f32" else 8)) % 16 != 0:
