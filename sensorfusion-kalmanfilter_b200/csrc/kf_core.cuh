@@ -52,7 +52,11 @@ __device__ __forceinline__ double fast_rcp(double a) {  // a normal and > 0; ~1 
   x = fma(x, e, x);
   return x;
 }
-__device__ __forceinline__ float fast_rcp(float a) { return 1.0f / a; }
+__device__ __forceinline__ float fast_rcp(float a) {  // a normal and > 0; one Newton step on the hardware seed
+  float x;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
+  return fmaf(x, fmaf(-a, x, 1.0f), x);
+}
 // one cubically convergent step x (1 + e + e^2), e = 1 - a x: error e0^3 from the hardware seed
 // (e0 <= 2^-20 -> below 2^-59) with 3 FMAs instead of the 4 of two Newton steps
 __device__ __forceinline__ double fast_rcp3(double a) {
@@ -61,7 +65,30 @@ __device__ __forceinline__ double fast_rcp3(double a) {
   const double e = fma(-a, x, 1.0);
   return fma(x, fma(e, e, e), x);
 }
-__device__ __forceinline__ float fast_rcp3(float a) { return 1.0f / a; }
+__device__ __forceinline__ float fast_rcp3(float a) { return fast_rcp(a); }
+
+// Per-step record of the ring kernels' packed schedule, in the arithmetic type of the launch (the
+// constants are evaluated in float64 and rounded once, by pack_schedule_kernel): (dt, type) for every
+// kernel, plus the warp-uniform constants of Sym2Filter::step_lean.  Sizes are multiples of 16 bytes
+// (bulk copies).
+template <typename real>
+struct LeanRecT;
+template <>
+struct alignas(16) LeanRecT<double> {  // 64 bytes
+  double dt, dt2;
+  double kap;   // dt sqrt(r1 / r0)
+  double lam;   // IMU: dt sqrt(r0 / r1)       GPS: sqrt(r1 / r0)
+  double kdt;   // IMU: kap dt                 GPS: r_gps / r0
+  double phi0;  // q0 dt / r0
+  double phi1;  // q1 dt / r1
+  int type;
+  int pad;
+};
+template <>
+struct alignas(16) LeanRecT<float> {  // 32 bytes, same fields
+  float dt, dt2, kap, lam, kdt, phi0, phi1;
+  int type;
+};
 
 // inv[i] = 1 / d[i] from ONE reciprocal; returns 1 / prod(d)
 template <int K>
@@ -1391,16 +1418,7 @@ struct Sym2Filter {
   // multiplicity are restored once at the end of the launch.
   static constexpr bool lean_ok =
       (B0::zk(0) == ZK_POS && B0::zk(1) == ZK_VEL && B0::pz(0) == B0::pz(1) && B0::gps(0) >= 0);
-  struct LeanRec {  // 64 bytes, warp-uniform
-    double dt, dt2;
-    double kap;   // dt sqrt(r1 / r0)
-    double lam;   // IMU: dt sqrt(r0 / r1)       GPS: sqrt(r1 / r0)
-    double kdt;   // IMU: kap dt                 GPS: r_gps / r0
-    double phi0;  // q0 dt / r0
-    double phi1;  // q1 dt / r1
-    int type;
-    int pad;
-  };
+  using LeanRec = LeanRecT<real>;  // warp-uniform
   __device__ __forceinline__ void to_normalized(const ModelConst& mc) {
     const double r0 = mc.r_imu[B0::gidx(0)], r1 = mc.r_imu[B0::gidx(1)];
     a = real(double(a) / r0);
@@ -1536,12 +1554,7 @@ struct Sym3CtrlFilter {
   real x0[M], x1[M], x2[M];
   real r0r1;  // unused scale of the lean aggregate (v is the chain determinant itself)
 
-  struct LeanRec {  // same 64 bytes as the step record of the launch; only (dt, dt^2, type) are read
-    double dt, dt2;
-    double unused[5];
-    int type;
-    int pad;
-  };
+  using LeanRec = LeanRecT<real>;  // only (dt, dt^2, type) are read
   template <class F>
   __device__ __forceinline__ static void members(F&& fn) {
     int m = 0;

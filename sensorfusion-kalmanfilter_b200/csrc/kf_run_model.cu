@@ -211,13 +211,26 @@ constexpr int kWsThreads = kTmaThreads + 32;  // + the producer warp (928 * 64 r
 #endif
 constexpr int kChunk = B200KF_CHUNK;    // steps per stage
 constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 KB of shared memory)
+// The ring has to hold the bytes in flight that cover HBM latency (~45 KB per SM at the copy peak), so
+// the per-filter ring kernel keeps the same BYTES in float32 as in float64: twice the steps per stage.
+#ifndef B200KF_F32_CHUNK
+#define B200KF_F32_CHUNK (2 * B200KF_CHUNK)
+#endif
+#ifndef B200KF_F32_STAGES
+#define B200KF_F32_STAGES B200KF_STAGES
+#endif
+template <typename real>
+constexpr int ring_chunk() {
+  return sizeof(real) == 4 ? B200KF_F32_CHUNK : kChunk;
+}
+template <typename real, int F>
+constexpr int ring_stages() {
+  return (sizeof(real) == 4 ? B200KF_F32_STAGES : kStages) * (896 / F);
+}
 
-struct SchedRec {  // 64 bytes (bulk copies need 16-byte granularity); layout of Sym2Filter::LeanRec:
-  double dt, dt2;  // only (dt, type) are read outside the lean symmetric loop
-  double kap, lam, kdt, phi0, phi1;
-  int type;
-  int pad;
-};
+// step record of the ring: LeanRecT<real> (64 bytes in float64, 32 in float32; only (dt, type) are read
+// outside the lean symmetric loop)
+using SchedRec = LeanRecT<double>;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return static_cast<unsigned>(__cvta_generic_to_shared(p));
@@ -259,23 +272,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 struct LeanConst {
   double q0, q1, r0, r1, rg;
 };
+template <typename real>
 static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, const double* __restrict__ dts,
-                                            int T, LeanConst lc, SchedRec* __restrict__ out) {
+                                            int T, LeanConst lc, LeanRecT<real>* __restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= T) return;
   const double dt = dts[k];
   const int ty = types[k];
   const double s10 = sqrt(lc.r1 / lc.r0), s01 = sqrt(lc.r0 / lc.r1);
-  SchedRec r;
-  r.dt = dt;
-  r.dt2 = dt * dt;
-  r.kap = dt * s10;
-  r.lam = (ty == EV_GPS) ? s10 : dt * s01;
-  r.kdt = (ty == EV_GPS) ? lc.rg / lc.r0 : r.kap * dt;
-  r.phi0 = lc.q0 * dt / lc.r0;
-  r.phi1 = lc.q1 * dt / lc.r1;
+  const double kap = dt * s10;
+  LeanRecT<real> r{};
+  r.dt = real(dt);
+  r.dt2 = real(dt * dt);
+  r.kap = real(kap);
+  r.lam = real((ty == EV_GPS) ? s10 : dt * s01);
+  r.kdt = real((ty == EV_GPS) ? lc.rg / lc.r0 : kap * dt);
+  r.phi0 = real(lc.q0 * dt / lc.r0);
+  r.phi1 = real(lc.q1 * dt / lc.r1);
   r.type = ty;
-  r.pad = 0;
   out[k] = r;
 }
 
@@ -298,11 +312,14 @@ template <typename real, int D, int F, int ST, int CH, class AuxRec = SchedRec>
 __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long long* full, unsigned long long* empty,
                                                const real* pay, long long N, int T, unsigned row_bytes,
                                                AuxRec* sched_buf = nullptr, const AuxRec* sched = nullptr,
-                                               const int* __restrict__ step_rows = nullptr) {
+                                               const int* __restrict__ step_rows = nullptr, int first_chunk = 0,
+                                               int chunk_stride = 1) {
+  // several copy lanes (one per warp, on different schedulers) may share the ring: lane w of W takes the
+  // chunks congruent to w modulo W; the barriers do not care who fills a stage
   static_assert(sizeof(AuxRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
   constexpr size_t kStageReals = static_cast<size_t>(CH) * D * F;
   const int nchunks = (T + CH - 1) / CH;
-  for (int chunk = 0; chunk < nchunks; ++chunk) {
+  for (int chunk = first_chunk; chunk < nchunks; chunk += chunk_stride) {
     const int s = chunk % ST;
     if (chunk >= ST) mbar_wait(&empty[s], static_cast<unsigned>(chunk / ST - 1) & 1u);
     const int k0 = chunk * CH;
@@ -311,21 +328,39 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
     mbar_expect_tx(&full[s], static_cast<unsigned>(steps) * D * row_bytes + rec_bytes);
     if (sched != nullptr) bulk_g2s(sched_buf + s * CH, sched + k0, rec_bytes, &full[s]);
     real* dst = stage_buf + s * kStageReals;
-    for (int c = 0; c < steps; ++c) {
-      const long long row = step_row(step_rows, k0 + c);
+    if (step_rows == nullptr) {  // consecutive rows: one running pointer for the steps * D copies of the chunk
+      const real* src = pay + static_cast<long long>(k0) * D * N;
+      for (int r = 0; r < steps * D; ++r, src += N, dst += F) bulk_g2s(dst, src, row_bytes, &full[s]);
+    } else {
+      for (int c = 0; c < steps; ++c) {
+        const long long row = step_rows[k0 + c];
 #pragma unroll
-      for (int j = 0; j < D; ++j) bulk_g2s(dst + (c * D + j) * F, pay + (row * D + j) * N, row_bytes, &full[s]);
+        for (int j = 0; j < D; ++j) bulk_g2s(dst + (c * D + j) * F, pay + (row * D + j) * N, row_bytes, &full[s]);
+      }
     }
   }
 }
 
+// copy warps of the per-filter ring kernel: one per scheduler, so the copy lanes' issue slots (about 15
+// instructions per bulk copy, each waiting its turn behind seven math warps) come off four schedulers
+// instead of one; with a single copy warp the float32 loop (two copies per 100 issue cycles and warp) ran
+// the ring dry 18 % of the time (profiles/r01c_ncu_f32.txt)
+#ifndef B200KF_COPY_WARPS
+#define B200KF_COPY_WARPS 4
+#endif
+constexpr int kCopyWarps = B200KF_COPY_WARPS;
+
 template <int MODEL, typename real, bool SYM, bool FULL, int F>
-__global__ void __launch_bounds__(F + 32, 1)
-    kf_run_tma_kernel(const RunParams p, const SchedRec* __restrict__ sched) {
+__global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
+    kf_run_tma_kernel(const RunParams p, const LeanRecT<real>* __restrict__ sched) {
   // F math threads (filters) per CTA: 896 fills an SM with one CTA; 448 / 224 keep every SM busy when a
   // GPU's shard is small (N <= 148 * 448), with a proportionally deeper ring in the same shared memory
   constexpr int kTmaThreads = F;
-  constexpr int kStages = b200kf::kStages * (896 / F);
+  constexpr int kStages = ring_stages<real, F>();
+  constexpr int kChunk = ring_chunk<real>();
+  // a copy lane waits on a stage's empty barrier by phase PARITY: that is only unambiguous while it can
+  // never be two uses of a stage ahead, i.e. while its stride (kCopyWarps chunks) is within one ring turn
+  static_assert(kStages >= kCopyWarps, "ring shallower than the copy lanes' stride");
   using MT = ModelTraits<MODEL, false, real>;
   using Flt = typename TmaFlt<MODEL, real, SYM>::type;
   constexpr int n = MT::n;
@@ -336,7 +371,8 @@ __global__ void __launch_bounds__(F + 32, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kStages][kChunk][D][kTmaThreads]
   constexpr size_t kStageReals = static_cast<size_t>(kChunk) * D * kTmaThreads;
-  SchedRec* sched_buf = reinterpret_cast<SchedRec*>(stage_buf + kStages * kStageReals);  // [kStages][kChunk]
+  using Rec = LeanRecT<real>;
+  Rec* sched_buf = reinterpret_cast<Rec*>(stage_buf + kStages * kStageReals);  // [kStages][kChunk]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(sched_buf + kStages * kChunk);
   unsigned long long* empty = full + kStages;
 
@@ -359,10 +395,12 @@ __global__ void __launch_bounds__(F + 32, 1)
   __syncthreads();
 
   if (tid >= kTmaThreads) {
-    // ---- producer warp: one lane keeps the ring full, decoupled from the math warps' progress ----
-    if (tid == kTmaThreads)
-      ring_copy_loop<real, D, F, kStages, kChunk>(stage_buf, full, empty, static_cast<const real*>(p.payload) + base, N, T,
-                                                  static_cast<unsigned>(nfb * sizeof(real)), sched_buf, sched, p.step_rows);
+    // ---- copy warps: one lane each keeps the ring full, decoupled from the math warps' progress ----
+    if (((tid - kTmaThreads) & 31) == 0)
+      ring_copy_loop<real, D, F, kStages, kChunk, Rec>(stage_buf, full, empty,
+                                                       static_cast<const real*>(p.payload) + base, N, T,
+                                                       static_cast<unsigned>(nfb * sizeof(real)), sched_buf, sched,
+                                                       p.step_rows, (tid - kTmaThreads) >> 5, kCopyWarps);
     return;
   }
 
@@ -380,9 +418,17 @@ __global__ void __launch_bounds__(F + 32, 1)
   // constant and the chain multiplicity are restored after the loop; validity (every det finite
   // and > 0) is tracked with integer min / max of the raw bits instead of an FP64 compare
   constexpr bool LEAN = SYM && !FULL && Flt::lean_ok;
-  int lean_sign = 0;  // sticky sign bit of every det seen (a zero det zeroes acc_mant; NaN / inf show in the max)
+  // float32 launches keep the lean aggregate in float32 too (no conversion, no FP64 in the loop): the
+  // running product's mantissa picks up <= 2^-24 relative per step, i.e. <= T 2^-24 absolute on a sum of
+  // T logarithms
+  constexpr bool LEAN32 = LEAN && sizeof(real) == 4;
+  // validity of the lean aggregate: integer min / max of the raw bits (a determinant <= 0 has a high word
+  // <= 0, NaN / inf exceed the largest finite pattern).  The running product is renormalised every step by
+  // masking its exponent field; the biased exponents are summed and the bias removed after the loop.
+  int min_hi = 0x7ff00000;
+  float mant32 = 1.0f;
+  int max32 = 0;
   if constexpr (LEAN) {
-    static_assert(sizeof(SchedRec) == sizeof(typename Flt::LeanRec), "SchedRec must mirror LeanRec");
     if (active && T > 0) flt.to_normalized(p.mc);
   }
 
@@ -394,53 +440,64 @@ __global__ void __launch_bounds__(F + 32, 1)
     const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
     if (active) {
       const real* sb = stage_buf + s * kStageReals + tid;
+      auto do_step = [&](int c) {
+        const Rec& rec = sched_buf[s * kChunk + c];
+        real u[D];
 #pragma unroll
-      for (int c = 0; c < kChunk; ++c) {
-        if (c < steps) {
-          const SchedRec rec = sched_buf[s * kChunk + c];
-          real u[D];
-#pragma unroll
-          for (int j = 0; j < D; ++j) u[j] = sb[(c * D + j) * kTmaThreads];
-          const real dt = static_cast<real>(rec.dt);
-          const int ty = rec.type;
-          if constexpr (LEAN) {
-            real v;
-            flt.step_lean(*reinterpret_cast<const typename Flt::LeanRec*>(&sched_buf[s * kChunk + c]), p.mc, u, v);
-            lean_sign |= __double2hiint(double(v));
+        for (int j = 0; j < D; ++j) u[j] = sb[(c * D + j) * kTmaThreads];
+        if constexpr (LEAN) {
+          real v;
+          flt.step_lean(rec, p.mc, u, v);
+          if constexpr (LEAN32) {
+            const int vb = __float_as_int(v);
+            max32 = max(max32, vb);
+            min_hi = min(min_hi, vb);
+            const unsigned mb = __float_as_uint(mant32 * v);
+            acc_expo += static_cast<int>(mb >> 23);
+            mant32 = __uint_as_float((mb & 0x007fffffu) | 0x3f800000u);
+          } else {
+            min_hi = min(min_hi, __double2hiint(double(v)));
             acc_max = max(acc_max, __double_as_longlong(double(v)));
             const double m = acc_mant * double(v);
-            const int hi = __double2hiint(m);
-            const int e = ((hi >> 20) & 0x7ff) - 1023;
-            acc_expo += e;
-            acc_mant = __hiloint2double(hi - (e << 20), __double2loint(m));
-            continue;
+            const unsigned hi = static_cast<unsigned>(__double2hiint(m));
+            acc_expo += static_cast<int>(hi >> 20);
+            acc_mant = __hiloint2double(static_cast<int>((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(m));
           }
-          flt.predict(dt, p.mc);
-          bool do_update = (ty != EV_PREDICT_ONLY);
-          if constexpr (FULL) {
-            if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > p.gate_threshold);  // :1023-1025
-          }
-          const double det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
-          if constexpr (FULL) {
-            const long long k = k0 + c;
-            if (p.traj != nullptr) {
-              real* tr = static_cast<real*>(p.traj) + (k * p.traj_ncomp) * N + f;
-              const int nc = p.traj_ncomp;
-              flt.for_each_state([&](auto G, real v) {
-                constexpr int g = G;
-                if (g < nc) __stcs(tr + static_cast<long long>(g) * N, v);
-              });
-            }
-            if (p.logdet != nullptr) __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(log(det)));
-            if (p.used != nullptr) p.used[k * N + f] = do_update ? 1 : 0;
-          }
-          acc_max = max(acc_max, __double_as_longlong(det));
-          const double m = acc_mant * det;
-          const int hi = __double2hiint(m);
-          const int e = ((hi >> 20) & 0x7ff) - 1023;
-          acc_expo += e;
-          acc_mant = __hiloint2double(hi - (e << 20), __double2loint(m));
+          return;
         }
+        const real dt = rec.dt;
+        const int ty = rec.type;
+        flt.predict(dt, p.mc);
+        bool do_update = (ty != EV_PREDICT_ONLY);
+        if constexpr (FULL) {
+          if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > p.gate_threshold);  // :1023-1025
+        }
+        const double det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
+        if constexpr (FULL) {
+          const long long k = k0 + c;
+          if (p.traj != nullptr) {
+            real* tr = static_cast<real*>(p.traj) + (k * p.traj_ncomp) * N + f;
+            const int nc = p.traj_ncomp;
+            flt.for_each_state([&](auto G, real v) {
+              constexpr int g = G;
+              if (g < nc) __stcs(tr + static_cast<long long>(g) * N, v);
+            });
+          }
+          if (p.logdet != nullptr) __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(log(det)));
+          if (p.used != nullptr) p.used[k * N + f] = do_update ? 1 : 0;
+        }
+        acc_max = max(acc_max, __double_as_longlong(det));
+        const double m = acc_mant * det;
+        const int hi = __double2hiint(m);
+        const int e = ((hi >> 20) & 0x7ff) - 1023;
+        acc_expo += e;
+        acc_mant = __hiloint2double(hi - (e << 20), __double2loint(m));
+      };
+      if (steps == kChunk) {  // every chunk but the last: no per-step bound check
+#pragma unroll
+        for (int c = 0; c < kChunk; ++c) do_step(c);
+      } else {
+        for (int c = 0; c < steps; ++c) do_step(c);
       }
     }
     __syncwarp();
@@ -450,7 +507,15 @@ __global__ void __launch_bounds__(F + 32, 1)
   if (!active) return;
   if constexpr (LEAN) {
     if (T > 0) {
-      ok = ok && lean_sign >= 0 && acc_mant >= 1.0 && acc_max < 0x7ff0000000000000LL;
+      if constexpr (LEAN32) {
+        ok = ok && min_hi > 0 && max32 < 0x7f800000;
+        acc_mant = double(mant32);
+        acc_max = __double_as_longlong(double(__int_as_float(max32)));
+        acc_expo -= 127 * T;
+      } else {
+        ok = ok && min_hi > 0 && acc_max < 0x7ff0000000000000LL;
+        acc_expo -= 1023 * T;
+      }
       flt.from_normalized(p.mc);
     }
   }
@@ -1072,9 +1137,9 @@ constexpr size_t shared_smem_bytes() {
 template <int MODEL, typename real, int F>
 constexpr size_t tma_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
-  constexpr int st = kStages * (896 / F);
-  return static_cast<size_t>(st) * kChunk * MT::d * F * sizeof(real) +
-         static_cast<size_t>(st) * kChunk * sizeof(SchedRec) + 2 * st * sizeof(unsigned long long);
+  constexpr int st = ring_stages<real, F>(), ch = ring_chunk<real>();
+  return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
+         static_cast<size_t>(st) * ch * sizeof(LeanRecT<real>) + 2 * st * sizeof(unsigned long long);
 }
 
 // filters per CTA of the ring kernels: the largest of {896, 448, 224} that still gives every SM a CTA
@@ -1133,17 +1198,17 @@ constexpr bool tma_sym_eligible() {
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL, int F>
-static cudaError_t launch_tma_f(const RunParams& p, const SchedRec* sched, cudaStream_t st) {
+static cudaError_t launch_tma_f(const RunParams& p, const LeanRecT<real>* sched, cudaStream_t st) {
   constexpr size_t smem = tma_smem_bytes<MODEL, real, F>();
   const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
   cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, FULL, F>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kf_run_tma_kernel<MODEL, real, SYM, FULL, F><<<blocks, F + 32, smem, st>>>(p, sched);
+  kf_run_tma_kernel<MODEL, real, SYM, FULL, F><<<blocks, F + 32 * kCopyWarps, smem, st>>>(p, sched);
   return cudaGetLastError();
 }
 template <int MODEL, typename real, bool SYM, bool FULL>
-static cudaError_t launch_tma_one(const RunParams& p, const SchedRec* sched, int f, cudaStream_t st) {
+static cudaError_t launch_tma_one(const RunParams& p, const LeanRecT<real>* sched, int f, cudaStream_t st) {
   if (f == 896) return launch_tma_f<MODEL, real, SYM, FULL, 896>(p, sched, st);
   if (f == 448) return launch_tma_f<MODEL, real, SYM, FULL, 448>(p, sched, st);
   return launch_tma_f<MODEL, real, SYM, FULL, 224>(p, sched, st);
@@ -1157,7 +1222,7 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     return cudaErrorInvalidValue;
   } else {
     constexpr bool kFast2 = MTl::Filter::fast2;
-    SchedRec* sched = reinterpret_cast<SchedRec*>(sched_scratch(m));
+    LeanRecT<real>* sched = reinterpret_cast<LeanRecT<real>*>(sched_scratch(m));
     LeanConst lc{1.0, 1.0, 1.0, 1.0, 1.0};  // rate constants of the symmetric group (only its lean step reads them)
     if constexpr (kFast2 && ModelTraits<MODEL, false, real>::Sym2::eligible) {
       using G0 = typename ModelTraits<MODEL, false, real>::Sym2::Lead;
@@ -1167,7 +1232,7 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
       lc.r1 = m->mc.r_imu[G0::gidx(1)];
       if constexpr (G0::gps(0) >= 0) lc.rg = m->mc.r_gps[G0::gps(0)];
     }
-    pack_schedule_kernel<<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc, sched);
+    pack_schedule_kernel<real><<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc, sched);
     cudaError_t err = cudaSuccess;
     const int f = pick_ring_f(p.n_filters, m->sm_count, m->ring_f_cap);
     if constexpr (kFast2) {
