@@ -211,21 +211,27 @@ constexpr int kWsThreads = kTmaThreads + 32;  // + the producer warp (928 * 64 r
 #endif
 constexpr int kChunk = B200KF_CHUNK;    // steps per stage
 constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 KB of shared memory)
-// The ring has to hold the bytes in flight that cover HBM latency (~45 KB per SM at the copy peak), so
-// the per-filter ring kernel keeps the same BYTES in float32 as in float64: twice the steps per stage.
-#ifndef B200KF_F32_CHUNK
-#define B200KF_F32_CHUNK (2 * B200KF_CHUNK)
+// Ring shape of the per-filter kernel.  The ring always holds the same BYTES (kStages * kChunk steps of
+// 896 float64 filters, ~215 KB for d = 3): a CTA with fewer filters, or float32 payload, gets
+// proportionally more steps.  Those go into LONGER chunks first (up to B200KF_MAX_CHUNK steps per stage):
+// a chunk costs every warp one mbarrier.try_wait (~90 cycles even when the phase is complete) and the copy
+// lanes one wait + expect_tx, which small CTAs (1.75 warps per scheduler) cannot hide; beyond that, into
+// more stages.
+#ifndef B200KF_MAX_CHUNK
+#define B200KF_MAX_CHUNK 8
 #endif
-#ifndef B200KF_F32_STAGES
-#define B200KF_F32_STAGES B200KF_STAGES
-#endif
-template <typename real>
+template <typename real, int F>
+constexpr int ring_steps() {
+  return kStages * kChunk * (896 / F) * (sizeof(real) == 4 ? 2 : 1);
+}
+template <typename real, int F>
 constexpr int ring_chunk() {
-  return sizeof(real) == 4 ? B200KF_F32_CHUNK : kChunk;
+  constexpr int want = ring_steps<real, F>() / kStages;
+  return want < B200KF_MAX_CHUNK ? want : B200KF_MAX_CHUNK;
 }
 template <typename real, int F>
 constexpr int ring_stages() {
-  return (sizeof(real) == 4 ? B200KF_F32_STAGES : kStages) * (896 / F);
+  return ring_steps<real, F>() / ring_chunk<real, F>();
 }
 
 // step record of the ring: LeanRecT<real> (64 bytes in float64, 32 in float32; only (dt, type) are read
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
   // GPU's shard is small (N <= 148 * 448), with a proportionally deeper ring in the same shared memory
   constexpr int kTmaThreads = F;
   constexpr int kStages = ring_stages<real, F>();
-  constexpr int kChunk = ring_chunk<real>();
+  constexpr int kChunk = ring_chunk<real, F>();
   // a copy lane waits on a stage's empty barrier by phase PARITY: that is only unambiguous while it can
   // never be two uses of a stage ahead, i.e. while its stride (kCopyWarps chunks) is within one ring turn
   static_assert(kStages >= kCopyWarps, "ring shallower than the copy lanes' stride");
@@ -1137,7 +1143,7 @@ constexpr size_t shared_smem_bytes() {
 template <int MODEL, typename real, int F>
 constexpr size_t tma_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
-  constexpr int st = ring_stages<real, F>(), ch = ring_chunk<real>();
+  constexpr int st = ring_stages<real, F>(), ch = ring_chunk<real, F>();
   return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
          static_cast<size_t>(st) * ch * sizeof(LeanRecT<real>) + 2 * st * sizeof(unsigned long long);
 }
