@@ -837,10 +837,22 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
 // and batches started from the reference's fixed P0 (configs[4]) take this path in AUTO mode.
 // ------------------------------------------------------------------------------------------
 template <int MODEL, typename real>
-struct SharedRing {  // ring depth per model: stages * chunk * d rows of 896 reals within ~200 KB
+struct SharedRing {  // ring depth per model: stages * chunk * d rows of 896 float64 within ~200 KB
   static constexpr int d = ModelTraits<MODEL, false, real>::d;
-  static constexpr int chunk = (d >= 8) ? 1 : 2;
+  static constexpr int chunk = ((d >= 8) ? 1 : 2) * (sizeof(real) == 4 ? 2 : 1);  // float32: same bytes, twice the steps
   static constexpr int stages = (d >= 8) ? 3 : (d >= 4 ? 3 : 4);
+  // Smaller CTAs take longer chunks, not more stages (a chunk costs every warp -- the gain warps' serial chain
+  // included -- one mbarrier.try_wait of ~90 cycles).  F = 224 keeps HALF the bytes of the larger CTAs so that
+  // two CTAs fit one SM: launches that small come in groups on concurrent streams (one per sampling rate in
+  // the scheduled sweep, 19 CTAs each), and a second resident CTA per SM keeps them in one wave.
+  template <int F>
+  static constexpr int chunk_for() {
+    return chunk * (F == 896 ? 1 : 2);
+  }
+  template <int F>
+  static constexpr int ctas_per_sm() {
+    return F == 224 ? 2 : 1;
+  }
 };
 
 // the blocks (tags) of a filter type, for "one gain warp per block"
@@ -871,7 +883,8 @@ struct FilterTags<FilterT<real, IC, Bs...>> {
 // the same schedule and P0) and stream in from global memory with the payload: no gain warps, no serial
 // recursion in the launch at all -- the kernel is a pure stream whatever the number of filters.
 template <int MODEL, typename real, bool FULL, int F, bool EXT = false>
-__global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTraits<MODEL, double>::Filter>::count) + 2), 1)
+__global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTraits<MODEL, double>::Filter>::count) + 2),
+                                  SharedRing<MODEL, real>::template ctas_per_sm<F>())
     kf_run_shared_generic_kernel(const RunParams p) {
   constexpr int kMathThreads = F;
   using MT = ModelTraits<MODEL, false, real>;
@@ -886,8 +899,8 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
   constexpr int NG = GainSlots<FltP>::value;
   constexpr int NCOV = GainSlots<FltP>::cov;
   using Rec = GainRecG<NG>;
-  constexpr int kSt = SharedRing<MODEL, real>::stages * (896 / F);
-  constexpr int kCh = SharedRing<MODEL, real>::chunk;
+  constexpr int kSt = SharedRing<MODEL, real>::stages;
+  constexpr int kCh = SharedRing<MODEL, real>::template chunk_for<F>();
   // warp roles after the F / 32 math warps: NB gain warps (one block each), the copy warp, the aggregate warp
   constexpr int NGW = EXT ? 0 : NB;  // gain warps in this launch
   constexpr int kGainBase = kMathThreads, kCopyTid = kMathThreads + 32 * NGW, kAggTid = kCopyTid + 32;
@@ -1126,7 +1139,7 @@ template <int MODEL, typename real, int F>
 constexpr size_t shared_generic_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
   using FltP = typename SymTraits<MODEL, double>::Filter;
-  constexpr int kSt = SharedRing<MODEL, real>::stages * (896 / F), kCh = SharedRing<MODEL, real>::chunk;
+  constexpr int kSt = SharedRing<MODEL, real>::stages, kCh = SharedRing<MODEL, real>::template chunk_for<F>();
   return static_cast<size_t>(kSt) * kCh * MT::d * F * sizeof(real) +
          static_cast<size_t>(kSt) * kCh * sizeof(GainRecG<GainSlots<FltP>::value>) +
          (GainSlots<FltP>::cov + 4) * sizeof(double) + 2 * kSt * sizeof(unsigned long long);
@@ -1434,17 +1447,23 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   }
   // AUTO: decide on the device, no host round trip.  Every candidate kernel is enqueued; the ones
   // whose mode does not match the flags exit at once.
+  // A shared-covariance launch can never be faster than n_steps x (one step of the gain warp's serial recursion,
+  // ~0.23 us); the lean per-filter ring kernels run the same recursion in every thread at ~0.17 us per step
+  // when an SM holds few warps, so shards below the 896-filter CTA regime (measured cross-over ~1e5 filters,
+  // profiles/r01c_small_shards.jsonl) stay per-filter in aggregate mode.
+  const bool small_shard = pick_ring_f(p.n_filters, m->sm_count, m->ring_f_cap) < 896;
+  const bool shared_auto = shared && !(small_shard && !full && (tma_sym || tma3));
   int* flag = dense_flag(m);
   B200KF_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
   B200KF_CUDA_TRY(cudaMemsetAsync(flag + 1, sym ? 0 : 1, sizeof(int), st));
-  B200KF_CUDA_TRY(cudaMemsetAsync(flag + 2, shared ? 0 : 1, sizeof(int), st));
+  B200KF_CUDA_TRY(cudaMemsetAsync(flag + 2, shared_auto ? 0 : 1, sizeof(int), st));
   const int ctpb = 128;
   chain_compat_kernel<MODEL, real>
       <<<static_cast<unsigned>((p.n_filters + ctpb - 1) / ctpb), ctpb, 0, st>>>(
           static_cast<const real*>(p.P), p.n_filters, flag);
   B200KF_CUDA_TRY(cudaGetLastError());
   p.dense_flag = flag;
-  if (shared) B200KF_CUDA_TRY((launch_shared<MODEL, real>(m, p, full, st)));
+  if (shared_auto) B200KF_CUDA_TRY((launch_shared<MODEL, real>(m, p, full, st)));
   if (tma) {
     B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym && tma_sym, true, full, st)));
   } else {

@@ -317,9 +317,11 @@ def test_ring_kernels_at_every_cta_size(N, monkeypatch):
     for name in ("CV6", "BIAS9"):
         m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=51)
         ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
-        for shared in ("1", "0"):
+        # AUTO keeps shards below the 896-filter CTA regime on the per-filter ring kernel: force the
+        # shared-covariance kernel explicitly to cover its small-CTA instantiations too
+        for mode, shared in (("shared", "1"), ("auto", "1"), ("auto", "0")):
             monkeypatch.setenv("B200KF_SHARED", shared)
-            out = Engine(name).run_batch(types, dts, payload, x0, P0)
+            out = Engine(name).run_batch(types, dts, payload, x0, P0, mode=mode)
             assert int(out["status"].sum()) == 0
             assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
             assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
