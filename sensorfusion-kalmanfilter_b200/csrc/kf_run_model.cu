@@ -571,18 +571,28 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
 constexpr int kMathThreads = kTmaThreads;           // 896 consumer threads, one filter each
 constexpr int kSharedThreads = kMathThreads + 64;   // + the gain warp + the copy warp
 
-struct GainRec {  // 56 bytes
-  double dt;
-  double g00, g01, g10, g11;  // IMU: x0 += g00 v + g01 u, x1 = g10 v + g11 u (predict folded in); GPS: (k0, -, k1, -)
-  double logdet;              // log det P of the whole filter after the step (per-step output only)
-  int type;                   // event type actually applied
+template <typename real>
+struct GainRecT {  // 56 bytes in float64, 32 in float32: the gain warp rounds once per step, not every thread
+  real dt;
+  real g00, g01, g10, g11;  // IMU: x0 += g00 v + g01 u, x1 = g10 v + g11 u (predict folded in); GPS: (k0, -, k1, -)
+  real logdet;              // log det P of the whole filter after the step (per-step output only)
+  int type;                 // event type actually applied
   int pad;
 };
 
+// ring shape of the CV6 shared-covariance kernel: 5 stages; float32 and the smaller CTAs take longer chunks
+// (same reasoning as SharedRing / ring_chunk), 224-filter CTAs half the bytes so that two share an SM
+template <typename real, int F>
+constexpr int shared_chunk() {
+  return b200kf::kChunk * (sizeof(real) == 4 ? 2 : 1) * (F == 896 ? 1 : 2);
+}
+
 template <int MODEL, typename real, bool FULL, int F>
-__global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParams p) {
+__global__ void __launch_bounds__(F + 64, F == 224 ? 2 : 1) kf_run_shared_kernel(const RunParams p) {
   constexpr int kMathThreads = F;
-  constexpr int kStages = b200kf::kStages * (896 / F);
+  constexpr int kStages = b200kf::kStages;
+  constexpr int kChunk = shared_chunk<real, F>();
+  using GainRec = GainRecT<real>;
   using MT = ModelTraits<MODEL, false, real>;
   using S2 = typename MT::Sym2;
   using B0 = typename S2::Lead;
@@ -596,6 +606,7 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
   real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kStages][kChunk][D][kMathThreads]
   constexpr size_t kStageReals = static_cast<size_t>(kChunk) * D * kMathThreads;
   GainRec* gain_buf = reinterpret_cast<GainRec*>(stage_buf + kStages * kStageReals);  // [kStages][kChunk]
+  static_assert((kStages * kChunk * sizeof(GainRec)) % 8 == 0, "aggregates behind the records must stay aligned");
   double* fin = reinterpret_cast<double*>(gain_buf + kStages * kChunk);  // a, b, c, max, sum, last, ok
   unsigned long long* full = reinterpret_cast<unsigned long long*>(fin + 8);
   unsigned long long* empty = full + kStages;
@@ -651,7 +662,7 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
             dt_nx = __ldg(p.dts + k0 + cc + 1);
             ty_nx = __ldg(p.types + k0 + cc + 1);
           }
-          GainRec rec;
+          GainRecT<double> rec;
           rec.dt = dt;
           rec.type = ty;
           rec.pad = 0;
@@ -698,7 +709,14 @@ __global__ void __launch_bounds__(F + 64, 1) kf_run_shared_kernel(const RunParam
           if constexpr (FULL) {
             if (p.logdet != nullptr) rec.logdet = log(detM);
           }
-          gain_buf[s * kChunk + cc] = rec;
+          if constexpr (sizeof(real) == 8) {
+            gain_buf[s * kChunk + cc] = rec;
+          } else {
+            GainRec r32;
+            r32.dt = real(rec.dt), r32.g00 = real(rec.g00), r32.g01 = real(rec.g01), r32.g10 = real(rec.g10);
+            r32.g11 = real(rec.g11), r32.logdet = real(rec.logdet), r32.type = rec.type, r32.pad = 0;
+            gain_buf[s * kChunk + cc] = r32;
+          }
         }
         mbar_arrive(&full[s]);  // release: the gain records are visible to whoever sees the phase flip
       }
@@ -1148,9 +1166,11 @@ constexpr size_t shared_generic_smem_bytes() {
 template <int MODEL, typename real, int F>
 constexpr size_t shared_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
-  constexpr int st = kStages * (896 / F);
-  return static_cast<size_t>(st) * kChunk * MT::d * F * sizeof(real) +
-         static_cast<size_t>(st) * kChunk * sizeof(GainRec) + 8 * sizeof(double) + 2 * st * sizeof(unsigned long long);
+  constexpr int st = kStages, ch = shared_chunk<real, F>();
+  // (the gain records are padded to whole doubles so that the aggregates behind them stay 8-byte aligned)
+  return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
+         ((static_cast<size_t>(st) * ch * sizeof(GainRecT<real>) + 7) / 8) * 8 + 8 * sizeof(double) +
+         2 * st * sizeof(unsigned long long);
 }
 
 template <int MODEL, typename real, int F>
