@@ -929,8 +929,11 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
   constexpr size_t kStageReals = static_cast<size_t>(kCh) * D * kMathThreads;
   Rec* gain_buf = reinterpret_cast<Rec*>(stage_buf + kSt * kStageReals);  // [kSt][kCh]
   double* fin = reinterpret_cast<double*>(gain_buf + kSt * kCh);          // cov[NCOV], max, sum, last, ok
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(fin + NCOV + 4);
+  double* pstage = fin + NCOV + 4;                                        // [kSt][kCh][NCOV]: P+ of every step, block after block
+  double* irbuf = pstage + (EXT ? 0 : kSt * kCh * NCOV);                  // [2][NB][kMaxN]: 1 / r per measured column (GPS, IMU)
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(irbuf + (EXT ? 0 : 2 * NB * kMaxN));
   unsigned long long* empty = full + kSt;
+  unsigned long long* pready = empty + kSt;  // the chain warps' covariances of a chunk are staged
 
   const int tid = threadIdx.x;
   const long long N = p.n_filters;
@@ -942,35 +945,98 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
 
   if (tid == 0) {
     for (int s = 0; s < kSt; ++s) {
-      mbar_init(&full[s], 1 + NGW);                    // the copy warp's expect_tx arrival + one arrival per gain warp
-      mbar_init(&empty[s], kMathThreads / 32 + 1);     // the math warps + the aggregate warp
+      // full: the copy warp's expect_tx arrival + the gain warp's (records written); with precomputed records
+      // they arrive with the copy.  empty: the math warps (+ the aggregate warp when it reads the records).
+      mbar_init(&full[s], EXT ? 1 : 2);
+      mbar_init(&empty[s], kMathThreads / 32 + (EXT ? 1 : 0));
+      mbar_init(&pready[s], NB > 0 ? NB : 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (tid >= kAggTid) {
-    // ---------------- aggregate warp: log-det aggregates of the whole filter from the block determinants ----
+    // ---------------- aggregate warp ---------------------------------------------------------------------
     if (tid == kAggTid) {
       LogDetAcc acc;
       bool ok = true;
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int s = chunk % kSt;
-        mbar_wait(&full[s], static_cast<unsigned>(chunk / kSt) & 1u);
-        const int k0 = chunk * kCh;
-        const int steps = (T - k0) < kCh ? (T - k0) : kCh;
-        for (int cc = 0; cc < steps; ++cc) {
-          const Rec* rec = gain_buf + s * kCh + cc;
-          double det = 1.0;
+      if constexpr (EXT) {
+        // precomputed records: log-det aggregates of the whole filter from the block determinants
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+          const int s = chunk % kSt;
+          mbar_wait(&full[s], static_cast<unsigned>(chunk / kSt) & 1u);
+          const int k0 = chunk * kCh;
+          const int steps = (T - k0) < kCh ? (T - k0) : kCh;
+          for (int cc = 0; cc < steps; ++cc) {
+            const Rec* rec = gain_buf + s * kCh + cc;
+            double det = 1.0;
 #pragma unroll
-          for (int k = 0; k < NB; ++k) {
-            const double dk = rec->det[k];
-            ok = ok && (dk > 0.0) && (dk < INFINITY);
-            det *= dk;
+            for (int k = 0; k < NB; ++k) {
+              const double dk = rec->det[k];
+              ok = ok && (dk > 0.0) && (dk < INFINITY);
+              det *= dk;
+            }
+            acc.add(det);
           }
-          acc.add(det);
+          mbar_arrive(&empty[s]);
         }
-        mbar_arrive(&empty[s]);
+      } else {
+        // Gain warp: everything that is NOT on the covariance recursion's serial chain.  The chain warps stage
+        // P+ of every step; this lane turns it into the step's gain record (K = P+ H^T R^-1 per block, block
+        // determinants, their logs for the per-step output) and the launch's log-det aggregates, one chunk
+        // behind the chain.  (With chain and gains on one lane a CA15 step was ~250 dependent instructions,
+        // 0.45-0.5 us, and bound every launch below ~10^5 filters and the float32 launches.)
+        static_for<0, NB>([&](auto Kc) {
+          constexpr int K = Kc;
+          using Blk = typename Tags::template block<K>;
+          Blk::template inv_noise<true>(p.mc, irbuf + K * kMaxN);
+          if constexpr (!CTRL) Blk::template inv_noise<false>(p.mc, irbuf + (NB + K) * kMaxN);
+        });
+        double dt_nx = (T > 0) ? __ldg(p.dts) : 0.0;
+        int ty_nx = (T > 0) ? __ldg(p.types) : 0;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+          const int s = chunk % kSt;
+          mbar_wait(&pready[s], static_cast<unsigned>(chunk / kSt) & 1u);
+          const int k0 = chunk * kCh;
+          const int steps = (T - k0) < kCh ? (T - k0) : kCh;
+          for (int cc = 0; cc < steps; ++cc) {
+            const double dt = dt_nx;
+            const int ty = ty_nx;
+            if (k0 + cc + 1 < T) {
+              dt_nx = __ldg(p.dts + k0 + cc + 1);
+              ty_nx = __ldg(p.types + k0 + cc + 1);
+            }
+            Rec* rec = gain_buf + s * kCh + cc;
+            const double* ps = pstage + (s * kCh + cc) * NCOV;
+            double det = 1.0;
+            static_for<0, NB>([&](auto Kc) {
+              constexpr int K = Kc;
+              using Blk = typename Tags::template block<K>;
+              constexpr int so = Tags::slot_offset(K);
+              constexpr int co = Tags::cov_offset(K);
+              Blk blk;
+#pragma unroll
+              for (int e = 0; e < Blk::NP; ++e) blk.P[e] = ps[co + e];
+              if (ty == EV_GPS) {
+                blk.template extract_gain<true>(irbuf + K * kMaxN, rec->g + so);
+              } else if (ty == EV_IMU) {
+                if constexpr (!CTRL) blk.template extract_gain<false>(irbuf + (NB + K) * kMaxN, rec->g + so);
+              }
+              const double dk = blk.det_total(ok);
+              ok = ok && (dk < INFINITY);
+              rec->det[K] = dk;
+              if constexpr (FULL) {
+                if (p.logdet != nullptr) rec->ldet[K] = log(dk);
+              }
+              det *= dk;
+            });
+            rec->dt = dt;
+            rec->type = ty;
+            rec->pad = 0;
+            acc.add(det);
+          }
+          mbar_arrive(&full[s]);  // release: the records are visible to whoever sees the phase flip
+        }
       }
       fin[NCOV + 0] = (T > 0) ? log(acc.maxdet) : -INFINITY;
       fin[NCOV + 1] = acc.sum_log();
@@ -988,7 +1054,7 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
                                              row_bytes, static_cast<SchedRec*>(nullptr), static_cast<const SchedRec*>(nullptr), p.step_rows);
     }
   } else if (!EXT && tid >= kGainBase) {
-    // ---------------- gain warps: block k's covariance recursion on one lane of warp k --------------
+    // ---------------- chain warps: block k's covariance recursion, and nothing else, on one lane of warp k ----
     const int gw = (tid - kGainBase) >> 5;
     if (((tid - kGainBase) & 31) == 0) {
       static_for<0, NB>([&](auto Kc) {
@@ -999,15 +1065,12 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
         FilterT<double, CTRL, Tag> flt;  // this block alone: blocks never couple
         const real* Pg = static_cast<const real*>(p.P) + base * (n * n);  // this CTA's first filter (all are equal)
         flt.head.load_cov_from(Pg, n);
-        double ir_gps[kMaxN], ir_imu[kMaxN];  // 1 / r per measured column
-        Blk::template inv_noise<true>(p.mc, ir_gps);
-        if constexpr (!CTRL) Blk::template inv_noise<false>(p.mc, ir_imu);
-        constexpr int so = Tags::slot_offset(K);
-        bool ok = true;
+        constexpr int co = Tags::cov_offset(K);
         double dt_nx = (T > 0) ? __ldg(p.dts) : 0.0;  // fetched one step ahead, off the serial chain
         int ty_nx = (T > 0) ? __ldg(p.types) : 0;
         for (int chunk = 0; chunk < nchunks; ++chunk) {
           const int s = chunk % kSt;
+          // the stage's staging area is free once its records were consumed (the gain warp read it before that)
           if (chunk >= kSt) mbar_wait(&empty[s], static_cast<unsigned>(chunk / kSt - 1) & 1u);
           const int k0 = chunk * kCh;
           const int steps = (T - k0) < kCh ? (T - k0) : kCh;
@@ -1018,28 +1081,14 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
               dt_nx = __ldg(p.dts + k0 + cc + 1);
               ty_nx = __ldg(p.types + k0 + cc + 1);
             }
-            Rec* rec = gain_buf + s * kCh + cc;
             filter_predict<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
-            filter_update<false>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
-            if (ty == EV_GPS) {
-              flt.head.template extract_gain<true>(ir_gps, rec->g + so);
-            } else if (ty == EV_IMU) {
-              if constexpr (!CTRL) flt.head.template extract_gain<false>(ir_imu, rec->g + so);
-            }
-            const double det = flt.head.det_total(ok);
-            rec->det[K] = det;
-            if constexpr (FULL) {
-              if (p.logdet != nullptr) rec->ldet[K] = log(det);
-            }
-            if constexpr (K == 0) {
-              rec->dt = dt;
-              rec->type = ty;
-              rec->pad = 0;
-            }
+            filter_update<false, true>(flt, dt, p.mc, ty, static_cast<const double*>(nullptr));
+            double* ps = pstage + (s * kCh + cc) * NCOV + co;
+#pragma unroll
+            for (int e = 0; e < Blk::NP; ++e) ps[e] = flt.head.P[e];
           }
-          mbar_arrive(&full[s]);  // release: this block's part of the records is visible with the phase flip
+          mbar_arrive(&pready[s]);  // release: this block's covariances of the chunk are staged
         }
-        constexpr int co = Tags::cov_offset(K);
 #pragma unroll
         for (int e = 0; e < Blk::NP; ++e) fin[co + e] = flt.head.P[e];
       });
@@ -1160,7 +1209,9 @@ constexpr size_t shared_generic_smem_bytes() {
   constexpr int kSt = SharedRing<MODEL, real>::stages, kCh = SharedRing<MODEL, real>::template chunk_for<F>();
   return static_cast<size_t>(kSt) * kCh * MT::d * F * sizeof(real) +
          static_cast<size_t>(kSt) * kCh * sizeof(GainRecG<GainSlots<FltP>::value>) +
-         (GainSlots<FltP>::cov + 4) * sizeof(double) + 2 * kSt * sizeof(unsigned long long);
+         (GainSlots<FltP>::cov + 4) * sizeof(double) +
+         (static_cast<size_t>(kSt) * kCh * GainSlots<FltP>::cov + 2 * kMaxGainBlocks * kMaxN) * sizeof(double) +
+         3 * kSt * sizeof(unsigned long long);
 }
 
 template <int MODEL, typename real, int F>

@@ -457,7 +457,7 @@ __global__ void select_greedy_kernel(const SelectParams p) {
     const int tys = p.types[pick];
     const double dt = ts - prev;  // :914
     filter_predict<false>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
-    filter_update<false>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
+    filter_update<false, true>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
     prev = ts;
     if (ns < p.max_sel) sel[ns] = static_cast<int>(pick);
     if constexpr (VAR == VAR_SYMMETRIC) {
