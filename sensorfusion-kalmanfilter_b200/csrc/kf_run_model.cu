@@ -844,11 +844,12 @@ __global__ void __launch_bounds__(F + 64, F == 224 ? 2 : 1) kf_run_shared_kernel
 
 // ------------------------------------------------------------------------------------------
 // Shared-covariance kernel for every model (CA15 / CA8 / BIAS9; CV6 keeps the tuned kernel above).
-// Same structure -- copy warp, gain warp, 28 math warps, payload ring -- with the model's generic
-// block engine: the gain warp runs the covariance-only filter of the axis-symmetric form
-// (filter_predict<false> / filter_update<false>, float64) and publishes per step the gain matrix
+// Same structure -- copy warp, covariance recursion on single lanes, 28 math warps, payload ring -- with the
+// model's generic block engine: one CHAIN warp per block runs the covariance-only filter of the
+// axis-symmetric form (filter_predict<false> / filter_update<false, joint>, float64) and stages P+ of
+// every step; the GAIN warp, one chunk behind, publishes per step the gain matrix
 // K = P+ H^T R^-1 of every block (columns of P+ over the measurement variances, exact for selector
-// H and diagonal R) plus the log-det; a math thread predicts its filter's state with the chain
+// H and diagonal R) plus determinants / log-dets and the launch's aggregates; a math thread predicts its filter's state with the chain
 // tables, builds the IMU pseudo-measurement from the predicted state (kf_workers.py:698-706) and
 // applies x += K (z - H x) jointly -- the same update as the stage-by-stage scalar form, in exact
 // arithmetic.  Monte-Carlo seeds of one configuration (BASELINE configs[1]: 4096 seeds per rate)
@@ -907,7 +908,7 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
   constexpr int kMathThreads = F;
   using MT = ModelTraits<MODEL, false, real>;
   using FltX = typename SymTraits<MODEL, real>::Filter;    // math warps: state only
-  using FltP = typename SymTraits<MODEL, double>::Filter;  // gain warps: covariance only, float64
+  using FltP = typename SymTraits<MODEL, double>::Filter;  // chain / gain warps: covariance only, float64
   using Tags = FilterTags<FltP>;
   constexpr int NB = Tags::count;
   static_assert(NB <= kMaxGainBlocks, "too many blocks");
@@ -919,8 +920,9 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
   using Rec = GainRecG<NG>;
   constexpr int kSt = SharedRing<MODEL, real>::stages;
   constexpr int kCh = SharedRing<MODEL, real>::template chunk_for<F>();
-  // warp roles after the F / 32 math warps: NB gain warps (one block each), the copy warp, the aggregate warp
-  constexpr int NGW = EXT ? 0 : NB;  // gain warps in this launch
+  // warp roles after the F / 32 math warps: NB chain warps (one block's covariance recursion each), the copy
+  // warp, and the aggregate warp, which is also the gain warp (gain records from the staged covariances)
+  constexpr int NGW = EXT ? 0 : NB;  // chain warps in this launch
   constexpr int kGainBase = kMathThreads, kCopyTid = kMathThreads + 32 * NGW, kAggTid = kCopyTid + 32;
   if (!mode_selected(p.dense_flag, MODE_SHARED)) return;
 
@@ -1170,7 +1172,7 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
     }
   }
 
-  __syncthreads();  // the gain warps' final covariance and the aggregate warp's results
+  __syncthreads();  // the chain warps' final covariance and the aggregate warp's results
   if (tid >= nfb) return;
   const long long f = base + tid;
   if (T > 0 && !EXT) {  // with external gains the covariance never enters the launch (its producer returns P)
