@@ -92,6 +92,27 @@ def test_run_batch_f32_mode(name):
     assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < RTOL32
 
 
+@pytest.mark.parametrize("name", ["CV6", "BIAS9"])
+def test_f32_lean_aggregate_over_a_long_launch(name):
+    """The float32 ring kernels keep the log-det aggregate in float32 (running mantissa product + integer
+    exponent sum): over 30 000 steps max / sum / last must still agree with the float64 path (itself checked
+    against the oracle above) to the float32 tolerance, with per-filter and with identical covariances."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 64, 30000
+    m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=17)
+    scale = 1.0 + (np.arange(N) % 16) / 16.0
+    for P in (P0 * scale[:, None, None], P0):
+        ref = Engine(name).run_batch(types, dts, payload, x0, P, mode="symmetric")
+        for mode in ("symmetric", "auto"):
+            out = Engine(name, precision="f32").run_batch(types, dts, payload, x0, P, mode=mode)
+            assert int(out["status"].sum()) == 0
+            assert rel(out["x"].cpu().numpy(), ref["x"].cpu().numpy()) < RTOL32
+            assert rel(out["P"].cpu().numpy(), ref["P"].cpu().numpy()) < RTOL32
+            a, b = out["agg"].cpu().numpy(), ref["agg"].cpu().numpy()
+            assert np.max(np.abs(a[:, :3] - b[:, :3]) / np.maximum(1.0, np.abs(b[:, :3]))) < RTOL32
+            assert np.all(a[:, 3] == T)
+
+
 def test_chunked_launches_continue_state_and_aggregates():
     from sensorfusion_kalmanfilter_b200.engine import Engine
     N, T = 33, 240
