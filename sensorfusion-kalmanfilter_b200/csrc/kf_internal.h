@@ -133,6 +133,7 @@ struct SelectParams {
   long long* n_sel;            // DEVICE [I]
   double* P_final;             // DEVICE [I, n, n] or null
   void* gain_recs;             // DEVICE [I, max_sel] gain records of the selected events (axis-symmetric form) or null
+  int lane_stride;             // set by the launcher: 32 = one instance per warp (few instances), 1 = packed
 };
 
 // run_brute_force_kalman_filter (KF_SensorFusion.ipynb:804-954): one event per window queue,

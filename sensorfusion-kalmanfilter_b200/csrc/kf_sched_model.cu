@@ -388,7 +388,12 @@ __global__ void select_greedy_kernel(const SelectParams p) {
   using MT = VariantTraits<MODEL, VAR, double>;
   constexpr bool DENSE = (VAR == VAR_DENSE);
   constexpr int n = MT::n;
-  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  // Instances close their windows at different events, so instances sharing a warp execute the union of their
+  // heavy iterations (12 sampling rates in one warp: a window closes at 99.7 % of the events).  With few
+  // instances each gets a warp of its own (lane_stride = 32) and walks only its own windows.
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt % p.lane_stride != 0) return;
+  const int inst = gt / p.lane_stride;
   if (inst >= p.n_inst) return;
   typename MT::Filter flt;
   flt.each([&](auto& b) { b.load_cov(p.P0 + static_cast<long long>(inst) * n * n, n); });
@@ -410,9 +415,15 @@ __global__ void select_greedy_kernel(const SelectParams p) {
   int* sel = p.sel + static_cast<long long>(inst) * p.max_sel;
   long long ns = 0;
   long long first_gps = -1, first_imu = -1, q_first = -1;  // queue summary
+  double t_nx = (p.n_events > 0) ? __ldg(p.times) : 0.0;  // fetched one event ahead of the serial chain
+  int ty_nx = (p.n_events > 0) ? __ldg(p.types) : 0;
   for (long long e = 0; e < p.n_events; ++e) {
-    const double t = p.times[e];
-    const int ty = p.types[e];
+    const double t = t_nx;
+    const int ty = ty_nx;
+    if (e + 1 < p.n_events) {
+      t_nx = __ldg(p.times + e + 1);
+      ty_nx = __ldg(p.types + e + 1);
+    }
     if (t - prev < period) {  // :880-882
       if (q_first < 0) q_first = e;
       if (ty == EV_GPS) { if (first_gps < 0) first_gps = e; }
@@ -505,11 +516,13 @@ __global__ void select_greedy_kernel(const SelectParams p) {
 }
 
 template <>
-int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams& p, unsigned flags,
+int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams& p_in, unsigned flags,
                                        cudaStream_t st) {
   using SymF = typename SymTraits<B200KF_INST_MODEL, double>::Filter;
   const int tpb = 32;
-  const unsigned blocks = static_cast<unsigned>((p.n_inst + tpb - 1) / tpb);
+  SelectParams p = p_in;
+  p.lane_stride = (p.n_inst <= 2048) ? 32 : 1;
+  const unsigned blocks = static_cast<unsigned>((static_cast<long long>(p.n_inst) * p.lane_stride + tpb - 1) / tpb);
   // P0 lives on the device, so the caller vouches for its structure: FORCE_SYMMETRIC = chain-compatible with
   // identical blocks across the axes of a group (one covariance per group), FORCE_DECOUPLED = chain-compatible;
   // without a flag the dense form, which is always valid

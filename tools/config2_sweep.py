@@ -24,6 +24,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--seeds", type=int, default=4096)
 ap.add_argument("--seconds", type=float, default=60.0)
 ap.add_argument("--no-concurrent", action="store_true")
+ap.add_argument("--use-gains", action="store_true", help="filters apply the gain records of the selection pass")
 a = ap.parse_args()
 rates = list(range(10, 121, 10))
 n_events = int(a.seconds * 210)
@@ -39,7 +40,7 @@ pay = base[:, :, None] + 0.05 * torch.randn((E, 9, a.seeds), generator=g, device
 x0 = np.zeros((a.seeds, 15))
 x0[:, :3] = ps.data[0, :3]
 P0 = eng.spec.default_P0()
-kw = dict(concurrent=not a.no_concurrent)
+kw = dict(concurrent=not a.no_concurrent, use_gains=a.use_gains)
 for _ in range(2):
     out = eng.scheduled_sweep(ps.types[1:], ps.times[1:], pay, rates, x0, P0, float(ps.times[0]), **kw)
 torch.cuda.synchronize()
@@ -51,6 +52,6 @@ torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / reps
 steps = sum(len(out[f]["sel"]) for f in rates) * a.seeds
 print(json.dumps({"config": "rate sweep 10-120 Hz x %d seeds, CA15, greedy scheduling, %.0f s stream (%d events)"
-                  % (a.seeds, a.seconds, E), "concurrent_streams": not a.no_concurrent, "filters": a.seeds * len(rates),
+                  % (a.seeds, a.seconds, E), "concurrent_streams": not a.no_concurrent, "use_gains": a.use_gains, "filters": a.seeds * len(rates),
                   "filter_steps": steps, "wall_s": dt, "filter_steps_per_s": steps / dt,
                   "selected_per_rate": {str(f): int(len(out[f]["sel"])) for f in rates}}))
