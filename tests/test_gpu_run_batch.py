@@ -350,6 +350,25 @@ def test_ring_kernels_at_every_cta_size(N, monkeypatch):
             assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
 
 
+@pytest.mark.parametrize("N", [33152, 40000, 70004])
+def test_ring_kernels_at_every_cta_size_f32(N, monkeypatch):
+    """The float32 instantiations of the same kernels (their rings hold twice the steps per stage, the
+    records and the lean aggregate are float32), against the oracle at the float32 tolerance."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    T = 45
+    for name in ("CV6", "BIAS9"):
+        m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=53)
+        ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
+        for mode, shared in (("shared", "1"), ("auto", "0")):
+            monkeypatch.setenv("B200KF_SHARED", shared)
+            out = Engine(name, precision="f32").run_batch(types, dts, payload, x0, P0, mode=mode)
+            assert int(out["status"].sum()) == 0
+            assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL32
+            assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL32
+            a = out["agg"].cpu().numpy()
+            assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL32
+
+
 def test_zero_measurement_variance_stays_exact():
     """A perfect sensor (r = 0 on the IMU velocity pseudo-measurement): the lean symmetric step and the
     shared-covariance kernels divide by the variances, so such a model must take the scalar-update
