@@ -369,6 +369,27 @@ def test_ring_kernels_at_every_cta_size_f32(N, monkeypatch):
             assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL32
 
 
+@pytest.mark.parametrize("name", ["CA15", "CA8", "CV6"])
+@pytest.mark.parametrize("scale", [1e-8, 1e-3, 1e2])  # (beyond ~1e3 the reference's (I - KH) P itself loses digits)
+def test_shared_covariance_joint_update_over_covariance_scales(name, scale):
+    """The chain warps update a fully measured block jointly (P+ = R S^-1 P through the cofactors of
+    S = P + R).  Covariances far below and far above the measurement variances -- where one or the other
+    term of S dominates -- against the reference formulation (inv(S)) of the oracle."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 64, 120
+    m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=71)
+    P0 = P0 * scale
+    ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
+    out = Engine(name).run_batch(types, dts, payload, x0, P0, mode="shared")
+    assert int(out["status"].sum()) == 0
+    assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
+    P, Pr = out["P"].cpu().numpy(), ref["P"]
+    d = np.sqrt(np.abs(np.einsum("fii->fi", Pr)))
+    assert np.max(np.abs(P - Pr) / (d[:, :, None] * d[:, None, :])) < RTOL64  # entry by entry, in correlation units
+    a = out["agg"].cpu().numpy()
+    assert np.max(np.abs(a[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < RTOL64
+
+
 def test_zero_measurement_variance_stays_exact():
     """A perfect sensor (r = 0 on the IMU velocity pseudo-measurement): the lean symmetric step and the
     shared-covariance kernels divide by the variances, so such a model must take the scalar-update
