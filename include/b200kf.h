@@ -151,6 +151,16 @@ int b200kf_run_batch_rows(const b200kf_model* model, int64_t n_filters, int64_t 
                           int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used, int32_t* status,
                           double gate_threshold, uint32_t flags, void* stream);
 
+/* b200kf_run_batch with ONE GATE THRESHOLD PER FILTER (gate_thresholds: DEVICE f64 [N]; a filter updates
+ * only when log det of its predicted P exceeds its threshold, kf_workers.py:1023-1025).  The reference's
+ * experiment runs the adaptive filter from the start of the stream once per window, each with its own
+ * R_threshold (kf_workers.py:2316): filters with different thresholds share one launch here. */
+int b200kf_run_batch_gated(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
+                           const uint8_t* types, const double* dts, const void* payload,
+                           const double* gate_thresholds, void* x, void* P, double* agg, void* traj,
+                           int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used, int32_t* status,
+                           uint32_t flags, void* stream);
+
 /* Same computation from HOST buffers (the call a drop-in user makes): streams `payload` to the
  * device in time chunks, overlapping host->device copies with the kernel, and copies x, P, agg
  * back.  Synchronous.  payload/x/P/agg are HOST pointers (pinned memory copies fastest); types

@@ -578,10 +578,34 @@ int b200kf_run_batch(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
                                logdet, used, status, gate_threshold, flags, stream);
 }
 
+static int run_batch_impl(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const uint8_t* types,
+                          const double* dts, const void* payload, const int32_t* step_rows, void* x, void* P,
+                          double* agg, void* traj, int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used,
+                          int32_t* status, double gate_threshold, const double* gate_thresholds, uint32_t flags,
+                          void* stream);
+
 int b200kf_run_batch_rows(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const uint8_t* types,
                           const double* dts, const void* payload, const int32_t* step_rows, void* x, void* P,
                           double* agg, void* traj, int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used,
                           int32_t* status, double gate_threshold, uint32_t flags, void* stream) {
+  return run_batch_impl(m, n_filters, n_steps, types, dts, payload, step_rows, x, P, agg, traj, traj_ncomp, ptraj,
+                        logdet, used, status, gate_threshold, nullptr, flags, stream);
+}
+
+int b200kf_run_batch_gated(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const uint8_t* types,
+                           const double* dts, const void* payload, const double* gate_thresholds, void* x, void* P,
+                           double* agg, void* traj, int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used,
+                           int32_t* status, uint32_t flags, void* stream) {
+  if (!gate_thresholds) return set_error(B200KF_ERR_INVALID, "gate_thresholds is required");
+  return run_batch_impl(m, n_filters, n_steps, types, dts, payload, nullptr, x, P, agg, traj, traj_ncomp, ptraj, logdet,
+                        used, status, 0.0, gate_thresholds, flags, stream);
+}
+
+static int run_batch_impl(const b200kf_model* m, int64_t n_filters, int64_t n_steps, const uint8_t* types,
+                          const double* dts, const void* payload, const int32_t* step_rows, void* x, void* P,
+                          double* agg, void* traj, int32_t traj_ncomp, void* ptraj, void* logdet, uint8_t* used,
+                          int32_t* status, double gate_threshold, const double* gate_thresholds, uint32_t flags,
+                          void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
   if (n_filters < 0 || n_steps < 0) return set_error(B200KF_ERR_INVALID, "negative size");
   if (n_steps > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_steps > 2^31-1 per call");
@@ -610,8 +634,9 @@ int b200kf_run_batch_rows(const b200kf_model* m, int64_t n_filters, int64_t n_st
   p.logdet = logdet;
   p.used = used;
   p.status = status;
-  p.gate_enabled = std::isnan(gate_threshold) ? 0 : 1;
+  p.gate_enabled = (gate_thresholds != nullptr || !std::isnan(gate_threshold)) ? 1 : 0;
   p.gate_threshold = gate_threshold;
+  p.gate_thresholds = gate_thresholds;
   p.agg_continue = (flags & B200KF_RUN_AGG_CONTINUE) ? 1 : 0;
   p.dense_flag = nullptr;
   p.gain_recs = nullptr;
@@ -990,6 +1015,7 @@ int b200kf_run_gains(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
   p.status = status;
   p.gate_enabled = 0;
   p.gate_threshold = 0.0;
+  p.gate_thresholds = nullptr;
   p.agg_continue = (flags & B200KF_RUN_AGG_CONTINUE) ? 1 : 0;
   p.dense_flag = nullptr;
   p.gain_recs = gain_records;

@@ -68,6 +68,7 @@ struct RunParams {
   uint8_t* used;
   int* status;
   double gate_threshold;
+  const double* gate_thresholds;  // DEVICE [N] or null: per-filter thresholds (b200kf_run_batch_gated)
   int gate_enabled;
   int agg_continue;
   const int* dense_flag;  // AUTO mode: int[3] {coupled, asymmetric, P differs between filters}; a kernel runs only if they select its mode

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
     flt.each([&](auto& b) { b.load(xg, Pg, n); });
   }
 
+  const double gate = (FULL && p.gate_thresholds != nullptr) ? p.gate_thresholds[f] : p.gate_threshold;
   double rprod = 1.0;
   if constexpr (FAST) rprod = fast2_rprod(flt, p.mc);
   // lean running aggregate: mantissa product + exponent sum + max; "last" is recomputed from the
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
         if constexpr (FULL) {
           if (p.gate_enabled) {  // kf_workers.py:1023-1025
             const double dpre = filter_det(flt, ok);
-            do_update = do_update && (log(dpre) > p.gate_threshold);
+            do_update = do_update && (log(dpre) > gate);
           }
         }
         double det;
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
     const real* Pg = static_cast<const real*>(p.P) + f * (n * n);
     flt.load(xg, Pg, n, p.mc);
   }
+  const double gate = (FULL && active && p.gate_thresholds != nullptr) ? p.gate_thresholds[f] : p.gate_threshold;
   double acc_mant = 1.0;
   long long acc_max = 0;  // max det as raw bits: positive doubles order like their bit patterns
   int acc_expo = 0;
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
         flt.predict(dt, p.mc);
         bool do_update = (ty != EV_PREDICT_ONLY);
         if constexpr (FULL) {
-          if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > p.gate_threshold);  // :1023-1025
+          if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > gate);  // :1023-1025
         }
         const double det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
         if constexpr (FULL) {

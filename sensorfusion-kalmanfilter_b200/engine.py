@@ -122,6 +122,20 @@ class Engine:
         used_d = torch.empty((T, N), dtype=torch.uint8, device=self.device) if want_used else None
         ptraj_d = torch.empty((T, sp.n * sp.n, N), dtype=self.real, device=self.device) if want_ptraj else None
         status_d = torch.zeros((N,), dtype=torch.int32, device=self.device)
+        if gate_threshold is not None and np.ndim(gate_threshold) > 0 or torch.is_tensor(gate_threshold):
+            # one threshold per filter (b200kf_run_batch_gated)
+            if rows_d is not None:
+                raise ValueError("per-filter gate thresholds and step_rows cannot be combined")
+            gates_d = self._dev(gate_threshold, torch.float64)
+            if int(gates_d.numel()) != N:
+                raise ValueError(f"gate_threshold must be a scalar or [N={N}]")
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.b200kf_run_batch_gated(
+                    self._h, N, T, _ptr(types_d), _ptr(dts_d), _ptr(pay_d), _ptr(gates_d), _ptr(x_d), _ptr(P_d),
+                    _ptr(agg_d), _ptr(traj_d), int(traj_ncomp), _ptr(ptraj_d), _ptr(ld_d), _ptr(used_d), _ptr(status_d),
+                    flags, self._stream(stream)))
+            return {"x": x_d, "P": P_d, "agg": agg_d, "traj": traj_d, "logdet": ld_d, "used": used_d,
+                    "ptraj": ptraj_d, "status": status_d}
         gate = float("nan") if gate_threshold is None else float(gate_threshold)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200kf_run_batch_rows(

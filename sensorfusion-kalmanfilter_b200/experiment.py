@@ -46,41 +46,48 @@ class ExperimentLog:
 def adaptive_warmups(sf, end_indices, thresholds):
     """For every (end_idx, R_threshold) pair: (states[-1], P) of
     `sf.run_adaptive_threshold_kalman_filter(end_idx=end_idx, R_threshold=R_threshold)` (:2316),
-    or None where the reference returns None (no GPS before end_idx).  Pairs with the same threshold
-    share one pass over the stream."""
+    or None where the reference returns None (no GPS before end_idx).  The adaptive filter is causal, so
+    ONE pass over the stream serves every pair: one filter per distinct threshold, all in the same launches
+    (b200kf_run_batch_gated: a gate threshold per filter), cut at the requested end indices."""
     ps = streams.pack_events(sf.indexed_sensor_data)
     n_ev = len(sf.indexed_sensor_data)
     out = [None] * len(end_indices)
-    groups = {}
-    for k, (e, thr) in enumerate(zip(end_indices, thresholds)):
-        groups.setdefault(float(thr), []).append((min(int(e), n_ev), k))
-    for thr, reqs in groups.items():
-        reqs.sort()
-        e_max = reqs[-1][0]
-        init = sf._first_gps(0, e_max)
-        if init is None:
+    if not len(end_indices):
+        return out
+    thr_list = sorted({float(t) for t in thresholds})
+    g_of = {t: g for g, t in enumerate(thr_list)}
+    reqs = sorted((min(int(e), n_ev), g_of[float(t)], k) for k, (e, t) in enumerate(zip(end_indices, thresholds)))
+    e_max = reqs[-1][0]
+    init = sf._first_gps(0, e_max)
+    if init is None:
+        return out
+    xt, prev_time, first = init
+    Pt = sf._default_P0().astype(np.float64)
+    keep, dts, _ = streams.schedule_dts(ps.times[first:e_max], prev_time, skip_advances_prev=False)
+    G = len(thr_list)
+    gates = np.array([t if t != -float("inf") else -1.0e300 for t in thr_list])
+    eng = sf._engine()
+    # carried on the device between launches (full 15-state x), one filter per threshold
+    x_d, P_d = np.repeat(xt[None], G, axis=0), np.repeat(Pt[None], G, axis=0)
+    last_time = prev_time
+    done = 0  # events of `keep` already filtered
+    for e, g, k in reqs:
+        if e <= first:  # the window starts before the first GPS fix: the reference finds no GPS (:995-1004)
             continue
-        xt, prev_time, first = init
-        Pt = sf._default_P0().astype(np.float64)
-        keep, dts, _ = streams.schedule_dts(ps.times[first:e_max], prev_time, skip_advances_prev=False)
-        state = (prev_time, *xt[:6])
-        gate = thr if thr != -float("inf") else -1.0e300
-        eng = sf._engine()
-        x_d, P_d = xt[None].copy(), Pt[None].copy()  # carried on the device between launches (full 15-state x)
-        done = 0  # events of `keep` already filtered
-        for e, k in reqs:
-            if e <= first:  # the window starts before the first GPS fix: the reference finds no GPS (:995-1004)
-                continue
-            upto = int(np.searchsorted(keep, e - first, side="left"))
-            if upto > done:
-                idx = first + keep[done:upto]
-                # only the state and covariance at the window start are used (:2316-2323): no per-step outputs
-                r = eng.run_batch(ps.types[idx], dts[done:upto], ps.payload(sf.MODEL_NAME, idx)[:, :, None], x_d, P_d,
-                                  want_agg=False, gate_threshold=gate)
-                x_d, P_d = r["x"], r["P"]
-                state = (float(ps.times[idx[-1]]), *x_d[0, :6].cpu().numpy())
-                done = upto
-            out[k] = (state, P_d[0].cpu().numpy().copy() if not isinstance(P_d, np.ndarray) else P_d[0].copy())
+        upto = int(np.searchsorted(keep, e - first, side="left"))
+        if upto > done:
+            idx = first + keep[done:upto]
+            pay = np.repeat(ps.payload(sf.MODEL_NAME, idx)[:, :, None], G, axis=2)
+            # only the state and covariance at the window start are used (:2316-2323): no per-step outputs
+            r = eng.run_batch(ps.types[idx], dts[done:upto], pay, x_d, P_d, want_agg=False,
+                              gate_threshold=gates if G > 1 else float(gates[0]))
+            x_d, P_d = r["x"], r["P"]
+            last_time = float(ps.times[idx[-1]])
+            done = upto
+        if isinstance(x_d, np.ndarray):
+            out[k] = ((last_time, *x_d[g, :6]), P_d[g].copy())
+        else:
+            out[k] = ((last_time, *x_d[g, :6].cpu().numpy()), P_d[g].cpu().numpy().copy())
     return out
 
 

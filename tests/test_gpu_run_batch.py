@@ -192,6 +192,36 @@ def test_ragged_and_empty_inputs():
         eng.run_batch(types, dts, payload[:, :2], x0, P0)
 
 
+@pytest.mark.parametrize("name", ["CA15", "CV6"])
+def test_one_gate_threshold_per_filter(name):
+    """b200kf_run_batch_gated: filters of one launch with different thresholds (the reference's experiment runs
+    the adaptive filter once per window, each with its own R_threshold, kf_workers.py:2316) equal the same
+    filters launched one threshold at a time, and the oracle."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 12, 220
+    m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=23)
+    eng = Engine(name)
+    full = eng.run_batch(types, dts, payload, x0, P0, want_logdet=True)
+    ld = full["logdet"].cpu().numpy()
+    qs = float(np.median(ld[T // 2:])) + np.array([0.5, 1.0, 2.0, 4.0])  # above the steady state: updates are skipped
+    thr = np.concatenate([np.repeat(qs, 3)[: N - 1], [-1.0e300]])  # the last filter always updates
+    out = eng.run_batch(types, dts, payload, x0, P0, gate_threshold=thr, want_used=True, want_logdet=True)
+    assert int(out["status"].sum()) == 0
+    for f in range(N):
+        one = eng.run_batch(types, dts, payload[:, :, f:f + 1], x0[f:f + 1], P0[f:f + 1], gate_threshold=float(thr[f]),
+                            want_used=True, want_logdet=True)
+        np.testing.assert_array_equal(out["used"].cpu().numpy()[:, f], one["used"].cpu().numpy()[:, 0])
+        assert rel(out["x"].cpu().numpy()[f], one["x"].cpu().numpy()[0]) < RTOL64
+        assert rel(out["P"].cpu().numpy()[f], one["P"].cpu().numpy()[0]) < RTOL64
+    ref = ko.run_batch(m, types, dts, payload[:, :, :1], x0[:1], P0[:1], gate_threshold=float(thr[0]))
+    assert rel(out["x"].cpu().numpy()[0], ref["x"][0]) < RTOL64
+    assert rel(out["P"].cpu().numpy()[0], ref["P"][0]) < RTOL64
+    u = out["used"].cpu().numpy()
+    assert u[:, -1].all() and all(0 < u[:, f].sum() < T for f in range(N - 1))
+    assert len({int(u[:, f].sum()) for f in range(0, N - 1, 3)}) > 1  # different thresholds, different decisions
+    assert rel(out["x"].cpu().numpy()[-1], full["x"].cpu().numpy()[-1]) < RTOL64
+
+
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 def test_tma_staged_kernel_matches_ldg_kernel_and_oracle(precision, monkeypatch):
     """The aggregate-mode CV6 launch uses the TMA-staged persistent kernel (cp.async.bulk + mbarrier
