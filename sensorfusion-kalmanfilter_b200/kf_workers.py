@@ -662,10 +662,9 @@ def find_start_idx_for_time_offset(sensor_fusion, time_offset, t0=1697739552.336
     """First event index whose time is >= t0 + time_offset (the helper the reference's __main__ uses;
     t0 is its hard-coded first-fix epoch, kf_workers.py:1993)."""
     target = t0 + time_offset
-    for i, ev in enumerate(sensor_fusion.indexed_sensor_data):
-        if ev[2] >= target:
-            return i
-    return len(sensor_fusion.indexed_sensor_data)
+    times = streams.pack_events(sensor_fusion.indexed_sensor_data).times  # packed once per stream
+    hit = np.flatnonzero(times >= target)  # the first such event, sorted stream or not (the reference scans)
+    return int(hit[0]) if hit.size else len(times)
 
 
 __all__ = ["KF_SensorFusion", "Scheduler", "evaluate_combo_chunk_worker", "find_start_idx_for_time_offset",
