@@ -440,6 +440,10 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
     if (active && T > 0) flt.to_normalized(p.mc);
   }
 
+  real* tr_run = (FULL && p.traj != nullptr) ? static_cast<real*>(p.traj) + f : nullptr;
+  real* ld_run = (FULL && p.logdet != nullptr) ? static_cast<real*>(p.logdet) + f : nullptr;
+  unsigned char* used_run = (FULL && p.used != nullptr) ? p.used + f : nullptr;
+  const int out_nc = p.traj_ncomp;
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int s = chunk % kStages;
     const unsigned use = static_cast<unsigned>(chunk / kStages);
@@ -482,17 +486,22 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
         }
         const double det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
         if constexpr (FULL) {
-          const long long k = k0 + c;
-          if (p.traj != nullptr) {
-            real* tr = static_cast<real*>(p.traj) + (k * p.traj_ncomp) * N + f;
-            const int nc = p.traj_ncomp;
+          // running output pointers: no reload of the launch parameters and no 64-bit multiply per step
+          if (tr_run != nullptr) {
             flt.for_each_state([&](auto G, real v) {
               constexpr int g = G;
-              if (g < nc) __stcs(tr + static_cast<long long>(g) * N, v);
+              if (g < out_nc) __stcs(tr_run + static_cast<long long>(g) * N, v);
             });
+            tr_run += static_cast<long long>(out_nc) * N;
           }
-          if (p.logdet != nullptr) __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(log(det)));
-          if (p.used != nullptr) p.used[k * N + f] = do_update ? 1 : 0;
+          if (ld_run != nullptr) {
+            __stcs(ld_run, static_cast<real>(log(det)));
+            ld_run += N;
+          }
+          if (used_run != nullptr) {
+            *used_run = do_update ? 1 : 0;
+            used_run += N;
+          }
         }
         acc_max = max(acc_max, __double_as_longlong(det));
         const double m = acc_mant * det;
