@@ -455,7 +455,10 @@ class Engine:
             side = spool[:len(rates)]
         cur = torch.cuda.current_stream(self.device)
         out = {}
-        for i, (f, sel) in enumerate(zip(rates, sels)):
+        # longest schedule first: its launch is the critical path, the host work of the others overlaps it
+        order = sorted(range(len(rates)), key=lambda j: -len(sels[j]))
+        for i in order:
+            f, sel = rates[i], sels[i]
             eng = engines[i] if side else self
             st_ = side[i] if side else cur
             if side:
@@ -476,7 +479,7 @@ class Engine:
             out[f] = r
         for st_ in side:
             cur.wait_stream(st_)
-        return out
+        return {f: out[f] for f in rates}
 
 
 def cov_update(Sigma, rows, H, R, device=None, stream=None):
