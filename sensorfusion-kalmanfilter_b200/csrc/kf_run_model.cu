@@ -1379,6 +1379,10 @@ static cudaError_t launch_shared_f(const RunParams& p, cudaStream_t st) {
     err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, FULL, F>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
+    if constexpr (F == 224) {  // two CTAs per SM need the whole shared-memory carve-out (a hint, not an error if refused)
+      (void)cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, FULL, F>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     kf_run_shared_generic_kernel<MODEL, real, FULL, F>
         <<<blocks, F + 32 * (FilterTags<typename SymTraits<MODEL, double>::Filter>::count + 2), smem, st>>>(p);
   } else {
@@ -1386,6 +1390,10 @@ static cudaError_t launch_shared_f(const RunParams& p, cudaStream_t st) {
     err = cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, FULL, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem));
     if (err != cudaSuccess) return err;
+    if constexpr (F == 224) {
+      (void)cudaFuncSetAttribute(kf_run_shared_kernel<MODEL, real, FULL, F>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+    }
     kf_run_shared_kernel<MODEL, real, FULL, F><<<blocks, F + 64, smem, st>>>(p);
   }
   return cudaGetLastError();
