@@ -1272,15 +1272,18 @@ static bool tma_possible(const b200kf_model* m, const RunParams& p, bool full) {
   }
 }
 
-// BIAS9-like models (control-input chains): the symmetric ring kernel exists for the aggregate-only launch;
-// per-step outputs, the adaptive gate and per-chain covariances stay with the LDG kernels
+// BIAS9-like models (control-input chains): the symmetric ring kernel, with or without per-step outputs;
+// the adaptive gate and per-chain covariances stay with the LDG kernels
 template <int MODEL, typename real>
 static bool tma_sym3_possible(const b200kf_model* m, const RunParams& p, bool full) {
   using MT = ModelTraits<MODEL, false, real>;
   if constexpr (MT::Filter::fast2 || !MT::Sym3::eligible) {
     return false;
   } else {
-    if (full || p.ptraj != nullptr || m->use_tma == 0) return false;
+    // per-step outputs run on the ring too; the adaptive gate does not (this filter applies the control input
+    // inside update(), which a gated step skips) and stays with the LDG kernel
+    (void)full;
+    if (p.gate_enabled || p.ptraj != nullptr || m->use_tma == 0) return false;
     const size_t need = static_cast<size_t>(p.n_steps) * sizeof(SchedRec);
     const long long align_elems = 16 / static_cast<long long>(sizeof(real));
     return p.n_steps >= 1 && need <= sched_capacity(m) && (p.n_filters % align_elems) == 0 &&
