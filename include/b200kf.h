@@ -12,6 +12,10 @@
  *     the call;
  *   - work is enqueued on the caller's stream (a cudaStream_t passed as void*, NULL = default
  *     stream); functions are asynchronous unless stated;
+ *   - a model object may be used from several host threads and on several streams at once: every call takes
+ *     its device scratch (dispatch flags, packed schedules, reduction partials) from the model's stream-ordered
+ *     pool on the caller's stream and returns it behind its last kernel, so concurrent calls share nothing;
+ *     b200kf_run_batch_host (synchronous, owns a copy/compute stream pair) serialises per model;
  *   - "real" buffers hold float64 or float32 according to the model's precision; time steps
  *     `dt` are ALWAYS float64 and are computed by the host as t - t_prev from float64 epoch
  *     seconds (kf_workers.py:682), never from float32 timestamps.

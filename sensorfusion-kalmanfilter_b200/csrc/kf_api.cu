@@ -517,9 +517,10 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   memcpy(m->mc.r_imu, desc->r_imu, sizeof(m->mc.r_imu));
   m->mc.c2 = desc->accel_coef;
   m->n = info.n, m->d = info.d, m->m_gps = info.m_gps;
-  m->arena = nullptr;
-  m->arena_bytes = kArenaBytes;
-  memset(&m->host_ws, 0, sizeof(m->host_ws));
+  m->pool = nullptr;
+  m->host_ws.ready = 0;
+  m->host_ws.slab = nullptr;
+  m->host_ws.cap = 0;
   m->tpb = 64;
   m->use_tma = 1;
   if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
@@ -537,8 +538,21 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   }
   e = cudaGetDevice(&m->device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
-  if (e == cudaSuccess) e = cudaMalloc(&m->arena, m->arena_bytes);
+  if (e == cudaSuccess) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = m->device;
+    e = cudaMemPoolCreate(&m->pool, &props);
+    if (e == cudaSuccess) {
+      unsigned long long keep = ~0ULL;  // never trim: the per-call scratch is re-used call after call
+      e = cudaMemPoolSetAttribute(m->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (e != cudaSuccess) {
+    if (m->pool) cudaMemPoolDestroy(m->pool);
     delete m;
     return cuda_fail(e, "b200kf_model_create");
   }
@@ -548,7 +562,7 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
 
 int b200kf_model_destroy(b200kf_model* m) {
   if (!m) return B200KF_OK;
-  if (m->arena) cudaFree(m->arena);
+  if (m->pool) cudaMemPoolDestroy(m->pool);
   if (m->host_ws.slab) cudaFree(m->host_ws.slab);
   if (m->host_ws.ready) {
     cudaStreamDestroy(m->host_ws.s_copy);
@@ -664,8 +678,9 @@ int b200kf_run_batch_host(const b200kf_model* m, int64_t n_filters, int64_t n_st
 
   // Persistent workspace owned by the model (streams, events, one growable device slab): the
   // per-call cudaMalloc/cudaFree of the first version cost more than the copies once NCCL had
-  // peer-mapped the device.  Not re-entrant for concurrent calls on the same model.
+  // peer-mapped the device.  Calls on one model serialise on the workspace mutex.
   HostWorkspace& ws = const_cast<b200kf_model*>(m)->host_ws;
+  std::lock_guard<std::mutex> ws_lock(ws.mu);  // concurrent callers of one model take turns
   auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
   const size_t pay_b = up(step_bytes * chunk_steps);
   const size_t nst = n_steps > 0 ? static_cast<size_t>(n_steps) : 1;
@@ -781,9 +796,11 @@ int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_
   p.threshold = threshold;
   p.initial_logdet = initial_logdet;
   p.per_schedule = per_schedule;
-  p.partials = search_scratch(m);
-  p.dense_flag = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ScratchBuf parts;  // per call: concurrent searches on one model never share their partial results
+  B200KF_CUDA_TRY(parts.alloc(m, sizeof(ScorePartial) * kMaxSearchPartials, st));
+  p.partials = parts.p;
+  p.dense_flag = nullptr;
   const int blocks = dispatch_score(m, p, flags, best, st);
   if (blocks < 0) return blocks;
   score_final_kernel<<<1, 256, 0, st>>>(static_cast<const ScorePartial*>(p.partials), blocks, n_events, best);
@@ -873,8 +890,10 @@ int b200kf_score_products(const b200kf_model* m, int32_t n_windows, const int32_
   p.first = first;
   p.count = count;
   p.per_combo = per_combo;
-  p.partials = search_scratch(m);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ScratchBuf parts;
+  B200KF_CUDA_TRY(parts.alloc(m, sizeof(ProductPartial) * kMaxSearchBlocks, st));
+  p.partials = parts.p;
   const int blocks = dispatch_product(m, p, flags, st);
   if (blocks < 0) return blocks;
   product_final_kernel<<<1, 256, 0, st>>>(static_cast<const ProductPartial*>(p.partials), blocks, count, best);
@@ -901,22 +920,26 @@ int b200kf_rmse_vs_track(const b200kf_model* m, int64_t n_filters, int64_t n_ste
   if (traj_ncomp < 3) return set_error(B200KF_ERR_INVALID, "the trajectory must hold the 3 position components");
   if (n_filters == 0) return B200KF_OK;
   if (!traj || !ref_pos || !rmse) return set_error(B200KF_ERR_INVALID, "null argument");
-  // time segments: enough threads to fill the GPU when there are few filters, bounded by the scratch
-  double* part = static_cast<double*>(search_scratch(m));
-  const long long cap = static_cast<long long>((kSchedOffset - 256) / sizeof(double));
+  // time segments: enough threads to fill the GPU when there are few filters, bounded by 8 MB of partials
+  const long long cap = static_cast<long long>((size_t(8) << 20) / sizeof(double));
   long long seg = (static_cast<long long>(m->sm_count) * 2048 + n_filters - 1) / n_filters;
   if (seg > n_steps) seg = n_steps;
   if (seg * n_filters > cap) seg = cap / n_filters;
-  double* dst = part;
-  if (seg < 1) {  // more filters than scratch doubles: one segment, partials straight into rmse
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ScratchBuf part;
+  double* dst = nullptr;
+  if (seg < 1) {  // more filters than partials: one segment, partial sums straight into rmse
     seg = 1;
     dst = rmse;
   }
   if (seg > 65535) seg = 65535;
   const long long seg_len = (n_steps + seg - 1) / seg;
   const int n_seg = static_cast<int>((n_steps + seg_len - 1) / seg_len);
+  if (dst == nullptr) {
+    B200KF_CUDA_TRY(part.alloc(m, sizeof(double) * static_cast<size_t>(n_seg) * n_filters, st));
+    dst = static_cast<double*>(part.p);
+  }
   const int tpb = 128;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(static_cast<unsigned>((n_filters + tpb - 1) / tpb), static_cast<unsigned>(n_seg));
   if (m->desc.precision == B200KF_F32)
     rmse_partial_kernel<float><<<grid, tpb, 0, st>>>(static_cast<const float*>(traj), traj_ncomp, n_filters, n_steps,

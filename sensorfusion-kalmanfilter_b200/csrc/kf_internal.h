@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <cuda_runtime.h>
 
 #include "../../include/b200kf.h"
@@ -10,6 +11,7 @@
 
 // b200kf_run_batch_host's persistent resources (created on first use, freed with the model)
 struct HostWorkspace {
+  std::mutex mu;  // b200kf_run_batch_host calls on one model serialise (they share the slab, streams and events)
   int ready;
   cudaStream_t s_copy, s_comp;
   cudaEvent_t ev_copied[2], ev_done[2];
@@ -23,9 +25,12 @@ struct b200kf_model {
   int n, d, m_gps;
   int device;
   int sm_count;
-  // device arena: [0] dense-needed flag, then reduction scratch for the schedule search
-  void* arena;
-  size_t arena_bytes;
+  // Per-call device scratch (dispatch flags, packed schedules, reduction partials) comes from this
+  // stream-ordered pool: allocated on the caller's stream, freed on it behind the last kernel that reads it.
+  // Calls on different streams / threads therefore never share scratch and one model can be in flight on
+  // many streams at once; the pool keeps what it ever held (release threshold = max), so a steady-state
+  // call costs two ~1 us driver calls and no device synchronisation.
+  cudaMemPool_t pool;
   int tpb;      // threads per block for the filter kernels (env B200KF_TPB)
   HostWorkspace host_ws;
   int use_sym;  // 1: axis-symmetric kernel when every filter's chains share one covariance (env B200KF_SYM=0 disables)
@@ -37,8 +42,6 @@ struct b200kf_model {
 
 namespace b200kf {
 
-constexpr size_t kArenaBytes = 8 << 20;
-constexpr size_t kSchedOffset = 1 << 20;  // packed (dt, type) records of the TMA kernel
 constexpr int kMaxSearchBlocks = 8192;
 constexpr int kMaxSearchPartials = 24000;  // 40-byte ScorePartial entries in the search scratch (< 1 MB)
 
@@ -193,13 +196,21 @@ int launch_product_m(const b200kf_model* m, const ProductParams& p, unsigned fla
 template <int MODEL>
 int launch_select_m(const b200kf_model* m, const SelectParams& p, unsigned flags, cudaStream_t st);
 
-inline int* dense_flag(const b200kf_model* m) { return reinterpret_cast<int*>(m->arena); }
-inline void* search_scratch(const b200kf_model* m) {
-  return reinterpret_cast<char*>(m->arena) + 256;
-}
-inline void* sched_scratch(const b200kf_model* m) {
-  return reinterpret_cast<char*>(m->arena) + kSchedOffset;
-}
-inline size_t sched_capacity(const b200kf_model* m) { return m->arena_bytes - kSchedOffset; }
+// One per-call scratch allocation from the model's pool, returned to the pool on the same stream when the
+// guard goes out of scope (i.e. behind every kernel the call enqueued).
+struct ScratchBuf {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  ScratchBuf() = default;
+  ScratchBuf(const ScratchBuf&) = delete;
+  ScratchBuf& operator=(const ScratchBuf&) = delete;
+  ~ScratchBuf() {
+    if (p != nullptr) cudaFreeAsync(p, st);
+  }
+  cudaError_t alloc(const b200kf_model* m, size_t bytes, cudaStream_t s) {
+    st = s;
+    return cudaMallocFromPoolAsync(&p, bytes > 0 ? bytes : 16, m->pool, s);
+  }
+};
 
 }  // namespace b200kf

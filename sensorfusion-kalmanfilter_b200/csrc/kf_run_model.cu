@@ -1264,10 +1264,9 @@ static bool tma_possible(const b200kf_model* m, const RunParams& p, bool full) {
   } else {
     if (p.ptraj != nullptr || m->use_tma == 0) return false;  // per-step P output: LDG kernel only
     (void)full;
-    const size_t need = static_cast<size_t>(p.n_steps) * sizeof(SchedRec);
     // bulk copies need 16-byte aligned rows: even filter count for f64, multiple of 4 for f32
     const long long align_elems = 16 / static_cast<long long>(sizeof(real));
-    return p.n_steps >= 1 && need <= sched_capacity(m) && (p.n_filters % align_elems) == 0 &&
+    return p.n_steps >= 1 && (p.n_filters % align_elems) == 0 &&
            (reinterpret_cast<uintptr_t>(p.payload) & 15u) == 0;
   }
 }
@@ -1284,9 +1283,8 @@ static bool tma_sym3_possible(const b200kf_model* m, const RunParams& p, bool fu
     // inside update(), which a gated step skips) and stays with the LDG kernel
     (void)full;
     if (p.gate_enabled || p.ptraj != nullptr || m->use_tma == 0) return false;
-    const size_t need = static_cast<size_t>(p.n_steps) * sizeof(SchedRec);
     const long long align_elems = 16 / static_cast<long long>(sizeof(real));
-    return p.n_steps >= 1 && need <= sched_capacity(m) && (p.n_filters % align_elems) == 0 &&
+    return p.n_steps >= 1 && (p.n_filters % align_elems) == 0 &&
            (reinterpret_cast<uintptr_t>(p.payload) & 15u) == 0;
   }
 }
@@ -1322,13 +1320,13 @@ static cudaError_t launch_tma_one(const RunParams& p, const LeanRecT<real>* sche
 
 template <int MODEL, typename real>
 static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool with_sym, bool with_dec,
-                              bool full, cudaStream_t st) {
+                              bool full, void* sched_mem, cudaStream_t st) {
   using MTl = ModelTraits<MODEL, false, real>;
   if constexpr (!MTl::Filter::fast2 && !MTl::Sym3::eligible) {
     return cudaErrorInvalidValue;
   } else {
     constexpr bool kFast2 = MTl::Filter::fast2;
-    LeanRecT<real>* sched = reinterpret_cast<LeanRecT<real>*>(sched_scratch(m));
+    LeanRecT<real>* sched = static_cast<LeanRecT<real>*>(sched_mem);  // [n_steps] records, scratch of this call
     LeanConst lc{1.0, 1.0, 1.0, 1.0, 1.0};  // rate constants of the symmetric group (only its lean step reads them)
     if constexpr (kFast2 && ModelTraits<MODEL, false, real>::Sym2::eligible) {
       using G0 = typename ModelTraits<MODEL, false, real>::Sym2::Lead;
@@ -1508,6 +1506,11 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   for (int i = 0; i < m->m_gps; ++i) r_pos = r_pos && m->mc.r_gps[i] > 0.0;
   const bool tma = tma_possible<MODEL, real>(m, p, full);
   const bool sym = sym_possible<MODEL, real>(m);
+  // scratch of THIS call (stream-ordered, freed behind the last kernel below): the three AUTO dispatch flags
+  // and the packed step records of the ring kernels
+  ScratchBuf scratch;
+  B200KF_CUDA_TRY(scratch.alloc(m, 256 + static_cast<size_t>(p.n_steps) * sizeof(SchedRec), st));
+  void* sched_mem = static_cast<char*>(scratch.p) + 256;
   const bool tma_sym = tma && tma_sym_eligible<MODEL, real>() && r_pos;
   // the shared-covariance kernels stream the payload with bulk copies: 16-byte aligned rows
   const long long align_elems = 16 / static_cast<long long>(sizeof(real));
@@ -1525,7 +1528,7 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && sym) {
     p.dense_flag = nullptr;
     if (tma_sym || tma3) {
-      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, st)));
+      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, sched_mem, st)));
     } else {
       B200KF_CUDA_TRY((launch_variant<MODEL, VAR_SYMMETRIC, real>(m, p, full, st)));
     }
@@ -1534,7 +1537,7 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC)) {
     p.dense_flag = nullptr;
     if (tma) {
-      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, false, true, full, st)));
+      B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, false, true, full, sched_mem, st)));
       return B200KF_OK;
     }
     B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DECOUPLED, real>(m, p, full, st)));
@@ -1548,7 +1551,7 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   // profiles/r01c_small_shards.jsonl) stay per-filter in aggregate mode.
   const bool small_shard = pick_ring_f(p.n_filters, m->sm_count, m->ring_f_cap) < 896;
   const bool shared_auto = shared && !(small_shard && !full && (tma_sym || tma3));
-  int* flag = dense_flag(m);
+  int* flag = static_cast<int*>(scratch.p);
   B200KF_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
   B200KF_CUDA_TRY(cudaMemsetAsync(flag + 1, sym ? 0 : 1, sizeof(int), st));
   B200KF_CUDA_TRY(cudaMemsetAsync(flag + 2, shared_auto ? 0 : 1, sizeof(int), st));
@@ -1560,9 +1563,9 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   p.dense_flag = flag;
   if (shared_auto) B200KF_CUDA_TRY((launch_shared<MODEL, real>(m, p, full, st)));
   if (tma) {
-    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym && tma_sym, true, full, st)));
+    B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, sym && tma_sym, true, full, sched_mem, st)));
   } else {
-    if (tma3) B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, st)));
+    if (tma3) B200KF_CUDA_TRY((launch_tma<MODEL, real>(m, p, true, false, full, sched_mem, st)));
     B200KF_CUDA_TRY((launch_variant<MODEL, VAR_DECOUPLED, real>(m, p, full, st)));
   }
   if (sym && !tma_sym && !tma3) B200KF_CUDA_TRY((launch_variant<MODEL, VAR_SYMMETRIC, real>(m, p, full, st)));

@@ -122,7 +122,12 @@ class Engine:
         used_d = torch.empty((T, N), dtype=torch.uint8, device=self.device) if want_used else None
         ptraj_d = torch.empty((T, sp.n * sp.n, N), dtype=self.real, device=self.device) if want_ptraj else None
         status_d = torch.zeros((N,), dtype=torch.int32, device=self.device)
-        if gate_threshold is not None and np.ndim(gate_threshold) > 0 or torch.is_tensor(gate_threshold):
+        if torch.is_tensor(gate_threshold) and gate_threshold.numel() == 1:
+            gate_threshold = float(gate_threshold.item())  # a 0-dim / one-element tensor is a scalar threshold
+        elif gate_threshold is not None and not torch.is_tensor(gate_threshold) and np.ndim(gate_threshold) > 0 \
+                and np.size(gate_threshold) == 1 and N != 1:
+            gate_threshold = float(np.asarray(gate_threshold).reshape(()))
+        if gate_threshold is not None and (torch.is_tensor(gate_threshold) or np.ndim(gate_threshold) > 0):
             # one threshold per filter (b200kf_run_batch_gated)
             if rows_d is not None:
                 raise ValueError("per-filter gate thresholds and step_rows cannot be combined")
@@ -340,9 +345,9 @@ class Engine:
         if mode == "auto" and not isinstance(P0, torch.Tensor):
             # P0 still on the host: a chain-compatible covariance takes the per-chain form of the kernel
             # (an order of magnitude faster than the dense 15 x 15 one for the reference's P0, :851)
-            from .models import axis_symmetric, chain_compatible
+            from .models import axis_symmetric, chain_compatible, rates_axis_symmetric
             P0h = np.asarray(P0, dtype=np.float64).reshape(I, sp.n, sp.n)
-            if axis_symmetric(sp.name, P0h):
+            if axis_symmetric(sp.name, P0h) and rates_axis_symmetric(sp):
                 mode = "symmetric"  # one covariance per group of axes (falls back to per-chain if the rates differ)
             elif chain_compatible(sp.name, P0h):
                 mode = "decoupled"
@@ -355,7 +360,11 @@ class Engine:
         P_f = torch.empty((I, sp.n, sp.n), dtype=torch.float64, device=self.device)
         recs = None
         if want_gains and mode == "symmetric":
-            recs = torch.empty((I, max_sel, self.gain_record_bytes()), dtype=torch.uint8, device=self.device)
+            from .models import rates_axis_symmetric
+            if rates_axis_symmetric(sp):  # the records exist in the symmetric form only; else: per-chain, no records
+                recs = torch.empty((I, max_sel, self.gain_record_bytes()), dtype=torch.uint8, device=self.device)
+            else:
+                mode = "decoupled"
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200kf_select_greedy_gains(
                 self._h, E, _ptr(types_d), _ptr(times_d), I, _ptr(per_d), _ptr(tp_d), _ptr(P0_d), max_sel,

@@ -56,7 +56,11 @@ def adaptive_warmups(sf, end_indices, thresholds):
         return out
     thr_list = sorted({float(t) for t in thresholds})
     g_of = {t: g for g, t in enumerate(thr_list)}
-    reqs = sorted((min(int(e), n_ev), g_of[float(t)], k) for k, (e, t) in enumerate(zip(end_indices, thresholds)))
+    # an unreachable window start (find_start_idx_for_time_offset -> None) is the caller's ERROR row, not a warm-up
+    reqs = sorted((min(int(e), n_ev), g_of[float(t)], k) for k, (e, t) in enumerate(zip(end_indices, thresholds))
+                  if e is not None)
+    if not reqs:
+        return out
     e_max = reqs[-1][0]
     init = sf._first_gps(0, e_max)
     if init is None:
@@ -108,6 +112,8 @@ def run_window_experiment(sf, start_indices, r_factors, *, start_offset=25, lb_e
         row = {"timestamp": datetime.now().isoformat(), "iteration": it, "start_idx": start_idx,
                "start_offset": start_offset}
         try:
+            if start_idx is None:  # the offset is past the end of the stream (:2310 returned None): `None + 25` at :2321
+                raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'int'")
             if w is None:
                 raise TypeError("cannot unpack non-iterable NoneType object")  # what the reference hits at :2316
             st_last, pt = w

@@ -658,13 +658,23 @@ def _lerp_extrapolate(x, xp, fp):
     return ((x - xp[lo]) / (xp[hi] - xp[lo])) * fp[hi] + ((xp[hi] - x) / (xp[hi] - xp[lo])) * fp[lo]
 
 
-def find_start_idx_for_time_offset(sensor_fusion, time_offset, t0=1697739552.3362827):
-    """First event index whose time is >= t0 + time_offset (the helper the reference's __main__ uses;
-    t0 is its hard-coded first-fix epoch, kf_workers.py:1993)."""
-    target = t0 + time_offset
+def find_start_idx_for_time_offset(sensor_fusion, target_seconds):
+    """Index of the first event at or after `target_seconds` past the data set's first fix
+    (kf_workers.py:1985-2003; 1697739552.3362827 is the reference's hard-coded first-fix epoch, :1993).
+    None -- with the reference's messages -- when the stream is missing or never reaches the target."""
+    if not hasattr(sensor_fusion, "indexed_sensor_data") or not sensor_fusion.indexed_sensor_data:
+        print("Sensor data not available. Run combine_sensor_data() first.")
+        return None
+    first_timestamp = 1697739552.3362827
+    target_timestamp = first_timestamp + target_seconds
     times = streams.pack_events(sensor_fusion.indexed_sensor_data).times  # packed once per stream
-    hit = np.flatnonzero(times >= target)  # the first such event, sorted stream or not (the reference scans)
-    return int(hit[0]) if hit.size else len(times)
+    hit = np.flatnonzero(times >= target_timestamp)  # the first such event, sorted stream or not (the reference scans)
+    if hit.size:
+        i = int(hit[0])
+        print(f"Found index {i} at time {times[i]:.3f}s (offset: {times[i] - first_timestamp:.3f}s)")
+        return i
+    print(f"Target time {target_seconds}s not found in data")
+    return None
 
 
 __all__ = ["KF_SensorFusion", "Scheduler", "evaluate_combo_chunk_worker", "find_start_idx_for_time_offset",

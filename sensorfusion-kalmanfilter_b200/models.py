@@ -211,3 +211,21 @@ def axis_symmetric(name: str, P: np.ndarray) -> bool:
             if np.any(blk != ref):
                 return False
     return True
+
+
+def rates_axis_symmetric(spec: ModelSpec) -> bool:
+    """True when the chains that are the same model on different axes also share their rate constants
+    (q, r_imu, r_gps) -- the second half of the symmetric kernels' validity condition
+    (kf_core.cuh SymBlock::constants_equal)."""
+    groups = {}
+    for ch in CHAINS[spec.name]:
+        groups.setdefault(len(ch), []).append(ch)
+    for chains in groups.values():
+        c0 = chains[0]
+        for ch in chains[1:]:
+            for a, b in zip(c0, ch):
+                if spec.q[a] != spec.q[b] or spec.r_imu[a] != spec.r_imu[b]:
+                    return False
+                if a < spec.m_gps and b < spec.m_gps and spec.r_gps[a] != spec.r_gps[b]:
+                    return False
+    return True

@@ -62,22 +62,53 @@ class PackedStream:
 
 _cache: "OrderedDict[int, tuple]" = OrderedDict()
 _CACHE_MAX = 4
+_PROBES = 64
+
+
+def _fingerprint(events):
+    """Length + the (type, time, first payload values) of up to 64 evenly spaced events: cheap evidence that
+    the list still holds what was packed (an in-place edit of the list almost surely moves one of them)."""
+    E = len(events)
+    if E == 0:
+        return (0,)
+    step = max(1, E // _PROBES)
+    probe = []
+    for k in list(range(0, E, step)) + [E - 1]:
+        _, stype, t, sdata = events[k]
+        if stype == "GPS":
+            probe.append((0, t, sdata["easting"], sdata["northing"]))
+        else:
+            probe.append((1, t, sdata[1], sdata[9]))
+    return (E, tuple(probe))
 
 
 def pack_events(events) -> PackedStream:
-    """Pack an indexed_sensor_data list, cached per list object (id + length + end times) so the
-    experiment loops that call run_* hundreds of times on one stream pack it once."""
+    """Pack an indexed_sensor_data list, cached per list OBJECT so the experiment loops that call run_*
+    hundreds of times on one stream pack it once.  The cache entry keeps a reference to the list it packed:
+    a hit requires `entry_list is events` (CPython reuses the id of a freed list, so an id alone would hand a
+    regenerated list of the same shape the old payload) and an unchanged fingerprint of sampled events (an
+    in-place edit repacks).  Callers that rewrite single events in place beyond what the 64 probes can see
+    must call `invalidate(events)`."""
     key = id(events)
-    sig = (len(events), events[0][2] if events else None, events[-1][2] if events else None)
+    sig = _fingerprint(events)
     hit = _cache.get(key)
-    if hit is not None and hit[0] == sig:
+    if hit is not None and hit[0] is events and hit[1] == sig:
         _cache.move_to_end(key)
-        return hit[1]
+        return hit[2]
     ps = PackedStream.from_events(events)
-    _cache[key] = (sig, ps)
+    _cache[key] = (events, sig, ps)
+    _cache.move_to_end(key)
     while len(_cache) > _CACHE_MAX:
         _cache.popitem(last=False)
     return ps
+
+
+def invalidate(events=None):
+    """Drop the packed form of `events` (or of every list) from the cache."""
+    if events is None:
+        _cache.clear()
+    else:
+        _cache.pop(id(events), None)
 
 
 def schedule_dts(times, prev_time, skip_advances_prev=True):

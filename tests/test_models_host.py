@@ -96,6 +96,32 @@ def test_packer_matches_oracle_payload():
             np.testing.assert_array_equal(pay[k], ko.event_payload(m, ev[k][1], ev[k][3]))
 
 
+def test_packer_cache_is_identity_safe():
+    """A regenerated list of the same shape (same length and end times, different measurements) must be
+    packed afresh even when CPython hands it the id of the freed one, and so must an in-place edit."""
+    import gc
+    streams.invalidate()
+    stale = 0
+    for seed in range(20):
+        ev = synth.make_indexed_sensor_data(90, seed=seed)
+        ps = streams.pack_events(ev)
+        want = streams.PackedStream.from_events(ev)
+        stale += not (np.array_equal(ps.data, want.data) and np.array_equal(ps.times, want.times))
+        del ev
+        gc.collect()
+    assert stale == 0
+    ev = synth.make_indexed_sensor_data(90, seed=1)
+    ps = streams.pack_events(ev)
+    k = next(i for i, e in enumerate(ev) if e[1] == "GPS")
+    g = dict(ev[k][3])
+    g["easting"] += 1.0
+    ev[k] = (ev[k][0], ev[k][1], ev[k][2], g)  # in-place edit of one event (every event is a probe at this size)
+    ps2 = streams.pack_events(ev)
+    assert ps2 is not ps and ps2.data[k, 0] == g["easting"]
+    streams.invalidate(ev)
+    assert streams.pack_events(ev) is not ps2
+
+
 def test_schedule_dts_rules():
     t = np.array([10.0, 10.5, 10.2, 10.6, 11.0])
     keep, dts, prev = streams.schedule_dts(t, 10.0, skip_advances_prev=True)  # kf_workers.py:682-685
