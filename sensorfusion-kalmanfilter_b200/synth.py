@@ -141,3 +141,20 @@ def write_config1_csvs(directory, n_imu=4000, n_gps_nan=12, seed=0, gps_csv=None
             else:
                 w.writerow([repr(float(t_gps[k])), repr(float(lat[k])), repr(float(lon[k])), repr(float(alt[k]))])
     return gps_path, imu_path
+
+
+def seed_noise(types, seed, sigma_imu=0.05, var_gps=3.0):
+    """Measurement noise of Monte-Carlo seed `seed` for a packed base stream (BASELINE configs[1],
+    SURVEY.md 8(d) config 2): GPS rows get N(0, R_GPS = 3) on their three columns, IMU rows N(0, sigma_imu^2)
+    on all nine channels.  Returns [E, 9] float64 to ADD to the base stream's data; seed 0 .. S-1 are
+    independent `default_rng(seed)` streams, so any subset of seeds can be regenerated on its own."""
+    types = np.asarray(types)
+    rng = np.random.default_rng(seed)
+    out = rng.normal(0.0, sigma_imu, (len(types), 9))
+    g = types == 0
+    ng = int(g.sum())
+    if ng:
+        rows = np.zeros((ng, 9))
+        rows[:, :3] = rng.normal(0.0, np.sqrt(var_gps), (ng, 3))
+        out[g] = rows
+    return out

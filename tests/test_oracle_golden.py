@@ -228,3 +228,39 @@ def test_accuracy_metrics(golden):
         rmse, interp = ko.accuracy_metrics(cand, gt)
         np.testing.assert_allclose(rmse, g[key], rtol=1e-9)
         np.testing.assert_allclose(interp, g["ground_truth_interp" if key == "rmse" else "tiny_interp"], rtol=1e-11)
+
+
+# ---- full-LENGTH golden vectors (oracle/make_golden_long.py): the oracle itself is held to the reference
+# over 120 000 events of the full filter and over the whole 2 808 s stream of the 10 Hz scheduled filter
+def _long_sample(a, stride):
+    a = np.asarray(a)
+    return np.concatenate([a[:-8:stride], a[-8:]], axis=0)
+
+
+def test_oracle_full_filter_at_120k_events(golden):
+    from sensorfusion_kalmanfilter_b200 import synth
+    g = golden("ca15_full_120k.npz")
+    n, stride = int(g["n_events"]), int(g["stride"])
+    ev = synth.make_indexed_sensor_data(n + 3, seed=int(g["base_seed"]))[3:]
+    st, ld, P, prev = ko.run_full(ko.get_model("CA15"), ev, 0, len(ev))
+    assert len(st) == int(g["n_states"]) and prev == float(g["prev_time"])
+    np.testing.assert_allclose(_long_sample(states_arr(st), stride), g["states"], rtol=1e-10, atol=1e-10)
+    ld = np.array(ld)
+    np.testing.assert_allclose(_long_sample(ld, stride), g["logdet"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose([ld.max(), ld.sum(), ld[-1]], g["agg"], rtol=1e-10)
+    np.testing.assert_allclose(P, g["P"], rtol=1e-10, atol=1e-12)
+
+
+def test_oracle_scheduled_filter_at_config2_length(golden):
+    from sensorfusion_kalmanfilter_b200 import streams, synth
+    g = golden("ca15_config2_full_length.npz")
+    n, stride, seed = int(g["n_events"]), int(g["stride"]), int(g["seeds"][1])
+    ev = synth.make_indexed_sensor_data(n + 3, seed=int(g["base_seed"]))[3:]
+    ps = streams.PackedStream.from_events(ev)
+    ev = arrays_to_events(ps.types, ps.times, ps.data + synth.seed_noise(ps.types, seed))
+    st, ld, P = ko.run_scheduled(ko.get_model("CA15"), ev, 10, 0, len(ev))
+    assert len(st) == int(g[f"r10_s{seed}_n_states"])
+    sel = np.searchsorted(ps.times, states_arr(st)[1:, 0])
+    np.testing.assert_array_equal(sel, np.cumsum(g["r10_sel_delta"].astype(np.int64)))
+    np.testing.assert_allclose(_long_sample(states_arr(st), stride), g[f"r10_s{seed}_states"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(P, g[f"r10_s{seed}_P"], rtol=1e-10, atol=1e-12)
