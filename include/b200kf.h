@@ -91,8 +91,11 @@ typedef struct b200kf_best {
   uint64_t first_feasible_index; /* first schedule, in the reference's enumeration order
                                     (kf_workers.py:1325-1336), with max(log det) < threshold */
   uint64_t n_feasible;           /* schedules in range with max(log det) < threshold */
-  uint64_t n_near_threshold;     /* schedules with |max - threshold| <= 1e-9*max(1,|threshold|):
-                                    the feasibility decisions a 1e-12 rounding difference could flip */
+  uint64_t n_near_threshold;     /* schedules whose largest DEVICE-computed term lies within
+                                    1e-9*max(1,|threshold|) of the threshold (and which the caller's exact
+                                    initial_logdet does not already rule out): the feasibility decisions a
+                                    1e-12 rounding difference could flip.  The host mirror re-scores exactly
+                                    those in the reference's numpy arithmetic (kf_workers.py epsilon guard) */
 } b200kf_best;
 
 /* Result of a product-of-queues search over one index range. */

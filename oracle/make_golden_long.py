@@ -90,8 +90,66 @@ def _full_job(_):
             "prev_time": np.float64(prev)}
 
 
+CFG1_IMU_ROWS = 160000  # 800 s of 200 Hz IMU: the 273 s without a fix + 527 s of fixes (5 270 of them)
+
+
+def config1():
+    """BASELINE configs[0] on the reference's ONE real input (SURVEY.md section 4 data pins): gps_data.csv is
+    stored as four float64 columns (tests/golden/gps_data_reference.npz, every field round-trips through
+    repr, so synth.write_gps_csv rebuilds the file byte for byte -- sha256 stored) and the UNMODIFIED
+    front ends + filters of hw5_2.py and kf_workers.py are run on it with a synthetic imu_data.csv
+    (synth.write_config1_csvs, hw5_1.py:29-31 schema).  `utm.from_latlon` is the product's restatement
+    (geo.py), as in make_golden.py csv: the UTM series itself stays unpinned."""
+    import csv
+    import hashlib
+    import tempfile
+    from oracle.ref_import import REFERENCE_DIR
+    from sensorfusion_kalmanfilter_b200 import geo, synth
+    kw, hw = load_reference()
+    sys.modules["utm"].from_latlon = geo.from_latlon
+    src = os.path.join(REFERENCE_DIR, "gps_data.csv")
+    raw = open(src, "rb").read()
+    rows = list(csv.reader(open(src, newline="")))[1:]
+    cols = np.array([[float(v) for v in r] for r in rows], dtype=np.float64)
+    g = {"sha256": np.frombuffer(hashlib.sha256(raw).digest(), dtype=np.uint8), "n_bytes": np.int64(len(raw)),
+         "time": cols[:, 0], "lat": cols[:, 1], "lon": cols[:, 2], "alt": cols[:, 3]}
+    np.savez_compressed(os.path.join(OUT, "gps_data_reference.npz"), **g)
+    out = {"imu_rows": np.int64(CFG1_IMU_ROWS), "stride": np.int64(STRIDE)}
+    with tempfile.TemporaryDirectory() as d:
+        gps_path = synth.write_gps_csv(os.path.join(d, "gps_data.csv"), *[cols[:, j] for j in range(4)])
+        assert open(gps_path, "rb").read() == raw
+        _, imu_path = synth.write_config1_csvs(d, n_imu=CFG1_IMU_ROWS, seed=0, gps_csv=gps_path)
+        for tag, mod in (("kw", kw), ("hw", hw)):
+            k = mod.KF_SensorFusion(gps_path, imu_path)
+            quiet(k.load_data)
+            quiet(k.gps_to_modified_utm if tag == "kw" else k.gps_to_utm)
+            wb, ab, fvi = quiet(k.compute_imu_biases, k.gps_data, k.imu_data)
+            quiet(k.unbias_imu_data, wb, ab)
+            quiet(k.combine_sensor_data)
+            ev = k.indexed_sensor_data
+            out.update({f"{tag}_n_events": np.int64(len(ev)), f"{tag}_n_fixes": np.int64(len(k.utm_data)),
+                        f"{tag}_first_valid": np.int64(fvi), f"{tag}_wbias": wb, f"{tag}_abias": ab,
+                        f"{tag}_first_fix_time": np.float64(k.utm_data[0]["time"]),
+                        f"{tag}_zone": np.array([k.utm_data[0]["zone_number"], ord(k.utm_data[0]["zone_letter"])])})
+            if tag == "kw":
+                out["kw_first_fix_alt"] = np.float64(k.utm_data[0]["altitude"])
+                st, ld, P, prev = quiet(k.run_kalman_filter_full, 0, len(ev))
+                st, ld = states_arr(st), np.array(ld, dtype=np.float64)
+                out.update(kw_n_states=np.int64(len(st)), kw_states=sample(st), kw_logdet=sample(ld),
+                           kw_agg=np.array([ld.max(), ld.sum(), ld[-1]]), kw_P=np.asarray(P, dtype=np.float64))
+            else:
+                st = np.array(quiet(k.run_kalman_filter), dtype=np.float64)
+                out.update(hw_n_states=np.int64(len(st)), hw_states=sample(st))
+    np.savez_compressed(os.path.join(OUT, "config1_real_gps.npz"), **out)
+    for f in ("gps_data_reference.npz", "config1_real_gps.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        config1()
+        return
     ctx = mp.get_context("fork")
     jobs = [(r, s) for r in RATES for s in SEEDS]
     with ctx.Pool(min(len(jobs) + 1, os.cpu_count() or 2)) as pool:

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
     double sm = acc.sum_log();
     double lastv = (acc.count > 0) ? log(acc.last) : p.initial_logdet;
     int cnt = acc.count;
+    const double mx_dev = mx;  // max over the terms computed HERE (the ones a rounding difference can move)
     if (host_ld0) {  // term 0 is the same for every schedule: take the caller's value verbatim
       mx = fmax(mx, p.initial_logdet);
       sm += p.initial_logdet;
@@ -125,7 +126,9 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
         const unsigned long long key = lex_key(s, L);
         best_key = key < best_key ? key : best_key;
       }
-      if (fabs(mx - p.threshold) <= near_tol) n_near += 1;
+      // undecided to rounding: a term computed here within near_tol of the threshold, unless the caller's exact
+      // term 0 already rules the schedule out (it does so in the reference's arithmetic too)
+      if (fabs(mx_dev - p.threshold) <= near_tol && !(host_ld0 && p.initial_logdet >= p.threshold)) n_near += 1;
     }
   }
 
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
       double sm = acc.sum_log();
       double lastv = (acc.count > 0) ? log(acc.last) : p.initial_logdet;
       int cnt = acc.count;
+      const double mx_dev = mx;
       if (host_ld0) {
         mx = fmax(mx, p.initial_logdet);
         sm += p.initial_logdet;
@@ -279,7 +283,9 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
           const unsigned long long key = lex_key(s, L);
           best_key = key < best_key ? key : best_key;
         }
-        if (fabs(mx - p.threshold) <= near_tol) n_near += 1;
+        // undecided to rounding: a term computed here within near_tol of the threshold, unless the caller's exact
+      // term 0 already rules the schedule out (it does so in the reference's arithmetic too)
+      if (fabs(mx_dev - p.threshold) <= near_tol && !(host_ld0 && p.initial_logdet >= p.threshold)) n_near += 1;
       }
     }
   }

@@ -83,14 +83,35 @@ def allgather_best(best, group=None, device=None):
     return merge_best(parts)
 
 
+def allgather_best_device(best_d, group=None):
+    """The same reduce with the host off the critical path: `best_d` is the raw 48-byte b200kf_best still on
+    the device (Engine.score_schedules(device_result=True)); ONE all_gather_into_tensor of it, stream-ordered
+    behind the scoring kernel (no host synchronisation in between), then ONE device->host copy of the
+    world_size x 48 bytes and the deterministic merge (a 48-byte-per-rank reduce; the order of ties is part of
+    the contract, so it is not an all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    from .engine import Engine
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return merge_best([Engine.best_from_bytes(best_d.cpu().numpy().tobytes())])
+    if dist.get_backend(group) != "nccl":
+        best_d = best_d.cpu()
+    out = torch.empty((world * best_d.numel(),), dtype=best_d.dtype, device=best_d.device)
+    dist.all_gather_into_tensor(out, best_d, group=group)
+    raw = out.cpu().numpy().reshape(world, -1)
+    return merge_best([Engine.best_from_bytes(raw[r].tobytes()) for r in range(world)])
+
+
 def search_sharded(engine, types, times, t_prev, t_end, P0, threshold, group=None, **kw):
-    """Brute-force search of all 2^L subset schedules sharded over the ranks of `group`."""
+    """Brute-force search of all 2^L subset schedules sharded over the ranks of `group`: contiguous index
+    ranges, no exchange during the search, one 48-byte all-gather at the end."""
     import torch.distributed as dist
     L = len(types)
     rank, world = 0, 1
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     first, count = shard_range(1 << L, world, rank)
-    best, _ = engine.score_schedules(types, times, t_prev, t_end, P0, first=first, count=count,
-                                     threshold=threshold, **kw)
-    return allgather_best(best, group=group, device=engine.device)
+    best_d, _ = engine.score_schedules(types, times, t_prev, t_end, P0, first=first, count=count,
+                                       threshold=threshold, device_result=True, **kw)
+    return allgather_best_device(best_d, group=group)

@@ -191,11 +191,13 @@ class Engine:
     # ------------------------------------------------------------------ schedule search
     def score_schedules(self, types, times, t_prev, t_end, P0, *, first=0, count=None,
                         threshold=float("inf"), initial_logdet=None, want_per_schedule=False, mode="auto",
-                        stream=None):
+                        stream=None, device_result=False):
         """Score the subset schedules [first, first+count) of a window (b200kf_score_schedules).
         initial_logdet: the caller's sign*logabsdet of P0 used verbatim as term 0 (exact ties with
         a threshold derived from it resolve as in the reference); None computes it on the device.
-        Returns (best: dict, per_schedule: torch [count,4] or None)."""
+        Returns (best: dict, per_schedule: torch [count,4] or None).  With device_result=True `best` is the
+        raw 48-byte b200kf_best as a CUDA uint8 tensor and nothing is copied to the host (no synchronisation:
+        the sharded search all-gathers it as it is, distributed.search_sharded)."""
         torch = _torch()
         types = np.ascontiguousarray(types, dtype=np.uint8)
         times = np.ascontiguousarray(times, dtype=np.float64)
@@ -211,10 +213,16 @@ class Engine:
                 float(t_prev), float(t_end), P0.ctypes.data_as(POINTER(c_double)), int(first), int(count),
                 float(threshold), float("nan") if initial_logdet is None else float(initial_logdet),
                 _ptr(per), _ptr(best_d), _MODES[mode], self._stream(stream)))
-        raw = bytes(best_d.cpu().numpy().tobytes())
-        b = _lib.Best.from_buffer_copy(raw)
+        if device_result:
+            return best_d, per
+        return self.best_from_bytes(best_d.cpu().numpy().tobytes()), per
+
+    @staticmethod
+    def best_from_bytes(raw):
+        """b200kf_best (include/b200kf.h) as a dict."""
+        b = _lib.Best.from_buffer_copy(bytes(raw))
         none = (1 << 64) - 1
-        best = {
+        return {
             "argmin_sum_score": b.argmin_sum_score,
             "argmin_sum_index": None if b.argmin_sum_index == none else int(b.argmin_sum_index),
             "first_feasible_key": int(b.first_feasible_key),
@@ -222,7 +230,6 @@ class Engine:
             "n_feasible": int(b.n_feasible),
             "n_near_threshold": int(b.n_near_threshold),
         }
-        return best, per
 
 
     def run_masked(self, types, times, payload, t_prev, t_end, x0, P0, masks, *, traj_ncomp=6,

@@ -626,6 +626,13 @@ class KF_SensorFusion:
         best, _ = eng.score_schedules(ps.types, ps.times, prev_time, last_measurement_time, Pt,
                                       threshold=R_threshold, initial_logdet=_slogdet_signed(Pt))
         mask = best["first_feasible_index"]
+        n_rescored = 0
+        if best["n_near_threshold"] > 0:
+            # epsilon guard: the reference compares max(log_det) < R_threshold strictly
+            # (:1353); a schedule whose max sits within 1e-9 of the threshold could be decided the other way by a
+            # 1e-12 rounding difference, so exactly those are re-scored in the reference's own arithmetic
+            mask, n_rescored = self._resolve_near_threshold(eng, ps, sensor_measurements, prev_time,
+                                                            last_measurement_time, Pt, R_threshold)
         if mask is None:
             print("\nBrute force search complete. No combination met the R_threshold.")
             return None
@@ -645,7 +652,78 @@ class KF_SensorFusion:
                 "num_measurements_used": len(sel),
                 # extras (not in the reference): how many feasibility decisions sat within 1e-9 of the
                 # threshold, and the winner as a bitmask over the window
-                "n_near_threshold": best["n_near_threshold"], "selected_mask": mask}
+                "n_near_threshold": best["n_near_threshold"], "n_rescored_on_host": n_rescored, "selected_mask": mask}
+
+    # ---- epsilon guard of the selection (kf_workers.py:1353-1358) -------------------------------
+    def _combo_logdets_host(self, combo, Pt, prev_time, target_end_time):
+        """log_det trace of ONE combo in the reference's numpy arithmetic, through this instance's own
+        (overridable) getters -- the covariance half of the worker, kf_workers.py:32-82.  Used only to
+        settle feasibility decisions the GPU reports as undecided to rounding."""
+        P = np.array(Pt, dtype=np.float64)
+        I = np.eye(P.shape[0])
+        log_det = [_slogdet_signed(P)]
+        cur = prev_time
+        for (_, stype, t, _sdata) in combo:
+            dt = t - cur
+            if dt < 0:
+                continue
+            F = self.get_state_transition_matrix(dt)
+            P = self.predict_covariance(P, F, self.get_process_noise_covariance_matrix(dt))
+            if stype == "GPS":
+                H, R = self.get_gps_observation_matrix(), self.get_gps_measurement_noise_covariance_matrix()
+            else:
+                H, R = self.get_imu_observation_matrix(), self.get_imu_measurement_noise_covariance_matrix()
+            K = self.calculate_kalman_gain(P, H, R)
+            P = np.dot(I - np.dot(K, H), P)
+            cur = t
+            log_det.append(_slogdet_signed(P))
+        if cur < target_end_time - 1e-8:
+            dt = target_end_time - cur
+            F = self.get_state_transition_matrix(dt)
+            P = self.predict_covariance(P, F, self.get_process_noise_covariance_matrix(dt))
+            log_det.append(_slogdet_signed(P))
+        return log_det
+
+    def _resolve_near_threshold(self, eng, ps, sensor_measurements, prev_time, target_end_time, Pt, R_threshold,
+                                chunk_bits=22):
+        """First feasible schedule in the reference's enumeration order when some decisions are within
+        1e-9 of the threshold: min key over (schedules the GPU finds feasible with a margin) and (undecided
+        schedules that are feasible in the reference's arithmetic).  Returns (mask or None, number re-scored)."""
+        torch = _torch_mod()
+        n = len(sensor_measurements)
+        tol = 1e-9 * max(1.0, abs(R_threshold))
+        ld0 = _slogdet_signed(Pt)
+        # (1) first schedule that is feasible with a margin: the same search against threshold - tol
+        sure, _ = eng.score_schedules(ps.types, ps.times, prev_time, target_end_time, Pt,
+                                      threshold=R_threshold - tol, initial_logdet=ld0)
+        sure_key = sure["first_feasible_key"] if sure["first_feasible_index"] is not None else None
+        # (2) the undecided ones, from the per-schedule maxima
+        total = 1 << n
+        cand = []
+        for first in range(0, total, 1 << chunk_bits):
+            count = min(1 << chunk_bits, total - first)
+            _, per = eng.score_schedules(ps.types, ps.times, prev_time, target_end_time, Pt, first=first, count=count,
+                                         threshold=R_threshold, initial_logdet=ld0, want_per_schedule=True)
+            near = torch.nonzero((per[:, 0] - R_threshold).abs() <= tol).flatten()
+            cand += [first + int(i) for i in near.cpu().tolist() if first + int(i) != 0]
+            del per
+        cand.sort(key=lambda m: _lex_key(m, n))
+        n_rescored = 0
+        for m in cand:  # ascending enumeration order: the first feasible one ahead of `sure` wins
+            if sure_key is not None and _lex_key(m, n) > sure_key:
+                break
+            combo = tuple(sensor_measurements[i] for i in range(n) if (m >> i) & 1)
+            n_rescored += 1
+            if max(self._combo_logdets_host(combo, Pt, prev_time, target_end_time)) < R_threshold:
+                return m, n_rescored
+        return sure["first_feasible_index"], n_rescored
+
+
+def _lex_key(mask, L):
+    """Position of subset `mask` in the reference's enumeration (cardinality ascending, then
+    itertools.combinations order, kf_workers.py:1325-1336) as a sortable key -- the device's lex_key."""
+    rev = int(format(mask, f"0{L}b")[::-1], 2) if L else 0
+    return (bin(mask).count("1") << 32) | (((1 << L) - 1) - rev)
 
 
 def _lerp_extrapolate(x, xp, fp):

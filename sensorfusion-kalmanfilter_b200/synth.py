@@ -158,3 +158,19 @@ def seed_noise(types, seed, sigma_imu=0.05, var_gps=3.0):
         rows[:, :3] = rng.normal(0.0, np.sqrt(var_gps), (ng, 3))
         out[g] = rows
     return out
+
+
+def write_gps_csv(path, time, lat, lon, alt):
+    """A `gps_data.csv` (hw5_1.py:28 schema: time, latitude, longitude, altitude; rows without a fix are
+    'nan') from float64 columns, written the way hw5_1.py writes it (csv.writer, repr of the floats), so a
+    log stored as arrays is rebuilt byte for byte."""
+    import csv
+
+    def txt(v):
+        return "nan" if np.isnan(v) else repr(float(v))
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["time", "latitude", "longitude", "altitude"])
+        for k in range(len(time)):
+            w.writerow([repr(float(time[k])), txt(lat[k]), txt(lon[k]), txt(alt[k])])
+    return path

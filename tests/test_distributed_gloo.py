@@ -33,6 +33,20 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     first, count = shard_range(1 << 10, world, rank)
     out = allgather_best(_fake_best(rank, first, count))
+    # the device-resident form of the same reduce (one all_gather_into_tensor of the raw 48-byte b200kf_best)
+    import ctypes
+    import torch
+    from sensorfusion_kalmanfilter_b200 import _lib
+    from sensorfusion_kalmanfilter_b200.distributed import allgather_best_device
+    fb = _fake_best(rank, first, count)
+    none = (1 << 64) - 1
+    raw = _lib.Best(fb["argmin_sum_score"], fb["argmin_sum_index"], fb["first_feasible_key"],
+                    none if fb["first_feasible_index"] is None else fb["first_feasible_index"], fb["n_feasible"],
+                    fb["n_near_threshold"])
+    best_d = torch.frombuffer(bytearray(bytes(raw)), dtype=torch.uint8).clone()
+    assert best_d.numel() == ctypes.sizeof(_lib.Best)
+    out2 = allgather_best_device(best_d)
+    assert out2 == out, (out2, out)
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()

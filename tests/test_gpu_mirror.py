@@ -296,3 +296,38 @@ def test_window_experiment_matches_reference_rows(golden):
     # a window that starts before the first GPS fix: the reference fails at :2316 and logs an ERROR row
     rows = run_window_experiment(k, [0], [0.5], start_offset=8, lb_end_idx=int(g["lb_end"]))
     assert rows[0]["final_greedy_log_det"] == "ERROR"
+
+
+def test_brute_force_epsilon_guard_settles_borderline_decisions_in_reference_arithmetic(bf):
+    """thresholds placed ONE ULP either side of a schedule's max log det as the
+    reference's numpy arithmetic computes it.  The kernel's value of that max differs by ~1e-13, so its
+    own strict comparison could go either way; the mirror must return what the reference's comparison
+    (kf_workers.py:1353-1358) returns -- here the oracle's loop-for-loop restatement of the driver."""
+    from oracle import kf_oracle as ko
+    k, g = bf
+    L, w0 = 9, int(g["w0"])
+    m = ko.get_model("CA15")
+    window = k.indexed_sensor_data[w0:w0 + L]
+    init = tuple(g["init_state"])
+    xt = np.zeros(15)
+    xt[0:6] = init[1:7]
+    # a small covariance: the log det GROWS over the gaps, so the max is a computed term, not the shared term 0
+    P0 = g["P0"] * 1e-4
+    t_end = k.indexed_sensor_data[w0 + L - 1][2]
+    order = [c for kk in range(1, L + 1) for c in itertools.combinations(range(L), kk)]
+    maxima = np.array([max(ko.worker_combo(m, tuple(window[i] for i in c), xt, P0, init[0], t_end)[3]) for c in order])
+    ld0 = np.linalg.slogdet(P0)[1]
+    assert np.sum(maxima > ld0 + 1e-6) > 100  # borderline candidates exist whose max is a computed term
+    n_guarded = 0
+    for r in (40, 130, 300):
+        # r-th distinct candidate: the threshold one ULP above its max makes it feasible, at its max infeasible
+        for thr in (np.nextafter(maxima[r], np.inf), maxima[r], np.nextafter(maxima[r], -np.inf)):
+            ref = ko.brute_force_select(m, window, xt, P0, init[0], t_end, float(thr))
+            out = k.run_brute_force_kalman_filter_no_sampling_min_usage(w0, w0 + L, float(thr), P0.copy(), init)
+            if ref is None:
+                assert out is None
+                continue
+            sel = tuple(e[0] - w0 for e in out["selected_sensors"])
+            assert sel == tuple(ref["selected_indices"]), (r, thr, sel, ref["selected_indices"])
+            n_guarded += out["n_rescored_on_host"] > 0
+    assert n_guarded >= 3  # the guard did run: these decisions were NOT taken from the kernel's rounding

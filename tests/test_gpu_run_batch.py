@@ -142,11 +142,28 @@ def test_gate_and_predict_only():
     eng = Engine("CA15")
     out = eng.run_batch(types, dts, payload, x0, P0, gate_threshold=thr, want_used=True, want_logdet=True)
     used = out["used"].cpu().numpy().astype(bool)
-    # decisions may only differ where the predicted log det is within rounding of the threshold
-    assert (used != ref["used"]).mean() < 1e-3
-    if np.array_equal(used, ref["used"]):
-        assert rel(out["x"].cpu().numpy(), ref["x"]) < RTOL64
-        assert rel(out["P"].cpu().numpy(), ref["P"]) < RTOL64
+    # A decision may differ from the oracle's only where the oracle's predicted log det sits within
+    # EPS of the threshold (a rounding difference could flip it); anywhere else a difference is a failure,
+    # and so is any difference in x / P of a filter whose decisions all agree.
+    EPS = 1e-9 * max(1.0, abs(thr))
+    xs, Ps = x0.copy(), P0.copy()
+    margin = np.full((T, N), np.inf)
+    for k in range(T):  # the oracle's gate quantity, step by step (kf_workers.py:1023-1025)
+        xp, Pp = ko.predict(m, xs, Ps, float(dts[k]))
+        s, l = ko.logdet(Pp)
+        margin[k] = np.abs(s * l - thr)
+        xu, Pu = ko.step(m, xs, Ps, int(types[k]), float(dts[k]), np.ascontiguousarray(payload[k].T))
+        g = ref["used"][k]
+        xs = np.where(g[:, None], xu, xp)
+        Ps = np.where(g[:, None, None], Pu, Pp)
+    differ = used != ref["used"]
+    for f in np.flatnonzero(differ.any(axis=0)):  # after its first flip a filter follows another path
+        k_first = int(np.argmax(differ[:, f]))
+        assert margin[k_first, f] <= EPS, "gate decision differs outside EPS of the threshold"
+    same = ~differ.any(axis=0)  # filters with identical decisions throughout
+    assert same.sum() >= N - 1  # at most a stray borderline filter, never the bulk
+    assert rel(out["x"].cpu().numpy()[same], ref["x"][same]) < RTOL64
+    assert rel(out["P"].cpu().numpy()[same], ref["P"][same]) < RTOL64
     assert 0.05 < used.mean() < 0.95
     types2 = np.full(T, 2, dtype=np.uint8)
     xs, Ps = x0.copy(), P0.copy()
