@@ -51,12 +51,15 @@ def parse():
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-traj", action="store_true")
     ap.add_argument("--no-shared", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config-2 (rate sweep) and config-5 (BIAS9) legs")
+    ap.add_argument("--passes-per-step", type=int, default=20,
+                    help="passes over the stream per bench step (one bench step = this many launches of the whole shard)")
     ap.add_argument("--traj-tsteps", type=int, default=1000, help="events per filter in the trajectory-mode leg")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return (f"{a.model} {a.filters} filters x {a.tsteps} steps per GPU, {a.precision}, GPS every 20th event "
+    return (f"{a.model} {a.filters} filters x {a.tsteps} steps per GPU and pass, {a.precision}, GPS every 20th event "
             f"(BASELINE configs[2]: 2^20 x 10k sharded over 8 GPUs)")
 
 
@@ -250,6 +253,246 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def _event_ms(evs):
+    return [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
+
+
+def _stats(ms):
+    ms = np.asarray(ms, dtype=np.float64)
+    return {"n": int(ms.size), "min": float(ms.min()), "median": float(np.median(ms)), "p90": float(np.percentile(ms, 90)),
+            "max": float(ms.max()), "mean": float(ms.mean()), "first_quarter_mean": float(ms[:max(1, ms.size // 4)].mean()),
+            "last_half_mean": float(ms[ms.size // 2:].mean())}
+
+
+def _timed_loop(fn, n, torch):
+    """n calls of fn with one CUDA event between consecutive calls (current stream); returns per-call ms."""
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    evs[0].record()
+    for i in range(n):
+        fn()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    return _event_ms(evs)
+
+
+def load_profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def search_window(L, seed=0):
+    rng = np.random.default_rng(seed)
+    stypes = np.where(np.arange(L) % 7 == 3, 0, 1).astype(np.uint8)
+    times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
+    return stypes, times
+
+
+def leg_search(torch, a, fma_peak_distinct):
+    """schedules scored / s (BASELINE configs[3]: all 2^20 subset schedules of a 20-event window, CA15) with the
+    FP64 view of the scoring kernel: executed FP64 thread-instructions per schedule (ncu, profiles/) x
+    schedules/s against the measured distinct-operand FMA peak."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    e15 = Engine("CA15")
+    L = 20
+    stypes, times = search_window(L)
+    P0 = e15.spec.default_P0() * 1e-3
+    t_prev, t_end = 999.995, float(times[-1])
+    # threshold = median of the per-schedule max over the first 2^16 schedules: some schedules are feasible,
+    # so the first-feasible-in-(cardinality, lexicographic)-order reduction does real work
+    _, per = e15.score_schedules(stypes, times, t_prev, t_end, P0, first=1, count=(1 << 16) - 1, want_per_schedule=True)
+    thr = float(per[:, 0].median().item())
+    del per
+    for _ in range(3):
+        e15.score_schedules(stypes, times, t_prev, t_end, P0, threshold=thr, device_result=True)
+    ms = _timed_loop(lambda: e15.score_schedules(stypes, times, t_prev, t_end, P0, threshold=thr, device_result=True),
+                     200, torch)
+    best, _ = e15.score_schedules(stypes, times, t_prev, t_end, P0, threshold=thr)
+    st = _stats(ms)
+    rate = (1 << L) / (st["mean"] * 1e-3)
+    out = {"metric": "schedules_scored_per_sec", "value": rate, "unit": "schedules/s",
+           "workload": "CA15, all 2^20 subset schedules of a 20-event window, 1 GPU, threshold = median of max "
+                       "(b200kf_score_schedules, result left on the device; 200 back-to-back searches)",
+           "ms": st["mean"], "ms_min": st["min"], "argmin_sum_index": best["argmin_sum_index"],
+           "first_feasible_index": best["first_feasible_index"], "n_feasible": best["n_feasible"],
+           "n_near_threshold": best["n_near_threshold"]}
+    prof = load_profile_json("r02_search_fp64.json")
+    if prof and "L20" in prof:
+        q = prof["L20"]
+        flop_per_sched = (2.0 * q["dfma"] + q["dmul"] + q["dadd"]) / q["schedules"]
+        ach = flop_per_sched * rate / 1e12
+        out["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fma_peak_distinct, "unit": "TFLOP/s",
+                           "frac": ach / fma_peak_distinct, "traffic": None,
+                           "fp64_thread_inst_per_schedule": (q["dfma"] + q["dmul"] + q["dadd"]) / q["schedules"],
+                           "flop_per_schedule": flop_per_sched, "kernel": q.get("kernel", "score_tree_kernel<CA15,sym>"),
+                           "peak_source": "b200kf_probe_fma_peak (distinct operands), measured in this run",
+                           "counts_from": "profiles/r02_search_fp64.json (ncu smsp__sass_thread_inst_executed_op_d*_pred_on)"}
+    return out
+
+
+def leg_search_large(torch, dist, a, world, dev, barrier, fma_peak_distinct, Ll):
+    """2^Ll subsets sharded over the ranks; the 48-byte result stays on the device until ONE all-gather + ONE
+    device->host copy (distributed.search_sharded)."""
+    from sensorfusion_kalmanfilter_b200.distributed import search_sharded
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    e15l = Engine("CA15")
+    stl, tml = search_window(Ll)
+    P0l = e15l.spec.default_P0() * 1e-3
+    t_prev, t_end = 999.995, float(tml[-1])
+    _, per = e15l.score_schedules(stl, tml, t_prev, t_end, P0l, first=1, count=(1 << 16) - 1, want_per_schedule=True)
+    thr = float(per[:, 0].median().item())
+    del per
+    reps = 3 if Ll <= 28 else 2
+    for _ in range(2):
+        bl = search_sharded(e15l, stl, tml, t_prev, t_end, P0l, thr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        bl = search_sharded(e15l, stl, tml, t_prev, t_end, P0l, thr)
+    torch.cuda.synchronize()
+    tl = (time.perf_counter() - t0) / reps
+    if world > 1:
+        tt = torch.tensor([tl], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tl = float(tt.item())
+    rate = (1 << Ll) / tl
+    out = {"metric": "schedules_scored_per_sec", "value": rate, "unit": "schedules/s",
+           "workload": f"CA15, all 2^{Ll} subset schedules of a {Ll}-event window sharded over {world} GPU(s), incl. the "
+                       "final all-gather + reduce + the one D2H (host wall clock, max over ranks)",
+           "ms": tl * 1e3, "first_feasible_index": bl["first_feasible_index"], "n_feasible": bl["n_feasible"],
+           "argmin_sum_index": bl["argmin_sum_index"]}
+    prof = load_profile_json("r02_search_fp64.json")
+    if prof and "L26" in prof:
+        q = prof["L26"]
+        flop_per_sched = (2.0 * q["dfma"] + q["dmul"] + q["dadd"]) / q["schedules"]
+        ach = flop_per_sched * rate / 1e12 / world
+        out["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fma_peak_distinct, "unit": "TFLOP/s per GPU",
+                           "frac": ach / fma_peak_distinct, "traffic": None, "flop_per_schedule": flop_per_sched,
+                           "note": "per-schedule FP64 count of the 2^26 capture (prefix sharing: ~1 filter step per schedule)"}
+    return out
+
+
+def leg_config5(torch, a, hbm_peak):
+    """BASELINE configs[4]: BIAS9, 262 144 filters x 50 000 steps, FP64 and FP32, every filter its own covariance.
+    314 GB (f64) of payload does not fit: ONE 10 000-step chunk is resident (63 GB / 31 GB, larger than L2) and is
+    replayed five times with the state carried (time-chunked launches, b200kf_run_batch + AGG_CONTINUE)."""
+    from sensorfusion_kalmanfilter_b200 import synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload
+    N, Tc, chunks = 262144, 10000, 5
+    out = {}
+    for prec in ("f64", "f32"):
+        os.environ["B200KF_SHARED"] = "0"
+        eng = Engine("BIAS9", precision=prec)
+        os.environ.pop("B200KF_SHARED", None)
+        sp = eng.spec
+        rb = 4 if prec == "f32" else 8
+        types, dts = synth.gps_imu_schedule(Tc)
+        types_d = torch.from_numpy(types).to(eng.device)
+        dts_d = torch.from_numpy(dts).to(eng.device)
+        pay = fill_payload(eng, types_d, N, seed=4321)
+        scale = 1.0 + (np.arange(N) % 1024) / 1024.0
+        x = torch.zeros((N, sp.n), dtype=eng.real, device=eng.device)
+        P = torch.from_numpy(sp.default_P0()[None] * scale[:, None, None]).to(device=eng.device, dtype=eng.real).contiguous()
+        agg = torch.zeros((N, 4), dtype=torch.float64, device=eng.device)
+
+        def job():
+            for c in range(chunks):
+                eng.run_batch(types_d, dts_d, pay, x, P, agg=agg if c else None, inplace=True)
+        job()
+        torch.cuda.synchronize()
+        ms = _timed_loop(job, 4, torch)
+        st = _stats(ms)
+        steps = float(N) * Tc * chunks
+        gbs = steps * sp.d * rb / (st["mean"] * 1e-3) / 1e9
+        out[prec] = {"value": steps / (st["mean"] * 1e-3), "unit": UNIT, "ms_per_job": st["mean"], "ms_min": st["min"],
+                     "algorithmic_bytes_per_filter_step": sp.d * rb, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+        del pay, x, P, agg, eng
+        torch.cuda.empty_cache()
+    out["workload"] = (f"BIAS9 {N} filters x {Tc * chunks} steps = {chunks} time chunks of {Tc} steps over one resident "
+                       "payload chunk, per-filter covariance, aggregates only")
+    return out
+
+
+def leg_config2(torch, a, hbm_peak):
+    """BASELINE configs[1] at full length: sampling rates 10..120 Hz x 4096 Monte-Carlo seeds of the 15-state filter
+    with greedy one-event-per-window scheduling (kf_workers.py:826-957) over the whole 2 808 s stream (589 679
+    events after the first fix).  174 GB of per-seed payload: time chunks, generated on the device per chunk
+    (base stream + N(0, 0.05^2) per seed) OUTSIDE the timed launches; the launches of every chunk are timed
+    with CUDA events and summed, the selection pass (once per stream) is timed with them."""
+    from sensorfusion_kalmanfilter_b200 import streams, synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    seeds, seconds = 4096, 2808.0
+    rates = list(range(10, 121, 10))
+    ev = synth.make_indexed_sensor_data(int(seconds * 210) + 3, seed=5)[3:]
+    ps = streams.PackedStream.from_events(ev)
+    del ev
+    eng = Engine("CA15")
+    dev = eng.device
+    base = torch.from_numpy(ps.data[1:]).to(dev)
+    E = int(base.shape[0])
+    gen = torch.Generator(device=dev).manual_seed(0)
+
+    def chunk(e0, e1):
+        return base[e0:e1, :, None] + 0.05 * torch.randn((e1 - e0, 9, seeds), generator=gen, device=dev, dtype=torch.float64)
+
+    x0 = np.zeros((seeds, 15))
+    x0[:, :3] = ps.data[0, :3]
+    P0 = eng.spec.default_P0()
+    res = {}
+    for use_gains in (False, True):
+        acc = {"ms": 0.0, "pairs": []}
+
+        def on_chunk(e0, e1, fn):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            fn()
+            s1.record()
+            acc["pairs"].append((s0, s1))
+
+        def run():
+            acc["pairs"] = []
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sel0, sel1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sel0.record()
+            # (the selection pass is inside scheduled_sweep_chunked; its time = total - chunk launches - generation)
+            out = eng.scheduled_sweep_chunked(ps.types[1:], ps.times[1:], rates, x0, P0, float(ps.times[0]), chunk, 25200,
+                                              use_gains=use_gains, on_chunk=on_chunk)
+            sel1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            launches = sum(p0.elapsed_time(p1) for p0, p1 in acc["pairs"])
+            return out, wall, launches, sel0.elapsed_time(sel1)
+
+        run()  # warm-up: engines, streams, allocator
+        out, wall, launches_ms, total_ms = run()
+        steps = float(sum(len(out[f]["sel"]) for f in rates)) * seeds
+        # time of the selection pass alone (covariance only, all rates in one launch)
+        types_d, times_d = torch.from_numpy(ps.types[1:]).to(dev), torch.from_numpy(ps.times[1:]).to(dev)
+        P0r = np.repeat(P0[None], len(rates), axis=0)
+        eng.select_greedy(types_d, times_d, [1.0 / f for f in rates], [float(ps.times[0])] * len(rates), P0r, want_gains=use_gains)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.select_greedy(types_d, times_d, [1.0 / f for f in rates], [float(ps.times[0])] * len(rates), P0r, want_gains=use_gains)
+        torch.cuda.synchronize()
+        sel_ms = (time.perf_counter() - t0) * 1e3
+        t_job = (sel_ms + launches_ms) * 1e-3
+        gbs = steps * 72.0 / t_job / 1e9
+        res["use_gains" if use_gains else "recursion_per_launch"] = {
+            "value": steps / t_job, "unit": UNIT, "filter_steps": steps, "selection_ms": sel_ms, "filter_launches_ms": launches_ms,
+            "job_ms": t_job * 1e3, "wall_s_incl_payload_generation": wall, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+            "algorithmic_bytes_per_filter_step": 72, "check_sum_logdet_120hz": float(out[120]["agg"][0, 1].item())}
+        del out
+    res["workload"] = (f"CA15, rates 10..120 Hz x {seeds} seeds = {len(rates) * seeds} filters over the {seconds:.0f} s stream "
+                       f"({E} events), greedy scheduling; {E // 25200 + 1} time chunks of 25 200 events (3.7 GB of payload each, "
+                       "generated on the device outside the timed launches)")
+    del base
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_gpu_arm(a):
     import torch
     import torch.distributed as dist
@@ -274,6 +517,7 @@ def run_gpu_arm(a):
     os.environ.pop("B200KF_SHARED", None)
     sp = eng.spec
     N, T = a.filters, a.tsteps
+    PPS = max(1, a.passes_per_step)
     rb = 4 if a.precision == "f32" else 8
     types, dts = synth.gps_imu_schedule(T)
     types_d = torch.from_numpy(types).to(dev)
@@ -284,7 +528,7 @@ def run_gpu_arm(a):
     p0_scale = 1.0 + (np.arange(N) % 1024) / 1024.0
     P = torch.from_numpy(sp.default_P0()[None] * p0_scale[:, None, None]).to(device=dev, dtype=eng.real).contiguous()
 
-    def one_step(mode):
+    def one_pass(mode):
         # state carries over from pass to pass (the filters keep running over the stream)
         eng.run_batch(types_d, dts_d, payload, x, P, mode=mode, inplace=True, want_agg=True)
 
@@ -293,98 +537,99 @@ def run_gpu_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        one_step(a.mode)
+    # ---- headline: K bench steps of PPS passes each, after W warm-up steps (W * PPS passes: ~0.5 s at the
+    # defaults, which takes the GPU from boost to its sustained, power-capped clock BEFORE the timed region)
+    for _ in range(a.warmup * PPS):
+        one_pass(a.mode)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_pass = a.steps * PPS
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_pass + 1)]
     barrier()
     w0 = time.time()
-    e0.record()
-    for _ in range(a.steps):
-        one_step(a.mode)
-    e1.record()
+    evs[0].record()
+    for i in range(n_pass):
+        one_pass(a.mode)
+        evs[i + 1].record()
     barrier()
     w1 = time.time()
-    ms = e0.elapsed_time(e1)
+    ms = evs[0].elapsed_time(evs[-1])
+    pass_ms = _event_ms(evs)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    # kernels of libb200kf launched per bench step: auto = chain_compat + pack_schedule + TMA filter kernel
+    # kernels of libb200kf launched per pass: auto = chain_compat + pack_schedule + TMA filter kernel
     # + dense kernel (exits at once); decoupled = pack_schedule + TMA kernel; dense = 1
     tma_on = os.environ.get("B200KF_TMA", "1") != "0" and a.model in ("CV6", "BIAS9")  # models with a per-filter ring kernel
     sym_k = tma_on and os.environ.get("B200KF_SYM", "1") != "0"
-    launches_per_step = {"auto": 3 + tma_on + sym_k, "decoupled": 1 + tma_on, "symmetric": 1 + tma_on, "dense": 1}[a.mode]
-    total_steps = float(world) * N * T * a.steps
+    launches_per_pass = {"auto": 3 + tma_on + sym_k, "decoupled": 1 + tma_on, "symmetric": 1 + tma_on, "dense": 1}[a.mode]
+    total_steps = float(world) * N * T * n_pass
     value = total_steps / (ms * 1e-3)
 
     line = None
+    roofline = traj_mode = shared_mode = None
+    hbm_peak, peak_src = load_peaks()
+    fma_peak = fma_peak_distinct = None
     if rank == 0:
-        # ---- dominant kernel alone (decoupled/dense as dispatched), CUDA events on the launch stream
+        # ---- dominant kernel alone, straight after the timed region (same sustained clock state), one CUDA event
+        # per launch on the launch stream
         # (auto resolves to the axis-symmetric kernel for this workload: P0 and the rates are the same on x, y, z)
         sym_on = os.environ.get("B200KF_SYM", "1") != "0" and tma_on
         sym_any = os.environ.get("B200KF_SYM", "1") != "0"  # every model has an axis-symmetric form (LDG kernel if not CV6)
         kmode = a.mode if a.mode != "auto" else ("symmetric" if (sym_on or (sym_any and a.model != "CV6")) else "decoupled")
-        for _ in range(2):
-            one_step(kmode)
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(3, a.steps)
-        k0.record()
-        for _ in range(reps):
-            one_step(kmode)
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
-        hbm_peak, peak_src = load_peaks()
+        k_reps = max(20, min(200, n_pass // 2))
+        kms_all = _timed_loop(lambda: one_pass(kmode), k_reps, torch)
+        kst = _stats(kms_all)
+        # forced modes launch pack_schedule (a few microseconds) + the filter kernel: the filter kernel's share of a
+        # pass comes from the committed ncu launch list of this very command (profiles/r02_launches.csv)
+        kms = kst["mean"]
         alg_bytes = float(N) * T * sp.d * rb + float(N) * (2 * (sp.n + sp.n * sp.n) * rb + 32)
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         fma_peak = probe_fma_peak(a.precision)
         fma_peak_distinct = probe_fma_peak(a.precision, distinct_operands=True)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel": (f"kf_run_tma_kernel<{a.model},{a.precision},{'sym' if kmode == 'symmetric' else 'per-chain'}>" if tma_on and kmode != "dense"
-                               else f"kf_run_kernel<{a.model},{kmode},{a.precision},agg>"),
-                    "kernel_ms": kms, "algorithmic_bytes_per_filter_step": sp.d * rb,
+                    "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                    "kernel": (f"kf_run_tma_kernel<{a.model},{a.precision},{'sym' if kmode == 'symmetric' else 'per-chain'}>"
+                               if tma_on and kmode != "dense" else f"kf_run_kernel<{a.model},{kmode},{a.precision},agg>"),
+                    "kernel_ms": kms, "kernel_ms_stats": kst, "timing": f"{k_reps} back-to-back launches right after the timed "
+                    "region (sustained clocks), mean; frac_burst from the fastest launch",
+                    "frac_burst": alg_bytes / (kst["min"] * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes_per_filter_step": sp.d * rb,
                     "fp_pipe": {"measured_fma_peak_tflops": fma_peak,
-                                "measured_fma_peak_distinct_operands_tflops": fma_peak_distinct, "kernel_filter_steps_per_s": N * T / (kms * 1e-3)}}
-
+                                "measured_fma_peak_distinct_operands_tflops": fma_peak_distinct,
+                                "kernel_filter_steps_per_s": N * T / (kms * 1e-3)}}
         roofline["traffic"] = load_traffic(a, roofline["kernel"])
 
         # ---- trajectory mode: per-step (x[0:6], log det) written out as the reference does
         # (kf_workers.py:714-717): 24 B in + 56 B out per filter-step
-        traj_mode = None
         if not a.no_traj:
             Tt = min(a.traj_tsteps, T)
             xt = torch.zeros((N, sp.n), dtype=eng.real, device=dev)
             Pt = P.clone()
-            for _ in range(2):
+
+            def traj_pass():
                 o = eng.run_batch(types_d[:Tt], dts_d[:Tt], payload[:Tt], xt, Pt, want_agg=False, traj_ncomp=6,
                                   want_logdet=True, inplace=True, mode=a.mode)
                 del o
-            torch.cuda.synchronize()
-            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0e.record()
             for _ in range(3):
-                o = eng.run_batch(types_d[:Tt], dts_d[:Tt], payload[:Tt], xt, Pt, want_agg=False, traj_ncomp=6,
-                                  want_logdet=True, inplace=True, mode=a.mode)
-                del o
-            t1e.record()
+                traj_pass()
             torch.cuda.synchronize()
-            tms = t0e.elapsed_time(t1e) / 3
+            tst = _stats(_timed_loop(traj_pass, 300, torch))
+            tms = tst["mean"]
             tbytes = float(N) * Tt * (sp.d + 7) * rb
-            traj_mode = {"value": N * Tt / (tms * 1e-3), "unit": UNIT, "workload": f"{N} filters x {Tt} steps, traj[0:6] + logdet out",
-                         "ms": tms, "algorithmic_bytes_per_filter_step": (sp.d + 7) * rb,
+            traj_mode = {"value": N * Tt / (tms * 1e-3), "unit": UNIT, "workload": f"{N} filters x {Tt} steps, traj[0:6] + logdet out, "
+                         "300 back-to-back launches", "ms": tms, "ms_stats": tst, "algorithmic_bytes_per_filter_step": (sp.d + 7) * rb,
                          "achieved_gbs": tbytes / (tms * 1e-3) / 1e9, "frac_of_hbm_peak": tbytes / (tms * 1e-3) / 1e9 / hbm_peak,
+                         "frac_burst": tbytes / (tst["min"] * 1e-3) / 1e9 / hbm_peak,
                          "includes": "output allocation by the caching allocator + chain-compat check + kernel"}
             del xt, Pt
 
         # ---- shared-covariance leg: all filters start from the SAME P0 (SURVEY 8(d) config 3 as written;
         # Monte-Carlo seeds of one configuration): AUTO runs ONE covariance / gain recursion per launch
-        shared_mode = None
         if os.environ.get("B200KF_TMA", "1") != "0" and os.environ.get("B200KF_SHARED", "1") != "0" and not a.no_shared:
             eng_sh = Engine(a.model, precision=a.precision)
             xs = torch.zeros((N, sp.n), dtype=eng.real, device=dev)
@@ -392,15 +637,11 @@ def run_gpu_arm(a):
             for _ in range(2):
                 eng_sh.run_batch(types_d, dts_d, payload, xs, Ps, mode="auto", inplace=True)
             torch.cuda.synchronize()
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            h0.record()
-            for _ in range(reps):
-                eng_sh.run_batch(types_d, dts_d, payload, xs, Ps, mode="auto", inplace=True)
-            h1.record()
-            torch.cuda.synchronize()
-            hms = h0.elapsed_time(h1) / reps
-            shared_mode = {"value": N * T / (hms * 1e-3), "unit": UNIT, "ms": hms,
-                           "workload": f"{N} filters x {T} steps, identical P0 for every filter, mode auto "
+            hst = _stats(_timed_loop(lambda: eng_sh.run_batch(types_d, dts_d, payload, xs, Ps, mode="auto", inplace=True),
+                                     100, torch))
+            hms = hst["mean"]
+            shared_mode = {"value": N * T / (hms * 1e-3), "unit": UNIT, "ms": hms, "ms_stats": hst,
+                           "workload": f"{N} filters x {T} steps, identical P0 for every filter, mode auto, 100 back-to-back launches "
                                        f"(chain-compat check + {'kf_run_shared_kernel' if a.model == 'CV6' else 'kf_run_shared_generic_kernel'})",
                            "achieved_gbs": alg_bytes / (hms * 1e-3) / 1e9,
                            "frac_of_hbm_peak": alg_bytes / (hms * 1e-3) / 1e9 / hbm_peak}
@@ -418,7 +659,7 @@ def run_gpu_arm(a):
         torch.cuda.synchronize()
         for _ in range(2):
             eng.run_batch_host(types[:Te], dts[:Te], pay_h, x_h, P_h, mode=a.mode, inplace=True)
-        reps_e = max(3, min(a.steps, 10))
+        reps_e = max(10, min(a.steps, 30))
         barrier()
         t0 = time.perf_counter()
         for _ in range(reps_e):
@@ -433,66 +674,37 @@ def run_gpu_arm(a):
         d2h = N * (sp.n + sp.n * sp.n) * rb + N * 36
         e2e = {"value": world * N * Te / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "workload": f"{N} filters x {Te} steps per call per GPU, pinned host buffers, "
-               "all ranks concurrently, max over ranks", "ms_per_call": te * 1e3,
+               f"all ranks concurrently, max over ranks, {reps_e} calls", "ms_per_call": te * 1e3,
                "host_gbs_per_gpu": (h2d + d2h) / te / 1e9, "check_sum_logdet": float(res["agg"][:, 1].mean()),
                "rank0_numa_node": numa_node}
+        if rank == 0 and world == 1:
+            # what a drop-in caller does: plain (pageable) numpy arrays in and out
+            pay_p = pay_h.numpy().copy()
+            x_p, P_p = np.zeros((N, sp.n), dtype=pay_p.dtype), P_h.numpy().copy()
+            eng.run_batch_host(types[:Te], dts[:Te], pay_p, x_p, P_p, mode=a.mode, inplace=True)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                eng.run_batch_host(types[:Te], dts[:Te], pay_p, x_p, P_p, mode=a.mode, inplace=True)
+            tp = (time.perf_counter() - t0) / 3
+            e2e["pageable_numpy"] = {"value": N * Te / tp, "unit": UNIT, "ms_per_call": tp * 1e3,
+                                     "host_gbs": (h2d + d2h) / tp / 1e9}
+            del pay_p, x_p, P_p
         del pay_h
 
-    # ---- larger horizon where several GPUs matter: 2^26 subsets sharded over the ranks, one 48-byte
-    # all-gather + deterministic reduce at the end (distributed.search_sharded)
-    search_large = None
+    # ---- larger horizons where several GPUs matter: 2^26 and 2^32 subsets sharded over the ranks
+    search_large = search_huge = None
     if not a.no_search:
-        from sensorfusion_kalmanfilter_b200.distributed import search_sharded
-        e15l = Engine("CA15")
-        Ll = 26
-        rngl = np.random.default_rng(0)
-        stl = np.where(np.arange(Ll) % 7 == 3, 0, 1).astype(np.uint8)
-        tml = 1000.0 + np.cumsum(0.005 + 0.0005 * rngl.random(Ll))
-        P0l = e15l.spec.default_P0() * 1e-3
-        for _ in range(2):
-            bl = search_sharded(e15l, stl, tml, 999.995, float(tml[-1]), P0l, -74.0)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            bl = search_sharded(e15l, stl, tml, 999.995, float(tml[-1]), P0l, -74.0)
-        torch.cuda.synchronize()
-        tl = (time.perf_counter() - t0) / 3
-        if world > 1:
-            tt = torch.tensor([tl], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            tl = float(tt.item())
-        search_large = {"metric": "schedules_scored_per_sec", "value": (1 << Ll) / tl, "unit": "schedules/s",
-                        "workload": f"CA15, 2^{Ll} subset schedules of a {Ll}-event window sharded over {world} GPU(s), "
-                                    "incl. the final all-gather + reduce (host wall clock, max over ranks)",
-                        "ms": tl * 1e3, "first_feasible_index": bl["first_feasible_index"], "n_feasible": bl["n_feasible"]}
+        if rank == 0 and fma_peak_distinct is None:
+            fma_peak_distinct = probe_fma_peak("f64", distinct_operands=True)
+        fpd = fma_peak_distinct if fma_peak_distinct else 1.0
+        search_large = leg_search_large(torch, dist, a, world, dev, barrier, fpd, 26)
+        search_huge = leg_search_large(torch, dist, a, world, dev, barrier, fpd, 32)
 
     if rank == 0:
-        # ---- secondary metric: schedules scored / s (BASELINE configs[3]: 2^20 schedules, L = 20, CA15)
-        search = None
+        search = products = None
         if not a.no_search:
-            e15 = Engine("CA15")
-            L = 20
-            rng = np.random.default_rng(0)
-            stypes = np.where(np.arange(L) % 7 == 3, 0, 1).astype(np.uint8)
-            times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
-            P0 = e15.spec.default_P0() * 1e-3
-            for _ in range(2):
-                e15.score_schedules(stypes, times, 999.995, float(times[-1]), P0, threshold=0.0)
-            torch.cuda.synchronize()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(5):
-                best, _ = e15.score_schedules(stypes, times, 999.995, float(times[-1]), P0, threshold=0.0)
-            s1.record()
-            torch.cuda.synchronize()
-            sms = s0.elapsed_time(s1) / 5
-            search = {"metric": "schedules_scored_per_sec", "value": (1 << L) / (sms * 1e-3), "unit": "schedules/s",
-                      "workload": "CA15, 2^20 subset schedules of a 20-event window, 1 GPU", "ms": sms,
-                      "argmin_sum_index": best["argmin_sum_index"]}
-
-        # ---- the notebook's product-of-queues brute force (RMSE objective): sequences scored / s
-        products = None
-        if not a.no_search:
+            search = leg_search(torch, a, fma_peak_distinct)
+            # ---- the notebook's product-of-queues brute force (RMSE objective): sequences scored / s
             e15p = Engine("CA15")
             Wp, qp = 10, 4
             rngp = np.random.default_rng(0)
@@ -504,17 +716,17 @@ def run_gpu_arm(a):
             for _ in range(2):
                 bp, _ = e15p.score_products([qp] * Wp, typ, tmp, payp, refp, np.zeros(15), P0p)
             torch.cuda.synchronize()
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
-            for _ in range(5):
-                bp, _ = e15p.score_products([qp] * Wp, typ, tmp, payp, refp, np.zeros(15), P0p)
-            p1.record()
-            torch.cuda.synchronize()
-            pms = p0.elapsed_time(p1) / 5
-            products = {"metric": "sequences_scored_per_sec", "value": qp ** Wp / (pms * 1e-3), "unit": "sequences/s",
+            pst = _stats(_timed_loop(lambda: e15p.score_products([qp] * Wp, typ, tmp, payp, refp, np.zeros(15), P0p), 50, torch))
+            products = {"metric": "sequences_scored_per_sec", "value": qp ** Wp / (pst["mean"] * 1e-3), "unit": "sequences/s",
                         "workload": f"CA15, {Wp} windows x {qp} candidates = {qp ** Wp} sequences, RMSE objective "
-                                    "(KF_SensorFusion.ipynb:804-954), incl. host<->device hand-off of the call", "ms": pms,
+                                    "(KF_SensorFusion.ipynb:804-954), incl. host<->device hand-off of the call", "ms": pst["mean"],
                         "best_index": bp["index"]}
+
+        # the big legs need the memory of the headline buffers
+        del payload, x, P
+        torch.cuda.empty_cache()
+        config5 = leg_config5(torch, a, hbm_peak) if not a.no_configs else None
+        config2 = leg_config2(torch, a, hbm_peak) if not a.no_configs else None
 
         cpu = None
         if not a.no_cpu_baseline:
@@ -535,14 +747,24 @@ def run_gpu_arm(a):
                    "sample": f"{cores} processes x {fpc} filters x 10000 events, per-filter numpy float64 loop "
                              f"(oracle port of kf_workers.py:681-721 for {a.model}); {dt:.1f} s"}
 
+        pst_ = _stats(pass_ms)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.precision, "data": "synthetic (device-generated payload, GPS ~N(0,3), accel ~N(0,0.1^2))",
-                "config": {"workload": workload_name(a), "mode": a.mode, "p0": "per-filter (reference P0 x (1 + (f % 1024)/1024)); shared-covariance kernel disabled for the headline", "l2": "inputs (31.5 GB at defaults) larger than L2; no flush",
-                           "filters_per_gpu": N, "events_per_filter": T, "payload_layout": "[T, d, N] time-major"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
-                "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large, "product_search": products,
-                "trajectory_mode": traj_mode, "shared_covariance": shared_mode}
+                "config": {"workload": workload_name(a), "mode": a.mode,
+                           "step": f"one bench step = {PPS} passes of the {N} filters over the {T}-event stream, state carried from "
+                                   f"pass to pass ({N * T * PPS:.3g} filter-steps per step and GPU)",
+                           "passes_per_step": PPS,
+                           "p0": "per-filter (reference P0 x (1 + (f % 1024)/1024)); shared-covariance kernel disabled for the headline",
+                           "l2": "inputs (31.5 GB at defaults) larger than L2; no flush",
+                           "filters_per_gpu": N, "events_per_filter_per_pass": T, "payload_layout": "[T, d, N] time-major"},
+                "timed_region_s": ms * 1e-3, "pass_ms": pst_,
+                "value_burst": float(world) * N * T / (pst_["min"] * 1e-3),
+                "value_last_half": float(world) * N * T / (pst_["last_half_mean"] * 1e-3),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_pass * n_pass,
+                "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large,
+                "search_2p32": search_huge, "product_search": products,
+                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "config5": config5, "config2": config2}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

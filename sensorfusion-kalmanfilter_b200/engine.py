@@ -498,6 +498,90 @@ class Engine:
         return {f: out[f] for f in rates}
 
 
+    def scheduled_sweep_chunked(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events, *,
+                                use_gains=False, on_chunk=None):
+        """scheduled_sweep over a stream whose per-seed payload does not fit the device at once (BASELINE
+        configs[1] at full length: 589 679 events x 9 channels x 4096 seeds = 174 GB): ONE selection pass over
+        the whole stream (it never reads a measurement), then time chunks of `chunk_events` events;
+        `payload_chunk(e0, e1)` returns that chunk's payload [e1 - e0, d, N] on the device (the caller
+        generates / uploads it), and every rate's filters carry x, P and the log-det aggregates from chunk to
+        chunk.  Returns {rate: dict(sel, x, P, agg)}; `on_chunk(e0, e1, fn)` -- if given -- is called with the
+        chunk's launch work as a callable so that a caller can time the launches apart from the payload
+        generation."""
+        torch = _torch()
+        sp = self.spec
+        rates = list(rates)
+        types = np.ascontiguousarray(types, dtype=np.uint8)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        E = len(types)
+        types_d = self._dev(types, torch.uint8)
+        times_d = self._dev(times, torch.float64)
+        P0 = np.asarray(P0, dtype=np.float64)
+        got = self.select_greedy(types_d, times_d, [1.0 / f for f in rates], [t_prev] * len(rates),
+                                 np.repeat(P0[None], len(rates), axis=0), want_gains=use_gains)
+        sels, P_fin, recs = got if use_gains else (got[0], got[1], None)
+        x0_d = self._dev(x0, self.real)
+        N = int(x0_d.shape[0])
+        if recs is not None and (N * (4 if sp.precision == "f32" else 8)) % 16 != 0:
+            recs = None
+        pool = getattr(self, "_sweep_engines", [])
+        while len(pool) < len(rates) - 1:
+            pool.append(Engine(self.spec, device=self.device.index))
+        self._sweep_engines = pool
+        engines = [self] + pool[:len(rates) - 1]
+        spool = getattr(self, "_sweep_streams", [])
+        while len(spool) < len(rates):
+            spool.append(torch.cuda.Stream(device=self.device))
+        self._sweep_streams = spool
+        cur = torch.cuda.current_stream(self.device)
+        sel_d = [torch.from_numpy(sel.astype(np.int64)).to(self.device) for sel in sels]
+        seltimes = [times[sel] for sel in sels]
+        st = [{"x": x0_d.clone(), "P": None if recs is not None else self._dev(np.repeat(P0[None], N, axis=0), self.real),
+               "agg": None, "done": 0, "prev": float(t_prev)} for _ in rates]
+        order = sorted(range(len(rates)), key=lambda j: -len(sels[j]))
+        for e0 in range(0, E, int(chunk_events)):
+            e1 = min(E, e0 + int(chunk_events))
+            pay_d = payload_chunk(e0, e1)
+
+            def launches(e0=e0, e1=e1, pay_d=pay_d):
+                for i in order:
+                    s_i = st[i]
+                    j0 = s_i["done"]
+                    j1 = int(np.searchsorted(sels[i], e1, side="left"))  # selected events inside this chunk
+                    if j1 == j0:
+                        continue
+                    stream = spool[i]
+                    stream.wait_stream(cur)
+                    with torch.cuda.stream(stream):
+                        rows = (sel_d[i][j0:j1] - e0).to(torch.int32)
+                        if recs is not None:
+                            r = engines[i].run_gains(recs[i, j0:j1], pay_d, s_i["x"], agg=s_i["agg"], stream=stream,
+                                                     step_rows=rows, inplace=True)
+                        else:
+                            tsel = seltimes[i][j0:j1]
+                            dts = np.diff(tsel, prepend=s_i["prev"])  # float64 on the host, as the reference (:914)
+                            r = engines[i].run_batch(types[sels[i][j0:j1]], dts, pay_d, s_i["x"], s_i["P"], agg=s_i["agg"],
+                                                     stream=stream, step_rows=rows, inplace=True)
+                            s_i["P"] = r["P"]
+                        s_i["x"], s_i["agg"] = r["x"], r["agg"]
+                        s_i["prev"] = float(seltimes[i][j1 - 1])
+                        s_i["done"] = j1
+                for stream in spool[:len(rates)]:
+                    cur.wait_stream(stream)
+
+            if on_chunk is not None:
+                on_chunk(e0, e1, launches)
+            else:
+                launches()
+            pay_d.record_stream(cur)
+            del pay_d
+        out = {}
+        for i, f in enumerate(rates):
+            P = st[i]["P"] if recs is None else P_fin[i].to(self.real).expand(N, sp.n, sp.n)
+            out[f] = {"sel": sels[i], "x": st[i]["x"], "P": P, "agg": st[i]["agg"]}
+        return out
+
+
 def cov_update(Sigma, rows, H, R, device=None, stream=None):
     """Batched Scheduler.cov_matrix (b200kf_cov_update).  Sigma [B, n, n] (numpy or torch), rows:
     0-based selected rows of (H, R).  Returns (Sigma_post [B,n,n], trace [B]) torch CUDA f64."""

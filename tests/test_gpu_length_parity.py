@@ -174,6 +174,38 @@ def test_config2_full_length_sweep_vs_reference(config2, use_gains):
             assert abs(max(a[0], ld0) - ref_agg[0]) < 1e-9 * max(1.0, abs(ref_agg[0]))
 
 
+@pytest.mark.parametrize("use_gains", [False, True])
+def test_config2_full_length_time_chunked_sweep_vs_reference(config2, use_gains):
+    """The same sweep in time chunks with state carried between them (how 4096 seeds x 589 679 events, 174 GB of
+    payload, run on one GPU): final covariance and the log-det aggregates against the reference, and the
+    final state against the one-launch sweep."""
+    import torch
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    g, ev, ps, noise = config2
+    rates = [int(r) for r in g["rates"]]
+    seeds = [int(s) for s in g["seeds"]]
+    eng = Engine("CA15")
+    data = np.stack([ps.data + z for z in noise], axis=2)
+    pay = torch.from_numpy(np.ascontiguousarray(data[1:])).to(eng.device)
+    x0 = np.zeros((len(seeds), 15))
+    x0[:, :3] = data[0, :3, :].T
+    P0 = eng.spec.default_P0()
+    one = eng.scheduled_sweep(ps.types[1:], ps.times[1:], pay, rates, x0, P0, float(ps.times[0]), use_gains=use_gains)
+    out = eng.scheduled_sweep_chunked(ps.types[1:], ps.times[1:], rates, x0, P0, float(ps.times[0]),
+                                      lambda e0, e1: pay[e0:e1], 70001, use_gains=use_gains)
+    ld0 = np.linalg.slogdet(P0)[1]
+    for f in rates:
+        np.testing.assert_array_equal(np.asarray(out[f]["sel"], dtype=np.int64) + 1,
+                                      np.cumsum(g[f"r{f}_sel_delta"].astype(np.int64)))
+        assert relmax(out[f]["x"].cpu().numpy(), one[f]["x"].cpu().numpy()) < 1e-12
+        for j, s in enumerate(seeds):
+            assert relmax(out[f]["P"][j].cpu().numpy(), g[f"r{f}_s{s}_P"]) < 1e-9
+            a, ref_agg = out[f]["agg"][j].cpu().numpy(), g[f"r{f}_s{s}_agg"]
+            assert abs(a[1] - (ref_agg[1] - ld0)) < 1e-9 * abs(ref_agg[1] - ld0)
+            assert abs(a[2] - ref_agg[2]) < 1e-9 * max(1.0, abs(ref_agg[2]))
+            assert a[3] == int(g[f"r{f}_s{s}_n_states"]) - 1
+
+
 @pytest.mark.parametrize("rate,seed", [(10, 1), (120, 2)])
 def test_config2_full_length_reference_facing_method(config2, rate, seed):
     from oracle.make_golden import arrays_to_events
