@@ -7,6 +7,8 @@
 #include <cstring>
 #include <new>
 
+#include <mutex>
+
 #include "kf_internal.h"
 
 namespace b200kf {
@@ -488,6 +490,35 @@ int b200kf_model_default_desc(int32_t model_id, int32_t precision, b200kf_model_
   return B200KF_OK;
 }
 
+// One stream-ordered scratch pool per DEVICE, created on first use and kept for the life of the process
+// (release threshold = max: a steady-state call sequence never reaches the driver's allocator).  It is shared by
+// every model on the device -- stream-ordered allocations of different models / streams never alias -- and is
+// never destroyed: destroying a per-model pool with frees still in flight (an Engine dropped right after an
+// asynchronous launch) crashed the process on the GPU box.
+static cudaError_t scratch_pool_for(int device, cudaMemPool_t* out) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(mu);
+  if (pools[device] == nullptr) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = ~0ULL;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) return e;
+    pools[device] = pool;
+  }
+  *out = pools[device];
+  return cudaSuccess;
+}
+
 int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   if (!desc || !out) return set_error(B200KF_ERR_INVALID, "null argument");
   if (desc->model_id < 0 || desc->model_id >= MODEL_COUNT)
@@ -524,6 +555,10 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   m->tpb = 64;
   m->use_tma = 1;
   if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
+  m->use_select_warp = 1;
+  if (const char* s = getenv("B200KF_SELECT_WARP")) m->use_select_warp = atoi(s) != 0;
+  m->use_bulk_out = 1;
+  if (const char* s = getenv("B200KF_BULK_OUT")) m->use_bulk_out = atoi(s) != 0;
   m->use_sym = 1;
   if (const char* s = getenv("B200KF_SYM")) m->use_sym = atoi(s) != 0;
   m->ring_f_cap = 896;
@@ -538,21 +573,8 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   }
   e = cudaGetDevice(&m->device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
-  if (e == cudaSuccess) {
-    cudaMemPoolProps props;
-    memset(&props, 0, sizeof(props));
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = m->device;
-    e = cudaMemPoolCreate(&m->pool, &props);
-    if (e == cudaSuccess) {
-      unsigned long long keep = ~0ULL;  // never trim: the per-call scratch is re-used call after call
-      e = cudaMemPoolSetAttribute(m->pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
+  if (e == cudaSuccess) e = scratch_pool_for(m->device, &m->pool);
   if (e != cudaSuccess) {
-    if (m->pool) cudaMemPoolDestroy(m->pool);
     delete m;
     return cuda_fail(e, "b200kf_model_create");
   }
@@ -562,7 +584,8 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
 
 int b200kf_model_destroy(b200kf_model* m) {
   if (!m) return B200KF_OK;
-  if (m->pool) cudaMemPoolDestroy(m->pool);
+  // (the scratch pool belongs to the device, not to the model: a model may be destroyed while its last
+  // launches -- and their stream-ordered scratch frees -- are still in flight)
   if (m->host_ws.slab) cudaFree(m->host_ws.slab);
   if (m->host_ws.ready) {
     cudaStreamDestroy(m->host_ws.s_copy);

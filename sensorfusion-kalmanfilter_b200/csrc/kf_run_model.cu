@@ -273,6 +273,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
       : "memory");
 }
 
+// shared -> global bulk store (the per-step outputs of the trajectory mode leave the SM as whole rows)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // all but the N latest groups have READ their shared-memory source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make this thread's shared-memory writes visible to the async proxy (the bulk-copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Ring shape of the per-filter kernel WITH an output ring (trajectory mode through bulk stores): 4 input stages
+// and 2 output stages of the same number of steps; at F = 896 float64 that is 4 x 21 KB in + 2 x 7 KB x rows out
+// (rows <= kBulkMaxRows).  Smaller CTAs / float32 keep the bytes and take more steps per stage.
+constexpr int kBulkInStages = 4;
+constexpr int kOutStages = 2;
+constexpr int kBulkMaxRows = 8;
+template <typename real, int F>
+constexpr int bulk_chunk() {
+  return (896 / F) * (sizeof(real) == 4 ? 2 : 1);
+}
+
 // Per-step records of the launch: (dt, type) plus the warp-uniform constants of the lean symmetric
 // step (Sym2Filter::LeanRec), which depend only on dt and the group's (q, r): evaluated once per
 // step here instead of once per step and filter.
@@ -357,17 +382,23 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
 #endif
 constexpr int kCopyWarps = B200KF_COPY_WARPS;
 
-template <int MODEL, typename real, bool SYM, bool FULL, int F>
+template <int MODEL, typename real, bool SYM, bool FULL, int F, bool BULK = false>
 __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
     kf_run_tma_kernel(const RunParams p, const LeanRecT<real>* __restrict__ sched) {
   // F math threads (filters) per CTA: 896 fills an SM with one CTA; 448 / 224 keep every SM busy when a
   // GPU's shard is small (N <= 148 * 448), with a proportionally deeper ring in the same shared memory
+  // BULK (per-step outputs only): the math threads write a step's outputs (trajectory rows, log det) into a
+  // shared-memory OUTPUT ring and the last service warp stores them with cp.async.bulk.global.shared -- whole
+  // 7 KB rows, no per-thread global stores in the loop (the per-thread STGs of the plain FULL kernel back up
+  // the store queue: long-scoreboard waits of 6.6 per issue, profiles/r01c_ncu_trajectory_kernel.txt).
+  static_assert(!BULK || FULL, "the output ring belongs to the per-step-output kernel");
   constexpr int kTmaThreads = F;
-  constexpr int kStages = ring_stages<real, F>();
-  constexpr int kChunk = ring_chunk<real, F>();
+  constexpr int kStages = BULK ? kBulkInStages : ring_stages<real, F>();
+  constexpr int kChunk = BULK ? bulk_chunk<real, F>() : ring_chunk<real, F>();
+  constexpr int kLoadWarps = BULK ? kCopyWarps - 1 : kCopyWarps;  // BULK: the last service warp stores
   // a copy lane waits on a stage's empty barrier by phase PARITY: that is only unambiguous while it can
-  // never be two uses of a stage ahead, i.e. while its stride (kCopyWarps chunks) is within one ring turn
-  static_assert(kStages >= kCopyWarps, "ring shallower than the copy lanes' stride");
+  // never be two uses of a stage ahead, i.e. while its stride (kLoadWarps chunks) is within one ring turn
+  static_assert(kStages >= kLoadWarps && kLoadWarps >= 1, "ring shallower than the copy lanes' stride");
   using MT = ModelTraits<MODEL, false, real>;
   using Flt = typename TmaFlt<MODEL, real, SYM>::type;
   constexpr int n = MT::n;
@@ -379,9 +410,16 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
   real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kStages][kChunk][D][kTmaThreads]
   constexpr size_t kStageReals = static_cast<size_t>(kChunk) * D * kTmaThreads;
   using Rec = LeanRecT<real>;
-  Rec* sched_buf = reinterpret_cast<Rec*>(stage_buf + kStages * kStageReals);  // [kStages][kChunk]
+  // output ring (BULK): [kOutStages][kChunk][out_rows][kTmaThreads], rows = the trajectory components, then log det
+  const int out_nc = (FULL && p.traj != nullptr) ? p.traj_ncomp : 0;
+  const int out_rows = out_nc + ((FULL && p.logdet != nullptr) ? 1 : 0);
+  real* out_buf = stage_buf + kStages * kStageReals;
+  const size_t out_stage_reals = BULK ? static_cast<size_t>(kChunk) * out_rows * kTmaThreads : 0;
+  Rec* sched_buf = reinterpret_cast<Rec*>(out_buf + (BULK ? kOutStages : 0) * out_stage_reals);  // [kStages][kChunk]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(sched_buf + kStages * kChunk);
   unsigned long long* empty = full + kStages;
+  unsigned long long* out_full = empty + kStages;     // BULK: a chunk's outputs are staged (all math warps arrived)
+  unsigned long long* out_empty = out_full + kOutStages;  // BULK: the stage's bulk stores have read it
 
   const int tid = threadIdx.x;
   const long long N = p.n_filters;
@@ -397,17 +435,49 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kTmaThreads / 32);
     }
+    if constexpr (BULK) {
+      for (int s = 0; s < kOutStages; ++s) {
+        mbar_init(&out_full[s], kTmaThreads / 32);
+        mbar_init(&out_empty[s], 1);
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (tid >= kTmaThreads) {
     // ---- copy warps: one lane each keeps the ring full, decoupled from the math warps' progress ----
-    if (((tid - kTmaThreads) & 31) == 0)
+    const int sw = (tid - kTmaThreads) >> 5;
+    if (((tid - kTmaThreads) & 31) != 0) return;
+    if (sw < kLoadWarps) {
       ring_copy_loop<real, D, F, kStages, kChunk, Rec>(stage_buf, full, empty,
                                                        static_cast<const real*>(p.payload) + base, N, T,
                                                        static_cast<unsigned>(nfb * sizeof(real)), sched_buf, sched,
-                                                       p.step_rows, (tid - kTmaThreads) >> 5, kCopyWarps);
+                                                       p.step_rows, sw, kLoadWarps);
+    } else if constexpr (BULK) {
+      // ---- store warp: one lane drains the output ring with bulk stores, a chunk per bulk group ----
+      const unsigned row_bytes = static_cast<unsigned>(nfb * sizeof(real));
+      real* trg = (p.traj != nullptr) ? static_cast<real*>(p.traj) + base : nullptr;
+      real* ldg = (p.logdet != nullptr) ? static_cast<real*>(p.logdet) + base : nullptr;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int os = chunk % kOutStages;
+        mbar_wait(&out_full[os], static_cast<unsigned>(chunk / kOutStages) & 1u);
+        const int k0 = chunk * kChunk;
+        const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+        const real* src = out_buf + os * out_stage_reals;
+        for (int c = 0; c < steps; ++c) {
+          const long long k = k0 + c;
+          for (int g = 0; g < out_nc; ++g)
+            bulk_s2g(trg + (k * out_nc + g) * N, src + (static_cast<size_t>(c) * out_rows + g) * kTmaThreads, row_bytes);
+          if (ldg != nullptr)
+            bulk_s2g(ldg + k * N, src + (static_cast<size_t>(c) * out_rows + out_nc) * kTmaThreads, row_bytes);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();  // the stores have READ the stage (not yet landed in HBM): the math warps may refill it
+        mbar_arrive(&out_empty[os]);
+      }
+      bulk_wait_all();  // the launch's outputs are complete when the kernel ends
+    }
     return;
   }
 
@@ -440,18 +510,22 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
     if (active && T > 0) flt.to_normalized(p.mc);
   }
 
-  real* tr_run = (FULL && p.traj != nullptr) ? static_cast<real*>(p.traj) + f : nullptr;
-  real* ld_run = (FULL && p.logdet != nullptr) ? static_cast<real*>(p.logdet) + f : nullptr;
-  unsigned char* used_run = (FULL && p.used != nullptr) ? p.used + f : nullptr;
-  const int out_nc = p.traj_ncomp;
+  real* tr_run = (FULL && !BULK && p.traj != nullptr) ? static_cast<real*>(p.traj) + f : nullptr;
+  real* ld_run = (FULL && !BULK && p.logdet != nullptr) ? static_cast<real*>(p.logdet) + f : nullptr;
+  unsigned char* used_run = (FULL && !BULK && p.used != nullptr) ? p.used + f : nullptr;
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int s = chunk % kStages;
     const unsigned use = static_cast<unsigned>(chunk / kStages);
     mbar_wait(&full[s], use & 1u);
     const int k0 = chunk * kChunk;
     const int steps = (T - k0) < kChunk ? (T - k0) : kChunk;
+    const int os = chunk % kOutStages;
+    if constexpr (BULK) {
+      if (chunk >= kOutStages) mbar_wait(&out_empty[os], static_cast<unsigned>(chunk / kOutStages - 1) & 1u);
+    }
     if (active) {
       const real* sb = stage_buf + s * kStageReals + tid;
+      real* ob = out_buf + os * out_stage_reals + tid;  // BULK: this thread's column of the output stage
       auto do_step = [&](int c) {
         const Rec& rec = sched_buf[s * kChunk + c];
         real u[D];
@@ -485,7 +559,14 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
           if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > gate);  // :1023-1025
         }
         const double det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
-        if constexpr (FULL) {
+        if constexpr (BULK) {
+          real* o = ob + static_cast<size_t>(c) * out_rows * kTmaThreads;
+          flt.for_each_state([&](auto G, real v) {
+            constexpr int g = G;
+            if (g < out_nc) o[g * kTmaThreads] = v;
+          });
+          if (out_rows > out_nc) o[out_nc * kTmaThreads] = static_cast<real>(log(det));
+        } else if constexpr (FULL) {
           // running output pointers: no reload of the launch parameters and no 64-bit multiply per step
           if (tr_run != nullptr) {
             flt.for_each_state([&](auto G, real v) {
@@ -517,8 +598,12 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
         for (int c = 0; c < steps; ++c) do_step(c);
       }
     }
+    if constexpr (BULK) fence_async_smem();  // this thread's staged outputs -> visible to the bulk-copy engine
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    if ((tid & 31) == 0) {
+      mbar_arrive(&empty[s]);
+      if constexpr (BULK) mbar_arrive(&out_full[os]);
+    }
   }
 
   if (!active) return;
@@ -1165,8 +1250,15 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
               }
               if (p.logdet != nullptr) {
                 double ld = 0.0;  // log det P = sum of the blocks' log-dets
+                if constexpr (EXT) {  // precomputed records carry determinants only (their producer takes no log)
+                  double dp = 1.0;
 #pragma unroll
-                for (int k2 = 0; k2 < NB; ++k2) ld += rec->ldet[k2];
+                  for (int k2 = 0; k2 < NB; ++k2) dp *= rec->det[k2];
+                  ld = log(dp);
+                } else {
+#pragma unroll
+                  for (int k2 = 0; k2 < NB; ++k2) ld += rec->ldet[k2];
+                }
                 __stcs(static_cast<real*>(p.logdet) + k * N + f, static_cast<real>(ld));
               }
               if (p.used != nullptr) p.used[k * N + f] = (ty != EV_PREDICT_ONLY) ? 1 : 0;
@@ -1242,7 +1334,15 @@ constexpr size_t tma_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
   constexpr int st = ring_stages<real, F>(), ch = ring_chunk<real, F>();
   return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
-         static_cast<size_t>(st) * ch * sizeof(LeanRecT<real>) + 2 * st * sizeof(unsigned long long);
+         static_cast<size_t>(st) * ch * sizeof(LeanRecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
+}
+template <int MODEL, typename real, int F>
+static size_t tma_bulk_smem_bytes(int out_rows) {
+  using MT = ModelTraits<MODEL, false, real>;
+  constexpr int st = kBulkInStages, ch = bulk_chunk<real, F>();
+  return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
+         static_cast<size_t>(kOutStages) * ch * out_rows * F * sizeof(real) +
+         static_cast<size_t>(st) * ch * sizeof(LeanRecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
 }
 
 // filters per CTA of the ring kernels: the largest of {896, 448, 224} that still gives every SM a CTA
@@ -1311,8 +1411,36 @@ static cudaError_t launch_tma_f(const RunParams& p, const LeanRecT<real>* sched,
   kf_run_tma_kernel<MODEL, real, SYM, FULL, F><<<blocks, F + 32 * kCopyWarps, smem, st>>>(p, sched);
   return cudaGetLastError();
 }
+template <int MODEL, typename real, bool SYM, int F>
+static cudaError_t launch_tma_bulk_f(const RunParams& p, const LeanRecT<real>* sched, int out_rows, cudaStream_t st) {
+  const size_t smem = tma_bulk_smem_bytes<MODEL, real, F>(out_rows);
+  const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
+  cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, true, F, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(tma_bulk_smem_bytes<MODEL, real, F>(kBulkMaxRows)));
+  if (err != cudaSuccess) return err;
+  kf_run_tma_kernel<MODEL, real, SYM, true, F, true><<<blocks, F + 32 * kCopyWarps, smem, st>>>(p, sched);
+  return cudaGetLastError();
+}
+// per-step outputs through the output ring: trajectory components and / or log det (at most kBulkMaxRows rows per
+// step), no `used` output (a byte per filter-step: per-thread stores)
+static bool bulk_out_ok(const b200kf_model* m, const RunParams& p, int* rows) {
+  const int nc = (p.traj != nullptr) ? p.traj_ncomp : 0;
+  *rows = nc + (p.logdet != nullptr ? 1 : 0);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p.traj) | reinterpret_cast<uintptr_t>(p.logdet)) & 15u) == 0;
+  return m->use_bulk_out != 0 && p.used == nullptr && *rows >= 1 && *rows <= kBulkMaxRows && aligned;
+}
 template <int MODEL, typename real, bool SYM, bool FULL>
-static cudaError_t launch_tma_one(const RunParams& p, const LeanRecT<real>* sched, int f, cudaStream_t st) {
+static cudaError_t launch_tma_one(const b200kf_model* m, const RunParams& p, const LeanRecT<real>* sched, int f,
+                                  cudaStream_t st) {
+  if constexpr (FULL) {
+    int rows = 0;
+    if (bulk_out_ok(m, p, &rows)) {
+      if (f == 896) return launch_tma_bulk_f<MODEL, real, SYM, 896>(p, sched, rows, st);
+      if (f == 448) return launch_tma_bulk_f<MODEL, real, SYM, 448>(p, sched, rows, st);
+      return launch_tma_bulk_f<MODEL, real, SYM, 224>(p, sched, rows, st);
+    }
+  }
   if (f == 896) return launch_tma_f<MODEL, real, SYM, FULL, 896>(p, sched, st);
   if (f == 448) return launch_tma_f<MODEL, real, SYM, FULL, 448>(p, sched, st);
   return launch_tma_f<MODEL, real, SYM, FULL, 224>(p, sched, st);
@@ -1341,15 +1469,15 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
     const int f = pick_ring_f(p.n_filters, m->sm_count, m->ring_f_cap);
     if constexpr (kFast2) {
       if (with_dec) {
-        err = full ? launch_tma_one<MODEL, real, false, true>(p, sched, f, st)
-                   : launch_tma_one<MODEL, real, false, false>(p, sched, f, st);
+        err = full ? launch_tma_one<MODEL, real, false, true>(m, p, sched, f, st)
+                   : launch_tma_one<MODEL, real, false, false>(m, p, sched, f, st);
         if (err != cudaSuccess) return err;
       }
     }
     if constexpr ((kFast2 && MTl::Sym2::eligible) || (!kFast2 && MTl::Sym3::eligible)) {
       if (with_sym) {
-        err = full ? launch_tma_one<MODEL, real, true, true>(p, sched, f, st)
-                   : launch_tma_one<MODEL, real, true, false>(p, sched, f, st);
+        err = full ? launch_tma_one<MODEL, real, true, true>(m, p, sched, f, st)
+                   : launch_tma_one<MODEL, real, true, false>(m, p, sched, f, st);
         if (err != cudaSuccess) return err;
       }
     }

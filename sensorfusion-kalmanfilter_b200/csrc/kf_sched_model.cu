@@ -503,13 +503,182 @@ __global__ void select_greedy_kernel(const SelectParams p) {
 #pragma unroll
         for (int q = 0; q < kMaxGainBlocks; ++q) {
           rec->det[q] = (q == 0) ? det : 1.0;
-          rec->ldet[q] = (q == 0) ? log(det) : 0.0;
+          rec->ldet[q] = 0.0;  // the consumer takes log(det) itself when a per-step log det is asked for
         }
       }
     }
     ns += 1;
     first_gps = first_imu = q_first = -1;
   }
+  p.n_sel[inst] = ns;
+  if (p.P_final != nullptr) {
+    double* Pg = p.P_final + static_cast<long long>(inst) * n * n;
+    if constexpr (!DENSE) {
+      for (int e = 0; e < n * n; ++e) Pg[e] = 0.0;
+    }
+    double xs[n];
+    flt.each([&](const auto& b) { b.store(xs, Pg, n); });
+  }
+}
+
+// Warp-per-instance form of the same walk (few instances: one per sampling rate in the scheduled sweep).  The
+// thread-per-instance loop above spends ~0.25 us per EVENT on a dependent global load of (time, type) -- 590 000
+// events of the 2 808 s stream = 150 ms for every rate, however few windows it has.  Here the warp loads 32 events
+// per iteration (coalesced, one batch ahead), finds the event that closes the window and the queue's first GPS /
+// IMU entries with ballots, and keeps the candidates' times in registers (no load on the decision path); all
+// lanes run the covariance recursion redundantly (warp-uniform, no divergence), lane 0 writes the outputs.
+// Same arithmetic, same order: selections and covariances are bit-identical to the thread-per-instance kernel.
+template <int MODEL, int VAR>
+__global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectParams p) {
+  using MT = VariantTraits<MODEL, VAR, double>;
+  constexpr bool DENSE = (VAR == VAR_DENSE);
+  constexpr int n = MT::n;
+  constexpr unsigned kAll = 0xffffffffu;
+  const int inst = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (inst >= p.n_inst) return;
+  typename MT::Filter flt;
+  flt.each([&](auto& b) { b.load_cov(p.P0 + static_cast<long long>(inst) * n * n, n); });
+  double ir_gps[kMaxN], ir_imu[kMaxN];
+  if constexpr (VAR == VAR_SYMMETRIC) {
+    int og = 0, oi = 0;
+    flt.each([&](const auto& b) {
+      using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+      BT::template inv_noise<true>(p.mc, ir_gps + og);
+      og += BT::template n_meas<true>();
+      if constexpr (!MT::imu_control) {
+        BT::template inv_noise<false>(p.mc, ir_imu + oi);
+        oi += BT::template n_meas<false>();
+      }
+    });
+  }
+  const double period = p.periods[inst];
+  double prev = p.t_prev[inst];
+  int* sel = p.sel + static_cast<long long>(inst) * p.max_sel;
+  const long long E = p.n_events;
+  long long ns = 0;
+  long long first_gps = -1, first_imu = -1, q_first = -1;  // queue summary
+  double t_gps = 0.0, t_imu = 0.0;                         // times of those candidates
+  int ty_imu = EV_IMU;                                     // type of the first non-GPS candidate
+  double t_nx = (lane < E) ? __ldg(p.times + lane) : 0.0;
+  int ty_nx = (lane < E) ? __ldg(p.types + lane) : -1;
+  for (long long e0 = 0; e0 < E; e0 += 32) {
+    const double t_l = t_nx;
+    const int ty_l = ty_nx;
+    if (e0 + 32 + lane < E) {  // next batch, off the serial chain
+      t_nx = __ldg(p.times + e0 + 32 + lane);
+      ty_nx = __ldg(p.types + e0 + 32 + lane);
+    }
+    const unsigned valid = __ballot_sync(kAll, e0 + lane < E);
+    const unsigned gps_m = __ballot_sync(kAll, ty_l == EV_GPS) & valid;
+    int pos = 0;  // first lane of the batch not yet consumed
+    while (true) {
+      const unsigned from = (pos >= 32) ? 0u : (kAll << pos);
+      const unsigned closes = __ballot_sync(kAll, !(t_l - prev < period)) & valid & from;  // :880-882
+      const int c = closes ? (__ffs(closes) - 1) : 32;
+      const unsigned range = valid & from & ((c >= 32) ? kAll : ((1u << c) - 1u));  // queued before the close
+      if (range) {
+        if (q_first < 0) q_first = e0 + __ffs(range) - 1;
+        const unsigned g = range & gps_m, im = range & ~gps_m;
+        if (first_gps < 0 && g) {
+          const int l = __ffs(g) - 1;
+          first_gps = e0 + l;
+          t_gps = __shfl_sync(kAll, t_l, l);
+        }
+        if (first_imu < 0 && im) {
+          const int l = __ffs(im) - 1;
+          first_imu = e0 + l;
+          t_imu = __shfl_sync(kAll, t_l, l);
+          ty_imu = __shfl_sync(kAll, ty_l, l);
+        }
+      }
+      if (c >= 32) break;  // batch exhausted, the queue carries over
+      if (q_first < 0) {   // empty queue: the triggering event is the only candidate (:884-886); else it is dropped
+        q_first = e0 + c;
+        const double tc = __shfl_sync(kAll, t_l, c);
+        const int tyc = __shfl_sync(kAll, ty_l, c);
+        if (tyc == EV_GPS) {
+          first_gps = q_first;
+          t_gps = tc;
+        } else {
+          first_imu = q_first;
+          t_imu = tc;
+          ty_imu = tyc;
+        }
+      }
+      // gains of the two sensor types for the current P (Scheduler.gain, :174-185)
+      double tr = 0.0, col2 = 0.0, p00 = 0.0;
+      flt.each([&](const auto& b) {
+        using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+        using TB = typename BT::Traits;
+        static_for<0, BT::n>([&](auto I) {
+          constexpr int i = I;
+          tr += static_cast<double>(BT::M) * b.P[BT::pidx(i, i)];
+          static_for<0, BT::n>([&](auto J) {
+            constexpr int j = J;
+            if constexpr (TB::gidx(j) == 0) {
+              col2 += b.P[BT::pidx(i, j)] * b.P[BT::pidx(i, j)];
+              if constexpr (i == j) p00 = b.P[BT::pidx(i, i)];
+            }
+          });
+        });
+      });
+      bool pick_gps;
+      if (first_gps < 0) pick_gps = false;
+      else if (first_imu < 0) pick_gps = true;
+      else {
+        const double gain_gps = tr - col2 / (p00 + p.mc.r_gps[0]);
+        const double gain_imu = tr - col2 / (p00 + p.mc.r_imu[0]);
+        // both present: the first entry attaining the max; on equal gains the earlier entry (strict '>' at :205)
+        const bool gps_first = first_gps < first_imu;
+        const double ga = gps_first ? gain_gps : gain_imu;
+        const double gb = gps_first ? gain_imu : gain_gps;
+        pick_gps = (gb > ga) ? !gps_first : gps_first;
+      }
+      const long long pick = pick_gps ? first_gps : first_imu;
+      const double ts = pick_gps ? t_gps : t_imu;
+      const int tys = pick_gps ? static_cast<int>(EV_GPS) : ty_imu;
+      const double dt = ts - prev;  // :914
+      filter_predict<false>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
+      filter_update<false, true>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
+      prev = ts;
+      if (lane == 0 && ns < p.max_sel) sel[ns] = static_cast<int>(pick);
+      if constexpr (VAR == VAR_SYMMETRIC) {
+        if (p.gain_recs != nullptr && ns < p.max_sel) {
+          using Rec = GainRecG<GainSlots<typename MT::Filter>::value>;
+          Rec* rec = static_cast<Rec*>(p.gain_recs) + static_cast<long long>(inst) * p.max_sel + ns;
+          bool okd = true;
+          const double det = filter_det(flt, okd);
+          if (lane == 0) {
+            int o = 0, oc = 0;
+            flt.each([&](const auto& b) {
+              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+              if (tys == EV_GPS) {
+                b.template extract_gain<true>(ir_gps + oc, rec->g + o);
+                oc += BT::template n_meas<true>();
+              } else if (tys == EV_IMU) {
+                if constexpr (!MT::imu_control) b.template extract_gain<false>(ir_imu + oc, rec->g + o);
+                oc += BT::template n_meas<false>();
+              }
+              o += BT::kslots;
+            });
+            rec->dt = dt;
+            rec->type = tys;
+            rec->pad = 0;
+#pragma unroll
+            for (int q = 0; q < kMaxGainBlocks; ++q) {
+              rec->det[q] = (q == 0) ? det : 1.0;
+              rec->ldet[q] = 0.0;  // the consumer takes log(det) itself when a per-step log det is asked for
+            }
+          }
+        }
+      }
+      ns += 1;
+      first_gps = first_imu = q_first = -1;
+      pos = c + 1;
+    }
+  }
+  if (lane != 0) return;
   p.n_sel[inst] = ns;
   if (p.P_final != nullptr) {
     double* Pg = p.P_final + static_cast<long long>(inst) * n * n;
@@ -535,6 +704,17 @@ int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams
   const bool sym_ok = (flags & B200KF_RUN_FORCE_SYMMETRIC) && m->use_sym && SymF::constants_equal(m->mc);
   if (p.gain_recs != nullptr && !sym_ok)
     return set_error(B200KF_ERR_UNSUPPORTED, "gain records need B200KF_RUN_FORCE_SYMMETRIC (an axis-symmetric P0 and equal rates)");
+  if (p.lane_stride == 32 && m->use_select_warp) {  // few instances: a warp each, events loaded 32 at a time
+    const unsigned wb = static_cast<unsigned>(p.n_inst);
+    if (sym_ok)
+      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<wb, 32, 0, st>>>(p);
+    else if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC))
+      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_DECOUPLED><<<wb, 32, 0, st>>>(p);
+    else
+      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_DENSE><<<wb, 32, 0, st>>>(p);
+    B200KF_CUDA_TRY(cudaGetLastError());
+    return B200KF_OK;
+  }
   if (sym_ok)
     select_greedy_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<blocks, tpb, 0, st>>>(p);
   else if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC))

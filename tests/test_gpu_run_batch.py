@@ -489,3 +489,35 @@ def test_step_rows_reads_a_selection_in_place(name, N, monkeypatch):
             np.testing.assert_array_equal(c[k].cpu().numpy(), d[k].cpu().numpy())
     ref = ko.run_batch(m, types, dts, payload[rows], x0, P0, want_traj=False)
     assert rel(b["x"].cpu().numpy(), ref["x"]) < RTOL64
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("N", [600, 33150, 70002, 140000])
+def test_output_ring_bulk_stores_match_per_thread_stores_and_oracle(precision, N, monkeypatch):
+    """Trajectory mode of the ring kernels: per-step outputs staged in a shared-memory output ring and
+    written with cp.async.bulk.global.shared (default) against the per-thread-store form of the same kernel
+    (B200KF_BULK_OUT=0) -- bit-identical -- and against the oracle, at every CTA size (224 / 448 / 896 filters,
+    ragged last CTA), odd step counts (partial last chunk) and every combination of outputs."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    T = 53
+    tol = RTOL64 if precision == "f64" else RTOL32
+    for name in ("CV6", "BIAS9"):
+        m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=61)
+        pick = np.unique(np.concatenate([np.arange(0, N, max(1, N // 37)), [N - 1]]))
+        ref = ko.run_batch(m, types, dts, payload[:, :, pick], x0[pick], P0[pick])
+        for ncomp, want_ld in ((6, True), (3, False), (0, True), (m.n if m.n <= 7 else 7, True)):
+            outs = {}
+            for bulk in ("1", "0"):
+                monkeypatch.setenv("B200KF_BULK_OUT", bulk)
+                outs[bulk] = Engine(name, precision=precision).run_batch(types, dts, payload, x0, P0, traj_ncomp=ncomp,
+                                                                         want_logdet=want_ld, mode="symmetric")
+            a, b = outs["1"], outs["0"]
+            assert int(a["status"].sum()) == 0
+            for k in ("x", "P", "agg") + (("traj",) if ncomp else ()) + (("logdet",) if want_ld else ()):
+                assert bool((a[k] == b[k]).all()), (name, ncomp, want_ld, k)
+            assert rel(a["x"].cpu().numpy()[pick], ref["x"]) < tol
+            if ncomp:
+                assert rel(a["traj"].cpu().numpy()[:, :, pick], ref["traj"][:, :ncomp]) < tol
+            if want_ld:
+                ld = a["logdet"].cpu().numpy()[:, pick]
+                assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < tol

@@ -234,3 +234,41 @@ def test_config4_full_size_properties(monkeypatch):
     hi_thr, _ = tree.score_schedules(types, times, t_prev, t_end, P0, threshold=thr + 0.5)
     assert lo_thr["n_feasible"] <= bt["n_feasible"] <= hi_thr["n_feasible"]
     assert lo_thr["argmin_sum_index"] == bt["argmin_sum_index"]  # the threshold does not enter the argmin
+
+
+@pytest.mark.parametrize("name", ["CA15", "CA8"])
+def test_warp_cooperative_selection_is_bit_identical_to_the_thread_walk(name, monkeypatch):
+    """b200kf_select_greedy with few instances runs one WARP per instance (events loaded 32 at a time, window
+    closing found with ballots); B200KF_SELECT_WARP=0 keeps the thread-per-instance walk.  Same selections,
+    covariances and gain records bit for bit, over a stream with batch-straddling queues, empty queues
+    (period shorter than the event spacing) and long queues (period of several batches)."""
+    from sensorfusion_kalmanfilter_b200 import streams, synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    ev = synth.make_indexed_sensor_data(5003, seed=8)[3:]
+    ps = streams.PackedStream.from_events(ev)
+    types, times = ps.types[1:], ps.times[1:]
+    periods = [1.0 / f for f in (3.0, 10.0, 55.0, 120.0, 180.0, 1000.0)]
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B200KF_SELECT_WARP", flag)
+        eng = Engine(name)
+        P0 = np.repeat(eng.spec.default_P0()[None], len(periods), axis=0)
+        for mode in ("symmetric", "decoupled", "dense"):
+            want_gains = mode == "symmetric"
+            got = eng.select_greedy(types, times, periods, [float(ps.times[0])] * len(periods), P0, mode=mode,
+                                    want_gains=want_gains)
+            outs[(flag, mode)] = got
+    for mode in ("symmetric", "decoupled", "dense"):
+        a, b = outs[("1", mode)], outs[("0", mode)]
+        for sa, sb in zip(a[0], b[0]):
+            np.testing.assert_array_equal(sa, sb)
+        assert bool((a[1] == b[1]).all())
+        if mode == "symmetric":
+            ra, rb = a[2].cpu().numpy(), b[2].cpu().numpy()
+            for i, sa in enumerate(a[0]):
+                np.testing.assert_array_equal(ra[i, :len(sa)], rb[i, :len(sa)])
+    # and the selections are the oracle's (greedy_schedule over the window queues, kf_workers.py:877-910)
+    if name == "CA15":
+        st, _, _ = ko.run_scheduled(ko.get_model(name), ev, 55.0, 0, len(ev))
+        sel_ref = np.searchsorted(ps.times, np.array([s[0] for s in st[1:]])) - 1
+        np.testing.assert_array_equal(outs[("1", "symmetric")][0][2], sel_ref)

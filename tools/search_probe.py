@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import search_window  # noqa: E402
+from bench import search_window, warm_cov  # noqa: E402
 from sensorfusion_kalmanfilter_b200.engine import Engine  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -23,7 +23,7 @@ ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 eng = Engine("CA15")
 st, tm = search_window(a.L)
-P0 = eng.spec.default_P0() * 1e-3
+P0 = warm_cov(eng)
 _, per = eng.score_schedules(st, tm, 999.995, float(tm[-1]), P0, first=1, count=(1 << 16) - 1, want_per_schedule=True)
 thr = float(per[:, 0].median().item())
 best, _ = eng.score_schedules(st, tm, 999.995, float(tm[-1]), P0, threshold=thr)
