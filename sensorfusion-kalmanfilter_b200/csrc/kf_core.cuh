@@ -1364,6 +1364,8 @@ constexpr bool same_pv2_shape() {
 
 template <typename real, class... Bs>
 struct Dec2Filter {
+  static constexpr bool rec_api = false;  // predict(dt, mc) / update(dt, mc, ...) interface
+  using LeanRec = LeanRecT<real>;  // only (dt, type) are read
   static constexpr bool lean_ok = false;
   FilterT<real, false, Bs...> f;
   double rprod;
@@ -1390,6 +1392,7 @@ struct Dec2Filter {
 
 template <typename real, class B0, class... Bs>
 struct Sym2Filter {
+  static constexpr bool rec_api = false;  // predict(dt, mc) / update(dt, mc, ...) interface
   static constexpr int M = 1 + sizeof...(Bs);
   using Lead = B0;
   static constexpr bool eligible = (same_pv2_shape<B0, Bs>() && ... && is_pv2<B0>());
@@ -1620,6 +1623,7 @@ constexpr bool is_vrb3() {  // [value, rate, bias]: value += dt rate - c2 dt^2 b
 
 template <typename real, class B0, class... Bs>
 struct Sym3CtrlFilter {
+  static constexpr bool rec_api = false;  // predict(dt, mc) / update(dt, mc, ...) interface
   static constexpr int M = 1 + sizeof...(Bs);
   static constexpr bool eligible = (is_vrb3<B0>() && ... && is_vrb3<Bs>());
   static constexpr bool lean_ok = eligible;
@@ -1763,6 +1767,321 @@ struct Sym3CtrlFilter {
 };
 
 // --------------------------------------------------------------------------------------
+// SymCAFilter: the lean form of the reference's OWN models (kf_workers.py:493-614 CA15, hw5_2.py:219-304 CA8):
+// ML identical (position, velocity, acceleration) chains + MA identical (angle, rate) chains, every state
+// measured by the IMU event (pseudo-measurement [X, V, a] on the linear chains, direct on the angular ones,
+// kf_workers.py:698-706), position measured by the GPS event.  One 3 x 3 and one 2 x 2 covariance per filter
+// (axis-symmetric P, checked per launch), the axis states in registers.
+//
+// The covariances are carried in R-NORMALISED coordinates P~ = D^-1 P D^-1, D = diag(sqrt r_imu): the H = I
+// update is then P~+ = P~ (P~ + I)^-1, written through the cofactors of S~ = P~ + I --
+//   diagonal      P~+_ii = (sum_k P~_ik C_ki) / det S~        off-diagonal  P~+_ij = -C_ij / det S~
+// -- one reciprocal, no multiplication by r and no cancelling subtraction; det P~+ = det P~ / det S~.  The state
+// stays in physical units: K = D P~+ D^-1, i.e. K_ii = P~+_ii and the off-diagonals scale by sqrt(r_i / r_j)
+// (launch constants).  Everything that depends only on (dt, q, r) arrives with the step record (CARecT).
+// One IMU step: 15 + 37 + 10 (3 x 3 covariance: predict, update, determinant) + 5 + 14 (2 x 2) + 8 (gain
+// scaling) + 16 per linear axis + 7 per angular axis FP64 instructions.
+// --------------------------------------------------------------------------------------
+template <class... Cs>
+struct ChainList {
+  static constexpr int size = sizeof...(Cs);
+};
+
+template <typename real>
+struct CARecT;
+template <>
+struct alignas(16) CARecT<double> {  // 112 bytes
+  double dt, e;           // dt, c2 dt^2
+  double k01, k02, k12;   // normalised F of the linear chain: dt sqrt(r1/r0), e sqrt(r2/r0), dt sqrt(r2/r1)
+  double f0, f1, f2;      // q_i dt / r_i
+  double ka, fa0, fa1;    // angular chain: dt sqrt(rb1/rb0), qb_i dt / rb_i
+  double gam;             // r_gps / r0
+  int type;
+  int pad[3];
+};
+template <>
+struct alignas(16) CARecT<float> {  // 64 bytes, same fields
+  float dt, e, k01, k02, k12, f0, f1, f2, ka, fa0, fa1, gam;
+  int type;
+  int pad[3];
+};
+
+template <class B>
+constexpr bool is_pva3() {  // [p, v, a]: p += dt v + c2 dt^2 a, v += dt a; IMU measures [X, V, a], GPS measures p
+  if (is_group_tag<B>::value) return false;
+  if (B::n != 3) return false;
+  return B::l1(0) == 1 && B::l2(0) == 2 && B::s1(0) == 1 && B::s2(0) == 1 && B::l1(1) == 2 && B::l2(1) < 0 &&
+         B::s1(1) == 1 && B::l1(2) < 0 && B::l2(2) < 0 && B::zk(0) == ZK_POS && B::zk(1) == ZK_VEL &&
+         B::zk(2) == ZK_DIRECT && B::pz(0) == B::pz(1) && B::pz(1) == B::pz(2) && B::gps(0) >= 0 && B::gps(1) < 0 &&
+         B::gps(2) < 0 && B::cu(0) == 0 && B::cu(1) == 0 && B::cu(2) == 0;
+}
+template <class B>
+constexpr bool is_ar2() {  // [angle, rate]: angle += dt rate; both measured directly by the IMU event, no GPS
+  if (is_group_tag<B>::value) return false;
+  if (B::n != 2) return false;
+  return B::l1(0) == 1 && B::l2(0) < 0 && B::s1(0) == 1 && B::l1(1) < 0 && B::l2(1) < 0 && B::zk(0) == ZK_DIRECT &&
+         B::zk(1) == ZK_DIRECT && B::gps(0) < 0 && B::gps(1) < 0 && B::cu(0) == 0 && B::cu(1) == 0;
+}
+
+template <typename real, class LinList, class AngList>
+struct SymCAFilter {  // models without the (linear chains, angular chains) shape
+  static constexpr bool eligible = false;
+  static constexpr bool lean_ok = false;
+  static constexpr bool rec_api = false;
+  static constexpr int M = 1;
+  using LeanRec = LeanRecT<real>;
+};
+
+template <typename real, class L0, class... Ls, class A0, class... As>
+struct SymCAFilter<real, ChainList<L0, Ls...>, ChainList<A0, As...>> {
+  static constexpr int ML = 1 + sizeof...(Ls), MA = 1 + sizeof...(As);
+  static constexpr bool eligible = (is_pva3<L0>() && ... && is_pva3<Ls>()) && (is_ar2<A0>() && ... && is_ar2<As>());
+  static constexpr bool lean_ok = eligible;
+  static constexpr bool rec_api = true;  // predict(rec) / update(rec, ...) take the step record, not (dt, mc)
+  static constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
+  static constexpr int M = gcd_(ML, MA);          // multiplicity restored on the lean aggregate (kf_run_tma_kernel)
+  static constexpr int EL = ML / M, EA = MA / M;  // v = (det lin)^EL (det ang)^EA per step
+  using Lead = L0;
+  using LeanRec = CARecT<real>;
+  real l00, l01, l02, l11, l12, l22;  // linear-chain covariance (R-normalised between to_/from_normalized)
+  real c00, c01, c11;                 // angular-chain covariance
+  real xp[ML], xv[ML], xa[ML];
+  real th[MA], om[MA];
+  real s01, s02, s12, s10, s20, s21;  // sqrt(r_i / r_j) of the linear chain's IMU variances
+  real t01, t10;                      // the same for the angular chain
+  real r0r1;                          // (r0 r1 r2)^EL (rb0 rb1)^EA: constant factor of the lean aggregate's v
+
+  template <class F>
+  __device__ __forceinline__ static void lin_members(F&& fn) {
+    int m = 0;
+    fn(L0{}, m++);
+    (fn(Ls{}, m++), ...);
+  }
+  template <class F>
+  __device__ __forceinline__ static void ang_members(F&& fn) {
+    int m = 0;
+    fn(A0{}, m++);
+    (fn(As{}, m++), ...);
+  }
+  __device__ __forceinline__ static real ipow(real v, int e) {
+    real r = v;
+    for (int i = 1; i < e; ++i) r *= v;
+    return r;
+  }
+
+  __device__ __forceinline__ void load(const real* xg, const real* Pg, int n, const ModelConst& mc) {
+    auto sl = [&](int i, int j) { return real(0.5) * (Pg[L0::gidx(i) * n + L0::gidx(j)] + Pg[L0::gidx(j) * n + L0::gidx(i)]); };
+    auto sa = [&](int i, int j) { return real(0.5) * (Pg[A0::gidx(i) * n + A0::gidx(j)] + Pg[A0::gidx(j) * n + A0::gidx(i)]); };
+    l00 = sl(0, 0), l01 = sl(0, 1), l02 = sl(0, 2), l11 = sl(1, 1), l12 = sl(1, 2), l22 = sl(2, 2);
+    c00 = sa(0, 0), c01 = sa(0, 1), c11 = sa(1, 1);
+    lin_members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      xp[m] = xg[BM::gidx(0)];
+      xv[m] = xg[BM::gidx(1)];
+      xa[m] = xg[BM::gidx(2)];
+    });
+    ang_members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      th[m] = xg[BM::gidx(0)];
+      om[m] = xg[BM::gidx(1)];
+    });
+    const double r0 = mc.r_imu[L0::gidx(0)], r1 = mc.r_imu[L0::gidx(1)], r2 = mc.r_imu[L0::gidx(2)];
+    const double b0 = mc.r_imu[A0::gidx(0)], b1 = mc.r_imu[A0::gidx(1)];
+    s01 = real(sqrt(r0 / r1)), s02 = real(sqrt(r0 / r2)), s12 = real(sqrt(r1 / r2));
+    s10 = real(sqrt(r1 / r0)), s20 = real(sqrt(r2 / r0)), s21 = real(sqrt(r2 / r1));
+    t01 = real(sqrt(b0 / b1)), t10 = real(sqrt(b1 / b0));
+    double rr = 1.0;
+    for (int i = 0; i < EL; ++i) rr *= r0 * r1 * r2;
+    for (int i = 0; i < EA; ++i) rr *= b0 * b1;
+    r0r1 = real(rr);
+  }
+  __device__ __forceinline__ void store(real* xg, real* Pg, int n) const {
+    const real L[3][3] = {{l00, l01, l02}, {l01, l11, l12}, {l02, l12, l22}};
+    const real A[2][2] = {{c00, c01}, {c01, c11}};
+    lin_members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      xg[BM::gidx(0)] = xp[m];
+      xg[BM::gidx(1)] = xv[m];
+      xg[BM::gidx(2)] = xa[m];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Pg[BM::gidx(i) * n + BM::gidx(j)] = L[i][j];
+    });
+    ang_members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      xg[BM::gidx(0)] = th[m];
+      xg[BM::gidx(1)] = om[m];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) Pg[BM::gidx(i) * n + BM::gidx(j)] = A[i][j];
+    });
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_state(F&& fn) const {
+    lin_members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      fn(std::integral_constant<int, BM::gidx(0)>{}, xp[m]);
+      fn(std::integral_constant<int, BM::gidx(1)>{}, xv[m]);
+      fn(std::integral_constant<int, BM::gidx(2)>{}, xa[m]);
+    });
+    ang_members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      fn(std::integral_constant<int, BM::gidx(0)>{}, th[m]);
+      fn(std::integral_constant<int, BM::gidx(1)>{}, om[m]);
+    });
+  }
+  // P <-> P~ = D^-1 P D^-1 (exact scalings by launch constants, once per launch each way)
+  __device__ __forceinline__ void to_normalized(const ModelConst& mc) {
+    const double r0 = mc.r_imu[L0::gidx(0)], r1 = mc.r_imu[L0::gidx(1)], r2 = mc.r_imu[L0::gidx(2)];
+    const double b0 = mc.r_imu[A0::gidx(0)], b1 = mc.r_imu[A0::gidx(1)];
+    l00 = real(double(l00) / r0), l11 = real(double(l11) / r1), l22 = real(double(l22) / r2);
+    l01 = real(double(l01) / sqrt(r0 * r1)), l02 = real(double(l02) / sqrt(r0 * r2)), l12 = real(double(l12) / sqrt(r1 * r2));
+    c00 = real(double(c00) / b0), c11 = real(double(c11) / b1), c01 = real(double(c01) / sqrt(b0 * b1));
+  }
+  __device__ __forceinline__ void from_normalized(const ModelConst& mc) {
+    const double r0 = mc.r_imu[L0::gidx(0)], r1 = mc.r_imu[L0::gidx(1)], r2 = mc.r_imu[L0::gidx(2)];
+    const double b0 = mc.r_imu[A0::gidx(0)], b1 = mc.r_imu[A0::gidx(1)];
+    l00 = real(double(l00) * r0), l11 = real(double(l11) * r1), l22 = real(double(l22) * r2);
+    l01 = real(double(l01) * sqrt(r0 * r1)), l02 = real(double(l02) * sqrt(r0 * r2)), l12 = real(double(l12) * sqrt(r1 * r2));
+    c00 = real(double(c00) * b0), c11 = real(double(c11) * b1), c01 = real(double(c01) * sqrt(b0 * b1));
+  }
+  // normalised determinants of the two covariances
+  __device__ __forceinline__ real lin_det() const {
+    return l00 * fma(l11, l22, -(l12 * l12)) - l01 * fma(l01, l22, -(l02 * l12)) + l02 * fma(l01, l12, -(l02 * l11));
+  }
+  __device__ __forceinline__ real ang_det() const { return fma(c00, c11, -(c01 * c01)); }
+  __device__ __forceinline__ real vnorm() const { return ipow(lin_det(), EL) * ipow(ang_det(), EA); }
+  // det P of the whole filter in physical units (normalised state assumed)
+  __device__ __forceinline__ double det(bool& ok) const {
+    const real dl = lin_det(), da = ang_det();
+    ok = ok && (dl > real(0)) && (da > real(0));
+    double r = 1.0;
+    const double d = double(ipow(dl, EL)) * double(ipow(da, EA)) * double(r0r1);
+#pragma unroll
+    for (int i = 0; i < M; ++i) r *= d;
+    return r;
+  }
+  // x = F x, P~ = F~ P~ F~^T + Q~ (entry by entry)
+  __device__ __forceinline__ void predict(const LeanRec& r) {
+    const real dt = r.dt, e = r.e;
+#pragma unroll
+    for (int m = 0; m < ML; ++m) {
+      xp[m] = fma(e, xa[m], fma(dt, xv[m], xp[m]));
+      xv[m] = fma(dt, xa[m], xv[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < MA; ++m) th[m] = fma(dt, om[m], th[m]);
+    const real k01 = r.k01, k02 = r.k02, k12 = r.k12;
+    const real a00 = fma(k02, l02, fma(k01, l01, l00));
+    const real a01 = fma(k02, l12, fma(k01, l11, l01));
+    const real a02 = fma(k02, l22, fma(k01, l12, l02));
+    const real a11 = fma(k12, l12, l11);
+    const real a12 = fma(k12, l22, l12);
+    l00 = fma(k02, a02, fma(k01, a01, a00)) + real(r.f0);
+    l01 = fma(k12, a02, a01);
+    l02 = a02;
+    l11 = fma(k12, a12, a11) + real(r.f1);
+    l12 = a12;
+    l22 = l22 + real(r.f2);
+    const real ka = r.ka;
+    const real bn = fma(ka, c11, c01);
+    c00 = fma(ka, c01 + bn, c00 + real(r.fa0));
+    c01 = bn;
+    c11 = c11 + real(r.fa1);
+  }
+  // IMU event on the predicted filter: joint H = I update of both covariances and of every axis state
+  __device__ __forceinline__ void imu_update(const LeanRec& r, const real* u) {
+    const real dt = r.dt;
+    {  // 3 x 3: P~+ = P~ (P~ + I)^-1 through the cofactors of S~
+      const real q00 = l00 + real(1), q11 = l11 + real(1), q22 = l22 + real(1);
+      const real C00 = fma(q11, q22, -(l12 * l12));
+      const real C01 = fma(l02, l12, -(l01 * q22));
+      const real C02 = fma(l01, l12, -(l02 * q11));
+      const real C11 = fma(q00, q22, -(l02 * l02));
+      const real C12 = fma(l01, l02, -(q00 * l12));
+      const real C22 = fma(q00, q11, -(l01 * l01));
+      const real dS = fma(q00, C00, fma(l01, C01, l02 * C02));
+      const real n0 = fma(l00, C00, fma(l01, C01, l02 * C02));
+      const real n1 = fma(l01, C01, fma(l11, C11, l12 * C12));
+      const real n2 = fma(l02, C02, fma(l12, C12, l22 * C22));
+      const real inv = fast_rcp3(dS);
+      const real ninv = -inv;
+      l00 = n0 * inv, l11 = n1 * inv, l22 = n2 * inv;
+      l01 = C01 * ninv, l02 = C02 * ninv, l12 = C12 * ninv;
+    }
+    {  // state: K = D P~+ D^-1; y = [(v- + u dt) dt, u dt, u - a] (kf_workers.py:698-709)
+      const real g01 = l01 * s01, g02 = l02 * s02, g12 = l12 * s12;
+      const real g10 = l01 * s10, g20 = l02 * s20, g21 = l12 * s21;
+      lin_members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        const real acc = u[BM::pz(0)];
+        const real w = acc * dt;
+        const real y0 = (xv[m] + w) * dt, y2 = acc - xa[m];
+        xp[m] = fma(l00, y0, fma(g01, w, fma(g02, y2, xp[m])));
+        xv[m] = fma(g10, y0, fma(l11, w, fma(g12, y2, xv[m])));
+        xa[m] = fma(g20, y0, fma(g21, w, fma(l22, y2, xa[m])));
+      });
+    }
+    {  // 2 x 2 (as Sym2Filter::step_lean)
+      const real detp = fma(c00, c11, -(c01 * c01));
+      const real u0 = detp + c00, u1 = detp + c11;
+      const real inv = fast_rcp3((u0 + real(1)) + c11);
+      c00 = u0 * inv;
+      c11 = u1 * inv;
+      c01 = c01 * inv;
+      const real h01 = c01 * t01, h10 = c01 * t10;
+      ang_members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        const real y0 = u[BM::pz(0)] - th[m], y1 = u[BM::pz(1)] - om[m];
+        th[m] = fma(c00, y0, fma(h01, y1, th[m]));
+        om[m] = fma(h10, y0, fma(c11, y1, om[m]));
+      });
+    }
+  }
+  // GPS event: scalar update of the position on the linear chains (gam = r_gps / r0); the angular chains only predict
+  __device__ __forceinline__ void gps_update(const LeanRec& r, const real* u) {
+    const real inv = fast_rcp3(l00 + real(r.gam));
+    const real k0 = l00 * inv, k1 = l01 * inv, k2 = l02 * inv, g = real(r.gam) * inv;
+    const real K1 = k1 * s10, K2 = k2 * s20;
+    lin_members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      const real y = u[BM::gps(0)] - xp[m];
+      xp[m] = fma(k0, y, xp[m]);
+      xv[m] = fma(K1, y, xv[m]);
+      xa[m] = fma(K2, y, xa[m]);
+    });
+    l11 = fma(-k1, l01, l11);
+    l12 = fma(-k1, l02, l12);
+    l22 = fma(-k2, l02, l22);
+    l00 *= g;
+    l01 *= g;
+    l02 *= g;
+  }
+  // record-driven interface of the ring kernel (rec_api)
+  __device__ __forceinline__ double update(const LeanRec& r, int ty, const real* u, bool& ok) {
+    if (ty == EV_IMU) imu_update(r, u);
+    else if (ty == EV_GPS) gps_update(r, u);
+    return det(ok);
+  }
+  // fused step of the aggregate-only loop; v = (det lin~)^EL (det ang~)^EA after the step
+  __device__ __forceinline__ void step_lean(const LeanRec& r, const ModelConst&, const real* u, real& v) {
+    predict(r);
+    if (r.type == EV_IMU) imu_update(r, u);
+    else if (r.type == EV_GPS) gps_update(r, u);
+    v = vnorm();
+  }
+};
+
+// linear / angular chain lists of the models that have the SymCAFilter shape
+template <int MODEL_ID>
+struct CALists {
+  using Lin = void;
+  using Ang = void;
+};
+
+// --------------------------------------------------------------------------------------
 // Model registry: decoupled chain list and dense union per model id
 // --------------------------------------------------------------------------------------
 template <int MODEL_ID, bool DENSE, typename real>
@@ -1787,6 +2106,7 @@ struct ChainIndex {
     using Dec2 = Dec2Filter<real, __VA_ARGS__>;                                \
     using Sym2 = Sym2Filter<real, __VA_ARGS__>;                                \
     using Sym3 = Sym3CtrlFilter<real, __VA_ARGS__>;                            \
+    using SymCA = SymCAFilter<real, typename CALists<ID>::Lin, typename CALists<ID>::Ang>; \
     static constexpr int chain_of(int g) { return ChainIndex<__VA_ARGS__>::of(g); } \
   };                                                                           \
   template <typename real>                                                     \
@@ -1797,6 +2117,17 @@ struct ChainIndex {
   };
 
 enum : int { MODEL_CV6 = 0, MODEL_CA8 = 1, MODEL_BIAS9 = 2, MODEL_CA15 = 3, MODEL_COUNT = 4 };
+
+template <>
+struct CALists<MODEL_CA8> {
+  using Lin = ChainList<CA8LinChain<0>, CA8LinChain<1>>;
+  using Ang = ChainList<CA8YawChain>;
+};
+template <>
+struct CALists<MODEL_CA15> {
+  using Lin = ChainList<CA15LinChain<0>, CA15LinChain<1>, CA15LinChain<2>>;
+  using Ang = ChainList<CA15AngChain<0>, CA15AngChain<1>, CA15AngChain<2>>;
+};
 
 B200KF_DEFINE_MODEL(MODEL_CV6, 6, 3, 3, false, CV6Chain<0>, CV6Chain<1>, CV6Chain<2>)
 B200KF_DEFINE_MODEL(MODEL_CA8, 8, 4, 2, false, CA8LinChain<0>, CA8LinChain<1>, CA8YawChain)

@@ -38,6 +38,7 @@ struct b200kf_model {
   int ring_f_cap;  // largest filters-per-CTA the ring kernels may pick: 896 / 448 / 224 (env B200KF_RING_F)
   int use_tree;  // 1: prefix-sharing schedule-search kernel for aligned blocks (env B200KF_TREE=0 disables)
   int use_select_warp;  // 1: warp-per-instance greedy selection for few instances (env B200KF_SELECT_WARP=0: thread per instance)
+  int use_ca_ring;  // 1: per-filter ring kernel for the constant-acceleration models CA15 / CA8 (env B200KF_CA_RING=0: LDG kernels)
   int use_bulk_out;  // 1: per-step outputs of the ring kernels leave through the shared-memory output ring + bulk stores (env B200KF_BULK_OUT=0: per-thread stores)
   int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };

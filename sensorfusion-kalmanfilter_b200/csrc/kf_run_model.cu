@@ -221,18 +221,20 @@ constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 
 #ifndef B200KF_MAX_CHUNK
 #define B200KF_MAX_CHUNK 8
 #endif
-template <typename real, int F>
+// (D = payload columns per step: 3 for the lean CV6 / BIAS9 rings the constants were tuned on; the constant-
+// acceleration models carry 4 / 9 columns and get the same bytes: fewer steps, at least kCopyWarps stages)
+template <typename real, int F, int D = 3>
 constexpr int ring_steps() {
-  return kStages * kChunk * (896 / F) * (sizeof(real) == 4 ? 2 : 1);
+  return kStages * kChunk * (896 / F) * (sizeof(real) == 4 ? 2 : 1) * 3 / D;
 }
-template <typename real, int F>
+template <typename real, int F, int D = 3>
 constexpr int ring_chunk() {
-  constexpr int want = ring_steps<real, F>() / kStages;
-  return want < B200KF_MAX_CHUNK ? want : B200KF_MAX_CHUNK;
+  constexpr int want = ring_steps<real, F, D>() / kStages;
+  return want < 1 ? 1 : (want < B200KF_MAX_CHUNK ? want : B200KF_MAX_CHUNK);
 }
-template <typename real, int F>
+template <typename real, int F, int D = 3>
 constexpr int ring_stages() {
-  return ring_steps<real, F>() / ring_chunk<real, F>();
+  return ring_steps<real, F, D>() / ring_chunk<real, F, D>();
 }
 
 // step record of the ring: LeanRecT<real> (64 bytes in float64, 32 in float32; only (dt, type) are read
@@ -293,9 +295,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 constexpr int kBulkInStages = 4;
 constexpr int kOutStages = 2;
 constexpr int kBulkMaxRows = 8;
-template <typename real, int F>
+template <typename real, int F, int D = 3>
 constexpr int bulk_chunk() {
-  return (896 / F) * (sizeof(real) == 4 ? 2 : 1);
+  constexpr int c = (896 / F) * (sizeof(real) == 4 ? 2 : 1) * 3 / D;
+  return c < 1 ? 1 : c;
 }
 
 // Per-step records of the launch: (dt, type) plus the warp-uniform constants of the lean symmetric
@@ -330,9 +333,38 @@ static __global__ void pack_schedule_kernel(const uint8_t* __restrict__ types, c
 template <int MODEL, typename real, bool SYM>
 struct TmaFlt {
   using MT = ModelTraits<MODEL, false, real>;
-  using type = std::conditional_t<!SYM, typename MT::Dec2,
-                                  std::conditional_t<MT::Filter::fast2, typename MT::Sym2, typename MT::Sym3>>;
+  using type = std::conditional_t<
+      !SYM, typename MT::Dec2,
+      std::conditional_t<MT::Filter::fast2, typename MT::Sym2,
+                         std::conditional_t<MT::Sym3::eligible, typename MT::Sym3, typename MT::SymCA>>>;
 };
+
+// step records of the constant-acceleration ring filter (SymCAFilter): everything that depends on (dt, q, r) only
+struct CAConst {
+  double r0, r1, r2, q0, q1, q2, b0, b1, qa0, qa1, rg, c2;
+};
+template <typename real>
+static __global__ void pack_ca_schedule_kernel(const uint8_t* __restrict__ types, const double* __restrict__ dts, int T,
+                                               CAConst c, CARecT<real>* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= T) return;
+  const double dt = dts[k], e = c.c2 * dt * dt;
+  CARecT<real> r{};
+  r.dt = real(dt);
+  r.e = real(e);
+  r.k01 = real(dt * sqrt(c.r1 / c.r0));
+  r.k02 = real(e * sqrt(c.r2 / c.r0));
+  r.k12 = real(dt * sqrt(c.r2 / c.r1));
+  r.f0 = real(c.q0 * dt / c.r0);
+  r.f1 = real(c.q1 * dt / c.r1);
+  r.f2 = real(c.q2 * dt / c.r2);
+  r.ka = real(dt * sqrt(c.b1 / c.b0));
+  r.fa0 = real(c.qa0 * dt / c.b0);
+  r.fa1 = real(c.qa1 * dt / c.b1);
+  r.gam = real(c.rg / c.r0);
+  r.type = types[k];
+  out[k] = r;
+}
 
 // The copy lane of every ring kernel: keeps the payload ring full, gated only by the ring's empty
 // barriers.  Stage s holds CH steps x D rows of F reals; the rows of one (step, column) are contiguous in
@@ -381,10 +413,19 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
 #define B200KF_COPY_WARPS 4
 #endif
 constexpr int kCopyWarps = B200KF_COPY_WARPS;
+// service warps of a model's per-filter ring kernel.  The constant-acceleration filter (24 state / covariance values
+// per thread) gets two: 448 math threads + 64 = 512 threads leave 128 registers per thread (576 threads round to 96),
+// and its FP64-bound loop (~160 FP64 instructions against 9 bulk copies per step) needs no more copy lanes.
+template <int MODEL, typename real>
+constexpr int svc_warps() {
+  using MT = ModelTraits<MODEL, false, real>;
+  return (!MT::Filter::fast2 && !MT::Sym3::eligible && MT::SymCA::eligible) ? 2 : kCopyWarps;
+}
 
 template <int MODEL, typename real, bool SYM, bool FULL, int F, bool BULK = false>
-__global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
-    kf_run_tma_kernel(const RunParams p, const LeanRecT<real>* __restrict__ sched) {
+__global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
+    kf_run_tma_kernel(const RunParams p, const void* __restrict__ sched_v) {
+  constexpr int kCopyWarps = svc_warps<MODEL, real>();  // (shadows the default: this model's service warps)
   // F math threads (filters) per CTA: 896 fills an SM with one CTA; 448 / 224 keep every SM busy when a
   // GPU's shard is small (N <= 148 * 448), with a proportionally deeper ring in the same shared memory
   // BULK (per-step outputs only): the math threads write a step's outputs (trajectory rows, log det) into a
@@ -393,8 +434,9 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
   // the store queue: long-scoreboard waits of 6.6 per issue, profiles/r01c_ncu_trajectory_kernel.txt).
   static_assert(!BULK || FULL, "the output ring belongs to the per-step-output kernel");
   constexpr int kTmaThreads = F;
-  constexpr int kStages = BULK ? kBulkInStages : ring_stages<real, F>();
-  constexpr int kChunk = BULK ? bulk_chunk<real, F>() : ring_chunk<real, F>();
+  constexpr int kD = ModelTraits<MODEL, false, real>::d;
+  constexpr int kStages = BULK ? kBulkInStages : ring_stages<real, F, kD>();
+  constexpr int kChunk = BULK ? bulk_chunk<real, F, kD>() : ring_chunk<real, F, kD>();
   constexpr int kLoadWarps = BULK ? kCopyWarps - 1 : kCopyWarps;  // BULK: the last service warp stores
   // a copy lane waits on a stage's empty barrier by phase PARITY: that is only unambiguous while it can
   // never be two uses of a stage ahead, i.e. while its stride (kLoadWarps chunks) is within one ring turn
@@ -403,13 +445,15 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
   using Flt = typename TmaFlt<MODEL, real, SYM>::type;
   constexpr int n = MT::n;
   constexpr int D = MT::d;
-  static_assert(MT::Filter::fast2 || (SYM && MT::Sym3::eligible), "ring kernel is for the closed-form filters");
+  static_assert(MT::Filter::fast2 || (SYM && (MT::Sym3::eligible || MT::SymCA::eligible)),
+                "ring kernel is for the closed-form filters");
   if (!mode_selected(p.dense_flag, SYM ? MODE_SYMMETRIC : MODE_DECOUPLED)) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   real* stage_buf = reinterpret_cast<real*>(smem_raw);  // [kStages][kChunk][D][kTmaThreads]
   constexpr size_t kStageReals = static_cast<size_t>(kChunk) * D * kTmaThreads;
-  using Rec = LeanRecT<real>;
+  using Rec = typename Flt::LeanRec;  // the filter's step record (LeanRecT, or CARecT for the constant-acceleration form)
+  const Rec* __restrict__ sched = static_cast<const Rec*>(sched_v);
   // output ring (BULK): [kOutStages][kChunk][out_rows][kTmaThreads], rows = the trajectory components, then log det
   const int out_nc = (FULL && p.traj != nullptr) ? p.traj_ncomp : 0;
   const int out_rows = out_nc + ((FULL && p.logdet != nullptr) ? 1 : 0);
@@ -506,7 +550,9 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
   int min_hi = 0x7ff00000;
   float mant32 = 1.0f;
   int max32 = 0;
-  if constexpr (LEAN) {
+  // filters that live in R-normalised coordinates: the lean aggregate loop, and the record-driven filter in every mode
+  constexpr bool NORM = LEAN || Flt::rec_api;
+  if constexpr (NORM) {
     if (active && T > 0) flt.to_normalized(p.mc);
   }
 
@@ -553,12 +599,15 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
         }
         const real dt = rec.dt;
         const int ty = rec.type;
-        flt.predict(dt, p.mc);
+        if constexpr (Flt::rec_api) flt.predict(rec);
+        else flt.predict(dt, p.mc);
         bool do_update = (ty != EV_PREDICT_ONLY);
         if constexpr (FULL) {
           if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > gate);  // :1023-1025
         }
-        const double det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
+        double det;
+        if constexpr (Flt::rec_api) det = do_update ? flt.update(rec, ty, u, ok) : flt.det(ok);
+        else det = do_update ? flt.update(dt, p.mc, ty, u, ok) : flt.det(ok);
         if constexpr (BULK) {
           real* o = ob + static_cast<size_t>(c) * out_rows * kTmaThreads;
           flt.for_each_state([&](auto G, real v) {
@@ -607,6 +656,10 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
   }
 
   if (!active) return;
+  double last_det = 1.0;  // record-driven filters: det P of the final state, taken in their normalised coordinates
+  if constexpr (Flt::rec_api) {
+    if (T > 0) last_det = flt.det(ok);
+  }
   if constexpr (LEAN) {
     if (T > 0) {
       if constexpr (LEAN32) {
@@ -620,6 +673,8 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
       }
       flt.from_normalized(p.mc);
     }
+  } else if constexpr (NORM) {
+    if (T > 0) flt.from_normalized(p.mc);
   }
   {
     real* xg = static_cast<real*>(p.x) + f * n;
@@ -643,7 +698,8 @@ __global__ void __launch_bounds__(F + 32 * kCopyWarps, 1)
     }
     a[0] = mx;
     a[1] = sm;
-    a[2] = (T > 0) ? log(flt.det(ok)) : (p.agg_continue ? a[2] : 0.0);
+    if constexpr (Flt::rec_api) a[2] = (T > 0) ? log(last_det) : (p.agg_continue ? a[2] : 0.0);
+    else a[2] = (T > 0) ? log(flt.det(ok)) : (p.agg_continue ? a[2] : 0.0);
     a[3] = cnt;
   }
   if (p.status != nullptr) {
@@ -1332,17 +1388,17 @@ constexpr size_t shared_smem_bytes() {
 template <int MODEL, typename real, int F>
 constexpr size_t tma_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
-  constexpr int st = ring_stages<real, F>(), ch = ring_chunk<real, F>();
+  constexpr int st = ring_stages<real, F, MT::d>(), ch = ring_chunk<real, F, MT::d>();
   return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
-         static_cast<size_t>(st) * ch * sizeof(LeanRecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
+         static_cast<size_t>(st) * ch * sizeof(CARecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
 }
 template <int MODEL, typename real, int F>
 static size_t tma_bulk_smem_bytes(int out_rows) {
   using MT = ModelTraits<MODEL, false, real>;
-  constexpr int st = kBulkInStages, ch = bulk_chunk<real, F>();
+  constexpr int st = kBulkInStages, ch = bulk_chunk<real, F, MT::d>();
   return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
          static_cast<size_t>(kOutStages) * ch * out_rows * F * sizeof(real) +
-         static_cast<size_t>(st) * ch * sizeof(LeanRecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
+         static_cast<size_t>(st) * ch * sizeof(CARecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
 }
 
 // filters per CTA of the ring kernels: the largest of {896, 448, 224} that still gives every SM a CTA
@@ -1376,8 +1432,15 @@ static bool tma_possible(const b200kf_model* m, const RunParams& p, bool full) {
 template <int MODEL, typename real>
 static bool tma_sym3_possible(const b200kf_model* m, const RunParams& p, bool full) {
   using MT = ModelTraits<MODEL, false, real>;
-  if constexpr (MT::Filter::fast2 || !MT::Sym3::eligible) {
+  if constexpr (MT::Filter::fast2 || !(MT::Sym3::eligible || MT::SymCA::eligible)) {
     return false;
+  } else if constexpr (MT::SymCA::eligible) {
+    // the constant-acceleration models (the reference's own CA15 / CA8): every mode incl. the adaptive gate runs on
+    // the ring (the gate only skips update(), the state predict is in predict()); per-step P stays with the LDG kernel
+    (void)full;
+    if (p.ptraj != nullptr || m->use_tma == 0 || m->use_ca_ring == 0) return false;
+    const long long align_elems = 16 / static_cast<long long>(sizeof(real));
+    return p.n_steps >= 1 && (p.n_filters % align_elems) == 0 && (reinterpret_cast<uintptr_t>(p.payload) & 15u) == 0;
   } else {
     // per-step outputs run on the ring too; the adaptive gate does not (this filter applies the control input
     // inside update(), which a gated step skips) and stays with the LDG kernel
@@ -1402,24 +1465,24 @@ constexpr bool tma_sym_eligible() {
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL, int F>
-static cudaError_t launch_tma_f(const RunParams& p, const LeanRecT<real>* sched, cudaStream_t st) {
+static cudaError_t launch_tma_f(const RunParams& p, const void* sched, cudaStream_t st) {
   constexpr size_t smem = tma_smem_bytes<MODEL, real, F>();
   const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
   cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, FULL, F>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kf_run_tma_kernel<MODEL, real, SYM, FULL, F><<<blocks, F + 32 * kCopyWarps, smem, st>>>(p, sched);
+  kf_run_tma_kernel<MODEL, real, SYM, FULL, F><<<blocks, F + 32 * svc_warps<MODEL, real>(), smem, st>>>(p, sched);
   return cudaGetLastError();
 }
 template <int MODEL, typename real, bool SYM, int F>
-static cudaError_t launch_tma_bulk_f(const RunParams& p, const LeanRecT<real>* sched, int out_rows, cudaStream_t st) {
+static cudaError_t launch_tma_bulk_f(const RunParams& p, const void* sched, int out_rows, cudaStream_t st) {
   const size_t smem = tma_bulk_smem_bytes<MODEL, real, F>(out_rows);
   const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
   cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, true, F, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(tma_bulk_smem_bytes<MODEL, real, F>(kBulkMaxRows)));
   if (err != cudaSuccess) return err;
-  kf_run_tma_kernel<MODEL, real, SYM, true, F, true><<<blocks, F + 32 * kCopyWarps, smem, st>>>(p, sched);
+  kf_run_tma_kernel<MODEL, real, SYM, true, F, true><<<blocks, F + 32 * svc_warps<MODEL, real>(), smem, st>>>(p, sched);
   return cudaGetLastError();
 }
 // per-step outputs through the output ring: trajectory components and / or log det (at most kBulkMaxRows rows per
@@ -1431,42 +1494,75 @@ static bool bulk_out_ok(const b200kf_model* m, const RunParams& p, int* rows) {
   return m->use_bulk_out != 0 && p.used == nullptr && *rows >= 1 && *rows <= kBulkMaxRows && aligned;
 }
 template <int MODEL, typename real, bool SYM, bool FULL>
-static cudaError_t launch_tma_one(const b200kf_model* m, const RunParams& p, const LeanRecT<real>* sched, int f,
+static cudaError_t launch_tma_one(const b200kf_model* m, const RunParams& p, const void* sched, int f,
                                   cudaStream_t st) {
+  using MTo = ModelTraits<MODEL, false, real>;
+  // (the constant-acceleration filter is never launched with 896 filters per CTA: not instantiated)
+  constexpr bool k896 = MTo::Filter::fast2 || MTo::Sym3::eligible;
   if constexpr (FULL) {
     int rows = 0;
     if (bulk_out_ok(m, p, &rows)) {
-      if (f == 896) return launch_tma_bulk_f<MODEL, real, SYM, 896>(p, sched, rows, st);
-      if (f == 448) return launch_tma_bulk_f<MODEL, real, SYM, 448>(p, sched, rows, st);
+      if constexpr (k896) {
+        if (f == 896) return launch_tma_bulk_f<MODEL, real, SYM, 896>(p, sched, rows, st);
+      }
+      if (f >= 448) return launch_tma_bulk_f<MODEL, real, SYM, 448>(p, sched, rows, st);
       return launch_tma_bulk_f<MODEL, real, SYM, 224>(p, sched, rows, st);
     }
   }
-  if (f == 896) return launch_tma_f<MODEL, real, SYM, FULL, 896>(p, sched, st);
-  if (f == 448) return launch_tma_f<MODEL, real, SYM, FULL, 448>(p, sched, st);
+  if constexpr (k896) {
+    if (f == 896) return launch_tma_f<MODEL, real, SYM, FULL, 896>(p, sched, st);
+  }
+  if (f >= 448) return launch_tma_f<MODEL, real, SYM, FULL, 448>(p, sched, st);
   return launch_tma_f<MODEL, real, SYM, FULL, 224>(p, sched, st);
 }
+
+// IMU variances / process-noise rates of the angular chains' lead member
+template <class A0, class... As>
+static void ca_ang_const(ChainList<A0, As...>, const ModelConst& mc, CAConst& c) {
+  c.b0 = mc.r_imu[A0::gidx(0)], c.b1 = mc.r_imu[A0::gidx(1)];
+  c.qa0 = mc.q[A0::gidx(0)], c.qa1 = mc.q[A0::gidx(1)];
+}
+static void ca_ang_const(...) {}
 
 template <int MODEL, typename real>
 static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool with_sym, bool with_dec,
                               bool full, void* sched_mem, cudaStream_t st) {
   using MTl = ModelTraits<MODEL, false, real>;
-  if constexpr (!MTl::Filter::fast2 && !MTl::Sym3::eligible) {
+  if constexpr (!MTl::Filter::fast2 && !MTl::Sym3::eligible && !MTl::SymCA::eligible) {
     return cudaErrorInvalidValue;
   } else {
     constexpr bool kFast2 = MTl::Filter::fast2;
-    LeanRecT<real>* sched = static_cast<LeanRecT<real>*>(sched_mem);  // [n_steps] records, scratch of this call
-    LeanConst lc{1.0, 1.0, 1.0, 1.0, 1.0};  // rate constants of the symmetric group (only its lean step reads them)
-    if constexpr (kFast2 && ModelTraits<MODEL, false, real>::Sym2::eligible) {
-      using G0 = typename ModelTraits<MODEL, false, real>::Sym2::Lead;
-      lc.q0 = m->mc.q[G0::gidx(0)];
-      lc.q1 = m->mc.q[G0::gidx(1)];
-      lc.r0 = m->mc.r_imu[G0::gidx(0)];
-      lc.r1 = m->mc.r_imu[G0::gidx(1)];
-      if constexpr (G0::gps(0) >= 0) lc.rg = m->mc.r_gps[G0::gps(0)];
+    constexpr bool kCA = !kFast2 && !MTl::Sym3::eligible && MTl::SymCA::eligible;
+    void* sched = sched_mem;  // [n_steps] step records of the filter's type, scratch of this call
+    if constexpr (kCA) {
+      using L0 = typename MTl::SymCA::Lead;
+      using A0 = typename CALists<MODEL>::Ang;
+      CAConst c{};
+      c.r0 = m->mc.r_imu[L0::gidx(0)], c.r1 = m->mc.r_imu[L0::gidx(1)], c.r2 = m->mc.r_imu[L0::gidx(2)];
+      c.q0 = m->mc.q[L0::gidx(0)], c.q1 = m->mc.q[L0::gidx(1)], c.q2 = m->mc.q[L0::gidx(2)];
+      ca_ang_const(A0{}, m->mc, c);
+      c.rg = m->mc.r_gps[L0::gps(0)];
+      c.c2 = m->mc.c2;
+      pack_ca_schedule_kernel<real><<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, c,
+                                                                             static_cast<CARecT<real>*>(sched));
+    } else {
+      LeanConst lc{1.0, 1.0, 1.0, 1.0, 1.0};  // rate constants of the symmetric group (only its lean step reads them)
+      if constexpr (kFast2 && ModelTraits<MODEL, false, real>::Sym2::eligible) {
+        using G0 = typename ModelTraits<MODEL, false, real>::Sym2::Lead;
+        lc.q0 = m->mc.q[G0::gidx(0)];
+        lc.q1 = m->mc.q[G0::gidx(1)];
+        lc.r0 = m->mc.r_imu[G0::gidx(0)];
+        lc.r1 = m->mc.r_imu[G0::gidx(1)];
+        if constexpr (G0::gps(0) >= 0) lc.rg = m->mc.r_gps[G0::gps(0)];
+      }
+      pack_schedule_kernel<real><<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc,
+                                                                          static_cast<LeanRecT<real>*>(sched));
     }
-    pack_schedule_kernel<real><<<(p.n_steps + 255) / 256, 256, 0, st>>>(p.types, p.dts, p.n_steps, lc, sched);
     cudaError_t err = cudaSuccess;
-    const int f = pick_ring_f(p.n_filters, m->sm_count, m->ring_f_cap);
+    // the constant-acceleration filter holds 24 state / covariance values per thread: 448 filters per CTA at most
+    // (576 threads x ~110 registers), which also keeps a step's rows (d = 9: 32 KB) small enough for a 6-deep ring
+    const int fcap = (kCA && m->ring_f_cap > 448) ? 448 : m->ring_f_cap;
+    const int f = pick_ring_f(p.n_filters, m->sm_count, fcap);
     if constexpr (kFast2) {
       if (with_dec) {
         err = full ? launch_tma_one<MODEL, real, false, true>(m, p, sched, f, st)
@@ -1474,7 +1570,7 @@ static cudaError_t launch_tma(const b200kf_model* m, const RunParams& p, bool wi
         if (err != cudaSuccess) return err;
       }
     }
-    if constexpr ((kFast2 && MTl::Sym2::eligible) || (!kFast2 && MTl::Sym3::eligible)) {
+    if constexpr ((kFast2 && MTl::Sym2::eligible) || (!kFast2 && (MTl::Sym3::eligible || MTl::SymCA::eligible))) {
       if (with_sym) {
         err = full ? launch_tma_one<MODEL, real, true, true>(m, p, sched, f, st)
                    : launch_tma_one<MODEL, real, true, false>(m, p, sched, f, st);
@@ -1637,7 +1733,8 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
   // scratch of THIS call (stream-ordered, freed behind the last kernel below): the three AUTO dispatch flags
   // and the packed step records of the ring kernels
   ScratchBuf scratch;
-  B200KF_CUDA_TRY(scratch.alloc(m, 256 + static_cast<size_t>(p.n_steps) * sizeof(SchedRec), st));
+  B200KF_CUDA_TRY(scratch.alloc(m, 256 + static_cast<size_t>(p.n_steps) * sizeof(CARecT<double>), st));
+  static_assert(sizeof(CARecT<double>) >= sizeof(SchedRec), "the scratch holds either record type");
   void* sched_mem = static_cast<char*>(scratch.p) + 256;
   const bool tma_sym = tma && tma_sym_eligible<MODEL, real>() && r_pos;
   // the shared-covariance kernels stream the payload with bulk copies: 16-byte aligned rows
@@ -1652,7 +1749,10 @@ static int launch_precision(const b200kf_model* m, RunParams p, unsigned flags, 
     return B200KF_OK;
   }
   if (flags & B200KF_RUN_FORCE_SHARED) flags |= B200KF_RUN_FORCE_SYMMETRIC;  // next-best guarantee
-  const bool tma3 = sym && tma_sym3_possible<MODEL, real>(m, p, full);  // BIAS9: symmetric ring kernel, aggregate mode
+  // BIAS9 (control-input chains) and the constant-acceleration models CA15 / CA8: symmetric-form ring kernels; the
+  // latter carry an R-normalised covariance and need positive measurement variances
+  const bool tma3 = sym && tma_sym3_possible<MODEL, real>(m, p, full) &&
+                    (!ModelTraits<MODEL, false, real>::SymCA::eligible || r_pos);
   if ((flags & B200KF_RUN_FORCE_SYMMETRIC) && sym) {
     p.dense_flag = nullptr;
     if (tma_sym || tma3) {

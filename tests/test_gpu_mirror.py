@@ -319,8 +319,12 @@ def test_brute_force_epsilon_guard_settles_borderline_decisions_in_reference_ari
     ld0 = np.linalg.slogdet(P0)[1]
     assert np.sum(maxima > ld0 + 1e-6) > 100  # borderline candidates exist whose max is a computed term
     n_guarded = 0
-    for r in (40, 130, 300):
-        # r-th distinct candidate: the threshold one ULP above its max makes it feasible, at its max infeasible
+    # candidates whose max is a strict minimum over everything enumerated before them: with the threshold at their
+    # max (+- one ULP) every earlier candidate is infeasible, so THEIR borderline decision picks the winner
+    prefix_min = [r for r in range(1, len(maxima)) if maxima[r] < maxima[:r].min() and maxima[r] > ld0 + 1e-6]
+    assert len(prefix_min) >= 3
+    for r in prefix_min[:2] + prefix_min[-2:]:
+        # the threshold one ULP above the candidate's max makes it feasible, at its max (strict <) infeasible
         for thr in (np.nextafter(maxima[r], np.inf), maxima[r], np.nextafter(maxima[r], -np.inf)):
             ref = ko.brute_force_select(m, window, xt, P0, init[0], t_end, float(thr))
             out = k.run_brute_force_kalman_filter_no_sampling_min_usage(w0, w0 + L, float(thr), P0.copy(), init)

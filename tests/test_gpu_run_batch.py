@@ -521,3 +521,63 @@ def test_output_ring_bulk_stores_match_per_thread_stores_and_oracle(precision, N
             if want_ld:
                 ld = a["logdet"].cpu().numpy()[:, pick]
                 assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < tol
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["CA15", "CA8"])
+@pytest.mark.parametrize("N", [1000, 40000])
+def test_constant_acceleration_ring_kernel_matches_ldg_kernel_and_oracle(name, N, precision, monkeypatch):
+    """The reference's own models (kf_workers.py:493-614 CA15, hw5_2.py:219-304 CA8) with one covariance per
+    filter run on the per-filter ring kernel in its constant-acceleration form (SymCAFilter: R-normalised 3 x 3 and
+    2 x 2 covariances, joint closed-form H = I update); B200KF_CA_RING=0 keeps the scalar-update LDG kernel.
+    Both against the oracle and against each other: aggregate mode, trajectory mode through the output ring,
+    time-chunked continuation, predict-only events and the adaptive gate, at both CTA sizes (224 / 448)."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    T = 61
+    tol = RTOL64 if precision == "f64" else RTOL32
+    m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=71)
+    rng = np.random.default_rng(5)
+    P0 = P0 * (1.0 + rng.random(N))[:, None, None]  # one covariance per filter (axis-symmetric, chain-compatible)
+    types = types.copy()
+    types[[17, 40]] = 2  # predict-only events in the stream
+    pick = np.unique(np.concatenate([np.arange(0, N, max(1, N // 41)), [N - 1]]))
+    ref = ko.run_batch(m, types, dts, payload[:, :, pick], x0[pick], P0[pick])
+    outs = {}
+    for ring in ("1", "0"):
+        monkeypatch.setenv("B200KF_CA_RING", ring)
+        eng = Engine(name, precision=precision)
+        agg = eng.run_batch(types, dts, payload, x0, P0)
+        full = eng.run_batch(types, dts, payload, x0, P0, traj_ncomp=6, want_logdet=True)
+        x, P, a = x0, P0, None
+        for k0 in range(0, T, 25):
+            sl = slice(k0, min(T, k0 + 25))
+            o = eng.run_batch(types[sl], dts[sl], payload[sl], x, P, agg=a)
+            x, P, a = o["x"], o["P"], o["agg"]
+        outs[ring] = (agg, full, o)
+        for out in (agg, full, o):
+            assert int(out["status"].sum()) == 0
+            assert rel(out["x"].cpu().numpy()[pick], ref["x"]) < tol
+            assert rel(out["P"].cpu().numpy()[pick], ref["P"]) < tol
+            ag = out["agg"].cpu().numpy()[pick]
+            assert np.max(np.abs(ag[:, :3] - ref["agg"]) / np.maximum(1.0, np.abs(ref["agg"]))) < tol
+            assert np.all(ag[:, 3] == T)
+        assert rel(full["traj"].cpu().numpy()[:, :, pick], ref["traj"][:, :6]) < tol
+        ld = full["logdet"].cpu().numpy()[:, pick]
+        assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < tol
+    # the two kernels agree far below the oracle tolerance (same recursion, different formulation)
+    t2 = 1e-11 if precision == "f64" else 2e-5
+    for a, b in zip(outs["1"], outs["0"]):
+        assert rel(a["x"].cpu().numpy(), b["x"].cpu().numpy()) < t2
+        assert rel(a["P"].cpu().numpy(), b["P"].cpu().numpy()) < t2
+    if precision == "f64" and N <= 1000:
+        # adaptive gate on the ring: the same decisions as the LDG kernel away from the threshold
+        thr = float(np.median(ref["logdet"][20:])) + 1.0
+        g = {}
+        for ring in ("1", "0"):
+            monkeypatch.setenv("B200KF_CA_RING", ring)
+            g[ring] = Engine(name).run_batch(types, dts, payload, x0, P0, gate_threshold=thr, want_used=True, want_logdet=True)
+        ua, ub = g["1"]["used"].cpu().numpy(), g["0"]["used"].cpu().numpy()
+        same = (ua == ub).all(axis=0)
+        assert same.mean() > 0.99 and 0.02 < ua.mean() < 0.98
+        assert rel(g["1"]["x"].cpu().numpy()[same], g["0"]["x"].cpu().numpy()[same]) < 1e-10
+        assert rel(g["1"]["P"].cpu().numpy()[same], g["0"]["P"].cpu().numpy()[same]) < 1e-10
