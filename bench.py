@@ -430,6 +430,47 @@ def leg_config5(torch, a, hbm_peak):
     return out
 
 
+def leg_reference_models(torch, a, hbm_peak):
+    """The reference's OWN models with one covariance per filter: CA15 (kf_workers.py:493-614, 72 B of payload per
+    step) and CA8 (hw5_2.py:219-304, 32 B), aggregate mode and trajectory mode (x[0:6] + log det per step, what
+    run_kalman_filter_full returns), on the per-filter ring kernel in its constant-acceleration form."""
+    from sensorfusion_kalmanfilter_b200 import synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload
+    N, T = 131072, 1500
+    out = {}
+    for name in ("CA15", "CA8"):
+        os.environ["B200KF_SHARED"] = "0"
+        eng = Engine(name)
+        os.environ.pop("B200KF_SHARED", None)
+        sp = eng.spec
+        types, dts = synth.gps_imu_schedule(T)
+        types_d, dts_d = torch.from_numpy(types).to(eng.device), torch.from_numpy(dts).to(eng.device)
+        pay = fill_payload(eng, types_d, N, seed=99)
+        scale = 1.0 + (np.arange(N) % 1024) / 1024.0
+        x = torch.zeros((N, sp.n), dtype=eng.real, device=eng.device)
+        P = torch.from_numpy(sp.default_P0()[None] * scale[:, None, None]).to(device=eng.device, dtype=eng.real).contiguous()
+        res = {}
+        for label, kw, out_b in (("aggregate", dict(want_agg=True), 0),
+                                 ("trajectory", dict(want_agg=False, traj_ncomp=6, want_logdet=True), 56)):
+            def one():
+                o = eng.run_batch(types_d, dts_d, pay, x, P, inplace=True, **kw)
+                del o
+            for _ in range(3):
+                one()
+            torch.cuda.synchronize()
+            st = _stats(_timed_loop(one, 60, torch))
+            bps = sp.d * 8 + out_b
+            gbs = float(N) * T * bps / (st["mean"] * 1e-3) / 1e9
+            res[label] = {"value": N * T / (st["mean"] * 1e-3), "unit": UNIT, "ms": st["mean"], "ms_min": st["min"],
+                          "algorithmic_bytes_per_filter_step": bps, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+                          "frac_burst": float(N) * T * bps / (st["min"] * 1e-3) / 1e9 / hbm_peak}
+        out[name] = res
+        del pay, x, P, eng
+        torch.cuda.empty_cache()
+    out["workload"] = f"{N} filters x {T} steps, f64, per-filter covariance (reference P0 x (1 + (f % 1024)/1024)), 60 back-to-back launches"
+    return out
+
+
 def leg_config2(torch, a, hbm_peak):
     """BASELINE configs[1] at full length: sampling rates 10..120 Hz x 4096 Monte-Carlo seeds of the 15-state filter
     with greedy one-event-per-window scheduling (kf_workers.py:826-957) over the whole 2 808 s stream (589 679
@@ -740,6 +781,7 @@ def run_gpu_arm(a):
         # the big legs need the memory of the headline buffers
         del payload, x, P
         torch.cuda.empty_cache()
+        ref_models = leg_reference_models(torch, a, hbm_peak) if not a.no_configs else None
         config5 = leg_config5(torch, a, hbm_peak) if not a.no_configs else None
         config2 = leg_config2(torch, a, hbm_peak) if not a.no_configs else None
 
@@ -779,7 +821,8 @@ def run_gpu_arm(a):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_pass * n_pass,
                 "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large,
                 "search_2p32": search_huge, "product_search": products,
-                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "config5": config5, "config2": config2}
+                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "reference_models": ref_models,
+                "config5": config5, "config2": config2}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

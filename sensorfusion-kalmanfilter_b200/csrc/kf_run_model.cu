@@ -277,8 +277,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 
 // shared -> global bulk store (the per-step outputs of the trajectory mode leave the SM as whole rows)
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+#ifdef B200KF_BULK_EVICT_FIRST
+  // streaming outputs: written once, never re-read by this launch -> do not let them displace the input rows in L2
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+               "r"(smem_u32(src)), "r"(bytes), "l"(pol)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
                : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -292,8 +301,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // Ring shape of the per-filter kernel WITH an output ring (trajectory mode through bulk stores): 4 input stages
 // and 2 output stages of the same number of steps; at F = 896 float64 that is 4 x 21 KB in + 2 x 7 KB x rows out
 // (rows <= kBulkMaxRows).  Smaller CTAs / float32 keep the bytes and take more steps per stage.
-constexpr int kBulkInStages = 4;
-constexpr int kOutStages = 2;
+#ifndef B200KF_BULK_IN_STAGES
+#define B200KF_BULK_IN_STAGES 4
+#endif
+#ifndef B200KF_BULK_OUT_STAGES
+#define B200KF_BULK_OUT_STAGES 2
+#endif
+constexpr int kBulkInStages = B200KF_BULK_IN_STAGES;
+constexpr int kOutStages = B200KF_BULK_OUT_STAGES;
 constexpr int kBulkMaxRows = 8;
 template <typename real, int F, int D = 3>
 constexpr int bulk_chunk() {
@@ -544,6 +559,7 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
   // running product's mantissa picks up <= 2^-24 relative per step, i.e. <= T 2^-24 absolute on a sum of
   // T logarithms
   constexpr bool LEAN32 = LEAN && sizeof(real) == 4;
+  constexpr int kRenorm = 4;  // float64 lean aggregate: steps between renormalisations of the running product
   // validity of the lean aggregate: integer min / max of the raw bits (a determinant <= 0 has a high word
   // <= 0, NaN / inf exceed the largest finite pattern).  The running product is renormalised every step by
   // masking its exponent field; the biased exponents are summed and the bias removed after the loop.
@@ -590,10 +606,22 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
           } else {
             min_hi = min(min_hi, __double2hiint(double(v)));
             acc_max = max(acc_max, __double_as_longlong(double(v)));
+#ifdef B200KF_AGG_RENORM_EVERY_STEP
             const double m = acc_mant * double(v);
             const unsigned hi = static_cast<unsigned>(__double2hiint(m));
             acc_expo += static_cast<int>(hi >> 20);
             acc_mant = __hiloint2double(static_cast<int>((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(m));
+#else
+            // the running product is renormalised once per kRenorm steps (below), not per step: between two
+            // renormalisations it holds a mantissa in [1, 2) times at most kRenorm determinants, each checked to
+            // lie in [2^-240, 2^240] (ok flag) -- no overflow, the same sum of logarithms
+            acc_mant *= double(v);
+            if (((c + 1) % kRenorm) == 0 || c + 1 == steps) {
+              const unsigned hi = static_cast<unsigned>(__double2hiint(acc_mant));
+              acc_expo += static_cast<int>(hi >> 20) - 1023;
+              acc_mant = __hiloint2double(static_cast<int>((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(acc_mant));
+            }
+#endif
           }
           return;
         }
@@ -668,8 +696,14 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
         acc_max = __double_as_longlong(double(__int_as_float(max32)));
         acc_expo -= 127 * T;
       } else {
+#ifdef B200KF_AGG_RENORM_EVERY_STEP
         ok = ok && min_hi > 0 && acc_max < 0x7ff0000000000000LL;
         acc_expo -= 1023 * T;
+#else
+        // every (normalised) determinant within [2^-240, 2^240]: the renormalise-every-kRenorm-steps product cannot
+        // have left the double range (a covariance beyond that is flagged like a non-positive one)
+        ok = ok && min_hi >= ((1023 - 240) << 20) && acc_max < (static_cast<long long>(1023 + 240) << 52);
+#endif
       }
       flt.from_normalized(p.mc);
     }
