@@ -290,6 +290,21 @@ int b200kf_select_greedy_gains(const b200kf_model* model, int64_t n_events, cons
                                void* stream);
 int b200kf_gain_record_bytes(const b200kf_model* model, size_t* bytes);
 
+/* The same walk in CHUNKS of the event stream (run_kalman_filter_scheduled's loop, kf_workers.py:877-947, cut at
+ * arbitrary event indices): events [e_begin, e_end) of types/times; the walk's state between calls -- previous
+ * selected time, the open window's queue summary -- lives in `carry` (DEVICE f64 [I, 8], zero-filled before the
+ * first chunk), the covariance in P_state (DEVICE f64 [I, n, n], written by every call, read by all but the
+ * first, which starts from P0 / t_prev) and the running selection count in n_sel (in/out).  sel / gain_records
+ * are filled at their global positions [I, max_sel].  Chunk after chunk gives bit for bit the selections,
+ * covariances and records of one b200kf_select_greedy_gains call over the whole stream; a caller can so run
+ * the selection of chunk c+1 on one stream while the filters of chunk c consume its records on another.
+ * At most 2048 instances (one warp each). */
+int b200kf_select_greedy_chunk(const b200kf_model* model, int64_t e_begin, int64_t e_end, const uint8_t* types,
+                               const double* times, int32_t n_inst, const double* periods,
+                               const double* t_prev, const double* P0, double* carry, double* P_state,
+                               int64_t max_sel, int32_t* sel, int64_t* n_sel, void* gain_records,
+                               uint32_t flags, void* stream);
+
 /* The filter loop for n_filters filters that share a schedule AND a covariance, given that
  * schedule's precomputed gain records (Monte-Carlo seeds of one configuration: the records are
  * computed once, every batch of seeds is then a pure stream -- no covariance recursion, no serial

@@ -78,6 +78,9 @@ SIGNATURES = {
                                      c_int64, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "b200kf_select_greedy_gains": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b200kf_select_greedy_chunk": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_uint32,
+                                           c_void_p]),
     "b200kf_gain_record_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),
     "b200kf_run_gains": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int32, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),

@@ -1004,6 +1004,39 @@ int b200kf_select_greedy_gains(const b200kf_model* m, int64_t n_events, const ui
   p.n_sel = reinterpret_cast<long long*>(n_sel);
   p.P_final = P_final;
   p.gain_recs = gain_records;
+  p.e_begin = 0;
+  p.carry = nullptr;
+  return dispatch_select(m, p, flags, static_cast<cudaStream_t>(stream));
+}
+
+int b200kf_select_greedy_chunk(const b200kf_model* m, int64_t e_begin, int64_t e_end, const uint8_t* types,
+                               const double* times, int32_t n_inst, const double* periods, const double* t_prev,
+                               const double* P0, double* carry, double* P_state, int64_t max_sel, int32_t* sel,
+                               int64_t* n_sel, void* gain_records, uint32_t flags, void* stream) {
+  if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
+  if (m->desc.model_id == MODEL_BIAS9)
+    return set_error(B200KF_ERR_UNSUPPORTED, "greedy selection needs an IMU measurement model");
+  if (e_begin < 0 || e_end < e_begin || n_inst < 0 || max_sel < 0) return set_error(B200KF_ERR_INVALID, "bad range or size");
+  if (e_end > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_events > 2^31-1");
+  if (n_inst == 0) return B200KF_OK;
+  if (!periods || !t_prev || !P0 || !carry || !P_state || !sel || !n_sel || (e_end > 0 && (!types || !times)))
+    return set_error(B200KF_ERR_INVALID, "null argument");
+  SelectParams p;
+  p.mc = m->mc;
+  p.n_events = e_end;
+  p.types = types;
+  p.times = times;
+  p.n_inst = n_inst;
+  p.periods = periods;
+  p.t_prev = t_prev;
+  p.P0 = P0;
+  p.max_sel = max_sel;
+  p.sel = sel;
+  p.n_sel = reinterpret_cast<long long*>(n_sel);
+  p.P_final = P_state;
+  p.gain_recs = gain_records;
+  p.e_begin = e_begin;
+  p.carry = carry;
   return dispatch_select(m, p, flags, static_cast<cudaStream_t>(stream));
 }
 

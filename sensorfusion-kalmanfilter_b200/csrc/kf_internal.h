@@ -141,7 +141,13 @@ struct SelectParams {
   double* P_final;             // DEVICE [I, n, n] or null
   void* gain_recs;             // DEVICE [I, max_sel] gain records of the selected events (axis-symmetric form) or null
   int lane_stride;             // set by the launcher: 32 = one instance per warp (few instances), 1 = packed
+  // chunked walk (b200kf_select_greedy_chunk): events [e_begin, n_events) of the stream, the walk's state between
+  // calls in `carry` (DEVICE f64 [I, 8]: prev, q_first, first_gps, first_imu, t_gps, t_imu, ty_imu, started), the
+  // covariance in P_final (in/out) and the selection count in n_sel (in/out).  carry == null: a whole walk.
+  long long e_begin;
+  double* carry;
 };
+constexpr int kSelectCarry = 8;
 
 // run_brute_force_kalman_filter (KF_SensorFusion.ipynb:804-954): one event per window queue,
 // full filter with state per sequence, RMSE-vs-track objective.

@@ -538,7 +538,9 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
   const int lane = threadIdx.x;
   if (inst >= p.n_inst) return;
   typename MT::Filter flt;
-  flt.each([&](auto& b) { b.load_cov(p.P0 + static_cast<long long>(inst) * n * n, n); });
+  double* cr = (p.carry != nullptr) ? p.carry + static_cast<long long>(inst) * kSelectCarry : nullptr;
+  const bool resume = cr != nullptr && cr[7] != 0.0;  // a later chunk of a chunked walk: state from the carry
+  flt.each([&](auto& b) { b.load_cov((resume ? p.P_final : p.P0) + static_cast<long long>(inst) * n * n, n); });
   double ir_gps[kMaxN], ir_imu[kMaxN];
   if constexpr (VAR == VAR_SYMMETRIC) {
     int og = 0, oi = 0;
@@ -560,9 +562,18 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
   long long first_gps = -1, first_imu = -1, q_first = -1;  // queue summary
   double t_gps = 0.0, t_imu = 0.0;                         // times of those candidates
   int ty_imu = EV_IMU;                                     // type of the first non-GPS candidate
-  double t_nx = (lane < E) ? __ldg(p.times + lane) : 0.0;
-  int ty_nx = (lane < E) ? __ldg(p.types + lane) : -1;
-  for (long long e0 = 0; e0 < E; e0 += 32) {
+  if (resume) {
+    prev = cr[0];
+    q_first = static_cast<long long>(cr[1]), first_gps = static_cast<long long>(cr[2]);
+    first_imu = static_cast<long long>(cr[3]);
+    t_gps = cr[4], t_imu = cr[5];
+    ty_imu = static_cast<int>(cr[6]);
+    ns = p.n_sel[inst];
+  }
+  const long long eb = p.e_begin;
+  double t_nx = (eb + lane < E) ? __ldg(p.times + eb + lane) : 0.0;
+  int ty_nx = (eb + lane < E) ? __ldg(p.types + eb + lane) : -1;
+  for (long long e0 = eb; e0 < E; e0 += 32) {
     const double t_l = t_nx;
     const int ty_l = ty_nx;
     if (e0 + 32 + lane < E) {  // next batch, off the serial chain
@@ -680,6 +691,13 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
   }
   if (lane != 0) return;
   p.n_sel[inst] = ns;
+  if (cr != nullptr) {  // the walk's state at the end of this chunk (the open queue carries over)
+    cr[0] = prev;
+    cr[1] = static_cast<double>(q_first), cr[2] = static_cast<double>(first_gps), cr[3] = static_cast<double>(first_imu);
+    cr[4] = t_gps, cr[5] = t_imu;
+    cr[6] = static_cast<double>(ty_imu);
+    cr[7] = 1.0;
+  }
   if (p.P_final != nullptr) {
     double* Pg = p.P_final + static_cast<long long>(inst) * n * n;
     if constexpr (!DENSE) {
@@ -704,6 +722,8 @@ int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams
   const bool sym_ok = (flags & B200KF_RUN_FORCE_SYMMETRIC) && m->use_sym && SymF::constants_equal(m->mc);
   if (p.gain_recs != nullptr && !sym_ok)
     return set_error(B200KF_ERR_UNSUPPORTED, "gain records need B200KF_RUN_FORCE_SYMMETRIC (an axis-symmetric P0 and equal rates)");
+  if (p.carry != nullptr && !(p.lane_stride == 32 && m->use_select_warp))
+    return set_error(B200KF_ERR_UNSUPPORTED, "chunked selection runs on the warp-per-instance kernel (<= 2048 instances)");
   if (p.lane_stride == 32 && m->use_select_warp) {  // few instances: a warp each, events loaded 32 at a time
     const unsigned wb = static_cast<unsigned>(p.n_inst);
     if (sym_ok)

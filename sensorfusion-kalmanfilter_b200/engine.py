@@ -381,6 +381,20 @@ class Engine:
         sels = [sel_h[i, :min(int(ns[i]), max_sel)].copy() for i in range(I)]
         return (sels, P_f, recs) if want_gains else (sels, P_f)
 
+    def scheduled_sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events):
+        """scheduled_sweep_chunked with the selection OFF the critical path: the greedy selection is itself walked
+        in time chunks (b200kf_select_greedy_chunk, one warp per rate, on its own stream) one chunk AHEAD of the
+        filters, which consume its gain records as pure streams (b200kf_run_gains).  Per chunk the host waits only
+        for that chunk's twelve selection counts (a 96-byte pinned copy).  The reference's P0 shape (axis-symmetric,
+        kf_workers.py:851) is assumed, as for use_gains.  Returns {rate: dict(sel (device), n_sel, x, P, agg)}."""
+        return _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events)
+
+    def select_state(self, types, times, periods, t_prev, P0, *, max_sel=None, want_gains=True):
+        """A chunked greedy selection (b200kf_select_greedy_chunk): returns a SelectState whose advance(e_end)
+        enqueues the walk over the next events; selections, covariances and gain records come out bit for bit as
+        from one select_greedy call.  The axis-symmetric form only (P0 as the reference's, kf_workers.py:851)."""
+        return SelectState(self, types, times, periods, t_prev, P0, max_sel, want_gains)
+
     def run_gains(self, gain_records, payload, x, *, want_agg=True, traj_ncomp=0, want_logdet=False, agg=None,
                   stream=None, inplace=False, step_rows=None):
         """N filters that share a schedule and a covariance, from that schedule's precomputed gain
@@ -580,6 +594,121 @@ class Engine:
             P = st[i]["P"] if recs is None else P_fin[i].to(self.real).expand(N, sp.n, sp.n)
             out[f] = {"sel": sels[i], "x": st[i]["x"], "P": P, "agg": st[i]["agg"]}
         return out
+
+
+def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events):
+    """Engine.scheduled_sweep_pipelined (defined below the class for length)."""
+    torch = _torch()
+    sp = self.spec
+    rates = list(rates)
+    R = len(rates)
+    types = np.ascontiguousarray(types, dtype=np.uint8)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    E = len(types)
+    bounds = list(range(0, E, int(chunk_events))) + [E]
+    nch = len(bounds) - 1
+    P0 = np.asarray(P0, dtype=np.float64)
+    st = self.select_state(types, times, [1.0 / f for f in rates], [t_prev] * R, np.repeat(P0[None], R, axis=0),
+                           want_gains=True)
+    x0_d = self._dev(x0, self.real)
+    N = int(x0_d.shape[0])
+    if (N * (4 if sp.precision == "f32" else 8)) % 16 != 0:
+        raise ValueError("the pipelined sweep streams the payload with bulk copies: N must make 16-byte rows")
+    pool = getattr(self, "_sweep_engines", [])
+    while len(pool) < R - 1:
+        pool.append(Engine(self.spec, device=self.device.index))
+    self._sweep_engines = pool
+    engines = [self] + pool[:R - 1]
+    spool = getattr(self, "_sweep_streams", [])
+    while len(spool) < R:
+        spool.append(torch.cuda.Stream(device=self.device))
+    self._sweep_streams = spool
+    sel_stream = getattr(self, "_select_stream", None)
+    if sel_stream is None:
+        sel_stream = self._select_stream = torch.cuda.Stream(device=self.device)
+    cur = torch.cuda.current_stream(self.device)
+    nsel_host = torch.zeros((nch, R), dtype=torch.int64).pin_memory()
+    evs = [torch.cuda.Event() for _ in range(nch)]
+    sel_stream.wait_stream(cur)
+
+    def enqueue_selection(c):
+        with torch.cuda.stream(sel_stream):
+            st.advance(bounds[c + 1], stream=sel_stream)
+            nsel_host[c].copy_(st.n_sel, non_blocking=True)
+            evs[c].record(sel_stream)
+
+    enqueue_selection(0)
+    xs = [x0_d.clone() for _ in rates]
+    aggs = [None] * R
+    done = [0] * R
+    order = sorted(range(R), key=lambda j: -rates[j])  # the highest rate has the longest launches: first
+    for c in range(nch):
+        if c + 1 < nch:
+            enqueue_selection(c + 1)  # runs while this chunk's filters stream
+        e0, e1 = bounds[c], bounds[c + 1]
+        pay_d = payload_chunk(e0, e1)
+        evs[c].synchronize()  # this chunk's selection counts are on the host
+        cur.wait_event(evs[c])
+        for i in order:
+            j0, j1 = done[i], int(nsel_host[c, i])
+            if j1 == j0:
+                continue
+            stream = spool[i]
+            stream.wait_stream(cur)
+            with torch.cuda.stream(stream):
+                rows = st.sel[i, j0:j1] - e0
+                r = engines[i].run_gains(st.recs[i, j0:j1], pay_d, xs[i], agg=aggs[i], stream=stream, step_rows=rows,
+                                         inplace=True)
+            xs[i], aggs[i] = r["x"], r["agg"]
+            done[i] = j1
+        for stream in spool[:R]:
+            cur.wait_stream(stream)
+        del pay_d
+    cur.wait_stream(sel_stream)
+    out = {}
+    for i, f in enumerate(rates):
+        out[f] = {"sel": st.sel[i, :done[i]], "n_sel": done[i], "x": xs[i], "agg": aggs[i],
+                  "P": st.P[i].to(self.real).expand(N, sp.n, sp.n)}
+    return out
+
+
+class SelectState:
+    """State of a chunked greedy selection on the device: event arrays, per-instance carry, covariance,
+    selection list, counts and (optionally) gain records."""
+
+    def __init__(self, eng, types, times, periods, t_prev, P0, max_sel, want_gains):
+        torch = _torch()
+        self.eng = eng
+        sp = eng.spec
+        self.types = eng._dev(types, torch.uint8)
+        self.times = eng._dev(times, torch.float64)
+        self.E = int(self.types.numel())
+        self.periods = eng._dev(np.atleast_1d(periods), torch.float64)
+        self.I = int(self.periods.numel())
+        self.t_prev = eng._dev(np.broadcast_to(np.atleast_1d(t_prev), (self.I,)).astype(np.float64), torch.float64)
+        self.P0 = eng._dev(np.asarray(P0, dtype=np.float64).reshape(self.I, sp.n, sp.n), torch.float64)
+        self.max_sel = int(self.E if max_sel is None else max_sel)
+        dev = eng.device
+        self.carry = torch.zeros((self.I, 8), dtype=torch.float64, device=dev)
+        self.P = torch.empty((self.I, sp.n, sp.n), dtype=torch.float64, device=dev)
+        self.sel = torch.empty((self.I, max(1, self.max_sel)), dtype=torch.int32, device=dev)
+        self.n_sel = torch.zeros((self.I,), dtype=torch.int64, device=dev)
+        self.recs = (torch.empty((self.I, max(1, self.max_sel), eng.gain_record_bytes()), dtype=torch.uint8, device=dev)
+                     if want_gains else None)
+        self.done = 0
+
+    def advance(self, e_end, stream=None):
+        """Walk events [done, e_end) on `stream` (default: the current stream)."""
+        e_end = min(int(e_end), self.E)
+        eng = self.eng
+        torch = _torch()
+        with torch.cuda.device(eng.device):
+            _lib.check(eng.lib.b200kf_select_greedy_chunk(
+                eng._h, self.done, e_end, _ptr(self.types), _ptr(self.times), self.I, _ptr(self.periods), _ptr(self.t_prev),
+                _ptr(self.P0), _ptr(self.carry), _ptr(self.P), max(1, self.max_sel), _ptr(self.sel), _ptr(self.n_sel),
+                _ptr(self.recs), _MODES["symmetric"], eng._stream(stream)))
+        self.done = e_end
+        return self
 
 
 def cov_update(Sigma, rows, H, R, device=None, stream=None):

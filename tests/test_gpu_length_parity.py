@@ -206,6 +206,33 @@ def test_config2_full_length_time_chunked_sweep_vs_reference(config2, use_gains)
             assert a[3] == int(g[f"r{f}_s{s}_n_states"]) - 1
 
 
+def test_config2_full_length_pipelined_sweep_equals_chunked_sweep(config2):
+    """The pipelined sweep (selection walked in chunks one chunk ahead of the filters, on its own stream) against
+    the chunked sweep with precomputed gains: same selections, final states, covariances and aggregates."""
+    import torch
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    g, ev, ps, noise = config2
+    rates = [int(r) for r in g["rates"]] + [50]
+    eng = Engine("CA15")
+    data = np.stack([ps.data + z for z in noise], axis=2)
+    pay = torch.from_numpy(np.ascontiguousarray(data[1:])).to(eng.device)
+    x0 = np.zeros((data.shape[2], 15))
+    x0[:, :3] = data[0, :3, :].T
+    P0 = eng.spec.default_P0()
+    args = (ps.types[1:], ps.times[1:], rates, x0, P0, float(ps.times[0]), lambda e0, e1: pay[e0:e1], 60007)
+    ref = eng.scheduled_sweep_chunked(*args, use_gains=True)
+    out = eng.scheduled_sweep_pipelined(*args)
+    for f in rates:
+        np.testing.assert_array_equal(out[f]["sel"].cpu().numpy(), np.asarray(ref[f]["sel"]))
+        assert bool((out[f]["x"] == ref[f]["x"]).all())
+        assert bool((out[f]["P"] == ref[f]["P"]).all())
+        a, b = out[f]["agg"].cpu().numpy(), ref[f]["agg"].cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+    for f in (10, 120):
+        np.testing.assert_array_equal(out[f]["sel"].cpu().numpy().astype(np.int64) + 1,
+                                      np.cumsum(g[f"r{f}_sel_delta"].astype(np.int64)))
+
+
 @pytest.mark.parametrize("rate,seed", [(10, 1), (120, 2)])
 def test_config2_full_length_reference_facing_method(config2, rate, seed):
     from oracle.make_golden import arrays_to_events

@@ -236,6 +236,24 @@ def test_config4_full_size_properties(monkeypatch):
     assert lo_thr["argmin_sum_index"] == bt["argmin_sum_index"]  # the threshold does not enter the argmin
 
 
+def _check_gain_records(ra, rb, rtol):
+    """Gain records [n, bytes] (uint8) of two producers: (dt, det[4], ldet[4], (type, pad), gains...).  dt and the
+    integer slot bit for bit; determinants and gains to `rtol` (0 = bit for bit).  An IMU event writes every gain
+    slot, a GPS event only the first block's n x 1 column -- unwritten slots are not compared."""
+    fa = np.ascontiguousarray(ra).view(np.float64)
+    fb = np.ascontiguousarray(rb).view(np.float64)
+    ia = np.ascontiguousarray(ra).view(np.int32).reshape(len(ra), -1)
+    ib = np.ascontiguousarray(rb).view(np.int32).reshape(len(rb), -1)
+    np.testing.assert_array_equal(ia[:, 18], ib[:, 18])  # event type (byte offset 72)
+    np.testing.assert_array_equal(fa[:, 0], fb[:, 0])    # dt
+    imu = ia[:, 18] == 1
+    for sl, rows in ((slice(1, 5), slice(None)), (slice(10, None), imu), (slice(10, 13), ~imu)):
+        if rtol == 0:
+            np.testing.assert_array_equal(fa[rows, sl], fb[rows, sl])
+        else:
+            np.testing.assert_allclose(fa[rows, sl], fb[rows, sl], rtol=rtol, atol=0)
+
+
 @pytest.mark.parametrize("name", ["CA15", "CA8"])
 def test_warp_cooperative_selection_is_bit_identical_to_the_thread_walk(name, monkeypatch):
     """b200kf_select_greedy with few instances runs one WARP per instance (events loaded 32 at a time, window
@@ -264,18 +282,39 @@ def test_warp_cooperative_selection_is_bit_identical_to_the_thread_walk(name, mo
             np.testing.assert_array_equal(sa, sb)
         assert bool((a[1] == b[1]).all())
         if mode == "symmetric":
-            # records: (dt, det[4], ldet[4], (type, pad), gains...) -- the integer slot bit for bit, the float64
-            # fields to rounding (the two kernels may contract the determinant's FMAs differently)
-            ra = a[2].cpu().numpy().view(np.float64)
-            rb = b[2].cpu().numpy().view(np.float64)
-            for i, sa in enumerate(a[0]):
-                xa_, xb_ = ra[i, :len(sa)], rb[i, :len(sa)]
-                np.testing.assert_array_equal(xa_[:, 9].view(np.int64), xb_[:, 9].view(np.int64))
-                fl = [c for c in range(xa_.shape[1]) if c != 9]
-                np.testing.assert_allclose(xa_[:, fl], xb_[:, fl], rtol=1e-13, atol=0)
-                np.testing.assert_array_equal(xa_[:, 0], xb_[:, 0])  # dt
+            ra, rb = a[2].cpu().numpy(), b[2].cpu().numpy()
+            for i, sa in enumerate(a[0]):  # (the two kernels may contract the determinant's FMAs differently)
+                _check_gain_records(ra[i, :len(sa)], rb[i, :len(sa)], rtol=1e-13)
     # and the selections are the oracle's (greedy_schedule over the window queues, kf_workers.py:877-910)
     if name == "CA15":
         st, _, _ = ko.run_scheduled(ko.get_model(name), ev, 55.0, 0, len(ev))
         sel_ref = np.searchsorted(ps.times, np.array([s[0] for s in st[1:]])) - 1
         np.testing.assert_array_equal(outs[("1", "symmetric")][0][2], sel_ref)
+
+
+def test_chunked_selection_equals_one_walk_bit_for_bit():
+    """b200kf_select_greedy_chunk: the greedy walk cut at arbitrary event indices (mid-queue, mid-batch, empty and
+    one-event chunks) gives the selections, covariances and gain records of ONE walk over the stream."""
+    import torch
+    from sensorfusion_kalmanfilter_b200 import streams, synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    ev = synth.make_indexed_sensor_data(6003, seed=12)[3:]
+    ps = streams.PackedStream.from_events(ev)
+    types, times = ps.types[1:], ps.times[1:]
+    E = len(types)
+    periods = [1.0 / f for f in (3.0, 10.0, 55.0, 120.0, 1000.0)]
+    eng = Engine("CA15")
+    P0 = np.repeat(eng.spec.default_P0()[None], len(periods), axis=0)
+    sels, P_fin, recs = eng.select_greedy(types, times, periods, [float(ps.times[0])] * len(periods), P0,
+                                          mode="symmetric", want_gains=True)
+    st = eng.select_state(types, times, periods, float(ps.times[0]), P0)
+    cuts = [1, 2, 33, 64, 64, 1000, 1001, 2500, 4097, E - 1, E]
+    for c in cuts:
+        st.advance(c)
+    torch.cuda.synchronize()
+    ns = st.n_sel.cpu().numpy()
+    for i, sa in enumerate(sels):
+        assert ns[i] == len(sa)
+        np.testing.assert_array_equal(st.sel[i, :len(sa)].cpu().numpy(), sa)
+        _check_gain_records(st.recs[i, :len(sa)].cpu().numpy(), recs[i, :len(sa)].cpu().numpy(), rtol=0)
+    assert bool((st.P == P_fin).all())
