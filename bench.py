@@ -389,6 +389,54 @@ def leg_search_large(torch, dist, a, world, dev, barrier, fma_peak_distinct, Ll)
     return out
 
 
+def leg_config3_one_gpu(torch, a, hbm_peak):
+    """BASELINE configs[2] WHOLE on one GPU: 2^20 CV6 filters x 10 000 steps = 1.05e10 filter-steps.  Its 252 GB of
+    payload exceed one GPU's HBM, so the job runs as 8 groups of 131 072 filters x 4 time chunks of 2 500 steps; each
+    (group, chunk) payload (7.9 GB) is generated on the device right before its launch (b200kf_fill_payload, its own
+    seed) and state + aggregates are carried from chunk to chunk.  The 32 filter launches are timed with CUDA events
+    and summed; the generation (not part of the path) is reported beside them."""
+    from sensorfusion_kalmanfilter_b200 import synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload
+    G, Ng, C, Tc = 8, 131072, 4, 2500
+    os.environ["B200KF_SHARED"] = "0"
+    eng = Engine("CV6")
+    os.environ.pop("B200KF_SHARED", None)
+    sp = eng.spec
+    types, dts = synth.gps_imu_schedule(C * Tc)
+    types_d = torch.from_numpy(types).to(eng.device)
+    dts_d = torch.from_numpy(dts).to(eng.device)
+    scale = 1.0 + (np.arange(Ng) % 1024) / 1024.0
+    P0 = torch.from_numpy(sp.default_P0()[None] * scale[:, None, None]).to(device=eng.device, dtype=eng.real).contiguous()
+    pairs = []
+    check = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for g in range(G):
+        x = torch.zeros((Ng, sp.n), dtype=eng.real, device=eng.device)
+        P = P0.clone()
+        agg = torch.zeros((Ng, 4), dtype=torch.float64, device=eng.device)
+        for c in range(C):
+            sl = slice(c * Tc, (c + 1) * Tc)
+            pay = fill_payload(eng, types_d[sl], Ng, seed=1000 * g + c)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.run_batch(types_d[sl], dts_d[sl], pay, x, P, agg=agg if c else None, inplace=True)
+            e1.record()
+            pairs.append((e0, e1))
+            del pay
+        check += float(agg[:, 1].mean().item())
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = sum(p0.elapsed_time(p1) for p0, p1 in pairs)
+    steps = float(G) * Ng * C * Tc
+    gbs = steps * sp.d * 8 / (ms * 1e-3) / 1e9
+    return {"value": steps / (ms * 1e-3), "unit": UNIT, "filters": G * Ng, "steps_per_filter": C * Tc, "filter_steps": steps,
+            "filter_launches_ms": ms, "wall_s_incl_payload_generation": wall, "launches": len(pairs),
+            "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "check_mean_sum_logdet": check / G,
+            "workload": f"CV6 2^20 filters x {C * Tc} steps on ONE GPU: {G} filter groups x {C} time chunks, payload regenerated "
+                        "per (group, chunk)"}
+
+
 def leg_config5(torch, a, hbm_peak):
     """BASELINE configs[4]: BIAS9, 262 144 filters x 50 000 steps, FP64 and FP32, every filter its own covariance.
     314 GB (f64) of payload does not fit: ONE 10 000-step chunk is resident (63 GB / 31 GB, larger than L2) and is
@@ -544,13 +592,14 @@ def leg_config2(torch, a, hbm_peak):
     # ---- pipelined: the selection walks one chunk ahead of the filters on its own stream; the filters apply its
     # gain records as pure streams.  Payload: TWO resident 25 200-event chunks (3.7 GB each, per-seed noise) used
     # alternately -- nothing is generated inside the timed job, so one pair of CUDA events brackets all of it.
-    bufs = [chunk(0, 25200), chunk(25200, 50400)]
+    bufs = [chunk(0, 25200 + 512), chunk(25200, 50400 + 512)]  # (+ the look-back rows of a chunk's open window)
     torch.cuda.synchronize()
     cnt = {"c": 0}
 
     def recycled(e0, e1):
         b = bufs[cnt["c"] % 2]
         cnt["c"] += 1
+        assert e1 - e0 <= b.shape[0]
         return b[:e1 - e0]
 
     def run_pipe():
@@ -814,6 +863,7 @@ def run_gpu_arm(a):
         # the big legs need the memory of the headline buffers
         del payload, x, P
         torch.cuda.empty_cache()
+        config3_full = leg_config3_one_gpu(torch, a, hbm_peak) if not a.no_configs else None
         ref_models = leg_reference_models(torch, a, hbm_peak) if not a.no_configs else None
         config5 = leg_config5(torch, a, hbm_peak) if not a.no_configs else None
         config2 = leg_config2(torch, a, hbm_peak) if not a.no_configs else None
@@ -854,7 +904,7 @@ def run_gpu_arm(a):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_pass * n_pass,
                 "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large,
                 "search_2p32": search_huge, "product_search": products,
-                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "reference_models": ref_models,
+                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "reference_models": ref_models, "config3_full_one_gpu": config3_full,
                 "config5": config5, "config2": config2}
     if world > 1:
         dist.barrier()

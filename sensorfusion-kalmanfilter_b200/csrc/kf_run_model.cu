@@ -114,7 +114,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
         if constexpr (FULL) {
           if (p.gate_enabled) {  // kf_workers.py:1023-1025
             const double dpre = filter_det(flt, ok);
-            do_update = do_update && (log(dpre) > gate);
+            do_update = do_update && (fast_log_pos(dpre) > gate);
           }
         }
         double det;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
           }
           if (p.logdet != nullptr)
             __stcs(static_cast<real*>(p.logdet) + static_cast<long long>(k) * N + f,
-                   static_cast<real>(log(det)));
+                   static_cast<real>(fast_log_pos(det)));
           if (p.used != nullptr)
             p.used[static_cast<long long>(k) * N + f] = do_update ? 1 : 0;
         }
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
         else flt.predict(dt, p.mc);
         bool do_update = (ty != EV_PREDICT_ONLY);
         if constexpr (FULL) {
-          if (p.gate_enabled) do_update = do_update && (log(flt.det(ok)) > gate);  // :1023-1025
+          if (p.gate_enabled) do_update = do_update && (fast_log_pos(flt.det(ok)) > gate);  // :1023-1025
         }
         double det;
         if constexpr (Flt::rec_api) det = do_update ? flt.update(rec, ty, u, ok) : flt.det(ok);
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
             constexpr int g = G;
             if (g < out_nc) o[g * kTmaThreads] = v;
           });
-          if (out_rows > out_nc) o[out_nc * kTmaThreads] = static_cast<real>(log(det));
+          if (out_rows > out_nc) o[out_nc * kTmaThreads] = static_cast<real>(fast_log_pos(det));
         } else if constexpr (FULL) {
           // running output pointers: no reload of the launch parameters and no 64-bit multiply per step
           if (tr_run != nullptr) {
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
             tr_run += static_cast<long long>(out_nc) * N;
           }
           if (ld_run != nullptr) {
-            __stcs(ld_run, static_cast<real>(log(det)));
+            __stcs(ld_run, static_cast<real>(fast_log_pos(det)));
             ld_run += N;
           }
           if (used_run != nullptr) {
@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(F + 64, F == 224 ? 2 : 1) kf_run_shared_kernel
           acc.add(detM);
           rec.logdet = 0.0;
           if constexpr (FULL) {
-            if (p.logdet != nullptr) rec.logdet = log(detM);
+            if (p.logdet != nullptr) rec.logdet = fast_log_pos(detM);
           }
           if constexpr (sizeof(real) == 8) {
             gain_buf[s * kChunk + cc] = rec;
@@ -1214,7 +1214,7 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
               ok = ok && (dk < INFINITY);
               rec->det[K] = dk;
               if constexpr (FULL) {
-                if (p.logdet != nullptr) rec->ldet[K] = log(dk);
+                if (p.logdet != nullptr) rec->ldet[K] = fast_log_pos(dk);
               }
               det *= dk;
             });
@@ -1344,7 +1344,7 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
                   double dp = 1.0;
 #pragma unroll
                   for (int k2 = 0; k2 < NB; ++k2) dp *= rec->det[k2];
-                  ld = log(dp);
+                  ld = fast_log_pos(dp);
                 } else {
 #pragma unroll
                   for (int k2 = 0; k2 < NB; ++k2) ld += rec->ldet[k2];

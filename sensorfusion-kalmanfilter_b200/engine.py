@@ -385,8 +385,10 @@ class Engine:
         """scheduled_sweep_chunked with the selection OFF the critical path: the greedy selection is itself walked
         in time chunks (b200kf_select_greedy_chunk, one warp per rate, on its own stream) one chunk AHEAD of the
         filters, which consume its gain records as pure streams (b200kf_run_gains).  Per chunk the host waits only
-        for that chunk's twelve selection counts (a 96-byte pinned copy).  The reference's P0 shape (axis-symmetric,
-        kf_workers.py:851) is assumed, as for use_gains.  Returns {rate: dict(sel (device), n_sel, x, P, agg)}."""
+        for that chunk's twelve selection counts (a 96-byte pinned copy).  `payload_chunk(e_lo, e1)` is asked for
+        ranges that reach back one window period before the chunk: an event queued before the boundary may be selected
+        after it.  The reference's P0 shape (axis-symmetric, kf_workers.py:851) is assumed, as for use_gains.
+        Returns {rate: dict(sel (device), n_sel, x, P, agg)}."""
         return _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events)
 
     def select_state(self, types, times, periods, t_prev, P0, *, max_sel=None, want_gains=True):
@@ -638,6 +640,7 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
             evs[c].record(sel_stream)
 
     enqueue_selection(0)
+    max_period = 1.0 / min(rates)
     xs = [x0_d.clone() for _ in rates]
     aggs = [None] * R
     done = [0] * R
@@ -646,7 +649,10 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
         if c + 1 < nch:
             enqueue_selection(c + 1)  # runs while this chunk's filters stream
         e0, e1 = bounds[c], bounds[c + 1]
-        pay_d = payload_chunk(e0, e1)
+        # A window that closes in this chunk may select an event queued before e0 (the open queue at the chunk
+        # boundary); queue entries are younger than one period, so the payload rows reach back that far
+        e_lo = max(0, int(np.searchsorted(times, times[e0 - 1] - max_period, side="left")) - 1) if e0 > 0 else 0
+        pay_d = payload_chunk(e_lo, e1)
         evs[c].synchronize()  # this chunk's selection counts are on the host
         cur.wait_event(evs[c])
         for i in order:
@@ -656,7 +662,7 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
             stream = spool[i]
             stream.wait_stream(cur)
             with torch.cuda.stream(stream):
-                rows = st.sel[i, j0:j1] - e0
+                rows = st.sel[i, j0:j1] - e_lo
                 r = engines[i].run_gains(st.recs[i, j0:j1], pay_d, xs[i], agg=aggs[i], stream=stream, step_rows=rows,
                                          inplace=True)
             xs[i], aggs[i] = r["x"], r["agg"]

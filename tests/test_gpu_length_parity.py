@@ -221,7 +221,13 @@ def test_config2_full_length_pipelined_sweep_equals_chunked_sweep(config2):
     P0 = eng.spec.default_P0()
     args = (ps.types[1:], ps.times[1:], rates, x0, P0, float(ps.times[0]), lambda e0, e1: pay[e0:e1], 60007)
     ref = eng.scheduled_sweep_chunked(*args, use_gains=True)
-    out = eng.scheduled_sweep_pipelined(*args)
+
+    def guarded_chunk(e0, e1):  # a copy with NaN rows around it: a read outside [e0, e1) poisons the state
+        buf = torch.full((e1 - e0 + 8, 9, pay.shape[2]), float("nan"), dtype=pay.dtype, device=pay.device)
+        buf[4:-4] = pay[e0:e1]
+        return buf[4:-4]
+
+    out = eng.scheduled_sweep_pipelined(*args[:6], guarded_chunk, 60007)
     for f in rates:
         np.testing.assert_array_equal(out[f]["sel"].cpu().numpy(), np.asarray(ref[f]["sel"]))
         assert bool((out[f]["x"] == ref[f]["x"]).all())
