@@ -30,7 +30,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-lineinfo", "-Xcompiler", "-fPIC",
           "-Xptxas", "-v"] + ARCH + EXTRA
 MODELS = (0, 1, 2, 3)
-HEADERS = ["kf_core.cuh", "kf_internal.h", os.path.join(ROOT, "include", "b200kf.h")]
+HEADERS = ["kf_core.cuh", "kf_axis.cuh", "kf_internal.h", os.path.join(ROOT, "include", "b200kf.h")]
 
 
 def _units():

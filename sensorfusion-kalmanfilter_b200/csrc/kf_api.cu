@@ -557,6 +557,8 @@ int b200kf_model_create(const b200kf_model_desc* desc, b200kf_model** out) {
   if (const char* s = getenv("B200KF_TMA")) m->use_tma = atoi(s) != 0;
   m->use_select_warp = 1;
   if (const char* s = getenv("B200KF_SELECT_WARP")) m->use_select_warp = atoi(s) != 0;
+  m->use_axis_dense = 1;
+  if (const char* s = getenv("B200KF_AXIS_DENSE")) m->use_axis_dense = atoi(s) != 0;
   m->use_ca_ring = 1;
   if (const char* s = getenv("B200KF_CA_RING")) m->use_ca_ring = atoi(s) != 0;
   m->use_bulk_out = 1;

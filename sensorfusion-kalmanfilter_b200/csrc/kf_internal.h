@@ -40,6 +40,7 @@ struct b200kf_model {
   int use_select_warp;  // 1: warp-per-instance greedy selection for few instances (env B200KF_SELECT_WARP=0: thread per instance)
   int use_ca_ring;  // 1: per-filter ring kernel for the constant-acceleration models CA15 / CA8 (env B200KF_CA_RING=0: LDG kernels)
   int use_bulk_out;  // 1: per-step outputs of the ring kernels leave through the shared-memory output ring + bulk stores (env B200KF_BULK_OUT=0: per-thread stores)
+  int use_axis_dense;  // 1: dense covariance of the three-axis model (CA15) on three lanes per filter (env B200KF_AXIS_DENSE=0: thread per filter)
   int use_tma;  // 1: TMA-staged kernel for the closed-form filters (env B200KF_TMA=0 disables)
 };
 

@@ -8,6 +8,7 @@
 #include <tuple>
 
 #include "kf_internal.h"
+#include "kf_axis.cuh"
 
 #ifndef B200KF_INST_MODEL
 #error "compile with -DB200KF_INST_MODEL=<model id>"
@@ -189,6 +190,171 @@ __global__ void __launch_bounds__((LaunchCfg<MODEL, VAR, real>::max_threads),
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Dense covariance of a three-axis model, three lanes per filter (kf_axis.cuh): the arbitrary-initial_pt
+// path of the 15-state filter (kf_workers.py:642-645) without local memory.  Ten filters per warp; lanes 30
+// and 31 run a clamped copy of the last filter and store nothing.  Same interface, outputs and aggregate
+// conventions as kf_run_kernel<MODEL, VAR_DENSE>.
+// ------------------------------------------------------------------------------------------
+constexpr int kAxisThreads = 128;
+constexpr int kAxisFiltersPerBlock = (kAxisThreads / 32) * 10;
+
+template <int MODEL, typename real, bool FULL, bool GATED>
+__global__ void __launch_bounds__(kAxisThreads, 2) kf_run_axis_kernel(const RunParams p) {
+  using AT = typename AxisTraits<MODEL>::Table;
+  using MT = ModelTraits<MODEL, true, real>;
+  static_assert(!MT::imu_control, "axis kernel: measurement-type IMU events only");
+  constexpr int n = MT::n;
+  constexpr int D = MT::d;
+  constexpr int NA = AT::n;
+  constexpr int NC = AT::ncols();
+  if (!mode_selected(p.dense_flag, VAR_DENSE)) return;
+  const int lane = threadIdx.x & 31;
+  const long long warp = blockIdx.x * static_cast<long long>(kAxisThreads / 32) + (threadIdx.x >> 5);
+  const long long N = p.n_filters;
+  const int T = p.n_steps;
+  long long f = warp * 10 + lane / 3;
+  const bool active = lane < 30 && f < N;
+  if (warp * 10 >= N) return;  // whole warp beyond the batch
+  if (f >= N) f = N - 1;
+
+  AxisDense<AT, real> flt;
+  flt.init_lane(lane, p.mc);
+  const int a = flt.a;
+  const bool lead = active && a == 0;
+  flt.load(static_cast<const real*>(p.x) + f * n, static_cast<const real*>(p.P) + f * (n * n), n);
+
+  // prod of the measured variances of an event (all three axes): det P+ = det P- * rprod / prod det S
+  double rprod_imu = 1.0, rprod_gps = 1.0;
+  static_for<0, NA>([&](auto I) {
+    constexpr int g = AT::gidx0(I);
+    if constexpr (AT::zk(I) != ZK_NONE) rprod_imu *= p.mc.r_imu[g] * p.mc.r_imu[g + 1] * p.mc.r_imu[g + 2];
+    if constexpr (AT::gps0(I) >= 0) {
+      constexpr int c = AT::gps0(I);
+      rprod_gps *= p.mc.r_gps[c] * p.mc.r_gps[c + 1] * p.mc.r_gps[c + 2];
+    }
+  });
+
+  const double gate = (GATED && p.gate_thresholds != nullptr) ? p.gate_thresholds[f] : p.gate_threshold;
+  double acc_mant = 1.0;
+  long long acc_max = 0;
+  int acc_expo = 0;
+  bool ok = true;
+  double det = 1.0;
+
+  const real* pay = static_cast<const real*>(p.payload) + f;
+  const long long step_stride = static_cast<long long>(D) * N;
+  real unext[NC];
+  if (T > 0) {
+    const real* src = pay + step_row(p.step_rows, 0) * step_stride;
+    static_for<0, NC>([&](auto S) { unext[S] = __ldcs(src + static_cast<long long>(AT::col(S) + a) * N); });
+  }
+
+  for (int k = 0; k < T; ++k) {
+    real u[NC];
+    static_for<0, NC>([&](auto S) { u[S] = unext[S]; });
+    if (k + 1 < T) {
+      const real* src = pay + step_row(p.step_rows, k + 1) * step_stride;
+      static_for<0, NC>([&](auto S) { unext[S] = __ldcs(src + static_cast<long long>(AT::col(S) + a) * N); });
+    }
+    const int ty = __ldg(p.types + k);
+    const real dt = static_cast<real>(__ldg(p.dts + k));
+
+    flt.predict(dt, real(p.mc.c2) * (dt * dt));
+    const double dpre = flt.det(ok);
+    bool do_update = (ty != EV_PREDICT_ONLY);
+    bool mixed = false;
+    if constexpr (GATED) {
+      {  // kf_workers.py:1023-1025; the lanes of a filter follow its first lane's decision
+        const int mine = (do_update && (fast_log_pos(dpre) > gate)) ? 1 : 0;
+        do_update = __shfl_sync(0xffffffffu, mine, (lane / 3) * 3) != 0;
+        const unsigned upd = __ballot_sync(0xffffffffu, do_update);
+        mixed = upd != 0u && upd != 0xffffffffu;
+      }
+    }
+    det = dpre;
+    // The stages shuffle across the whole warp, so the warp updates as one: when the gate lets only some of its
+    // filters update, all run the update and the others restore their predicted state afterwards.
+    if (do_update || mixed) {
+      AxisDense<AT, real> keep;
+      if constexpr (GATED) {
+        if (mixed) keep = flt;
+      }
+      if (ty == EV_GPS) {
+        real z[NA];
+        static_for<0, NA>([&](auto I) {
+          if constexpr (AT::gps0(I) >= 0) z[I] = u[AT::slot(I, true)];
+          else z[I] = real(0);
+        });
+        const double sprod = flt.template update<true>(z);
+        det = dpre * rprod_gps / sprod;
+      } else if (ty == EV_IMU) {
+        real z[NA];
+        flt.build_imu_z(dt, u, z);
+        const double sprod = flt.template update<false>(z);
+        det = dpre * rprod_imu / sprod;
+      }
+      if constexpr (GATED) {
+        if (mixed && !do_update) {
+          flt = keep;
+          det = dpre;
+        }
+      }
+    }
+    ok = ok && (det > 0.0);
+    {
+      acc_max = max(acc_max, __double_as_longlong(det));
+      const double m = acc_mant * det;
+      const int hi = __double2hiint(m);
+      const int e = ((hi >> 20) & 0x7ff) - 1023;
+      acc_expo += e;
+      acc_mant = __hiloint2double(hi - (e << 20), __double2loint(m));
+    }
+
+    if constexpr (FULL) {
+      if (p.traj != nullptr && active) {
+        real* tr = static_cast<real*>(p.traj) + (static_cast<long long>(k) * p.traj_ncomp) * N + f;
+        const int nc = p.traj_ncomp;
+        static_for<0, NA>([&](auto I) {
+          const int g = AT::gidx0(I) + a;
+          if (g < nc) __stcs(tr + static_cast<long long>(g) * N, flt.x[I]);
+        });
+      }
+      if (p.ptraj != nullptr && active) {  // sf_KF_covariance.append(Pt.copy()), kf_workers.py:822
+        real* pt = static_cast<real*>(p.ptraj) + (static_cast<long long>(k) * (n * n)) * N + f;
+        flt.for_each_cov([&](int gi, int gj, real v) { pt[static_cast<long long>(gi * n + gj) * N] = v; });
+      }
+      if (p.logdet != nullptr && lead)
+        __stcs(static_cast<real*>(p.logdet) + static_cast<long long>(k) * N + f, static_cast<real>(fast_log_pos(det)));
+      if (p.used != nullptr && lead) p.used[static_cast<long long>(k) * N + f] = do_update ? 1 : 0;
+    }
+  }
+
+  if (active) flt.store(static_cast<real*>(p.x) + f * n, static_cast<real*>(p.P) + f * (n * n), n);
+  // status: a non-positive pivot seen by any lane of the filter
+  const unsigned bad_lanes = __ballot_sync(0xffffffffu, !ok);
+  if (p.agg != nullptr && lead) {
+    double* ag = p.agg + f * 4;
+    double mx = (T > 0) ? log(__longlong_as_double(acc_max)) : -INFINITY;
+    double sm = log(acc_mant) + static_cast<double>(acc_expo) * 0.6931471805599453094;
+    double cnt = static_cast<double>(T);
+    if (p.agg_continue) {
+      mx = fmax(mx, ag[0]);
+      sm += ag[1];
+      cnt += ag[3];
+    }
+    ag[0] = mx;
+    ag[1] = sm;
+    if (T > 0) ag[2] = log(det);
+    else if (!p.agg_continue) ag[2] = 0.0;
+    ag[3] = cnt;
+  }
+  if (p.status != nullptr && lead) {
+    const int bad = (bad_lanes & flt.gmask) != 0 ? 1 : 0;
+    p.status[f] = p.agg_continue ? (p.status[f] | bad) : bad;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // TMA-staged variant for the closed-form filters (aggregate mode): one persistent 896-thread CTA
@@ -1738,6 +1904,18 @@ __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filt
 template <int MODEL, int VAR, typename real>
 static cudaError_t launch_variant(const b200kf_model* m, const RunParams& p, bool full,
                                   cudaStream_t st) {
+  if constexpr (VAR == VAR_DENSE && AxisTraits<MODEL>::eligible) {
+    if (m->use_axis_dense != 0) {
+      const long long blocks = (p.n_filters + kAxisFiltersPerBlock - 1) / kAxisFiltersPerBlock;
+      if (p.gate_enabled)
+        kf_run_axis_kernel<MODEL, real, true, true><<<static_cast<unsigned>(blocks), kAxisThreads, 0, st>>>(p);
+      else if (full)
+        kf_run_axis_kernel<MODEL, real, true, false><<<static_cast<unsigned>(blocks), kAxisThreads, 0, st>>>(p);
+      else
+        kf_run_axis_kernel<MODEL, real, false, false><<<static_cast<unsigned>(blocks), kAxisThreads, 0, st>>>(p);
+      return cudaGetLastError();
+    }
+  }
   using LC = LaunchCfg<MODEL, VAR, real>;
   const int tpb = LC::fast ? LC::max_threads : (m->tpb <= LC::max_threads ? m->tpb : LC::max_threads);
   const long long blocks = (p.n_filters + tpb - 1) / tpb;
