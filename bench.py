@@ -478,7 +478,65 @@ def leg_config5(torch, a, hbm_peak):
     return out
 
 
-def leg_reference_models(torch, a, hbm_peak):
+def _fp64_view(prof, key, rate, fma_peak, fma_peak_distinct, src):
+    """FP64-pipe view of a leg: executed FP64 thread-instructions per filter-step (ncu, profiles/) x measured
+    filter-steps/s against the measured FMA peaks of this run."""
+    if not prof or key not in prof or not fma_peak_distinct:
+        return None
+    q = prof[key]
+    inst = q["dfma_per_step"] + q["dmul_per_step"] + q["dadd_per_step"]
+    flop = 2.0 * q["dfma_per_step"] + q["dmul_per_step"] + q["dadd_per_step"]
+    ach = flop * rate / 1e12
+    # a DMUL / DADD occupies the pipe like a DFMA: the pipe's issue rate is (FMA peak) / 2 instructions per second
+    return {"bound": "fp64", "achieved": ach, "unit": "TFLOP/s", "peak": fma_peak_distinct,
+            "frac": ach / fma_peak_distinct, "frac_of_plain_fma_peak": (ach / fma_peak) if fma_peak else None,
+            "pipe_issue_frac": inst * rate / (fma_peak_distinct * 1e12 / 2.0),
+            "pipe_issue_frac_of_plain_fma_peak": (inst * rate / (fma_peak * 1e12 / 2.0)) if fma_peak else None,
+            "fp64_thread_inst_per_filter_step": inst, "flop_per_filter_step": flop,
+            "fp64_thread_inst_per_s": inst * rate, "kernel": q.get("kernel"),
+            "peak_source": "b200kf_probe_fma_peak (distinct operands; plain = loop-invariant operands), measured in this run",
+            "counts_from": src}
+
+
+def leg_dense(torch, a, fma_peak, fma_peak_distinct):
+    """The 15-state filter with an ARBITRARY dense initial_pt (kf_workers.py:642-645: every state coupled): three
+    lanes per filter, the covariance as a 3 x 3 grid of per-axis 5 x 5 blocks (csrc/kf_axis.cuh).  ~4 900 FP64
+    instructions per filter-step against 72 B of payload: FP64-pipe-bound by construction."""
+    from sensorfusion_kalmanfilter_b200 import synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload
+    N, T = 131072, 200
+    eng = Engine("CA15")
+    types, dts = synth.gps_imu_schedule(T)
+    types_d, dts_d = torch.from_numpy(types).to(eng.device), torch.from_numpy(dts).to(eng.device)
+    pay = fill_payload(eng, types_d, N, seed=5)
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(1024, 15, 15))
+    P0 = np.tile(A @ np.swapaxes(A, 1, 2) + 5.0 * np.eye(15), (N // 1024, 1, 1))
+    P0_d = torch.from_numpy(P0).to(eng.device)
+    x = torch.zeros((N, 15), dtype=torch.float64, device=eng.device)
+    P = P0_d.clone()
+
+    def one():
+        P.copy_(P0_d)  # every launch starts from the coupled P0 (the filter decorrelates it over time)
+        o = eng.run_batch(types_d, dts_d, pay, x, P, inplace=True)
+        del o
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    st = _stats(_timed_loop(one, 30, torch))
+    rate = N * T / (st["mean"] * 1e-3)
+    out = {"value": rate, "unit": UNIT, "ms": st["mean"], "ms_min": st["min"],
+           "workload": f"CA15 {N} filters x {T} steps, f64, dense coupled P0 per filter (A A^T + 5 I), mode auto -> "
+                       "kf_run_axis_kernel (three lanes per filter), aggregates only, 30 back-to-back launches "
+                       "(each incl. the 236 MB P0 restore copy)",
+           "roofline": _fp64_view(load_profile_json("r02j_dense_fp64.json"), "CA15_f64_dense_aggregate", rate, fma_peak,
+                                  fma_peak_distinct, "profiles/r02j_dense_fp64.json (ncu smsp__sass_thread_inst_executed_op_d*_pred_on)")}
+    del pay, x, P, P0_d, eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_reference_models(torch, a, hbm_peak, fma_peak=None, fma_peak_distinct=None):
     """The reference's OWN models with one covariance per filter: CA15 (kf_workers.py:493-614, 72 B of payload per
     step) and CA8 (hw5_2.py:219-304, 32 B), aggregate mode and trajectory mode (x[0:6] + log det per step, what
     run_kalman_filter_full returns), on the per-filter ring kernel in its constant-acceleration form."""
@@ -512,6 +570,10 @@ def leg_reference_models(torch, a, hbm_peak):
             res[label] = {"value": N * T / (st["mean"] * 1e-3), "unit": UNIT, "ms": st["mean"], "ms_min": st["min"],
                           "algorithmic_bytes_per_filter_step": bps, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
                           "frac_burst": float(N) * T * bps / (st["min"] * 1e-3) / 1e9 / hbm_peak}
+            fp = _fp64_view(load_profile_json("r02j_ca_ring_fp64.json"), f"{name}_f64_{label}", res[label]["value"], fma_peak,
+                            fma_peak_distinct, "profiles/r02j_ca_ring_fp64.json (ncu smsp__sass_thread_inst_executed_op_d*_pred_on)")
+            if fp:
+                res[label]["fp64"] = fp  # these loops sit on the FP64 pipe, not on HBM: the binding roofline
         out[name] = res
         del pay, x, P, eng
         torch.cuda.empty_cache()
@@ -864,7 +926,8 @@ def run_gpu_arm(a):
         del payload, x, P
         torch.cuda.empty_cache()
         config3_full = leg_config3_one_gpu(torch, a, hbm_peak) if not a.no_configs else None
-        ref_models = leg_reference_models(torch, a, hbm_peak) if not a.no_configs else None
+        ref_models = leg_reference_models(torch, a, hbm_peak, fma_peak, fma_peak_distinct) if not a.no_configs else None
+        dense_mode = leg_dense(torch, a, fma_peak, fma_peak_distinct) if not a.no_configs else None
         config5 = leg_config5(torch, a, hbm_peak) if not a.no_configs else None
         config2 = leg_config2(torch, a, hbm_peak) if not a.no_configs else None
 
@@ -904,7 +967,7 @@ def run_gpu_arm(a):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_pass * n_pass,
                 "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large,
                 "search_2p32": search_huge, "product_search": products,
-                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "reference_models": ref_models, "config3_full_one_gpu": config3_full,
+                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "reference_models": ref_models, "dense_ca15": dense_mode, "config3_full_one_gpu": config3_full,
                 "config5": config5, "config2": config2}
     if world > 1:
         dist.barrier()

@@ -1904,7 +1904,9 @@ __global__ void chain_compat_kernel(const real* __restrict__ P, long long n_filt
 template <int MODEL, int VAR, typename real>
 static cudaError_t launch_variant(const b200kf_model* m, const RunParams& p, bool full,
                                   cudaStream_t st) {
-  if constexpr (VAR == VAR_DENSE && AxisTraits<MODEL>::eligible) {
+  // float64 only: in float32 the 120 entries fit the thread-per-filter kernel's registers and it is the faster
+  // one (6.0e9 vs 4.8e9 steps/s, profiles/r02i_dense_ca15.jsonl)
+  if constexpr (VAR == VAR_DENSE && AxisTraits<MODEL>::eligible && sizeof(real) == 8) {
     if (m->use_axis_dense != 0) {
       const long long blocks = (p.n_filters + kAxisFiltersPerBlock - 1) / kAxisFiltersPerBlock;
       if (p.gate_enabled)

@@ -141,7 +141,7 @@ def test_axis_dense_chunks_predict_only_and_gate():
     assert flips <= 1
 
 
-def test_axis_dense_f32():
+def test_dense_f32_stays_on_the_thread_per_filter_kernel_and_matches():
     from sensorfusion_kalmanfilter_b200.engine import Engine
     N, T = 50, 200
     m, types, dts, payload, x0, P0 = dense_case(N, T, seed=8)
