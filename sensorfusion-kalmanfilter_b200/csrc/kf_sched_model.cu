@@ -521,6 +521,15 @@ __global__ void select_greedy_kernel(const SelectParams p) {
   }
 }
 
+// 16-byte global store under a predicate, without a branch (see emit_pending below)
+__device__ __forceinline__ void st_pred(bool pred, double2* addr, double a, double b) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p st.global.v2.f64 [%1], {%2, %3};\n\t}"
+      :
+      : "r"(static_cast<int>(pred)), "l"(addr), "d"(a), "d"(b)
+      : "memory");
+}
+
 // Warp-per-instance form of the same walk (few instances: one per sampling rate in the scheduled sweep).  The
 // thread-per-instance loop above spends ~0.25 us per EVENT on a dependent global load of (time, type) -- 590 000
 // events of the 2 808 s stream = 150 ms for every rate, however few windows it has.  Here the warp loads 32 events
@@ -528,7 +537,7 @@ __global__ void select_greedy_kernel(const SelectParams p) {
 // IMU entries with ballots, and keeps the candidates' times in registers (no load on the decision path); all
 // lanes run the covariance recursion redundantly (warp-uniform, no divergence), lane 0 writes the outputs.
 // Same arithmetic, same order: selections and covariances are bit-identical to the thread-per-instance kernel.
-template <int MODEL, int VAR>
+template <int MODEL, int VAR, bool RECS>
 __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectParams p) {
   using MT = VariantTraits<MODEL, VAR, double>;
   constexpr bool DENSE = (VAR == VAR_DENSE);
@@ -570,6 +579,62 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
     ty_imu = static_cast<int>(cr[6]);
     ns = p.n_sel[inst];
   }
+  // Deferred gain record (VAR_SYMMETRIC): the record of a selected event = K = P+ H^T R^-1 per block + det P+ of
+  // the covariance that window left in `flt`; it is written at the start of the NEXT window (or after the loop),
+  // branch-free -- every lane computes the values, both sensor formats, lane 0 stores twelve 16-byte pieces.
+  long long pend_idx = -1;
+  double pend_dt = 0.0;
+  int pend_ty = 0;
+  auto emit_pending = [&]() {
+    if constexpr (VAR == VAR_SYMMETRIC && RECS) {
+      using Rec = GainRecG<GainSlots<typename MT::Filter>::value>;
+      constexpr int NG = GainSlots<typename MT::Filter>::value;
+      static_assert(sizeof(Rec) % 16 == 0 && offsetof(Rec, g) == 80, "record layout");
+      const bool valid = pend_idx >= 0;
+      const bool is_gps = pend_ty == EV_GPS;
+      bool okd = true;
+      const double det = filter_det(flt, okd);
+      double g[NG + 1];
+#pragma unroll
+      for (int q = 0; q <= NG; ++q) g[q] = 0.0;
+      int o = 0, ocg = 0, oci = 0;
+      flt.each([&](const auto& b) {
+        using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+        constexpr int NMG = BT::template n_meas<true>();
+        constexpr int NMI = MT::imu_control ? 0 : BT::template n_meas<false>();
+        static_for<0, BT::kslots>([&](auto Sl) {
+          constexpr int sl = Sl;
+          double vg = 0.0, vi = 0.0;
+          if constexpr (NMG > 0 && sl < BT::n * NMG) {
+            constexpr int sc = BT::template meas_state<true>(sl % NMG);
+            vg = double(b.P[BT::pidx(sl / NMG, sc)]) * ir_gps[ocg + sl % NMG];
+          }
+          if constexpr (NMI > 0 && sl < BT::n * NMI) {
+            constexpr int sc = BT::template meas_state<false>(sl % NMI);
+            vi = double(b.P[BT::pidx(sl / NMI, sc)]) * ir_imu[oci + sl % NMI];
+          }
+          g[o + sl] = is_gps ? vg : vi;
+        });
+        o += BT::kslots;
+        ocg += NMG;
+        oci += NMI;
+      });
+      // EVERY lane issues the (identical) stores, predicated on `valid` instead of branching around them: a
+      // lane-0 branch would be a divergent region the warp executes on its own, after the chain; predicated
+      // warp-uniform stores are twelve more instructions of this basic block (same address, same value: the
+      // memory pipe merges them into one write)
+      double2* out = reinterpret_cast<double2*>(static_cast<Rec*>(p.gain_recs) + static_cast<long long>(inst) * p.max_sel +
+                                                (valid ? pend_idx : 0));
+      st_pred(valid, out + 0, pend_dt, det);  // dt, det[0]
+      st_pred(valid, out + 1, 1.0, 1.0);      // det[1..2]: unused blocks are 1
+      st_pred(valid, out + 2, 1.0, 0.0);      // det[3], ldet[0] (the consumer takes log(det) itself when asked)
+      st_pred(valid, out + 3, 0.0, 0.0);      // ldet[1..2]
+      st_pred(valid, out + 4, 0.0, __hiloint2double(0, pend_ty));  // ldet[3], (type, pad)
+#pragma unroll
+      for (int q = 0; q < (NG + 1) / 2; ++q) st_pred(valid, out + 5 + q, g[2 * q], g[2 * q + 1]);
+      pend_idx = -1;
+    }
+  };
   const long long eb = p.e_begin;
   double t_nx = (eb + lane < E) ? __ldg(p.times + eb + lane) : 0.0;
   int ty_nx = (eb + lane < E) ? __ldg(p.types + eb + lane) : -1;
@@ -650,38 +715,19 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
       const double ts = pick_gps ? t_gps : t_imu;
       const int tys = pick_gps ? static_cast<int>(EV_GPS) : ty_imu;
       const double dt = ts - prev;  // :914
+      // the gain record of the PREVIOUS window is cut from the covariance it left behind, here, in the same
+      // straight-line block as this window's decision and predict: its ~45 independent instructions fill the
+      // issue slots the serial chain leaves empty instead of extending the chain
+      if constexpr (VAR == VAR_SYMMETRIC) emit_pending();
       filter_predict<false>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
       filter_update<false, true>(flt, dt, p.mc, tys, static_cast<const double*>(nullptr));
       prev = ts;
       if (lane == 0 && ns < p.max_sel) sel[ns] = static_cast<int>(pick);
-      if constexpr (VAR == VAR_SYMMETRIC) {
-        if (p.gain_recs != nullptr && ns < p.max_sel) {
-          using Rec = GainRecG<GainSlots<typename MT::Filter>::value>;
-          Rec* rec = static_cast<Rec*>(p.gain_recs) + static_cast<long long>(inst) * p.max_sel + ns;
-          bool okd = true;
-          const double det = filter_det(flt, okd);
-          if (lane == 0) {
-            int o = 0, oc = 0;
-            flt.each([&](const auto& b) {
-              using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
-              if (tys == EV_GPS) {
-                b.template extract_gain<true>(ir_gps + oc, rec->g + o);
-                oc += BT::template n_meas<true>();
-              } else if (tys == EV_IMU) {
-                if constexpr (!MT::imu_control) b.template extract_gain<false>(ir_imu + oc, rec->g + o);
-                oc += BT::template n_meas<false>();
-              }
-              o += BT::kslots;
-            });
-            rec->dt = dt;
-            rec->type = tys;
-            rec->pad = 0;
-#pragma unroll
-            for (int q = 0; q < kMaxGainBlocks; ++q) {
-              rec->det[q] = (q == 0) ? det : 1.0;
-              rec->ldet[q] = 0.0;  // the consumer takes log(det) itself when a per-step log det is asked for
-            }
-          }
+      if constexpr (VAR == VAR_SYMMETRIC && RECS) {
+        if (ns < p.max_sel) {
+          pend_idx = ns;
+          pend_dt = dt;
+          pend_ty = tys;
         }
       }
       ns += 1;
@@ -689,6 +735,7 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
       pos = c + 1;
     }
   }
+  if constexpr (VAR == VAR_SYMMETRIC) emit_pending();  // the last window's record
   if (lane != 0) return;
   p.n_sel[inst] = ns;
   if (cr != nullptr) {  // the walk's state at the end of this chunk (the open queue carries over)
@@ -726,12 +773,14 @@ int launch_select_m<B200KF_INST_MODEL>(const b200kf_model* m, const SelectParams
     return set_error(B200KF_ERR_UNSUPPORTED, "chunked selection runs on the warp-per-instance kernel (<= 2048 instances)");
   if (p.lane_stride == 32 && m->use_select_warp) {  // few instances: a warp each, events loaded 32 at a time
     const unsigned wb = static_cast<unsigned>(p.n_inst);
-    if (sym_ok)
-      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC><<<wb, 32, 0, st>>>(p);
+    if (sym_ok && p.gain_recs != nullptr)
+      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC, true><<<wb, 32, 0, st>>>(p);
+    else if (sym_ok)
+      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_SYMMETRIC, false><<<wb, 32, 0, st>>>(p);
     else if (flags & (B200KF_RUN_FORCE_DECOUPLED | B200KF_RUN_FORCE_SYMMETRIC))
-      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_DECOUPLED><<<wb, 32, 0, st>>>(p);
+      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_DECOUPLED, false><<<wb, 32, 0, st>>>(p);
     else
-      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_DENSE><<<wb, 32, 0, st>>>(p);
+      select_greedy_warp_kernel<B200KF_INST_MODEL, VAR_DENSE, false><<<wb, 32, 0, st>>>(p);
     B200KF_CUDA_TRY(cudaGetLastError());
     return B200KF_OK;
   }
