@@ -7,6 +7,8 @@ from __future__ import annotations
 import ctypes
 from ctypes import POINTER, byref, c_double, c_int32, c_uint8, c_void_p
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -645,6 +647,10 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
     aggs = [None] * R
     done = [0] * R
     order = sorted(range(R), key=lambda j: -rates[j])  # the highest rate has the longest launches: first
+    if os.environ.get("B200KF_SWEEP_ORDER"):  # diagnostic: launch order of a chunk's rates, e.g. "50,60,...,120,40,...,10"
+        want = [float(v) for v in os.environ["B200KF_SWEEP_ORDER"].split(",")]
+        order = [rates.index(v) for v in want if v in rates]
+        order += [j for j in range(R) if j not in order]
     for c in range(nch):
         if c + 1 < nch:
             enqueue_selection(c + 1)  # runs while this chunk's filters stream

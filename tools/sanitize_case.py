@@ -38,3 +38,27 @@ b2, _ = e.score_products(q, (rng.random(E) < 0.8).astype(np.uint8), 5.0 + np.sor
                          rng.normal(0, 0.1, (E, 9)), rng.normal(0, 1, (E, 3)), np.zeros(15), e.spec.default_P0(),
                          want_per_combo=True)
 print("products", b2["index"])
+# round 2: the three-lanes-per-filter dense kernel (ragged filter counts, all outputs, mixed gate decisions),
+# the constant-acceleration ring kernels and the warp-per-instance selection with deferred gain records
+e = Engine("CA15")
+for N in (1, 13, 250):
+    T = 23
+    types, dts = synth.gps_imu_schedule(T, gps_every=5)
+    pay = synth.make_payload(9, types, N, seed=2, m_gps=3)
+    A = rng.normal(size=(N, 15, 15))
+    Pd = A @ np.swapaxes(A, 1, 2) + 5.0 * np.eye(15)
+    x0 = rng.normal(0, 1, (N, 15))
+    a = e.run_batch(types, dts, pay, x0, Pd)
+    b = e.run_batch(types, dts, pay, x0, Pd, traj_ncomp=15, want_logdet=True, want_ptraj=True, want_used=True)
+    thr = np.linspace(float(b["logdet"].min()), float(b["logdet"].max()), N)
+    c = e.run_batch(types, dts, pay, x0, Pd, gate_threshold=thr, want_used=True)
+    print("dense", N, float(a["agg"][:, 1].mean()), float(b["logdet"].mean()), float(c["used"].float().mean()))
+ev_t, ev_dt = synth.gps_imu_schedule(700, gps_every=9)
+times = 50.0 + np.cumsum(np.maximum(ev_dt, 1e-4))
+rates = [10.0, 45.0, 120.0]
+P0 = np.repeat(e.spec.default_P0()[None], len(rates), axis=0)
+sels, Pf, recs = e.select_greedy(ev_t, times, [1.0 / r for r in rates], [49.99] * len(rates), P0, want_gains=True)
+st = e.select_state(ev_t, times, [1.0 / r for r in rates], [49.99] * len(rates), P0)
+for e_end in (100, 333, 700):
+    st.advance(e_end)
+print("select", [len(s) for s in sels], float(Pf.sum()), None if recs is None else int(recs.shape[1]))
