@@ -69,6 +69,10 @@ extern "C" {
                                          filter of the launch carries the same P: one covariance /
                                          gain recursion per launch; falls back to FORCE_SYMMETRIC
                                          when the model / launch cannot use it */
+#define B200KF_RUN_SMALL_TILES 32u    /* b200kf_run_gains only: 128 filters per CTA where 224 would be used.  For launches
+                                         that share the GPU with others (one per sampling rate of a sweep,
+                                         kf_workers.py:826-957 run once per rate): a CTA streams ~40 GB/s (ring bytes over
+                                         memory latency), so the rate with the longest schedule needs more CTAs */
 
 typedef struct b200kf_model b200kf_model; /* opaque, library-owned */
 
@@ -314,7 +318,7 @@ int b200kf_select_greedy_chunk(const b200kf_model* model, int64_t e_begin, int64
  *   gain_records DEVICE [T] records (b200kf_select_greedy_gains)      payload DEVICE real [T, d, N]
  *   step_rows    DEVICE i32 [T] nullable: payload row of step k (as b200kf_run_batch_rows)
  *   x       DEVICE real [N, n] in/out        agg DEVICE f64 [N, 4] nullable (from the records' det P)
- *   traj / logdet / used / status as b200kf_run_batch; flags: B200KF_RUN_AGG_CONTINUE
+ *   traj / logdet / used / status as b200kf_run_batch; flags: B200KF_RUN_AGG_CONTINUE, B200KF_RUN_SMALL_TILES
  * Rows must be 16-byte aligned: N even (float64) or a multiple of 4 (float32). */
 int b200kf_run_gains(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
                      const void* gain_records, const void* payload, const int32_t* step_rows, void* x,

@@ -20,6 +20,7 @@ F64, F32 = 0, 1
 EV_GPS, EV_IMU, EV_PREDICT_ONLY = 0, 1, 2
 RUN_AUTO, RUN_FORCE_DENSE, RUN_FORCE_DECOUPLED, RUN_AGG_CONTINUE, RUN_FORCE_SYMMETRIC = 0, 1, 2, 4, 8
 RUN_FORCE_SHARED = 16
+RUN_SMALL_TILES = 32
 
 
 class ModelDesc(Structure):

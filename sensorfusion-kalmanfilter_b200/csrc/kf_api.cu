@@ -682,6 +682,7 @@ static int run_batch_impl(const b200kf_model* m, int64_t n_filters, int64_t n_st
   p.dense_flag = nullptr;
   p.gain_recs = nullptr;
   p.step_rows = step_rows;
+  p.small_tiles = 0;
   return dispatch_run(m, p, flags, static_cast<cudaStream_t>(stream));
 }
 
@@ -1103,6 +1104,7 @@ int b200kf_run_gains(const b200kf_model* m, int64_t n_filters, int64_t n_steps, 
   p.dense_flag = nullptr;
   p.gain_recs = gain_records;
   p.step_rows = step_rows;
+  p.small_tiles = (flags & B200KF_RUN_SMALL_TILES) ? 1 : 0;
   return dispatch_gains(m, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -81,6 +81,7 @@ struct RunParams {
   const int* dense_flag;  // AUTO mode: int[3] {coupled, asymmetric, P differs between filters}; a kernel runs only if they select its mode
   const void* gain_recs;  // b200kf_run_gains: DEVICE [T] precomputed gain records (GainRecG of the model)
   const int* step_rows;   // DEVICE [T] payload row of every step, or null (step k reads row k)
+  int small_tiles;        // b200kf_run_gains: 128 filters per CTA where 224 would be picked (B200KF_RUN_SMALL_TILES)
 };
 
 constexpr int kMaxEvents = 32;

@@ -564,8 +564,21 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
   static_assert(sizeof(AuxRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
   constexpr size_t kStageReals = static_cast<size_t>(CH) * D * F;
   const int nchunks = (T + CH - 1) / CH;
+  // step_rows (a selection of a longer stream): the row indices of this lane's NEXT chunk are fetched before the
+  // wait for the current one, so the global-load latency (~0.5 us, once per chunk on the lane's serial path: it
+  // capped a launch at ~2.5 steps/us = 725 GB/s whatever the CTA count) hides behind the wait and the copies
+  int rows_nx[CH];
+  auto fetch_rows = [&](int chunk) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) rows_nx[c] = (chunk * CH + c < T) ? __ldg(step_rows + chunk * CH + c) : 0;
+  };
+  if (step_rows != nullptr && first_chunk < nchunks) fetch_rows(first_chunk);
   for (int chunk = first_chunk; chunk < nchunks; chunk += chunk_stride) {
     const int s = chunk % ST;
+    int rows_cur[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) rows_cur[c] = rows_nx[c];
+    if (step_rows != nullptr && chunk + chunk_stride < nchunks) fetch_rows(chunk + chunk_stride);
     if (chunk >= ST) mbar_wait(&empty[s], static_cast<unsigned>(chunk / ST - 1) & 1u);
     const int k0 = chunk * CH;
     const int steps = (T - k0) < CH ? (T - k0) : CH;
@@ -577,10 +590,13 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
       const real* src = pay + static_cast<long long>(k0) * D * N;
       for (int r = 0; r < steps * D; ++r, src += N, dst += F) bulk_g2s(dst, src, row_bytes, &full[s]);
     } else {
-      for (int c = 0; c < steps; ++c) {
-        const long long row = step_rows[k0 + c];
 #pragma unroll
-        for (int j = 0; j < D; ++j) bulk_g2s(dst + (c * D + j) * F, pay + (row * D + j) * N, row_bytes, &full[s]);
+      for (int c = 0; c < CH; ++c) {
+        if (c < steps) {
+          const long long row = rows_cur[c];
+#pragma unroll
+          for (int j = 0; j < D; ++j) bulk_g2s(dst + (c * D + j) * F, pay + (row * D + j) * N, row_bytes, &full[s]);
+        }
       }
     }
   }
@@ -1216,13 +1232,16 @@ struct SharedRing {  // ring depth per model: stages * chunk * d rows of 896 flo
   // included -- one mbarrier.try_wait of ~90 cycles).  F = 224 keeps HALF the bytes of the larger CTAs so that
   // two CTAs fit one SM: launches that small come in groups on concurrent streams (one per sampling rate in
   // the scheduled sweep, 19 CTAs each), and a second resident CTA per SM keeps them in one wave.
+  // F = 128 (b200kf_run_gains with B200KF_RUN_SMALL_TILES): the gain-applying launches of a rate sweep share the GPU,
+  // and a CTA streams only (ring bytes) / (memory latency) ~ 40 GB/s: the rate with the longest schedule sets the
+  // sweep's time unless its filters are spread over more CTAs.  About the ring bytes of F = 224, two CTAs per SM.
   template <int F>
   static constexpr int chunk_for() {
-    return chunk * (F == 896 ? 1 : 2);
+    return chunk * (F == 896 ? 1 : (F == 128 ? 3 : 2));
   }
   template <int F>
   static constexpr int ctas_per_sm() {
-    return F == 224 ? 2 : 1;
+    return F <= 224 ? 2 : 1;
   }
 };
 
@@ -1848,6 +1867,10 @@ static cudaError_t launch_gains_f(const RunParams& p, cudaStream_t st) {
   cudaError_t err = cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, FULL, F, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
+  if constexpr (F <= 224) {  // two CTAs per SM need the whole shared-memory carve-out (a hint, not an error if refused)
+    (void)cudaFuncSetAttribute(kf_run_shared_generic_kernel<MODEL, real, FULL, F, true>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   kf_run_shared_generic_kernel<MODEL, real, FULL, F, true><<<blocks, F + 64, smem, st>>>(p);
   return cudaGetLastError();
 }
@@ -1858,7 +1881,9 @@ static int launch_gains_precision(const b200kf_model* m, const RunParams& p, cud
   const int cap = (kStepBytes896 > 36 * 1024 && m->ring_f_cap > 448) ? 448 : m->ring_f_cap;
   const int f = pick_ring_f(p.n_filters, m->sm_count, cap);
   cudaError_t e;
-  if (full)
+  if (p.small_tiles && f == 224)
+    e = full ? launch_gains_f<MODEL, real, true, 128>(p, st) : launch_gains_f<MODEL, real, false, 128>(p, st);
+  else if (full)
     e = f == 896 ? launch_gains_f<MODEL, real, true, 896>(p, st)
                  : (f == 448 ? launch_gains_f<MODEL, real, true, 448>(p, st) : launch_gains_f<MODEL, real, true, 224>(p, st));
   else

@@ -613,7 +613,9 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
             constexpr int sc = BT::template meas_state<false>(sl % NMI);
             vi = double(b.P[BT::pidx(sl / NMI, sc)]) * ir_imu[oci + sl % NMI];
           }
-          g[o + sl] = is_gps ? vg : vi;
+          // (slots beyond the GPS format keep the IMU-format value: a GPS record's consumer never reads them)
+          if constexpr (NMG > 0 && sl < BT::n * NMG) g[o + sl] = is_gps ? vg : vi;
+          else g[o + sl] = vi;
         });
         o += BT::kslots;
         ocg += NMG;

@@ -400,11 +400,12 @@ class Engine:
         return SelectState(self, types, times, periods, t_prev, P0, max_sel, want_gains)
 
     def run_gains(self, gain_records, payload, x, *, want_agg=True, traj_ncomp=0, want_logdet=False, agg=None,
-                  stream=None, inplace=False, step_rows=None):
+                  stream=None, inplace=False, step_rows=None, small_tiles=False):
         """N filters that share a schedule and a covariance, from that schedule's precomputed gain
         records (b200kf_run_gains): gain_records torch uint8 [T, bytes] (one instance's slice of
         select_greedy(..., want_gains=True)), payload [T, d, N], x [N, n].  Returns dict of torch CUDA
-        tensors x, agg [N, 4], traj, logdet, status."""
+        tensors x, agg [N, 4], traj, logdet, status.  small_tiles: 128 filters per CTA (B200KF_RUN_SMALL_TILES) for a
+        launch that runs beside others and carries the longest schedule of them."""
         torch = _torch()
         sp = self.spec
         rec = gain_records.contiguous()
@@ -421,7 +422,7 @@ class Engine:
                 raise ValueError(f"step_rows must be [T={T}] and payload [rows, d={sp.d}, N={N}]")
         elif T and tuple(pay_d.shape) != (T, sp.d, N):
             raise ValueError(f"payload must be [T={T}, d={sp.d}, N={N}], got {tuple(pay_d.shape)}")
-        flags = 0
+        flags = _lib.RUN_SMALL_TILES if small_tiles else 0
         agg_d = None
         if agg is not None:
             agg_d = self._dev(agg, torch.float64)
@@ -503,7 +504,8 @@ class Engine:
                 dts = torch.diff(st, prepend=torch.tensor([t_prev], dtype=torch.float64, device=self.device))
                 rows = sel_d.to(torch.int32)  # the kernels read the selected rows in place: no gathered payload copy
                 if recs is not None:  # the selection pass already walked this covariance recursion: pure stream
-                    r = eng.run_gains(recs[i, :len(sel)], pay_d, x0_d, traj_ncomp=traj_ncomp, stream=st_, step_rows=rows)
+                    r = eng.run_gains(recs[i, :len(sel)], pay_d, x0_d, traj_ncomp=traj_ncomp, stream=st_, step_rows=rows,
+                                      small_tiles=bool(side) and _small_tiles(len(sel), max(len(v) for v in sels)))
                     r["P"] = P_fin[i].to(self.real).expand(N, sp.n, sp.n)
                 else:
                     r = eng.run_batch(types_d.index_select(0, sel_d), dts, pay_d, x0_d, P0_d, traj_ncomp=traj_ncomp,
@@ -562,6 +564,7 @@ class Engine:
             pay_d = payload_chunk(e0, e1)
 
             def launches(e0=e0, e1=e1, pay_d=pay_d):
+                longest = max(int(np.searchsorted(sels[i], e1, side="left")) - st[i]["done"] for i in range(len(rates)))
                 for i in order:
                     s_i = st[i]
                     j0 = s_i["done"]
@@ -574,7 +577,7 @@ class Engine:
                         rows = (sel_d[i][j0:j1] - e0).to(torch.int32)
                         if recs is not None:
                             r = engines[i].run_gains(recs[i, j0:j1], pay_d, s_i["x"], agg=s_i["agg"], stream=stream,
-                                                     step_rows=rows, inplace=True)
+                                                     step_rows=rows, inplace=True, small_tiles=_small_tiles(j1 - j0, longest))
                         else:
                             tsel = seltimes[i][j0:j1]
                             dts = np.diff(tsel, prepend=s_i["prev"])  # float64 on the host, as the reference (:914)
@@ -598,6 +601,15 @@ class Engine:
             P = st[i]["P"] if recs is None else P_fin[i].to(self.real).expand(N, sp.n, sp.n)
             out[f] = {"sel": sels[i], "x": st[i]["x"], "P": P, "agg": st[i]["agg"]}
         return out
+
+
+def _small_tiles(steps, longest):
+    """Concurrent gain-applying launches of a sweep: the schedules above half the longest one take 128-filter CTAs
+    (B200KF_SWEEP_SMALL_TILES=0 disables, =all applies it to every launch)."""
+    mode = os.environ.get("B200KF_SWEEP_SMALL_TILES", "1")
+    if mode == "0":
+        return False
+    return mode == "all" or 2 * steps > longest
 
 
 def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events):
@@ -661,6 +673,7 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
         pay_d = payload_chunk(e_lo, e1)
         evs[c].synchronize()  # this chunk's selection counts are on the host
         cur.wait_event(evs[c])
+        longest = max(int(nsel_host[c, i]) - done[i] for i in range(R))
         for i in order:
             j0, j1 = done[i], int(nsel_host[c, i])
             if j1 == j0:
@@ -669,8 +682,9 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
             stream.wait_stream(cur)
             with torch.cuda.stream(stream):
                 rows = st.sel[i, j0:j1] - e_lo
+                # the chunk lasts as long as its longest schedule's launch: those get twice the CTAs
                 r = engines[i].run_gains(st.recs[i, j0:j1], pay_d, xs[i], agg=aggs[i], stream=stream, step_rows=rows,
-                                         inplace=True)
+                                         inplace=True, small_tiles=_small_tiles(j1 - j0, longest))
             xs[i], aggs[i] = r["x"], r["agg"]
             done[i] = j1
         for stream in spool[:R]:

@@ -87,13 +87,15 @@ for i, f in enumerate(rates):
 res["one_chunk_each_rate_alone"] = alone
 
 
-def together(order):
+def together(order, small="none"):
     cur = torch.cuda.current_stream(dev)
+    longest = max(k for k, _ in rows_all)
     for i in order:
         k, rows = rows_all[i]
         strs[i].wait_stream(cur)
         with torch.cuda.stream(strs[i]):
-            engines[i].run_gains(recs[i, :k], pay, x_d.clone(), step_rows=rows, stream=strs[i], inplace=True)
+            st = small == "all" or (small == "heavy" and 2 * k > longest)
+            engines[i].run_gains(recs[i, :k], pay, x_d.clone(), step_rows=rows, stream=strs[i], inplace=True, small_tiles=st)
     for s in strs:
         cur.wait_stream(s)
 
@@ -104,4 +106,11 @@ for name, order in (("descending", sorted(range(len(rates)), key=lambda j: -rate
                     ("first_wave_ascending", [rates.index(v) for v in (50, 60, 70, 80, 90, 100, 110, 120, 40, 30, 20, 10)])):
     ms, _ = timed(lambda: together(order), reps=3)
     res["one_chunk_together_" + name] = {"ms": ms, "gbs": tot_steps * 72 / (ms * 1e-3) / 1e9}
+desc = sorted(range(len(rates)), key=lambda j: -rates[j])
+for small in ("heavy", "all"):
+    ms, _ = timed(lambda: together(desc, small), reps=3)
+    res["one_chunk_together_descending_small_tiles_" + small] = {"ms": ms, "gbs": tot_steps * 72 / (ms * 1e-3) / 1e9}
+k, rows = rows_all[-1]
+ms, _ = timed(lambda: engines[-1].run_gains(recs[len(rates) - 1, :k], pay, x_d, step_rows=rows, inplace=True, small_tiles=True))
+res["one_chunk_120hz_alone_small_tiles"] = {"steps": k, "ms": ms, "gbs": k * N * 72 / (ms * 1e-3) / 1e9}
 print(json.dumps(res))
