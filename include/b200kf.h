@@ -285,7 +285,9 @@ int b200kf_select_greedy(const b200kf_model* model, int64_t n_events, const uint
  * hand that filter its gain schedule: gain_records DEVICE [I, max_sel] records of
  * b200kf_gain_record_bytes(model) bytes each (16-byte aligned), record j of instance i = (dt, type,
  * K = P+ H^T R^-1 of every block of the model's axis-symmetric form, det P) of its j-th selected
- * event.  Needs B200KF_RUN_FORCE_SYMMETRIC (the caller vouches for a chain-compatible P0 with
+ * event -- or, from the warp-per-instance walk (<= 2048 instances), the same record in its COVARIANCE
+ * form (dt, type, P+ of every block; flagged in the record): b200kf_run_gains forms K and det P from it,
+ * the same products.  Records are opaque to the caller: hand them to b200kf_run_gains unchanged.  Needs B200KF_RUN_FORCE_SYMMETRIC (the caller vouches for a chain-compatible P0 with
  * identical blocks across axes; the reference's P0 and every P it produces).  NULL = no records. */
 int b200kf_select_greedy_gains(const b200kf_model* model, int64_t n_events, const uint8_t* types,
                                const double* times, int32_t n_inst, const double* periods,

@@ -572,6 +572,31 @@ struct BlockKF {
       });
     }
   }
+  // correct() from a COVARIANCE record: Pp = this block's P+ (upper triangle, pidx order), ir = 1 / r of the
+  // event's measured columns; the gain K = P+ H^T R^-1 is formed where it is used (the same product, the same FMA)
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void correct_cov(const double* __restrict__ Pp, const double* __restrict__ ir, real dt,
+                                              const real* u) {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    if constexpr (NM > 0) {
+      real y[NM];
+      static_for<0, NM>([&](auto C) {
+        constexpr int sc = meas_state<GPS_EVENT>(C);
+        if constexpr (GPS_EVENT) y[C] = u[B::gps(sc) >= 0 ? B::gps(sc) : 0] - x[sc];
+        else if constexpr (B::zk(sc) == ZK_POS) y[C] = (x[B::l1(sc)] + u[B::pz(sc)] * dt) * dt;
+        else if constexpr (B::zk(sc) == ZK_VEL) y[C] = u[B::pz(sc)] * dt;
+        else y[C] = u[B::pz(sc)] - x[sc];
+      });
+      static_for<0, n>([&](auto I) {
+        real acc = x[I];
+        static_for<0, NM>([&](auto C) {
+          constexpr int sc = meas_state<GPS_EVENT>(C);
+          acc = fma(real(Pp[pidx(I, sc)] * ir[C]), y[C], acc);
+        });
+        x[I] = acc;
+      });
+    }
+  }
   template <typename T>
   __device__ __forceinline__ void store_cov_to(const double* cov, T* __restrict__ Pg, int n_total) const {
     static_for<0, n>([&](auto I) {
@@ -857,6 +882,33 @@ struct SymBlock {
         static_for<0, n>([&](auto I) {
           real acc = x[Mi][I];
           static_for<0, NM>([&](auto C) { acc = fma(real(K[I * NM + C]), y[C], acc); });
+          x[Mi][I] = acc;
+        });
+      });
+    }
+  }
+  // correct() from a COVARIANCE record (see BlockKF::correct_cov)
+  template <bool GPS_EVENT>
+  __device__ __forceinline__ void correct_cov(const double* __restrict__ Pp, const double* __restrict__ ir, real dt,
+                                              const real* u) {
+    constexpr int NM = n_meas<GPS_EVENT>();
+    if constexpr (NM > 0) {
+      members([&](auto Bm, auto Mi) {
+        using BM = decltype(Bm);
+        real y[NM];
+        static_for<0, NM>([&](auto C) {
+          constexpr int sc = meas_state<GPS_EVENT>(C);
+          if constexpr (GPS_EVENT) y[C] = u[BM::gps(sc) >= 0 ? BM::gps(sc) : 0] - x[Mi][sc];
+          else if constexpr (BM::zk(sc) == ZK_POS) y[C] = (x[Mi][BM::l1(sc)] + u[BM::pz(sc)] * dt) * dt;
+          else if constexpr (BM::zk(sc) == ZK_VEL) y[C] = u[BM::pz(sc)] * dt;
+          else y[C] = u[BM::pz(sc)] - x[Mi][sc];
+        });
+        static_for<0, n>([&](auto I) {
+          real acc = x[Mi][I];
+          static_for<0, NM>([&](auto C) {
+            constexpr int sc = meas_state<GPS_EVENT>(C);
+            acc = fma(real(Pp[pidx(I, sc)] * ir[C]), y[C], acc);
+          });
           x[Mi][I] = acc;
         });
       });
@@ -2208,6 +2260,10 @@ struct GainSlots<FilterT<real, IC, B0, Bs...>> {
 };
 
 constexpr int kMaxGainBlocks = 4;
+// GainRecG::pad == kCovRecord: a COVARIANCE record -- g[0 .. cov) holds P+ of every block (upper triangle, block after
+// block) instead of the gains, det / ldet are not written: the consumer forms K = P+ H^T R^-1 and det P itself.  The
+// greedy selection's warp walk writes these (a record costs its serial walk 7 stores instead of ~80 instructions).
+constexpr int kCovRecord = 1;
 template <int NG>
 struct alignas(16) GainRecG {    // a multiple of 16 bytes: records travel by bulk copy
   double dt;

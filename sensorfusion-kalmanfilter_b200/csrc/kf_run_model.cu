@@ -1304,7 +1304,7 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
   double* fin = reinterpret_cast<double*>(gain_buf + kSt * kCh);          // cov[NCOV], max, sum, last, ok
   double* pstage = fin + NCOV + 4;                                        // [kSt][kCh][NCOV]: P+ of every step, block after block
   double* irbuf = pstage + (EXT ? 0 : kSt * kCh * NCOV);                  // [2][NB][kMaxN]: 1 / r per measured column (GPS, IMU)
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(irbuf + (EXT ? 0 : 2 * NB * kMaxN));
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(irbuf + 2 * NB * kMaxN);
   unsigned long long* empty = full + kSt;
   unsigned long long* pready = empty + kSt;  // the chain warps' covariances of a chunk are staged
 
@@ -1325,6 +1325,14 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
       mbar_init(&pready[s], NB > 0 ? NB : 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if constexpr (EXT) {  // covariance records (b200kf_select_greedy's warp walk): the gains are formed here, K = P+ H^T R^-1
+      static_for<0, NB>([&](auto Kc) {
+        constexpr int K = Kc;
+        using Blk = typename Tags::template block<K>;
+        Blk::template inv_noise<true>(p.mc, irbuf + K * kMaxN);
+        if constexpr (!CTRL) Blk::template inv_noise<false>(p.mc, irbuf + (NB + K) * kMaxN);
+      });
+    }
   }
   __syncthreads();
 
@@ -1343,11 +1351,24 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
           for (int cc = 0; cc < steps; ++cc) {
             const Rec* rec = gain_buf + s * kCh + cc;
             double det = 1.0;
+            if (rec->pad == kCovRecord) {  // covariance record: g holds P+ block after block, det P from it
+              static_for<0, NB>([&](auto Kc) {
+                constexpr int K = Kc;
+                using Blk = typename Tags::template block<K>;
+                Blk blk;
 #pragma unroll
-            for (int k = 0; k < NB; ++k) {
-              const double dk = rec->det[k];
-              ok = ok && (dk > 0.0) && (dk < INFINITY);
-              det *= dk;
+                for (int e = 0; e < Blk::NP; ++e) blk.P[e] = rec->g[Tags::cov_offset(K) + e];
+                const double dk = blk.det_total(ok);
+                ok = ok && (dk < INFINITY);
+                det *= dk;
+              });
+            } else {
+#pragma unroll
+              for (int k = 0; k < NB; ++k) {
+                const double dk = rec->det[k];
+                ok = ok && (dk > 0.0) && (dk < INFINITY);
+                det *= dk;
+              }
             }
             acc.add(det);
           }
@@ -1492,9 +1513,18 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
 #pragma unroll
             for (int j = 0; j < D; ++j) u[j] = sb[(cc * D + j) * kMathThreads];
             flt.each([&](auto& b) { b.predict_state(dt, p.mc); });
+            const bool cov_rec = EXT && rec->pad == kCovRecord;  // warp-uniform
             if (ty == EV_IMU) {
               if constexpr (CTRL) {
                 flt.each([&](auto& b) { b.control(dt, p.mc, u); });
+              } else if (cov_rec) {
+                int oc = 0, kb = 0;
+                flt.each([&](auto& b) {
+                  using BT = std::remove_reference_t<decltype(b)>;
+                  b.template correct_cov<false>(rec->g + oc, irbuf + (NB + kb) * kMaxN, dt, u);
+                  oc += BT::NP;
+                  kb += 1;
+                });
               } else {
                 int o = 0;
                 flt.each([&](auto& b) {
@@ -1504,12 +1534,22 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
                 });
               }
             } else if (ty == EV_GPS) {
-              int o = 0;
-              flt.each([&](auto& b) {
-                using BT = std::remove_reference_t<decltype(b)>;
-                b.template correct<true>(rec->g + o, dt, u);
-                o += BT::kslots;
-              });
+              if (cov_rec) {
+                int oc = 0, kb = 0;
+                flt.each([&](auto& b) {
+                  using BT = std::remove_reference_t<decltype(b)>;
+                  b.template correct_cov<true>(rec->g + oc, irbuf + kb * kMaxN, dt, u);
+                  oc += BT::NP;
+                  kb += 1;
+                });
+              } else {
+                int o = 0;
+                flt.each([&](auto& b) {
+                  using BT = std::remove_reference_t<decltype(b)>;
+                  b.template correct<true>(rec->g + o, dt, u);
+                  o += BT::kslots;
+                });
+              }
             }
             if constexpr (FULL) {
               const long long k = k0 + cc;
@@ -1527,8 +1567,20 @@ __global__ void __launch_bounds__(F + 32 * ((EXT ? 0 : FilterTags<typename SymTr
                 double ld = 0.0;  // log det P = sum of the blocks' log-dets
                 if constexpr (EXT) {  // precomputed records carry determinants only (their producer takes no log)
                   double dp = 1.0;
+                  if (cov_rec) {  // ... or the covariance itself
+                    bool okd = true;
+                    static_for<0, NB>([&](auto Kc) {
+                      constexpr int K = Kc;
+                      using Blk = typename Tags::template block<K>;
+                      Blk blk;
 #pragma unroll
-                  for (int k2 = 0; k2 < NB; ++k2) dp *= rec->det[k2];
+                      for (int e = 0; e < Blk::NP; ++e) blk.P[e] = rec->g[Tags::cov_offset(K) + e];
+                      dp *= blk.det_total(okd);
+                    });
+                  } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < NB; ++k2) dp *= rec->det[k2];
+                  }
                   ld = fast_log_pos(dp);
                 } else {
 #pragma unroll

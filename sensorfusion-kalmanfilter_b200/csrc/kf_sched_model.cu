@@ -579,9 +579,12 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
     ty_imu = static_cast<int>(cr[6]);
     ns = p.n_sel[inst];
   }
-  // Deferred gain record (VAR_SYMMETRIC): the record of a selected event = K = P+ H^T R^-1 per block + det P+ of
-  // the covariance that window left in `flt`; it is written at the start of the NEXT window (or after the loop),
-  // branch-free -- every lane computes the values, both sensor formats, lane 0 stores twelve 16-byte pieces.
+  // Deferred COVARIANCE record (VAR_SYMMETRIC, kCovRecord): (dt, type, P+ of every block) of a selected event, cut
+  // from the covariance that window left in `flt` at the start of the NEXT window (or after the loop), in the same
+  // straight-line block as that window's decision and predict.  The consumer (b200kf_run_gains) forms the gains
+  // K = P+ H^T R^-1 and det P+ itself: a record costs this serial walk seven predicated warp-uniform 16-byte stores
+  // (same address, same value from every lane: one write) instead of ~80 instructions -- one warp issues about one
+  // instruction per three cycles here whatever their dependencies, so the walk's time is its instruction count.
   long long pend_idx = -1;
   double pend_dt = 0.0;
   int pend_ty = 0;
@@ -589,51 +592,24 @@ __global__ void __launch_bounds__(32) select_greedy_warp_kernel(const SelectPara
     if constexpr (VAR == VAR_SYMMETRIC && RECS) {
       using Rec = GainRecG<GainSlots<typename MT::Filter>::value>;
       constexpr int NG = GainSlots<typename MT::Filter>::value;
-      static_assert(sizeof(Rec) % 16 == 0 && offsetof(Rec, g) == 80, "record layout");
-      const bool valid = pend_idx >= 0;
-      const bool is_gps = pend_ty == EV_GPS;
-      bool okd = true;
-      const double det = filter_det(flt, okd);
-      double g[NG + 1];
-#pragma unroll
-      for (int q = 0; q <= NG; ++q) g[q] = 0.0;
-      int o = 0, ocg = 0, oci = 0;
+      constexpr int NCV = GainSlots<typename MT::Filter>::cov;
+      static_assert(sizeof(Rec) % 16 == 0 && offsetof(Rec, g) == 80 && offsetof(Rec, type) == 72, "record layout");
+      // (control-input models -- covariance larger than their gain slots -- never reach the selection: rejected by the API)
+      const bool valid = pend_idx >= 0 && NCV <= NG;
+      double g[NCV + 1];
+      g[NCV] = 0.0;
+      int oc = 0;
       flt.each([&](const auto& b) {
         using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
-        constexpr int NMG = BT::template n_meas<true>();
-        constexpr int NMI = MT::imu_control ? 0 : BT::template n_meas<false>();
-        static_for<0, BT::kslots>([&](auto Sl) {
-          constexpr int sl = Sl;
-          double vg = 0.0, vi = 0.0;
-          if constexpr (NMG > 0 && sl < BT::n * NMG) {
-            constexpr int sc = BT::template meas_state<true>(sl % NMG);
-            vg = double(b.P[BT::pidx(sl / NMG, sc)]) * ir_gps[ocg + sl % NMG];
-          }
-          if constexpr (NMI > 0 && sl < BT::n * NMI) {
-            constexpr int sc = BT::template meas_state<false>(sl % NMI);
-            vi = double(b.P[BT::pidx(sl / NMI, sc)]) * ir_imu[oci + sl % NMI];
-          }
-          // (slots beyond the GPS format keep the IMU-format value: a GPS record's consumer never reads them)
-          if constexpr (NMG > 0 && sl < BT::n * NMG) g[o + sl] = is_gps ? vg : vi;
-          else g[o + sl] = vi;
-        });
-        o += BT::kslots;
-        ocg += NMG;
-        oci += NMI;
+        static_for<0, BT::NP>([&](auto I) { g[oc + I] = double(b.P[I]); });
+        oc += BT::NP;
       });
-      // EVERY lane issues the (identical) stores, predicated on `valid` instead of branching around them: a
-      // lane-0 branch would be a divergent region the warp executes on its own, after the chain; predicated
-      // warp-uniform stores are twelve more instructions of this basic block (same address, same value: the
-      // memory pipe merges them into one write)
       double2* out = reinterpret_cast<double2*>(static_cast<Rec*>(p.gain_recs) + static_cast<long long>(inst) * p.max_sel +
                                                 (valid ? pend_idx : 0));
-      st_pred(valid, out + 0, pend_dt, det);  // dt, det[0]
-      st_pred(valid, out + 1, 1.0, 1.0);      // det[1..2]: unused blocks are 1
-      st_pred(valid, out + 2, 1.0, 0.0);      // det[3], ldet[0] (the consumer takes log(det) itself when asked)
-      st_pred(valid, out + 3, 0.0, 0.0);      // ldet[1..2]
-      st_pred(valid, out + 4, 0.0, __hiloint2double(0, pend_ty));  // ldet[3], (type, pad)
+      st_pred(valid, out + 0, pend_dt, 0.0);                                  // dt, (det[0] unused)
+      st_pred(valid, out + 4, 0.0, __hiloint2double(kCovRecord, pend_ty));    // (ldet[3] unused), (type, pad = kCovRecord)
 #pragma unroll
-      for (int q = 0; q < (NG + 1) / 2; ++q) st_pred(valid, out + 5 + q, g[2 * q], g[2 * q + 1]);
+      for (int q = 0; q < (NCV + 1) / 2; ++q) st_pred(valid, out + 5 + q, g[2 * q], g[2 * q + 1]);
       pend_idx = -1;
     }
   };

@@ -236,18 +236,68 @@ def test_config4_full_size_properties(monkeypatch):
     assert lo_thr["argmin_sum_index"] == bt["argmin_sum_index"]  # the threshold does not enter the argmin
 
 
-def _check_gain_records(ra, rb, rtol):
-    """Gain records [n, bytes] (uint8) of two producers: (dt, det[4], ldet[4], (type, pad), gains...).  dt and the
-    integer slot bit for bit; determinants and gains to `rtol` (0 = bit for bit).  An IMU event writes every gain
-    slot, a GPS event only the first block's n x 1 column -- unwritten slots are not compared."""
+# records of the 15- / 8-state models: 13 gain slots; one 3 x 3 and one 2 x 2 covariance (6 + 3 entries); the linear
+# block's K is row-major [3][n_meas], the angular block's [2][2] starts at slot 9
+_IR_IMU = {"CA15": ([0, 6, 12], [3, 9]), "CA8": ([0, 3, 6], [2, 5])}  # measured global states per block, in column order
+
+
+def _gains_of_cov_records(fa, imu, name):
+    """Gain slots [n, 13] of COVARIANCE records (pad = 1: g[0:9] = P+ of the two blocks, upper triangles): K = P+ H^T R^-1,
+    the product the consumer forms (IMU: every state of a block measured; GPS: the first block's position only)."""
+    from oracle import kf_oracle as ko
+    m = ko.get_model(name)
+    r_imu, r_gps = np.diag(m.R_imu()), np.diag(m.R_gps())
+    lin_states, ang_states = _IR_IMU[name]
+    # H_imu rows select states in the model's own order: the variance of measured STATE s is R_imu[row with H[row, s] = 1]
+    H = m.H_imu()
+    var_of_state = {int(np.argmax(H[r])): r_imu[r] for r in range(H.shape[0])}
+    P = fa[:, 10:19]
+    lin = np.zeros((len(fa), 3, 3))
+    iu = np.triu_indices(3)
+    lin[:, iu[0], iu[1]] = P[:, :6]
+    lin = lin + np.swapaxes(lin, 1, 2) - np.einsum("fij,ij->fij", lin, np.eye(3))
+    ang = np.zeros((len(fa), 2, 2))
+    ju = np.triu_indices(2)
+    ang[:, ju[0], ju[1]] = P[:, 6:9]
+    ang = ang + np.swapaxes(ang, 1, 2) - np.einsum("fij,ij->fij", ang, np.eye(2))
+    K = np.zeros((len(fa), 13))
+    ir_lin = np.array([1.0 / var_of_state[s] for s in lin_states])
+    ir_ang = np.array([1.0 / var_of_state[s] for s in ang_states])
+    K[imu, 0:9] = (lin[imu] * ir_lin[None, None, :]).reshape(-1, 9)
+    K[imu, 9:13] = (ang[imu] * ir_ang[None, None, :]).reshape(-1, 4)
+    K[~imu, 0:3] = lin[~imu][:, :, 0] / r_gps[0]
+    return K
+
+
+def _check_gain_records(ra, rb, rtol, name="CA15"):
+    """Records [n, bytes] (uint8) of two producers: (dt, det[4], ldet[4], (type, pad), 13 slots).  pad = 0: GAIN records
+    (slots = K, det[0] = det P); pad = 1: COVARIANCE records (slots 0..8 = P+, nothing else written).  dt and the event
+    type bit for bit; two records of the same kind slot by slot to `rtol` (0 = bit for bit; an IMU event writes every
+    gain slot, a GPS event only the first block's n x 1 column -- unwritten slots are not compared); a covariance record
+    against a gain record through K = P+ H^T R^-1."""
     fa = np.ascontiguousarray(ra).view(np.float64)
     fb = np.ascontiguousarray(rb).view(np.float64)
     ia = np.ascontiguousarray(ra).view(np.int32).reshape(len(ra), -1)
     ib = np.ascontiguousarray(rb).view(np.int32).reshape(len(rb), -1)
     np.testing.assert_array_equal(ia[:, 18], ib[:, 18])  # event type (byte offset 72)
     np.testing.assert_array_equal(fa[:, 0], fb[:, 0])    # dt
+    if len(fa) == 0:
+        return
     imu = ia[:, 18] == 1
-    for sl, rows in ((slice(1, 5), slice(None)), (slice(10, 23), imu), (slice(10, 13), ~imu)):  # 13 gain slots (+ padding)
+    cov_a, cov_b = bool((ia[:, 19] == 1).all()), bool((ib[:, 19] == 1).all())
+    assert cov_a or bool((ia[:, 19] == 0).all())
+    assert cov_b or bool((ib[:, 19] == 0).all())
+    if cov_a and cov_b:
+        cmp = [(slice(10, 19), slice(None))]
+    elif not cov_a and not cov_b:
+        cmp = [(slice(1, 5), slice(None)), (slice(10, 23), imu), (slice(10, 13), ~imu)]
+    else:
+        ka = _gains_of_cov_records(fa, imu, name) if cov_a else fa[:, 10:23]
+        kb = _gains_of_cov_records(fb, imu, name) if cov_b else fb[:, 10:23]
+        np.testing.assert_allclose(ka[imu], kb[imu], rtol=max(rtol, 1e-13), atol=0)
+        np.testing.assert_allclose(ka[~imu, :3], kb[~imu, :3], rtol=max(rtol, 1e-13), atol=0)
+        return
+    for sl, rows in cmp:
         if rtol == 0:
             np.testing.assert_array_equal(fa[rows, sl], fb[rows, sl])
         else:
@@ -257,8 +307,8 @@ def _check_gain_records(ra, rb, rtol):
 @pytest.mark.parametrize("name", ["CA15", "CA8"])
 def test_warp_cooperative_selection_is_bit_identical_to_the_thread_walk(name, monkeypatch):
     """b200kf_select_greedy with few instances runs one WARP per instance (events loaded 32 at a time, window
-    closing found with ballots); B200KF_SELECT_WARP=0 keeps the thread-per-instance walk.  Same selections,
-    covariances and gain records bit for bit, over a stream with batch-straddling queues, empty queues
+    closing found with ballots); B200KF_SELECT_WARP=0 keeps the thread-per-instance walk.  Same selections and
+    covariances bit for bit, the warp walk's covariance records give the thread walk's gain records, over a stream with batch-straddling queues, empty queues
     (period shorter than the event spacing) and long queues (period of several batches)."""
     from sensorfusion_kalmanfilter_b200 import streams, synth
     from sensorfusion_kalmanfilter_b200.engine import Engine
@@ -284,7 +334,7 @@ def test_warp_cooperative_selection_is_bit_identical_to_the_thread_walk(name, mo
         if mode == "symmetric":
             ra, rb = a[2].cpu().numpy(), b[2].cpu().numpy()
             for i, sa in enumerate(a[0]):  # (the two kernels may contract the determinant's FMAs differently)
-                _check_gain_records(ra[i, :len(sa)], rb[i, :len(sa)], rtol=1e-13)
+                _check_gain_records(ra[i, :len(sa)], rb[i, :len(sa)], rtol=1e-13, name=name)
     # and the selections are the oracle's (greedy_schedule over the window queues, kf_workers.py:877-910)
     if name == "CA15":
         st, _, _ = ko.run_scheduled(ko.get_model(name), ev, 55.0, 0, len(ev))
