@@ -652,9 +652,10 @@ def leg_config2(torch, a, hbm_peak):
             "algorithmic_bytes_per_filter_step": 72, "check_sum_logdet_120hz": float(out[120]["agg"][0, 1].item())}
         del out
     # ---- pipelined: the selection walks one chunk ahead of the filters on its own stream; the filters apply its
-    # gain records as pure streams.  Payload: TWO resident 25 200-event chunks (3.7 GB each, per-seed noise) used
+    # gain records as pure streams.  Payload: TWO resident chunks (per-seed noise; 12 600 events = 1.9 GB each) used
     # alternately -- nothing is generated inside the timed job, so one pair of CUDA events brackets all of it.
-    bufs = [chunk(0, 25200 + 512), chunk(25200, 50400 + 512)]  # (+ the look-back rows of a chunk's open window)
+    pch = int(os.environ.get("B200KF_CONFIG2_PIPE_CHUNK", "12600"))  # events per chunk of the pipelined job
+    bufs = [chunk(0, pch + 512), chunk(pch, 2 * pch + 512)]  # (+ the look-back rows of a chunk's open window)
     torch.cuda.synchronize()
     cnt = {"c": 0}
 
@@ -670,7 +671,8 @@ def leg_config2(torch, a, hbm_peak):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         j0.record()
-        out = eng.scheduled_sweep_pipelined(ps.types[1:], ps.times[1:], rates, x0, P0, float(ps.times[0]), recycled, 25200)
+        out = eng.scheduled_sweep_pipelined(ps.types[1:], ps.times[1:], rates, x0, P0, float(ps.times[0]), recycled, pch,
+                                            payload_depth=2)
         j1.record()
         torch.cuda.synchronize()
         return out, j0.elapsed_time(j1), time.perf_counter() - t0
@@ -682,7 +684,8 @@ def leg_config2(torch, a, hbm_peak):
     res["pipelined"] = {"value": steps / (job_ms * 1e-3), "unit": UNIT, "filter_steps": steps, "job_ms": job_ms, "wall_s": wall,
                         "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "algorithmic_bytes_per_filter_step": 72,
                         "timing": "CUDA events around the whole job: chunked selection (own stream, one chunk ahead) + "
-                                  "24 x 12 gain-applying filter launches; payload = two resident chunks used alternately",
+                                  f"{E // pch + 1} x 12 gain-applying filter launches ({pch} events per chunk); payload = two resident chunks used alternately "
+                                  "(payload_depth=2: the rates' streams meet only where a buffer is reused)",
                         "check_sum_logdet_120hz": float(outp[120]["agg"][0, 1].item())}
     del outp, bufs
     res["workload"] = (f"CA15, rates 10..120 Hz x {seeds} seeds = {len(rates) * seeds} filters over the {seconds:.0f} s stream "

@@ -383,15 +383,20 @@ class Engine:
         sels = [sel_h[i, :min(int(ns[i]), max_sel)].copy() for i in range(I)]
         return (sels, P_f, recs) if want_gains else (sels, P_f)
 
-    def scheduled_sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events):
+    def scheduled_sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events, *,
+                                  payload_depth=1):
         """scheduled_sweep_chunked with the selection OFF the critical path: the greedy selection is itself walked
         in time chunks (b200kf_select_greedy_chunk, one warp per rate, on its own stream) one chunk AHEAD of the
         filters, which consume its gain records as pure streams (b200kf_run_gains).  Per chunk the host waits only
         for that chunk's twelve selection counts (a 96-byte pinned copy).  `payload_chunk(e_lo, e1)` is asked for
         ranges that reach back one window period before the chunk: an event queued before the boundary may be selected
         after it.  The reference's P0 shape (axis-symmetric, kf_workers.py:851) is assumed, as for use_gains.
+        payload_depth: how many consecutive chunks' payload may be alive at once -- 1 (default): `payload_chunk` may
+        reuse one buffer, so a chunk's launches all finish before the next chunk's payload is asked for; k > 1: the
+        callback cycles through k buffers (the caller's promise), and the rates' streams run up to k - 1 chunks apart
+        instead of meeting at every chunk boundary (the highest rate's launch is the longest of every chunk).
         Returns {rate: dict(sel (device), n_sel, x, P, agg)}."""
-        return _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events)
+        return _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events, payload_depth)
 
     def select_state(self, types, times, periods, t_prev, P0, *, max_sel=None, want_gains=True):
         """A chunked greedy selection (b200kf_select_greedy_chunk): returns a SelectState whose advance(e_end)
@@ -612,7 +617,7 @@ def _small_tiles(steps, longest):
     return mode == "all" or 2 * steps > longest
 
 
-def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events):
+def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, chunk_events, payload_depth=1):
     """Engine.scheduled_sweep_pipelined (defined below the class for length)."""
     torch = _torch()
     sp = self.spec
@@ -658,6 +663,8 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
     xs = [x0_d.clone() for _ in rates]
     aggs = [None] * R
     done = [0] * R
+    depth = max(1, int(payload_depth))
+    chunk_done = []  # per chunk: one event per launch stream, recorded behind the chunk's launch on it
     order = sorted(range(R), key=lambda j: -rates[j])  # the highest rate has the longest launches: first
     if os.environ.get("B200KF_SWEEP_ORDER"):  # diagnostic: launch order of a chunk's rates, e.g. "50,60,...,120,40,...,10"
         want = [float(v) for v in os.environ["B200KF_SWEEP_ORDER"].split(",")]
@@ -670,6 +677,9 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
         # A window that closes in this chunk may select an event queued before e0 (the open queue at the chunk
         # boundary); queue entries are younger than one period, so the payload rows reach back that far
         e_lo = max(0, int(np.searchsorted(times, times[e0 - 1] - max_period, side="left")) - 1) if e0 > 0 else 0
+        if c >= depth:  # the buffer this chunk's payload lands in was last read by chunk c - depth
+            for ev_ in chunk_done[c - depth]:
+                cur.wait_event(ev_)
         pay_d = payload_chunk(e_lo, e1)
         evs[c].synchronize()  # this chunk's selection counts are on the host
         cur.wait_event(evs[c])
@@ -687,9 +697,15 @@ def _sweep_pipelined(self, types, times, rates, x0, P0, t_prev, payload_chunk, c
                                          inplace=True, small_tiles=_small_tiles(j1 - j0, longest))
             xs[i], aggs[i] = r["x"], r["agg"]
             done[i] = j1
+        evd = []
         for stream in spool[:R]:
-            cur.wait_stream(stream)
+            ev_ = torch.cuda.Event()
+            ev_.record(stream)
+            evd.append(ev_)
+        chunk_done.append(evd)
         del pay_d
+    for stream in spool[:R]:
+        cur.wait_stream(stream)
     cur.wait_stream(sel_stream)
     out = {}
     for i, f in enumerate(rates):

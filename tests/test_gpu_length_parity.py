@@ -227,13 +227,26 @@ def test_config2_full_length_pipelined_sweep_equals_chunked_sweep(config2):
         buf[4:-4] = pay[e0:e1]
         return buf[4:-4]
 
-    out = eng.scheduled_sweep_pipelined(*args[:6], guarded_chunk, 60007)
-    for f in rates:
-        np.testing.assert_array_equal(out[f]["sel"].cpu().numpy(), np.asarray(ref[f]["sel"]))
-        assert bool((out[f]["x"] == ref[f]["x"]).all())
-        assert bool((out[f]["P"] == ref[f]["P"]).all())
-        a, b = out[f]["agg"].cpu().numpy(), ref[f]["agg"].cpu().numpy()
-        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+    # payload_depth=3: the callback cycles through three buffers (each refilled, NaN around the rows, when its turn
+    # comes again) and the rates' streams meet only where a buffer is reused
+    pool = [torch.empty((60007 + 1024, 9, pay.shape[2]), dtype=pay.dtype, device=pay.device) for _ in range(3)]
+    turn = {"c": 0}
+
+    def cycling_chunk(e0, e1):
+        buf = pool[turn["c"] % 3]
+        turn["c"] += 1
+        buf.fill_(float("nan"))
+        buf[4:4 + e1 - e0] = pay[e0:e1]
+        return buf[4:4 + e1 - e0]
+
+    for out in (eng.scheduled_sweep_pipelined(*args[:6], guarded_chunk, 60007),
+                eng.scheduled_sweep_pipelined(*args[:6], cycling_chunk, 60007, payload_depth=3)):
+        for f in rates:
+            np.testing.assert_array_equal(out[f]["sel"].cpu().numpy(), np.asarray(ref[f]["sel"]))
+            assert bool((out[f]["x"] == ref[f]["x"]).all())
+            assert bool((out[f]["P"] == ref[f]["P"]).all())
+            a, b = out[f]["agg"].cpu().numpy(), ref[f]["agg"].cpu().numpy()
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
     for f in (10, 120):
         np.testing.assert_array_equal(out[f]["sel"].cpu().numpy().astype(np.int64) + 1,
                                       np.cumsum(g[f"r{f}_sel_delta"].astype(np.int64)))

@@ -58,7 +58,8 @@ def timed(fn, reps=2):
 
 
 res = {"events": E, "seeds": N, "chunks": E // a.chunk + 1, "order": os.environ.get("B200KF_SWEEP_ORDER", "descending")}
-ms, out = timed(lambda: eng.scheduled_sweep_pipelined(ps.types[1:], ps.times[1:], rates, x0, P0, t_prev, recycled, a.chunk))
+ms, out = timed(lambda: eng.scheduled_sweep_pipelined(ps.types[1:], ps.times[1:], rates, x0, P0, t_prev, recycled, a.chunk,
+                                                       payload_depth=int(os.environ.get("PIPE_DEPTH", "2"))))
 steps = float(sum(out[f]["n_sel"] for f in rates)) * N
 res["pipelined_ms"] = ms
 res["pipelined_gbs"] = steps * 72 / (ms * 1e-3) / 1e9
