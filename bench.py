@@ -97,6 +97,35 @@ def cpu_sample(model_name, filters_per_core, n_steps, cores):
     return done, dt
 
 
+def _cpu_sched_worker(job):
+    lo, hi = job
+    from oracle import kf_oracle as ko
+    m = ko.get_model("CA15")
+    stypes, times = search_window(20)
+    P0 = m.P0()
+    acc = 0.0
+    for mask in range(lo, hi):  # one schedule at a time, as evaluate_combo_chunk_worker (kf_workers.py:22-97)
+        lds = ko.schedule_trace(m, stypes, times, mask, P0, 999.995, float(times[-1]))
+        acc += max(lds) + sum(lds) + lds[-1]
+    return hi - lo
+
+
+def cpu_schedule_sample(n_schedules, cores):
+    """Pool(cores) over `n_schedules` subset schedules of the 20-event window (BASELINE configs[3]), the oracle port of
+    the reference worker's covariance-only trace: schedules scored per second on the host."""
+    import multiprocessing as mp
+    first = (1 << 19) + 12345  # schedules from the middle of the index space: ~10 used events each, like the average
+    per = n_schedules // cores
+    jobs = [(first + i * per, first + (i + 1) * per) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_sched_worker, [(1, 3)] * cores)
+        t0 = time.perf_counter()
+        done = sum(pool.map(_cpu_sched_worker, jobs, chunksize=1))
+        dt = time.perf_counter() - t0
+    return done, dt
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -949,7 +978,11 @@ def run_gpu_arm(a):
             t1 = time.perf_counter()
             st1 = ko.run_full(ko.get_model("CA15"), ev1, 0, len(ev1))[0]
             single = (len(st1) - 1) / (time.perf_counter() - t1)
+            sdone, sdt = cpu_schedule_sample(1 << 13, cores)
             cpu = {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port", "single_filter_ca15": single,
+                   "schedules_per_s": sdone / sdt,
+                   "schedules_sample": f"{sdone} subset schedules of the 20-event CA15 window on {cores} processes, oracle port of "
+                                       f"the worker's covariance-only trace (kf_workers.py:22-97); {sdt:.1f} s",
                    "sample": f"{cores} processes x {fpc} filters x 10000 events, per-filter numpy float64 loop "
                              f"(oracle port of kf_workers.py:681-721 for {a.model}); {dt:.1f} s"}
 
