@@ -473,8 +473,17 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #ifndef B200KF_BULK_OUT_STAGES
 #define B200KF_BULK_OUT_STAGES 2
 #endif
-constexpr int kBulkInStages = B200KF_BULK_IN_STAGES;
-constexpr int kOutStages = B200KF_BULK_OUT_STAGES;
+// Three-column payloads (CV6 / BIAS9: 24 B in, 56 B out per step) take 3 + 3 stages instead: the stores are 70 % of
+// the traffic and a third output stage keeps the store lane fed (trajectory mode 5 540 -> 5 960 GB/s, 0.85 -> 0.91 of
+// the HBM peak; the 72-byte-per-step CA15 ring measured 1 % slower with it and keeps 4 + 2).
+template <int D>
+constexpr int bulk_in_stages() {
+  return D <= 3 ? 3 : B200KF_BULK_IN_STAGES;
+}
+template <int D>
+constexpr int bulk_out_stages() {
+  return D <= 3 ? 3 : B200KF_BULK_OUT_STAGES;
+}
 constexpr int kBulkMaxRows = 8;
 template <typename real, int F, int D = 3>
 constexpr int bulk_chunk() {
@@ -632,7 +641,8 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
   static_assert(!BULK || FULL, "the output ring belongs to the per-step-output kernel");
   constexpr int kTmaThreads = F;
   constexpr int kD = ModelTraits<MODEL, false, real>::d;
-  constexpr int kStages = BULK ? kBulkInStages : ring_stages<real, F, kD>();
+  constexpr int kOutStages = bulk_out_stages<kD>();
+  constexpr int kStages = BULK ? bulk_in_stages<kD>() : ring_stages<real, F, kD>();
   constexpr int kChunk = BULK ? bulk_chunk<real, F, kD>() : ring_chunk<real, F, kD>();
   constexpr int kLoadWarps = BULK ? kCopyWarps - 1 : kCopyWarps;  // BULK: the last service warp stores
   // a copy lane waits on a stage's empty barrier by phase PARITY: that is only unambiguous while it can
@@ -714,8 +724,24 @@ __global__ void __launch_bounds__(F + 32 * svc_warps<MODEL, real>(), 1)
             bulk_s2g(ldg + k * N, src + (static_cast<size_t>(c) * out_rows + out_nc) * kTmaThreads, row_bytes);
         }
         bulk_commit();
-        bulk_wait_read<0>();  // the stores have READ the stage (not yet landed in HBM): the math warps may refill it
-        mbar_arrive(&out_empty[os]);
+        if constexpr (kOutStages >= 3) {
+          // one bulk group in flight behind the one just committed: the previous chunk's stage is released once ITS
+          // stores have read it, while this chunk's are already issued (with only two output stages this makes the
+          // math warps wait a chunk longer for a free stage: -8 % on the CA15 ring)
+          if (chunk > 0) {
+            bulk_wait_read<1>();
+            mbar_arrive(&out_empty[(chunk - 1) % kOutStages]);
+          }
+        } else {
+          bulk_wait_read<0>();  // the stores have READ the stage (not yet landed in HBM): the math warps may refill it
+          mbar_arrive(&out_empty[os]);
+        }
+      }
+      if constexpr (kOutStages >= 3) {
+        if (nchunks > 0) {
+          bulk_wait_read<0>();
+          mbar_arrive(&out_empty[(nchunks - 1) % kOutStages]);
+        }
       }
       bulk_wait_all();  // the launch's outputs are complete when the kernel ends
     }
@@ -1661,15 +1687,15 @@ constexpr size_t tma_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
   constexpr int st = ring_stages<real, F, MT::d>(), ch = ring_chunk<real, F, MT::d>();
   return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
-         static_cast<size_t>(st) * ch * sizeof(CARecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
+         static_cast<size_t>(st) * ch * sizeof(CARecT<real>) + (2 * st + 2 * bulk_out_stages<MT::d>()) * sizeof(unsigned long long);
 }
 template <int MODEL, typename real, int F>
 static size_t tma_bulk_smem_bytes(int out_rows) {
   using MT = ModelTraits<MODEL, false, real>;
-  constexpr int st = kBulkInStages, ch = bulk_chunk<real, F, MT::d>();
+  constexpr int st = bulk_in_stages<MT::d>(), kOut = bulk_out_stages<MT::d>(), ch = bulk_chunk<real, F, MT::d>();
   return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
-         static_cast<size_t>(kOutStages) * ch * out_rows * F * sizeof(real) +
-         static_cast<size_t>(st) * ch * sizeof(CARecT<real>) + (2 * st + 2 * kOutStages) * sizeof(unsigned long long);
+         static_cast<size_t>(kOut) * ch * out_rows * F * sizeof(real) +
+         static_cast<size_t>(st) * ch * sizeof(CARecT<real>) + (2 * st + 2 * kOut) * sizeof(unsigned long long);
 }
 
 // filters per CTA of the ring kernels: the largest of {896, 448, 224} that still gives every SM a CTA
@@ -1745,13 +1771,15 @@ static cudaError_t launch_tma_f(const RunParams& p, const void* sched, cudaStrea
   kf_run_tma_kernel<MODEL, real, SYM, FULL, F><<<blocks, F + 32 * svc_warps<MODEL, real>(), smem, st>>>(p, sched);
   return cudaGetLastError();
 }
+constexpr size_t kMaxDynSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 template <int MODEL, typename real, bool SYM, int F>
 static cudaError_t launch_tma_bulk_f(const RunParams& p, const void* sched, int out_rows, cudaStream_t st) {
   const size_t smem = tma_bulk_smem_bytes<MODEL, real, F>(out_rows);
   const unsigned blocks = static_cast<unsigned>((p.n_filters + F - 1) / F);
+  const size_t smem_cap = tma_bulk_smem_bytes<MODEL, real, F>(kBulkMaxRows);
   cudaError_t err = cudaFuncSetAttribute(kf_run_tma_kernel<MODEL, real, SYM, true, F, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(tma_bulk_smem_bytes<MODEL, real, F>(kBulkMaxRows)));
+                                         static_cast<int>(smem_cap < kMaxDynSmem ? smem_cap : kMaxDynSmem));
   if (err != cudaSuccess) return err;
   kf_run_tma_kernel<MODEL, real, SYM, true, F, true><<<blocks, F + 32 * svc_warps<MODEL, real>(), smem, st>>>(p, sched);
   return cudaGetLastError();
@@ -1774,10 +1802,13 @@ static cudaError_t launch_tma_one(const b200kf_model* m, const RunParams& p, con
     int rows = 0;
     if (bulk_out_ok(m, p, &rows)) {
       if constexpr (k896) {
-        if (f == 896) return launch_tma_bulk_f<MODEL, real, SYM, 896>(p, sched, rows, st);
+        if (f == 896 && tma_bulk_smem_bytes<MODEL, real, 896>(rows) <= kMaxDynSmem)
+          return launch_tma_bulk_f<MODEL, real, SYM, 896>(p, sched, rows, st);
       }
-      if (f >= 448) return launch_tma_bulk_f<MODEL, real, SYM, 448>(p, sched, rows, st);
-      return launch_tma_bulk_f<MODEL, real, SYM, 224>(p, sched, rows, st);
+      if (f >= 448 && tma_bulk_smem_bytes<MODEL, real, 448>(rows) <= kMaxDynSmem)
+        return launch_tma_bulk_f<MODEL, real, SYM, 448>(p, sched, rows, st);
+      if (f < 448 && tma_bulk_smem_bytes<MODEL, real, 224>(rows) <= kMaxDynSmem)
+        return launch_tma_bulk_f<MODEL, real, SYM, 224>(p, sched, rows, st);
     }
   }
   if constexpr (k896) {

@@ -1,0 +1,12 @@
+set -x
+mkdir -p gpurun_out
+L=sensorfusion-kalmanfilter_b200
+for v in base ca43 base ca43; do
+  if [ $v = base ]; then unset B200KF_LIB; else export B200KF_LIB=$PWD/$L/libb200kf_$v.so; fi
+  for m in CV6 CA15 CA8; do
+    timeout 300 python tools/traj_probe.py --reps 300 --model $m >> gpurun_out/r02za_traj_$v.jsonl 2>&1
+  done
+done
+unset B200KF_LIB
+timeout 900 python -m pytest tests/test_gpu_run_batch.py tests/test_gpu_full_size.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/r02za_pytest.log 2>&1; tail -3 gpurun_out/r02za_pytest.log
+B200KF_LIB=$PWD/$L/libb200kf_ca43.so timeout 900 python -m pytest tests/test_gpu_run_batch.py -m gpu -q --timeout 600 -p no:cacheprovider -k "output_ring or constant_acceleration" > gpurun_out/r02za_pytest_ca43.log 2>&1; tail -3 gpurun_out/r02za_pytest_ca43.log
