@@ -565,6 +565,44 @@ def leg_dense(torch, a, fma_peak, fma_peak_distinct):
     return out
 
 
+def leg_explicit_bu(torch, a, hbm_peak):
+    """The north star's predict step as written, x = F x + B u, P = F P F^T + Q, for the six-state filter (model
+    CVBU6: IMU acceleration as control input, GPS-only updates; SURVEY.md 8(d) config 3, explicit-Bu variant): one
+    covariance per filter on the ring kernel (Sym2CtrlFilter), aggregate and trajectory mode."""
+    from sensorfusion_kalmanfilter_b200 import synth
+    from sensorfusion_kalmanfilter_b200.engine import Engine, fill_payload
+    N, T = 131072, 2000
+    os.environ["B200KF_SHARED"] = "0"
+    eng = Engine("CVBU6")
+    os.environ.pop("B200KF_SHARED", None)
+    sp = eng.spec
+    types, dts = synth.gps_imu_schedule(T)
+    types_d, dts_d = torch.from_numpy(types).to(eng.device), torch.from_numpy(dts).to(eng.device)
+    pay = fill_payload(eng, types_d, N, seed=77)
+    scale = 1.0 + (np.arange(N) % 1024) / 1024.0
+    x = torch.zeros((N, sp.n), dtype=eng.real, device=eng.device)
+    P = torch.from_numpy(sp.default_P0()[None] * scale[:, None, None]).to(device=eng.device, dtype=eng.real).contiguous()
+    out = {}
+    for label, kw, out_b in (("aggregate", dict(want_agg=True), 0),
+                             ("trajectory", dict(want_agg=False, traj_ncomp=6, want_logdet=True), 56)):
+        def one():
+            o = eng.run_batch(types_d, dts_d, pay, x, P, inplace=True, **kw)
+            del o
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize()
+        st = _stats(_timed_loop(one, 100, torch))
+        bps = sp.d * 8 + out_b
+        gbs = float(N) * T * bps / (st["mean"] * 1e-3) / 1e9
+        out[label] = {"value": N * T / (st["mean"] * 1e-3), "unit": UNIT, "ms": st["mean"], "ms_min": st["min"],
+                      "algorithmic_bytes_per_filter_step": bps, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+                      "frac_burst": float(N) * T * bps / (st["min"] * 1e-3) / 1e9 / hbm_peak}
+    out["workload"] = f"CVBU6 {N} filters x {T} steps, f64, per-filter covariance (P0 x (1 + (f % 1024)/1024)), 100 back-to-back launches"
+    del pay, x, P, eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def leg_reference_models(torch, a, hbm_peak, fma_peak=None, fma_peak_distinct=None):
     """The reference's OWN models with one covariance per filter: CA15 (kf_workers.py:493-614, 72 B of payload per
     step) and CA8 (hw5_2.py:219-304, 32 B), aggregate mode and trajectory mode (x[0:6] + log det per step, what
@@ -960,6 +998,7 @@ def run_gpu_arm(a):
         config3_full = leg_config3_one_gpu(torch, a, hbm_peak) if not a.no_configs else None
         ref_models = leg_reference_models(torch, a, hbm_peak, fma_peak, fma_peak_distinct) if not a.no_configs else None
         dense_mode = leg_dense(torch, a, fma_peak, fma_peak_distinct) if not a.no_configs else None
+        bu_mode = leg_explicit_bu(torch, a, hbm_peak) if not a.no_configs else None
         config5 = leg_config5(torch, a, hbm_peak) if not a.no_configs else None
         config2 = leg_config2(torch, a, hbm_peak) if not a.no_configs else None
 
@@ -1003,7 +1042,7 @@ def run_gpu_arm(a):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_pass * n_pass,
                 "roofline": roofline, "cpu_baseline": cpu, "search": search, "search_large": search_large,
                 "search_2p32": search_huge, "product_search": products,
-                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "reference_models": ref_models, "dense_ca15": dense_mode, "config3_full_one_gpu": config3_full,
+                "trajectory_mode": traj_mode, "shared_covariance": shared_mode, "reference_models": ref_models, "dense_ca15": dense_mode, "explicit_bu_cv6": bu_mode, "config3_full_one_gpu": config3_full,
                 "config5": config5, "config2": config2}
     if world > 1:
         dist.barrier()

@@ -45,6 +45,7 @@ extern "C" {
 #define B200KF_MODEL_CA8 1   /* hw5_2.py:219-304  [x,y,th,vx,vy,thdot,ax,ay] */
 #define B200KF_MODEL_BIAS9 2 /* [p(3),v(3),b(3)], IMU acceleration as control input */
 #define B200KF_MODEL_CA15 3  /* kf_workers.py:493-614  [p,rpy,v,w,a] */
+#define B200KF_MODEL_CVBU6 4 /* [p(3),v(3)], x = F x + B u: IMU acceleration as control input, GPS-only updates */
 
 #define B200KF_F64 0
 #define B200KF_F32 1
@@ -134,7 +135,7 @@ int b200kf_model_dims(const b200kf_model* model, int32_t* n, int32_t* d, int32_t
  *   dts     DEVICE f64 [T]        t - t_prev per step
  *   payload DEVICE real[T, d, N]  time-major, filter index fastest.  GPS rows: (E, N, alt) in
  *                                 columns 0..m_gps-1; IMU rows: CA15 (r,p,y,wx,wy,wz,ax,ay,az),
- *                                 CA8 (yaw, wz, ax, ay), CV6/BIAS9 (ax, ay, az)
+ *                                 CA8 (yaw, wz, ax, ay), CV6/BIAS9/CVBU6 (ax, ay, az)
  *   x       DEVICE real[N, n]     in: state before step 0, out: state after step T-1
  *   P       DEVICE real[N, n, n]  in/out covariance, row-major, full symmetric
  *   agg     DEVICE f64 [N, 4]     nullable; (max, sum, last) of log det P over the steps and the

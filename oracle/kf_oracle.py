@@ -10,7 +10,7 @@ tests/golden/*.npz, which oracle/make_golden.py produced by running the UNMODIFI
 (imported from /root/reference through oracle/ref_import.py) on seeded synthetic streams.
 The reference itself ships no tests or golden vectors for this path, and its
 saved notebook outputs need the absent imu_data.csv, so "outputs of the reference itself run
-here" is the pin.  The CV6 and BIAS9 models do not exist in the reference (SURVEY.md 8(d)
+here" is the pin.  The CV6, BIAS9 and CVBU6 models do not exist in the reference (SURVEY.md 8(d)
 defines them); for those the oracle is the definition and parity is "restatement only".
 
 Everything works on a leading batch axis: x is [..., n], P is [..., n, n]; a single filter is
@@ -191,7 +191,37 @@ class BIAS9(OracleModel):
         return np.diag([10000.0] * 3 + [1000.0] * 3 + [10000.0] * 3)
 
 
-MODELS = {"CA15": CA15, "CA8": CA8, "CV6": CV6, "BIAS9": BIAS9}
+class CVBU6(OracleModel):
+    """6-state [p(3), v(3)] model in the north star's explicit-control form x = F x + B u, P = F P F^T + Q
+    ("explicit-Bu variant"): B = [[dt^2/2 I], [dt I]], IMU acceleration is the control
+    input (no IMU update), GPS events predict with u = 0 and update the position rows.  F, Q, P0 as CV6."""
+
+    name, n, m_gps, d = "CVBU6", 6, 3, 3
+    imu_is_control = True
+
+    def F(self, dt):
+        F = np.eye(6)
+        F[0, 3] = F[1, 4] = F[2, 5] = dt
+        return F
+
+    def B(self, dt):
+        B = np.zeros((6, 3))
+        for ax in range(3):
+            B[ax, ax] = 0.5 * dt ** 2
+            B[3 + ax, ax] = dt
+        return B
+
+    def Q(self, dt):
+        return np.diag([5 * dt] * 3 + [1 * dt] * 3)
+
+    def R_imu(self):
+        return np.zeros((6, 6))
+
+    def P0(self):
+        return np.diag([10000.0] * 3 + [1000.0] * 3)
+
+
+MODELS = {"CA15": CA15, "CA8": CA8, "CV6": CV6, "BIAS9": BIAS9, "CVBU6": CVBU6}
 
 
 def get_model(name):

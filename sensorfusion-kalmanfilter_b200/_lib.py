@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200KF_LIB") or os.path.join(PKG_DIR, "libb200kf.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
-MODEL_CV6, MODEL_CA8, MODEL_BIAS9, MODEL_CA15 = 0, 1, 2, 3
+MODEL_CV6, MODEL_CA8, MODEL_BIAS9, MODEL_CA15, MODEL_CVBU6 = 0, 1, 2, 3, 4
 F64, F32 = 0, 1
 EV_GPS, EV_IMU, EV_PREDICT_ONLY = 0, 1, 2
 RUN_AUTO, RUN_FORCE_DENSE, RUN_FORCE_DECOUPLED, RUN_AGG_CONTINUE, RUN_FORCE_SYMMETRIC = 0, 1, 2, 4, 8

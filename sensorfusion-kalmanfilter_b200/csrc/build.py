@@ -29,7 +29,7 @@ NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-lineinfo", "-Xcompiler", "-fPIC",
           "-Xptxas", "-v"] + ARCH + EXTRA
-MODELS = (0, 1, 2, 3)
+MODELS = (0, 1, 2, 3, 4)
 HEADERS = ["kf_core.cuh", "kf_axis.cuh", "kf_internal.h", os.path.join(ROOT, "include", "b200kf.h")]
 
 

@@ -33,7 +33,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct ModelInfo {
   int n, d, m_gps;
 };
-static const ModelInfo kInfo[MODEL_COUNT] = {{6, 3, 3}, {8, 4, 2}, {9, 3, 3}, {15, 9, 3}};
+static const ModelInfo kInfo[MODEL_COUNT] = {{6, 3, 3}, {8, 4, 2}, {9, 3, 3}, {15, 9, 3}, {6, 3, 3}};
 
 static int dispatch_run(const b200kf_model* m, const RunParams& p, unsigned flags, cudaStream_t st) {
   switch (m->desc.model_id) {
@@ -41,6 +41,7 @@ static int dispatch_run(const b200kf_model* m, const RunParams& p, unsigned flag
     case MODEL_CA8: return launch_run_m<MODEL_CA8>(m, p, flags, st);
     case MODEL_BIAS9: return launch_run_m<MODEL_BIAS9>(m, p, flags, st);
     case MODEL_CA15: return launch_run_m<MODEL_CA15>(m, p, flags, st);
+    case MODEL_CVBU6: return launch_run_m<MODEL_CVBU6>(m, p, flags, st);
   }
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
@@ -52,6 +53,7 @@ static int dispatch_score(const b200kf_model* m, const ScoreParams& p, unsigned 
     case MODEL_CA8: return launch_score_m<MODEL_CA8>(m, p, flags, best, st);
     case MODEL_BIAS9: return launch_score_m<MODEL_BIAS9>(m, p, flags, best, st);
     case MODEL_CA15: return launch_score_m<MODEL_CA15>(m, p, flags, best, st);
+    case MODEL_CVBU6: return launch_score_m<MODEL_CVBU6>(m, p, flags, best, st);
   }
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
@@ -62,6 +64,7 @@ static int dispatch_masked(const b200kf_model* m, const MaskedParams& p, unsigne
     case MODEL_CA8: return launch_masked_m<MODEL_CA8>(m, p, flags, st);
     case MODEL_BIAS9: return launch_masked_m<MODEL_BIAS9>(m, p, flags, st);
     case MODEL_CA15: return launch_masked_m<MODEL_CA15>(m, p, flags, st);
+    case MODEL_CVBU6: return launch_masked_m<MODEL_CVBU6>(m, p, flags, st);
   }
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
@@ -72,6 +75,7 @@ static int dispatch_product(const b200kf_model* m, const ProductParams& p, unsig
     case MODEL_CA8: return launch_product_m<MODEL_CA8>(m, p, flags, st);
     case MODEL_BIAS9: return launch_product_m<MODEL_BIAS9>(m, p, flags, st);
     case MODEL_CA15: return launch_product_m<MODEL_CA15>(m, p, flags, st);
+    case MODEL_CVBU6: return launch_product_m<MODEL_CVBU6>(m, p, flags, st);
   }
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
@@ -82,6 +86,7 @@ static int dispatch_gains(const b200kf_model* m, const RunParams& p, cudaStream_
     case MODEL_CA8: return launch_gains_m<MODEL_CA8>(m, p, st);
     case MODEL_BIAS9: return launch_gains_m<MODEL_BIAS9>(m, p, st);
     case MODEL_CA15: return launch_gains_m<MODEL_CA15>(m, p, st);
+    case MODEL_CVBU6: return launch_gains_m<MODEL_CVBU6>(m, p, st);
   }
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
@@ -92,6 +97,7 @@ static int dispatch_select(const b200kf_model* m, const SelectParams& p, unsigne
     case MODEL_CA8: return launch_select_m<MODEL_CA8>(m, p, flags, st);
     case MODEL_BIAS9: return launch_select_m<MODEL_BIAS9>(m, p, flags, st);
     case MODEL_CA15: return launch_select_m<MODEL_CA15>(m, p, flags, st);
+    case MODEL_CVBU6: return launch_select_m<MODEL_CVBU6>(m, p, flags, st);
   }
   return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
 }
@@ -479,6 +485,9 @@ int b200kf_model_default_desc(int32_t model_id, int32_t precision, b200kf_model_
     }
     case MODEL_BIAS9:
       set3(desc->q, 0, 5.0), set3(desc->q, 3, 1.0), set3(desc->q, 6, 2.0);
+      break;
+    case MODEL_CVBU6:  // CV6's process noise; the IMU event is a control input: no IMU variances
+      set3(desc->q, 0, 5.0), set3(desc->q, 3, 1.0);
       break;
     case MODEL_CA15:  // kf_workers.py:521-543, 589-613
       set3(desc->q, 0, 5.0), set3(desc->q, 3, 0.05), set3(desc->q, 6, 1.0), set3(desc->q, 9, 0.1),
@@ -986,7 +995,7 @@ int b200kf_select_greedy_gains(const b200kf_model* m, int64_t n_events, const ui
                                const double* P0, int64_t max_sel, int32_t* sel, int64_t* n_sel, double* P_final,
                                void* gain_records, uint32_t flags, void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
-  if (m->desc.model_id == MODEL_BIAS9)
+  if (m->desc.model_id == MODEL_BIAS9 || m->desc.model_id == MODEL_CVBU6)
     return set_error(B200KF_ERR_UNSUPPORTED, "greedy selection needs an IMU measurement model");
   if (n_events < 0 || n_inst < 0 || max_sel < 0) return set_error(B200KF_ERR_INVALID, "negative size");
   if (n_events > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_events > 2^31-1");
@@ -1017,7 +1026,7 @@ int b200kf_select_greedy_chunk(const b200kf_model* m, int64_t e_begin, int64_t e
                                const double* P0, double* carry, double* P_state, int64_t max_sel, int32_t* sel,
                                int64_t* n_sel, void* gain_records, uint32_t flags, void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
-  if (m->desc.model_id == MODEL_BIAS9)
+  if (m->desc.model_id == MODEL_BIAS9 || m->desc.model_id == MODEL_CVBU6)
     return set_error(B200KF_ERR_UNSUPPORTED, "greedy selection needs an IMU measurement model");
   if (e_begin < 0 || e_end < e_begin || n_inst < 0 || max_sel < 0) return set_error(B200KF_ERR_INVALID, "bad range or size");
   if (e_end > 0x7fffffffLL) return set_error(B200KF_ERR_UNSUPPORTED, "n_events > 2^31-1");
@@ -1057,6 +1066,7 @@ int b200kf_gain_record_bytes(const b200kf_model* m, size_t* bytes) {
     case MODEL_CV6: *bytes = gain_record_bytes_m<MODEL_CV6>(); break;
     case MODEL_CA8: *bytes = gain_record_bytes_m<MODEL_CA8>(); break;
     case MODEL_BIAS9: *bytes = gain_record_bytes_m<MODEL_BIAS9>(); break;
+    case MODEL_CVBU6: *bytes = gain_record_bytes_m<MODEL_CVBU6>(); break;
     case MODEL_CA15: *bytes = gain_record_bytes_m<MODEL_CA15>(); break;
     default: return set_error(B200KF_ERR_UNSUPPORTED, "unknown model id %d", m->desc.model_id);
   }

@@ -244,6 +244,20 @@ struct BIAS9Chain {  // [p, v, b]; p += dt v - c2 dt^2 b, v -= dt b; u = accel (
   static constexpr int cu(int i) { return i == 0 ? 1 : (i == 1 ? 2 : 0); }
 };
 
+template <int AXIS>
+struct CVBU6Chain {  // [p, v]; the north star's x = F x + B u for six states: p += dt v + c2 dt^2 u, v += dt u (u = accel),
+  static constexpr int n = 2;  // IMU events update nothing, GPS measures p (the explicit-Bu variant)
+  static constexpr int gidx(int i) { return i == 0 ? AXIS : 3 + AXIS; }
+  static constexpr int l1(int i) { return i == 0 ? 1 : -1; }
+  static constexpr int l2(int) { return -1; }
+  static constexpr int s1(int) { return 1; }
+  static constexpr int s2(int) { return 1; }
+  static constexpr int gps(int i) { return i == 0 ? AXIS : -1; }
+  static constexpr int zk(int) { return ZK_NONE; }
+  static constexpr int pz(int) { return AXIS; }
+  static constexpr int cu(int i) { return i == 0 ? 1 : 2; }
+};
+
 // The dense form of a model: one block holding every state of the listed chains.
 template <class... Bs>
 struct Union {
@@ -1852,6 +1866,148 @@ struct Sym3CtrlFilter {
 };
 
 // --------------------------------------------------------------------------------------
+// Sym2CtrlFilter: the two-state form of Sym3CtrlFilter -- M identical (value, rate) chains whose IMU event is
+// the control input x = F x + B u, B = [c2 dt^2, dt] (the north star's predict step as written; CVBU6), GPS
+// measures the value.  One 2 x 2 covariance per filter: 6 (covariance) + 2 (det) + 3 per axis FP64 per IMU step.
+// --------------------------------------------------------------------------------------
+template <class B>
+constexpr bool is_vr2c() {  // [value, rate]: value += dt rate; control on value (c2 dt^2 u) and rate (dt u)
+  if (is_group_tag<B>::value) return false;
+  if (B::n != 2) return false;
+  return B::l1(0) == 1 && B::l2(0) < 0 && B::s1(0) == 1 && B::l1(1) < 0 && B::l2(1) < 0 && B::cu(0) == 1 &&
+         B::cu(1) == 2 && B::gps(0) >= 0 && B::gps(1) < 0 && B::zk(0) == ZK_NONE && B::zk(1) == ZK_NONE;
+}
+
+template <typename real, class B0, class... Bs>
+struct Sym2CtrlFilter {
+  static constexpr bool rec_api = false;  // predict(dt, mc) / update(dt, mc, ...) interface
+  static constexpr int M = 1 + sizeof...(Bs);
+  static constexpr bool eligible = (is_vr2c<B0>() && ... && is_vr2c<Bs>());
+  static constexpr bool lean_ok = eligible;
+  using Lead = B0;
+  real p00, p01, p11;  // the shared chain covariance (upper triangle)
+  real x0[M], x1[M];
+  real r0r1;  // unused scale of the lean aggregate (v is the chain determinant itself)
+
+  using LeanRec = LeanRecT<real>;  // only (dt, dt^2, type) are read
+  template <class F>
+  __device__ __forceinline__ static void members(F&& fn) {
+    int m = 0;
+    fn(B0{}, m++);
+    (fn(Bs{}, m++), ...);
+  }
+  __device__ __forceinline__ void load(const real* xg, const real* Pg, int n, const ModelConst&) {
+    p00 = Pg[B0::gidx(0) * n + B0::gidx(0)];
+    p01 = real(0.5) * (Pg[B0::gidx(0) * n + B0::gidx(1)] + Pg[B0::gidx(1) * n + B0::gidx(0)]);
+    p11 = Pg[B0::gidx(1) * n + B0::gidx(1)];
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      x0[m] = xg[BM::gidx(0)];
+      x1[m] = xg[BM::gidx(1)];
+    });
+    r0r1 = real(1);
+  }
+  __device__ __forceinline__ void store(real* xg, real* Pg, int n) const {
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      xg[BM::gidx(0)] = x0[m];
+      xg[BM::gidx(1)] = x1[m];
+      Pg[BM::gidx(0) * n + BM::gidx(0)] = p00;
+      Pg[BM::gidx(0) * n + BM::gidx(1)] = p01;
+      Pg[BM::gidx(1) * n + BM::gidx(0)] = p01;
+      Pg[BM::gidx(1) * n + BM::gidx(1)] = p11;
+    });
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_state(F&& fn) const {
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      fn(std::integral_constant<int, BM::gidx(0)>{}, x0[m]);
+      fn(std::integral_constant<int, BM::gidx(1)>{}, x1[m]);
+    });
+  }
+  __device__ __forceinline__ void to_normalized(const ModelConst&) {}
+  __device__ __forceinline__ void from_normalized(const ModelConst&) {}
+  __device__ __forceinline__ real chain_det() const { return fma(p00, p11, -(p01 * p01)); }
+  __device__ __forceinline__ double det(bool& ok) const {
+    const real d = chain_det();
+    ok = ok && (d > real(0));
+    double r = double(d);
+#pragma unroll
+    for (int i = 1; i < M; ++i) r *= double(d);
+    return r;
+  }
+  // P = F P F^T + Q, entry by entry
+  __device__ __forceinline__ void predict_cov(real dt, const ModelConst& mc) {
+    const real a00 = fma(dt, p01, p00);
+    const real a01 = fma(dt, p11, p01);
+    p00 = fma(real(mc.q[B0::gidx(0)]), dt, fma(dt, a01, a00));
+    p01 = a01;
+    p11 = fma(real(mc.q[B0::gidx(1)]), dt, p11);
+  }
+  __device__ __forceinline__ void predict_state(real dt) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) x0[m] = fma(dt, x1[m], x0[m]);
+  }
+  __device__ __forceinline__ void gps_update(const ModelConst& mc, const real* u) {
+    const real r = real(mc.r_gps[B0::gps(0)]);
+    const real inv = fast_rcp3(p00 + r);
+    const real k0 = p00 * inv, k1 = p01 * inv, g = r * inv;
+    members([&](auto Bm, int m) {
+      using BM = decltype(Bm);
+      const real y = u[BM::gps(0)] - x0[m];
+      x0[m] = fma(k0, y, x0[m]);
+      x1[m] = fma(k1, y, x1[m]);
+    });
+    p11 = fma(-k1, p01, p11);
+    p00 *= g;  // row 0 of (I - K H) P is row * r / (P00 + r)
+    p01 *= g;
+  }
+  // fused predict (+ control or GPS update); v = det of the chain covariance after the step
+  __device__ __forceinline__ void step_lean(const LeanRec& rec, const ModelConst& mc, const real* u, real& v) {
+    const real dt = real(rec.dt);
+    const real e = real(mc.c2) * real(rec.dt2);
+    predict_cov(dt, mc);
+    if (rec.type == EV_IMU) {  // x = F x + B u: the control enters value and rate
+      members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        const real acc = u[BM::pz(0)];
+        x0[m] = fma(e, acc, fma(dt, x1[m], x0[m]));
+        x1[m] = fma(dt, acc, x1[m]);
+      });
+    } else {
+      predict_state(dt);
+      if (rec.type == EV_GPS) gps_update(mc, u);
+    }
+    v = chain_det();
+  }
+  // the non-lean interface of the ring kernel (per-step outputs)
+  __device__ __forceinline__ void predict(real dt, const ModelConst& mc) {
+    predict_cov(dt, mc);
+    predict_state(dt);
+  }
+  __device__ __forceinline__ double update(real dt, const ModelConst& mc, int ty, const real* u, bool& ok) {
+    if (ty == EV_IMU) {
+      const real e = real(mc.c2) * (dt * dt);
+      members([&](auto Bm, int m) {
+        using BM = decltype(Bm);
+        x0[m] = fma(e, u[BM::pz(0)], x0[m]);
+        x1[m] = fma(dt, u[BM::pz(0)], x1[m]);
+      });
+    } else if (ty == EV_GPS) {
+      gps_update(mc, u);
+    }
+    return det(ok);
+  }
+};
+
+// the control-input ring filter of a model: the three-state or the two-state form, by the shape of its first chain
+template <typename real, class B0, class... Bs>
+struct CtrlSymSelect {
+  using type = std::conditional_t<is_vr2c<B0>(), Sym2CtrlFilter<real, B0, Bs...>, Sym3CtrlFilter<real, B0, Bs...>>;
+};
+
+// --------------------------------------------------------------------------------------
 // SymCAFilter: the lean form of the reference's OWN models (kf_workers.py:493-614 CA15, hw5_2.py:219-304 CA8):
 // ML identical (position, velocity, acceleration) chains + MA identical (angle, rate) chains, every state
 // measured by the IMU event (pseudo-measurement [X, V, a] on the linear chains, direct on the angular ones,
@@ -2190,7 +2346,7 @@ struct ChainIndex {
     using Filter = FilterT<real, CTRL, __VA_ARGS__>;                           \
     using Dec2 = Dec2Filter<real, __VA_ARGS__>;                                \
     using Sym2 = Sym2Filter<real, __VA_ARGS__>;                                \
-    using Sym3 = Sym3CtrlFilter<real, __VA_ARGS__>;                            \
+    using Sym3 = typename CtrlSymSelect<real, __VA_ARGS__>::type;              \
     using SymCA = SymCAFilter<real, typename CALists<ID>::Lin, typename CALists<ID>::Ang>; \
     static constexpr int chain_of(int g) { return ChainIndex<__VA_ARGS__>::of(g); } \
   };                                                                           \
@@ -2201,7 +2357,7 @@ struct ChainIndex {
     using Filter = FilterT<real, CTRL, Union<__VA_ARGS__>>;                    \
   };
 
-enum : int { MODEL_CV6 = 0, MODEL_CA8 = 1, MODEL_BIAS9 = 2, MODEL_CA15 = 3, MODEL_COUNT = 4 };
+enum : int { MODEL_CV6 = 0, MODEL_CA8 = 1, MODEL_BIAS9 = 2, MODEL_CA15 = 3, MODEL_CVBU6 = 4, MODEL_COUNT = 5 };
 
 template <>
 struct CALists<MODEL_CA8> {
@@ -2217,6 +2373,7 @@ struct CALists<MODEL_CA15> {
 B200KF_DEFINE_MODEL(MODEL_CV6, 6, 3, 3, false, CV6Chain<0>, CV6Chain<1>, CV6Chain<2>)
 B200KF_DEFINE_MODEL(MODEL_CA8, 8, 4, 2, false, CA8LinChain<0>, CA8LinChain<1>, CA8YawChain)
 B200KF_DEFINE_MODEL(MODEL_BIAS9, 9, 3, 3, true, BIAS9Chain<0>, BIAS9Chain<1>, BIAS9Chain<2>)
+B200KF_DEFINE_MODEL(MODEL_CVBU6, 6, 3, 3, true, CVBU6Chain<0>, CVBU6Chain<1>, CVBU6Chain<2>)
 B200KF_DEFINE_MODEL(MODEL_CA15, 15, 9, 3, false, CA15LinChain<0>, CA15LinChain<1>, CA15LinChain<2>,
                     CA15AngChain<0>, CA15AngChain<1>, CA15AngChain<2>)
 
@@ -2235,6 +2392,10 @@ struct SymTraits<MODEL_CA8, real> {
 template <typename real>
 struct SymTraits<MODEL_BIAS9, real> {
   using Filter = FilterT<real, true, SymGroup<BIAS9Chain<0>, BIAS9Chain<1>, BIAS9Chain<2>>>;
+};
+template <typename real>
+struct SymTraits<MODEL_CVBU6, real> {
+  using Filter = FilterT<real, true, SymGroup<CVBU6Chain<0>, CVBU6Chain<1>, CVBU6Chain<2>>>;
 };
 template <typename real>
 struct SymTraits<MODEL_CA15, real> {

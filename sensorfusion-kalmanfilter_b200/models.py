@@ -1,7 +1,7 @@
 """Model descriptors: the VALUES behind the reference's eight model getters.
 
 The CUDA kernels compile in the state layout and the sparsity of F(dt), H and the diagonal shape
-of Q(dt), R for four models (CV6, CA8, BIAS9, CA15); the rate constants are data.
+of Q(dt), R for five models (CV6, CA8, BIAS9, CA15, CVBU6); the rate constants are data.
 `spec_from_getters` turns a `KF_SensorFusion`-like object into a descriptor by CALLING its getters
 (kf_workers.py:493-621 / hw5_2.py:219-311) -- so a subclass that overrides Q or R changes the GPU
 results, and one that leaves the compiled family (dense Q, different F sparsity, non-selector H)
@@ -16,8 +16,8 @@ import numpy as np
 from . import _lib
 
 MODEL_IDS = {"CV6": _lib.MODEL_CV6, "CA8": _lib.MODEL_CA8, "BIAS9": _lib.MODEL_BIAS9,
-             "CA15": _lib.MODEL_CA15}
-DIMS = {"CV6": (6, 3, 3), "CA8": (8, 4, 2), "BIAS9": (9, 3, 3), "CA15": (15, 9, 3)}  # n, d, m_gps
+             "CA15": _lib.MODEL_CA15, "CVBU6": _lib.MODEL_CVBU6}
+DIMS = {"CV6": (6, 3, 3), "CA8": (8, 4, 2), "BIAS9": (9, 3, 3), "CA15": (15, 9, 3), "CVBU6": (6, 3, 3)}  # n, d, m_gps
 
 # chains: groups of state indices that F, H, Q, R never couple (csrc/kf_core.cuh)
 CHAINS = {
@@ -25,6 +25,7 @@ CHAINS = {
     "CA8": [(0, 3, 6), (1, 4, 7), (2, 5)],
     "BIAS9": [(0, 3, 6), (1, 4, 7), (2, 5, 8)],
     "CA15": [(0, 6, 12), (1, 7, 13), (2, 8, 14), (3, 9), (4, 10), (5, 11)],
+    "CVBU6": [(0, 3), (1, 4), (2, 5)],
 }
 
 
@@ -55,7 +56,7 @@ class ModelSpec:
 
     @property
     def imu_is_control(self):
-        return self.name == "BIAS9"
+        return self.name in ("BIAS9", "CVBU6")
 
     def default_P0(self):
         """Cold-start covariance of the reference (kf_workers.py:651, hw5_2.py:317-326)."""
@@ -80,18 +81,21 @@ _P0_DIAG = {
     "CA8": [1000, 1000, 100, 100, 100, 100, 1000, 1000],
     "BIAS9": [1e4] * 3 + [1e3] * 3 + [1e4] * 3,
     "CA15": [1e4] * 3 + [1e3] * 3 + [1e3] * 3 + [1e3] * 3 + [1e4] * 3,
+    "CVBU6": [1e4] * 3 + [1e3] * 3,
 }
 _Q = {
     "CV6": [5] * 3 + [1] * 3,
     "CA8": [5, 5, 0.05, 1, 1, 0.1, 2, 2],
     "BIAS9": [5] * 3 + [1] * 3 + [2] * 3,
     "CA15": [5] * 3 + [0.05] * 3 + [1] * 3 + [0.1] * 3 + [2] * 3,
+    "CVBU6": [5] * 3 + [1] * 3,
 }
 _R_IMU = {
     "CV6": [50] * 3 + [10] * 3,
     "CA8": [50, 50, 0.05, 10, 10, 0.1, 100, 100],
     "BIAS9": [0] * 9,
     "CA15": [50] * 3 + [0.05] * 3 + [10] * 3 + [0.1] * 3 + [100] * 3,
+    "CVBU6": [0] * 6,
 }
 
 

@@ -33,7 +33,7 @@ def make_case(name, N, T, seed, dense_P0=False):
     return m, types, dts, payload, x0, P0
 
 
-@pytest.mark.parametrize("name", ["CV6", "CA8", "BIAS9", "CA15"])
+@pytest.mark.parametrize("name", ["CV6", "CA8", "BIAS9", "CA15", "CVBU6"])
 @pytest.mark.parametrize("mode", ["decoupled", "dense", "auto", "symmetric", "shared"])
 def test_run_batch_f64_matches_oracle(name, mode):
     from sensorfusion_kalmanfilter_b200.engine import Engine
@@ -57,7 +57,7 @@ def test_run_batch_f64_matches_oracle(name, mode):
     np.testing.assert_allclose(out2["agg"].cpu().numpy(), agg, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["CV6", "CA15", "BIAS9"])
+@pytest.mark.parametrize("name", ["CV6", "CA15", "BIAS9", "CVBU6"])
 def test_dense_P0_uses_dense_kernel_and_matches(name):
     """An arbitrary dense initial covariance must take the dense path in auto mode."""
     from sensorfusion_kalmanfilter_b200.engine import Engine
@@ -78,7 +78,7 @@ def test_dense_P0_uses_dense_kernel_and_matches(name):
     assert rel(out1["P"].cpu().numpy(), ref1["P"]) < RTOL64
 
 
-@pytest.mark.parametrize("name", ["CV6", "BIAS9", "CA15"])
+@pytest.mark.parametrize("name", ["CV6", "BIAS9", "CA15", "CVBU6"])
 def test_run_batch_f32_mode(name):
     from sensorfusion_kalmanfilter_b200.engine import Engine
     N, T = 64, 300
@@ -92,7 +92,7 @@ def test_run_batch_f32_mode(name):
     assert np.max(np.abs(ld - ref["logdet"]) / np.maximum(1.0, np.abs(ref["logdet"]))) < RTOL32
 
 
-@pytest.mark.parametrize("name", ["CV6", "BIAS9"])
+@pytest.mark.parametrize("name", ["CV6", "BIAS9", "CVBU6"])
 def test_f32_lean_aggregate_over_a_long_launch(name):
     """The float32 ring kernels keep the log-det aggregate in float32 (running mantissa product + integer
     exponent sum): over 30 000 steps max / sum / last must still agree with the float64 path (itself checked
@@ -312,7 +312,7 @@ def test_axis_symmetric_kernel_matches_per_chain_kernel_and_oracle(monkeypatch):
     assert rel(out2["x"].cpu().numpy(), ref2["x"]) < RTOL64
 
 
-@pytest.mark.parametrize("name", ["CV6", "CA15", "BIAS9", "CA8"])
+@pytest.mark.parametrize("name", ["CV6", "CA15", "BIAS9", "CA8", "CVBU6"])
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 def test_shared_covariance_kernel_matches_symmetric_kernel_and_oracle(name, precision, monkeypatch):
     """All filters start from the SAME P (Monte-Carlo seeds of one configuration): AUTO runs the
@@ -354,7 +354,7 @@ def test_shared_covariance_kernel_matches_symmetric_kernel_and_oracle(name, prec
     assert np.max(np.abs(a[:, :3] - ref1["agg"]) / np.maximum(1.0, np.abs(ref1["agg"]))) < tol
 
 
-@pytest.mark.parametrize("name", ["CV6", "CA15", "BIAS9", "CA8"])
+@pytest.mark.parametrize("name", ["CV6", "CA15", "BIAS9", "CA8", "CVBU6"])
 def test_shared_covariance_chunked_continuation_and_predict_only(name):
     from sensorfusion_kalmanfilter_b200.engine import Engine
     N, T = 900, 240
@@ -382,7 +382,7 @@ def test_ring_kernels_at_every_cta_size(N, monkeypatch):
     launch of each size class, per-filter covariance and shared covariance, against the oracle."""
     from sensorfusion_kalmanfilter_b200.engine import Engine
     T = 45
-    for name in ("CV6", "BIAS9"):
+    for name in ("CV6", "BIAS9", "CVBU6"):
         m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=51)
         ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
         # AUTO keeps shards below the 896-filter CTA regime on the per-filter ring kernel: force the
@@ -403,7 +403,7 @@ def test_ring_kernels_at_every_cta_size_f32(N, monkeypatch):
     records and the lean aggregate are float32), against the oracle at the float32 tolerance."""
     from sensorfusion_kalmanfilter_b200.engine import Engine
     T = 45
-    for name in ("CV6", "BIAS9"):
+    for name in ("CV6", "BIAS9", "CVBU6"):
         m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=53)
         ref = ko.run_batch(m, types, dts, payload, x0, P0, want_traj=False)
         for mode, shared in (("shared", "1"), ("auto", "0")):
@@ -465,7 +465,7 @@ def test_zero_measurement_variance_stays_exact():
         assert np.max(np.abs(out["P"].cpu().numpy() - refp["P"])) < 1e-9 * np.max(np.abs(refp["P"]) + 1.0)
 
 
-@pytest.mark.parametrize("name,N", [("CV6", 2000), ("CV6", 33), ("CA15", 2000), ("BIAS9", 900)])
+@pytest.mark.parametrize("name,N", [("CV6", 2000), ("CV6", 33), ("CA15", 2000), ("BIAS9", 900), ("CVBU6", 700)])
 def test_step_rows_reads_a_selection_in_place(name, N, monkeypatch):
     """b200kf_run_batch_rows: step k reads payload row step_rows[k] of a longer stream (what the scheduled
     filter does with its selected events).  Same bits as a launch on the gathered copy, on every kernel family
@@ -501,7 +501,7 @@ def test_output_ring_bulk_stores_match_per_thread_stores_and_oracle(precision, N
     from sensorfusion_kalmanfilter_b200.engine import Engine
     T = 53
     tol = RTOL64 if precision == "f64" else RTOL32
-    for name in ("CV6", "BIAS9"):
+    for name in ("CV6", "BIAS9", "CVBU6"):
         m, types, dts, payload, x0, P0 = make_case(name, N, T, seed=61)
         pick = np.unique(np.concatenate([np.arange(0, N, max(1, N // 37)), [N - 1]]))
         ref = ko.run_batch(m, types, dts, payload[:, :, pick], x0[pick], P0[pick])

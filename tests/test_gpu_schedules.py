@@ -90,7 +90,7 @@ def test_sharded_ranges_reduce_to_the_same_answer(brute):
     assert merged["argmin_sum_score"] == full["argmin_sum_score"]
 
 
-@pytest.mark.parametrize("name", ["CV6", "BIAS9", "CA8"])
+@pytest.mark.parametrize("name", ["CV6", "BIAS9", "CA8", "CVBU6"])
 def test_other_models_match_oracle(name):
     from sensorfusion_kalmanfilter_b200.engine import Engine
     m = ko.get_model(name)

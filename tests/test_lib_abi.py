@@ -42,7 +42,7 @@ def test_version_and_default_desc():
     np.testing.assert_array_equal(np.array(d.r_imu[:15]), spec.r_imu)
     np.testing.assert_array_equal(np.array(d.r_gps[:3]), spec.r_gps)
     assert d.accel_coef == 0.5
-    for name in ("CV6", "CA8", "BIAS9"):
+    for name in ("CV6", "CA8", "BIAS9", "CVBU6"):
         _lib.check(lib.b200kf_model_default_desc(models.MODEL_IDS[name], _lib.F64, ctypes.byref(d)))
         s = models.default_spec(name)
         np.testing.assert_array_equal(np.array(d.q[:s.n]), s.q)

@@ -71,7 +71,7 @@ def test_spec_from_getters_rejects_models_outside_the_family():
 
 
 def test_chain_compatible():
-    for name in ("CV6", "CA8", "BIAS9", "CA15"):
+    for name in ("CV6", "CA8", "BIAS9", "CA15", "CVBU6"):
         m = ko.get_model(name)
         assert models.chain_compatible(name, m.P0())
         P = m.P0().copy()
@@ -89,7 +89,7 @@ def test_packer_matches_oracle_payload():
     ev = synth.make_indexed_sensor_data(120, seed=3)
     ps = streams.pack_events(ev)
     assert streams.pack_events(ev) is ps  # cached
-    for name in ("CA15", "CA8", "CV6", "BIAS9"):
+    for name in ("CA15", "CA8", "CV6", "BIAS9", "CVBU6"):
         m = ko.get_model(name)
         pay = ps.payload(name)
         for k in (0, 3, 4, 57, 119):
@@ -154,7 +154,7 @@ def test_shard_range_and_merge():
 
 def test_axis_symmetric():
     from sensorfusion_kalmanfilter_b200.models import axis_symmetric, default_spec
-    for name in ("CV6", "CA8", "BIAS9", "CA15"):
+    for name in ("CV6", "CA8", "BIAS9", "CA15", "CVBU6"):
         P = default_spec(name).default_P0()
         assert axis_symmetric(name, P) and axis_symmetric(name, np.stack([P, 2 * P]))
         Q = P.copy()
