@@ -376,8 +376,27 @@ constexpr int kWsThreads = kTmaThreads + 32;  // + the producer warp (928 * 64 r
 #ifndef B200KF_STAGES
 #define B200KF_STAGES 5
 #endif
-constexpr int kChunk = B200KF_CHUNK;    // steps per stage
-constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 KB of shared memory)
+constexpr int kChunk = B200KF_CHUNK;    // float32 launches: steps per stage
+constexpr int kStages = B200KF_STAGES;  // float32 launches: ring depth (kStages * kChunk * d * 7 KB of shared memory)
+// float64 launches take 3 stages of 3 steps (and three copy warps): at the power-capped clock the lean float64 loop is
+// bound by its instruction issue, and a chunk costs every warp a try_wait + an arrive -- one per three steps instead
+// of one per two is 3-4 % of the loop (headline 0.86 -> 0.89 at 1 470 MHz, 0.92 -> 0.95 at 1 580 MHz on the same boxes;
+// CA15 / CA8 aggregate + 2-3 %).  The float32 rings keep 5 x 2 and four copy warps: their copy lanes are the bound
+// (BIAS9 f32 loses 9 % with three).
+#ifndef B200KF_STAGES_F64
+#define B200KF_STAGES_F64 3
+#endif
+#ifndef B200KF_CHUNK_F64
+#define B200KF_CHUNK_F64 3
+#endif
+template <typename real>
+constexpr int base_stages() {
+  return sizeof(real) == 8 ? B200KF_STAGES_F64 : B200KF_STAGES;
+}
+template <typename real>
+constexpr int base_chunk() {
+  return sizeof(real) == 8 ? B200KF_CHUNK_F64 : B200KF_CHUNK;
+}
 // Ring shape of the per-filter kernel.  The ring always holds the same BYTES (kStages * kChunk steps of
 // 896 float64 filters, ~215 KB for d = 3): a CTA with fewer filters, or float32 payload, gets
 // proportionally more steps.  Those go into LONGER chunks first (up to B200KF_MAX_CHUNK steps per stage):
@@ -391,11 +410,11 @@ constexpr int kStages = B200KF_STAGES;  // ring depth (kStages * kChunk * d * 7 
 // acceleration models carry 4 / 9 columns and get the same bytes: fewer steps, at least kCopyWarps stages)
 template <typename real, int F, int D = 3>
 constexpr int ring_steps() {
-  return kStages * kChunk * (896 / F) * (sizeof(real) == 4 ? 2 : 1) * 3 / D;
+  return base_stages<real>() * base_chunk<real>() * (896 / F) * (sizeof(real) == 4 ? 2 : 1) * 3 / D;
 }
 template <typename real, int F, int D = 3>
 constexpr int ring_chunk() {
-  constexpr int want = ring_steps<real, F, D>() / kStages;
+  constexpr int want = ring_steps<real, F, D>() / base_stages<real>();
   return want < 1 ? 1 : (want < B200KF_MAX_CHUNK ? want : B200KF_MAX_CHUNK);
 }
 template <typename real, int F, int D = 3>
@@ -485,9 +504,13 @@ constexpr int bulk_out_stages() {
   return D <= 3 ? 3 : B200KF_BULK_OUT_STAGES;
 }
 constexpr int kBulkMaxRows = 8;
+#ifndef B200KF_BULK_CHUNK_D4
+#define B200KF_BULK_CHUNK_D4 1
+#endif
 template <typename real, int F, int D = 3>
 constexpr int bulk_chunk() {
   constexpr int c = (896 / F) * (sizeof(real) == 4 ? 2 : 1) * 3 / D;
+  if (D == 4) return (c < 1 ? 1 : c) * B200KF_BULK_CHUNK_D4;  // four-column payload (CA8): room for longer chunks
   return c < 1 ? 1 : c;
 }
 
@@ -618,14 +641,19 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
 #ifndef B200KF_COPY_WARPS
 #define B200KF_COPY_WARPS 4
 #endif
-constexpr int kCopyWarps = B200KF_COPY_WARPS;
+constexpr int kCopyWarps = B200KF_COPY_WARPS;  // float32 launches
+#ifndef B200KF_COPY_WARPS_F64
+#define B200KF_COPY_WARPS_F64 3
+#endif
 // service warps of a model's per-filter ring kernel.  The constant-acceleration filter (24 state / covariance values
 // per thread) gets two: 448 math threads + 64 = 512 threads leave 128 registers per thread (576 threads round to 96),
 // and its FP64-bound loop (~160 FP64 instructions against 9 bulk copies per step) needs no more copy lanes.
 template <int MODEL, typename real>
 constexpr int svc_warps() {
   using MT = ModelTraits<MODEL, false, real>;
-  return (!MT::Filter::fast2 && !MT::Sym3::eligible && MT::SymCA::eligible) ? 2 : kCopyWarps;
+  return (!MT::Filter::fast2 && !MT::Sym3::eligible && MT::SymCA::eligible)
+             ? 2
+             : (sizeof(real) == 8 ? B200KF_COPY_WARPS_F64 : kCopyWarps);
 }
 
 template <int MODEL, typename real, bool SYM, bool FULL, int F, bool BULK = false>
@@ -978,13 +1006,13 @@ struct GainRecT {  // 56 bytes in float64, 32 in float32: the gain warp rounds o
 // (same reasoning as SharedRing / ring_chunk), 224-filter CTAs half the bytes so that two share an SM
 template <typename real, int F>
 constexpr int shared_chunk() {
-  return b200kf::kChunk * (sizeof(real) == 4 ? 2 : 1) * (F == 896 ? 1 : 2);
+  return base_chunk<real>() * (sizeof(real) == 4 ? 2 : 1) * (F == 896 ? 1 : 2);
 }
 
 template <int MODEL, typename real, bool FULL, int F>
 __global__ void __launch_bounds__(F + 64, F == 224 ? 2 : 1) kf_run_shared_kernel(const RunParams p) {
   constexpr int kMathThreads = F;
-  constexpr int kStages = b200kf::kStages;
+  constexpr int kStages = base_stages<real>();
   constexpr int kChunk = shared_chunk<real, F>();
   using GainRec = GainRecT<real>;
   using MT = ModelTraits<MODEL, false, real>;
@@ -1675,7 +1703,7 @@ constexpr size_t shared_generic_smem_bytes() {
 template <int MODEL, typename real, int F>
 constexpr size_t shared_smem_bytes() {
   using MT = ModelTraits<MODEL, false, real>;
-  constexpr int st = kStages, ch = shared_chunk<real, F>();
+  constexpr int st = base_stages<real>(), ch = shared_chunk<real, F>();
   // (the gain records are padded to whole doubles so that the aggregates behind them stay 8-byte aligned)
   return static_cast<size_t>(st) * ch * MT::d * F * sizeof(real) +
          ((static_cast<size_t>(st) * ch * sizeof(GainRecT<real>) + 7) / 8) * 8 + 8 * sizeof(double) +
