@@ -599,7 +599,7 @@ __device__ __forceinline__ void ring_copy_loop(real* stage_buf, unsigned long lo
   // step_rows (a selection of a longer stream): the row indices of this lane's NEXT chunk are fetched before the
   // wait for the current one, so the global-load latency (~0.5 us, once per chunk on the lane's serial path: it
   // capped a launch at ~2.5 steps/us = 725 GB/s whatever the CTA count) hides behind the wait and the copies
-  int rows_nx[CH];
+  int rows_nx[CH] = {};
   auto fetch_rows = [&](int chunk) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) rows_nx[c] = (chunk * CH + c < T) ? __ldg(step_rows + chunk * CH + c) : 0;
