@@ -204,6 +204,19 @@ int b200kf_score_schedules(const b200kf_model* model, int32_t n_events, const ui
                            uint64_t first, uint64_t count, double threshold, double initial_logdet,
                            double* per_schedule, b200kf_best* best, uint32_t flags, void* stream);
 
+/* The same search over the schedules that SHARE their n_low earliest decisions: schedule
+ * s = low_bits | (j << n_low) for j in [first, first + count), j < 2^(n_events - n_low); per_schedule
+ * rows are indexed by j - first, every index in `best` is the full schedule s.  This is how the
+ * enumeration of run_brute_force_kalman_filter_no_sampling_min_usage (kf_workers.py:1325-1371)
+ * is split over workers of EQUAL cost: the fixed early events are filtered once per thread,
+ * whereas a contiguous index range fixes the LATEST events, which every schedule pays on its own
+ * (8 ranges of a 2^32 search: 16.4 ... 23.9 ms).  n_low = 0 is b200kf_score_schedules. */
+int b200kf_score_schedules_strided(const b200kf_model* model, int32_t n_events, const uint8_t* types,
+                                   const double* times, double t_prev, double t_end, const double* P0,
+                                   uint64_t low_bits, int32_t n_low, uint64_t first, uint64_t count,
+                                   double threshold, double initial_logdet, double* per_schedule,
+                                   b200kf_best* best, uint32_t flags, void* stream);
+
 /* The brute-force worker WITH state: replaces evaluate_combo_chunk_worker (kf_workers.py:22-97)
  * for n_schedules combos that are subsets of one shared window of n_events <= 64 time-ordered
  * events.  Schedule f uses event i iff bit i of masks[f] is set.  Float64 only.

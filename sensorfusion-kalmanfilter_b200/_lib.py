@@ -67,6 +67,9 @@ SIGNATURES = {
     "b200kf_score_schedules": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), c_double,
                                        c_double, POINTER(c_double), c_uint64, c_uint64, c_double,
                                        c_double, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b200kf_score_schedules_strided": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), c_double,
+                                               c_double, POINTER(c_double), c_uint64, c_int32, c_uint64, c_uint64,
+                                               c_double, c_double, c_void_p, c_void_p, c_uint32, c_void_p]),
     "b200kf_run_masked": (c_int, [c_void_p, c_int32, POINTER(c_uint8), POINTER(c_double), POINTER(c_double),
                                   c_double, c_double, POINTER(c_double), POINTER(c_double), c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_uint32, c_void_p]),

@@ -803,18 +803,23 @@ done:
   return rc;
 }
 
-int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_t* types,
-                           const double* times, double t_prev, double t_end, const double* P0,
-                           uint64_t first, uint64_t count, double threshold, double initial_logdet,
-                           double* per_schedule, b200kf_best* best, uint32_t flags, void* stream) {
+int b200kf_score_schedules_strided(const b200kf_model* m, int32_t n_events, const uint8_t* types,
+                                   const double* times, double t_prev, double t_end, const double* P0,
+                                   uint64_t low_bits, int32_t n_low, uint64_t first, uint64_t count,
+                                   double threshold, double initial_logdet, double* per_schedule,
+                                   b200kf_best* best, uint32_t flags, void* stream) {
   if (!m) return set_error(B200KF_ERR_INVALID, "model is null");
   if (n_events < 1 || n_events > kMaxEvents)
     return set_error(B200KF_ERR_UNSUPPORTED, "n_events must be in [1, %d]", kMaxEvents);
   if (!types || !times || !P0 || !best) return set_error(B200KF_ERR_INVALID, "null argument");
-  const uint64_t total = 1ULL << n_events;
+  if (n_low < 0 || n_low > n_events || (low_bits >> n_low) != 0)
+    return set_error(B200KF_ERR_INVALID, "n_low must be in [0, n_events] and low_bits < 2^n_low");
+  const uint64_t total = 1ULL << (n_events - n_low);  // schedules that share these low bits
   if (first > total || count > total - first)
-    return set_error(B200KF_ERR_INVALID, "schedule range exceeds 2^n_events");
+    return set_error(B200KF_ERR_INVALID, "schedule range exceeds 2^(n_events - n_low)");
   ScoreParams p;
+  p.low_bits = low_bits;
+  p.n_low = n_low;
   p.mc = m->mc;
   p.n_events = n_events;
   memset(p.types, 0, sizeof(p.types));
@@ -843,6 +848,14 @@ int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_
   score_final_kernel<<<1, 256, 0, st>>>(static_cast<const ScorePartial*>(p.partials), blocks, n_events, best);
   B200KF_CUDA_TRY(cudaGetLastError());
   return B200KF_OK;
+}
+
+int b200kf_score_schedules(const b200kf_model* m, int32_t n_events, const uint8_t* types,
+                           const double* times, double t_prev, double t_end, const double* P0,
+                           uint64_t first, uint64_t count, double threshold, double initial_logdet,
+                           double* per_schedule, b200kf_best* best, uint32_t flags, void* stream) {
+  return b200kf_score_schedules_strided(m, n_events, types, times, t_prev, t_end, P0, 0, 0, first, count, threshold,
+                                        initial_logdet, per_schedule, best, flags, stream);
 }
 
 int b200kf_run_masked(const b200kf_model* m, int32_t n_events, const uint8_t* types, const double* times,

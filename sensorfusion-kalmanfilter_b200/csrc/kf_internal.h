@@ -101,6 +101,10 @@ struct ScoreParams {
   const int* dense_flag;
   unsigned long long out_base;  // first schedule of the API call (a call may be split into several launches)
   int tree_a, tree_k;           // prefix-sharing kernel: [first, first + 2^tree_a) aligned block, DFS over its top tree_k bits
+  // Strided enumeration (b200kf_score_schedules_strided): first / count / out_base / tree_a index j, and the schedule
+  // is s = low_bits | (j << n_low) -- the EARLIEST n_low events are fixed, the way a sharded search splits the space
+  unsigned long long low_bits;
+  int n_low;
 };
 
 constexpr int kMaxMaskedEvents = 64;

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
 
   for (unsigned long long idx = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
        idx < p.count; idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-    const unsigned long long s = p.first + idx;
+    const unsigned long long j = p.first + idx;
+    const unsigned long long s = p.low_bits | (j << p.n_low);
     typename MT::Filter flt;
     flt.each([&](auto& b) { b.load_cov(p.P0, n); });
     bool ok = true;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
     }
     if (!ok) mx = sm = lastv = NAN;
     if (p.per_schedule != nullptr) {
-      double* o = p.per_schedule + (s - p.out_base) * 4;
+      double* o = p.per_schedule + (j - p.out_base) * 4;
       o[0] = mx;
       o[1] = sm;
       o[2] = lastv;
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
   const int L = p.n_events;
   const int a = p.tree_a, k = p.tree_k;
   const int npre = a - k;  // events decided by the thread index
+  const int nl = p.n_low;  // events fixed for the whole call (strided enumeration): walked once per thread, first
   const double near_tol = 1e-9 * fmax(1.0, fabs(p.threshold));
   const bool host_ld0 = !isnan(p.initial_logdet);
 
@@ -238,20 +240,23 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
     ok = true;
     if (!host_ld0) acc.add(filter_det(flt, ok));  // log_det[0], kf_workers.py:32
     tcur = p.t_prev;
+    for (int i = 0; i < nl; ++i)
+      if ((p.low_bits >> i) & 1ULL) apply(i);
     for (int i = 0; i < npre; ++i)
-      if ((t >> i) & 1ULL) apply(i);
+      if ((t >> i) & 1ULL) apply(nl + i);
     save(0);
     const unsigned n_leaf = 1u << k;
     for (unsigned c = 0; c < n_leaf; ++c) {
       const int lvl0 = (c == 0) ? 0 : (k - 1 - (__ffs(c) - 1));  // first level whose decision changed
       if (c != 0) restore(lvl0);
       for (int lv = lvl0; lv < k; ++lv) {
-        if ((c >> (k - 1 - lv)) & 1u) apply(npre + lv);
+        if ((c >> (k - 1 - lv)) & 1u) apply(nl + npre + lv);
         if (lv + 1 < k) save(lv + 1);
       }
       const unsigned long long m = (k > 0) ? (static_cast<unsigned long long>(__brev(c)) >> (32 - k)) : 0ULL;
-      const unsigned long long s = p.first | t | (m << npre);
-      for (int i = a; i < L; ++i)
+      const unsigned long long j = p.first | t | (m << npre);
+      const unsigned long long s = p.low_bits | (j << nl);
+      for (int i = a + nl; i < L; ++i)
         if ((s >> i) & 1ULL) apply(i);
       if (tcur < p.t_end - 1e-8) {  // kf_workers.py:74-82
         const double dt = p.t_end - tcur;
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
       }
       if (!ok) mx = sm = lastv = NAN;
       if (p.per_schedule != nullptr) {
-        double* o = p.per_schedule + (s - p.out_base) * 4;
+        double* o = p.per_schedule + (j - p.out_base) * 4;
         o[0] = mx;
         o[1] = sm;
         o[2] = lastv;

@@ -1,7 +1,9 @@
-"""Multi-GPU plumbing: one process per GPU, contiguous sharding, one tiny final collective.
+"""Multi-GPU plumbing: one process per GPU, sharding by index range (filters) or by the earliest decisions
+(schedules), one tiny final collective.
 
 The path shards naturally: filters are independent, and so are candidate
-schedules, so rank r owns a contiguous index range and nothing is exchanged during compute.  The
+schedules, so rank r owns a contiguous range of filters, or the schedules whose earliest decisions spell r
+(shard_strided), and nothing is exchanged during compute.  The
 reference's own "parallelism" is a `multiprocessing.Pool(30)` whose chunks are awaited one by one
 (kf_workers.py:1333-1346).  The only collective here is the end-of-search all-gather of each
 rank's `b200kf_best` (48 bytes) followed by the same deterministic reduce on every rank -- an
@@ -103,15 +105,39 @@ def allgather_best_device(best_d, group=None):
     return merge_best([Engine.best_from_bytes(raw[r].tobytes()) for r in range(world)])
 
 
+def shard_strided(n_events: int, world_size: int, rank: int):
+    """(low_bits, n_low) of rank `rank`'s slice of the 2^n_events subset schedules, or None.
+
+    A schedule's cost grows with the events it uses, and the prefix-sharing kernel pays the events ABOVE an aligned
+    index block once per schedule: with one contiguous range per rank, the rank whose top bits are all ones works
+    1.46 x as long as rank 0 (8 ranks, 2^32 schedules: 23.9 vs 16.4 ms, tools/search_shard_probe.py), and finer
+    contiguous blocks only fix more late events (8 complementary blocks per rank: 28.1 ms).  Fixing the EARLIEST
+    log2(world) decisions instead costs nothing per schedule (they are filtered once per thread, before the shared
+    prefix) and every rank walks the same tree over the remaining events.  None when the world size is not a
+    power of two or the window is too short: contiguous ranges then."""
+    world_size, rank = int(world_size), int(rank)
+    if world_size <= 1 or (world_size & (world_size - 1)) != 0:
+        return None
+    n_low = world_size.bit_length() - 1
+    if n_low > int(n_events):
+        return None
+    return rank, n_low
+
+
 def search_sharded(engine, types, times, t_prev, t_end, P0, threshold, group=None, **kw):
-    """Brute-force search of all 2^L subset schedules sharded over the ranks of `group`: contiguous index
-    ranges, no exchange during the search, one 48-byte all-gather at the end."""
+    """Brute-force search of all 2^L subset schedules sharded over the ranks of `group`: rank r takes the schedules
+    whose earliest log2(world) decisions spell r (equal work, shard_strided; contiguous index ranges for other
+    world sizes), no exchange during the search, one 48-byte all-gather at the end."""
     import torch.distributed as dist
     L = len(types)
     rank, world = 0, 1
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-    first, count = shard_range(1 << L, world, rank)
-    best_d, _ = engine.score_schedules(types, times, t_prev, t_end, P0, first=first, count=count,
-                                       threshold=threshold, device_result=True, **kw)
+    strided = shard_strided(L, world, rank)
+    if strided is not None:
+        kw = dict(kw, low_bits=strided[0], n_low=strided[1], first=0, count=None)
+    else:
+        first, count = shard_range(1 << L, world, rank)
+        kw = dict(kw, first=first, count=count)
+    best_d, _ = engine.score_schedules(types, times, t_prev, t_end, P0, threshold=threshold, device_result=True, **kw)
     return allgather_best_device(best_d, group=group)

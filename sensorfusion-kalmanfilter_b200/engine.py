@@ -193,8 +193,10 @@ class Engine:
     # ------------------------------------------------------------------ schedule search
     def score_schedules(self, types, times, t_prev, t_end, P0, *, first=0, count=None,
                         threshold=float("inf"), initial_logdet=None, want_per_schedule=False, mode="auto",
-                        stream=None, device_result=False):
+                        stream=None, device_result=False, low_bits=0, n_low=0):
         """Score the subset schedules [first, first+count) of a window (b200kf_score_schedules).
+        With n_low > 0 (b200kf_score_schedules_strided) the range indexes j and the schedules are
+        low_bits | (j << n_low): the slice of the search whose n_low earliest decisions are low_bits.
         initial_logdet: the caller's sign*logabsdet of P0 used verbatim as term 0 (exact ties with
         a threshold derived from it resolve as in the reference); None computes it on the device.
         Returns (best: dict, per_schedule: torch [count,4] or None).  With device_result=True `best` is the
@@ -206,13 +208,14 @@ class Engine:
         P0 = np.ascontiguousarray(P0, dtype=np.float64)
         L = int(types.shape[0])
         if count is None:
-            count = (1 << L) - first
+            count = (1 << (L - int(n_low))) - first
         per = torch.empty((count, 4), dtype=torch.float64, device=self.device) if want_per_schedule else None
         best_d = torch.zeros((ctypes.sizeof(_lib.Best),), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.b200kf_score_schedules(
+            _lib.check(self.lib.b200kf_score_schedules_strided(
                 self._h, L, types.ctypes.data_as(POINTER(c_uint8)), times.ctypes.data_as(POINTER(c_double)),
-                float(t_prev), float(t_end), P0.ctypes.data_as(POINTER(c_double)), int(first), int(count),
+                float(t_prev), float(t_end), P0.ctypes.data_as(POINTER(c_double)), int(low_bits), int(n_low),
+                int(first), int(count),
                 float(threshold), float("nan") if initial_logdet is None else float(initial_logdet),
                 _ptr(per), _ptr(best_d), _MODES[mode], self._stream(stream)))
         if device_result:

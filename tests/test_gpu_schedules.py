@@ -236,6 +236,53 @@ def test_config4_full_size_properties(monkeypatch):
     assert lo_thr["argmin_sum_index"] == bt["argmin_sum_index"]  # the threshold does not enter the argmin
 
 
+@pytest.mark.parametrize("L,n_low", [(18, 1), (18, 3), (20, 3), (10, 2), (6, 6)])
+def test_strided_slices_are_bit_identical_rows_of_the_full_search(L, n_low, monkeypatch):
+    """b200kf_score_schedules_strided (the sharded search's slices: the n_low earliest decisions fixed): every slice's
+    per-schedule rows ARE the rows low | (j << n_low) of the full search, bit for bit, on the prefix-sharing kernel
+    (L - n_low >= 14) and on the flat one, for ragged sub-ranges too; the slices' results merge (the reduce every rank
+    applies after the all-gather) to the full search's answer."""
+    from sensorfusion_kalmanfilter_b200.distributed import merge_best, shard_strided
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    m = ko.get_model("CA15")
+    rng = np.random.default_rng(11)
+    types = np.where(np.arange(L) % 5 == 1, 0, 1).astype(np.uint8)
+    times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
+    P0 = m.P0() * 1e-8
+    t_prev, t_end = 999.995, float(times[-1])
+    eng = Engine("CA15")
+    _, probe = eng.score_schedules(types, times, t_prev, t_end, P0, first=1, count=min(4096, (1 << L) - 1),
+                                   want_per_schedule=True)
+    thr = float(np.quantile(probe.cpu().numpy()[:, 0], 0.4))
+    full, per = eng.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, want_per_schedule=True)
+    per = per.cpu().numpy()
+    parts = []
+    for low in range(1 << n_low):
+        if L > n_low:
+            assert shard_strided(L, 1 << n_low, low) == (low, n_low)
+        b, sl = eng.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, want_per_schedule=True,
+                                    low_bits=low, n_low=n_low)
+        sl = sl.cpu().numpy()
+        idx = low | (np.arange(1 << (L - n_low), dtype=np.int64) << n_low)
+        np.testing.assert_array_equal(sl, per[idx])
+        parts.append(b)
+    merged = merge_best(parts)
+    for k in ("argmin_sum_index", "first_feasible_index", "n_feasible", "n_near_threshold", "argmin_sum_score"):
+        assert merged[k] == full[k], k
+    if L - n_low >= 8:  # a ragged sub-range of one slice (head and tail on the flat kernel around aligned tree blocks)
+        low = (1 << n_low) - 1
+        first, count = 37, (1 << (L - n_low)) - 37 - 101
+        _, sl = eng.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, want_per_schedule=True,
+                                    low_bits=low, n_low=n_low, first=first, count=count)
+        idx = low | (np.arange(first, first + count, dtype=np.int64) << n_low)
+        np.testing.assert_array_equal(sl.cpu().numpy(), per[idx])
+    with pytest.raises(Exception):
+        eng.score_schedules(types, times, t_prev, t_end, P0, low_bits=1 << n_low, n_low=n_low)
+    with pytest.raises(Exception):
+        eng.score_schedules(types, times, t_prev, t_end, P0, low_bits=0, n_low=n_low, first=0,
+                            count=(1 << (L - n_low)) + 1)
+
+
 # records of the 15- / 8-state models: 13 gain slots; one 3 x 3 and one 2 x 2 covariance (6 + 3 entries); the linear
 # block's K is row-major [3][n_meas], the angular block's [2][2] starts at slot 9
 _IR_IMU = {"CA15": ([0, 6, 12], [3, 9]), "CA8": ([0, 3, 6], [2, 5])}  # measured global states per block, in column order

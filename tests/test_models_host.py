@@ -163,3 +163,17 @@ def test_axis_symmetric():
         Q = P.copy()
         Q[0, 1] = Q[1, 0] = 0.5  # couples two chains: not even chain-compatible
         assert not axis_symmetric(name, Q)
+
+
+def test_shard_strided():
+    """Sharded subset search: power-of-two worlds fix the log2(world) earliest decisions (rank = their value);
+    other world sizes and windows shorter than that keep contiguous ranges."""
+    from sensorfusion_kalmanfilter_b200.distributed import shard_strided
+    for L, W in ((32, 8), (20, 2), (26, 4), (3, 8)):
+        got = [shard_strided(L, W, r) for r in range(W)]
+        n_low = W.bit_length() - 1
+        assert got == [(r, n_low) for r in range(W)]
+        covered = sorted(low | (j << n_low) for low, _ in got for j in range(1 << min(L - n_low, 6)))
+        assert covered == list(range(len(covered))) or L - n_low > 6
+    for L, W in ((32, 1), (32, 3), (32, 6), (2, 8)):
+        assert all(shard_strided(L, W, r) is None for r in range(W))
