@@ -838,6 +838,15 @@ int b200kf_score_schedules_strided(const b200kf_model* m, int32_t n_events, cons
   p.threshold = threshold;
   p.initial_logdet = initial_logdet;
   p.per_schedule = per_schedule;
+  {
+    const double tol = 1e-9 * fmax(1.0, fabs(threshold));
+    p.det_thr = exp(threshold);
+    p.det_lo = exp(threshold - tol);  // NaN for an infinite threshold: nothing is "near" it
+    p.det_hi = exp(threshold + tol);
+    // sum = (exponent + log2 mantissa) ln 2 (+ term 0): a schedule whose exponent + mantissa exceeds the best's by
+    // this much is larger by >= half of it in the sum, far above the rounding of either (1e-16 relative)
+    p.q_slack = 1e-9 * (1.0 + (isnan(initial_logdet) ? 0.0 : fabs(initial_logdet)));
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ScratchBuf parts;  // per call: concurrent searches on one model never share their partial results
   B200KF_CUDA_TRY(parts.alloc(m, sizeof(ScorePartial) * kMaxSearchPartials, st));

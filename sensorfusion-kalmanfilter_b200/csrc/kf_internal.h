@@ -105,6 +105,9 @@ struct ScoreParams {
   // is s = low_bits | (j << n_low) -- the EARLIEST n_low events are fixed, the way a sharded search splits the space
   unsigned long long low_bits;
   int n_low;
+  // the threshold in the determinant's own scale (score_leaf): exp(threshold), exp(threshold -/+ 1e-9 max(1, |threshold|));
+  // q_slack: relative slack of the (exponent + mantissa) pre-filter of the sum score
+  double det_thr, det_lo, det_hi, q_slack;
 };
 
 constexpr int kMaxMaskedEvents = 64;

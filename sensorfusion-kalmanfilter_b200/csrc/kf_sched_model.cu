@@ -66,15 +66,70 @@ __device__ __forceinline__ void score_block_reduce(double best_sc, unsigned long
   }
 }
 
+// ---- one scored schedule -> the thread's running results ----------------------------------------
+// The decisions are taken on the determinants themselves, without a logarithm per schedule: feasibility
+// max(log det) < threshold (kf_workers.py:1353) as maxdet < exp(threshold), the undecided-to-rounding zone
+// |max - threshold| <= 1e-9 as exp(threshold -/+ tol) <= maxdet <= ..., both bounds formed once on the host
+// (the two forms can only differ inside that zone, which the caller re-scores in the reference's arithmetic);
+// the sum of log-dets is formed -- log(mantissa) + exponent * ln 2, as before -- only for a schedule whose running
+// product (exponent, mantissa) is not above the thread's current best by more than 1e-9 relative, i.e. for the few
+// schedules that can win or tie: same winner, same tie order (lowest index), same reported score.
+struct ThreadBest {
+  double sc = INFINITY;
+  unsigned long long ix = ~0ULL, key = ~0ULL, n_feas = 0, n_near = 0;
+  double q_limit = INFINITY;  // exponent + mantissa of the best so far, plus the slack
+};
+
+__device__ __forceinline__ void score_leaf(const ScoreParams& p, const LogDetAcc& acc, bool ok, bool host_ld0,
+                                           unsigned long long s, unsigned long long j, int L, ThreadBest& tb) {
+  if (p.per_schedule != nullptr) {
+    double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
+    double sm = acc.sum_log();
+    double lastv = (acc.count > 0) ? log(acc.last) : p.initial_logdet;
+    int cnt = acc.count;
+    if (host_ld0) {  // term 0 is the same for every schedule: take the caller's value verbatim
+      mx = fmax(mx, p.initial_logdet);
+      sm += p.initial_logdet;
+      cnt += 1;
+    }
+    if (!ok) mx = sm = lastv = NAN;
+    double* o = p.per_schedule + (j - p.out_base) * 4;
+    o[0] = mx;
+    o[1] = sm;
+    o[2] = lastv;
+    o[3] = static_cast<double>(cnt);
+  }
+  if (s != 0 && ok) {  // the reference never enumerates the empty set (:1325)
+    const double q = static_cast<double>(acc.expo) + acc.mant;
+    if (q <= tb.q_limit) {
+      double sm = acc.sum_log();
+      if (host_ld0) sm += p.initial_logdet;
+      if (sm < tb.sc || (sm == tb.sc && s < tb.ix)) {
+        tb.sc = sm;
+        tb.ix = s;
+        tb.q_limit = q + p.q_slack * (fabs(q) + 1.0);
+      }
+    }
+    // max over the terms computed HERE (the ones a rounding difference can move); the caller's exact term 0
+    // decides on its own (it does so in the reference's arithmetic too)
+    const bool ld0_ok = !(host_ld0 && p.initial_logdet >= p.threshold);
+    const bool dev_ok = (acc.count > 0) ? (acc.maxdet < p.det_thr) : (-INFINITY < p.threshold);
+    if (dev_ok && ld0_ok) {  // :1353
+      tb.n_feas += 1;
+      const unsigned long long key = lex_key(s, L);
+      tb.key = key < tb.key ? key : tb.key;
+    }
+    if (acc.count > 0 && acc.maxdet >= p.det_lo && acc.maxdet <= p.det_hi && ld0_ok) tb.n_near += 1;
+  }
+}
+
 template <int MODEL, int VAR>
 __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
   using MT = VariantTraits<MODEL, VAR, double>;
   constexpr int n = MT::n;
 
-  double best_sc = INFINITY;
-  unsigned long long best_ix = ~0ULL, best_key = ~0ULL, n_feas = 0, n_near = 0;
+  ThreadBest tb;
   const int L = p.n_events;
-  const double near_tol = 1e-9 * fmax(1.0, fabs(p.threshold));
 
   for (unsigned long long idx = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
        idx < p.count; idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
@@ -102,38 +157,10 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
       filter_predict<false>(flt, dt, p.mc, EV_PREDICT_ONLY, static_cast<const double*>(nullptr));
       acc.add(filter_det(flt, ok));
     }
-    double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
-    double sm = acc.sum_log();
-    double lastv = (acc.count > 0) ? log(acc.last) : p.initial_logdet;
-    int cnt = acc.count;
-    const double mx_dev = mx;  // max over the terms computed HERE (the ones a rounding difference can move)
-    if (host_ld0) {  // term 0 is the same for every schedule: take the caller's value verbatim
-      mx = fmax(mx, p.initial_logdet);
-      sm += p.initial_logdet;
-      cnt += 1;
-    }
-    if (!ok) mx = sm = lastv = NAN;
-    if (p.per_schedule != nullptr) {
-      double* o = p.per_schedule + (j - p.out_base) * 4;
-      o[0] = mx;
-      o[1] = sm;
-      o[2] = lastv;
-      o[3] = static_cast<double>(cnt);
-    }
-    if (s != 0 && ok) {  // the reference never enumerates the empty set (:1325)
-      better_sum(best_sc, best_ix, sm, s);
-      if (mx < p.threshold) {  // :1353
-        n_feas += 1;
-        const unsigned long long key = lex_key(s, L);
-        best_key = key < best_key ? key : best_key;
-      }
-      // undecided to rounding: a term computed here within near_tol of the threshold, unless the caller's exact
-      // term 0 already rules the schedule out (it does so in the reference's arithmetic too)
-      if (fabs(mx_dev - p.threshold) <= near_tol && !(host_ld0 && p.initial_logdet >= p.threshold)) n_near += 1;
-    }
+    score_leaf(p, acc, ok, host_ld0, s, j, L, tb);
   }
 
-  score_block_reduce(best_sc, best_ix, best_key, n_feas, n_near, static_cast<ScorePartial*>(p.partials));
+  score_block_reduce(tb.sc, tb.ix, tb.key, tb.n_feas, tb.n_near, static_cast<ScorePartial*>(p.partials));
 }
 
 // ---- prefix-sharing variant ----------------------------------------------------------------------
@@ -168,13 +195,11 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
   constexpr int n = MT::n;
   constexpr int NC = CovCount<Flt>::value;
 
-  double best_sc = INFINITY;
-  unsigned long long best_ix = ~0ULL, best_key = ~0ULL, n_feas = 0, n_near = 0;
+  ThreadBest tb;
   const int L = p.n_events;
   const int a = p.tree_a, k = p.tree_k;
   const int npre = a - k;  // events decided by the thread index
   const int nl = p.n_low;  // events fixed for the whole call (strided enumeration): walked once per thread, first
-  const double near_tol = 1e-9 * fmax(1.0, fabs(p.threshold));
   const bool host_ld0 = !isnan(p.initial_logdet);
 
   struct Saved {
@@ -263,38 +288,10 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
         filter_predict<false>(flt, dt, p.mc, EV_PREDICT_ONLY, static_cast<const double*>(nullptr));
         acc.add(filter_det(flt, ok));
       }
-      double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
-      double sm = acc.sum_log();
-      double lastv = (acc.count > 0) ? log(acc.last) : p.initial_logdet;
-      int cnt = acc.count;
-      const double mx_dev = mx;
-      if (host_ld0) {
-        mx = fmax(mx, p.initial_logdet);
-        sm += p.initial_logdet;
-        cnt += 1;
-      }
-      if (!ok) mx = sm = lastv = NAN;
-      if (p.per_schedule != nullptr) {
-        double* o = p.per_schedule + (j - p.out_base) * 4;
-        o[0] = mx;
-        o[1] = sm;
-        o[2] = lastv;
-        o[3] = static_cast<double>(cnt);
-      }
-      if (s != 0 && ok) {
-        better_sum(best_sc, best_ix, sm, s);
-        if (mx < p.threshold) {
-          n_feas += 1;
-          const unsigned long long key = lex_key(s, L);
-          best_key = key < best_key ? key : best_key;
-        }
-        // undecided to rounding: a term computed here within near_tol of the threshold, unless the caller's exact
-      // term 0 already rules the schedule out (it does so in the reference's arithmetic too)
-      if (fabs(mx_dev - p.threshold) <= near_tol && !(host_ld0 && p.initial_logdet >= p.threshold)) n_near += 1;
-      }
+      score_leaf(p, acc, ok, host_ld0, s, j, L, tb);
     }
   }
-  score_block_reduce(best_sc, best_ix, best_key, n_feas, n_near, static_cast<ScorePartial*>(p.partials));
+  score_block_reduce(tb.sc, tb.ix, tb.key, tb.n_feas, tb.n_near, static_cast<ScorePartial*>(p.partials));
 }
 
 // ---- worker with state: full filter per schedule over one shared window ----------------------
@@ -790,7 +787,27 @@ static void launch_score_var(const ScoreParams& p, bool tree, unsigned blocks, c
 // Every launch appends its per-block partials to the same array; returns their total number.
 constexpr int kTreeMinA = 14;
 constexpr int kMaxFlatBlocks = 2048;  // grid-stride beyond that
-constexpr int kMaxTreeBlocks = 1184;  // 148 SMs x 8 blocks of 128 threads (72 registers); lowered when a call needs many tree launches
+constexpr int kMaxTreeBlocks = 1184;  // upper bound (148 SMs x 8); a launch takes ONE resident wave (tree_wave_blocks), fewer when a call needs many tree launches
+
+// Blocks of the prefix-sharing kernel that are resident at once on this device (6 per SM at 78 registers; forcing 72
+// registers for 7 measured 6 % slower).  The kernel grid-strides over its threads, so a grid of exactly one wave
+// keeps every SM equally loaded: 1184 blocks on 888 slots ran a second, one-third-full wave.
+template <int VAR>
+static int tree_wave_blocks() {
+  static int cached = 0;
+  if (cached == 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_tree_kernel<B200KF_INST_MODEL, VAR>, kScoreTpb, 0) != cudaSuccess ||
+        cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || per_sm < 1 || sms < 1) {
+      cudaGetLastError();
+      return kMaxTreeBlocks;
+    }
+    const int wave = per_sm * sms;
+    cached = wave < kMaxTreeBlocks ? wave : kMaxTreeBlocks;
+  }
+  return cached;
+}
 
 template <>
 int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsigned flags,
@@ -838,6 +855,8 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
       q.tree_k = k;
       threads = 1ULL << (a - k);
     }
+    // (64-thread blocks for launches below one wave -- config 4: 6.9 blocks per SM instead of 3.5 of 128 threads --
+    // measured no faster: 47.1 vs 45.6 us per 2^20 search, tools/gpu_round2_zq.sh)
     unsigned long long blocks = (threads + kScoreTpb - 1) / kScoreTpb;
     const unsigned long long cap = (a >= 0) ? tree_cap : kMaxFlatBlocks;
     if (blocks > cap) blocks = cap;
@@ -865,7 +884,8 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
   }
   if (n_tree > 0) {
     const int fit = (kMaxSearchPartials - 2 * kMaxFlatBlocks) / n_tree;
-    tree_cap = fit < kMaxTreeBlocks ? fit : kMaxTreeBlocks;
+    const int wave = (var == VAR_SYMMETRIC) ? tree_wave_blocks<VAR_SYMMETRIC>() : tree_wave_blocks<VAR_DECOUPLED>();
+    tree_cap = fit < wave ? fit : wave;
   }
   if (p.count == 0) {
     launch(p.first, 0, -1);  // one block of idle threads writes the neutral partial

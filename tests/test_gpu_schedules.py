@@ -283,6 +283,50 @@ def test_strided_slices_are_bit_identical_rows_of_the_full_search(L, n_low, monk
                             count=(1 << (L - n_low)) + 1)
 
 
+@pytest.mark.parametrize("use_ld0", [False, True])
+def test_decisions_taken_on_determinants_equal_the_decisions_on_the_logged_rows(use_ld0):
+    """The search decides on the determinants (no logarithm per schedule: maxdet < exp(threshold), sum formed only for
+    schedules that can win); the per-schedule rows carry the logarithms.  Recomputing winner, first feasible schedule
+    and counts FROM THE ROWS must give the same answer (the two can differ only for schedules the call reports as
+    undecided to rounding, n_near_threshold), with and without the caller's exact term 0."""
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    from sensorfusion_kalmanfilter_b200.kf_workers import _lex_key
+    m = ko.get_model("CA15")
+    L = 16
+    rng = np.random.default_rng(5)
+    types = np.where(np.arange(L) % 6 == 2, 0, 1).astype(np.uint8)
+    times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
+    P0 = m.P0() * 1e-8
+    t_prev, t_end = 999.995, float(times[-1])
+    ld0 = float(np.linalg.slogdet(P0)[1]) if use_ld0 else None
+    eng = Engine("CA15")
+    _, per = eng.score_schedules(types, times, t_prev, t_end, P0, initial_logdet=ld0, want_per_schedule=True)
+    rows = per.cpu().numpy()
+    idx = np.arange(1, 1 << L)
+    win = int(idx[np.lexsort((idx, rows[1:, 1]))[0]])
+    for quant in (0.05, 0.4, 0.9):
+        thr = float(np.quantile(rows[1:, 0], quant))
+        for with_rows in (False, True):
+            best, _ = eng.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, initial_logdet=ld0,
+                                          want_per_schedule=with_rows)
+            assert best["argmin_sum_index"] == win
+            assert best["argmin_sum_score"] == rows[win, 1]
+            feas = idx[rows[1:, 0] < thr]
+            near = int(np.sum(np.abs(rows[1:, 0] - thr) <= 1e-9 * max(1.0, abs(thr))))
+            if use_ld0 and ld0 >= thr:  # the caller's exact term 0 rules every schedule out on its own: none is undecided
+                near = 0
+            assert abs(best["n_near_threshold"] - near) <= 1  # the zone's two edges are themselves rounded
+            assert abs(best["n_feasible"] - len(feas)) <= best["n_near_threshold"]
+            if best["n_near_threshold"] == 0:
+                assert best["n_feasible"] == len(feas)
+                first = min(feas.tolist(), key=lambda s: _lex_key(s, L)) if len(feas) else None
+                assert best["first_feasible_index"] == first
+    # thresholds beyond any determinant: everything / nothing feasible, nothing near
+    for thr, n in ((float("inf"), (1 << L) - 1), (800.0, (1 << L) - 1), (-800.0, 0), (float("-inf"), 0)):
+        best, _ = eng.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, initial_logdet=ld0)
+        assert best["n_feasible"] == n and best["n_near_threshold"] == 0 and best["argmin_sum_index"] == win
+
+
 # records of the 15- / 8-state models: 13 gain slots; one 3 x 3 and one 2 x 2 covariance (6 + 3 entries); the linear
 # block's K is row-major [3][n_meas], the angular block's [2][2] starts at slot 9
 _IR_IMU = {"CA15": ([0, 6, 12], [3, 9]), "CA8": ([0, 3, 6], [2, 5])}  # measured global states per block, in column order

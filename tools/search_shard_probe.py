@@ -26,7 +26,7 @@ t_prev, t_end = 999.995, float(tm[-1])
 _, per = eng.score_schedules(st, tm, t_prev, t_end, P0, first=1, count=(1 << 16) - 1, want_per_schedule=True)
 thr = float(per[:, 0].median().item())
 res = {"L": a.L, "world": a.world, "sharding": "contiguous" if a.contiguous else "strided", "ranks": {}}
-for rank in sorted({0, 1, a.world // 2, a.world - 1}):
+for rank in sorted({0, min(1, a.world - 1), a.world // 2 if a.world > 1 else 0, a.world - 1}):
     kw = {}
     if a.contiguous or shard_strided(a.L, a.world, rank) is None:
         first, count = shard_range(1 << a.L, a.world, rank)
