@@ -103,37 +103,39 @@ static int dispatch_select(const b200kf_model* m, const SelectParams& p, unsigne
 }
 
 // ---- schedule-search finaliser: reduce the per-block partials to one b200kf_best -------------
-__global__ void score_final_kernel(const ScorePartial* parts, int n_parts, int L, b200kf_best* out) {
-  __shared__ ScorePartial sh[256];
+__device__ __forceinline__ void score_partial_merge(ScorePartial& a, const ScorePartial& b) {
+  if (b.score < a.score || (b.score == a.score && b.index < a.index)) {
+    a.score = b.score;
+    a.index = b.index;
+  }
+  a.key = b.key < a.key ? b.key : a.key;
+  a.n_feasible += b.n_feasible;
+  a.n_near += b.n_near;
+}
+
+// Launched with programmatic stream serialisation behind the last scoring kernel: the block is resident and waiting
+// at the grid dependency when that kernel drains, so the search pays the reduce (warp shuffles, one shared-memory
+// hand-off) but not a second launch latency -- a 2^20 search is 40 us in all.
+__global__ void __launch_bounds__(256) score_final_kernel(const ScorePartial* parts, int n_parts, int L, b200kf_best* out) {
+  cudaGridDependencySynchronize();
+  __shared__ ScorePartial sh[8];
   ScorePartial r{INFINITY, ~0ULL, ~0ULL, 0ULL, 0ULL};
-  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) {
-    const ScorePartial q = parts[i];
-    if (q.score < r.score || (q.score == r.score && q.index < r.index)) {
-      r.score = q.score;
-      r.index = q.index;
-    }
-    r.key = q.key < r.key ? q.key : r.key;
-    r.n_feasible += q.n_feasible;
-    r.n_near += q.n_near;
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) score_partial_merge(r, parts[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ScorePartial o;
+    o.score = __shfl_down_sync(0xffffffffu, r.score, off);
+    o.index = __shfl_down_sync(0xffffffffu, r.index, off);
+    o.key = __shfl_down_sync(0xffffffffu, r.key, off);
+    o.n_feasible = __shfl_down_sync(0xffffffffu, r.n_feasible, off);
+    o.n_near = __shfl_down_sync(0xffffffffu, r.n_near, off);
+    score_partial_merge(r, o);
   }
-  sh[threadIdx.x] = r;
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = r;
   __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      ScorePartial& a = sh[threadIdx.x];
-      const ScorePartial b = sh[threadIdx.x + s];
-      if (b.score < a.score || (b.score == a.score && b.index < a.index)) {
-        a.score = b.score;
-        a.index = b.index;
-      }
-      a.key = b.key < a.key ? b.key : a.key;
-      a.n_feasible += b.n_feasible;
-      a.n_near += b.n_near;
-    }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    const ScorePartial a = sh[0];
+    ScorePartial a = sh[0];
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) score_partial_merge(a, sh[w]);
     out->argmin_sum_score = a.score;
     out->argmin_sum_index = a.index;
     out->first_feasible_key = a.key;
@@ -854,7 +856,20 @@ int b200kf_score_schedules_strided(const b200kf_model* m, int32_t n_events, cons
   p.dense_flag = nullptr;
   const int blocks = dispatch_score(m, p, flags, best, st);
   if (blocks < 0) return blocks;
-  score_final_kernel<<<1, 256, 0, st>>>(static_cast<const ScorePartial*>(p.partials), blocks, n_events, best);
+  {
+    static const bool pdl = []() { const char* e = getenv("B200KF_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    B200KF_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_final_kernel, static_cast<const ScorePartial*>(p.partials), blocks,
+                                       static_cast<int>(n_events), best));
+  }
   B200KF_CUDA_TRY(cudaGetLastError());
   return B200KF_OK;
 }
