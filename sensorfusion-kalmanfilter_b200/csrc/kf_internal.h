@@ -17,6 +17,10 @@ struct HostWorkspace {
   cudaEvent_t ev_copied[2], ev_done[2];
   void* slab;
   size_t cap;
+  // pinned staging for callers whose payload lives in pageable memory (plain numpy arrays): two chunk buffers
+  // filled by a few host threads while the previous chunk's host->device copy is in flight
+  void* h_stage[2];
+  size_t h_cap;
 };
 
 struct b200kf_model {

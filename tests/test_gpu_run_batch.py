@@ -187,6 +187,26 @@ def test_host_buffer_path_matches_device_path():
     assert host["status"].sum() == 0
 
 
+def test_pageable_payload_is_staged_on_host_threads_and_matches_the_pinned_path():
+    """A drop-in caller's payload is a plain numpy array (pageable): b200kf_run_batch_host stages it through two pinned
+    chunk buffers filled by several host threads (chunks above 8 MB are split into per-thread slices).  Same bytes
+    reach the device, so the results equal the pinned-buffer call's bit for bit -- over several chunks with a ragged
+    last one, and a second call reusing the staging buffers."""
+    import torch
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    N, T = 16384, 100
+    m, types, dts, payload, x0, P0 = make_case("CV6", N, T, seed=33)
+    eng = Engine("CV6")
+    pinned = torch.from_numpy(np.ascontiguousarray(payload)).pin_memory()
+    ref = eng.run_batch_host(types, dts, pinned, x0, P0, chunk_steps=32)
+    for rep in range(2):
+        got = eng.run_batch_host(types, dts, np.ascontiguousarray(payload).copy(), x0, P0, chunk_steps=32)
+        for k in ("x", "P", "agg", "status"):
+            np.testing.assert_array_equal(got[k], ref[k])
+    dev = eng.run_batch(types, dts, payload, x0, P0)
+    np.testing.assert_allclose(ref["x"], dev["x"].cpu().numpy(), rtol=1e-13, atol=1e-13)
+
+
 def test_ragged_and_empty_inputs():
     from sensorfusion_kalmanfilter_b200.engine import Engine
     eng = Engine("CV6")
