@@ -213,7 +213,32 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
   LogDetAcc acc;
   bool ok;
   double tcur;
+  // The deepest levels are the busy ones (level k-1 is restored by every other leaf, k-2 by every fourth): they live
+  // in shared memory, [level][word][thread] -- no write-through to L2, no local-memory queue -- the rest in local memory.
+#ifndef B200KF_TREE_SMEM_LEVELS
+#define B200KF_TREE_SMEM_LEVELS 2
+#endif
+  constexpr int NS = (NC <= 16) ? B200KF_TREE_SMEM_LEVELS : 0;
+  constexpr int NW = NC + 5;  // covariance entries, mant, maxdet, last, tcur, (expo, count | ok << 30)
+  __shared__ double sst[NS > 0 ? NS : 1][NS > 0 ? NW : 1][NS > 0 ? kScoreTpb : 1];
+  const int tix = threadIdx.x;
   auto save = [&](int lvl) {
+    if (NS > 0 && lvl >= k - NS) {
+      auto& sl = sst[lvl - (k - NS)];
+      int o = 0;
+      flt.each([&](const auto& b) {
+        using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+#pragma unroll
+        for (int e = 0; e < BT::NP; ++e) sl[o + e][tix] = b.P[e];
+        o += BT::NP;
+      });
+      sl[NC][tix] = acc.mant;
+      sl[NC + 1][tix] = acc.maxdet;
+      sl[NC + 2][tix] = acc.last;
+      sl[NC + 3][tix] = tcur;
+      sl[NC + 4][tix] = __hiloint2double(acc.expo, acc.count | (ok ? (1 << 30) : 0));
+      return;
+    }
     Saved& sv = stk[lvl];
     int o = 0;
     flt.each([&](const auto& b) {
@@ -231,6 +256,26 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
     sv.ok = ok ? 1 : 0;
   };
   auto restore = [&](int lvl) {
+    if (NS > 0 && lvl >= k - NS) {
+      const auto& sl = sst[lvl - (k - NS)];
+      int o = 0;
+      flt.each([&](auto& b) {
+        using BT = std::remove_cv_t<std::remove_reference_t<decltype(b)>>;
+#pragma unroll
+        for (int e = 0; e < BT::NP; ++e) b.P[e] = sl[o + e][tix];
+        o += BT::NP;
+      });
+      acc.mant = sl[NC][tix];
+      acc.maxdet = sl[NC + 1][tix];
+      acc.last = sl[NC + 2][tix];
+      tcur = sl[NC + 3][tix];
+      const double w = sl[NC + 4][tix];
+      acc.expo = __double2hiint(w);
+      const int cw = __double2loint(w);
+      acc.count = cw & ~(1 << 30);
+      ok = (cw >> 30) & 1;
+      return;
+    }
     const Saved& sv = stk[lvl];
     int o = 0;
     flt.each([&](auto& b) {
