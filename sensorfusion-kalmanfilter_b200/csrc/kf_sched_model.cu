@@ -28,6 +28,14 @@ __device__ __forceinline__ unsigned long long lex_key(unsigned long long s, int 
   return (static_cast<unsigned long long>(__popcll(s)) << 32) | (full - rev);
 }
 
+// The same key for the searches' 32-bit schedule indices (windows hold at most 32 events)
+static_assert(kMaxEvents <= 32, "the search kernels carry schedule indices in 32 bits");
+__device__ __forceinline__ unsigned long long lex_key32(unsigned s, int L) {
+  const unsigned rev = __brev(s) >> (32 - L);
+  const unsigned full = (L >= 32) ? ~0u : ((1u << L) - 1u);
+  return (static_cast<unsigned long long>(__popc(s)) << 32) | (full - rev);
+}
+
 __device__ __forceinline__ void better_sum(double& sc, unsigned long long& ix, double osc,
                                            unsigned long long oix) {
   if (osc < sc || (osc == sc && oix < ix)) {
@@ -76,12 +84,13 @@ __device__ __forceinline__ void score_block_reduce(double best_sc, unsigned long
 // schedules that can win or tie: same winner, same tie order (lowest index), same reported score.
 struct ThreadBest {
   double sc = INFINITY;
-  unsigned long long ix = ~0ULL, key = ~0ULL, n_feas = 0, n_near = 0;
+  unsigned long long ix = ~0ULL, key = ~0ULL;
+  unsigned n_feas = 0, n_near = 0;  // per thread: far below 2^32 schedules
   double q_limit = INFINITY;  // exponent + mantissa of the best so far, plus the slack
 };
 
 __device__ __forceinline__ void score_leaf(const ScoreParams& p, const LogDetAcc& acc, bool ok, bool host_ld0,
-                                           unsigned long long s, unsigned long long j, int L, ThreadBest& tb) {
+                                           unsigned s, unsigned j, int L, ThreadBest& tb) {
   if (p.per_schedule != nullptr) {
     double mx = (acc.count > 0) ? log(acc.maxdet) : -INFINITY;
     double sm = acc.sum_log();
@@ -93,7 +102,7 @@ __device__ __forceinline__ void score_leaf(const ScoreParams& p, const LogDetAcc
       cnt += 1;
     }
     if (!ok) mx = sm = lastv = NAN;
-    double* o = p.per_schedule + (j - p.out_base) * 4;
+    double* o = p.per_schedule + (static_cast<unsigned long long>(j) - p.out_base) * 4;
     o[0] = mx;
     o[1] = sm;
     o[2] = lastv;
@@ -116,7 +125,7 @@ __device__ __forceinline__ void score_leaf(const ScoreParams& p, const LogDetAcc
     const bool dev_ok = (acc.count > 0) ? (acc.maxdet < p.det_thr) : (-INFINITY < p.threshold);
     if (dev_ok && ld0_ok) {  // :1353
       tb.n_feas += 1;
-      const unsigned long long key = lex_key(s, L);
+      const unsigned long long key = lex_key32(s, L);
       tb.key = key < tb.key ? key : tb.key;
     }
     if (acc.count > 0 && acc.maxdet >= p.det_lo && acc.maxdet <= p.det_hi && ld0_ok) tb.n_near += 1;
@@ -133,8 +142,8 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
 
   for (unsigned long long idx = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
        idx < p.count; idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-    const unsigned long long j = p.first + idx;
-    const unsigned long long s = p.low_bits | (j << p.n_low);
+    const unsigned j = static_cast<unsigned>(p.first + idx);  // < 2^32: at most 32 events
+    const unsigned s = static_cast<unsigned>(p.low_bits) | (p.n_low < 32 ? j << p.n_low : 0u);
     typename MT::Filter flt;
     flt.each([&](auto& b) { b.load_cov(p.P0, n); });
     bool ok = true;
@@ -143,7 +152,7 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
     if (!host_ld0) acc.add(filter_det(flt, ok));  // log_det[0], kf_workers.py:32
     double tcur = p.t_prev;
     for (int i = 0; i < L; ++i) {
-      if (!((s >> i) & 1ULL)) continue;
+      if (!((s >> i) & 1u)) continue;
       const double dt = p.times[i] - tcur;  // merged gap, kf_workers.py:37
       if (dt < 0) continue;                 // :38-40
       const int ty = p.types[i];
@@ -302,18 +311,20 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
     acc.add(filter_det(flt, ok));
   };
 
-  const unsigned long long n_prefix = 1ULL << npre;
-  for (unsigned long long t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; t < n_prefix;
-       t += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+  // 32-bit indices throughout: a window holds at most 32 events, an aligned tree block at most 2^32 schedules and
+  // 2^(32 - 3) prefixes
+  const unsigned n_prefix = 1u << npre;
+  const unsigned low = static_cast<unsigned>(p.low_bits), first = static_cast<unsigned>(p.first);
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n_prefix; t += gridDim.x * blockDim.x) {
     flt.each([&](auto& b) { b.load_cov(p.P0, n); });
     acc = LogDetAcc();
     ok = true;
     if (!host_ld0) acc.add(filter_det(flt, ok));  // log_det[0], kf_workers.py:32
     tcur = p.t_prev;
     for (int i = 0; i < nl; ++i)
-      if ((p.low_bits >> i) & 1ULL) apply(i);
+      if ((low >> i) & 1u) apply(i);
     for (int i = 0; i < npre; ++i)
-      if ((t >> i) & 1ULL) apply(nl + i);
+      if ((t >> i) & 1u) apply(nl + i);
     save(0);
     const unsigned n_leaf = 1u << k;
     for (unsigned c = 0; c < n_leaf; ++c) {
@@ -323,11 +334,11 @@ __global__ void __launch_bounds__(kScoreTpb) score_tree_kernel(const ScoreParams
         if ((c >> (k - 1 - lv)) & 1u) apply(nl + npre + lv);
         if (lv + 1 < k) save(lv + 1);
       }
-      const unsigned long long m = (k > 0) ? (static_cast<unsigned long long>(__brev(c)) >> (32 - k)) : 0ULL;
-      const unsigned long long j = p.first | t | (m << npre);
-      const unsigned long long s = p.low_bits | (j << nl);
+      const unsigned m = (k > 0) ? (__brev(c) >> (32 - k)) : 0u;
+      const unsigned j = first | t | (m << npre);
+      const unsigned s = low | (j << nl);
       for (int i = a + nl; i < L; ++i)
-        if ((s >> i) & 1ULL) apply(i);
+        if ((s >> i) & 1u) apply(i);
       if (tcur < p.t_end - 1e-8) {  // kf_workers.py:74-82
         const double dt = p.t_end - tcur;
         filter_predict<false>(flt, dt, p.mc, EV_PREDICT_ONLY, static_cast<const double*>(nullptr));
