@@ -905,7 +905,11 @@ int launch_score_m<B200KF_INST_MODEL>(const b200kf_model* m, ScoreParams p, unsi
     unsigned long long threads = cnt;
     q.tree_a = q.tree_k = 0;
     if (a >= 0) {
-      int k = a - 16;
+      // threads = 2^(a - k): 2^16 up to a = 20 (config 4: 40.9 us against 43.0 with 2^17), 2^17 beyond (a = 22 / 24:
+      // 98 / 307 us against 107 / 364 with 2^16; tools/gpu_round2_zza.sh), until k reaches its maximum at a = 25
+      static const int env_shift = []() { const char* e = getenv("B200KF_TREE_SHIFT"); return e ? atoi(e) : 0; }();
+      const int shift = env_shift > 0 ? env_shift : (a >= 21 ? 17 : 16);
+      int k = a - shift;
       k = k < 3 ? 3 : (k > kTreeMaxK ? kTreeMaxK : k);
       q.tree_a = a;
       q.tree_k = k;
