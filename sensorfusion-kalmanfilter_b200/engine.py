@@ -210,7 +210,7 @@ class Engine:
         if count is None:
             count = (1 << (L - int(n_low))) - first
         per = torch.empty((count, 4), dtype=torch.float64, device=self.device) if want_per_schedule else None
-        best_d = torch.zeros((ctypes.sizeof(_lib.Best),), dtype=torch.uint8, device=self.device)
+        best_d = torch.empty((ctypes.sizeof(_lib.Best),), dtype=torch.uint8, device=self.device)  # every field is written
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200kf_score_schedules_strided(
                 self._h, L, types.ctypes.data_as(POINTER(c_uint8)), times.ctypes.data_as(POINTER(c_double)),
