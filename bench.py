@@ -236,7 +236,7 @@ def load_traffic(a, kernel_name):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), when
     the workload matches the one that was profiled; else None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02zzc_traffic.json")) as f:
             t = json.load(f)
         w = t["workload"]
         if (w["model"], w["precision"], w["filters"], w["tsteps"]) == (a.model, a.precision, a.filters, a.tsteps) \
