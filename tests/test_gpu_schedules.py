@@ -171,6 +171,32 @@ def test_prefix_sharing_kernel_is_bit_identical_to_flat_kernel(name, mode, monke
         assert abs(per[s][2] - tr[-1]) <= 1e-9 * max(1, abs(tr[-1]))
 
 
+@pytest.mark.parametrize("L,rows", [(22, True), (25, False)])
+def test_deep_trees_match_the_flat_kernel(L, rows, monkeypatch):
+    """Deeper depth-first walks than the 17- and 20-event cases reach: 5 levels at 22 events (the two deepest in shared
+    memory, three in local memory), the maximum of 8 at 25.  Same per-schedule rows (22 events) and the same winner,
+    first feasible schedule and counts (both) as one thread per schedule."""
+    import torch
+    from sensorfusion_kalmanfilter_b200.engine import Engine
+    m = ko.get_model("CA15")
+    rng = np.random.default_rng(41)
+    types = np.where(np.arange(L) % 6 == 4, 0, 1).astype(np.uint8)
+    times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
+    P0 = m.P0() * 1e-8
+    t_prev, t_end = 999.995, float(times[-1])
+    monkeypatch.setenv("B200KF_TREE", "0")
+    flat = Engine("CA15")
+    monkeypatch.setenv("B200KF_TREE", "1")
+    tree = Engine("CA15")
+    _, probe = tree.score_schedules(types, times, t_prev, t_end, P0, first=1, count=(1 << 16) - 1, want_per_schedule=True)
+    thr = float(probe[:, 0].median().item())
+    bt, pt = tree.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, want_per_schedule=rows)
+    bf, pf = flat.score_schedules(types, times, t_prev, t_end, P0, threshold=thr, want_per_schedule=rows)
+    assert bt == bf and 0 < bt["n_feasible"] < (1 << L) - 1
+    if rows:
+        assert torch.equal(pt, pf)
+
+
 def test_bf_schedule_tree_matches_restatement():
     """a17: the exhaustive multi-day schedule tree of sensor_scheduling_algorithm.ipynb:213-291 with the
     sizes of its first cell (n = 2 states, G = 5 sensors, K = 3 per day, horizon 3) and a larger case.

@@ -1,5 +1,6 @@
-"""Sharded brute-force schedule search under torchrun (NCCL): every rank scores its contiguous slice of
-the 2^L subsets and all ranks end with the same reduced answer (distributed.search_sharded).
+"""Sharded brute-force schedule search under torchrun (NCCL): every rank scores its slice of the 2^L subsets (the
+earliest log2(world) decisions fixed; windows of <= 22 events are searched whole by every rank, no collective) and all
+ranks end with the same reduced answer (distributed.search_sharded).
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/search_multi_gpu.py"""
 import json
 import os
@@ -19,7 +20,7 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 eng = Engine("CA15")
-for L in (20, 26):
+for L in (20, 24, 26):
     rng = np.random.default_rng(0)
     types = np.where(np.arange(L) % 7 == 3, 0, 1).astype(np.uint8)
     times = 1000.0 + np.cumsum(0.005 + 0.0005 * rng.random(L))
