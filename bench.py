@@ -362,7 +362,7 @@ def leg_search(torch, a, fma_peak_distinct):
            "ms": st["mean"], "ms_min": st["min"], "argmin_sum_index": best["argmin_sum_index"],
            "first_feasible_index": best["first_feasible_index"], "n_feasible": best["n_feasible"],
            "n_near_threshold": best["n_near_threshold"]}
-    prof = load_profile_json("r02zt_search_fp64.json")
+    prof = load_profile_json("r02zze_search_fp64.json")
     if prof and "L20" in prof:
         q = prof["L20"]
         flop_per_sched = (2.0 * q["dfma"] + q["dmul"] + q["dadd"]) / q["schedules"]
@@ -373,7 +373,7 @@ def leg_search(torch, a, fma_peak_distinct):
                            "flop_per_schedule": flop_per_sched, "kernel": q.get("kernel", "score_tree_kernel<CA15,sym>"),
                            "thread_inst_per_schedule": 32.0 * q["warp_inst"] / q["schedules"],
                            "peak_source": "b200kf_probe_fma_peak (distinct operands), measured in this run",
-                           "counts_from": "profiles/r02zt_search_fp64.json (ncu smsp__sass_thread_inst_executed_op_d*_pred_on)"}
+                           "counts_from": "profiles/r02zze_search_fp64.json (ncu smsp__sass_thread_inst_executed_op_d*_pred_on)"}
     return out
 
 
@@ -408,7 +408,7 @@ def leg_search_large(torch, dist, a, world, dev, barrier, fma_peak_distinct, Ll)
                        "final all-gather + reduce + the one D2H (host wall clock, max over ranks)",
            "ms": tl * 1e3, "first_feasible_index": bl["first_feasible_index"], "n_feasible": bl["n_feasible"],
            "argmin_sum_index": bl["argmin_sum_index"]}
-    prof = load_profile_json("r02zt_search_fp64.json")
+    prof = load_profile_json("r02zze_search_fp64.json")
     if prof and "L26" in prof:
         q = prof["L26"]
         flop_per_sched = (2.0 * q["dfma"] + q["dmul"] + q["dadd"]) / q["schedules"]
