@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(kScoreTpb) score_kernel(const ScoreParams p) {
 // next re-enters the tree at the level of the lowest set bit of the counter, which costs one filter
 // step per leaf on average instead of one per used event (L/2).  Bits >= a (fixed by `first`) and
 // the end-of-window propagation are applied per leaf.  Same arithmetic, order of operations and
-// reductions as score_kernel, so the two agree bit for bit.
+// reductions as score_kernel, so the two agree bit for bit.  Strided enumeration (n_low > 0) fixes the
+// n_low EARLIEST events instead: they are walked once per thread before the prefix, so a sharded search
+// pays nothing per schedule for the bits that name the shard (fixed LATE events cost every leaf a step).
 constexpr int kTreeMaxK = 8;
 
 template <class Flt>
