@@ -717,7 +717,11 @@ static void staged_memcpy(void* dst, const void* src, size_t bytes, int n_thread
     const size_t off = slice * t;
     if (off >= bytes) break;
     const size_t len = bytes - off < slice ? bytes - off : slice;
-    th.emplace_back([=]() { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    try {
+      th.emplace_back([=]() { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    } catch (...) {  // no thread to be had (std::system_error): this slice is copied here; nothing crosses the C ABI
+      memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len);
+    }
   }
   memcpy(dst, src, slice < bytes ? slice : bytes);
   for (auto& t : th) t.join();
