@@ -175,8 +175,10 @@ int b200kf_run_batch_gated(const b200kf_model* model, int64_t n_filters, int64_t
 
 /* Same computation from HOST buffers (the call a drop-in user makes): streams `payload` to the
  * device in time chunks, overlapping host->device copies with the kernel, and copies x, P, agg
- * back.  Synchronous.  payload/x/P/agg are HOST pointers (pinned memory copies fastest); types
- * and dts are host arrays.  chunk_steps = 0 picks a default. */
+ * back.  Synchronous.  payload/x/P/agg are HOST pointers (pinned memory copies fastest; a payload
+ * in pageable memory -- a plain numpy array -- is staged through two pinned chunk buffers by a few
+ * host threads, env B200KF_STAGE_THREADS); types and dts are host arrays.  chunk_steps = 0 picks a
+ * default. */
 int b200kf_run_batch_host(const b200kf_model* model, int64_t n_filters, int64_t n_steps,
                           const uint8_t* types, const double* dts, const void* payload, void* x,
                           void* P, double* agg, int32_t* status, int64_t chunk_steps, uint32_t flags);
