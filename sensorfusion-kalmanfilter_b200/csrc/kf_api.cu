@@ -738,8 +738,13 @@ int b200kf_run_batch_host(const b200kf_model* m, int64_t n_filters, int64_t n_st
   const size_t rs = m->desc.precision == B200KF_F32 ? 4 : 8;
   const size_t step_bytes = static_cast<size_t>(m->d) * n_filters * rs;
   if (chunk_steps <= 0) {
-    chunk_steps = static_cast<int64_t>((size_t(128) << 20) / (step_bytes ? step_bytes : 1));
-    if (chunk_steps < 16) chunk_steps = 16;
+    static const size_t chunk_mb = []() {
+      const char* e = getenv("B200KF_HOST_CHUNK_MB");
+      const long v = e ? atol(e) : 0;
+      return static_cast<size_t>(v > 0 ? v : 128);
+    }();
+    chunk_steps = static_cast<int64_t>((chunk_mb << 20) / (step_bytes ? step_bytes : 1));
+    if (chunk_steps < 4) chunk_steps = 4;
   }
   if (chunk_steps > n_steps) chunk_steps = n_steps > 0 ? n_steps : 1;
   const size_t xb = static_cast<size_t>(n_filters) * m->n * rs;
